@@ -1,0 +1,79 @@
+/* ms_tables.h — flat, canonical dump of the graph-construction result.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Shared by the two checkers under oracle/:
+ *   - oracle/ms_oracle.c      (plain-C restatement of the reference algorithm)
+ *   - oracle/ref_driver.cpp   (thin driver around the reference's own classes,
+ *                              compiled from /root/reference into oracle/_ref/)
+ * The product (muchsalsa_b200/csrc, include/msgpu.h) never includes this file.
+ *
+ * Everything is indexed by the ids the reference assigns when it runs with ONE
+ * worker thread (the only deterministic mode, SURVEY.md §8a rules i-vii):
+ * read id / unitig id = rank of the first accepted PAF line naming it
+ * (Registry.cpp:36-45 reached from BlastFileReader.cpp:110-111).
+ *
+ * Sort orders (so two dumps can be compared with memcmp / array_equal):
+ *   vertex matches : (read, unitig)
+ *   edges          : (first, second)
+ *   edge matches   : (first, second, unitig); edge e owns rows
+ *                    [edge_em_begin[e], edge_em_begin[e+1])
+ */
+#ifndef MS_ORACLE_TABLES_H
+#define MS_ORACLE_TABLES_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ms_tables {
+  /* reads (graph vertices): Vertex(id, nanoporeLength, lineIdx), Vertex.h:185-188 */
+  uint64_t  n_reads;
+  uint64_t *read_name_off; /* n_reads + 1 */
+  char     *read_names;    /* concatenated, no terminators */
+  uint64_t *read_nlen;     /* Vertex::getNanoporeLength() */
+  uint64_t *read_line;     /* Vertex::getMetaDatum<size_t>(0) */
+
+  /* unitigs ("illumina ids") */
+  uint64_t  n_unitigs;
+  uint64_t *unitig_name_off; /* n_unitigs + 1 */
+  char     *unitig_names;
+
+  /* VertexMatch rows, MatchMap.h:51-59 */
+  uint64_t  n_vm;
+  uint32_t *vm_read;
+  uint32_t *vm_unitig;
+  int32_t  *vm_nr0, *vm_nr1; /* nanoporeRange */
+  int32_t  *vm_ir0, *vm_ir1; /* illuminaRange */
+  double   *vm_rratio;
+  uint8_t  *vm_dir;
+  uint8_t  *vm_prim;
+  uint64_t *vm_score;
+  uint64_t *vm_line;
+
+  /* edges, Edge::getVertices() order (Edge.h:235-237) */
+  uint64_t  n_edges;
+  uint32_t *edge_first;
+  uint32_t *edge_second;
+  uint64_t *edge_em_begin; /* n_edges + 1 */
+
+  /* EdgeMatch rows, MatchMap.h:68-74 */
+  uint64_t  n_em;
+  uint32_t *em_unitig;
+  int32_t  *em_ov0, *em_ov1;
+  double   *em_score;
+  uint8_t  *em_dir;
+  uint8_t  *em_prim;
+  uint64_t *em_line;
+
+  /* wall-clock seconds of the phases, for the CPU baseline */
+  double t_index, t_read, t_edges;
+} ms_tables;
+
+void ms_tables_free(ms_tables *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

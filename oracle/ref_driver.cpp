@@ -1,0 +1,372 @@
+// ref_driver.cpp — runs the REFERENCE's own graph-construction path and dumps it.
+//
+// TEST INFRASTRUCTURE ONLY.  This file is compiled (by oracle/Makefile) together
+// with the reference's unmodified sources taken where they lie under
+// /root/reference into oracle/_ref/libmsref.so and oracle/_ref/msref_cli.  No
+// reference source is copied into this repository; this driver only *calls* the
+// reference's public classes exactly the way its main() does
+// (src/main.cpp:143-157 for construction, src/main.cpp:161-163 for the sequence
+// index) and flattens what they hold into ms_tables.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load
+// the result.
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <string_view>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "BlastFileAccessor.h"
+#include "BlastFileReader.h"
+#include "Registry.h"
+#include "SequenceAccessor.h"
+#include "SequenceUtils.h"
+#include "graph/Edge.h"
+#include "graph/Graph.h"
+#include "graph/Vertex.h"
+#include "matching/MatchMap.h"
+#include "threading/ThreadPool.h"
+#include "types/Toggle.h"
+
+#include "ms_tables.h"
+
+namespace {
+
+using clk = std::chrono::steady_clock;
+double secs(clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); }
+
+template <class T> T *dup(std::vector<T> const &v) {
+  T *p = static_cast<T *>(std::malloc(std::max<size_t>(1, v.size()) * sizeof(T)));
+  if (!v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(T));
+  return p;
+}
+
+struct NameTable {
+  std::vector<std::string> names;
+  void set(unsigned id, std::string const &s) {
+    if (id >= names.size()) names.resize(id + 1);
+    if (names[id].empty()) names[id] = s;
+  }
+  void flatten(uint64_t n, uint64_t **off, char **blob) const {
+    std::vector<uint64_t> o(n + 1, 0);
+    std::string           b;
+    for (uint64_t i = 0; i < n; ++i) {
+      o[i] = b.size();
+      if (i < names.size()) b += names[i];
+    }
+    o[n]  = b.size();
+    *off  = dup(o);
+    *blob = static_cast<char *>(std::malloc(std::max<size_t>(1, b.size())));
+    std::memcpy(*blob, b.data(), b.size());
+  }
+};
+
+} // namespace
+
+extern "C" {
+
+void ms_tables_free(ms_tables *t) {
+  if (!t) return;
+  void *ptrs[] = {t->read_name_off, t->read_names,  t->read_nlen,  t->read_line,  t->unitig_name_off, t->unitig_names,
+                  t->vm_read,       t->vm_unitig,   t->vm_nr0,     t->vm_nr1,     t->vm_ir0,          t->vm_ir1,
+                  t->vm_rratio,     t->vm_dir,      t->vm_prim,    t->vm_score,   t->vm_line,         t->edge_first,
+                  t->edge_second,   t->edge_em_begin, t->em_unitig, t->em_ov0,    t->em_ov1,          t->em_score,
+                  t->em_dir,        t->em_prim,     t->em_line};
+  for (void *p : ptrs) std::free(p);
+  std::memset(t, 0, sizeof(*t));
+}
+
+// Runs BlastFileReader::read() + MatchMap::calculateEdges() on `paf_path` with a
+// `threads`-sized pool (1 = the canonical, deterministic mode) and fills `out`.
+// do_dump = 0 only measures the phase times (used by the CPU baseline).
+int msref_build(const char *paf_path, int threads, int do_dump, ms_tables *out) {
+  using namespace muchsalsa;
+  std::memset(out, 0, sizeof(*out));
+  try {
+    auto pool             = threading::ThreadPool(static_cast<std::size_t>(threads));
+    auto graph            = graph::Graph();
+    auto matchMap         = matching::MatchMap(&pool, &graph);
+    auto registryNanopore = Registry();
+    auto registryIllumina = Registry();
+
+    auto t0         = clk::now();
+    auto bfAccessor = BlastFileAccessor(paf_path);
+    auto t1         = clk::now();
+    auto reader     = BlastFileReader(&pool, &bfAccessor, &graph, &matchMap, &registryNanopore, &registryIllumina);
+    reader.read();
+    auto t2 = clk::now();
+    matchMap.calculateEdges();
+    auto t3      = clk::now();
+    out->t_index = secs(t0, t1);
+    out->t_read  = secs(t1, t2);
+    out->t_edges = secs(t2, t3);
+
+    out->n_reads = graph.getOrder();
+    out->n_edges = graph.getSize();
+    if (!do_dump) {
+      // still report the row counts the baseline rates are quoted on
+      for (auto *pE : graph.getEdges()) {
+        auto const *pEm = matchMap.getEdgeMatches(pE);
+        if (pEm) out->n_em += pEm->size();
+      }
+      for (auto *pV : graph.getVertices()) {
+        auto const *pVm = matchMap.getVertexMatches(pV->getId());
+        if (pVm) out->n_vm += pVm->size();
+      }
+      return 0;
+    }
+
+    // ---- vertices, by id
+    auto vertices = graph.getVertices();
+    std::sort(vertices.begin(), vertices.end(), [](auto *a, auto *b) { return a->getId() < b->getId(); });
+    std::vector<uint64_t> nlen, vline;
+    for (auto *pV : vertices) {
+      nlen.push_back(pV->getNanoporeLength());
+      vline.push_back(pV->template getMetaDatum<std::size_t>(0));
+    }
+    out->read_nlen = dup(nlen);
+    out->read_line = dup(vline);
+
+    // ---- vertex matches, by (read, unitig)
+    std::vector<uint32_t> vmRead, vmUnitig;
+    std::vector<int32_t>  nr0, nr1, ir0, ir1;
+    std::vector<double>   rr;
+    std::vector<uint8_t>  vdir, vprim;
+    std::vector<uint64_t> vscore, vmline;
+    unsigned              maxUnitig = 0;
+    bool                  anyVm     = false;
+    for (auto *pV : vertices) {
+      auto const *pVm = matchMap.getVertexMatches(pV->getId());
+      if (!pVm) continue;
+      std::vector<unsigned> ids;
+      for (auto const &kv : *pVm) ids.push_back(kv.first);
+      std::sort(ids.begin(), ids.end());
+      for (auto u : ids) {
+        auto const &m = *pVm->at(u);
+        vmRead.push_back(pV->getId());
+        vmUnitig.push_back(u);
+        nr0.push_back(m.nanoporeRange.first);
+        nr1.push_back(m.nanoporeRange.second);
+        ir0.push_back(m.illuminaRange.first);
+        ir1.push_back(m.illuminaRange.second);
+        rr.push_back(m.rRatio);
+        vdir.push_back(static_cast<bool>(m.direction) ? 1 : 0);
+        vprim.push_back(static_cast<bool>(m.isPrimary) ? 1 : 0);
+        vscore.push_back(m.score);
+        vmline.push_back(m.lineNumber);
+        maxUnitig = std::max(maxUnitig, u);
+        anyVm     = true;
+      }
+    }
+    out->n_vm      = vmRead.size();
+    out->vm_read   = dup(vmRead);
+    out->vm_unitig = dup(vmUnitig);
+    out->vm_nr0    = dup(nr0);
+    out->vm_nr1    = dup(nr1);
+    out->vm_ir0    = dup(ir0);
+    out->vm_ir1    = dup(ir1);
+    out->vm_rratio = dup(rr);
+    out->vm_dir    = dup(vdir);
+    out->vm_prim   = dup(vprim);
+    out->vm_score  = dup(vscore);
+    out->vm_line   = dup(vmline);
+    out->n_unitigs = anyVm ? maxUnitig + 1 : 0;
+
+    // ---- names: the Registry has no reverse lookup, so ask it for the id of
+    // the names on every accepted line (operator[] on a known name only reads).
+    {
+      NameTable     readNames, unitigNames;
+      std::ifstream in(paf_path);
+      std::string   line;
+      std::vector<uint8_t> accepted(bfAccessor.getLineCount(), 0);
+      for (auto l : vmline) accepted[l] = 1;
+      for (std::size_t li = 0; std::getline(in, line); ++li) {
+        if (li >= accepted.size() || !accepted[li]) continue;
+        std::vector<std::string> tok;
+        std::size_t              p = 0;
+        while (tok.size() < 6) {
+          auto q = line.find('\t', p);
+          tok.push_back(line.substr(p, q == std::string::npos ? q : q - p));
+          if (q == std::string::npos) break;
+          p = q + 1;
+        }
+        if (tok.size() < 6) continue;
+        unitigNames.set(registryIllumina[tok[0]], tok[0]);
+        readNames.set(registryNanopore[tok[5]], tok[5]);
+      }
+      readNames.flatten(out->n_reads, &out->read_name_off, &out->read_names);
+      unitigNames.flatten(out->n_unitigs, &out->unitig_name_off, &out->unitig_names);
+    }
+
+    // ---- edges by (first, second) and their edge matches by unitig
+    auto edges = graph.getEdges();
+    std::sort(edges.begin(), edges.end(), [](auto *a, auto *b) {
+      auto va = a->getVertices(), vb = b->getVertices();
+      return std::make_pair(va.first->getId(), va.second->getId()) <
+             std::make_pair(vb.first->getId(), vb.second->getId());
+    });
+    std::vector<uint32_t> ef, es, emU;
+    std::vector<uint64_t> eb, emLine;
+    std::vector<int32_t>  ov0, ov1;
+    std::vector<double>   emScore;
+    std::vector<uint8_t>  emDir, emPrim;
+    for (auto *pE : edges) {
+      auto v = pE->getVertices();
+      ef.push_back(v.first->getId());
+      es.push_back(v.second->getId());
+      eb.push_back(emU.size());
+      auto const *pEm = matchMap.getEdgeMatches(pE);
+      if (!pEm) continue;
+      std::vector<unsigned> ids;
+      for (auto const &kv : *pEm) ids.push_back(kv.first);
+      std::sort(ids.begin(), ids.end());
+      for (auto u : ids) {
+        auto const &m = *pEm->at(u);
+        emU.push_back(u);
+        ov0.push_back(m.overlap.first);
+        ov1.push_back(m.overlap.second);
+        emScore.push_back(m.score);
+        emDir.push_back(static_cast<bool>(m.direction) ? 1 : 0);
+        emPrim.push_back(static_cast<bool>(m.isPrimary) ? 1 : 0);
+        emLine.push_back(m.lineNumber);
+      }
+    }
+    eb.push_back(emU.size());
+    out->edge_first    = dup(ef);
+    out->edge_second   = dup(es);
+    out->edge_em_begin = dup(eb);
+    out->n_em          = emU.size();
+    out->em_unitig     = dup(emU);
+    out->em_ov0        = dup(ov0);
+    out->em_ov1        = dup(ov1);
+    out->em_score      = dup(emScore);
+    out->em_dir        = dup(emDir);
+    out->em_prim       = dup(emPrim);
+    out->em_line       = dup(emLine);
+    return 0;
+  } catch (std::exception const &e) {
+    std::fprintf(stderr, "msref_build: %s\n", e.what());
+    return 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sequence path: strSlice / getReverseComplement (SequenceUtils.cpp:27-61) and the FASTA/FASTQ store
+// (SequenceAccessor.cpp:54-231) + get{Illumina,Nanopore}Sequence (SequenceUtils.cpp:63-85).
+// ---------------------------------------------------------------------------------------------------------------------
+
+// returns the slice length, or -1 if the reference threw (std::out_of_range from substr)
+int64_t msref_strslice(const char *s, uint64_t n, int i, int j, char *out) {
+  try {
+    auto v = muchsalsa::strSlice(std::string_view(s, n), i, j);
+    std::memcpy(out, v.data(), v.size());
+    return static_cast<int64_t>(v.size());
+  } catch (std::exception const &) {
+    return -1;
+  }
+}
+
+void msref_revcomp(const char *s, uint64_t n, char *out) {
+  auto r = muchsalsa::getReverseComplement(std::string(s, n));
+  std::memcpy(out, r.data(), r.size());
+}
+
+struct msref_seq {
+  std::unique_ptr<muchsalsa::threading::ThreadPool> pool;
+  muchsalsa::Registry                               regNanopore, regIllumina;
+  std::unique_ptr<muchsalsa::SequenceAccessor>      acc;
+};
+
+// Opens the two sequence files and builds the offset index like src/main.cpp:161-163.  When `prime_*` name lists are
+// given (newline separated) they are registered first, in order — that is what ingest has done to the registries by
+// the time main() reaches the sequence files.
+msref_seq *msref_seq_open(const char *nanopore_path, const char *unitigs_path, const char *prime_reads,
+                          const char *prime_unitigs) {
+  try {
+    auto h  = std::make_unique<msref_seq>();
+    h->pool = std::make_unique<muchsalsa::threading::ThreadPool>(1);
+    auto prime = [](muchsalsa::Registry &reg, const char *names) {
+      if (!names) return;
+      std::string_view sv(names);
+      while (!sv.empty()) {
+        auto q = sv.find('\n');
+        auto t = sv.substr(0, q);
+        if (!t.empty()) reg[std::string(t)];
+        if (q == std::string_view::npos) break;
+        sv.remove_prefix(q + 1);
+      }
+    };
+    prime(h->regNanopore, prime_reads);
+    prime(h->regIllumina, prime_unitigs);
+    h->acc = std::make_unique<muchsalsa::SequenceAccessor>(h->pool.get(), nanopore_path, unitigs_path, &h->regNanopore,
+                                                           &h->regIllumina);
+    h->acc->buildIndex();
+    return h.release();
+  } catch (std::exception const &e) {
+    std::fprintf(stderr, "msref_seq_open: %s\n", e.what());
+    return nullptr;
+  }
+}
+
+void msref_seq_close(msref_seq *h) { delete h; }
+
+// id the registry holds for `name` (which: 0 = unitig/illumina, 1 = nanopore)
+uint32_t msref_seq_id(msref_seq *h, int which, const char *name) {
+  return which ? h->regNanopore[name] : h->regIllumina[name];
+}
+
+// whole record (whitespace stripped); returns length or -1 when the reference threw
+int64_t msref_seq_full(msref_seq *h, int which, uint32_t id, char *out, uint64_t cap) {
+  try {
+    auto s = which ? h->acc->getNanoporeSequence(id) : h->acc->getIlluminaSequence(id);
+    if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+    return static_cast<int64_t>(s.size());
+  } catch (std::exception const &) {
+    return -1;
+  }
+}
+
+// get{Illumina,Nanopore}Sequence(acc, id, l, r, dir); returns length or -1 when the reference threw
+int64_t msref_seq_fetch(msref_seq *h, int which, uint32_t id, int l, int r, int dir, char *out, uint64_t cap) {
+  try {
+    auto s = which ? muchsalsa::getNanoporeSequence(*h->acc, id, l, r, muchsalsa::Toggle(dir != 0))
+                   : muchsalsa::getIlluminaSequence(*h->acc, id, l, r, muchsalsa::Toggle(dir != 0));
+    if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+    return static_cast<int64_t>(s.size());
+  } catch (std::exception const &) {
+    return -1;
+  }
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// msref_cli: `msref_cli <paf> <threads>` prints one line of phase timings + counts.  It is a separate PROCESS on
+// purpose: with threads >= 2 the reference races on GraphBase::m_adjacencyList (Graph.cpp:96-116 vs 212-230) and can
+// segfault; bench.py reports that exit status faithfully instead of dying with it.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifdef MSREF_CLI
+int main(int argc, char **argv) {
+  if (argc < 3) {
+    std::fprintf(stderr, "usage: %s <paf> <threads>\n", argv[0]);
+    return 2;
+  }
+  ms_tables t;
+  int       rc = msref_build(argv[1], std::atoi(argv[2]), 0, &t);
+  if (rc) return rc;
+  std::printf("{\"threads\": %d, \"t_index\": %.6f, \"t_read\": %.6f, \"t_edges\": %.6f, \"n_reads\": %llu, "
+              "\"n_vm\": %llu, \"n_edges\": %llu, \"n_em\": %llu}\n",
+              std::atoi(argv[2]), t.t_index, t.t_read, t.t_edges, (unsigned long long)t.n_reads,
+              (unsigned long long)t.n_vm, (unsigned long long)t.n_edges, (unsigned long long)t.n_em);
+  return 0;
+}
+#endif
