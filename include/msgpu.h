@@ -1,0 +1,190 @@
+/* msgpu.h — C ABI of the B200 graph-construction path for MuCHSALSA.
+ *
+ * This is the drop-in boundary.  The reference (MuCHSALSA v0.0.2, a CPU-only C++20 program) has no plugin / FFI
+ * interface; the seam is two statements of its main() plus four free functions.  Every entry point below names the
+ * reference interface it replaces (file:line relative to the reference tree):
+ *
+ *   construction   src/main.cpp:156-157      blastFileReader.read(); matchMap.calculateEdges();
+ *                  = BlastFileAccessor.cpp:40-91, BlastFileReader.cpp:72-130, Registry.cpp:36-45,
+ *                    Graph.cpp:141-149,212-230,291-311, MatchMap.cpp:53-81,109-134,161-224
+ *   sequences      include/ms/SequenceUtils.h:37-45 (strSlice, getReverseComplement, getIlluminaSequence,
+ *                  getNanoporeSequence) over SequenceAccessor.cpp:54-85,114-139,143-231
+ *
+ * INTEGRATION.md shows the ~60-line C++ shim that replays a msgpu_host_result into the reference's own
+ * Graph / MatchMap / Registry objects through their public API, so everything downstream is untouched.
+ *
+ * Conventions: plain pointers and sizes only; every function returns an msgpu_status (0 = ok) and never throws;
+ * msgpu_last_error() gives the message for the last failing call on that context.  A context is bound to ONE CUDA
+ * device and is used by one thread at a time for construction; msgpu_seq_fetch_batch() may be called concurrently
+ * from many threads (the reference fetches sequences from pool threads, src/main.cpp:645-653).
+ *
+ * Determinism contract (= the reference run with one worker thread, its only deterministic mode):
+ *   - the last line of the PAF is never parsed                                   (BlastFileReader.cpp:76)
+ *   - a line is accepted iff matches >= 400 and c3 - c2 >= 400                   (BlastFileReader.cpp:106-107)
+ *   - read ids / unitig ids = rank of the first accepted line naming them        (Registry.cpp:36-45)
+ *   - a read's vertex carries the line index and read length of that first line  (Graph.cpp:148)
+ *   - per (read, unitig) the accepted line with the smallest index is kept       (MatchMap.cpp:64-73)
+ *   - per unitig every pair of kept matches whose unitig overlap is > 100 gives one edge match; an edge exists iff
+ *     it has >= 1 edge match; edge.first is the read with the smaller id        (MatchMap.cpp:185-218)
+ */
+#ifndef MSGPU_H
+#define MSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSGPU_ABI_VERSION 1
+
+typedef enum msgpu_status {
+  MSGPU_OK               = 0,
+  MSGPU_ERR_INVALID_ARG  = 1,
+  MSGPU_ERR_CUDA         = 2, /* a CUDA runtime call failed; message in msgpu_last_error */
+  MSGPU_ERR_IO           = 3, /* "Can't open blast file." / "Can't open sequence file(s)." */
+  MSGPU_ERR_INVALID_PAF  = 4, /* "Invalid BLAST file." (fewer than 10 fields) or a field std::stoi would reject */
+  MSGPU_ERR_NOMEM        = 5,
+  MSGPU_ERR_LIMIT        = 6, /* > 2^32-2 lines in one PAF buffer, or a shape the kernels do not support */
+  MSGPU_ERR_NO_RESULT    = 7, /* result accessor called before a successful build */
+  MSGPU_ERR_OUT_OF_RANGE = 8, /* sequence fetch: unknown id, or strSlice would throw std::out_of_range */
+  MSGPU_ERR_INTERNAL     = 9
+} msgpu_status;
+
+typedef struct msgpu_ctx msgpu_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------------------
+ * replaces: ThreadPool construction (src/main.cpp:143-144) — the GPU is the worker pool of this path. */
+int         msgpu_create(int cuda_device, msgpu_ctx **out_ctx);
+void        msgpu_destroy(msgpu_ctx *ctx);
+const char *msgpu_last_error(const msgpu_ctx *ctx);
+int         msgpu_abi_version(void);
+/* All work of the context is enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own stream). */
+int         msgpu_set_stream(msgpu_ctx *ctx, void *cuda_stream);
+
+/* ---- construction -------------------------------------------------------------------------------------------------
+ * Each build replaces the context's previous result.
+ *
+ * msgpu_build_from_paf        : replaces BlastFileAccessor(path) + read() + calculateEdges() (src/main.cpp:153-157).
+ * msgpu_build_from_paf_buffer : same, PAF text already in host memory (pinned memory avoids a staging copy).
+ * msgpu_build_from_paf_device : same, PAF text already resident in HBM; nothing is copied to the host.
+ */
+int msgpu_build_from_paf(msgpu_ctx *ctx, const char *paf_path);
+int msgpu_build_from_paf_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes);
+int msgpu_build_from_paf_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes);
+
+/* Packed structure-of-arrays match records (the result of ingest, = the VertexMatch rows of MatchMap.h:51-59 plus
+ * their ids), grouped by unitig and ordered by line inside a unitig.  Device pointers.
+ * flags: bit0 = direction ('+'), bit1 = isPrimary. */
+typedef struct msgpu_match_soa {
+  uint64_t        n;
+  const uint32_t *unitig; /* non-decreasing */
+  const uint32_t *read;
+  const int32_t  *ir0, *ir1; /* illuminaRange (inclusive) */
+  const int32_t  *nr0, *nr1; /* nanoporeRange (inclusive) */
+  const int32_t  *score;     /* number of matches (PAF column 10) */
+  const uint32_t *line;      /* PAF line index */
+  const uint8_t  *flags;
+} msgpu_match_soa;
+
+/* msgpu_build_from_records : pairing + keyed merge only (MatchMap::calculateEdges, MatchMap.cpp:161-224) on records
+ * that are already packed in HBM.  n_reads / n_unitigs bound the ids.  The read table of the result is left empty. */
+int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *dev_records, uint32_t n_reads,
+                             uint32_t n_unitigs);
+
+typedef struct msgpu_counts {
+  uint64_t n_lines;   /* lines in the buffer (BlastFileAccessor::getLineCount) */
+  uint64_t n_reads;   /* graph order */
+  uint64_t n_unitigs;
+  uint64_t n_matches; /* kept VertexMatch rows */
+  uint64_t n_pairs;   /* candidate pairs examined, sum over unitigs of k(k-1)/2 */
+  uint64_t n_edges;   /* graph size */
+  uint64_t n_edge_matches;
+} msgpu_counts;
+
+int msgpu_result_counts(const msgpu_ctx *ctx, msgpu_counts *out);
+
+/* The result as flat arrays.  Row orders:
+ *   reads / unitigs : by id
+ *   matches         : grouped by unitig (ascending id), by line inside a unitig
+ *   edges           : by (first, second), first < second
+ *   edge matches    : by (first, second, unitig); edge e owns rows [edge_em_begin[e], edge_em_begin[e+1])
+ * In msgpu_device_result every pointer is a device pointer, in msgpu_host_result a pointer into pinned host memory;
+ * both stay valid until the next build on the context or msgpu_destroy. */
+typedef struct msgpu_tables {
+  /* Vertex(id, nanoporeLength, lineIdx) — Vertex.h:185-188 */
+  const int32_t  *read_nlen;     /* as parsed by std::stoi; the reference widens it to size_t */
+  const uint32_t *read_line;
+  const uint64_t *read_name_off; /* n_reads + 1, into read_names */
+  const char     *read_names;
+  const uint64_t *unitig_name_off; /* n_unitigs + 1 */
+  const char     *unitig_names;
+  /* VertexMatch — MatchMap.h:51-59 */
+  const uint32_t *m_unitig, *m_read;
+  const int32_t  *m_nr0, *m_nr1, *m_ir0, *m_ir1;
+  const double   *m_rratio;
+  const int32_t  *m_score;  /* the reference widens it to size_t */
+  const uint32_t *m_line;
+  const uint8_t  *m_flags;  /* bit0 direction, bit1 isPrimary */
+  /* Edge — Edge::getVertices() order */
+  const uint32_t *edge_first, *edge_second;
+  const uint64_t *edge_em_begin; /* n_edges + 1 */
+  /* EdgeMatch — MatchMap.h:68-74 */
+  const uint32_t *em_unitig;
+  const int32_t  *em_ov0, *em_ov1;
+  const double   *em_score;
+  const uint32_t *em_line;
+  const uint8_t  *em_flags; /* bit0 direction, bit1 isPrimary */
+} msgpu_tables;
+
+int msgpu_result_device(const msgpu_ctx *ctx, msgpu_tables *out);
+/* Copies the result to pinned host memory (once per build; later calls return the same pointers). */
+int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out);
+
+/* Device time of the stages of the last build, milliseconds (CUDA events on the context's stream). */
+typedef struct msgpu_timings {
+  float h2d_ms, ingest_ms, pair_ms, merge_ms, d2h_ms, total_ms;
+} msgpu_timings;
+int msgpu_result_timings(const msgpu_ctx *ctx, msgpu_timings *out);
+
+/* ---- sequences ----------------------------------------------------------------------------------------------------
+ * msgpu_seq_load   replaces SequenceAccessor(...) + buildIndex() (src/main.cpp:161-163): both files are indexed,
+ *                  whitespace-stripped and kept resident in HBM.  Ids continue the numbering of the context's last
+ *                  build (the reference passes the same two Registry objects, src/main.cpp:161-162); names the PAF
+ *                  never mentioned get the next free ids in file order.  A file whose extension is not .fa/.fasta
+ *                  (case-insensitive) is FASTQ (SequenceAccessor.cpp:71-78); the unitig file is always FASTA.
+ * msgpu_seq_fetch_batch  replaces getIlluminaSequence / getNanoporeSequence (SequenceUtils.cpp:63-85) for a batch:
+ *                  request i yields strSlice(record, left, right + 1), reverse-complemented iff !direction, written
+ *                  at out + out_off[i] (out_off has n + 1 entries, filled by the call).  Requests the reference
+ *                  would answer with an exception get status[i] != 0 and an empty slice.
+ */
+typedef struct msgpu_seq_req {
+  uint32_t which; /* 0 = unitig (getIlluminaSequence), 1 = nanopore read (getNanoporeSequence) */
+  uint32_t id;
+  int32_t  left, right;
+  uint32_t direction; /* Toggle: non-zero = forward, zero = reverse complement */
+} msgpu_seq_req;
+
+int msgpu_seq_load(msgpu_ctx *ctx, const char *unitigs_fasta_path, const char *nanopore_path);
+int msgpu_seq_load_buffers(msgpu_ctx *ctx, const char *unitigs_fasta, size_t n_unitigs_bytes,
+                           const char *nanopore, size_t n_nanopore_bytes, int nanopore_is_fastq);
+/* id of a sequence name (which as above); MSGPU_ERR_OUT_OF_RANGE if unknown */
+int msgpu_seq_id(const msgpu_ctx *ctx, uint32_t which, const char *name, uint32_t *out_id);
+/* upper bound of the bytes a batch needs, so the caller can size `out` */
+int msgpu_seq_batch_bound(const msgpu_ctx *ctx, const msgpu_seq_req *reqs, size_t n, uint64_t *out_bytes);
+int msgpu_seq_fetch_batch(msgpu_ctx *ctx, const msgpu_seq_req *reqs, size_t n, char *out, uint64_t out_capacity,
+                          uint64_t *out_off, uint8_t *status);
+/* same with every buffer resident in HBM (requests, output, offsets, status) — the path bench.py times */
+int msgpu_seq_fetch_batch_device(msgpu_ctx *ctx, const msgpu_seq_req *dev_reqs, size_t n, char *dev_out,
+                                 uint64_t out_capacity, uint64_t *dev_out_off, uint8_t *dev_status);
+/* strSlice / getReverseComplement on caller-provided text (SequenceUtils.cpp:27-61), batched, device pointers:
+ * text i = text[text_off[i] .. text_off[i+1]) ; writes like msgpu_seq_fetch_batch_device. */
+int msgpu_slice_revcomp_device(msgpu_ctx *ctx, const char *dev_text, const uint64_t *dev_text_off,
+                               const int32_t *dev_left, const int32_t *dev_right, const uint8_t *dev_revcomp, size_t n,
+                               char *dev_out, uint64_t out_capacity, uint64_t *dev_out_off, uint8_t *dev_status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSGPU_H */

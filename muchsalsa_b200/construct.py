@@ -1,0 +1,212 @@
+"""Thin Python host layer over the C ABI (include/msgpu.h) — used by tests, bench.py and the multi-GPU driver.
+
+The product is libmsgpu.so; this module only moves pointers.  Names follow the reference: a `GraphBuilder` does what
+`BlastFileReader::read()` + `MatchMap::calculateEdges()` do (src/main.cpp:156-157), `SequenceStore` what
+`SequenceAccessor` + `get{Illumina,Nanopore}Sequence` do (SequenceUtils.cpp:63-85).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+STATUS = {0: "OK", 1: "INVALID_ARG", 2: "CUDA", 3: "IO", 4: "INVALID_PAF", 5: "NOMEM", 6: "LIMIT", 7: "NO_RESULT",
+          8: "OUT_OF_RANGE", 9: "INTERNAL"}
+
+
+class MsGpuError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"msgpu status {status} ({STATUS.get(status, '?')}): {message}")
+        self.status = status
+        self.message = message
+
+
+@dataclass
+class Construction:
+    """Host copy of a construction result; row orders as documented in include/msgpu.h."""
+    counts: dict
+    read_names: list
+    read_nlen: np.ndarray
+    read_line: np.ndarray
+    unitig_names: list
+    matches: dict  # unitig read nr0 nr1 ir0 ir1 rratio score line flags
+    edge_first: np.ndarray
+    edge_second: np.ndarray
+    edge_em_begin: np.ndarray
+    edge_matches: dict  # unitig ov0 ov1 score line flags
+    timings: dict
+
+
+def _np(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+
+
+def _names(off_ptr, blob_ptr, n):
+    if n == 0 or not off_ptr:
+        return []
+    off = np.ctypeslib.as_array(off_ptr, shape=(int(n) + 1,))
+    blob = C.string_at(blob_ptr, int(off[-1])) if off[-1] else b""
+    return [blob[int(off[i]):int(off[i + 1])].decode("latin-1") for i in range(int(n))]
+
+
+class GraphBuilder:
+    """One msgpu context = one GPU.  `build_*` replaces read() + calculateEdges()."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.msgpu_create(device, C.byref(h))
+        if rc != 0:
+            raise MsGpuError(rc, "msgpu_create failed: no usable CUDA device (there is no CPU fallback)")
+        self._h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.msgpu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MsGpuError(rc, self._lib.msgpu_last_error(self._h).decode("utf-8", "replace"))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self._lib.msgpu_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    # ---- construction
+    def build_from_paf(self, path):
+        self._check(self._lib.msgpu_build_from_paf(self._h, os.fspath(path).encode()))
+        return self
+
+    def build_from_buffer(self, buf):
+        """buf: bytes / bytearray / numpy uint8 array / anything with (data_ptr(), numel()) in HOST memory."""
+        ptr, n, keep = _host_ptr(buf)
+        self._keep = keep
+        self._check(self._lib.msgpu_build_from_paf_buffer(self._h, C.c_void_p(ptr), n))
+        return self
+
+    def build_from_device(self, dev_ptr: int, n_bytes: int):
+        self._check(self._lib.msgpu_build_from_paf_device(self._h, C.c_void_p(dev_ptr), n_bytes))
+        return self
+
+    def build_from_records(self, rec: dict, n_reads: int, n_unitigs: int):
+        """rec: dict of torch CUDA tensors (unitig, read, ir0, ir1, nr0, nr1, score, line, flags)."""
+        soa = _lib.MatchSoA()
+        soa.n = int(rec["unitig"].numel())
+        for k in ("unitig", "read", "ir0", "ir1", "nr0", "nr1", "score", "line", "flags"):
+            setattr(soa, k, rec[k].data_ptr())
+        self._keep = rec
+        self._check(self._lib.msgpu_build_from_records(self._h, C.byref(soa), n_reads, n_unitigs))
+        return self
+
+    # ---- results
+    def counts(self) -> dict:
+        c = _lib.Counts()
+        self._check(self._lib.msgpu_result_counts(self._h, C.byref(c)))
+        return {k: int(getattr(c, k)) for k, _ in c._fields_}
+
+    def timings(self) -> dict:
+        t = _lib.Timings()
+        self._check(self._lib.msgpu_result_timings(self._h, C.byref(t)))
+        return {k: float(getattr(t, k)) for k, _ in t._fields_}
+
+    def device_tables(self) -> _lib.Tables:
+        t = _lib.Tables()
+        self._check(self._lib.msgpu_result_device(self._h, C.byref(t)))
+        return t
+
+    def host_tables(self) -> _lib.Tables:
+        """Pointers into the library's pinned host slab (valid until the next build)."""
+        t = _lib.Tables()
+        self._check(self._lib.msgpu_result_host(self._h, C.byref(t)))
+        return t
+
+    def result(self) -> Construction:
+        c = self.counts()
+        t = self.host_tables()
+        R, U, M, E, EM = c["n_reads"], c["n_unitigs"], c["n_matches"], c["n_edges"], c["n_edge_matches"]
+        m = dict(unitig=_np(t.m_unitig, M, np.uint32), read=_np(t.m_read, M, np.uint32),
+                 nr0=_np(t.m_nr0, M, np.int32), nr1=_np(t.m_nr1, M, np.int32), ir0=_np(t.m_ir0, M, np.int32),
+                 ir1=_np(t.m_ir1, M, np.int32), rratio=_np(t.m_rratio, M, np.float64),
+                 score=_np(t.m_score, M, np.int32), line=_np(t.m_line, M, np.uint32),
+                 flags=_np(t.m_flags, M, np.uint8))
+        em = dict(unitig=_np(t.em_unitig, EM, np.uint32), ov0=_np(t.em_ov0, EM, np.int32),
+                  ov1=_np(t.em_ov1, EM, np.int32), score=_np(t.em_score, EM, np.float64),
+                  line=_np(t.em_line, EM, np.uint32), flags=_np(t.em_flags, EM, np.uint8))
+        have_names = bool(t.read_name_off)
+        return Construction(
+            counts=c,
+            read_names=_names(t.read_name_off, t.read_names, R) if have_names else [],
+            read_nlen=_np(t.read_nlen, R if have_names else 0, np.int32),
+            read_line=_np(t.read_line, R if have_names else 0, np.uint32),
+            unitig_names=_names(t.unitig_name_off, t.unitig_names, U) if have_names else [],
+            matches=m, edge_first=_np(t.edge_first, E, np.uint32), edge_second=_np(t.edge_second, E, np.uint32),
+            edge_em_begin=_np(t.edge_em_begin, E + 1, np.uint64), edge_matches=em, timings=self.timings())
+
+    # ---- sequences
+    def seq_load(self, unitigs_path, nanopore_path):
+        self._check(self._lib.msgpu_seq_load(self._h, os.fspath(unitigs_path).encode(),
+                                             os.fspath(nanopore_path).encode()))
+        return self
+
+    def seq_load_buffers(self, unitigs: bytes, nanopore: bytes, nanopore_is_fastq: bool):
+        self._check(self._lib.msgpu_seq_load_buffers(self._h, unitigs, len(unitigs), nanopore, len(nanopore),
+                                                     1 if nanopore_is_fastq else 0))
+        return self
+
+    def seq_id(self, which: int, name: str):
+        out = C.c_uint32()
+        rc = self._lib.msgpu_seq_id(self._h, which, name.encode("latin-1"), C.byref(out))
+        if rc == 8:
+            return None
+        self._check(rc)
+        return int(out.value)
+
+    def seq_fetch_batch(self, reqs):
+        """reqs: iterable of (which, id, left, right, direction).  Returns a list of bytes, None where the reference
+        would throw."""
+        reqs = list(reqs)
+        n = len(reqs)
+        arr = (_lib.SeqReq * max(1, n))()
+        for i, (w, id_, l, r, d) in enumerate(reqs):
+            arr[i] = _lib.SeqReq(w, id_, l, r, 1 if d else 0)
+        bound = C.c_uint64()
+        self._check(self._lib.msgpu_seq_batch_bound(self._h, arr, n, C.byref(bound)))
+        out = C.create_string_buffer(int(bound.value) + 1)
+        off = (C.c_uint64 * (n + 1))()
+        st = (C.c_uint8 * max(1, n))()
+        rc = self._lib.msgpu_seq_fetch_batch(self._h, arr, n, out, int(bound.value), off, st)
+        if rc != 0:
+            raise MsGpuError(rc, "msgpu_seq_fetch_batch failed")
+        raw = out.raw
+        return [None if st[i] else raw[off[i]:off[i + 1]] for i in range(n)]
+
+
+def _host_ptr(buf):
+    if hasattr(buf, "data_ptr"):  # torch tensor (pinned or pageable host memory)
+        return int(buf.data_ptr()), int(buf.numel() * buf.element_size()), buf
+    if isinstance(buf, np.ndarray):
+        a = np.ascontiguousarray(buf)
+        return int(a.ctypes.data), int(a.nbytes), a
+    if isinstance(buf, (bytes, bytearray)):
+        a = np.frombuffer(buf, np.uint8)
+        return int(a.ctypes.data), int(a.nbytes), (a, buf)
+    raise TypeError(f"unsupported buffer type {type(buf)}")

@@ -1,0 +1,161 @@
+// common.cuh — shared host/device helpers of libmsgpu (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace msgpu {
+
+constexpr int kNumSMs = 148; // B200: 2 dies x 74 SMs; grids are sized in multiples of this (persistent / grid-stride)
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define MSGPU_CUDA(expr)                                                                                    \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) {                                                                                \
+      throw ::msgpu::CudaError(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                               ":" + std::to_string(__LINE__) + ")");                                       \
+    }                                                                                                       \
+  } while (0)
+
+#define MSGPU_LAUNCH_CHECK() MSGPU_CUDA(cudaGetLastError())
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Device arena: one growing list of cudaMalloc'd slabs, bump-allocated, reset per build.  Slabs are kept across builds
+// (HBM is 180 GB; re-running the same workload must not pay cudaMalloc again) and coalesced into one slab of the
+// high-water size on reset.
+// ---------------------------------------------------------------------------------------------------------------------
+class Arena {
+public:
+  ~Arena() { release(); }
+  void release() {
+    for (auto &s : m_slabs) cudaFree(s.base);
+    m_slabs.clear();
+    m_used = m_high = 0;
+  }
+  // start a new build: if the previous one spilled into several slabs, replace them by one of the total size
+  void reset() {
+    if (m_slabs.size() > 1) {
+      size_t total = 0;
+      for (auto &s : m_slabs) total += s.size;
+      for (auto &s : m_slabs) cudaFree(s.base);
+      m_slabs.clear();
+      Slab  s{nullptr, total, 0};
+      MSGPU_CUDA(cudaMalloc(&s.base, total));
+      m_slabs.push_back(s);
+    }
+    for (auto &s : m_slabs) s.used = 0;
+    m_used = 0;
+  }
+  template <class T> T *alloc(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~size_t(255);
+    if (bytes == 0) bytes = 256;
+    for (auto &s : m_slabs) {
+      if (s.size - s.used >= bytes) {
+        void *p = static_cast<char *>(s.base) + s.used;
+        s.used += bytes;
+        m_used += bytes;
+        if (m_used > m_high) m_high = m_used;
+        return static_cast<T *>(p);
+      }
+    }
+    size_t want = bytes > (size_t(64) << 20) ? bytes : (size_t(64) << 20);
+    if (want < m_high / 2) want = m_high / 2;
+    Slab s{nullptr, want, 0};
+    MSGPU_CUDA(cudaMalloc(&s.base, want));
+    m_slabs.push_back(s);
+    return alloc<T>(n);
+  }
+  size_t high_water() const { return m_high; }
+
+private:
+  struct Slab {
+    void  *base;
+    size_t size, used;
+  };
+  std::vector<Slab> m_slabs;
+  size_t            m_used = 0, m_high = 0;
+};
+
+inline int grid_for(size_t n_items, int block, int max_waves = 8) {
+  // grid = multiple of the SM count, capped at `max_waves` x (SMs x resident blocks); kernels are grid-stride
+  size_t need   = (n_items + block - 1) / block;
+  size_t per_sm = 2048 / block;
+  size_t cap    = size_t(kNumSMs) * per_sm * max_waves;
+  if (need > cap) need = cap;
+  size_t g = ((need + kNumSMs - 1) / kNumSMs) * kNumSMs;
+  return static_cast<int>(g ? g : kNumSMs);
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
+
+template <class T> __device__ __forceinline__ T warp_inclusive_scan(T v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T n = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane_id() >= (unsigned)d) v += n;
+  }
+  return v;
+}
+
+template <class T> __device__ __forceinline__ T warp_reduce_sum(T v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// Block-wide exclusive scan of one value per thread (blockDim.x <= 1024, multiple of 32).  `smem` holds 33 T.
+// Returns the exclusive prefix of the calling thread; *total receives the block sum.  Ends with a __syncthreads()
+// so `smem` can be reused immediately.
+template <class T> __device__ __forceinline__ T block_exclusive_scan(T v, T *smem, T *total) {
+  T        incl = warp_inclusive_scan(v);
+  unsigned w = warp_id(), l = lane_id(), nw = blockDim.x >> 5;
+  if (l == 31) smem[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    T x  = l < nw ? smem[l] : T(0);
+    T xs = warp_inclusive_scan(x);
+    if (l < nw) smem[l] = xs - x;
+    if (l == nw - 1) smem[32] = xs;
+  }
+  __syncthreads();
+  T res  = smem[w] + incl - v;
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+// 128-bit streaming loads / stores: the inputs of the big passes are read once, so keep them out of L1
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// 64-bit mix (splitmix64 finaliser) — used to spread keys over the open-addressing tables
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+#endif // __CUDACC__
+
+} // namespace msgpu

@@ -1,0 +1,621 @@
+// ingest.cu — PAF text resident in HBM -> packed structure-of-arrays match records (kernels K1-K5 of SURVEY.md §2).
+//
+// Replaces, for the reference run with one worker thread (file:line relative to the reference tree):
+//   K1 line index            BlastFileAccessor::_buildIndex   BlastFileAccessor.cpp:77-91 (+ readline, IO.cpp:54-97)
+//   K1 tokenise              BlastFileReader::parseLine       BlastFileReader.cpp:86-104
+//   K2 filter + derive       BlastFileReader::parseLine       BlastFileReader.cpp:101-125
+//   K3 id interning, vertex  Registry::operator[]             Registry.cpp:36-45 ; Graph::_addVertex Graph.cpp:141-149
+//   K4 keep-min-line dedup   MatchMap::addVertexMatch         MatchMap.cpp:53-81
+//   K5 group by unitig       m_scaffolds + sort by line       MatchMap.cpp:77-79,178-183
+//
+// Everything order-dependent in the reference is made order-free here:
+//   "first request gets the next id"  ->  atomicMin of the line index per name, then id = rank of that line among the
+//                                         first-appearance lines (one prefix sum over lines)
+//   "first Vertex of an id wins"      ->  the vertex takes its fields from that same first-appearance line
+//   "smaller line replaces"           ->  atomicMin of the line index per (unitig, read) key
+// Names are hashed (64 bit) for the open-addressing tables, and every line then compares its name bytes with the
+// representative of its slot; a mismatch (a 64-bit collision) restarts interning with another hash seed.
+#include <algorithm>
+
+#include "../../include/msgpu.h"
+#include "internal.h"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace msgpu {
+
+// thresholds: BlastFileReader.cpp:48-50
+constexpr int      kMinimumMatches = 400;
+constexpr int      kThLength       = 500;
+constexpr uint64_t kThMatches      = 500;
+
+constexpr uint8_t kFAccepted = 1, kFDir = 2, kFPrim = 4, kFFirstRead = 8, kFFirstUnitig = 16, kFSurvivor = 32;
+
+struct IngestStatus {
+  unsigned long long first_bad_line; // smallest line index the reference would have thrown on; ~0 = none
+  unsigned           n_accepted;
+  unsigned           collision;
+  unsigned           unsorted;
+  unsigned           pad;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1a: line index.  A thread owns 32 consecutive bytes (two aligned 128-bit loads), a block a tile of 8 KB.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kNlBlock = 256;
+constexpr int kNlTile  = kNlBlock * 32;
+
+__device__ __forceinline__ unsigned nl_mask4(unsigned w) {
+  unsigned y = (__vcmpeq4(w, 0x0a0a0a0au) & 0x80808080u) >> 7; // bit 0/8/16/24 set where the byte is '\n'
+  return ((y * 0x00204081u) >> 21) & 0xfu;
+}
+__device__ __forceinline__ unsigned nl_mask16(uint4 v) {
+  return nl_mask4(v.x) | (nl_mask4(v.y) << 4) | (nl_mask4(v.z) << 8) | (nl_mask4(v.w) << 12);
+}
+
+// newline bit mask of the 32 virtual bytes [vb, vb+32) of the buffer that starts `mis` bytes after a 16-byte boundary
+__device__ __forceinline__ unsigned nl_mask32(const uint4 *aligned, uint64_t vb, uint64_t mis, uint64_t nv) {
+  if (vb >= nv) return 0;
+  unsigned m = nl_mask16(ld_stream_u4(aligned + (vb >> 4)));
+  if (vb + 16 < nv) m |= nl_mask16(ld_stream_u4(aligned + (vb >> 4) + 1)) << 16;
+  if (vb < mis) m &= ~0u << (mis - vb);                        // bytes before the buffer
+  if (vb + 32 > nv) m &= (nv - vb >= 32) ? ~0u : ((1u << (nv - vb)) - 1u); // bytes after it
+  return m;
+}
+
+__global__ void __launch_bounds__(kNlBlock)
+    newline_count_kernel(const uint4 *__restrict__ aligned, uint64_t mis, uint64_t nv, uint32_t *__restrict__ tile_cnt) {
+  __shared__ uint32_t sm[33];
+  uint64_t            vb = uint64_t(blockIdx.x) * kNlTile + uint64_t(threadIdx.x) * 32;
+  uint32_t            c  = __popc(nl_mask32(aligned, vb, mis, nv));
+  uint32_t            total;
+  block_exclusive_scan<uint32_t>(c, sm, &total);
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+}
+
+// line_start[k+1] = offset of the byte after the k-th newline
+__global__ void __launch_bounds__(kNlBlock)
+    newline_write_kernel(const uint4 *__restrict__ aligned, uint64_t mis, uint64_t nv,
+                         const uint32_t *__restrict__ tile_off, uint64_t *__restrict__ line_start) {
+  __shared__ uint32_t sm[33];
+  uint64_t            vb = uint64_t(blockIdx.x) * kNlTile + uint64_t(threadIdx.x) * 32;
+  unsigned            m  = nl_mask32(aligned, vb, mis, nv);
+  uint32_t            total;
+  uint32_t            rank = block_exclusive_scan<uint32_t>(__popc(m), sm, &total) + tile_off[blockIdx.x];
+  while (m) {
+    int b = __ffs(m) - 1;
+    m &= m - 1;
+    line_start[uint64_t(rank) + 1] = vb + b - mis + 1;
+    ++rank;
+  }
+}
+
+__global__ void line_index_finish_kernel(const char *__restrict__ paf, uint64_t n, const uint32_t *n_newlines,
+                                         uint64_t *line_start, uint64_t *n_lines_out) {
+  // a trailing run of bytes without '\n' is one more line (IO.cpp:92-95); give it a virtual terminator so that
+  // length(line i) = line_start[i+1] - line_start[i] - 1 holds for every line
+  uint64_t nn   = *n_newlines;
+  bool     open = n > 0 && paf[n - 1] != '\n';
+  line_start[0] = 0;
+  if (open) line_start[nn + 1] = n + 1;
+  *n_lines_out = nn + (open ? 1 : 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1b + K2: tokenise, std::stoi the numeric fields, accept filter.  One thread per line; a warp covers ~2-3 KB of
+// contiguous text, which L1 serves after the first touch of each 128-byte line.
+// ---------------------------------------------------------------------------------------------------------------------
+struct LineFields { // per-line scratch, structure-of-arrays, indexed by line
+  int32_t  *c2, *ir1, *c6, *nr0, *nr1, *c9;
+  uint32_t *rname_rel; // offset of the read name (field 5) from the line start
+  uint16_t *rname_len, *uname_len;
+  uint64_t *rhash, *uhash;
+  uint8_t  *flags;
+};
+
+__device__ __forceinline__ bool dev_isspace(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+// std::stoi on [s, s+n): false if it would throw (no digits / out of int range)
+__device__ __forceinline__ bool dev_stoi(const char *s, uint32_t n, int *out) {
+  uint32_t i = 0;
+  while (i < n && dev_isspace(s[i])) ++i;
+  bool neg = false;
+  if (i < n && (s[i] == '+' || s[i] == '-')) {
+    neg = s[i] == '-';
+    ++i;
+  }
+  if (i >= n || s[i] < '0' || s[i] > '9') return false;
+  long long v = 0;
+  for (; i < n && s[i] >= '0' && s[i] <= '9'; ++i) {
+    v = v * 10 + (s[i] - '0');
+    if (v > 2147483648ll) return false;
+  }
+  if (neg) v = -v;
+  if (v > 2147483647ll || v < -2147483648ll) return false;
+  *out = int(v);
+  return true;
+}
+
+__device__ __forceinline__ uint64_t name_hash(const char *s, uint32_t n, uint64_t seed) {
+  uint64_t h = 1469598103934665603ull ^ seed;
+  for (uint32_t i = 0; i < n; ++i) h = (h ^ (unsigned char)s[i]) * 1099511628211ull;
+  return mix64(h) | 1ull; // 0 is the empty-slot marker
+}
+
+__global__ void __launch_bounds__(256)
+    parse_lines_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ line_start, uint64_t n_parse,
+                       uint64_t seed, LineFields f, IngestStatus *status) {
+  unsigned n_acc = 0;
+  for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
+       li += uint64_t(gridDim.x) * blockDim.x) {
+    const char *s   = paf + line_start[li];
+    uint64_t    len = line_start[li + 1] - line_start[li] - 1; // getLine() drops the last character of the line
+    // std::getline(iss, token, '\t'): a field exists iff at least one character is left
+    uint32_t fo[10], fl[10];
+    int      ntok = 0;
+    uint64_t p    = 0;
+    while (p < len && ntok < 10) {
+      uint64_t q = p;
+      while (q < len && s[q] != '\t') ++q;
+      fo[ntok] = uint32_t(p);
+      fl[ntok] = uint32_t(q - p);
+      ++ntok;
+      p = q + 1;
+    }
+    uint8_t flags = 0;
+    bool    bad   = ntok < 10; // BlastFileReader.cpp:97 ("Invalid BLAST file.")
+    int     c2 = 0, c3 = 0, c9 = 0, c6 = 0, c7 = 0, c8 = 0;
+    if (!bad)
+      bad = !(dev_stoi(s + fo[2], fl[2], &c2) && dev_stoi(s + fo[3], fl[3], &c3) && dev_stoi(s + fo[9], fl[9], &c9) &&
+              dev_stoi(s + fo[6], fl[6], &c6));
+    if (!bad) {
+      int      ir1     = c3 - 1;
+      int      ilen    = ir1 - c2 + 1;
+      uint64_t matches = uint64_t((long long)c9); // static_cast<std::size_t>(int), BlastFileReader.cpp:102
+      bool     add     = matches >= uint64_t(kMinimumMatches) && ilen >= kMinimumMatches;
+      if (add) {
+        bad = !(dev_stoi(s + fo[7], fl[7], &c7) && dev_stoi(s + fo[8], fl[8], &c8));
+        if (!bad && (fl[5] > 0xffffu || fl[0] > 0xffffu)) bad = true; // names longer than 64 KiB are not supported
+        if (!bad) {
+          flags = kFAccepted;
+          if (fl[4] == 1 && s[fo[4]] == '+') flags |= kFDir;
+          if (ilen >= kThLength && matches >= kThMatches) flags |= kFPrim;
+          f.c2[li]        = c2;
+          f.ir1[li]       = ir1;
+          f.c6[li]        = c6;
+          f.nr0[li]       = c7;
+          f.nr1[li]       = c8 - 1;
+          f.c9[li]        = c9;
+          f.rname_rel[li] = fo[5];
+          f.rname_len[li] = uint16_t(fl[5]);
+          f.uname_len[li] = uint16_t(fl[0]);
+          f.rhash[li]     = name_hash(s + fo[5], fl[5], seed);
+          f.uhash[li]     = name_hash(s + fo[0], fl[0], seed ^ 0x9e3779b97f4a7c15ull);
+          ++n_acc;
+        }
+      }
+    }
+    if (bad) atomicMin(&status->first_bad_line, (unsigned long long)li);
+    f.flags[li] = flags;
+  }
+  n_acc = warp_reduce_sum(n_acc);
+  if (lane_id() == 0 && n_acc) atomicAdd(&status->n_accepted, n_acc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K3: interning.  Open addressing on the 64-bit name hash; the slot keeps the smallest accepted line naming it.
+// ---------------------------------------------------------------------------------------------------------------------
+struct InternTable {
+  unsigned long long *keys;    // 0 = empty
+  uint32_t           *minline; // 0xffffffff initially
+  uint32_t           *id;
+  uint64_t            mask;
+};
+
+__global__ void __launch_bounds__(256)
+    intern_insert_kernel(const uint8_t *__restrict__ flags, const uint64_t *__restrict__ hash, uint64_t n_parse,
+                         InternTable t, uint32_t *__restrict__ slot_of_line) {
+  for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
+       li += uint64_t(gridDim.x) * blockDim.x) {
+    if (!(flags[li] & kFAccepted)) continue;
+    unsigned long long h = hash[li];
+    uint64_t           p = (h >> 1) & t.mask;
+    for (;;) {
+      unsigned long long prev = atomicCAS(&t.keys[p], 0ull, h);
+      if (prev == 0ull || prev == h) break;
+      p = (p + 1) & t.mask;
+    }
+    atomicMin(&t.minline[p], uint32_t(li));
+    slot_of_line[li] = uint32_t(p);
+  }
+}
+
+// every accepted line checks its name against the representative line of its slot and learns whether it is the
+// first appearance of the name
+__global__ void __launch_bounds__(256)
+    intern_verify_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ line_start, uint64_t n_parse,
+                         LineFields f, InternTable rt, const uint32_t *__restrict__ rslot, InternTable ut,
+                         const uint32_t *__restrict__ uslot, IngestStatus *status) {
+  for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
+       li += uint64_t(gridDim.x) * blockDim.x) {
+    uint8_t fl = f.flags[li];
+    if (!(fl & kFAccepted)) continue;
+    bool     clash = false;
+    uint32_t rrep  = rt.minline[rslot[li]];
+    if (rrep == uint32_t(li)) {
+      fl |= kFFirstRead;
+    } else {
+      uint32_t    n = f.rname_len[li];
+      const char *a = paf + line_start[li] + f.rname_rel[li];
+      const char *b = paf + line_start[rrep] + f.rname_rel[rrep];
+      clash         = f.rname_len[rrep] != n;
+      for (uint32_t i = 0; i < n && !clash; ++i) clash = a[i] != b[i];
+    }
+    uint32_t urep = ut.minline[uslot[li]];
+    if (urep == uint32_t(li)) {
+      fl |= kFFirstUnitig;
+    } else if (!clash) {
+      uint32_t    n = f.uname_len[li];
+      const char *a = paf + line_start[li];
+      const char *b = paf + line_start[urep];
+      clash         = f.uname_len[urep] != n;
+      for (uint32_t i = 0; i < n && !clash; ++i) clash = a[i] != b[i];
+    }
+    if (clash) status->collision = 1;
+    f.flags[li] = fl;
+  }
+}
+
+// the first-appearance lines publish the id of their name (= their rank among first-appearance lines) and fill the
+// vertex / name tables
+__global__ void __launch_bounds__(256)
+    intern_assign_kernel(const uint64_t *__restrict__ line_start, uint64_t n_parse, LineFields f, InternTable rt,
+                         const uint32_t *__restrict__ rslot, const uint32_t *__restrict__ rrank, InternTable ut,
+                         const uint32_t *__restrict__ uslot, const uint32_t *__restrict__ urank,
+                         int32_t *__restrict__ read_nlen, uint32_t *__restrict__ read_line,
+                         uint64_t *__restrict__ read_name_src, uint32_t *__restrict__ read_name_len,
+                         uint64_t *__restrict__ unitig_name_src, uint32_t *__restrict__ unitig_name_len) {
+  for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
+       li += uint64_t(gridDim.x) * blockDim.x) {
+    uint8_t fl = f.flags[li];
+    if (fl & kFFirstRead) {
+      uint32_t id        = rrank[li];
+      rt.id[rslot[li]]   = id;
+      read_nlen[id]      = f.c6[li];
+      read_line[id]      = uint32_t(li);
+      read_name_src[id]  = line_start[li] + f.rname_rel[li];
+      read_name_len[id]  = f.rname_len[li];
+    }
+    if (fl & kFFirstUnitig) {
+      uint32_t id         = urank[li];
+      ut.id[uslot[li]]    = id;
+      unitig_name_src[id] = line_start[li];
+      unitig_name_len[id] = f.uname_len[li];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    gather_names_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ src,
+                        const uint64_t *__restrict__ dst_off, uint64_t n, char *__restrict__ out) {
+  // one warp per name
+  uint64_t w  = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  for (; w < n; w += nw) {
+    uint64_t b = dst_off[w], e = dst_off[w + 1];
+    for (uint64_t i = lane_id(); i < e - b; i += 32) out[b + i] = paf[src[w] + i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4: per (unitig, read) keep the accepted line with the smallest index (MatchMap.cpp:64-73).  The key is exact
+// (two dense ids), so this table needs no verification.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    dedup_insert_kernel(uint64_t n_parse, LineFields f, InternTable rt, const uint32_t *__restrict__ rslot,
+                        InternTable ut, const uint32_t *__restrict__ uslot, InternTable dt,
+                        uint32_t *__restrict__ dslot, uint32_t *__restrict__ rid_of_line,
+                        uint32_t *__restrict__ uid_of_line) {
+  for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
+       li += uint64_t(gridDim.x) * blockDim.x) {
+    if (!(f.flags[li] & kFAccepted)) continue;
+    uint32_t           rid = rt.id[rslot[li]], uid = ut.id[uslot[li]];
+    unsigned long long key = ((unsigned long long)uid << 32 | rid) + 1ull;
+    uint64_t           p   = mix64(key) & dt.mask;
+    for (;;) {
+      unsigned long long prev = atomicCAS(&dt.keys[p], 0ull, key);
+      if (prev == 0ull || prev == key) break;
+      p = (p + 1) & dt.mask;
+    }
+    atomicMin(&dt.minline[p], uint32_t(li));
+    dslot[li]       = uint32_t(p);
+    rid_of_line[li] = rid;
+    uid_of_line[li] = uid;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    dedup_flag_kernel(uint64_t n_parse, uint8_t *__restrict__ flags, InternTable dt,
+                      const uint32_t *__restrict__ dslot) {
+  for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
+       li += uint64_t(gridDim.x) * blockDim.x) {
+    uint8_t fl = flags[li];
+    if ((fl & kFAccepted) && dt.minline[dslot[li]] == uint32_t(li)) flags[li] = fl | kFSurvivor;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K5: compaction of the surviving lines into the packed match records (line order), rRatio included
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    compact_matches_kernel(uint64_t n_parse, LineFields f, const uint32_t *__restrict__ pos,
+                           const uint32_t *__restrict__ rid_of_line, const uint32_t *__restrict__ uid_of_line,
+                           MatchSoA m) {
+  for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
+       li += uint64_t(gridDim.x) * blockDim.x) {
+    uint8_t fl = f.flags[li];
+    if (!(fl & kFSurvivor)) continue;
+    uint32_t o  = pos[li];
+    int      c2 = f.c2[li], ir1 = f.ir1[li], nr0 = f.nr0[li], nr1 = f.nr1[li];
+    m.unitig[o] = uid_of_line[li];
+    m.read[o]   = rid_of_line[li];
+    m.ir0[o]    = c2;
+    m.ir1[o]    = ir1;
+    m.nr0[o]    = nr0;
+    m.nr1[o]    = nr1;
+    m.score[o]  = f.c9[li];
+    m.line[o]   = uint32_t(li);
+    m.flags[o]  = ((fl & kFDir) ? 1 : 0) | ((fl & kFPrim) ? 2 : 0);
+    // BlastFileReader.cpp:118-119 — one IEEE-754 double division, operands exact
+    m.rratio[o] = __ddiv_rn(double(ir1 - c2 + 1), double(nr1 - nr0 + 1));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    check_grouped_kernel(const uint32_t *__restrict__ unitig, uint64_t n, IngestStatus *status) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x + 1; i < n;
+       i += uint64_t(gridDim.x) * blockDim.x)
+    if (unitig[i] < unitig[i - 1]) status->unsorted = 1;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+    gather_kernel(const T *__restrict__ in, const uint32_t *__restrict__ idx, uint64_t n, T *__restrict__ out) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
+    out[i] = in[idx[i]];
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t *out, uint64_t n) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
+    out[i] = uint32_t(i);
+}
+
+// grp_off[u] = first row of unitig u.  Every unitig id owns at least one row (its first accepted line survives the
+// dedup), so boundaries alone define the table; ids without rows (possible for caller-packed records) are filled by
+// running a max-scan backwards on the host-free path below.
+__global__ void __launch_bounds__(256)
+    group_bounds_kernel(const uint32_t *__restrict__ unitig, uint64_t n, uint32_t n_unitigs,
+                        uint32_t *__restrict__ grp_off) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i <= n; i += uint64_t(gridDim.x) * blockDim.x) {
+    uint32_t lo = i == 0 ? 0u : unitig[i - 1] + 1u;       // first id not yet started before row i
+    uint32_t hi = i == n ? n_unitigs : unitig[i];         // ids lo..hi start at row i
+    if (i == 0 || i == n || unitig[i] != unitig[i - 1])
+      for (uint32_t u = lo; u <= hi && u <= n_unitigs; ++u) grp_off[u] = uint32_t(i);
+  }
+}
+
+static uint64_t next_pow2(uint64_t x) {
+  uint64_t p = 1024;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+static InternTable make_table(Arena &arena, cudaStream_t st, uint64_t expect) {
+  InternTable t;
+  uint64_t    cap = next_pow2(expect * 2 + 2);
+  t.keys          = arena.alloc<unsigned long long>(cap);
+  t.minline       = arena.alloc<uint32_t>(cap);
+  t.id            = arena.alloc<uint32_t>(cap);
+  t.mask          = cap - 1;
+  MSGPU_CUDA(cudaMemsetAsync(t.keys, 0, cap * sizeof(unsigned long long), st));
+  MSGPU_CUDA(cudaMemsetAsync(t.minline, 0xff, cap * sizeof(uint32_t), st));
+  return t;
+}
+
+template <class T> static T read_back(cudaStream_t st, const T *d) {
+  T h;
+  MSGPU_CUDA(cudaMemcpyAsync(&h, d, sizeof(T), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaStreamSynchronize(st));
+  return h;
+}
+
+static void build_name_table(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n, const uint64_t *src,
+                             const uint32_t *len, NameTable &out) {
+  out.n        = n;
+  out.name_off = arena.alloc<uint64_t>(n + 1);
+  uint64_t *total = arena.alloc<uint64_t>(1);
+  exclusive_scan<uint64_t>(arena, st, LoadAs<uint32_t, uint64_t>{len}, n, out.name_off, total);
+  MSGPU_CUDA(cudaMemcpyAsync(out.name_off + n, total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+  out.n_bytes = read_back(st, total);
+  out.names   = arena.alloc<char>(out.n_bytes);
+  if (n) {
+    gather_names_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(d_paf, src, out.name_off, n, out.names);
+    MSGPU_LAUNCH_CHECK();
+  }
+}
+
+void build_group_offsets(Arena &arena, cudaStream_t st, const MatchSoA &m, UnitigTable &unitigs) {
+  unitigs.grp_off = arena.alloc<uint32_t>(unitigs.n + 1);
+  group_bounds_kernel<<<grid_for(m.n + 1, 256), 256, 0, st>>>(m.unitig, m.n, uint32_t(unitigs.n), unitigs.grp_off);
+  MSGPU_LAUNCH_CHECK();
+}
+
+void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
+                ReadTable &reads, UnitigTable &unitigs, MatchSoA &m) {
+  reads = ReadTable{};
+  unitigs = UnitigTable{};
+  m = MatchSoA{};
+  *n_lines_out = 0;
+
+  // ---- K1a line index
+  uint64_t     mis      = reinterpret_cast<uintptr_t>(d_paf) & 15u;
+  const uint4 *aligned  = reinterpret_cast<const uint4 *>(d_paf - mis);
+  uint64_t     nv       = mis + n_bytes;
+  uint64_t     n_tiles  = (nv + kNlTile - 1) / kNlTile;
+  uint32_t    *tile_cnt = arena.alloc<uint32_t>(n_tiles + 1);
+  uint32_t    *d_n_nl   = arena.alloc<uint32_t>(1);
+  uint64_t    *d_nlines = arena.alloc<uint64_t>(1);
+  if (n_tiles) {
+    newline_count_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt);
+    MSGPU_LAUNCH_CHECK();
+  }
+  exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{tile_cnt}, n_tiles, tile_cnt, d_n_nl);
+  uint32_t n_newlines = read_back(st, d_n_nl);
+  if (uint64_t(n_newlines) + 2 >= 0xffffffffull) throw BuildError{MSGPU_ERR_LIMIT, "more than 2^32-2 lines in one PAF"};
+  uint64_t *line_start = arena.alloc<uint64_t>(uint64_t(n_newlines) + 2);
+  if (n_tiles) {
+    newline_write_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt, line_start);
+    MSGPU_LAUNCH_CHECK();
+  }
+  line_index_finish_kernel<<<1, 1, 0, st>>>(d_paf, n_bytes, d_n_nl, line_start, d_nlines);
+  MSGPU_LAUNCH_CHECK();
+  uint64_t n_lines = read_back(st, d_nlines);
+  *n_lines_out     = n_lines;
+  // BlastFileReader::read(): lines 0 .. lineCount-2 (BlastFileReader.cpp:76)
+  uint64_t n_parse = n_lines ? n_lines - 1 : 0;
+
+  IngestStatus *d_status = arena.alloc<IngestStatus>(1);
+  IngestStatus  h_status{~0ull, 0, 0, 0, 0};
+
+  LineFields f;
+  f.c2        = arena.alloc<int32_t>(n_parse);
+  f.ir1       = arena.alloc<int32_t>(n_parse);
+  f.c6        = arena.alloc<int32_t>(n_parse);
+  f.nr0       = arena.alloc<int32_t>(n_parse);
+  f.nr1       = arena.alloc<int32_t>(n_parse);
+  f.c9        = arena.alloc<int32_t>(n_parse);
+  f.rname_rel = arena.alloc<uint32_t>(n_parse);
+  f.rname_len = arena.alloc<uint16_t>(n_parse);
+  f.uname_len = arena.alloc<uint16_t>(n_parse);
+  f.rhash     = arena.alloc<uint64_t>(n_parse);
+  f.uhash     = arena.alloc<uint64_t>(n_parse);
+  f.flags     = arena.alloc<uint8_t>(n_parse);
+  uint32_t *rslot = arena.alloc<uint32_t>(n_parse), *uslot = arena.alloc<uint32_t>(n_parse);
+  uint32_t *dslot = arena.alloc<uint32_t>(n_parse);
+  uint32_t *rid_of_line = arena.alloc<uint32_t>(n_parse), *uid_of_line = arena.alloc<uint32_t>(n_parse);
+  uint32_t *rank_a = arena.alloc<uint32_t>(n_parse), *rank_b = arena.alloc<uint32_t>(n_parse);
+  uint32_t *d_cnt = arena.alloc<uint32_t>(4);
+
+  const int grid_lines = grid_for(n_parse, 256);
+  uint32_t  n_reads = 0, n_unitigs = 0;
+  InternTable rt{}, ut{};
+
+  for (int attempt = 0;; ++attempt) {
+    if (attempt == 4) throw BuildError{MSGPU_ERR_INTERNAL, "name hash collisions persisted over 4 seeds"};
+    MSGPU_CUDA(cudaMemcpyAsync(d_status, &h_status, sizeof(h_status), cudaMemcpyHostToDevice, st));
+    if (n_parse) {
+      parse_lines_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, n_parse,
+                                                     0x243f6a8885a308d3ull * uint64_t(attempt + 1), f, d_status);
+      MSGPU_LAUNCH_CHECK();
+    }
+    IngestStatus s1 = read_back(st, d_status);
+    if (s1.first_bad_line != ~0ull)
+      throw BuildError{MSGPU_ERR_INVALID_PAF, "Invalid BLAST file. (line " + std::to_string(s1.first_bad_line) + ")"};
+    uint64_t n_acc = s1.n_accepted;
+
+    // ---- K3 interning
+    rt = make_table(arena, st, n_acc);
+    ut = make_table(arena, st, n_acc);
+    if (n_parse) {
+      intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.rhash, n_parse, rt, rslot);
+      MSGPU_LAUNCH_CHECK();
+      intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.uhash, n_parse, ut, uslot);
+      MSGPU_LAUNCH_CHECK();
+      intern_verify_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, n_parse, f, rt, rslot, ut, uslot, d_status);
+      MSGPU_LAUNCH_CHECK();
+    }
+    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstRead}, n_parse, rank_a, d_cnt + 0);
+    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstUnitig}, n_parse, rank_b, d_cnt + 1);
+    IngestStatus s2 = read_back(st, d_status);
+    if (s2.collision) continue; // astronomically rare: two different names with the same 64-bit hash
+    n_reads   = read_back(st, d_cnt + 0);
+    n_unitigs = read_back(st, d_cnt + 1);
+    break;
+  }
+
+  reads.nlen = arena.alloc<int32_t>(n_reads);
+  reads.line = arena.alloc<uint32_t>(n_reads);
+  uint64_t *rsrc = arena.alloc<uint64_t>(n_reads), *usrc = arena.alloc<uint64_t>(n_unitigs);
+  uint32_t *rlen = arena.alloc<uint32_t>(n_reads), *ulen = arena.alloc<uint32_t>(n_unitigs);
+  if (n_parse) {
+    intern_assign_kernel<<<grid_lines, 256, 0, st>>>(line_start, n_parse, f, rt, rslot, rank_a, ut, uslot, rank_b,
+                                                     reads.nlen, reads.line, rsrc, rlen, usrc, ulen);
+    MSGPU_LAUNCH_CHECK();
+  }
+  build_name_table(arena, st, d_paf, n_reads, rsrc, rlen, reads);
+  build_name_table(arena, st, d_paf, n_unitigs, usrc, ulen, unitigs);
+
+  // ---- K4 dedup
+  uint64_t    n_acc = read_back(st, d_status).n_accepted;
+  InternTable dt    = make_table(arena, st, n_acc);
+  if (n_parse) {
+    dedup_insert_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line,
+                                                    uid_of_line);
+    MSGPU_LAUNCH_CHECK();
+    dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f.flags, dt, dslot);
+    MSGPU_LAUNCH_CHECK();
+  }
+
+  // ---- K5 compaction (+ grouping sort when the PAF is not grouped by unitig)
+  exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFSurvivor}, n_parse, rank_a, d_cnt + 2);
+  uint64_t M = read_back(st, d_cnt + 2);
+  auto alloc_soa = [&](MatchSoA &s) {
+    s.n      = M;
+    s.unitig = arena.alloc<uint32_t>(M);
+    s.read   = arena.alloc<uint32_t>(M);
+    s.ir0    = arena.alloc<int32_t>(M);
+    s.ir1    = arena.alloc<int32_t>(M);
+    s.nr0    = arena.alloc<int32_t>(M);
+    s.nr1    = arena.alloc<int32_t>(M);
+    s.score  = arena.alloc<int32_t>(M);
+    s.line   = arena.alloc<uint32_t>(M);
+    s.flags  = arena.alloc<uint8_t>(M);
+    s.rratio = arena.alloc<double>(M);
+  };
+  alloc_soa(m);
+  if (n_parse) {
+    compact_matches_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f, rank_a, rid_of_line, uid_of_line, m);
+    MSGPU_LAUNCH_CHECK();
+  }
+  if (M > 1) {
+    check_grouped_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, M, d_status);
+    MSGPU_LAUNCH_CHECK();
+  }
+  if (read_back(st, d_status).unsorted) {
+    // stable sort by unitig id keeps the line order inside a unitig (rows are in line order now)
+    uint32_t *keys = arena.alloc<uint32_t>(M), *keys2 = arena.alloc<uint32_t>(M);
+    uint32_t *idx = arena.alloc<uint32_t>(M), *idx2 = arena.alloc<uint32_t>(M);
+    int       g = grid_for(M, 256);
+    MSGPU_CUDA(cudaMemcpyAsync(keys, m.unitig, M * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    iota_kernel<<<g, 256, 0, st>>>(idx, M);
+    MSGPU_LAUNCH_CHECK();
+    radix_sort_pairs<uint32_t, uint32_t>(arena, st, keys, idx, keys2, idx2, M, {0, bits_for(n_unitigs)});
+    MatchSoA s;
+    alloc_soa(s);
+    gather_kernel<<<g, 256, 0, st>>>(m.unitig, idx, M, s.unitig);
+    gather_kernel<<<g, 256, 0, st>>>(m.read, idx, M, s.read);
+    gather_kernel<<<g, 256, 0, st>>>(m.ir0, idx, M, s.ir0);
+    gather_kernel<<<g, 256, 0, st>>>(m.ir1, idx, M, s.ir1);
+    gather_kernel<<<g, 256, 0, st>>>(m.nr0, idx, M, s.nr0);
+    gather_kernel<<<g, 256, 0, st>>>(m.nr1, idx, M, s.nr1);
+    gather_kernel<<<g, 256, 0, st>>>(m.score, idx, M, s.score);
+    gather_kernel<<<g, 256, 0, st>>>(m.line, idx, M, s.line);
+    gather_kernel<<<g, 256, 0, st>>>(m.flags, idx, M, s.flags);
+    gather_kernel<<<g, 256, 0, st>>>(m.rratio, idx, M, s.rratio);
+    MSGPU_LAUNCH_CHECK();
+    m = s;
+  }
+  build_group_offsets(arena, st, m, unitigs);
+}
+
+} // namespace msgpu

@@ -1,0 +1,65 @@
+// internal.h — structures shared by the translation units of libmsgpu (not part of the ABI).
+#pragma once
+
+#include <cstdint>
+#include <string>
+
+#include "common.cuh"
+
+namespace msgpu {
+
+// VertexMatch rows (MatchMap.h:51-59) packed as structure-of-arrays, grouped by unitig, by line inside a unitig
+struct MatchSoA {
+  uint64_t  n      = 0;
+  uint32_t *unitig = nullptr, *read = nullptr;
+  int32_t  *ir0 = nullptr, *ir1 = nullptr, *nr0 = nullptr, *nr1 = nullptr, *score = nullptr;
+  uint32_t *line   = nullptr;
+  uint8_t  *flags  = nullptr; // bit0 direction, bit1 isPrimary
+  double   *rratio = nullptr;
+};
+
+struct NameTable {
+  uint64_t  n        = 0;
+  uint64_t *name_off = nullptr; // n + 1
+  char     *names    = nullptr;
+  uint64_t  n_bytes  = 0;
+};
+
+struct ReadTable : NameTable {
+  int32_t  *nlen = nullptr;
+  uint32_t *line = nullptr;
+};
+
+struct UnitigTable : NameTable {
+  uint32_t *grp_off = nullptr; // n + 1 : matches of unitig u are rows [grp_off[u], grp_off[u+1])
+};
+
+struct EdgeTables {
+  uint64_t  n_pairs = 0;
+  uint64_t  n_edges = 0;
+  uint32_t *first = nullptr, *second = nullptr;
+  uint64_t *em_begin = nullptr; // n_edges + 1
+  uint64_t  n_em     = 0;
+  uint32_t *em_unitig = nullptr;
+  int32_t  *em_ov0 = nullptr, *em_ov1 = nullptr;
+  double   *em_score = nullptr;
+  uint32_t *em_line  = nullptr;
+  uint8_t  *em_flags = nullptr;
+};
+
+struct BuildError {
+  int         status;
+  std::string message;
+};
+
+// ingest.cu : PAF text in HBM -> read table, unitig table (+ group offsets), match SoA   (K1-K5)
+void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
+                ReadTable &reads, UnitigTable &unitigs, MatchSoA &matches);
+// group offsets for records that arrive already packed (msgpu_build_from_records)
+void build_group_offsets(Arena &arena, cudaStream_t st, const MatchSoA &matches, UnitigTable &unitigs);
+
+// pair_sort.cu : per-unitig pair enumeration + global radix sort + run-length edges   (K6, K7; sort-based variant)
+void run_pairing_sorted(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs,
+                        uint64_t n_reads, EdgeTables &edges, cudaEvent_t ev_pair_done);
+
+} // namespace msgpu

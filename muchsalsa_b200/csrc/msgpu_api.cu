@@ -1,0 +1,491 @@
+// msgpu_api.cu — the C ABI declared in include/msgpu.h: context, construction entry points, result marshalling.
+//
+// The host side of this path is C++ like the reference's; no exception crosses the boundary (the reference reports
+// errors as std::runtime_error — "Can't open blast file." BlastFileAccessor.cpp:44, "Invalid BLAST file."
+// BlastFileReader.cpp:98 — which become status codes + msgpu_last_error()).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/msgpu.h"
+#include "internal.h"
+#include "seq.h"
+
+using namespace msgpu;
+
+namespace {
+
+struct PinnedBuf {
+  void  *p   = nullptr;
+  size_t cap = 0;
+  void  *get(size_t bytes) {
+    if (bytes > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      size_t want = bytes + bytes / 4 + 4096;
+      MSGPU_CUDA(cudaMallocHost(&p, want));
+      cap = want;
+    }
+    return p;
+  }
+  ~PinnedBuf() {
+    if (p) cudaFreeHost(p);
+  }
+};
+
+} // namespace
+
+struct msgpu_ctx {
+  int          device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  Arena        arena;       // per-build device memory
+  Arena        input_arena; // staged PAF text
+  std::string  error;
+
+  bool          have_result = false;
+  uint64_t      n_lines     = 0;
+  ReadTable     reads;
+  UnitigTable   unitigs;
+  MatchSoA      matches;
+  EdgeTables    edges;
+  msgpu_timings timings{};
+  cudaEvent_t   ev[6]{};
+
+  PinnedBuf    host_result; // one pinned slab holding every host table
+  PinnedBuf    staging;     // pinned staging for pageable PAF input
+  bool         host_valid = false;
+  msgpu_tables host_tables{};
+
+  SeqStore *seq = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <class Fn> int guarded(msgpu_ctx *ctx, Fn &&fn) {
+  if (!ctx) return MSGPU_ERR_INVALID_ARG;
+  try {
+    DeviceGuard g(ctx->device);
+    fn();
+    ctx->error.clear();
+    return MSGPU_OK;
+  } catch (BuildError const &e) {
+    ctx->error = e.message;
+    return e.status;
+  } catch (CudaError const &e) {
+    ctx->error = e.what();
+    return MSGPU_ERR_CUDA;
+  } catch (std::bad_alloc const &) {
+    ctx->error = "out of host memory";
+    return MSGPU_ERR_NOMEM;
+  } catch (std::exception const &e) {
+    ctx->error = e.what();
+    return MSGPU_ERR_INTERNAL;
+  }
+}
+
+float elapsed(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+// device part of a build: PAF text in HBM -> all tables in HBM
+void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes) {
+  cudaStream_t st  = ctx->stream;
+  ctx->have_result = false;
+  ctx->host_valid  = false;
+  ctx->arena.reset();
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
+  run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches);
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
+  run_pairing_sorted(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3]);
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
+  MSGPU_CUDA(cudaStreamSynchronize(st));
+  ctx->timings.ingest_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  ctx->timings.pair_ms   = elapsed(ctx->ev[2], ctx->ev[3]);
+  ctx->timings.merge_ms  = elapsed(ctx->ev[3], ctx->ev[4]);
+  ctx->timings.total_ms  = elapsed(ctx->ev[1], ctx->ev[4]);
+  ctx->timings.h2d_ms = ctx->timings.d2h_ms = 0.f;
+  ctx->have_result = true;
+}
+
+void build_host(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes) {
+  cudaStream_t st = ctx->stream;
+  ctx->input_arena.reset();
+  char *d_paf = ctx->input_arena.alloc<char>(n_bytes + 16);
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[0], st));
+  if (n_bytes) MSGPU_CUDA(cudaMemcpyAsync(d_paf, host_paf, n_bytes, cudaMemcpyHostToDevice, st));
+  build_device(ctx, d_paf, n_bytes);
+  ctx->timings.h2d_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+  ctx->timings.total_ms += ctx->timings.h2d_ms;
+}
+
+template <class T> size_t slab_reserve(size_t &off, size_t n) {
+  size_t at = (off + 63) & ~size_t(63);
+  off       = at + n * sizeof(T);
+  return at;
+}
+
+} // namespace
+
+extern "C" {
+
+int msgpu_abi_version(void) { return MSGPU_ABI_VERSION; }
+
+int msgpu_create(int cuda_device, msgpu_ctx **out_ctx) {
+  if (!out_ctx) return MSGPU_ERR_INVALID_ARG;
+  *out_ctx = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || cuda_device < 0 || cuda_device >= n_dev) {
+    // No CPU fallback exists on purpose: without a CUDA device this library cannot do anything.
+    return MSGPU_ERR_CUDA;
+  }
+  msgpu_ctx *ctx = new (std::nothrow) msgpu_ctx;
+  if (!ctx) return MSGPU_ERR_NOMEM;
+  ctx->device = cuda_device;
+  int rc      = guarded(ctx, [&] {
+    MSGPU_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (auto &e : ctx->ev) MSGPU_CUDA(cudaEventCreate(&e));
+  });
+  if (rc != MSGPU_OK) {
+    delete ctx;
+    return rc;
+  }
+  *out_ctx = ctx;
+  return MSGPU_OK;
+}
+
+void msgpu_destroy(msgpu_ctx *ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  seq_destroy(ctx->seq);
+  for (auto &e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  ctx->arena.release();
+  ctx->input_arena.release();
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+const char *msgpu_last_error(const msgpu_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int msgpu_set_stream(msgpu_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return MSGPU_ERR_INVALID_ARG;
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return MSGPU_OK;
+}
+
+int msgpu_build_from_paf_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes) {
+  return guarded(ctx, [&] {
+    if (!dev_paf && n_bytes) throw BuildError{MSGPU_ERR_INVALID_ARG, "null PAF buffer"};
+    build_device(ctx, dev_paf, n_bytes);
+  });
+}
+
+int msgpu_build_from_paf_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes) {
+  return guarded(ctx, [&] {
+    if (!host_paf && n_bytes) throw BuildError{MSGPU_ERR_INVALID_ARG, "null PAF buffer"};
+    build_host(ctx, host_paf, n_bytes);
+  });
+}
+
+int msgpu_build_from_paf(msgpu_ctx *ctx, const char *paf_path) {
+  return guarded(ctx, [&] {
+    if (!paf_path) throw BuildError{MSGPU_ERR_INVALID_ARG, "null path"};
+    int fd = ::open(paf_path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) throw BuildError{MSGPU_ERR_IO, "Can't open blast file."}; // BlastFileAccessor.cpp:44
+    struct stat sb {};
+    if (fstat(fd, &sb) != 0) {
+      ::close(fd);
+      throw BuildError{MSGPU_ERR_IO, "Can't open blast file."};
+    }
+    size_t n   = size_t(sb.st_size);
+    void  *map = n ? mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    ::close(fd);
+    if (n && map == MAP_FAILED) throw BuildError{MSGPU_ERR_IO, "Can't open blast file."};
+    try {
+      build_host(ctx, static_cast<const char *>(map), n);
+    } catch (...) {
+      if (n) munmap(map, n);
+      throw;
+    }
+    if (n) munmap(map, n);
+  });
+}
+
+int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t n_reads, uint32_t n_unitigs) {
+  return guarded(ctx, [&] {
+    if (!r) throw BuildError{MSGPU_ERR_INVALID_ARG, "null records"};
+    cudaStream_t st  = ctx->stream;
+    ctx->have_result = false;
+    ctx->host_valid  = false;
+    ctx->arena.reset();
+    ctx->reads   = ReadTable{};
+    ctx->unitigs = UnitigTable{};
+    ctx->reads.n = n_reads;
+    ctx->unitigs.n = n_unitigs;
+    ctx->n_lines = 0;
+    MatchSoA &m = ctx->matches;
+    m = MatchSoA{};
+    m.n      = r->n;
+    m.unitig = const_cast<uint32_t *>(r->unitig);
+    m.read   = const_cast<uint32_t *>(r->read);
+    m.ir0    = const_cast<int32_t *>(r->ir0);
+    m.ir1    = const_cast<int32_t *>(r->ir1);
+    m.nr0    = const_cast<int32_t *>(r->nr0);
+    m.nr1    = const_cast<int32_t *>(r->nr1);
+    m.score  = const_cast<int32_t *>(r->score);
+    m.line   = const_cast<uint32_t *>(r->line);
+    m.flags  = const_cast<uint8_t *>(r->flags);
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
+    build_group_offsets(ctx->arena, st, m, ctx->unitigs);
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
+    run_pairing_sorted(ctx->arena, st, m, ctx->unitigs, n_reads, ctx->edges, ctx->ev[3]);
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
+    MSGPU_CUDA(cudaStreamSynchronize(st));
+    ctx->timings           = msgpu_timings{};
+    ctx->timings.ingest_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+    ctx->timings.pair_ms   = elapsed(ctx->ev[2], ctx->ev[3]);
+    ctx->timings.merge_ms  = elapsed(ctx->ev[3], ctx->ev[4]);
+    ctx->timings.total_ms  = elapsed(ctx->ev[1], ctx->ev[4]);
+    ctx->have_result       = true;
+  });
+}
+
+int msgpu_result_counts(const msgpu_ctx *ctx, msgpu_counts *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->have_result) return MSGPU_ERR_NO_RESULT;
+  out->n_lines        = ctx->n_lines;
+  out->n_reads        = ctx->reads.n;
+  out->n_unitigs      = ctx->unitigs.n;
+  out->n_matches      = ctx->matches.n;
+  out->n_pairs        = ctx->edges.n_pairs;
+  out->n_edges        = ctx->edges.n_edges;
+  out->n_edge_matches = ctx->edges.n_em;
+  return MSGPU_OK;
+}
+
+int msgpu_result_device(const msgpu_ctx *ctx, msgpu_tables *t) {
+  if (!ctx || !t) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->have_result) return MSGPU_ERR_NO_RESULT;
+  std::memset(t, 0, sizeof(*t));
+  t->read_nlen       = ctx->reads.nlen;
+  t->read_line       = ctx->reads.line;
+  t->read_name_off   = ctx->reads.name_off;
+  t->read_names      = ctx->reads.names;
+  t->unitig_name_off = ctx->unitigs.name_off;
+  t->unitig_names    = ctx->unitigs.names;
+  t->m_unitig        = ctx->matches.unitig;
+  t->m_read          = ctx->matches.read;
+  t->m_nr0           = ctx->matches.nr0;
+  t->m_nr1           = ctx->matches.nr1;
+  t->m_ir0           = ctx->matches.ir0;
+  t->m_ir1           = ctx->matches.ir1;
+  t->m_rratio        = ctx->matches.rratio;
+  t->m_score         = ctx->matches.score;
+  t->m_line          = ctx->matches.line;
+  t->m_flags         = ctx->matches.flags;
+  t->edge_first      = ctx->edges.first;
+  t->edge_second     = ctx->edges.second;
+  t->edge_em_begin   = ctx->edges.em_begin;
+  t->em_unitig       = ctx->edges.em_unitig;
+  t->em_ov0          = ctx->edges.em_ov0;
+  t->em_ov1          = ctx->edges.em_ov1;
+  t->em_score        = ctx->edges.em_score;
+  t->em_line         = ctx->edges.em_line;
+  t->em_flags        = ctx->edges.em_flags;
+  return MSGPU_OK;
+}
+
+int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->have_result) return MSGPU_ERR_NO_RESULT;
+  if (ctx->host_valid) {
+    *out = ctx->host_tables;
+    return MSGPU_OK;
+  }
+  return guarded(ctx, [&] {
+    cudaStream_t st = ctx->stream;
+    msgpu_tables d;
+    msgpu_result_device(ctx, &d);
+    const uint64_t R = ctx->reads.n, U = ctx->unitigs.n, M = ctx->matches.n, E = ctx->edges.n_edges,
+                   EM = ctx->edges.n_em;
+    const bool have_names = ctx->reads.name_off != nullptr;
+    // lay every table out in one pinned slab
+    size_t off = 0;
+    struct Copy {
+      const void *src;
+      size_t      at, bytes;
+      const void **dst;
+    };
+    std::vector<Copy> copies;
+    msgpu_tables     &h = ctx->host_tables;
+    std::memset(&h, 0, sizeof(h));
+    auto add = [&](auto const *src, size_t n, auto const **dst) {
+      using T   = std::remove_cv_t<std::remove_pointer_t<decltype(src)>>;
+      size_t at = slab_reserve<T>(off, n);
+      copies.push_back(Copy{src, at, n * sizeof(T), reinterpret_cast<const void **>(dst)});
+    };
+    if (have_names) {
+      add(d.read_nlen, R, &h.read_nlen);
+      add(d.read_line, R, &h.read_line);
+      add(d.read_name_off, R + 1, &h.read_name_off);
+      add(d.read_names, ctx->reads.n_bytes, &h.read_names);
+      add(d.unitig_name_off, U + 1, &h.unitig_name_off);
+      add(d.unitig_names, ctx->unitigs.n_bytes, &h.unitig_names);
+    }
+    add(d.m_unitig, M, &h.m_unitig);
+    add(d.m_read, M, &h.m_read);
+    add(d.m_nr0, M, &h.m_nr0);
+    add(d.m_nr1, M, &h.m_nr1);
+    add(d.m_ir0, M, &h.m_ir0);
+    add(d.m_ir1, M, &h.m_ir1);
+    if (d.m_rratio) add(d.m_rratio, M, &h.m_rratio);
+    add(d.m_score, M, &h.m_score);
+    add(d.m_line, M, &h.m_line);
+    add(d.m_flags, M, &h.m_flags);
+    add(d.edge_first, E, &h.edge_first);
+    add(d.edge_second, E, &h.edge_second);
+    add(d.edge_em_begin, E + 1, &h.edge_em_begin);
+    add(d.em_unitig, EM, &h.em_unitig);
+    add(d.em_ov0, EM, &h.em_ov0);
+    add(d.em_ov1, EM, &h.em_ov1);
+    add(d.em_score, EM, &h.em_score);
+    add(d.em_line, EM, &h.em_line);
+    add(d.em_flags, EM, &h.em_flags);
+    char *slab = static_cast<char *>(ctx->host_result.get(off + 64));
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
+    for (auto &c : copies) {
+      *c.dst = slab + c.at;
+      if (c.bytes) MSGPU_CUDA(cudaMemcpyAsync(slab + c.at, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
+    }
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[5], st));
+    MSGPU_CUDA(cudaStreamSynchronize(st));
+    ctx->timings.d2h_ms = elapsed(ctx->ev[4], ctx->ev[5]);
+    ctx->timings.total_ms += ctx->timings.d2h_ms;
+    ctx->host_valid = true;
+    *out            = h;
+  });
+}
+
+int msgpu_result_timings(const msgpu_ctx *ctx, msgpu_timings *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->have_result) return MSGPU_ERR_NO_RESULT;
+  *out = ctx->timings;
+  return MSGPU_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// sequence entry points: thin forwarding to seq.cu (the store lives in the context)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+// names of the last build, in id order, so the sequence index continues the construction's numbering
+// (the reference hands the same Registry objects to SequenceAccessor, src/main.cpp:161-162)
+void prime_names(msgpu_ctx *ctx, std::vector<std::string> &reads, std::vector<std::string> &unitigs) {
+  if (!ctx->have_result || !ctx->reads.name_off) return;
+  msgpu_tables h;
+  int          rc = msgpu_result_host(ctx, &h);
+  if (rc != MSGPU_OK) throw BuildError{rc, ctx->error};
+  for (uint64_t i = 0; i < ctx->reads.n; ++i)
+    reads.emplace_back(h.read_names + h.read_name_off[i], h.read_names + h.read_name_off[i + 1]);
+  for (uint64_t i = 0; i < ctx->unitigs.n; ++i)
+    unitigs.emplace_back(h.unitig_names + h.unitig_name_off[i], h.unitig_names + h.unitig_name_off[i + 1]);
+}
+
+} // namespace
+
+extern "C" {
+
+int msgpu_seq_load_buffers(msgpu_ctx *ctx, const char *unitigs_fasta, size_t n_u, const char *nanopore, size_t n_n,
+                           int nanopore_is_fastq) {
+  return guarded(ctx, [&] {
+    std::vector<std::string> rn, un;
+    prime_names(ctx, rn, un);
+    seq_destroy(ctx->seq);
+    ctx->seq = nullptr;
+    ctx->seq = seq_create(ctx->stream, unitigs_fasta, n_u, nanopore, n_n, nanopore_is_fastq != 0, rn, un);
+  });
+}
+
+int msgpu_seq_load(msgpu_ctx *ctx, const char *unitigs_path, const char *nanopore_path) {
+  return guarded(ctx, [&] {
+    if (!unitigs_path || !nanopore_path) throw BuildError{MSGPU_ERR_INVALID_ARG, "null path"};
+    MappedFile fu(unitigs_path), fn(nanopore_path);
+    if (!fu.ok || !fn.ok) throw BuildError{MSGPU_ERR_IO, "Can't open sequence file(s)."}; // SequenceAccessor.cpp:110
+    std::vector<std::string> rn, un;
+    prime_names(ctx, rn, un);
+    seq_destroy(ctx->seq);
+    ctx->seq = nullptr;
+    ctx->seq = seq_create(ctx->stream, fu.data, fu.size, fn.data, fn.size, path_is_fastq(nanopore_path), rn, un);
+  });
+}
+
+int msgpu_seq_id(const msgpu_ctx *ctx, uint32_t which, const char *name, uint32_t *out_id) {
+  if (!ctx || !name || !out_id || which > 1) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->seq) return MSGPU_ERR_NO_RESULT;
+  return seq_lookup(ctx->seq, which, name, out_id) ? MSGPU_OK : MSGPU_ERR_OUT_OF_RANGE;
+}
+
+int msgpu_seq_batch_bound(const msgpu_ctx *ctx, const msgpu_seq_req *reqs, size_t n, uint64_t *out_bytes) {
+  if (!ctx || (!reqs && n) || !out_bytes) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->seq) return MSGPU_ERR_NO_RESULT;
+  *out_bytes = seq_batch_bound(ctx->seq, reqs, n);
+  return MSGPU_OK;
+}
+
+int msgpu_seq_fetch_batch(msgpu_ctx *ctx, const msgpu_seq_req *reqs, size_t n, char *out, uint64_t cap,
+                          uint64_t *out_off, uint8_t *status) {
+  if (!ctx || (!reqs && n) || !out_off || !status || (!out && cap)) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->seq) return MSGPU_ERR_NO_RESULT;
+  // thread-safe: the store is immutable after load and every call uses its own stream + scratch
+  try {
+    DeviceGuard g(ctx->device);
+    seq_fetch_host(ctx->seq, reqs, n, out, cap, out_off, status);
+    return MSGPU_OK;
+  } catch (BuildError const &e) {
+    return e.status;
+  } catch (std::exception const &) {
+    return MSGPU_ERR_CUDA;
+  }
+}
+
+int msgpu_seq_fetch_batch_device(msgpu_ctx *ctx, const msgpu_seq_req *dev_reqs, size_t n, char *dev_out, uint64_t cap,
+                                 uint64_t *dev_out_off, uint8_t *dev_status) {
+  return guarded(ctx, [&] {
+    if (!ctx->seq) throw BuildError{MSGPU_ERR_NO_RESULT, "no sequence store loaded"};
+    seq_fetch_device(ctx->seq, ctx->stream, dev_reqs, n, dev_out, cap, dev_out_off, dev_status);
+  });
+}
+
+int msgpu_slice_revcomp_device(msgpu_ctx *ctx, const char *dev_text, const uint64_t *dev_text_off,
+                               const int32_t *dev_left, const int32_t *dev_right, const uint8_t *dev_revcomp, size_t n,
+                               char *dev_out, uint64_t cap, uint64_t *dev_out_off, uint8_t *dev_status) {
+  return guarded(ctx, [&] {
+    slice_revcomp_device(ctx->stream, dev_text, dev_text_off, dev_left, dev_right, dev_revcomp, n, dev_out, cap,
+                         dev_out_off, dev_status);
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,103 @@
+// scan.cuh — device-wide exclusive prefix sum (reduce / scan-partials / down-sweep), hand-written.
+//
+// The arrays scanned on this path are per-line, per-match or per-unitig: one to two orders of magnitude smaller than
+// the edge-match stream, so the three-kernel form (2 reads + 1 write of the input) is used instead of a single-pass
+// look-back scan.  Input values come from a functor so flags packed in bytes / derived counts need no staging array.
+#pragma once
+
+#include "common.cuh"
+
+namespace msgpu {
+
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8; // contiguous items per thread
+constexpr int kScanTile  = kScanBlock * kScanItems;
+
+template <class T, class InFn>
+__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(InFn in, uint64_t n, T *__restrict__ partials) {
+  __shared__ T sm[33];
+  uint64_t     base = uint64_t(blockIdx.x) * kScanTile + uint64_t(threadIdx.x) * kScanItems;
+  T            s    = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    uint64_t i = base + j;
+    if (i < n) s += in(i);
+  }
+  T total;
+  block_exclusive_scan<T>(s, sm, &total);
+  if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+// one block: exclusive scan of the per-tile sums in place; writes the grand total
+template <class T>
+__global__ void __launch_bounds__(1024) scan_partials_kernel(T *__restrict__ partials, uint64_t n_tiles,
+                                                             T *__restrict__ total_out) {
+  __shared__ T sm[33];
+  T            carry = 0;
+  for (uint64_t start = 0; start < n_tiles; start += blockDim.x) {
+    uint64_t i = start + threadIdx.x;
+    T        v = i < n_tiles ? partials[i] : T(0);
+    T        total;
+    T        ex = block_exclusive_scan<T>(v, sm, &total);
+    if (i < n_tiles) partials[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+template <class T, class InFn>
+__global__ void __launch_bounds__(kScanBlock)
+    scan_downsweep_kernel(InFn in, uint64_t n, const T *__restrict__ partials, T *out /* may alias the input */) {
+  __shared__ T sm[33];
+  uint64_t     base = uint64_t(blockIdx.x) * kScanTile + uint64_t(threadIdx.x) * kScanItems;
+  T            v[kScanItems];
+  T            s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    uint64_t i = base + j;
+    v[j]       = i < n ? in(i) : T(0);
+    s += v[j];
+  }
+  T total;
+  T ex = block_exclusive_scan<T>(s, sm, &total) + partials[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    uint64_t i = base + j;
+    if (i < n) out[i] = ex;
+    ex += v[j];
+  }
+}
+
+// out[i] = sum_{j<i} in(j) for i < n; *total_out (device) = sum of all.  `out` may be null (total only).
+// Scratch comes from the arena.  n == 0 is allowed (total = 0).
+template <class T, class InFn>
+void exclusive_scan(Arena &arena, cudaStream_t st, InFn in, uint64_t n, T *out, T *total_out) {
+  if (n == 0) {
+    if (total_out) MSGPU_CUDA(cudaMemsetAsync(total_out, 0, sizeof(T), st));
+    return;
+  }
+  uint64_t n_tiles  = (n + kScanTile - 1) / kScanTile;
+  T       *partials = arena.alloc<T>(n_tiles);
+  scan_reduce_kernel<T, InFn><<<(unsigned)n_tiles, kScanBlock, 0, st>>>(in, n, partials);
+  MSGPU_LAUNCH_CHECK();
+  scan_partials_kernel<T><<<1, 1024, 0, st>>>(partials, n_tiles, total_out);
+  MSGPU_LAUNCH_CHECK();
+  if (out) {
+    scan_downsweep_kernel<T, InFn><<<(unsigned)n_tiles, kScanBlock, 0, st>>>(in, n, partials, out);
+    MSGPU_LAUNCH_CHECK();
+  }
+}
+
+// common input functors
+template <class S, class T> struct LoadAs {
+  const S *p;
+  __device__ T operator()(uint64_t i) const { return T(p[i]); }
+};
+// 1 iff (flags[i] & mask) == mask
+template <class T> struct FlagBit {
+  const uint8_t *p;
+  uint8_t        mask;
+  __device__ T operator()(uint64_t i) const { return T((p[i] & mask) == mask); }
+};
+
+} // namespace msgpu

@@ -1,0 +1,100 @@
+"""GPU parity tests: the CUDA construction path, called through the C ABI, against the oracle on the same inputs
+(bit-exact, doubles compared as bit patterns) and against the golden vectors recorded from the reference."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+import util
+from muchsalsa_b200 import synth
+from oracle.pyoracle import tables_digest, tables_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(builder, oracle, paf):
+    got = util.gpu_to_tables(builder.build_from_buffer(paf).result())
+    want = oracle.build(paf)
+    assert tables_equal(got, want) == []
+    return got
+
+
+@pytest.mark.parametrize("name", sorted(util.edge_case_pafs()))
+def test_edge_cases_vs_oracle(builder, oracle, name):
+    got = _same(builder, oracle, util.edge_case_pafs()[name])
+    if name == "kat8":
+        assert got.em["score"].tolist() == [3800.0, 573.33333333333326, 1670.0, 3215.0]
+
+
+@pytest.mark.parametrize("paf", [b"", b"\n", util.paf_line("u", 900, 0, 800, "+", "r", 1000, 0, 800, 700)])
+def test_empty_inputs(builder, paf):
+    c = builder.build_from_buffer(paf).counts()
+    assert (c["n_reads"], c["n_matches"], c["n_edges"], c["n_edge_matches"]) == (0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("name", sorted(util.invalid_pafs()))
+def test_invalid_paf_is_an_error(builder, name):
+    from muchsalsa_b200.construct import MsGpuError
+    with pytest.raises(MsGpuError) as e:
+        builder.build_from_buffer(util.invalid_pafs()[name])
+    assert e.value.status == 4 and "Invalid BLAST file." in e.value.message
+
+
+@pytest.mark.parametrize("name", ["small", "small_shuffled", "ecoli", "ecoli_shuffled"])
+def test_synthetic_vs_oracle_and_reference_digest(builder, oracle, name):
+    cfg = dataclasses.replace(synth.CONFIGS[name.split("_")[0]], shuffle_groups=name.endswith("_shuffled"))
+    paf = synth.generate_paf(cfg)
+    got = _same(builder, oracle, paf)
+    g = util.load_golden("digests.json")[name]
+    assert got.counts == g["counts"] and tables_digest(got) == g["digest"]  # recorded from the reference itself
+
+
+def test_unaligned_device_buffer_and_file_entry(builder, oracle, tmp_path):
+    """The three entry points agree: file path, host buffer, device buffer at an odd address."""
+    import torch
+    paf = synth.generate_paf("small")
+    want = oracle.build(paf)
+    p = tmp_path / "small.paf"
+    p.write_bytes(paf)
+    assert tables_equal(util.gpu_to_tables(builder.build_from_paf(p).result()), want) == []
+    dev = torch.empty(len(paf) + 64, dtype=torch.uint8, device="cuda")
+    for shift in (0, 1, 7, 13):
+        dev[shift:shift + len(paf)] = torch.frombuffer(bytearray(paf), dtype=torch.uint8).cuda()
+        torch.cuda.synchronize()
+        builder.build_from_device(dev.data_ptr() + shift, len(paf))
+        assert tables_equal(util.gpu_to_tables(builder.result()), want) == []
+
+
+def test_missing_file(builder):
+    from muchsalsa_b200.construct import MsGpuError
+    with pytest.raises(MsGpuError) as e:
+        builder.build_from_paf("/nonexistent/x.paf")
+    assert e.value.status == 3 and "Can't open blast file." in e.value.message
+
+
+def test_yeast_scale_invariants_and_digest(builder):
+    """Full-size check without the (slow) oracle: structural invariants + the digest recorded from the reference."""
+    paf = synth.generate_paf("yeast")
+    res = builder.build_from_buffer(paf).result()
+    util.check_invariants(res)
+    g = util.load_golden("digests.json").get("yeast")
+    if g:
+        t = util.gpu_to_tables(res)
+        assert t.counts == g["counts"] and tables_digest(t) == g["digest"]
+
+
+def test_records_entry_matches_paf_entry(builder):
+    """msgpu_build_from_records (packed SoA already in HBM) gives the same edges as the PAF entry."""
+    import torch
+    paf = synth.generate_paf("small")
+    full = builder.build_from_buffer(paf).result()
+    m = full.matches
+    rec = {k: torch.from_numpy(m[k].copy()).cuda() for k in
+           ("unitig", "read", "ir0", "ir1", "nr0", "nr1", "score", "line", "flags")}
+    res = builder.build_from_records(rec, full.counts["n_reads"], full.counts["n_unitigs"]).result()
+    assert np.array_equal(res.edge_first, full.edge_first) and np.array_equal(res.edge_second, full.edge_second)
+    assert np.array_equal(res.edge_em_begin, full.edge_em_begin)
+    for k in full.edge_matches:
+        a, b = res.edge_matches[k], full.edge_matches[k]
+        assert np.array_equal(a.view(np.uint64) if a.dtype == np.float64 else a,
+                              b.view(np.uint64) if b.dtype == np.float64 else b), k
