@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — graph-construction throughput (PAF matches/s, edges/s) of the B200 path, with its roofline and the
+reference's CPU path beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ecoli|yeast|small|thaliana] [--impl reference]
+
+One "step" = one pass of the hot path (PAF text -> read/unitig/match/edge/edge-match tables) over one synthetic PAF.
+  value   : kept matches / s with the PAF text already resident in HBM and the tables left in HBM (CUDA events on the
+            library's stream, L2 flushed between steps)
+  e2e     : the same metric through the reference-facing C ABI with HOST buffers: msgpu_build_from_paf_buffer (pinned
+            host PAF -> device) + msgpu_result_host (every table -> pinned host), wall clock
+  roofline: algorithmic HBM bytes of the dominant kernel / its CUDA-event duration / measured copy bandwidth
+  cpu_baseline / --impl reference: the reference's own code (oracle/_ref/msref_cli, compiled from the reference
+            sources) on this box's host cores on the same PAF
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "PAF matches/s (graph build; edges/s alongside)"
+UNIT = "matches/s"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+# bounded CPU sample per workload: (shard index, shard count) of the synthetic generator, None = the whole workload
+CPU_SAMPLE = {"small": None, "ecoli": None, "yeast": (0, 24), "thaliana": (0, 400), "human": (0, 8000)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index=0, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period, self.stop_flag = index, period, threading.Event()
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self.stop_flag.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: report that instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "samples": len(sm),
+                "reasons": sorted(self.reasons)}
+
+
+def make_workload(name, shard=None):
+    from muchsalsa_b200 import synth
+    cfg = synth.CONFIGS[name]
+    return synth.columns_to_paf(synth.generate_columns(cfg, shard))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# algorithmic HBM bytes per launch of the kernels that can dominate (DESIGN.md "Kernels and their rooflines")
+#   M kept matches, EM edge matches, E edges, P candidate pairs, B PAF bytes
+# ---------------------------------------------------------------------------------------------------------------------
+def kernel_bytes(name, c, paf_bytes):
+    M, EM, E = c["n_matches"], c["n_edge_matches"], c["n_edges"]
+    table = {
+        # sort-based variant
+        "radix_scatter": 2 * 12 * EM,            # (key u64 + index u32) read once + written once per digit pass
+        "radix_hist": 8 * EM,                    # keys read once
+        "pair_emit": 29 * M + 33 * EM,           # match fields read once; key + payload of each kept pair written once
+        "pair_count": 12 * M,                    # unitig ranges + read ids read once (pairing happens on chip)
+        "gather_sorted": (12 + 25 + 25 + 1) * EM,
+        "write_edges": 9 * EM + 16 * E,
+        # fused variant
+        "pair_fused": 29 * M + 25 * EM + 16 * E,  # every match read once, every edge match + edge written once
+        # ingest
+        "parse_lines": paf_bytes + 8 * c["n_lines"] + 50 * c["n_lines"],
+        "newline_count": paf_bytes, "newline_write": paf_bytes + 8 * c["n_lines"],
+    }
+    return table.get(name)
+
+
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from muchsalsa_b200.construct import GraphBuilder
+
+    if world > 1:
+        from muchsalsa_b200 import multi_gpu
+        out = multi_gpu.bench(args, rank, world, local, dist)
+        if rank == 0:
+            print(json.dumps(out))
+        dist.destroy_process_group()
+        return
+
+    paf = make_workload(args.workload)
+    n_bytes = len(paf)
+    host = torch.frombuffer(bytearray(paf), dtype=torch.uint8).pin_memory()
+    dev = host.cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    gb = GraphBuilder(local)
+    stream = torch.cuda.current_stream()
+    gb.set_stream(stream.cuda_stream)
+
+    def step_device():
+        gb.build_from_device(dev.data_ptr(), n_bytes)
+
+    def step_e2e():
+        gb.build_from_buffer(host)
+        gb.host_tables()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    counts = gb.counts()
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: device-resident throughput
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = gb.launch_count()
+    ms = []
+    for _ in range(args.steps):
+        flush.zero_()  # evict L2 between steps (not timed)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        step_device()
+        b.record(stream)
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    launches = gb.launch_count() - launches0
+    t_dev = sum(ms) / 1e3
+
+    # ---- timed region 2: end to end through the C ABI with host buffers
+    for _ in range(2):
+        step_e2e()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    stage = gb.timings()
+    clocks = sampler.summary()
+
+    # ---- per-kernel durations (CUDA events around every launch) for the roofline
+    gb.profile(True)
+    agg = {}
+    for _ in range(args.steps):
+        flush.zero_()
+        step_device()
+        for k, (n, t) in gb.kernel_stats().items():
+            a = agg.setdefault(k, [0, 0.0])
+            a[0] += n
+            a[1] += t
+    gb.profile(False)
+    per_kernel = {k: {"launches_per_step": n / args.steps, "ms_per_step": t / args.steps, "us_per_launch": 1e3 * t / n}
+                  for k, (n, t) in agg.items()}
+    top = sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_per_step"])
+    peak, peak_src = peaks()
+    roof = None
+    for name, st in top:
+        b = kernel_bytes(name, counts, n_bytes)
+        if b is None:
+            continue
+        achieved = b / (st["us_per_launch"] * 1e-6) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(args.workload, {}).get(name)
+        roof = {"kernel": name, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(b), "us_per_launch": round(st["us_per_launch"], 2),
+                "share_of_step": round(st["ms_per_step"] / sum(v["ms_per_step"] for v in per_kernel.values()), 3)}
+        break
+
+    # ---- the reference's CPU path beside it (bounded sample, rank 0 only)
+    cpu = cpu_baseline(args.workload)
+
+    bytes_d2h = result_bytes(counts, gb)
+    out = {
+        "metric": METRIC, "value": counts["n_matches"] * args.steps / t_dev, "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32 keys + f64 scores",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}-scale synthetic PAF (muchsalsa_b200.synth, seed fixed)",
+                   "paf_bytes": n_bytes, "lines": counts["n_lines"], "kept_matches": counts["n_matches"],
+                   "reads": counts["n_reads"], "unitigs": counts["n_unitigs"], "pairs": counts["n_pairs"],
+                   "edges": counts["n_edges"], "edge_matches": counts["n_edge_matches"],
+                   "l2": "flushed between steps (256 MiB memset)", "matches_counted": "kept VertexMatch rows"},
+        "edges_per_s": counts["n_edges"] * args.steps / t_dev,
+        "edge_matches_per_s": counts["n_edge_matches"] * args.steps / t_dev,
+        "e2e": {"value": counts["n_matches"] * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": n_bytes,
+                "d2h_bytes_per_step": bytes_d2h, "ms_per_step": 1e3 * t_e2e / args.steps,
+                "edges_per_s": counts["n_edges"] * args.steps / t_e2e,
+                "stages_ms_last_step": {k: round(v, 3) for k, v in stage.items()}},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "kernels": {k: {kk: round(vv, 3) for kk, vv in v.items()} for k, v in top[:12]},
+        "variant": os.environ.get("MSGPU_VARIANT", "default"),
+    }
+    gb.close()
+    print(json.dumps(out))
+
+
+def result_bytes(c, gb):
+    R, U, M, E, EM = c["n_reads"], c["n_unitigs"], c["n_matches"], c["n_edges"], c["n_edge_matches"]
+    names = 0
+    try:
+        r = gb.result()
+        names = sum(len(x) for x in r.read_names) + sum(len(x) for x in r.unitig_names)
+    except Exception:
+        pass
+    return int(R * 8 + (R + 1) * 8 + (U + 1) * 8 + names + M * (4 * 8 + 8 + 1) + E * 8 + (E + 1) * 8 + EM * 25)
+
+
+def _run_ref_cli(paf_path, threads, timeout=1800):
+    cli = os.path.join(ROOT, "oracle", "_ref", "msref_cli")
+    p = subprocess.run([cli, paf_path, str(threads)], capture_output=True, text=True, timeout=timeout)
+    if p.returncode != 0:
+        return None, p.returncode
+    return json.loads(p.stdout.strip().splitlines()[-1]), 0
+
+
+def cpu_baseline(workload, steps=1):
+    """The reference's own read() + calculateEdges() on this host (oracle/_ref/msref_cli), on a bounded sample."""
+    cli = os.path.join(ROOT, "oracle", "_ref", "msref_cli")
+    shard = CPU_SAMPLE.get(workload)
+    sample = "whole workload" if shard is None else f"unitig shard {shard[0]} of {shard[1]} of the workload"
+    paf = make_workload(workload, shard)
+    with tempfile.NamedTemporaryFile(suffix=".paf", delete=False) as f:
+        f.write(paf)
+        path = f.name
+    try:
+        if not os.path.exists(cli):
+            return cpu_baseline_port(paf, sample)
+        ncpu = os.cpu_count() or 1
+        multi, rc = _run_ref_cli(path, ncpu) if ncpu > 1 else (None, 0)
+        res, threads, note = multi, ncpu, None
+        if multi is None:
+            note = (f"reference with {ncpu} threads exited with status {rc} (data race on the adjacency list, "
+                    "Graph.cpp:96-116 vs 212-230); timed with 1 thread, its only reliable mode")
+            best = None
+            for _ in range(steps):
+                r1, rc1 = _run_ref_cli(path, 1)
+                if r1 is None:
+                    return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
+                            "note": f"reference failed with status {rc1}"}
+                t = r1["t_index"] + r1["t_read"] + r1["t_edges"]
+                if best is None or t < best[0]:
+                    best = (t, r1)
+            res, threads = best[1], 1
+        t = res["t_index"] + res["t_read"] + res["t_edges"]
+        return {"value": res["n_vm"] / t, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+                "seconds": round(t, 3), "edges_per_s": res["n_edges"] / t, "edge_matches_per_s": res["n_em"] / t,
+                "phases_s": {k: res[k] for k in ("t_index", "t_read", "t_edges")},
+                "rows": {k: res[k] for k in ("n_reads", "n_vm", "n_edges", "n_em")}, "host_cpus": ncpu, "note": note}
+    finally:
+        os.unlink(path)
+
+
+def cpu_baseline_port(paf, sample):
+    from oracle.pyoracle import Oracle
+    o = Oracle()
+    t0 = time.perf_counter()
+    t = o.build(paf)
+    dt = time.perf_counter() - t0
+    c = t.counts
+    return {"value": c["vm"] / dt, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+            "seconds": round(dt, 3), "edges_per_s": c["edges"] / dt, "note": "oracle/_ref absent: timed the C port"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores, same metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shard = CPU_SAMPLE.get(args.workload)
+    paf = make_workload(args.workload, shard)
+    with tempfile.NamedTemporaryFile(suffix=".paf", delete=False) as f:
+        f.write(paf)
+        path = f.name
+    try:
+        ncpu = os.cpu_count() or 1
+        threads, note = ncpu, None
+        probe, rc = _run_ref_cli(path, ncpu) if ncpu > 1 else (None, 0)
+        if probe is None:
+            threads = 1
+            note = (f"{ncpu} threads: exit status {rc} (unlocked adjacency-list reads race the writer, "
+                    "Graph.cpp:96-116 vs 212-230); 1 thread is the reference's only reliable mode")
+        for _ in range(args.warmup):
+            _run_ref_cli(path, threads)
+        tot, rows = 0.0, None
+        for _ in range(args.steps):
+            r, rc = _run_ref_cli(path, threads)
+            if r is None:
+                threads, note = 1, f"{ncpu}-thread run crashed mid-benchmark (status {rc}); fell back to 1 thread"
+                r, rc = _run_ref_cli(path, 1)
+            tot += r["t_index"] + r["t_read"] + r["t_edges"]
+            rows = r
+        value = rows["n_vm"] * args.steps / tot
+        sample = "whole workload" if shard is None else f"unitig shard {shard[0]} of {shard[1]} of the workload"
+        out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32 keys + f64 scores",
+               "data": "synthetic",
+               "config": {"workload": f"{args.workload}-scale synthetic PAF (muchsalsa_b200.synth, seed fixed)",
+                          "sample": sample, "kept_matches": rows["n_vm"], "edges": rows["n_edges"],
+                          "edge_matches": rows["n_em"]},
+               "edges_per_s": rows["n_edges"] * args.steps / tot,
+               "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                                "sample": sample, "host_cpus": ncpu, "note": note},
+               "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+    finally:
+        os.unlink(path)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("MSGPU_WORKLOAD", "ecoli"))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

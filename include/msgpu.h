@@ -148,6 +148,18 @@ typedef struct msgpu_timings {
 } msgpu_timings;
 int msgpu_result_timings(const msgpu_ctx *ctx, msgpu_timings *out);
 
+/* Per-kernel device time of the last build (CUDA events around every launch, on the context's stream) — what
+ * bench.py uses for the roofline of the dominant kernel.  Off by default: the events cost host time per launch. */
+typedef struct msgpu_kernel_stat {
+  char     name[48];
+  uint32_t launches;
+  float    total_ms;
+} msgpu_kernel_stat;
+int      msgpu_profile_enable(msgpu_ctx *ctx, int enable);
+int      msgpu_profile_read(msgpu_ctx *ctx, msgpu_kernel_stat *out, size_t capacity, size_t *n_out);
+/* kernels this context has launched since it was created (the library's own count; bench.py's `gpu_launches`) */
+uint64_t msgpu_launch_count(const msgpu_ctx *ctx);
+
 /* ---- sequences ----------------------------------------------------------------------------------------------------
  * msgpu_seq_load   replaces SequenceAccessor(...) + buildIndex() (src/main.cpp:161-163): both files are indexed,
  *                  whitespace-stripped and kept resident in HBM.  Ids continue the numbering of the context's last

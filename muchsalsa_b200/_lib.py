@@ -34,6 +34,10 @@ class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "ingest_ms", "pair_ms", "merge_ms", "d2h_ms", "total_ms")]
 
 
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint32), ("total_ms", C.c_float)]
+
+
 class MatchSoA(C.Structure):
     _fields_ = [("n", C.c_uint64), ("unitig", C.c_void_p), ("read", C.c_void_p), ("ir0", C.c_void_p),
                 ("ir1", C.c_void_p), ("nr0", C.c_void_p), ("nr1", C.c_void_p), ("score", C.c_void_p),
@@ -60,6 +64,9 @@ SIGNATURES = {
     "msgpu_result_device": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),
     "msgpu_result_host": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),
     "msgpu_result_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
+    "msgpu_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "msgpu_profile_read": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_size_t, C.POINTER(C.c_size_t)]),
+    "msgpu_launch_count": (C.c_uint64, [C.c_void_p]),
     "msgpu_seq_load": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     "msgpu_seq_load_buffers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
     "msgpu_seq_id": (C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p, u32p]),

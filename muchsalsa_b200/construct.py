@@ -128,6 +128,19 @@ class GraphBuilder:
         self._check(self._lib.msgpu_result_timings(self._h, C.byref(t)))
         return {k: float(getattr(t, k)) for k, _ in t._fields_}
 
+    def profile(self, enable: bool):
+        self._check(self._lib.msgpu_profile_enable(self._h, 1 if enable else 0))
+
+    def kernel_stats(self) -> dict:
+        """{kernel name: (launches, total ms)} of the last build (needs profile(True) before it)."""
+        arr = (_lib.KernelStat * 128)()
+        n = C.c_size_t()
+        self._check(self._lib.msgpu_profile_read(self._h, arr, 128, C.byref(n)))
+        return {arr[i].name.decode(): (int(arr[i].launches), float(arr[i].total_ms)) for i in range(min(n.value, 128))}
+
+    def launch_count(self) -> int:
+        return int(self._lib.msgpu_launch_count(self._h))
+
     def device_tables(self) -> _lib.Tables:
         t = _lib.Tables()
         self._check(self._lib.msgpu_result_device(self._h, C.byref(t)))

@@ -85,6 +85,74 @@ private:
   size_t            m_used = 0, m_high = 0;
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Launch accounting + optional per-kernel timing (CUDA events on the launching stream).  Every kernel launch of the
+// library goes through MSGPU_LAUNCH, so `launches` is the library's own count of what it put on the GPU; when
+// `enabled`, each launch is bracketed by two events and bench.py reads per-kernel durations for the roofline.
+// ---------------------------------------------------------------------------------------------------------------------
+struct Profiler {
+  struct Rec {
+    const char *name;
+    cudaEvent_t a, b;
+  };
+  bool                     enabled  = false;
+  uint64_t                 launches = 0;
+  std::vector<Rec>         recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get_event() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    MSGPU_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+  void clear() {
+    for (auto &r : recs) {
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    recs.clear();
+  }
+  ~Profiler() {
+    clear();
+    for (auto e : pool) cudaEventDestroy(e);
+  }
+};
+
+inline Profiler *&current_profiler() {
+  static thread_local Profiler *p = nullptr;
+  return p;
+}
+
+struct KernelScope {
+  Profiler    *prof;
+  cudaStream_t st;
+  cudaEvent_t  stop = nullptr;
+  KernelScope(const char *name, cudaStream_t s) : prof(current_profiler()), st(s) {
+    if (!prof) return;
+    ++prof->launches;
+    if (prof->enabled) {
+      Profiler::Rec r{name, prof->get_event(), prof->get_event()};
+      stop = r.b;
+      cudaEventRecord(r.a, st);
+      prof->recs.push_back(r);
+    }
+  }
+  ~KernelScope() {
+    if (stop) cudaEventRecord(stop, st);
+  }
+};
+
+#define MSGPU_LAUNCH(name, stream, ...)        \
+  do {                                         \
+    ::msgpu::KernelScope _ks(name, stream);    \
+    __VA_ARGS__;                               \
+    MSGPU_LAUNCH_CHECK();                      \
+  } while (0)
+
 inline int grid_for(size_t n_items, int block, int max_waves = 8) {
   // grid = multiple of the SM count, capped at `max_waves` x (SMs x resident blocks); kernels are grid-stride
   size_t need   = (n_items + block - 1) / block;

@@ -439,15 +439,13 @@ static void build_name_table(Arena &arena, cudaStream_t st, const char *d_paf, u
   out.n_bytes = read_back(st, total);
   out.names   = arena.alloc<char>(out.n_bytes);
   if (n) {
-    gather_names_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(d_paf, src, out.name_off, n, out.names);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("gather_names", st, gather_names_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(d_paf, src, out.name_off, n, out.names));
   }
 }
 
 void build_group_offsets(Arena &arena, cudaStream_t st, const MatchSoA &m, UnitigTable &unitigs) {
   unitigs.grp_off = arena.alloc<uint32_t>(unitigs.n + 1);
-  group_bounds_kernel<<<grid_for(m.n + 1, 256), 256, 0, st>>>(m.unitig, m.n, uint32_t(unitigs.n), unitigs.grp_off);
-  MSGPU_LAUNCH_CHECK();
+  MSGPU_LAUNCH("group_bounds", st, group_bounds_kernel<<<grid_for(m.n + 1, 256), 256, 0, st>>>(m.unitig, m.n, uint32_t(unitigs.n), unitigs.grp_off));
 }
 
 void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
@@ -466,19 +464,16 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   uint32_t    *d_n_nl   = arena.alloc<uint32_t>(1);
   uint64_t    *d_nlines = arena.alloc<uint64_t>(1);
   if (n_tiles) {
-    newline_count_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("newline_count", st, newline_count_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt));
   }
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{tile_cnt}, n_tiles, tile_cnt, d_n_nl);
   uint32_t n_newlines = read_back(st, d_n_nl);
   if (uint64_t(n_newlines) + 2 >= 0xffffffffull) throw BuildError{MSGPU_ERR_LIMIT, "more than 2^32-2 lines in one PAF"};
   uint64_t *line_start = arena.alloc<uint64_t>(uint64_t(n_newlines) + 2);
   if (n_tiles) {
-    newline_write_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt, line_start);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("newline_write", st, newline_write_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt, line_start));
   }
-  line_index_finish_kernel<<<1, 1, 0, st>>>(d_paf, n_bytes, d_n_nl, line_start, d_nlines);
-  MSGPU_LAUNCH_CHECK();
+  MSGPU_LAUNCH("line_index_finish", st, line_index_finish_kernel<<<1, 1, 0, st>>>(d_paf, n_bytes, d_n_nl, line_start, d_nlines));
   uint64_t n_lines = read_back(st, d_nlines);
   *n_lines_out     = n_lines;
   // BlastFileReader::read(): lines 0 .. lineCount-2 (BlastFileReader.cpp:76)
@@ -514,9 +509,8 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     if (attempt == 4) throw BuildError{MSGPU_ERR_INTERNAL, "name hash collisions persisted over 4 seeds"};
     MSGPU_CUDA(cudaMemcpyAsync(d_status, &h_status, sizeof(h_status), cudaMemcpyHostToDevice, st));
     if (n_parse) {
-      parse_lines_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, n_parse,
-                                                     0x243f6a8885a308d3ull * uint64_t(attempt + 1), f, d_status);
-      MSGPU_LAUNCH_CHECK();
+      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, n_parse,
+                                                     0x243f6a8885a308d3ull * uint64_t(attempt + 1), f, d_status));
     }
     IngestStatus s1 = read_back(st, d_status);
     if (s1.first_bad_line != ~0ull)
@@ -527,12 +521,9 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     rt = make_table(arena, st, n_acc);
     ut = make_table(arena, st, n_acc);
     if (n_parse) {
-      intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.rhash, n_parse, rt, rslot);
-      MSGPU_LAUNCH_CHECK();
-      intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.uhash, n_parse, ut, uslot);
-      MSGPU_LAUNCH_CHECK();
-      intern_verify_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, n_parse, f, rt, rslot, ut, uslot, d_status);
-      MSGPU_LAUNCH_CHECK();
+      MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.rhash, n_parse, rt, rslot));
+      MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.uhash, n_parse, ut, uslot));
+      MSGPU_LAUNCH("intern_verify", st, intern_verify_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, n_parse, f, rt, rslot, ut, uslot, d_status));
     }
     exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstRead}, n_parse, rank_a, d_cnt + 0);
     exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstUnitig}, n_parse, rank_b, d_cnt + 1);
@@ -548,9 +539,8 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   uint64_t *rsrc = arena.alloc<uint64_t>(n_reads), *usrc = arena.alloc<uint64_t>(n_unitigs);
   uint32_t *rlen = arena.alloc<uint32_t>(n_reads), *ulen = arena.alloc<uint32_t>(n_unitigs);
   if (n_parse) {
-    intern_assign_kernel<<<grid_lines, 256, 0, st>>>(line_start, n_parse, f, rt, rslot, rank_a, ut, uslot, rank_b,
-                                                     reads.nlen, reads.line, rsrc, rlen, usrc, ulen);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("intern_assign", st, intern_assign_kernel<<<grid_lines, 256, 0, st>>>(line_start, n_parse, f, rt, rslot, rank_a, ut, uslot, rank_b,
+                                                     reads.nlen, reads.line, rsrc, rlen, usrc, ulen));
   }
   build_name_table(arena, st, d_paf, n_reads, rsrc, rlen, reads);
   build_name_table(arena, st, d_paf, n_unitigs, usrc, ulen, unitigs);
@@ -559,11 +549,9 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   uint64_t    n_acc = read_back(st, d_status).n_accepted;
   InternTable dt    = make_table(arena, st, n_acc);
   if (n_parse) {
-    dedup_insert_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line,
-                                                    uid_of_line);
-    MSGPU_LAUNCH_CHECK();
-    dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f.flags, dt, dslot);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("dedup_insert", st, dedup_insert_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line,
+                                                    uid_of_line));
+    MSGPU_LAUNCH("dedup_flag", st, dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f.flags, dt, dslot));
   }
 
   // ---- K5 compaction (+ grouping sort when the PAF is not grouped by unitig)
@@ -584,12 +572,10 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   };
   alloc_soa(m);
   if (n_parse) {
-    compact_matches_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f, rank_a, rid_of_line, uid_of_line, m);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("compact_matches", st, compact_matches_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f, rank_a, rid_of_line, uid_of_line, m));
   }
   if (M > 1) {
-    check_grouped_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, M, d_status);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, M, d_status));
   }
   if (read_back(st, d_status).unsorted) {
     // stable sort by unitig id keeps the line order inside a unitig (rows are in line order now)
@@ -597,22 +583,20 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     uint32_t *idx = arena.alloc<uint32_t>(M), *idx2 = arena.alloc<uint32_t>(M);
     int       g = grid_for(M, 256);
     MSGPU_CUDA(cudaMemcpyAsync(keys, m.unitig, M * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    iota_kernel<<<g, 256, 0, st>>>(idx, M);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("iota", st, iota_kernel<<<g, 256, 0, st>>>(idx, M));
     radix_sort_pairs<uint32_t, uint32_t>(arena, st, keys, idx, keys2, idx2, M, {0, bits_for(n_unitigs)});
     MatchSoA s;
     alloc_soa(s);
-    gather_kernel<<<g, 256, 0, st>>>(m.unitig, idx, M, s.unitig);
-    gather_kernel<<<g, 256, 0, st>>>(m.read, idx, M, s.read);
-    gather_kernel<<<g, 256, 0, st>>>(m.ir0, idx, M, s.ir0);
-    gather_kernel<<<g, 256, 0, st>>>(m.ir1, idx, M, s.ir1);
-    gather_kernel<<<g, 256, 0, st>>>(m.nr0, idx, M, s.nr0);
-    gather_kernel<<<g, 256, 0, st>>>(m.nr1, idx, M, s.nr1);
-    gather_kernel<<<g, 256, 0, st>>>(m.score, idx, M, s.score);
-    gather_kernel<<<g, 256, 0, st>>>(m.line, idx, M, s.line);
-    gather_kernel<<<g, 256, 0, st>>>(m.flags, idx, M, s.flags);
-    gather_kernel<<<g, 256, 0, st>>>(m.rratio, idx, M, s.rratio);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.unitig, idx, M, s.unitig));
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.read, idx, M, s.read));
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.ir0, idx, M, s.ir0));
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.ir1, idx, M, s.ir1));
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.nr0, idx, M, s.nr0));
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.nr1, idx, M, s.nr1));
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.score, idx, M, s.score));
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.line, idx, M, s.line));
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.flags, idx, M, s.flags));
+    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.rratio, idx, M, s.rratio));
     m = s;
   }
   build_group_offsets(arena, st, m, unitigs);

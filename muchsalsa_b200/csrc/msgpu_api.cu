@@ -8,6 +8,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -63,6 +64,7 @@ struct msgpu_ctx {
   msgpu_tables host_tables{};
 
   SeqStore *seq = nullptr;
+  Profiler  profiler;
 };
 
 namespace {
@@ -80,8 +82,13 @@ struct DeviceGuard {
 
 template <class Fn> int guarded(msgpu_ctx *ctx, Fn &&fn) {
   if (!ctx) return MSGPU_ERR_INVALID_ARG;
+  struct ProfScope {
+    explicit ProfScope(Profiler *p) { current_profiler() = p; }
+    ~ProfScope() { current_profiler() = nullptr; }
+  };
   try {
     DeviceGuard g(ctx->device);
+    ProfScope   ps(&ctx->profiler);
     fn();
     ctx->error.clear();
     return MSGPU_OK;
@@ -112,6 +119,7 @@ void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes) {
   ctx->have_result = false;
   ctx->host_valid  = false;
   ctx->arena.reset();
+  ctx->profiler.clear();
   MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
   run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches);
   MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
@@ -239,6 +247,7 @@ int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t 
     ctx->have_result = false;
     ctx->host_valid  = false;
     ctx->arena.reset();
+    ctx->profiler.clear();
     ctx->reads   = ReadTable{};
     ctx->unitigs = UnitigTable{};
     ctx->reads.n = n_reads;
@@ -384,6 +393,38 @@ int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out) {
     ctx->timings.total_ms += ctx->timings.d2h_ms;
     ctx->host_valid = true;
     *out            = h;
+  });
+}
+
+int msgpu_profile_enable(msgpu_ctx *ctx, int enable) {
+  if (!ctx) return MSGPU_ERR_INVALID_ARG;
+  ctx->profiler.enabled = enable != 0;
+  return MSGPU_OK;
+}
+
+uint64_t msgpu_launch_count(const msgpu_ctx *ctx) { return ctx ? ctx->profiler.launches : 0; }
+
+int msgpu_profile_read(msgpu_ctx *ctx, msgpu_kernel_stat *out, size_t cap, size_t *n_out) {
+  if (!ctx || !n_out || (!out && cap)) return MSGPU_ERR_INVALID_ARG;
+  return guarded(ctx, [&] {
+    MSGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<msgpu_kernel_stat> stats;
+    for (auto const &r : ctx->profiler.recs) {
+      float ms = 0.f;
+      MSGPU_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+      auto it = std::find_if(stats.begin(), stats.end(),
+                             [&](msgpu_kernel_stat const &s) { return std::strncmp(s.name, r.name, 47) == 0; });
+      if (it == stats.end()) {
+        msgpu_kernel_stat s{};
+        std::strncpy(s.name, r.name, 47);
+        stats.push_back(s);
+        it = stats.end() - 1;
+      }
+      it->launches += 1;
+      it->total_ms += ms;
+    }
+    *n_out = stats.size();
+    for (size_t i = 0; i < stats.size() && i < cap; ++i) out[i] = stats[i];
   });
 }
 

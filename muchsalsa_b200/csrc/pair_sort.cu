@@ -193,8 +193,7 @@ void run_pairing_sorted(Arena &arena, cudaStream_t st, const MatchSoA &m, const 
   uint32_t *block_cnt = arena.alloc<uint32_t>(n_blocks);
   uint32_t *d_nem     = arena.alloc<uint32_t>(2);
   if (P) {
-    pair_count_kernel<<<n_blocks, kPairBlock, 0, st>>>(m, pair_off, unitigs.grp_off, U, P, per_block, block_cnt);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("pair_count", st, pair_count_kernel<<<n_blocks, kPairBlock, 0, st>>>(m, pair_off, unitigs.grp_off, U, P, per_block, block_cnt));
   } else {
     MSGPU_CUDA(cudaMemsetAsync(block_cnt, 0, n_blocks * sizeof(uint32_t), st));
   }
@@ -211,8 +210,7 @@ void run_pairing_sorted(Arena &arena, cudaStream_t st, const MatchSoA &m, const 
   c.line   = arena.alloc<uint32_t>(n_em);
   c.flags  = arena.alloc<uint8_t>(n_em);
   if (P) {
-    pair_emit_kernel<<<n_blocks, kPairBlock, 0, st>>>(m, pair_off, unitigs.grp_off, U, P, per_block, block_cnt, c);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("pair_emit", st, pair_emit_kernel<<<n_blocks, kPairBlock, 0, st>>>(m, pair_off, unitigs.grp_off, U, P, per_block, block_cnt, c));
   }
   if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st));
 
@@ -235,16 +233,14 @@ void run_pairing_sorted(Arena &arena, cudaStream_t st, const MatchSoA &m, const 
   uint8_t  *head      = arena.alloc<uint8_t>(n_em);
   uint32_t *edge_rank = arena.alloc<uint32_t>(n_em);
   if (n_em) {
-    gather_sorted_kernel<<<g, 256, 0, st>>>(key, idx, n_em, c, e, head);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("gather_sorted", st, gather_sorted_kernel<<<g, 256, 0, st>>>(key, idx, n_em, c, e, head));
   }
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint8_t, uint32_t>{head}, n_em, edge_rank, d_nem + 1);
   e.n_edges  = read_back(st, d_nem + 1);
   e.first    = arena.alloc<uint32_t>(e.n_edges);
   e.second   = arena.alloc<uint32_t>(e.n_edges);
   e.em_begin = arena.alloc<uint64_t>(e.n_edges + 1);
-  write_edges_kernel<<<g, 256, 0, st>>>(key, head, edge_rank, n_em, e, d_nem + 1);
-  MSGPU_LAUNCH_CHECK();
+  MSGPU_LAUNCH("write_edges", st, write_edges_kernel<<<g, 256, 0, st>>>(key, head, edge_rank, n_em, e, d_nem + 1));
 }
 
 } // namespace msgpu

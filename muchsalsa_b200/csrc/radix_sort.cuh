@@ -95,13 +95,10 @@ void radix_sort_pairs(Arena &arena, cudaStream_t st, K *&keys, V *&vals, K *&key
     for (int lo = bit_ranges[r]; lo < bit_ranges[r + 1]; lo += 8) {
       int      bits = bit_ranges[r + 1] - lo < 8 ? bit_ranges[r + 1] - lo : 8;
       unsigned mask = (1u << bits) - 1u;
-      radix_hist_kernel<K><<<n_tiles, kSortBlock, 0, st>>>(keys, n, lo, mask, n_tiles, hist);
-      MSGPU_LAUNCH_CHECK();
+      MSGPU_LAUNCH("radix_hist", st, radix_hist_kernel<K><<<n_tiles, kSortBlock, 0, st>>>(keys, n, lo, mask, n_tiles, hist));
       exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{hist}, uint64_t(256) * n_tiles, hist,
                                (uint32_t *)nullptr);
-      radix_scatter_kernel<K, V>
-          <<<n_tiles, kSortBlock, 0, st>>>(keys, vals, keys_tmp, vals_tmp, n, lo, mask, n_tiles, hist);
-      MSGPU_LAUNCH_CHECK();
+      MSGPU_LAUNCH("radix_scatter", st, radix_scatter_kernel<K, V><<<n_tiles, kSortBlock, 0, st>>>(keys, vals, keys_tmp, vals_tmp, n, lo, mask, n_tiles, hist));
       std::swap(keys, keys_tmp);
       std::swap(vals, vals_tmp);
     }

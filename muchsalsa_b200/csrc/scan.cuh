@@ -78,13 +78,10 @@ void exclusive_scan(Arena &arena, cudaStream_t st, InFn in, uint64_t n, T *out, 
   }
   uint64_t n_tiles  = (n + kScanTile - 1) / kScanTile;
   T       *partials = arena.alloc<T>(n_tiles);
-  scan_reduce_kernel<T, InFn><<<(unsigned)n_tiles, kScanBlock, 0, st>>>(in, n, partials);
-  MSGPU_LAUNCH_CHECK();
-  scan_partials_kernel<T><<<1, 1024, 0, st>>>(partials, n_tiles, total_out);
-  MSGPU_LAUNCH_CHECK();
+  MSGPU_LAUNCH("scan_reduce", st, scan_reduce_kernel<T, InFn><<<(unsigned)n_tiles, kScanBlock, 0, st>>>(in, n, partials));
+  MSGPU_LAUNCH("scan_partials", st, scan_partials_kernel<T><<<1, 1024, 0, st>>>(partials, n_tiles, total_out));
   if (out) {
-    scan_downsweep_kernel<T, InFn><<<(unsigned)n_tiles, kScanBlock, 0, st>>>(in, n, partials, out);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("scan_downsweep", st, scan_downsweep_kernel<T, InFn><<<(unsigned)n_tiles, kScanBlock, 0, st>>>(in, n, partials, out));
   }
 }
 

@@ -380,16 +380,14 @@ void load_file(SeqStore *s, cudaStream_t st, int which, const char *data, size_t
   uint64_t  n_tiles = (uint64_t(n) + 1 + kStripTile - 1) / kStripTile;
   uint64_t *tile    = scratch.alloc<uint64_t>(n_tiles);
   uint64_t *d_total = scratch.alloc<uint64_t>(1);
-  strip_kernel<false><<<unsigned(n_tiles), kStripBlock, 0, st>>>(d_raw, n, d_rb, d_re, R, tile, nullptr, nullptr,
-                                                                 nullptr);
-  MSGPU_LAUNCH_CHECK();
+  MSGPU_LAUNCH("strip", st, strip_kernel<false><<<unsigned(n_tiles), kStripBlock, 0, st>>>(d_raw, n, d_rb, d_re, R, tile, nullptr, nullptr,
+                                                                 nullptr));
   exclusive_scan<uint64_t>(scratch, st, LoadAs<uint64_t, uint64_t>{tile}, n_tiles, tile, d_total);
   uint64_t total = 0;
   MSGPU_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
   MSGPU_CUDA(cudaStreamSynchronize(st));
   char *packed = s->arena.alloc<char>(total + 16);
-  strip_kernel<true><<<unsigned(n_tiles), kStripBlock, 0, st>>>(d_raw, n, d_rb, d_re, R, tile, packed, d_pb, d_pe);
-  MSGPU_LAUNCH_CHECK();
+  MSGPU_LAUNCH("strip", st, strip_kernel<true><<<unsigned(n_tiles), kStripBlock, 0, st>>>(d_raw, n, d_rb, d_re, R, tile, packed, d_pb, d_pe));
   std::vector<uint64_t> pb(R), pe(R);
   if (R) {
     MSGPU_CUDA(cudaMemcpyAsync(pb.data(), d_pb, R * 8, cudaMemcpyDeviceToHost, st));
@@ -432,17 +430,15 @@ void fetch_on_stream(SeqStore *s, Arena &arena, cudaStream_t st, const msgpu_seq
                      uint64_t cap, uint64_t *d_out_off, uint8_t *d_status) {
   Window *win = arena.alloc<Window>(n);
   if (n) {
-    seq_window_kernel<<<grid_for(n, 256), 256, 0, st>>>(s->dev, d_reqs, n, win, d_status);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("seq_window", st, seq_window_kernel<<<grid_for(n, 256), 256, 0, st>>>(s->dev, d_reqs, n, win, d_status));
   }
   uint64_t *d_total = arena.alloc<uint64_t>(1);
   exclusive_scan<uint64_t>(arena, st, WindowCount{win}, n, d_out_off, d_total);
   MSGPU_CUDA(cudaMemcpyAsync(d_out_off + n, d_total, 8, cudaMemcpyDeviceToDevice, st));
   if (n) {
-    slice_copy_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(StoreSrc{d_reqs, s->dev.packed[0], s->dev.packed[1]},
+    MSGPU_LAUNCH("slice_copy", st, slice_copy_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(StoreSrc{d_reqs, s->dev.packed[0], s->dev.packed[1]},
                                                              StoreRev{d_reqs}, win, d_out_off, n, cap, d_out,
-                                                             d_status);
-    MSGPU_LAUNCH_CHECK();
+                                                             d_status));
   }
 }
 
@@ -555,16 +551,14 @@ void slice_revcomp_device(cudaStream_t st, const char *d_text, const uint64_t *d
   Arena   arena;
   Window *win = arena.alloc<Window>(n);
   if (n) {
-    text_window_kernel<<<grid_for(n, 256), 256, 0, st>>>(d_text_off, d_left, d_right, n, win, d_status);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("text_window", st, text_window_kernel<<<grid_for(n, 256), 256, 0, st>>>(d_text_off, d_left, d_right, n, win, d_status));
   }
   uint64_t *d_total = arena.alloc<uint64_t>(1);
   exclusive_scan<uint64_t>(arena, st, WindowCount{win}, n, d_out_off, d_total);
   MSGPU_CUDA(cudaMemcpyAsync(d_out_off + n, d_total, 8, cudaMemcpyDeviceToDevice, st));
   if (n) {
-    slice_copy_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(TextSrc{d_text}, TextRev{d_revcomp}, win, d_out_off, n,
-                                                             cap, d_out, d_status);
-    MSGPU_LAUNCH_CHECK();
+    MSGPU_LAUNCH("slice_copy", st, slice_copy_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(TextSrc{d_text}, TextRev{d_revcomp}, win, d_out_off, n,
+                                                             cap, d_out, d_status));
   }
   MSGPU_CUDA(cudaStreamSynchronize(st)); // `arena` is released on return
 }
