@@ -123,7 +123,7 @@ void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes) {
   MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
   run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches);
   MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
-  run_pairing_sorted(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3]);
+  run_pairing(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3]);
   MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
   MSGPU_CUDA(cudaStreamSynchronize(st));
   ctx->timings.ingest_ms = elapsed(ctx->ev[1], ctx->ev[2]);
@@ -268,7 +268,7 @@ int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t 
     MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
     build_group_offsets(ctx->arena, st, m, ctx->unitigs);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
-    run_pairing_sorted(ctx->arena, st, m, ctx->unitigs, n_reads, ctx->edges, ctx->ev[3]);
+    run_pairing(ctx->arena, st, m, ctx->unitigs, n_reads, ctx->edges, ctx->ev[3]);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
     MSGPU_CUDA(cudaStreamSynchronize(st));
     ctx->timings           = msgpu_timings{};
