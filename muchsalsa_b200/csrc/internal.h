@@ -62,14 +62,14 @@ void build_group_offsets(Arena &arena, cudaStream_t st, const MatchSoA &matches,
 void run_pairing_sorted(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs,
                         uint64_t n_reads, EdgeTables &edges, cudaEvent_t ev_pair_done);
 
-// pair_fused.cu : the same result from ONE persistent kernel (per-read tiles sorted in shared memory, ordered output
-// through a decoupled look-back).  Returns false when the input has reads too heavy for a tile; the caller then uses
-// the sort-based variant.
-bool run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs,
-                       uint64_t n_reads, EdgeTables &edges, cudaEvent_t ev_pair_done);
+// pair_fused.cu : the product variant — ONE persistent kernel (per-row tiles sorted in shared memory, ordered output
+// through a decoupled look-back).  `part` of `n_parts`: this device handles that contiguous share of the tiles, and its
+// tables are that slice of the global result (multi-GPU); 0 of 1 = everything.
+void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs,
+                       uint64_t n_reads, EdgeTables &edges, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts);
 
-// picks the variant: fused unless MSGPU_VARIANT=sorted or the input needs the fallback
+// picks the variant: fused unless MSGPU_VARIANT=sorted (kept as an independent cross-check of the fused kernel)
 void run_pairing(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs, uint64_t n_reads,
-                 EdgeTables &edges, cudaEvent_t ev_pair_done);
+                 EdgeTables &edges, cudaEvent_t ev_pair_done, uint32_t part = 0, uint32_t n_parts = 1);
 
 } // namespace msgpu

@@ -1,27 +1,32 @@
-// pair_fused.cu — candidate-pair generation AND keyed merge in ONE persistent kernel (K6 + K7, the fused variant).
+// pair_fused.cu — candidate-pair generation AND keyed merge in ONE persistent kernel (K6 + K7, the product variant).
 //
 // Replaces MatchMap::calculateEdges / processScaffold (MatchMap.cpp:161-224) + Graph::addEdge (Graph.cpp:212-230,
 // 291-311) + MatchMap::addEdgeMatch (MatchMap.cpp:109-134).
 //
-// The sort-based variant (pair_sort.cu) writes every candidate to HBM in unitig order and then moves it through
-// 4-6 radix passes; at yeast scale that is ~250 B of HBM traffic per edge match for 25 B of result.  Here the work is
-// turned around so that the output is produced directly in its final order and touched once:
+// The reference walks every unitig group and throws each accepted pair at two global hash maps.  The sort-based
+// variant (pair_sort.cu) writes every candidate to HBM in unitig order and moves it through 4-6 radix passes: ~250 B
+// of HBM traffic per edge match for 25 B of result.  Here the work is turned around so that every output row is
+// produced directly at its final position and touches HBM once:
 //
-//   * the reduction key is (first, second) with first < second.  All candidates of ONE read r as `first` come from
-//     the unitig groups r belongs to; so a CTA that owns a run of consecutive reads (a "tile") can enumerate, in
-//     shared memory, every candidate those reads own: for each match a of r (its unitig u), every other member b of
-//     u's group with read(b) > r and unitig overlap > 100 (MatchMap.cpp:189-192).
-//   * the tile's candidates (<= 4096) are sorted in shared memory by (read, second) with a stable LSD radix sort over
-//     only the significant key bits; they were generated in unitig order, so rows of one edge come out by unitig.
-//   * tiles are handed out in increasing read order by an atomic ticket, and each tile obtains the global offset of
-//     its first edge match and of its first edge with a decoupled look-back over per-tile status words (aggregate
-//     published as soon as it is known, inclusive prefix after the look-back).  The kernel therefore writes the
-//     edge-match columns, the edge table and its CSR offsets exactly once, coalesced, already in (first, second,
-//     unitig) order: algorithmic traffic = every match record read once + 25 B per edge match + 16 B per edge.
+//   * The reduction key is (first, second), first < second (read ids; MatchMap.cpp:204-213).  Call the edge matches
+//     whose `first` is read r "row r".  Row r is the union, over the matches a of r (its "sources", one per unitig),
+//     of the members b of a's unitig group with read(b) > r and unitig overlap > 100 (MatchMap.cpp:189-192).
+//   * A pre-pass re-orders every unitig group by read id (rank by counting inside the group).  Then the partners of a
+//     source are exactly the SUFFIX of its group behind it, already sorted by `second`, and sum(suffix lengths) is
+//     exactly the number of candidate pairs sum k(k-1)/2.
+//   * Rows are cut into tiles of <= 4096 candidates.  Light rows are packed, several consecutive rows per tile.  A row
+//     heavier than a tile (a read that crosses a high-multiplicity repeat) is split into sub-tiles by VALUE RANGES of
+//     `second`: the boundaries are found by bisection on the merged rank over the row's sorted suffixes, so every
+//     sub-tile is bounded, no edge straddles two sub-tiles and the sub-tiles of a row are in output order.
+//   * One CTA per tile (persistent, tiles handed out in order by an atomic ticket): stage the sources, enumerate the
+//     candidates into shared memory, radix-sort them there by (row, second) — stable, and candidates are generated in
+//     unitig order, so rows of one edge come out by unitig — find the run heads (= edges), obtain the global offsets
+//     of the tile's first edge match and first edge by a decoupled look-back over per-tile status words, then compute
+//     and write each edge match, each edge and its CSR offset exactly once, coalesced, in (first, second, unitig) order.
 //
-// A small pre-pass builds what the tiles need: per read the list of its matches (unitig order), and tile boundaries
-// such that a tile never holds more than kTileCap candidates / kSrcCap matches.  Reads too heavy for one tile
-// (thousands of partners: high-multiplicity repeats) make the caller fall back to the sort-based variant.
+// Algorithmic HBM traffic = every match record once + 25 B per edge match + 16 B per edge.  The k^2 work never leaves
+// the SM.  The same kernel serves multi-GPU runs: a rank processes a contiguous range of tiles, so its output is a
+// contiguous slice of the global (first, second)-sorted result and no candidate ever crosses NVLink.
 #include <cstdlib>
 #include <string>
 
@@ -35,297 +40,569 @@ constexpr int kThOverlapF = 100; // MatchMap.cpp:41
 
 constexpr int      kFusedBlock = 256;
 constexpr int      kFusedWarps = kFusedBlock / 32;
-constexpr int      kTileCap    = 4096; // candidates per tile
-constexpr int      kSrcCap     = 1024; // matches ("sources") per tile
-constexpr int      kSrcRatio   = (kTileCap / 2) / (kSrcCap / 2);
-constexpr uint32_t kMinWeight  = (kTileCap / 2) / 128; // caps a tile at 256 reads
+constexpr int      kIdxBits    = 12;
+constexpr uint32_t kTileCap    = 1u << kIdxBits; // candidates per tile
+constexpr uint32_t kSrcCap     = 512;            // sources per tile
 constexpr uint32_t kHalfCap    = kTileCap / 2;
+constexpr uint32_t kSrcRatio   = kHalfCap / (kSrcCap / 2); // a source weighs at least this much when tiles are packed
+constexpr int      kItems      = kTileCap / kFusedBlock;   // sort items per thread
+
+// One match, as the pairing kernel gathers it (32 bytes = one L2 sector).  Rows are grouped by unitig and ordered by
+// read id inside a unitig.
+struct __align__(16) PairRow {
+  int32_t  ir0, ir1; // illuminaRange (inclusive)
+  uint32_t read;
+  int32_t  score;
+  uint32_t line, flags, unitig, pad;
+};
 
 // ---------------------------------------------------------------------------------------------------------------------
-// pre-pass
+// pre-pass 1: order every group by read id, build the pair rows, and accumulate per read its number of sources and
+// its number of candidates
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    read_stats_kernel(const uint32_t *__restrict__ unitig, const uint32_t *__restrict__ read,
-                      const uint32_t *__restrict__ grp_off, uint64_t n, uint32_t *__restrict__ deg,
-                      unsigned long long *__restrict__ ub) {
-  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
-    uint32_t u = unitig[i];
-    uint32_t k = grp_off[u + 1] - grp_off[u];
-    if (k >= 2) { // a match alone in its group has no partner (MatchMap.cpp:185: the outer loop starts at the 2nd)
-      atomicAdd(&deg[read[i]], 1u);
-      atomicAdd(&ub[read[i]], (unsigned long long)(k - 1));
+    rank_rows_kernel(MatchSoA m, const uint32_t *__restrict__ grp_off, PairRow *__restrict__ rows,
+                     uint32_t *__restrict__ p_read, int32_t *__restrict__ p_ir0, int32_t *__restrict__ p_ir1,
+                     uint32_t *__restrict__ deg, unsigned long long *__restrict__ wgt) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t u = m.unitig[i], g0 = grp_off[u], g1 = grp_off[u + 1], my = m.read[i];
+    // reads are unique inside a group (MatchMap.cpp:64-73 keeps one match per (read, unitig)), so the rank is exact
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, j = g0;
+    for (; j + 4 <= g1; j += 4) {
+      r0 += m.read[j] < my;
+      r1 += m.read[j + 1] < my;
+      r2 += m.read[j + 2] < my;
+      r3 += m.read[j + 3] < my;
+    }
+    for (; j < g1; ++j) r0 += m.read[j] < my;
+    const uint32_t q = g0 + r0 + r1 + r2 + r3;
+    PairRow        row;
+    row.ir0    = m.ir0[i];
+    row.ir1    = m.ir1[i];
+    row.read   = my;
+    row.score  = m.score[i];
+    row.line   = m.line[i];
+    row.flags  = m.flags[i];
+    row.unitig = u;
+    row.pad    = 0;
+    rows[q]    = row;
+    p_read[q]  = my;
+    p_ir0[q]   = row.ir0;
+    p_ir1[q]   = row.ir1;
+    const uint32_t len = g1 - q - 1; // partners = the members behind q
+    if (len) {
+      atomicAdd(&deg[my], 1u);
+      atomicAdd(&wgt[my], (unsigned long long)len);
     }
   }
 }
 
+// pre-pass 2: per read the list of its sources (positions in the pair rows), in unitig order
 __global__ void __launch_bounds__(256)
-    scatter_sources_kernel(const uint32_t *__restrict__ unitig, const uint32_t *__restrict__ read,
+    scatter_sources_kernel(const uint32_t *__restrict__ p_read, const PairRow *__restrict__ rows,
                            const uint32_t *__restrict__ grp_off, uint64_t n, const uint32_t *__restrict__ rd_off,
                            uint32_t *__restrict__ cursor, uint32_t *__restrict__ rd_tmp) {
-  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
-    uint32_t u = unitig[i];
-    if (grp_off[u + 1] - grp_off[u] >= 2) {
-      uint32_t r               = read[i];
-      rd_tmp[rd_off[r] + atomicAdd(&cursor[r], 1u)] = uint32_t(i);
+  for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < n; q += uint64_t(gridDim.x) * blockDim.x) {
+    if (grp_off[rows[q].unitig + 1] - uint32_t(q) - 1 > 0) {
+      uint32_t r                                    = p_read[q];
+      rd_tmp[rd_off[r] + atomicAdd(&cursor[r], 1u)] = uint32_t(q);
     }
   }
 }
 
-// the atomics above leave a read's list in arbitrary order: rank-sort it (lists are short) so that it is in match
-// order = unitig order, which makes the candidate stream of a tile deterministic
+// the atomics above leave a read's list in arbitrary order: rank-sort it (lists are short) so that it is in row order
+// = unitig order, which makes the candidate stream of a tile deterministic
 __global__ void __launch_bounds__(256)
-    order_sources_kernel(const uint32_t *__restrict__ read, const uint32_t *__restrict__ rd_off,
+    order_sources_kernel(const uint32_t *__restrict__ p_read, const uint32_t *__restrict__ rd_off,
                          const uint32_t *__restrict__ rd_tmp, uint64_t n_src, uint32_t *__restrict__ rd_src) {
-  for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < n_src;
-       q += uint64_t(gridDim.x) * blockDim.x) {
-    uint32_t me = rd_tmp[q];
-    uint32_t r  = read[me];
+  for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < n_src;
+       x += uint64_t(gridDim.x) * blockDim.x) {
+    uint32_t me = rd_tmp[x];
+    uint32_t r  = p_read[me];
     uint32_t lo = rd_off[r], hi = rd_off[r + 1], rank = 0;
     for (uint32_t p = lo; p < hi; ++p) rank += rd_tmp[p] < me;
     rd_src[lo + rank] = me;
   }
 }
 
-struct TileWeight { // weight of a read when tiles are formed; clipped so that any run of reads < one tile
+// ---------------------------------------------------------------------------------------------------------------------
+// tile planning
+// ---------------------------------------------------------------------------------------------------------------------
+struct RowPlan {
   const uint32_t           *deg;
-  const unsigned long long *ub;
-  __device__ uint64_t raw(uint64_t r) const {
-    uint64_t w = ub[r], d = uint64_t(deg[r]) * kSrcRatio;
-    w          = w > d ? w : d;
-    return w > kMinWeight ? w : kMinWeight;
+  const unsigned long long *wgt;
+  __device__ uint64_t weight(uint64_t r) const { // what a light row costs a tile
+    uint64_t w = wgt[r], d = uint64_t(deg[r]) * kSrcRatio;
+    return w > d ? w : d;
   }
-  __device__ uint64_t operator()(uint64_t r) const {
-    uint64_t w = raw(r);
-    return w > kHalfCap ? kHalfCap : w;
+  __device__ bool     heavy(uint64_t r) const { return weight(r) > kHalfCap; }
+  __device__ uint32_t sub_cap(uint64_t r) const { return kTileCap - deg[r]; } // see split_heavy_kernel
+  __device__ uint32_t n_sub(uint64_t r) const {
+    uint64_t t = sub_cap(r);
+    uint64_t n = (wgt[r] + t - 1) / t;
+    return uint32_t(n ? n : 1);
   }
 };
 
-struct TileStart { // 1 where a tile begins: quotient of the weight prefix changes, or a heavy read is involved
-  TileWeight      w;
+struct ClippedWeight {
+  RowPlan p;
+  __device__ uint64_t operator()(uint64_t r) const { return p.heavy(r) ? uint64_t(kHalfCap) : p.weight(r); }
+};
+
+// tiles that start at row r: 1 where a packed tile begins, n_sub for a heavy row
+struct TileCount {
+  RowPlan         p;
   const uint64_t *prefix;
-  __device__ uint32_t operator()(uint64_t r) const {
-    if (r == 0) return 1u;
-    if (prefix[r] / kHalfCap != prefix[r - 1] / kHalfCap) return 1u;
-    return (w.raw(r) > kHalfCap || w.raw(r - 1) > kHalfCap) ? 1u : 0u;
+  __device__ bool start(uint64_t r) const {
+    if (r == 0) return true;
+    if (prefix[r] / kHalfCap != prefix[r - 1] / kHalfCap) return true;
+    return p.heavy(r - 1);
   }
+  __device__ uint32_t operator()(uint64_t r) const { return p.heavy(r) ? p.n_sub(r) : (start(r) ? 1u : 0u); }
+};
+
+// slice table entries of a heavy row: (n_sub + 1) boundaries x deg sources
+struct SliceCount {
+  RowPlan p;
+  __device__ uint64_t operator()(uint64_t r) const {
+    return p.heavy(r) ? uint64_t(p.n_sub(r) + 1) * p.deg[r] : 0ull;
+  }
+};
+
+struct WeightOf {
+  const unsigned long long *wgt;
+  __device__ uint64_t operator()(uint64_t r) const { return wgt[r]; }
 };
 
 __global__ void __launch_bounds__(256)
-    write_tiles_kernel(TileStart start, const uint32_t *__restrict__ tile_rank, uint64_t n_reads,
-                       const uint32_t *n_tiles, uint32_t *__restrict__ tile_first, uint32_t *__restrict__ n_heavy) {
+    write_tiles_kernel(TileCount tc, const uint32_t *__restrict__ tile_idx, uint64_t n_reads, uint32_t n_tiles,
+                       uint32_t *__restrict__ tile_row, uint32_t *__restrict__ tile_kind,
+                       uint32_t *__restrict__ too_many_sources) {
   for (uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n_reads;
        r += uint64_t(gridDim.x) * blockDim.x) {
-    if (start(r)) tile_first[tile_rank[r]] = uint32_t(r);
-    if (start.w.raw(r) > kHalfCap) atomicAdd(n_heavy, 1u);
+    if (tc.p.deg[r] > kSrcCap) *too_many_sources = 1;
+    uint32_t t = tile_idx[r];
+    if (tc.p.heavy(r)) {
+      uint32_t ns = tc.p.n_sub(r);
+      for (uint32_t j = 0; j < ns; ++j) {
+        tile_row[t + j]  = uint32_t(r);
+        tile_kind[t + j] = 1 + j;
+      }
+    } else if (tc.start(r)) {
+      tile_row[t]  = uint32_t(r);
+      tile_kind[t] = 0;
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) tile_first[*n_tiles] = uint32_t(n_reads);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    tile_row[n_tiles]  = uint32_t(n_reads);
+    tile_kind[n_tiles] = 0;
+  }
+}
+
+// first position in [lo, hi) of the ascending array whose value is >= s
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi,
+                                                    uint32_t s) {
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < s) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Heavy rows: one warp per sub-tile finds the value s_j that starts the sub-tile, the largest s with
+//   C(s) := #{candidates of the row with second < s}  <=  j * T,   T = kTileCap - deg,
+// by bisection over s (C is monotone; every source suffix is sorted by read id, so C is a sum of lower bounds).  One
+// value of `second` occurs at most once per source, so C jumps by <= deg and sub-tile j = [s_j, s_j+1) holds fewer
+// than T + deg = kTileCap candidates.  Written out: for every source the row position where each sub-tile begins.
+__global__ void __launch_bounds__(256)
+    split_heavy_kernel(const uint32_t *__restrict__ tile_row, const uint32_t *__restrict__ tile_kind, uint32_t n_tiles,
+                       RowPlan plan, const uint64_t *__restrict__ slice_off, const uint32_t *__restrict__ rd_off,
+                       const uint32_t *__restrict__ rd_src, const PairRow *__restrict__ rows,
+                       const uint32_t *__restrict__ grp_off, const uint32_t *__restrict__ p_read, uint32_t n_reads,
+                       uint32_t *__restrict__ slices) {
+  const unsigned l  = threadIdx.x & 31;
+  uint64_t       wi = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  for (; wi < n_tiles; wi += nw) {
+    const uint32_t kind = tile_kind[wi];
+    if (kind == 0) continue;
+    const uint32_t r = tile_row[wi], j = kind - 1, d = plan.deg[r], ns = plan.n_sub(r);
+    if (d > kSrcCap) continue; // reported by write_tiles_kernel; the build fails with MSGPU_ERR_LIMIT
+    const uint32_t q0 = rd_off[r];
+    uint32_t      *out = slices + slice_off[r];
+    const uint64_t target = uint64_t(j) * plan.sub_cap(r);
+    // bisection: largest s in [0, n_reads] with C(s) <= target
+    uint32_t lo = 0, hi = n_reads; // invariant: C(lo) <= target
+    while (lo < hi) {
+      uint32_t mid = lo + ((hi - lo + 1) >> 1);
+      uint64_t c   = 0;
+      for (uint32_t a = l; a < d; a += 32) {
+        uint32_t q = rd_src[q0 + a], b = q + 1, e = grp_off[rows[q].unitig + 1];
+        c += lower_bound_u32(p_read, b, e, mid) - b;
+      }
+      c = warp_reduce_sum(c);
+      if (c <= target) lo = mid; else hi = mid - 1;
+    }
+    for (uint32_t a = l; a < d; a += 32) {
+      uint32_t q = rd_src[q0 + a], b = q + 1, e = grp_off[rows[q].unitig + 1];
+      out[uint64_t(j) * d + a] = j == 0 ? b : lower_bound_u32(p_read, b, e, lo);
+      if (j == ns - 1) out[uint64_t(ns) * d + a] = e;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // the fused kernel
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr unsigned long long kStAggregate = 1ull << 62, kStPrefix = 2ull << 62, kStMask = (1ull << 62) - 1;
+constexpr uint16_t           kNoSource    = 0xffffu; // candidate failed the overlap test
 
 struct FusedArgs {
-  MatchSoA        m;
+  const PairRow  *rows;
+  const uint32_t *p_read;
+  const int32_t  *p_ir0, *p_ir1;
   const uint32_t *grp_off;
-  const uint32_t *rd_off, *rd_src, *tile_first;
-  uint32_t        n_tiles;
+  const uint32_t *rd_off, *rd_src;
+  const uint32_t *tile_row, *tile_kind;
+  const uint64_t *slice_off;
+  const uint32_t *slices;
+  uint32_t        tile_lo, tile_hi; // this launch processes tiles [tile_lo, tile_hi)
   unsigned int   *ticket;
-  volatile unsigned long long *st_em, *st_edge; // per tile: flag (2 bits) | value
-  unsigned long long *totals;                   // [0] = edge matches, [1] = edges, [2] = error flag
+  unsigned long long *st_em, *st_edge; // per tile: flag (2 bits) | value
+  unsigned long long *totals;          // [0] = edge matches, [1] = edges, [2] = error code
   EdgeTables      out;
 };
 
-struct FusedSmem {
-  uint32_t keyA[kTileCap], keyB[kTileCap];
-  uint32_t ent_ib[kTileCap];
-  uint16_t idxA[kTileCap], idxB[kTileCap];
-  uint16_t ent_j[kTileCap];
-  uint32_t src_ia[kSrcCap], src_base[kSrcCap];
-  uint32_t warp_cnt[kFusedWarps][256];
-  uint32_t bin_base[256], chunk_base[256];
-  uint32_t scan[33];
-  uint32_t tile, n_ent, n_heads, smin, smax;
-  unsigned long long em_base, edge_base;
+struct SrcStage { // the sources of the tile, staged in shared memory (structure of arrays)
+  uint32_t begin[kSrcCap];    // first partner row
+  uint32_t base[kSrcCap + 1]; // exclusive prefix of the slice lengths = first candidate slot
+  int32_t  ir0[kSrcCap], ir1[kSrcCap], score[kSrcCap];
+  uint32_t line[kSrcCap], read[kSrcCap], unitig[kSrcCap];
+  uint16_t row_local[kSrcCap]; // dense rank of the source's read inside the tile
+  uint8_t  flags[kSrcCap];
 };
 
-__device__ __forceinline__ bool overlaps(int a0, int a1, int b0, int b1) {
-  int o0 = a0 > b0 ? a0 : b0, o1 = a1 < b1 ? a1 : b1;
-  return o0 <= o1 && o1 - o0 > kThOverlapF; // MatchMap.cpp:192
+struct FusedShared { // everything but the two sort buffers, which follow it in dynamic shared memory
+  uint16_t ent_j[kTileCap]; // candidate slot -> source (kNoSource: failed the overlap test)
+  SrcStage src;
+  uint32_t warp_cnt[kFusedWarps][256];
+  uint32_t bin_base[256];
+  uint32_t scan[33];
+  uint32_t tile, smin, smax, n_invalid;
+  unsigned long long em_base, edge_base;
+};
+constexpr size_t kSharedOff  = (sizeof(FusedShared) + 15) & ~size_t(15);
+constexpr size_t kFusedBytes = kSharedOff + 2 * kTileCap * sizeof(unsigned long long);
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// stable LSD radix sort of n (key, idx) pairs in shared memory over key bits [0, nbits); returns true if the result
-// is in the B buffers.  blockDim.x == 256.
-__device__ bool cta_radix_sort(FusedSmem &s, uint32_t n, int nbits) {
-  const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
-  uint32_t      *kin = s.keyA, *kout = s.keyB;
-  uint16_t      *iin = s.idxA, *iout = s.idxB;
-  bool           in_b = false;
-  for (int shift = 0; shift < nbits; shift += 8) {
-    const unsigned mask = nbits - shift >= 8 ? 255u : ((1u << (nbits - shift)) - 1u);
-    s.bin_base[t] = 0;
-    __syncthreads();
-    for (uint32_t e = t; e < n; e += kFusedBlock) atomicAdd(&s.bin_base[(kin[e] >> shift) & mask], 1u);
-    __syncthreads();
-    uint32_t total;
-    uint32_t ex   = block_exclusive_scan<uint32_t>(s.bin_base[t], s.scan, &total);
-    s.bin_base[t] = ex;
-    for (uint32_t c0 = 0; c0 < n; c0 += kFusedBlock) {
-#pragma unroll
-      for (int ww = 0; ww < kFusedWarps; ++ww) s.warp_cnt[ww][t] = 0;
-      __syncthreads();
-      uint32_t e     = c0 + t;
-      bool     valid = e < n;
-      uint32_t key   = valid ? kin[e] : 0u;
-      uint16_t idx   = valid ? iin[e] : uint16_t(0);
-      unsigned d     = valid ? ((key >> shift) & mask) : 256u;
-      unsigned peers = __match_any_sync(0xffffffffu, d);
-      unsigned rank  = __popc(peers & ((1u << l) - 1u));
-      if (valid && rank == 0) s.warp_cnt[w][d] = __popc(peers);
-      __syncthreads();
-      {
-        uint32_t sum = 0;
-#pragma unroll
-        for (int ww = 0; ww < kFusedWarps; ++ww) {
-          uint32_t c        = s.warp_cnt[ww][t];
-          s.warp_cnt[ww][t] = sum;
-          sum += c;
-        }
-        s.chunk_base[t] = s.bin_base[t];
-        s.bin_base[t] += sum;
-      }
-      __syncthreads();
-      if (valid) {
-        uint32_t dst = s.chunk_base[d] + s.warp_cnt[w][d] + rank;
-        kout[dst]    = key;
-        iout[dst]    = idx;
-      }
-      __syncthreads();
-    }
-    uint32_t *tk = kin;
-    kin          = kout;
-    kout         = tk;
-    uint16_t *ti = iin;
-    iin          = iout;
-    iout         = ti;
-    in_b         = !in_b;
-  }
-  return in_b;
-}
-
-__device__ __forceinline__ void publish(volatile unsigned long long *st, uint32_t tile, unsigned long long flag,
-                                        unsigned long long v) {
-  st[tile] = flag | v;
-}
-
-// decoupled look-back: exclusive prefix of this tile's value; then the inclusive prefix is published
-__device__ unsigned long long look_back(volatile unsigned long long *st, uint32_t tile, unsigned long long mine) {
+// Decoupled look-back by ONE WARP: exclusive prefix over the tiles before `idx` (status index); then the tile's
+// inclusive prefix is published.  A status word carries flag and value together, so no fence is needed.
+__device__ unsigned long long look_back(unsigned long long *st, uint32_t idx, unsigned long long mine) {
+  const unsigned     l    = threadIdx.x & 31;
   unsigned long long excl = 0;
-  for (int64_t t = int64_t(tile) - 1; t >= 0; --t) {
-    unsigned long long v;
-    do {
-      v = st[t];
-    } while ((v >> 62) == 0);
-    excl += v & kStMask;
-    if ((v >> 62) == 2) break;
+  int64_t            top  = int64_t(idx) - 1; // newest predecessor not yet summed
+  while (top >= 0) {
+    int64_t            t = top - l;
+    unsigned long long v = kStPrefix; // lanes past the beginning count as an (empty) inclusive prefix
+    if (t >= 0) {
+      do {
+        v = ld_status(st + t);
+      } while ((v >> 62) == 0);
+    }
+    unsigned pref = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+    unsigned stop = pref ? unsigned(__ffs(pref) - 1) : 32u; // first lane (newest tile) holding an inclusive prefix
+    unsigned long long add = l <= stop ? (v & kStMask) : 0ull;
+    excl += warp_reduce_sum(add);
+    if (pref) break;
+    top -= 32;
   }
-  __threadfence();
-  st[tile] = kStPrefix | (excl + mine);
+  if (l == 0) st_status(st + idx, kStPrefix | (excl + mine));
   return excl;
+}
+
+// Stable LSD radix sort of n words in shared memory on bits [lo, hi); warp w owns a contiguous block of items and
+// ranks it with __match_any_sync + per-warp digit counters, so equal digits keep their order.  Returns the buffer
+// that holds the result.  blockDim.x == 256.
+template <class W> __device__ W *cta_radix_sort(FusedShared &s, W *in, W *out, uint32_t n, int lo, int hi) {
+  const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
+  const int      kb = hi - lo;
+  if (kb <= 0 || n <= 1) return in;
+  const int      n_pass = (kb + 7) / 8, bits = (kb + n_pass - 1) / n_pass;
+  const uint32_t per    = (n + kFusedBlock - 1) / kFusedBlock; // items per thread in this tile
+  const uint32_t wbase  = w * per * 32;
+  for (int shift = lo; shift < hi; shift += bits) {
+    const int      b    = hi - shift < bits ? hi - shift : bits;
+    const unsigned mask = (1u << b) - 1u;
+#pragma unroll
+    for (int ww = 0; ww < kFusedWarps; ++ww) s.warp_cnt[ww][t] = 0;
+    __syncthreads();
+    W        word[kItems];
+    uint16_t rank[kItems];
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      if (uint32_t(it) < per) {
+        uint32_t idx   = wbase + it * 32 + l;
+        bool     valid = idx < n;
+        W        x     = valid ? in[idx] : W(0);
+        unsigned d     = valid ? (unsigned(x >> shift) & mask) : 256u; // lanes past the end form their own group
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned lead  = __ffs(peers) - 1;
+        uint32_t old   = 0;
+        if (l == lead && valid) {
+          old              = s.warp_cnt[w][d];
+          s.warp_cnt[w][d] = old + __popc(peers);
+        }
+        old      = __shfl_sync(0xffffffffu, old, lead);
+        word[it] = x;
+        rank[it] = uint16_t(old + __popc(peers & ((1u << l) - 1u)));
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    { // digit t: exclusive prefix over the warps, then over the digits
+      uint32_t sum = 0;
+#pragma unroll
+      for (int ww = 0; ww < kFusedWarps; ++ww) {
+        uint32_t c        = s.warp_cnt[ww][t];
+        s.warp_cnt[ww][t] = sum;
+        sum += c;
+      }
+      uint32_t total;
+      uint32_t ex   = block_exclusive_scan<uint32_t>(sum, s.scan, &total);
+      s.bin_base[t] = ex;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      if (uint32_t(it) < per) {
+        uint32_t idx = wbase + it * 32 + l;
+        if (idx < n) {
+          unsigned d = unsigned(word[it] >> shift) & mask;
+          out[s.bin_base[d] + s.warp_cnt[w][d] + rank[it]] = word[it];
+        }
+      }
+    }
+    __syncthreads();
+    W *tmp = in;
+    in     = out;
+    out    = tmp;
+  }
+  return in;
+}
+
+// S2-S5 of a tile, for sort words of type W (32 bits when row + second + slot fit, else 64)
+template <class W>
+__device__ __forceinline__ void tile_tail(const FusedArgs &a, FusedShared &s, W *wa, W *wb, uint32_t tile,
+                                          uint32_t st_idx, uint32_t n_src, uint32_t n_ent, int sb, int rb) {
+  const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
+  const uint32_t smin = s.smin;
+
+  // ---- S2: materialise the candidates in generation order (source by source = unitig order inside a row)
+  {
+    uint32_t n_bad = 0;
+    for (uint32_t e = t; e < n_ent; e += kFusedBlock) {
+      uint32_t lo = 0, hi = n_src; // last source with base <= e (empty slices share their base with the next one)
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (s.src.base[mid] <= e) lo = mid; else hi = mid;
+      }
+      const uint32_t j  = lo;
+      const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
+      const uint32_t sr = a.p_read[ib];
+      const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = a.p_ir0[ib], b1 = a.p_ir1[ib];
+      const int      o0 = a0 > b0 ? a0 : b0, o1 = a1 < b1 ? a1 : b1;
+      const bool     keep = o0 <= o1 && o1 - o0 > kThOverlapF; // MatchMap.cpp:192
+      const W        key  = (W(s.src.row_local[j]) << sb) | W(sr - smin);
+      wa[e]               = (key << kIdxBits) | W(e);
+      s.ent_j[e]          = keep ? uint16_t(j) : kNoSource;
+      n_bad += keep ? 0u : 1u;
+    }
+    n_bad = warp_reduce_sum(n_bad);
+    if (l == 0 && n_bad) atomicAdd(&s.n_invalid, n_bad);
+  }
+  __syncthreads();
+  const uint32_t n_valid = n_ent - s.n_invalid;
+  if (t == 0) st_status(a.st_em + st_idx, (st_idx == 0 ? kStPrefix : kStAggregate) | n_valid);
+
+  // ---- S3: sort by (row, second); generation order (= unitig order) breaks ties because the sort is stable
+  W        *sorted = cta_radix_sort<W>(s, wa, wb, n_ent, kIdxBits, kIdxBits + sb + rb);
+  uint32_t *pre    = reinterpret_cast<uint32_t *>(sorted == wa ? wb : wa);
+
+  // ---- S4: run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the
+  // key of its pair) but is skipped; the head of a run is its first surviving candidate.
+  // pre[k] = surviving rows before k (bits 0-15) | heads before k (bits 16-28) | survives (bit 30) | head (bit 31)
+  uint32_t carry = 0;
+  for (uint32_t c0 = 0; c0 < n_ent; c0 += kFusedBlock) {
+    const uint32_t k = c0 + t;
+    uint32_t       v = 0, fl = 0;
+    if (k < n_ent) {
+      const W x = sorted[k];
+      if (s.ent_j[uint32_t(x) & (kTileCap - 1)] != kNoSource) {
+        bool    head = true;
+        const W key  = x >> kIdxBits;
+        for (uint32_t p = k; p > 0;) {
+          --p;
+          const W y = sorted[p];
+          if ((y >> kIdxBits) != key) break;
+          if (s.ent_j[uint32_t(y) & (kTileCap - 1)] != kNoSource) {
+            head = false;
+            break;
+          }
+        }
+        v  = 1u | (head ? 0x10000u : 0u);
+        fl = (1u << 30) | (head ? (1u << 31) : 0u);
+      }
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan<uint32_t>(v, s.scan, &total);
+    if (k < n_ent) pre[k] = (carry + ex) | fl;
+    carry += total;
+  }
+  const uint32_t n_heads = carry >> 16;
+  if (w == 0) {
+    unsigned long long eb = look_back(a.st_em, st_idx, n_valid);
+    if (l == 0) s.em_base = eb;
+  } else if (w == 1) {
+    if (l == 0 && st_idx != 0) st_status(a.st_edge + st_idx, kStAggregate | n_heads);
+    unsigned long long eb = look_back(a.st_edge, st_idx, n_heads);
+    if (l == 0) s.edge_base = eb;
+  }
+  __syncthreads();
+  const unsigned long long em_base = s.em_base, edge_base = s.edge_base;
+
+  // ---- S5: compute and write each row once, in final order
+  for (uint32_t k = t; k < n_ent; k += kFusedBlock) {
+    const uint32_t pv = pre[k];
+    if (!(pv & (1u << 30))) continue;
+    const uint32_t e  = uint32_t(sorted[k]) & (kTileCap - 1);
+    const uint32_t j  = s.ent_j[e];
+    const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
+    const PairRow  pb = a.rows[ib];
+    const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = pb.ir0, b1 = pb.ir1;
+    const int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
+    // MatchMap.cpp:195-202: score_x * common / len_x for the outer and the inner match, summed.  IEEE addition is
+    // commutative, so which of the two is "outer" (the later line) does not change the sum.  No FMA contraction.
+    const double   common = double(ov1 - ov0 + 1);
+    const double   sa     = double((unsigned long long)(long long)s.src.score[j]); // size_t widened from int
+    const double   sbb    = double((unsigned long long)(long long)pb.score);
+    const double   sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
+    const double   sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
+    const uint32_t la = s.src.line[j], lb = pb.line;
+    const uint32_t fa = s.src.flags[j], fb = pb.flags;
+    const unsigned long long o = em_base + (pv & 0xffffu);
+    a.out.em_unitig[o] = s.src.unitig[j];
+    a.out.em_ov0[o]    = ov0;
+    a.out.em_ov1[o]    = ov1;
+    a.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
+    a.out.em_line[o]   = la > lb ? la : lb; // the outer match is the one on the later line (MatchMap.cpp:218)
+    a.out.em_flags[o]  = uint8_t((((fa ^ fb) & 1u) ? 0u : 1u) | ((fa & fb & 2u) ? 2u : 0u));
+    if (pv >> 31) {
+      const unsigned long long eo = edge_base + ((pv >> 16) & 0x1fffu);
+      a.out.first[eo]    = s.src.read[j];
+      a.out.second[eo]   = pb.read;
+      a.out.em_begin[eo] = o;
+    }
+  }
+  if (tile == a.tile_hi - 1 && t == 0) { // the last tile closes the CSR and reports the totals
+    a.out.em_begin[edge_base + n_heads] = em_base + n_valid;
+    a.totals[0]                         = em_base + n_valid;
+    a.totals[1]                         = edge_base + n_heads;
+  }
 }
 
 __global__ void __launch_bounds__(kFusedBlock, 2) pair_fused_kernel(FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FusedSmem     &s = *reinterpret_cast<FusedSmem *>(smem_raw);
+  FusedShared   &s = *reinterpret_cast<FusedShared *>(smem_raw);
   const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
-  const MatchSoA &m = a.m;
 
   for (;;) {
     __syncthreads(); // previous tile fully done with shared memory
     if (t == 0) {
-      s.tile = atomicAdd(a.ticket, 1u);
-      s.smin = 0xffffffffu;
-      s.smax = 0;
+      s.tile      = a.tile_lo + atomicAdd(a.ticket, 1u);
+      s.smin      = 0xffffffffu;
+      s.smax      = 0;
+      s.n_invalid = 0;
     }
     __syncthreads();
     const uint32_t tile = s.tile;
-    if (tile >= a.n_tiles) break;
-    const uint32_t r0 = a.tile_first[tile], r1 = a.tile_first[tile + 1];
-    const uint32_t q0 = a.rd_off[r0], n_src = a.rd_off[r1] - q0;
-    // a tile that violates its capacity invariant (cannot happen: tile weights) reports the error, contributes
-    // nothing, keeps the look-back chain alive and never touches memory out of bounds
+    if (tile >= a.tile_hi) break;
+    const uint32_t st_idx = tile - a.tile_lo;
+    const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
+    const uint32_t q0 = a.rd_off[r0];
+    const uint32_t n_src = (kind ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
+
+    // a tile that violates its capacity invariant (cannot happen: see the planning kernels) reports the error,
+    // contributes nothing, keeps the look-back chain alive and never touches memory out of bounds
     auto bail = [&](unsigned long long code) {
-      if (t == 0) {
-        a.totals[2] = code;
-        publish(a.st_em, tile, tile == 0 ? kStPrefix : kStAggregate, 0);
-        publish(a.st_edge, tile, tile == 0 ? kStPrefix : kStAggregate, 0);
-        if (tile) {
-          look_back(a.st_em, tile, 0);
-          look_back(a.st_edge, tile, 0);
-        }
+      if (w == 0) {
+        if (l == 0) a.totals[2] = code;
+        look_back(a.st_em, st_idx, 0);
+        look_back(a.st_edge, st_idx, 0);
       }
     };
-    if (n_src > uint32_t(kSrcCap)) {
+    if (n_src > kSrcCap) {
       bail(1);
       continue;
     }
-    for (uint32_t q = t; q < n_src; q += kFusedBlock) s.src_ia[q] = a.rd_src[q0 + q];
-    __syncthreads();
 
-    // ---- phase 1: how many candidates does each source own?  (one warp per source, lanes over the group)
-    for (uint32_t j = w; j < n_src; j += kFusedWarps) {
-      uint32_t ia = s.src_ia[j];
-      uint32_t u  = m.unitig[ia], r = m.read[ia];
-      int      a0 = m.ir0[ia], a1 = m.ir1[ia];
-      uint32_t g0 = a.grp_off[u], g1 = a.grp_off[u + 1], cnt = 0;
-      for (uint32_t b = g0; b < g1; b += 32) {
-        uint32_t ib   = b + l;
-        bool     keep = ib < g1 && m.read[ib] > r && overlaps(a0, a1, m.ir0[ib], m.ir1[ib]);
-        cnt += __popc(__ballot_sync(0xffffffffu, keep));
-      }
-      if (l == 0) s.src_base[j] = cnt;
-    }
-    __syncthreads();
-    uint32_t carry = 0;
-    for (uint32_t c0 = 0; c0 < n_src; c0 += kFusedBlock) { // exclusive scan of the per-source counts
-      uint32_t j = c0 + t, v = j < n_src ? s.src_base[j] : 0u, total;
-      uint32_t ex = block_exclusive_scan<uint32_t>(v, s.scan, &total);
-      if (j < n_src) s.src_base[j] = carry + ex;
-      carry += total;
-    }
-    const uint32_t n_ent = carry;
-    if (n_ent > uint32_t(kTileCap)) {
-      bail(2);
-      continue;
-    }
-    if (t == 0) publish(a.st_em, tile, tile == 0 ? kStPrefix : kStAggregate, n_ent);
-    __syncthreads();
-
-    // ---- phase 2: materialise the candidate list (second read, partner row, source) in generation order
+    // ---- S1: stage the sources; slice = the partners this tile takes from each source
     {
-      uint32_t lmin = 0xffffffffu, lmax = 0;
-      for (uint32_t j = w; j < n_src; j += kFusedWarps) {
-        uint32_t ia = s.src_ia[j];
-        uint32_t u  = m.unitig[ia], r = m.read[ia];
-        int      a0 = m.ir0[ia], a1 = m.ir1[ia];
-        uint32_t g0 = a.grp_off[u], g1 = a.grp_off[u + 1], base = s.src_base[j];
-        for (uint32_t b = g0; b < g1; b += 32) {
-          uint32_t ib   = b + l;
-          uint32_t sr   = ib < g1 ? m.read[ib] : 0u;
-          bool     keep = ib < g1 && sr > r && overlaps(a0, a1, m.ir0[ib], m.ir1[ib]);
-          unsigned mk   = __ballot_sync(0xffffffffu, keep);
-          if (keep) {
-            uint32_t e  = base + __popc(mk & ((1u << l) - 1u));
-            s.keyA[e]   = sr;
-            s.ent_ib[e] = ib;
-            s.ent_j[e]  = uint16_t(j);
-            lmin        = sr < lmin ? sr : lmin;
-            lmax        = sr > lmax ? sr : lmax;
-          }
-          base += __popc(mk);
-        }
+      const uint32_t *sl0 = nullptr, *sl1 = nullptr;
+      if (kind) {
+        sl0 = a.slices + a.slice_off[r0] + uint64_t(kind - 1) * n_src;
+        sl1 = sl0 + n_src;
       }
+      uint32_t lmin = 0xffffffffu, lmax = 0, carry_len = 0, carry_row = 0;
+      for (uint32_t c0 = 0; c0 < n_src; c0 += kFusedBlock) {
+        const uint32_t j = c0 + t;
+        uint32_t       len = 0, newrow = 0;
+        if (j < n_src) {
+          const uint32_t q   = a.rd_src[q0 + j];
+          const PairRow  row = a.rows[q];
+          uint32_t       b, e;
+          if (kind) {
+            b = sl0[j];
+            e = sl1[j];
+          } else {
+            b = q + 1;
+            e = a.grp_off[row.unitig + 1];
+          }
+          len             = e - b;
+          s.src.begin[j]  = b;
+          s.src.ir0[j]    = row.ir0;
+          s.src.ir1[j]    = row.ir1;
+          s.src.score[j]  = row.score;
+          s.src.line[j]   = row.line;
+          s.src.read[j]   = row.read;
+          s.src.unitig[j] = row.unitig;
+          s.src.flags[j]  = uint8_t(row.flags);
+          if (len) { // the slice is sorted by read id
+            uint32_t f = a.p_read[b], g = a.p_read[e - 1];
+            lmin       = f < lmin ? f : lmin;
+            lmax       = g > lmax ? g : lmax;
+          }
+          newrow = (j > 0 && a.p_read[a.rd_src[q0 + j - 1]] != row.read) ? 1u : 0u;
+        }
+        // slice lengths in the low half, new-row flags in the high half: a tile has < 2^16 candidates by plan, but
+        // a violated plan must not corrupt the row ranks, so the two are scanned separately when a chunk is large
+        uint32_t tot, ex = block_exclusive_scan<uint32_t>(len, s.scan, &tot);
+        uint32_t tot_row, ex_row = block_exclusive_scan<uint32_t>(newrow, s.scan, &tot_row);
+        if (j < n_src) {
+          s.src.base[j]      = carry_len + ex;
+          s.src.row_local[j] = uint16_t(carry_row + ex_row + newrow);
+        }
+        carry_len += tot;
+        carry_row += tot_row;
+      }
+      if (t == 0) s.src.base[n_src] = carry_len;
       for (int d = 16; d > 0; d >>= 1) {
         uint32_t omin = __shfl_xor_sync(0xffffffffu, lmin, d), omax = __shfl_xor_sync(0xffffffffu, lmax, d);
         lmin = omin < lmin ? omin : lmin;
@@ -337,83 +614,21 @@ __global__ void __launch_bounds__(kFusedBlock, 2) pair_fused_kernel(FusedArgs a)
       }
     }
     __syncthreads();
-
-    // ---- sort by (read, second); generation order (= unitig order) breaks ties because the sort is stable
-    bool     in_b = false;
-    int      sb   = 0;
-    uint32_t smin = s.smin;
-    if (n_ent) {
-      uint32_t range = s.smax - smin;
-      sb             = range ? 32 - __clz(range) : 0;
-      int rb         = (r1 - r0 > 1) ? 32 - __clz(r1 - r0 - 1) : 0;
-      if (sb + rb > 32) { // > 2^24 reads with a 256-read tile: outside the supported shape
-        if (t == 0) a.totals[2] = 3;
-        sb = 32 - rb;
-      }
-      for (uint32_t e = t; e < n_ent; e += kFusedBlock) {
-        uint32_t rl = m.read[s.src_ia[s.ent_j[e]]] - r0;
-        s.keyA[e]   = (sb < 32 ? (rl << sb) : 0u) | (s.keyA[e] - smin);
-        s.idxA[e]   = uint16_t(e);
-      }
-      __syncthreads();
-      in_b = cta_radix_sort(s, n_ent, sb + rb);
+    const uint32_t n_ent  = s.src.base[n_src];
+    const uint32_t n_rows = n_src ? uint32_t(s.src.row_local[n_src - 1]) + 1u : 0u;
+    if (n_ent > kTileCap) {
+      bail(2);
+      continue;
     }
-    uint32_t *key  = in_b ? s.keyB : s.keyA;
-    uint16_t *idx  = in_b ? s.idxB : s.idxA;
-    uint32_t *rank = in_b ? s.keyA : s.keyB; // the free key buffer: edge rank of every run head
-
-    // ---- run heads = edges of this tile
-    carry = 0;
-    for (uint32_t c0 = 0; c0 < n_ent; c0 += kFusedBlock) {
-      uint32_t k    = c0 + t;
-      uint32_t head = (k < n_ent && (k == 0 || key[k] != key[k - 1])) ? 1u : 0u, total;
-      uint32_t ex   = block_exclusive_scan<uint32_t>(head, s.scan, &total);
-      if (k < n_ent) rank[k] = head ? carry + ex : 0xffffffffu;
-      carry += total;
-    }
-    const uint32_t n_heads = carry;
-    if (t == 0) publish(a.st_edge, tile, tile == 0 ? kStPrefix : kStAggregate, n_heads);
-    if (t == 0) s.em_base = tile ? look_back(a.st_em, tile, n_ent) : 0ull;
-    if (t == 32) s.edge_base = tile ? look_back(a.st_edge, tile, n_heads) : 0ull;
-    __syncthreads();
-    const unsigned long long em_base = s.em_base, edge_base = s.edge_base;
-
-    // ---- materialise and write each row once, in final order
-    for (uint32_t k = t; k < n_ent; k += kFusedBlock) {
-      uint32_t e  = idx[k];
-      uint32_t ib = s.ent_ib[e], ia = s.src_ia[s.ent_j[e]];
-      int      a0 = m.ir0[ia], a1 = m.ir1[ia], b0 = m.ir0[ib], b1 = m.ir1[ib];
-      int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
-      // MatchMap.cpp:195-202: score_x * common / len_x, summed; the sum is commutative so outer/inner need not be told
-      // apart for the score.  No FMA contraction (explicit _rn intrinsics).
-      double  common = double(ov1 - ov0 + 1);
-      double  sa     = double((unsigned long long)(long long)m.score[ia]);
-      double  sbb    = double((unsigned long long)(long long)m.score[ib]);
-      double  sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
-      double  sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
-      uint8_t fa = m.flags[ia], fb = m.flags[ib];
-      // the outer match is the one on the later line = the later row of the group (rows are in line order)
-      double             score = ia > ib ? __dadd_rn(sc_a, sc_b) : __dadd_rn(sc_b, sc_a);
-      unsigned long long o     = em_base + k;
-      a.out.em_unitig[o]       = m.unitig[ia];
-      a.out.em_ov0[o]          = ov0;
-      a.out.em_ov1[o]          = ov1;
-      a.out.em_score[o]        = score;
-      a.out.em_line[o]         = m.line[ia > ib ? ia : ib]; // MatchMap.cpp:218
-      a.out.em_flags[o]        = (((fa ^ fb) & 1) ? 0 : 1) | ((fa & fb & 2) ? 2 : 0);
-      uint32_t er              = rank[k];
-      if (er != 0xffffffffu) {
-        unsigned long long eo = edge_base + er;
-        uint32_t           kk = key[k];
-        a.out.first[eo]       = r0 + (sb < 32 ? (kk >> sb) : 0u);
-        a.out.second[eo]      = smin + (sb < 32 ? (kk & ((1u << sb) - 1u)) : kk);
-        a.out.em_begin[eo]    = o;
-      }
-    }
-    if (tile == a.n_tiles - 1 && t == 0) { // the last tile closes the CSR and reports the totals
-      a.out.em_begin[edge_base + n_heads] = em_base + n_ent;
-      a.totals[0]                         = em_base + n_ent;
-      a.totals[1]                         = edge_base + n_heads;
+    const int sb = (n_ent && s.smax > s.smin) ? 32 - __clz(s.smax - s.smin) : 0;
+    const int rb = n_rows > 1 ? 32 - __clz(n_rows - 1) : 0;
+    unsigned char *words = smem_raw + kSharedOff;
+    if (sb + rb + kIdxBits <= 32) {
+      uint32_t *wa = reinterpret_cast<uint32_t *>(words);
+      tile_tail<uint32_t>(a, s, wa, wa + kTileCap, tile, st_idx, n_src, n_ent, sb, rb);
+    } else {
+      unsigned long long *wa = reinterpret_cast<unsigned long long *>(words);
+      tile_tail<unsigned long long>(a, s, wa, wa + kTileCap, tile, st_idx, n_src, n_ent, sb, rb);
     }
   }
 }
@@ -425,106 +640,138 @@ template <class T> static T read_back(cudaStream_t st, const T *d) {
   return h;
 }
 
-bool run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs,
-                       uint64_t n_reads, EdgeTables &e, cudaEvent_t ev_pair_done) {
+static void launch_fused(cudaStream_t st, const FusedArgs &a, uint32_t n_tiles) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSGPU_CUDA(cudaFuncSetAttribute(pair_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedBytes)));
+    attr_set = true;
+  }
+  int grid = kNumSMs * 2; // persistent: two CTAs per SM
+  if (uint32_t(grid) > n_tiles) grid = int(n_tiles);
+  MSGPU_LAUNCH("pair_fused", st, pair_fused_kernel<<<grid, kFusedBlock, kFusedBytes, st>>>(a));
+}
+
+void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
+                       EdgeTables &e, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts) {
   e = EdgeTables{};
   const uint64_t M = m.n, R = n_reads;
-  if (R >= (1ull << 24)) return false; // key packing (8 + 24 bits); the sort-based variant has no such limit
+  if (R >= 0xfffffff0ull || M >= 0xfffffff0ull)
+    throw BuildError{MSGPU_ERR_LIMIT, "pairing supports < 2^32 reads and matches per device"};
 
-  // ---- pre-pass: per-read source lists
+  // ---- pre-pass: groups ordered by read id, per-read source lists
+  PairRow  *rows   = arena.alloc<PairRow>(M);
+  uint32_t *p_read = arena.alloc<uint32_t>(M);
+  int32_t  *p_ir0 = arena.alloc<int32_t>(M), *p_ir1 = arena.alloc<int32_t>(M);
   uint32_t           *deg    = arena.alloc<uint32_t>(R + 1);
-  unsigned long long *ub     = arena.alloc<unsigned long long>(R + 1);
+  unsigned long long *wgt    = arena.alloc<unsigned long long>(R + 1);
   uint32_t           *cursor = arena.alloc<uint32_t>(R + 1);
   uint32_t           *rd_off = arena.alloc<uint32_t>(R + 1);
   uint32_t           *d_u32  = arena.alloc<uint32_t>(4);
-  uint64_t           *d_u64  = arena.alloc<uint64_t>(2);
+  uint64_t           *d_u64  = arena.alloc<uint64_t>(4);
   MSGPU_CUDA(cudaMemsetAsync(deg, 0, (R + 1) * sizeof(uint32_t), st));
-  MSGPU_CUDA(cudaMemsetAsync(ub, 0, (R + 1) * sizeof(unsigned long long), st));
+  MSGPU_CUDA(cudaMemsetAsync(wgt, 0, (R + 1) * sizeof(unsigned long long), st));
   MSGPU_CUDA(cudaMemsetAsync(cursor, 0, (R + 1) * sizeof(uint32_t), st));
   MSGPU_CUDA(cudaMemsetAsync(d_u32, 0, 4 * sizeof(uint32_t), st));
   const int gm = grid_for(M, 256), gr = grid_for(R, 256);
-  if (M) MSGPU_LAUNCH("read_stats", st, read_stats_kernel<<<gm, 256, 0, st>>>(m.unitig, m.read, unitigs.grp_off, M, deg, ub));
+  if (M) MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<gm, 256, 0, st>>>(m, unitigs.grp_off, rows, p_read, p_ir0, p_ir1, deg, wgt));
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{deg}, R, rd_off, d_u32 + 0);
   MSGPU_CUDA(cudaMemcpyAsync(rd_off + R, d_u32 + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-  // weights -> tile boundaries
-  TileWeight wgt{deg, ub};
-  uint64_t  *prefix = arena.alloc<uint64_t>(R + 1);
-  exclusive_scan<uint64_t>(arena, st, wgt, R, prefix, d_u64 + 0);
-  uint32_t *tile_rank = arena.alloc<uint32_t>(R + 1);
-  TileStart start{wgt, prefix};
-  exclusive_scan<uint32_t>(arena, st, start, R, tile_rank, d_u32 + 1);
-  // sum of the per-read partner counts = 2 x the candidate pairs (each unordered pair is seen from both reads)
-  exclusive_scan<uint64_t>(arena, st, LoadAs<unsigned long long, uint64_t>{ub}, R, (uint64_t *)nullptr, d_u64 + 1);
-  uint32_t n_src   = read_back(st, d_u32 + 0);
-  uint32_t n_tiles = read_back(st, d_u32 + 1);
-  uint64_t P       = read_back(st, d_u64 + 1) / 2;
-  e.n_pairs        = P;
-  uint32_t *tile_first = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1);
-  if (R) MSGPU_LAUNCH("write_tiles", st, write_tiles_kernel<<<gr, 256, 0, st>>>(start, tile_rank, R, d_u32 + 1, tile_first, d_u32 + 2));
-  if (read_back(st, d_u32 + 2) != 0) return false; // heavy reads: let the sort-based variant handle this input
-  uint32_t *rd_tmp = arena.alloc<uint32_t>(n_src), *rd_src = arena.alloc<uint32_t>(n_src);
-  if (M) MSGPU_LAUNCH("scatter_sources", st, scatter_sources_kernel<<<gm, 256, 0, st>>>(m.unitig, m.read, unitigs.grp_off, M, rd_off, cursor, rd_tmp));
-  if (n_src) MSGPU_LAUNCH("order_sources", st, order_sources_kernel<<<grid_for(n_src, 256), 256, 0, st>>>(m.read, rd_off, rd_tmp, n_src, rd_src));
 
-  // ---- outputs: E_m <= P and E <= E_m, so P rows of capacity are always enough
-  e.em_unitig = arena.alloc<uint32_t>(P);
-  e.em_ov0    = arena.alloc<int32_t>(P);
-  e.em_ov1    = arena.alloc<int32_t>(P);
-  e.em_score  = arena.alloc<double>(P);
-  e.em_line   = arena.alloc<uint32_t>(P);
-  e.em_flags  = arena.alloc<uint8_t>(P);
-  e.first     = arena.alloc<uint32_t>(P);
-  e.second    = arena.alloc<uint32_t>(P);
-  e.em_begin  = arena.alloc<uint64_t>(P + 1);
+  // ---- tile planning
+  RowPlan   plan{deg, wgt};
+  uint64_t *prefix = arena.alloc<uint64_t>(R + 1);
+  exclusive_scan<uint64_t>(arena, st, ClippedWeight{plan}, R, prefix, (uint64_t *)nullptr);
+  TileCount tc{plan, prefix};
+  uint32_t *tile_idx = arena.alloc<uint32_t>(R + 1);
+  exclusive_scan<uint32_t>(arena, st, tc, R, tile_idx, d_u32 + 1);
+  uint64_t *slice_off = arena.alloc<uint64_t>(R + 1);
+  exclusive_scan<uint64_t>(arena, st, SliceCount{plan}, R, slice_off, d_u64 + 0);
+  exclusive_scan<uint64_t>(arena, st, WeightOf{wgt}, R, (uint64_t *)nullptr, d_u64 + 1);
+  uint32_t h32[4];
+  uint64_t h64[4];
+  MSGPU_CUDA(cudaMemcpyAsync(h32, d_u32, sizeof(h32), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaMemcpyAsync(h64, d_u64, sizeof(h64), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaStreamSynchronize(st));
+  const uint32_t n_src = h32[0], n_tiles = h32[1];
+  const uint64_t n_slices = h64[0], P = h64[1]; // P = sum k(k-1)/2: every unordered pair is one suffix member
+  e.n_pairs = P;
+
+  uint32_t *tile_row = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1), *tile_kind = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1);
+  if (R) MSGPU_LAUNCH("write_tiles", st, write_tiles_kernel<<<gr, 256, 0, st>>>(tc, tile_idx, R, n_tiles, tile_row, tile_kind, d_u32 + 2));
+  uint32_t *rd_tmp = arena.alloc<uint32_t>(n_src), *rd_src = arena.alloc<uint32_t>(n_src);
+  if (M) MSGPU_LAUNCH("scatter_sources", st, scatter_sources_kernel<<<gm, 256, 0, st>>>(p_read, rows, unitigs.grp_off, M, rd_off, cursor, rd_tmp));
+  if (n_src) MSGPU_LAUNCH("order_sources", st, order_sources_kernel<<<grid_for(n_src, 256), 256, 0, st>>>(p_read, rd_off, rd_tmp, n_src, rd_src));
+  uint32_t *slices = arena.alloc<uint32_t>(n_slices);
+  if (n_slices) {
+    MSGPU_LAUNCH("split_heavy", st, split_heavy_kernel<<<grid_for(uint64_t(n_tiles) * 32, 256), 256, 0, st>>>(
+                                        tile_row, tile_kind, n_tiles, plan, slice_off, rd_off, rd_src, rows,
+                                        unitigs.grp_off, p_read, uint32_t(R), slices));
+  }
+
+  // ---- this device's share: a contiguous range of tiles (tiles weigh about the same)
+  if (n_parts == 0) n_parts = 1;
+  const uint32_t tile_lo = uint32_t(uint64_t(n_tiles) * part / n_parts);
+  const uint32_t tile_hi = uint32_t(uint64_t(n_tiles) * (part + 1) / n_parts);
+  const uint32_t my_tiles = tile_hi - tile_lo;
+  // capacity of the outputs: a tile emits at most kTileCap rows, and never more than there are pairs
+  uint64_t cap = uint64_t(my_tiles) * kTileCap;
+  if (cap > P) cap = P;
+  e.em_unitig = arena.alloc<uint32_t>(cap);
+  e.em_ov0    = arena.alloc<int32_t>(cap);
+  e.em_ov1    = arena.alloc<int32_t>(cap);
+  e.em_score  = arena.alloc<double>(cap);
+  e.em_line   = arena.alloc<uint32_t>(cap);
+  e.em_flags  = arena.alloc<uint8_t>(cap);
+  e.first     = arena.alloc<uint32_t>(cap);
+  e.second    = arena.alloc<uint32_t>(cap);
+  e.em_begin  = arena.alloc<uint64_t>(cap + 1);
 
   FusedArgs a;
-  a.m          = m;
-  a.grp_off    = unitigs.grp_off;
-  a.rd_off     = rd_off;
-  a.rd_src     = rd_src;
-  a.tile_first = tile_first;
-  a.n_tiles    = n_tiles;
-  a.ticket     = arena.alloc<unsigned int>(1);
-  a.st_em      = arena.alloc<unsigned long long>(uint64_t(n_tiles) + 1);
-  a.st_edge    = arena.alloc<unsigned long long>(uint64_t(n_tiles) + 1);
-  a.totals     = arena.alloc<unsigned long long>(4);
-  a.out        = e;
+  a.rows      = rows;
+  a.p_read    = p_read;
+  a.p_ir0     = p_ir0;
+  a.p_ir1     = p_ir1;
+  a.grp_off   = unitigs.grp_off;
+  a.rd_off    = rd_off;
+  a.rd_src    = rd_src;
+  a.tile_row  = tile_row;
+  a.tile_kind = tile_kind;
+  a.slice_off = slice_off;
+  a.slices    = slices;
+  a.tile_lo   = tile_lo;
+  a.tile_hi   = tile_hi;
+  a.ticket    = arena.alloc<unsigned int>(1);
+  a.st_em     = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
+  a.st_edge   = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
+  a.totals    = arena.alloc<unsigned long long>(4);
+  a.out       = e;
   MSGPU_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), st));
-  MSGPU_CUDA(cudaMemsetAsync((void *)a.st_em, 0, (uint64_t(n_tiles) + 1) * 8, st));
-  MSGPU_CUDA(cudaMemsetAsync((void *)a.st_edge, 0, (uint64_t(n_tiles) + 1) * 8, st));
+  MSGPU_CUDA(cudaMemsetAsync(a.st_em, 0, (uint64_t(my_tiles) + 1) * 8, st));
+  MSGPU_CUDA(cudaMemsetAsync(a.st_edge, 0, (uint64_t(my_tiles) + 1) * 8, st));
   MSGPU_CUDA(cudaMemsetAsync(a.totals, 0, 4 * 8, st));
   MSGPU_CUDA(cudaMemsetAsync(e.em_begin, 0, 8, st)); // em_begin[0] when there is no edge at all
-  if (n_tiles) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      MSGPU_CUDA(cudaFuncSetAttribute(pair_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(sizeof(FusedSmem))));
-      attr_set = true;
-    }
-    int grid = kNumSMs * 2;
-    if (uint32_t(grid) > n_tiles) grid = int(n_tiles);
-    MSGPU_LAUNCH("pair_fused", st, pair_fused_kernel<<<grid, kFusedBlock, sizeof(FusedSmem), st>>>(a));
-  }
-  if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st));
+  if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st)); // planning done; the fused kernel is "merge" time
+  if (my_tiles) launch_fused(st, a, my_tiles);
   unsigned long long totals[4];
+  uint32_t           too_many = 0;
   MSGPU_CUDA(cudaMemcpyAsync(totals, a.totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaMemcpyAsync(&too_many, d_u32 + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   MSGPU_CUDA(cudaStreamSynchronize(st));
+  if (too_many)
+    throw BuildError{MSGPU_ERR_LIMIT, "a read matches more than " + std::to_string(kSrcCap) + " unitigs with partners"};
   if (totals[2] != 0)
     throw BuildError{MSGPU_ERR_INTERNAL, "fused pairing: tile invariant violated (code " + std::to_string(totals[2]) + ")"};
   e.n_em    = totals[0];
   e.n_edges = totals[1];
-  return true;
 }
 
-} // namespace msgpu
-
-namespace msgpu {
-
 void run_pairing(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
-                 EdgeTables &e, cudaEvent_t ev_pair_done) {
+                 EdgeTables &e, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts) {
   const char *v = std::getenv("MSGPU_VARIANT");
-  if (!(v && std::string(v) == "sorted") && run_pairing_fused(arena, st, m, unitigs, n_reads, e, ev_pair_done)) return;
-  run_pairing_sorted(arena, st, m, unitigs, n_reads, e, ev_pair_done);
+  if (v && std::string(v) == "sorted" && n_parts <= 1)
+    run_pairing_sorted(arena, st, m, unitigs, n_reads, e, ev_pair_done);
+  else
+    run_pairing_fused(arena, st, m, unitigs, n_reads, e, ev_pair_done, part, n_parts);
 }
 
 } // namespace msgpu

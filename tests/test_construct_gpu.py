@@ -98,3 +98,22 @@ def test_records_entry_matches_paf_entry(builder):
         a, b = res.edge_matches[k], full.edge_matches[k]
         assert np.array_equal(a.view(np.uint64) if a.dtype == np.float64 else a,
                               b.view(np.uint64) if b.dtype == np.float64 else b), k
+
+
+def test_heavy_rows_vs_oracle(builder, oracle):
+    """Rows with thousands of candidates (reads crossing a repeat that thousands of reads cross): the pairing kernel
+    splits them into sub-tiles by value ranges of the partner id; the result must not show the seams."""
+    paf = util.heavy_rows_paf()
+    got = _same(builder, oracle, paf)
+    assert got.counts["em"] > 4_000_000
+
+
+def test_sort_based_variant_agrees_with_fused(builder, monkeypatch):
+    """The sort-based pairing (global radix sort of the candidate stream) is an independent implementation of the
+    same tables: both variants must agree bit for bit."""
+    paf = synth.generate_paf("ecoli")
+    fused = util.gpu_to_tables(builder.build_from_buffer(paf).result())
+    monkeypatch.setenv("MSGPU_VARIANT", "sorted")
+    srt = util.gpu_to_tables(builder.build_from_buffer(paf).result())
+    monkeypatch.delenv("MSGPU_VARIANT")
+    assert tables_equal(fused, srt) == []

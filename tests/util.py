@@ -150,3 +150,31 @@ def invalid_pafs() -> dict:
         "int_overflow": good + b"u1\t5000\t0\t99999999999\t+\tr1\t20000\t100\t3100\t2900\t3000\t60\n" + sentinel,
         "bad_read_coord_on_accepted": good + b"u1\t5000\t0\t3000\t+\tr1\t20000\t\t3100\t2900\t3000\t60\n" + sentinel,
     }
+
+
+def heavy_rows_paf(k0=3000, k1=2500, shared_from=1000, seed=11, small_groups=40) -> bytes:
+    """Two high-multiplicity unitigs that share most of their reads (a repeat seen by thousands of reads), so that
+    rows of the edge table hold far more candidates than one pairing tile (4096): exercises the value-range split of
+    heavy rows, with duplicates (two edge matches per edge) on both sides of every split point.  Lines of the two
+    unitigs are interleaved and the reads appear in shuffled order, so read ids are not monotone inside a group."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    L = paf_line
+    rows = []
+    ulen = 20000
+    for u, (lo, k) in enumerate([(0, k0), (shared_from, k1)]):
+        for r in rng.permutation(np.arange(lo, lo + k)):
+            a = int(rng.integers(0, ulen - 3000))
+            b = int(min(ulen, a + rng.integers(420, 15000)))
+            rows.append((int(rng.integers(0, 1 << 30)),
+                         L(f"H{u}", ulen, a, b, "+-"[int(rng.integers(0, 2))], f"x{r}", 60000, 500, 500 + (b - a),
+                           int((b - a) * 0.93))))
+    for g in range(small_groups):
+        k = int(rng.integers(2, 30))
+        for r in rng.choice(k0 + k1, k, replace=False):
+            a = int(rng.integers(0, 4000))
+            b = int(a + rng.integers(420, 5000))
+            rows.append((int(rng.integers(0, 1 << 30)),
+                         L(f"s{g}", 9000, a, b, "+", f"x{r}", 60000, 100, 100 + (b - a), int((b - a) * 0.9))))
+    rows.sort(key=lambda t: t[0])
+    sentinel = L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
+    return b"".join(r[1] for r in rows) + sentinel
