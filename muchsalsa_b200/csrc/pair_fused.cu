@@ -1,4 +1,4 @@
-// pair_fused.cu — candidate-pair generation AND keyed merge in ONE persistent kernel (K6 + K7, the product variant).
+// pair_fused.cu — candidate-pair generation AND keyed merge without ever sorting in HBM (K6 + K7, the product variant).
 //
 // Replaces MatchMap::calculateEdges / processScaffold (MatchMap.cpp:161-224) + Graph::addEdge (Graph.cpp:212-230,
 // 291-311) + MatchMap::addEdgeMatch (MatchMap.cpp:109-134).
@@ -6,7 +6,7 @@
 // The reference walks every unitig group and throws each accepted pair at two global hash maps.  The sort-based
 // variant (pair_sort.cu) writes every candidate to HBM in unitig order and moves it through 4-6 radix passes: ~250 B
 // of HBM traffic per edge match for 25 B of result.  Here the work is turned around so that every output row is
-// produced directly at its final position and touches HBM once:
+// produced directly at its final position:
 //
 //   * The reduction key is (first, second), first < second (read ids; MatchMap.cpp:204-213).  Call the edge matches
 //     whose `first` is read r "row r".  Row r is the union, over the matches a of r (its "sources", one per unitig),
@@ -18,15 +18,22 @@
 //     heavier than a tile (a read that crosses a high-multiplicity repeat) is split into sub-tiles by VALUE RANGES of
 //     `second`: the boundaries are found by bisection on the merged rank over the row's sorted suffixes, so every
 //     sub-tile is bounded, no edge straddles two sub-tiles and the sub-tiles of a row are in output order.
-//   * One CTA per tile (persistent, tiles handed out in order by an atomic ticket): stage the sources, enumerate the
-//     candidates into shared memory, radix-sort them there by (row, second) — stable, and candidates are generated in
-//     unitig order, so rows of one edge come out by unitig — find the run heads (= edges), obtain the global offsets
-//     of the tile's first edge match and first edge by a decoupled look-back over per-tile status words, then compute
-//     and write each edge match, each edge and its CSR offset exactly once, coalesced, in (first, second, unitig) order.
+//   * pair_tiles_kernel, one CTA per tile, no dependency between tiles: stage the sources, enumerate the candidates
+//     into shared memory, radix-sort them there by (row, second) — stable, and candidates are generated in unitig
+//     order, so rows of one edge come out by unitig — find the run heads (= edges) and write the tile's surviving
+//     candidates as compact 8-byte records (partner row, source, head flag, heads before) plus two counts.
+//   * scan_tiles_kernel turns the per-tile counts into the global offset of every tile's first edge match and edge.
+//   * pair_emit_rows_kernel, embarrassingly parallel: each record gathers its two matches (one 32-byte sector each),
+//     evaluates the reference's score expression in IEEE double and writes the edge match — and, for a run head, the
+//     edge and its CSR offset — exactly once, coalesced, in (first, second, unitig) order.
+//   (An earlier version did all of it in one persistent kernel with a decoupled look-back for the offsets; ncu showed
+//    27 % of its stall samples at the barrier behind the look-back, because a tile's counts exist only after its sort.
+//    The 8-byte records cost +0.66 GB of traffic at yeast scale and remove every inter-CTA wait.)
 //
-// Algorithmic HBM traffic = every match record once + 25 B per edge match + 16 B per edge.  The k^2 work never leaves
-// the SM.  The same kernel serves multi-GPU runs: a rank processes a contiguous range of tiles, so its output is a
-// contiguous slice of the global (first, second)-sorted result and no candidate ever crosses NVLink.
+// Algorithmic HBM traffic = every match record once + 25 B per edge match + 16 B per edge; actual traffic adds one
+// write and one read of 8 B per edge match.  The k^2 work never leaves the SM.  The same kernels serve multi-GPU runs:
+// a rank processes a contiguous range of tiles, so its output is a contiguous slice of the global
+// (first, second)-sorted result and no candidate ever crosses NVLink.
 #include <cstdlib>
 #include <string>
 
@@ -252,12 +259,13 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// the fused kernel
+// K6/K7a: one CTA per tile — enumerate, sort in shared memory, find run heads, write the tile's compact records
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr unsigned long long kStAggregate = 1ull << 62, kStPrefix = 2ull << 62, kStMask = (1ull << 62) - 1;
-constexpr uint16_t           kNoSource    = 0xffffu; // candidate failed the overlap test
+constexpr uint16_t kNoSource = 0xffffu; // candidate failed the overlap test
+constexpr int      kSrcBits  = 9;       // kSrcCap == 1 << kSrcBits
+static_assert(kSrcCap == (1u << kSrcBits), "record packing");
 
-struct FusedArgs {
+struct TileArgs {
   const PairRow  *rows;
   const uint32_t *p_read;
   const int32_t  *p_ir0, *p_ir1;
@@ -267,71 +275,34 @@ struct FusedArgs {
   const uint64_t *slice_off;
   const uint32_t *slices;
   uint32_t        tile_lo, tile_hi; // this launch processes tiles [tile_lo, tile_hi)
-  unsigned int   *ticket;
-  unsigned long long *st_em, *st_edge; // per tile: flag (2 bits) | value
-  unsigned long long *totals;          // [0] = edge matches, [1] = edges, [2] = error code
-  EdgeTables      out;
+  uint2          *records;          // per tile kTileCap slots: (partner row, source | head << 9 | heads before << 10)
+  uint2          *tile_cnt;         // per tile: (surviving candidates, run heads)
+  unsigned int   *error;
 };
 
 struct SrcStage { // the sources of the tile, staged in shared memory (structure of arrays)
   uint32_t begin[kSrcCap];    // first partner row
   uint32_t base[kSrcCap + 1]; // exclusive prefix of the slice lengths = first candidate slot
-  int32_t  ir0[kSrcCap], ir1[kSrcCap], score[kSrcCap];
-  uint32_t line[kSrcCap], read[kSrcCap], unitig[kSrcCap];
+  int32_t  ir0[kSrcCap], ir1[kSrcCap];
   uint16_t row_local[kSrcCap]; // dense rank of the source's read inside the tile
-  uint8_t  flags[kSrcCap];
 };
 
-struct FusedShared { // everything but the two sort buffers, which follow it in dynamic shared memory
+struct TileShared { // everything but the two sort buffers, which follow it in dynamic shared memory
   uint16_t ent_j[kTileCap]; // candidate slot -> source (kNoSource: failed the overlap test)
   SrcStage src;
   uint32_t warp_cnt[kFusedWarps][256];
   uint32_t bin_base[256];
   uint32_t scan[33];
-  uint32_t tile, smin, smax, n_invalid;
-  unsigned long long em_base, edge_base;
+  uint32_t warp_tot[kFusedWarps];
+  uint32_t smin, smax;
 };
-constexpr size_t kSharedOff  = (sizeof(FusedShared) + 15) & ~size_t(15);
-constexpr size_t kFusedBytes = kSharedOff + 2 * kTileCap * sizeof(unsigned long long);
-
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// Decoupled look-back by ONE WARP: exclusive prefix over the tiles before `idx` (status index); then the tile's
-// inclusive prefix is published.  A status word carries flag and value together, so no fence is needed.
-__device__ unsigned long long look_back(unsigned long long *st, uint32_t idx, unsigned long long mine) {
-  const unsigned     l    = threadIdx.x & 31;
-  unsigned long long excl = 0;
-  int64_t            top  = int64_t(idx) - 1; // newest predecessor not yet summed
-  while (top >= 0) {
-    int64_t            t = top - l;
-    unsigned long long v = kStPrefix; // lanes past the beginning count as an (empty) inclusive prefix
-    if (t >= 0) {
-      do {
-        v = ld_status(st + t);
-      } while ((v >> 62) == 0);
-    }
-    unsigned pref = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-    unsigned stop = pref ? unsigned(__ffs(pref) - 1) : 32u; // first lane (newest tile) holding an inclusive prefix
-    unsigned long long add = l <= stop ? (v & kStMask) : 0ull;
-    excl += warp_reduce_sum(add);
-    if (pref) break;
-    top -= 32;
-  }
-  if (l == 0) st_status(st + idx, kStPrefix | (excl + mine));
-  return excl;
-}
+constexpr size_t kSharedOff = (sizeof(TileShared) + 15) & ~size_t(15);
+constexpr size_t kTileBytes = kSharedOff + 2 * kTileCap * sizeof(unsigned long long);
 
 // Stable LSD radix sort of n words in shared memory on bits [lo, hi); warp w owns a contiguous block of items and
 // ranks it with __match_any_sync + per-warp digit counters, so equal digits keep their order.  Returns the buffer
 // that holds the result.  blockDim.x == 256.
-template <class W> __device__ W *cta_radix_sort(FusedShared &s, W *in, W *out, uint32_t n, int lo, int hi) {
+template <class W> __device__ W *cta_radix_sort(TileShared &s, W *in, W *out, uint32_t n, int lo, int hi) {
   const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
   const int      kb = hi - lo;
   if (kb <= 0 || n <= 1) return in;
@@ -398,56 +369,54 @@ template <class W> __device__ W *cta_radix_sort(FusedShared &s, W *in, W *out, u
   return in;
 }
 
-// S2-S5 of a tile, for sort words of type W (32 bits when row + second + slot fit, else 64)
+// enumerate + sort + heads of one tile, for sort words of type W (32 bits when row + second + slot fit, else 64)
 template <class W>
-__device__ __forceinline__ void tile_tail(const FusedArgs &a, FusedShared &s, W *wa, W *wb, uint32_t tile,
-                                          uint32_t st_idx, uint32_t n_src, uint32_t n_ent, int sb, int rb) {
+__device__ __forceinline__ void tile_tail(const TileArgs &a, TileShared &s, W *wa, W *wb, uint32_t st_idx,
+                                          uint32_t n_src, uint32_t n_ent, int sb, int rb) {
   const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
-  const uint32_t smin = s.smin;
+  const uint32_t smin  = s.smin;
+  const uint32_t per   = (n_ent + kFusedBlock - 1) / kFusedBlock;
+  const uint32_t wbase = w * per * 32; // warp w owns slots / sorted positions [wbase, wbase + per * 32)
 
-  // ---- S2: materialise the candidates in generation order (source by source = unitig order inside a row)
-  {
-    uint32_t n_bad = 0;
-    for (uint32_t e = t; e < n_ent; e += kFusedBlock) {
-      uint32_t lo = 0, hi = n_src; // last source with base <= e (empty slices share their base with the next one)
-      while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (s.src.base[mid] <= e) lo = mid; else hi = mid;
-      }
-      const uint32_t j  = lo;
-      const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
-      const uint32_t sr = a.p_read[ib];
-      const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = a.p_ir0[ib], b1 = a.p_ir1[ib];
-      const int      o0 = a0 > b0 ? a0 : b0, o1 = a1 < b1 ? a1 : b1;
-      const bool     keep = o0 <= o1 && o1 - o0 > kThOverlapF; // MatchMap.cpp:192
-      const W        key  = (W(s.src.row_local[j]) << sb) | W(sr - smin);
-      wa[e]               = (key << kIdxBits) | W(e);
-      s.ent_j[e]          = keep ? uint16_t(j) : kNoSource;
-      n_bad += keep ? 0u : 1u;
+  // ---- materialise the candidates in generation order (source by source = unitig order inside a row)
+  if (wbase < n_ent) {
+    uint32_t j = 0, hi = n_src; // last source with base <= wbase (empty slices share their base with the next one)
+    while (hi - j > 1) {
+      uint32_t mid = (j + hi) >> 1;
+      if (s.src.base[mid] <= wbase) j = mid; else hi = mid;
     }
-    n_bad = warp_reduce_sum(n_bad);
-    if (l == 0 && n_bad) atomicAdd(&s.n_invalid, n_bad);
+    for (uint32_t it = 0; it < per; ++it) {
+      const uint32_t e = wbase + it * 32 + l;
+      if (e < n_ent) {
+        while (s.src.base[j + 1] <= e) ++j; // slots grow with `it`, so every lane walks forward only
+        const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
+        const uint32_t sr = a.p_read[ib];
+        const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = a.p_ir0[ib], b1 = a.p_ir1[ib];
+        const int      o0 = a0 > b0 ? a0 : b0, o1 = a1 < b1 ? a1 : b1;
+        const bool     keep = o0 <= o1 && o1 - o0 > kThOverlapF; // MatchMap.cpp:192
+        const W        key  = (W(s.src.row_local[j]) << sb) | W(sr - smin);
+        wa[e]               = (key << kIdxBits) | W(e);
+        s.ent_j[e]          = keep ? uint16_t(j) : kNoSource;
+      }
+    }
   }
   __syncthreads();
-  const uint32_t n_valid = n_ent - s.n_invalid;
-  if (t == 0) st_status(a.st_em + st_idx, (st_idx == 0 ? kStPrefix : kStAggregate) | n_valid);
 
-  // ---- S3: sort by (row, second); generation order (= unitig order) breaks ties because the sort is stable
-  W        *sorted = cta_radix_sort<W>(s, wa, wb, n_ent, kIdxBits, kIdxBits + sb + rb);
-  uint32_t *pre    = reinterpret_cast<uint32_t *>(sorted == wa ? wb : wa);
+  // ---- sort by (row, second); generation order (= unitig order) breaks ties because the sort is stable
+  W *sorted = cta_radix_sort<W>(s, wa, wb, n_ent, kIdxBits, kIdxBits + sb + rb);
 
-  // ---- S4: run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the
-  // key of its pair) but is skipped; the head of a run is its first surviving candidate.
-  // pre[k] = surviving rows before k (bits 0-15) | heads before k (bits 16-28) | survives (bit 30) | head (bit 31)
-  uint32_t carry = 0;
-  for (uint32_t c0 = 0; c0 < n_ent; c0 += kFusedBlock) {
-    const uint32_t k = c0 + t;
-    uint32_t       v = 0, fl = 0;
+  // ---- run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the key
+  // of its pair) but is skipped; the head of a run is its first surviving candidate.
+  uint32_t vmask = 0, hmask = 0, n_v = 0, n_h = 0; // bit `it`: this lane's item of iteration `it` survives / is a head
+  for (uint32_t it = 0; it < per; ++it) {
+    const uint32_t k = wbase + it * 32 + l;
+    bool           ok = false, head = false;
     if (k < n_ent) {
       const W x = sorted[k];
-      if (s.ent_j[uint32_t(x) & (kTileCap - 1)] != kNoSource) {
-        bool    head = true;
-        const W key  = x >> kIdxBits;
+      ok        = s.ent_j[uint32_t(x) & (kTileCap - 1)] != kNoSource;
+      if (ok) {
+        head        = true;
+        const W key = x >> kIdxBits;
         for (uint32_t p = k; p > 0;) {
           --p;
           const W y = sorted[p];
@@ -457,103 +426,70 @@ __device__ __forceinline__ void tile_tail(const FusedArgs &a, FusedShared &s, W 
             break;
           }
         }
-        v  = 1u | (head ? 0x10000u : 0u);
-        fl = (1u << 30) | (head ? (1u << 31) : 0u);
       }
     }
-    uint32_t total;
-    uint32_t ex = block_exclusive_scan<uint32_t>(v, s.scan, &total);
-    if (k < n_ent) pre[k] = (carry + ex) | fl;
-    carry += total;
+    vmask |= (ok ? 1u : 0u) << it;
+    hmask |= (head ? 1u : 0u) << it;
+    n_v += __popc(__ballot_sync(0xffffffffu, ok));
+    n_h += __popc(__ballot_sync(0xffffffffu, head));
   }
-  const uint32_t n_heads = carry >> 16;
-  if (w == 0) {
-    unsigned long long eb = look_back(a.st_em, st_idx, n_valid);
-    if (l == 0) s.em_base = eb;
-  } else if (w == 1) {
-    if (l == 0 && st_idx != 0) st_status(a.st_edge + st_idx, kStAggregate | n_heads);
-    unsigned long long eb = look_back(a.st_edge, st_idx, n_heads);
-    if (l == 0) s.edge_base = eb;
-  }
+  if (l == 0) s.warp_tot[w] = n_v | (n_h << 16);
   __syncthreads();
-  const unsigned long long em_base = s.em_base, edge_base = s.edge_base;
-
-  // ---- S5: compute and write each row once, in final order
-  for (uint32_t k = t; k < n_ent; k += kFusedBlock) {
-    const uint32_t pv = pre[k];
-    if (!(pv & (1u << 30))) continue;
-    const uint32_t e  = uint32_t(sorted[k]) & (kTileCap - 1);
-    const uint32_t j  = s.ent_j[e];
-    const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
-    const PairRow  pb = a.rows[ib];
-    const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = pb.ir0, b1 = pb.ir1;
-    const int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
-    // MatchMap.cpp:195-202: score_x * common / len_x for the outer and the inner match, summed.  IEEE addition is
-    // commutative, so which of the two is "outer" (the later line) does not change the sum.  No FMA contraction.
-    const double   common = double(ov1 - ov0 + 1);
-    const double   sa     = double((unsigned long long)(long long)s.src.score[j]); // size_t widened from int
-    const double   sbb    = double((unsigned long long)(long long)pb.score);
-    const double   sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
-    const double   sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
-    const uint32_t la = s.src.line[j], lb = pb.line;
-    const uint32_t fa = s.src.flags[j], fb = pb.flags;
-    const unsigned long long o = em_base + (pv & 0xffffu);
-    a.out.em_unitig[o] = s.src.unitig[j];
-    a.out.em_ov0[o]    = ov0;
-    a.out.em_ov1[o]    = ov1;
-    a.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
-    a.out.em_line[o]   = la > lb ? la : lb; // the outer match is the one on the later line (MatchMap.cpp:218)
-    a.out.em_flags[o]  = uint8_t((((fa ^ fb) & 1u) ? 0u : 1u) | ((fa & fb & 2u) ? 2u : 0u));
-    if (pv >> 31) {
-      const unsigned long long eo = edge_base + ((pv >> 16) & 0x1fffu);
-      a.out.first[eo]    = s.src.read[j];
-      a.out.second[eo]   = pb.read;
-      a.out.em_begin[eo] = o;
-    }
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int ww = 0; ww < kFusedWarps; ++ww) {
+    uint32_t c = s.warp_tot[ww];
+    before += ww < int(w) ? c : 0u;
+    total += c;
   }
-  if (tile == a.tile_hi - 1 && t == 0) { // the last tile closes the CSR and reports the totals
-    a.out.em_begin[edge_base + n_heads] = em_base + n_valid;
-    a.totals[0]                         = em_base + n_valid;
-    a.totals[1]                         = edge_base + n_heads;
+  if (t == 0) a.tile_cnt[st_idx] = make_uint2(total & 0xffffu, total >> 16);
+
+  // ---- the tile's records, compacted, in final order
+  uint2   *rec = a.records + uint64_t(st_idx) * kTileCap;
+  uint32_t pv = before & 0xffffu, ph = before >> 16;
+  for (uint32_t it = 0; it < per; ++it) {
+    const uint32_t k    = wbase + it * 32 + l;
+    const bool     ok   = (vmask >> it) & 1u, head = (hmask >> it) & 1u;
+    const unsigned bv   = __ballot_sync(0xffffffffu, ok), bh = __ballot_sync(0xffffffffu, head);
+    const unsigned lt   = (1u << l) - 1u;
+    if (ok) {
+      const uint32_t e  = uint32_t(sorted[k]) & (kTileCap - 1);
+      const uint32_t j  = s.ent_j[e];
+      const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
+      rec[pv + __popc(bv & lt)] = make_uint2(ib, j | (head ? 1u << kSrcBits : 0u) | ((ph + __popc(bh & lt)) << (kSrcBits + 1)));
+    }
+    pv += __popc(bv);
+    ph += __popc(bh);
   }
 }
 
-__global__ void __launch_bounds__(kFusedBlock, 2) pair_fused_kernel(FusedArgs a) {
+__global__ void __launch_bounds__(kFusedBlock, 2) pair_tiles_kernel(TileArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FusedShared   &s = *reinterpret_cast<FusedShared *>(smem_raw);
-  const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
+  TileShared    &s = *reinterpret_cast<TileShared *>(smem_raw);
+  const unsigned t = threadIdx.x, l = t & 31;
 
-  for (;;) {
+  for (uint32_t tile = a.tile_lo + blockIdx.x; tile < a.tile_hi; tile += gridDim.x) {
     __syncthreads(); // previous tile fully done with shared memory
     if (t == 0) {
-      s.tile      = a.tile_lo + atomicAdd(a.ticket, 1u);
-      s.smin      = 0xffffffffu;
-      s.smax      = 0;
-      s.n_invalid = 0;
+      s.smin = 0xffffffffu;
+      s.smax = 0;
     }
     __syncthreads();
-    const uint32_t tile = s.tile;
-    if (tile >= a.tile_hi) break;
     const uint32_t st_idx = tile - a.tile_lo;
     const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
     const uint32_t q0 = a.rd_off[r0];
     const uint32_t n_src = (kind ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
-
-    // a tile that violates its capacity invariant (cannot happen: see the planning kernels) reports the error,
-    // contributes nothing, keeps the look-back chain alive and never touches memory out of bounds
-    auto bail = [&](unsigned long long code) {
-      if (w == 0) {
-        if (l == 0) a.totals[2] = code;
-        look_back(a.st_em, st_idx, 0);
-        look_back(a.st_edge, st_idx, 0);
-      }
-    };
+    // a tile that violates its capacity invariant (cannot happen: see the planning kernels) reports the error and
+    // contributes nothing
     if (n_src > kSrcCap) {
-      bail(1);
+      if (t == 0) {
+        *a.error            = 1;
+        a.tile_cnt[st_idx] = make_uint2(0, 0);
+      }
       continue;
     }
 
-    // ---- S1: stage the sources; slice = the partners this tile takes from each source
+    // ---- stage the sources; slice = the partners this tile takes from each source
     {
       const uint32_t *sl0 = nullptr, *sl1 = nullptr;
       if (kind) {
@@ -575,15 +511,10 @@ __global__ void __launch_bounds__(kFusedBlock, 2) pair_fused_kernel(FusedArgs a)
             b = q + 1;
             e = a.grp_off[row.unitig + 1];
           }
-          len             = e - b;
-          s.src.begin[j]  = b;
-          s.src.ir0[j]    = row.ir0;
-          s.src.ir1[j]    = row.ir1;
-          s.src.score[j]  = row.score;
-          s.src.line[j]   = row.line;
-          s.src.read[j]   = row.read;
-          s.src.unitig[j] = row.unitig;
-          s.src.flags[j]  = uint8_t(row.flags);
+          len            = e - b;
+          s.src.begin[j] = b;
+          s.src.ir0[j]   = row.ir0;
+          s.src.ir1[j]   = row.ir1;
           if (len) { // the slice is sorted by read id
             uint32_t f = a.p_read[b], g = a.p_read[e - 1];
             lmin       = f < lmin ? f : lmin;
@@ -591,8 +522,8 @@ __global__ void __launch_bounds__(kFusedBlock, 2) pair_fused_kernel(FusedArgs a)
           }
           newrow = (j > 0 && a.p_read[a.rd_src[q0 + j - 1]] != row.read) ? 1u : 0u;
         }
-        // slice lengths in the low half, new-row flags in the high half: a tile has < 2^16 candidates by plan, but
-        // a violated plan must not corrupt the row ranks, so the two are scanned separately when a chunk is large
+        // a chunk holds <= 256 sources; slice lengths are scanned in 32 bits and the new-row flags ride in the top
+        // byte-and-a-bit only when the lengths cannot reach them (planned tiles hold <= 4096 candidates)
         uint32_t tot, ex = block_exclusive_scan<uint32_t>(len, s.scan, &tot);
         uint32_t tot_row, ex_row = block_exclusive_scan<uint32_t>(newrow, s.scan, &tot_row);
         if (j < n_src) {
@@ -617,7 +548,10 @@ __global__ void __launch_bounds__(kFusedBlock, 2) pair_fused_kernel(FusedArgs a)
     const uint32_t n_ent  = s.src.base[n_src];
     const uint32_t n_rows = n_src ? uint32_t(s.src.row_local[n_src - 1]) + 1u : 0u;
     if (n_ent > kTileCap) {
-      bail(2);
+      if (t == 0) {
+        *a.error            = 2;
+        a.tile_cnt[st_idx] = make_uint2(0, 0);
+      }
       continue;
     }
     const int sb = (n_ent && s.smax > s.smin) ? 32 - __clz(s.smax - s.smin) : 0;
@@ -625,30 +559,88 @@ __global__ void __launch_bounds__(kFusedBlock, 2) pair_fused_kernel(FusedArgs a)
     unsigned char *words = smem_raw + kSharedOff;
     if (sb + rb + kIdxBits <= 32) {
       uint32_t *wa = reinterpret_cast<uint32_t *>(words);
-      tile_tail<uint32_t>(a, s, wa, wa + kTileCap, tile, st_idx, n_src, n_ent, sb, rb);
+      tile_tail<uint32_t>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent, sb, rb);
     } else {
       unsigned long long *wa = reinterpret_cast<unsigned long long *>(words);
-      tile_tail<unsigned long long>(a, s, wa, wa + kTileCap, tile, st_idx, n_src, n_ent, sb, rb);
+      tile_tail<unsigned long long>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent, sb, rb);
     }
   }
 }
 
-template <class T> static T read_back(cudaStream_t st, const T *d) {
-  T h;
-  MSGPU_CUDA(cudaMemcpyAsync(&h, d, sizeof(T), cudaMemcpyDeviceToHost, st));
-  MSGPU_CUDA(cudaStreamSynchronize(st));
-  return h;
+// ---------------------------------------------------------------------------------------------------------------------
+// K7b: tile counts -> global offsets of every tile's first edge match and first edge (one CTA; tiles are few)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+    scan_tiles_kernel(const uint2 *__restrict__ tile_cnt, uint32_t n_tiles, unsigned long long *__restrict__ em_base,
+                      unsigned long long *__restrict__ edge_base, unsigned long long *__restrict__ totals,
+                      uint64_t *__restrict__ em_begin) {
+  __shared__ unsigned long long sm[33];
+  unsigned long long            carry_v = 0, carry_h = 0;
+  for (uint32_t c0 = 0; c0 < n_tiles; c0 += blockDim.x) {
+    const uint32_t i = c0 + threadIdx.x;
+    const uint2    c = i < n_tiles ? tile_cnt[i] : make_uint2(0, 0);
+    // both counts are <= 4096 per tile and a chunk has 1024 tiles: pack them into one 64-bit scan
+    unsigned long long tot, ex = block_exclusive_scan<unsigned long long>((unsigned long long)c.x | ((unsigned long long)c.y << 32), sm, &tot);
+    if (i < n_tiles) {
+      em_base[i]   = carry_v + (ex & 0xffffffffull);
+      edge_base[i] = carry_h + (ex >> 32);
+    }
+    carry_v += tot & 0xffffffffull;
+    carry_h += tot >> 32;
+  }
+  if (threadIdx.x == 0) {
+    totals[0]         = carry_v;
+    totals[1]         = carry_h;
+    em_begin[carry_h] = carry_v; // closes the CSR
+  }
 }
 
-static void launch_fused(cudaStream_t st, const FusedArgs &a, uint32_t n_tiles) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSGPU_CUDA(cudaFuncSetAttribute(pair_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedBytes)));
-    attr_set = true;
+// ---------------------------------------------------------------------------------------------------------------------
+// K7c: every record becomes one edge match (and, for run heads, one edge) at its final position
+// ---------------------------------------------------------------------------------------------------------------------
+struct EmitArgs {
+  const PairRow  *rows;
+  const uint32_t *rd_off, *rd_src, *tile_row;
+  uint32_t        tile_lo, n_tiles;
+  const uint2    *records, *tile_cnt;
+  const unsigned long long *em_base, *edge_base;
+  EdgeTables      out;
+};
+
+__global__ void __launch_bounds__(256) pair_emit_rows_kernel(EmitArgs a) {
+  for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
+    const uint32_t           n_valid = a.tile_cnt[ti].x;
+    const unsigned long long em0 = a.em_base[ti], ed0 = a.edge_base[ti];
+    const uint32_t           q0  = a.rd_off[a.tile_row[a.tile_lo + ti]];
+    const uint2             *rec = a.records + uint64_t(ti) * kTileCap;
+    for (uint32_t k = threadIdx.x; k < n_valid; k += blockDim.x) {
+      const uint2    r  = rec[k];
+      const uint32_t ib = r.x, j = r.y & (kSrcCap - 1);
+      const PairRow  pa = a.rows[a.rd_src[q0 + j]], pb = a.rows[ib];
+      const int      a0 = pa.ir0, a1 = pa.ir1, b0 = pb.ir0, b1 = pb.ir1;
+      const int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
+      // MatchMap.cpp:195-202: score_x * common / len_x for the outer and the inner match, summed.  IEEE addition
+      // is commutative, so which of the two is "outer" (the later line) does not change the sum.  No FMA contraction.
+      const double common = double(ov1 - ov0 + 1);
+      const double sa     = double((unsigned long long)(long long)pa.score); // size_t widened from int
+      const double sbb    = double((unsigned long long)(long long)pb.score);
+      const double sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
+      const double sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
+      const unsigned long long o = em0 + k;
+      a.out.em_unitig[o] = pa.unitig;
+      a.out.em_ov0[o]    = ov0;
+      a.out.em_ov1[o]    = ov1;
+      a.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
+      a.out.em_line[o]   = pa.line > pb.line ? pa.line : pb.line; // outer = the later line (MatchMap.cpp:218)
+      a.out.em_flags[o]  = uint8_t((((pa.flags ^ pb.flags) & 1u) ? 0u : 1u) | ((pa.flags & pb.flags & 2u) ? 2u : 0u));
+      if (r.y & (1u << kSrcBits)) {
+        const unsigned long long eo = ed0 + (r.y >> (kSrcBits + 1));
+        a.out.first[eo]    = pa.read;
+        a.out.second[eo]   = pb.read;
+        a.out.em_begin[eo] = o;
+      }
+    }
   }
-  int grid = kNumSMs * 2; // persistent: two CTAs per SM
-  if (uint32_t(grid) > n_tiles) grid = int(n_tiles);
-  MSGPU_LAUNCH("pair_fused", st, pair_fused_kernel<<<grid, kFusedBlock, kFusedBytes, st>>>(a));
 }
 
 void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
@@ -726,7 +718,13 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   e.second    = arena.alloc<uint32_t>(cap);
   e.em_begin  = arena.alloc<uint64_t>(cap + 1);
 
-  FusedArgs a;
+  uint2              *records  = arena.alloc<uint2>(uint64_t(my_tiles) * kTileCap);
+  uint2              *tile_cnt = arena.alloc<uint2>(uint64_t(my_tiles) + 1);
+  unsigned long long *em_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
+  unsigned long long *ed_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
+  unsigned long long *totals  = arena.alloc<unsigned long long>(2);
+
+  TileArgs a;
   a.rows      = rows;
   a.p_read    = p_read;
   a.p_ir0     = p_ir0;
@@ -740,29 +738,49 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   a.slices    = slices;
   a.tile_lo   = tile_lo;
   a.tile_hi   = tile_hi;
-  a.ticket    = arena.alloc<unsigned int>(1);
-  a.st_em     = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
-  a.st_edge   = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
-  a.totals    = arena.alloc<unsigned long long>(4);
-  a.out       = e;
-  MSGPU_CUDA(cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), st));
-  MSGPU_CUDA(cudaMemsetAsync(a.st_em, 0, (uint64_t(my_tiles) + 1) * 8, st));
-  MSGPU_CUDA(cudaMemsetAsync(a.st_edge, 0, (uint64_t(my_tiles) + 1) * 8, st));
-  MSGPU_CUDA(cudaMemsetAsync(a.totals, 0, 4 * 8, st));
-  MSGPU_CUDA(cudaMemsetAsync(e.em_begin, 0, 8, st)); // em_begin[0] when there is no edge at all
-  if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st)); // planning done; the fused kernel is "merge" time
-  if (my_tiles) launch_fused(st, a, my_tiles);
-  unsigned long long totals[4];
-  uint32_t           too_many = 0;
-  MSGPU_CUDA(cudaMemcpyAsync(totals, a.totals, sizeof(totals), cudaMemcpyDeviceToHost, st));
-  MSGPU_CUDA(cudaMemcpyAsync(&too_many, d_u32 + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  a.records   = records;
+  a.tile_cnt  = tile_cnt;
+  a.error     = d_u32 + 3;
+  if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st)); // planning done; what follows is "merge" time
+  if (my_tiles) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileBytes)));
+      attr_set = true;
+    }
+    int grid = kNumSMs * 2 * 4; // a few waves of two resident CTAs per SM, tiles strided over them
+    if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
+    MSGPU_LAUNCH("pair_tiles", st, pair_tiles_kernel<<<grid, kFusedBlock, kTileBytes, st>>>(a));
+  }
+  MSGPU_LAUNCH("scan_tiles", st, scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_cnt, my_tiles, em_base, ed_base, totals, e.em_begin));
+  if (my_tiles) {
+    EmitArgs ea;
+    ea.rows      = rows;
+    ea.rd_off    = rd_off;
+    ea.rd_src    = rd_src;
+    ea.tile_row  = tile_row;
+    ea.tile_lo   = tile_lo;
+    ea.n_tiles   = my_tiles;
+    ea.records   = records;
+    ea.tile_cnt  = tile_cnt;
+    ea.em_base   = em_base;
+    ea.edge_base = ed_base;
+    ea.out       = e;
+    int grid = kNumSMs * 8;
+    if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
+    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, 256, 0, st>>>(ea));
+  }
+  unsigned long long h_tot[2];
+  uint32_t           h_flags[4];
+  MSGPU_CUDA(cudaMemcpyAsync(h_tot, totals, sizeof(h_tot), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaMemcpyAsync(h_flags, d_u32, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
   MSGPU_CUDA(cudaStreamSynchronize(st));
-  if (too_many)
+  if (h_flags[2])
     throw BuildError{MSGPU_ERR_LIMIT, "a read matches more than " + std::to_string(kSrcCap) + " unitigs with partners"};
-  if (totals[2] != 0)
-    throw BuildError{MSGPU_ERR_INTERNAL, "fused pairing: tile invariant violated (code " + std::to_string(totals[2]) + ")"};
-  e.n_em    = totals[0];
-  e.n_edges = totals[1];
+  if (h_flags[3])
+    throw BuildError{MSGPU_ERR_INTERNAL, "pairing: tile invariant violated (code " + std::to_string(h_flags[3]) + ")"};
+  e.n_em    = h_tot[0];
+  e.n_edges = h_tot[1];
 }
 
 void run_pairing(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
