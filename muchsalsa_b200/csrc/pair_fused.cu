@@ -45,7 +45,7 @@ namespace msgpu {
 
 constexpr int kThOverlapF = 100; // MatchMap.cpp:41
 
-constexpr int      kFusedBlock = 256;
+constexpr int      kFusedBlock = 512;
 constexpr int      kFusedWarps = kFusedBlock / 32;
 constexpr int      kIdxBits    = 12;
 constexpr uint32_t kTileCap    = 1u << kIdxBits; // candidates per tile
@@ -301,7 +301,7 @@ constexpr size_t kTileBytes = kSharedOff + 2 * kTileCap * sizeof(unsigned long l
 
 // Stable LSD radix sort of n words in shared memory on bits [lo, hi); warp w owns a contiguous block of items and
 // ranks it with __match_any_sync + per-warp digit counters, so equal digits keep their order.  Returns the buffer
-// that holds the result.  blockDim.x == 256.
+// that holds the result.  blockDim.x == kFusedBlock.
 template <class W> __device__ W *cta_radix_sort(TileShared &s, W *in, W *out, uint32_t n, int lo, int hi) {
   const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
   const int      kb = hi - lo;
@@ -312,43 +312,63 @@ template <class W> __device__ W *cta_radix_sort(TileShared &s, W *in, W *out, ui
   for (int shift = lo; shift < hi; shift += bits) {
     const int      b    = hi - shift < bits ? hi - shift : bits;
     const unsigned mask = (1u << b) - 1u;
-#pragma unroll
-    for (int ww = 0; ww < kFusedWarps; ++ww) s.warp_cnt[ww][t] = 0;
+    for (uint32_t z = t; z < kFusedWarps * 256; z += kFusedBlock) (&s.warp_cnt[0][0])[z] = 0;
     __syncthreads();
     W        word[kItems];
+    unsigned peer[kItems];
+    // peers of every item first (independent, so the votes pipeline), then the serial counter updates
+#pragma unroll
+    for (int it = 0; it < kItems; ++it) {
+      word[it] = W(0);
+      peer[it] = 0;
+      if (uint32_t(it) < per) {
+        const uint32_t idx   = wbase + it * 32 + l;
+        const bool     valid = idx < n;
+        const W        x     = valid ? in[idx] : W(0);
+        const unsigned d     = unsigned(x >> shift) & mask;
+        // lanes with the same digit, by one vote per digit bit (cost independent of how many digits are distinct)
+        const unsigned vb = __ballot_sync(0xffffffffu, valid);
+        unsigned       pm = valid ? vb : 0u;
+        for (int bit = 0; bit < b; ++bit) {
+          const bool     on  = (d >> bit) & 1u;
+          const unsigned bal = __ballot_sync(0xffffffffu, on);
+          pm &= on ? bal : ~bal;
+        }
+        word[it] = x;
+        peer[it] = pm; // 0 for lanes past the end
+      }
+    }
     uint16_t rank[kItems];
 #pragma unroll
     for (int it = 0; it < kItems; ++it) {
       if (uint32_t(it) < per) {
-        uint32_t idx   = wbase + it * 32 + l;
-        bool     valid = idx < n;
-        W        x     = valid ? in[idx] : W(0);
-        unsigned d     = valid ? (unsigned(x >> shift) & mask) : 256u; // lanes past the end form their own group
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        unsigned lead  = __ffs(peers) - 1;
-        uint32_t old   = 0;
-        if (l == lead && valid) {
+        const unsigned pm   = peer[it];
+        const unsigned d    = unsigned(word[it] >> shift) & mask;
+        const unsigned lead = pm ? unsigned(__ffs(pm) - 1) : l;
+        uint32_t       old  = 0;
+        if (pm && l == lead) {
           old              = s.warp_cnt[w][d];
-          s.warp_cnt[w][d] = old + __popc(peers);
+          s.warp_cnt[w][d] = old + __popc(pm);
         }
         old      = __shfl_sync(0xffffffffu, old, lead);
-        word[it] = x;
-        rank[it] = uint16_t(old + __popc(peers & ((1u << l) - 1u)));
+        rank[it] = uint16_t(old + __popc(pm & ((1u << l) - 1u)));
         __syncwarp();
       }
     }
     __syncthreads();
-    { // digit t: exclusive prefix over the warps, then over the digits
+    { // thread t < 256 owns digit t: exclusive prefix over the warps, then over the digits
       uint32_t sum = 0;
+      if (t < 256) {
 #pragma unroll
-      for (int ww = 0; ww < kFusedWarps; ++ww) {
-        uint32_t c        = s.warp_cnt[ww][t];
-        s.warp_cnt[ww][t] = sum;
-        sum += c;
+        for (int ww = 0; ww < kFusedWarps; ++ww) {
+          uint32_t c        = s.warp_cnt[ww][t];
+          s.warp_cnt[ww][t] = sum;
+          sum += c;
+        }
       }
       uint32_t total;
-      uint32_t ex   = block_exclusive_scan<uint32_t>(sum, s.scan, &total);
-      s.bin_base[t] = ex;
+      uint32_t ex = block_exclusive_scan<uint32_t>(sum, s.scan, &total);
+      if (t < 256) s.bin_base[t] = ex;
     }
     __syncthreads();
 #pragma unroll
@@ -607,37 +627,72 @@ struct EmitArgs {
   EdgeTables      out;
 };
 
+constexpr int kEmitBatch = 4; // records in flight per thread: the gathers are latency-bound, so overlap them
+
+__device__ __forceinline__ PairRow ld_row(const PairRow *p) { // two 128-bit read-only loads = one 32-byte sector
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4        x = __ldg(q), y = __ldg(q + 1);
+  PairRow      r;
+  r.ir0    = int32_t(x.x);
+  r.ir1    = int32_t(x.y);
+  r.read   = x.z;
+  r.score  = int32_t(x.w);
+  r.line   = y.x;
+  r.flags  = y.y;
+  r.unitig = y.z;
+  r.pad    = 0;
+  return r;
+}
+
 __global__ void __launch_bounds__(256) pair_emit_rows_kernel(EmitArgs a) {
   for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
     const uint32_t           n_valid = a.tile_cnt[ti].x;
     const unsigned long long em0 = a.em_base[ti], ed0 = a.edge_base[ti];
     const uint32_t           q0  = a.rd_off[a.tile_row[a.tile_lo + ti]];
     const uint2             *rec = a.records + uint64_t(ti) * kTileCap;
-    for (uint32_t k = threadIdx.x; k < n_valid; k += blockDim.x) {
-      const uint2    r  = rec[k];
-      const uint32_t ib = r.x, j = r.y & (kSrcCap - 1);
-      const PairRow  pa = a.rows[a.rd_src[q0 + j]], pb = a.rows[ib];
-      const int      a0 = pa.ir0, a1 = pa.ir1, b0 = pb.ir0, b1 = pb.ir1;
-      const int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
-      // MatchMap.cpp:195-202: score_x * common / len_x for the outer and the inner match, summed.  IEEE addition
-      // is commutative, so which of the two is "outer" (the later line) does not change the sum.  No FMA contraction.
-      const double common = double(ov1 - ov0 + 1);
-      const double sa     = double((unsigned long long)(long long)pa.score); // size_t widened from int
-      const double sbb    = double((unsigned long long)(long long)pb.score);
-      const double sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
-      const double sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
-      const unsigned long long o = em0 + k;
-      a.out.em_unitig[o] = pa.unitig;
-      a.out.em_ov0[o]    = ov0;
-      a.out.em_ov1[o]    = ov1;
-      a.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
-      a.out.em_line[o]   = pa.line > pb.line ? pa.line : pb.line; // outer = the later line (MatchMap.cpp:218)
-      a.out.em_flags[o]  = uint8_t((((pa.flags ^ pb.flags) & 1u) ? 0u : 1u) | ((pa.flags & pb.flags & 2u) ? 2u : 0u));
-      if (r.y & (1u << kSrcBits)) {
-        const unsigned long long eo = ed0 + (r.y >> (kSrcBits + 1));
-        a.out.first[eo]    = pa.read;
-        a.out.second[eo]   = pb.read;
-        a.out.em_begin[eo] = o;
+    for (uint32_t k0 = threadIdx.x; k0 < n_valid; k0 += blockDim.x * kEmitBatch) {
+      uint2 r[kEmitBatch];
+#pragma unroll
+      for (int u = 0; u < kEmitBatch; ++u) {
+        const uint32_t k = k0 + u * blockDim.x;
+        r[u]             = k < n_valid ? __ldg(rec + k) : make_uint2(0, 0);
+      }
+      uint32_t qa[kEmitBatch];
+#pragma unroll
+      for (int u = 0; u < kEmitBatch; ++u) qa[u] = __ldg(a.rd_src + q0 + (r[u].y & (kSrcCap - 1)));
+      PairRow pa[kEmitBatch], pb[kEmitBatch];
+#pragma unroll
+      for (int u = 0; u < kEmitBatch; ++u) {
+        pa[u] = ld_row(a.rows + qa[u]);
+        pb[u] = ld_row(a.rows + r[u].x);
+      }
+#pragma unroll
+      for (int u = 0; u < kEmitBatch; ++u) {
+        const uint32_t k = k0 + u * blockDim.x;
+        if (k >= n_valid) continue;
+        const int a0 = pa[u].ir0, a1 = pa[u].ir1, b0 = pb[u].ir0, b1 = pb[u].ir1;
+        const int ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
+        // MatchMap.cpp:195-202: score_x * common / len_x for the outer and the inner match, summed.  IEEE addition
+        // is commutative, so which of the two is "outer" (the later line) does not change the sum.  No FMA
+        // contraction (explicit _rn intrinsics, and the library is built with --fmad=false).
+        const double common = double(ov1 - ov0 + 1);
+        const double sa     = double((unsigned long long)(long long)pa[u].score); // size_t widened from int
+        const double sbb    = double((unsigned long long)(long long)pb[u].score);
+        const double sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
+        const double sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
+        const unsigned long long o = em0 + k;
+        a.out.em_unitig[o] = pa[u].unitig;
+        a.out.em_ov0[o]    = ov0;
+        a.out.em_ov1[o]    = ov1;
+        a.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
+        a.out.em_line[o]   = pa[u].line > pb[u].line ? pa[u].line : pb[u].line; // outer = later line (MatchMap.cpp:218)
+        a.out.em_flags[o]  = uint8_t((((pa[u].flags ^ pb[u].flags) & 1u) ? 0u : 1u) | ((pa[u].flags & pb[u].flags & 2u) ? 2u : 0u));
+        if (r[u].y & (1u << kSrcBits)) {
+          const unsigned long long eo = ed0 + (r[u].y >> (kSrcBits + 1));
+          a.out.first[eo]    = pa[u].read;
+          a.out.second[eo]   = pb[u].read;
+          a.out.em_begin[eo] = o;
+        }
       }
     }
   }
