@@ -103,8 +103,10 @@ def kernel_bytes(name, c, paf_bytes):
         "pair_count": 12 * M,                    # unitig ranges + read ids read once (pairing happens on chip)
         "gather_sorted": (12 + 25 + 25 + 1) * EM,
         "write_edges": 9 * EM + 16 * E,
-        # fused variant
-        "pair_fused": 29 * M + 25 * EM + 16 * E,  # every match read once, every edge match + edge written once
+        # product variant (pair_fused.cu): the tile kernel reads every match once (32 B row + 12 B of columns) and
+        # writes one 8 B record per edge match; the emit kernel reads the records and writes the tables once
+        "pair_tiles": 44 * M + 8 * EM,
+        "pair_emit_rows": 8 * EM + 32 * M + 25 * EM + 16 * E,
         # ingest
         "parse_lines": paf_bytes + 8 * c["n_lines"] + 50 * c["n_lines"],
         "newline_count": paf_bytes, "newline_write": paf_bytes + 8 * c["n_lines"],
@@ -120,65 +122,93 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    dev_t = torch.device("cuda", local)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev_t)
+    from muchsalsa_b200 import multi_gpu, synth
     from muchsalsa_b200.construct import GraphBuilder
 
-    if world > 1:
-        from muchsalsa_b200 import multi_gpu
-        out = multi_gpu.bench(args, rank, world, local, dist)
-        if rank == 0:
-            print(json.dumps(out))
-        dist.destroy_process_group()
-        return
-
-    paf = make_workload(args.workload)
+    # ---- workload: at N ranks the genome is N times longer and rank r holds the r-th contiguous chunk of the PAF
+    # (weak scaling: every GPU adds one base-size share; reads and unitigs of a boundary region meet in the merge)
+    if world == 1:
+        paf = make_workload(args.workload)
+    else:
+        cfg = synth.scaled(args.workload, world)
+        paf = synth.columns_to_paf(synth.generate_columns(cfg, (rank, world), sentinel=(rank == world - 1)))
     n_bytes = len(paf)
-    host = torch.frombuffer(bytearray(paf), dtype=torch.uint8).pin_memory()
+    host = torch.frombuffer(bytearray(paf) if n_bytes else bytearray(1), dtype=torch.uint8)[:n_bytes].pin_memory()
     dev = host.cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     gb = GraphBuilder(local)
     stream = torch.cuda.current_stream()
     gb.set_stream(stream.cuda_stream)
+    sb = multi_gpu.ShardedBuilder(gb, rank, world, dist, dev_t)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
 
     def step_device():
-        gb.build_from_device(dev.data_ptr(), n_bytes)
+        if world == 1:
+            gb.build_from_device(dev.data_ptr(), n_bytes)
+        else:
+            sb.build_device(dev.data_ptr(), n_bytes)
 
     def step_e2e():
-        gb.build_from_buffer(host)
+        if world == 1:
+            gb.build_from_buffer(host)
+        else:
+            sb.build_buffer(host)
         gb.host_tables()
+
+    def reduce(x, op):
+        if dist is None:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
 
     for _ in range(max(args.warmup, 3)):
         step_device()
     counts = gb.counts()
     torch.cuda.synchronize()
+    barrier()
 
-    # ---- timed region 1: device-resident throughput
+    # ---- timed region 1: device-resident throughput (CUDA events on the library's stream, max over ranks)
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = gb.launch_count()
-    ms = []
+    ms, xch_ms = [], []
     for _ in range(args.steps):
         flush.zero_()  # evict L2 between steps (not timed)
+        torch.cuda.synchronize()
+        barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         step_device()
         b.record(stream)
         b.synchronize()
         ms.append(a.elapsed_time(b))
+        if world > 1:
+            xch_ms.append(sb.last_exchange_ms())
+    torch.cuda.synchronize()
+    barrier()
     launches = gb.launch_count() - launches0
-    t_dev = sum(ms) / 1e3
+    t_dev = reduce(sum(ms) / 1e3, "MAX")
 
     # ---- timed region 2: end to end through the C ABI with host buffers
     for _ in range(2):
         step_e2e()
+    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
+    barrier()
+    t_e2e = reduce(time.perf_counter() - t0, "MAX")
     stage = gb.timings()
     clocks = sampler.summary()
 
@@ -212,33 +242,59 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": int(b), "us_per_launch": round(st["us_per_launch"], 2),
                 "share_of_step": round(st["ms_per_step"] / sum(v["ms_per_step"] for v in per_kernel.values()), 3)}
         break
+    # the whole pairing + merge (K6 + K7: plan, tile sort, tile scan, emit) against the bytes it must move
+    pm_kernels = ("rank_rows", "scatter_sources", "order_sources", "write_tiles", "split_heavy", "pair_tiles",
+                  "scan_tiles", "pair_emit_rows")
+    pm_ms = sum(per_kernel[k]["ms_per_step"] for k in pm_kernels if k in per_kernel)
+    if roof is not None and pm_ms > 0:
+        M, EM, E = counts["n_matches"], counts["n_edge_matches"], counts["n_edges"]
+        strict = 29 * M + 25 * EM + 16 * E                     # every match once, every edge match + edge once
+        survey = 3 * 40 * M + 3 * 40 * EM + 12 * E             # SURVEY.md §8(d) B_tot (sort-shaped passes)
+        roof["pairing_and_merge"] = {
+            "ms": round(pm_ms, 3), "bytes_written_once": int(strict),
+            "achieved_gbs": round(strict / pm_ms / 1e6, 1), "frac": round(strict / pm_ms / 1e6 / peak, 4),
+            "survey_8d_bytes": int(survey), "survey_8d_frac": round(survey / pm_ms / 1e6 / peak, 4)}
 
-    # ---- the reference's CPU path beside it (bounded sample, rank 0 only)
-    cpu = cpu_baseline(args.workload)
+    # ---- the reference's CPU path beside it (bounded sample, rank 0 at N = 1 only)
+    cpu = cpu_baseline(args.workload) if world == 1 else None
 
-    bytes_d2h = result_bytes(counts, gb)
+    n_edges = reduce(counts["n_edges"], "SUM")
+    n_em = reduce(counts["n_edge_matches"], "SUM")
+    bytes_d2h = reduce(result_bytes(counts, gb), "SUM")
+    bytes_h2d = reduce(n_bytes, "SUM")
     out = {
-        "metric": METRIC, "value": counts["n_matches"] * args.steps / t_dev, "unit": UNIT, "n_gpus": 1,
+        "metric": METRIC, "value": counts["n_matches"] * args.steps / t_dev, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32 keys + f64 scores",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}-scale synthetic PAF (muchsalsa_b200.synth, seed fixed)",
-                   "paf_bytes": n_bytes, "lines": counts["n_lines"], "kept_matches": counts["n_matches"],
+        "config": {"workload": f"{args.workload}-scale synthetic PAF x{world} (muchsalsa_b200.synth, seed fixed; at N "
+                               "GPUs the genome is N times longer and rank r holds the r-th chunk of the PAF)",
+                   "paf_bytes": int(bytes_h2d), "lines": counts["n_lines"], "kept_matches": counts["n_matches"],
                    "reads": counts["n_reads"], "unitigs": counts["n_unitigs"], "pairs": counts["n_pairs"],
-                   "edges": counts["n_edges"], "edge_matches": counts["n_edge_matches"],
+                   "edges": int(n_edges), "edge_matches": int(n_em),
                    "l2": "flushed between steps (256 MiB memset)", "matches_counted": "kept VertexMatch rows"},
-        "edges_per_s": counts["n_edges"] * args.steps / t_dev,
-        "edge_matches_per_s": counts["n_edge_matches"] * args.steps / t_dev,
-        "e2e": {"value": counts["n_matches"] * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": n_bytes,
-                "d2h_bytes_per_step": bytes_d2h, "ms_per_step": 1e3 * t_e2e / args.steps,
-                "edges_per_s": counts["n_edges"] * args.steps / t_e2e,
+        "edges_per_s": n_edges * args.steps / t_dev,
+        "edge_matches_per_s": n_em * args.steps / t_dev,
+        "e2e": {"value": counts["n_matches"] * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(bytes_h2d),
+                "d2h_bytes_per_step": int(bytes_d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
+                "edges_per_s": n_edges * args.steps / t_e2e,
                 "stages_ms_last_step": {k: round(v, 3) for k, v in stage.items()}},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "kernels": {k: {kk: round(vv, 3) for kk, vv in v.items()} for k, v in top[:12]},
         "variant": os.environ.get("MSGPU_VARIANT", "default"),
     }
+    if world > 1:
+        x = [v for v in xch_ms if v is not None]
+        x_ms = reduce(sum(x) / len(x), "MAX") if x else None
+        out["exchange"] = {"what": "all-gather of the ranks' match-table blobs (NCCL over NVLink)",
+                           "bytes_received_per_rank": sb.exchange_bytes, "ms": x_ms,
+                           "gbs_per_rank": (sb.exchange_bytes / x_ms / 1e6) if x_ms else None,
+                           "nvlink_peak_gbs": 770.0}
     gb.close()
-    print(json.dumps(out))
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def result_bytes(c, gb):
@@ -360,7 +416,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("MSGPU_WORKLOAD", "ecoli"))
+    ap.add_argument("--workload", default=os.environ.get("MSGPU_WORKLOAD", "yeast"))
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -93,6 +93,33 @@ typedef struct msgpu_match_soa {
 int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *dev_records, uint32_t n_reads,
                              uint32_t n_unitigs);
 
+/* ---- multi-GPU construction (one context = one GPU = one process; the caller moves bytes between ranks) ------------
+ * The reference has no distributed mode (its only parallelism is one in-process ThreadPool, ThreadPool.cpp:38-91);
+ * these entry points produce the reference's single-threaded result on the WHOLE PAF from N GPUs:
+ *
+ *   1. msgpu_shard_ingest_*   rank r parses the r-th contiguous chunk of the PAF (split at line boundaries; only the
+ *                             last chunk drops its last line, BlastFileReader.cpp:76) -> chunk-local tables
+ *   2. msgpu_shard_describe / msgpu_shard_export   the chunk-local tables as ONE flat device blob; the ranks
+ *                             all-gather headers and blobs (NCCL over NVLink: torch.distributed.all_gather_into_tensor)
+ *   3. msgpu_build_from_shards   every rank merges all blobs into the global id space (ids = rank of first accepted
+ *                             line over the whole file, keep-min-line across chunks, Registry.cpp:36-45,
+ *                             MatchMap.cpp:64-73) and pairs ITS share `part` of `n_parts` of the edge rows.
+ * After step 3 the read / unitig / match tables of the result are global (identical on every rank) and the edge /
+ * edge-match tables are the rank's contiguous slice of the global (first, second)-sorted tables; concatenating the
+ * slices in rank order gives exactly the single-GPU result (edge_em_begin is relative to the slice).
+ * Only match records cross NVLink; candidate pairs (two orders of magnitude more) never leave their GPU. */
+typedef struct msgpu_shard_header {
+  uint64_t magic, n_lines, n_reads, n_unitigs, n_matches, read_name_bytes, unitig_name_bytes, blob_bytes;
+} msgpu_shard_header;
+
+int msgpu_shard_ingest_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes, int is_last_shard);
+int msgpu_shard_ingest_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes, int is_last_shard);
+int msgpu_shard_describe(const msgpu_ctx *ctx, msgpu_shard_header *out);
+/* writes blob_bytes bytes (see msgpu_shard_describe) to dev_blob, on the context's stream */
+int msgpu_shard_export(msgpu_ctx *ctx, void *dev_blob, uint64_t capacity);
+int msgpu_build_from_shards(msgpu_ctx *ctx, uint32_t n_shards, const msgpu_shard_header *headers,
+                            const void *const *dev_blobs, uint32_t part, uint32_t n_parts);
+
 typedef struct msgpu_counts {
   uint64_t n_lines;   /* lines in the buffer (BlastFileAccessor::getLineCount) */
   uint64_t n_reads;   /* graph order */

@@ -44,6 +44,11 @@ class MatchSoA(C.Structure):
                 ("line", C.c_void_p), ("flags", C.c_void_p)]
 
 
+class ShardHeader(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("magic", "n_lines", "n_reads", "n_unitigs", "n_matches", "read_name_bytes",
+                                          "unitig_name_bytes", "blob_bytes")]
+
+
 class SeqReq(C.Structure):
     _fields_ = [("which", C.c_uint32), ("id", C.c_uint32), ("left", C.c_int32), ("right", C.c_int32),
                 ("direction", C.c_uint32)]
@@ -60,6 +65,12 @@ SIGNATURES = {
     "msgpu_build_from_paf_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "msgpu_build_from_paf_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "msgpu_build_from_records": (C.c_int, [C.c_void_p, C.POINTER(MatchSoA), C.c_uint32, C.c_uint32]),
+    "msgpu_shard_ingest_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "msgpu_shard_ingest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "msgpu_shard_describe": (C.c_int, [C.c_void_p, C.POINTER(ShardHeader)]),
+    "msgpu_shard_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "msgpu_build_from_shards": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ShardHeader), C.POINTER(C.c_void_p),
+                                          C.c_uint32, C.c_uint32]),
     "msgpu_result_counts": (C.c_int, [C.c_void_p, C.POINTER(Counts)]),
     "msgpu_result_device": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),
     "msgpu_result_host": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),

@@ -117,6 +117,35 @@ class GraphBuilder:
         self._check(self._lib.msgpu_build_from_records(self._h, C.byref(soa), n_reads, n_unitigs))
         return self
 
+    # ---- multi-GPU construction (see muchsalsa_b200/multi_gpu.py for the collectives between the steps)
+    def shard_ingest_buffer(self, buf, is_last_shard: bool):
+        ptr, n, keep = _host_ptr(buf)
+        self._keep = keep
+        self._check(self._lib.msgpu_shard_ingest_buffer(self._h, C.c_void_p(ptr), n, 1 if is_last_shard else 0))
+        return self
+
+    def shard_ingest_device(self, dev_ptr: int, n_bytes: int, is_last_shard: bool):
+        self._check(self._lib.msgpu_shard_ingest_device(self._h, C.c_void_p(dev_ptr), n_bytes,
+                                                        1 if is_last_shard else 0))
+        return self
+
+    def shard_header(self) -> "_lib.ShardHeader":
+        h = _lib.ShardHeader()
+        self._check(self._lib.msgpu_shard_describe(self._h, C.byref(h)))
+        return h
+
+    def shard_export(self, dev_ptr: int, capacity: int):
+        self._check(self._lib.msgpu_shard_export(self._h, C.c_void_p(dev_ptr), capacity))
+        return self
+
+    def build_from_shards(self, headers, blob_ptrs, part: int, n_parts: int):
+        """headers: list of _lib.ShardHeader (one per rank, rank order); blob_ptrs: device pointers of the blobs."""
+        n = len(headers)
+        hs = (_lib.ShardHeader * n)(*headers)
+        ps = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in blob_ptrs])
+        self._check(self._lib.msgpu_build_from_shards(self._h, n, hs, ps, part, n_parts))
+        return self
+
     # ---- results
     def counts(self) -> dict:
         c = _lib.Counts()

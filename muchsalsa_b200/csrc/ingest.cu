@@ -372,10 +372,10 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    check_grouped_kernel(const uint32_t *__restrict__ unitig, uint64_t n, IngestStatus *status) {
+    check_grouped_kernel(const uint32_t *__restrict__ unitig, uint64_t n, uint32_t *unsorted) {
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x + 1; i < n;
        i += uint64_t(gridDim.x) * blockDim.x)
-    if (unitig[i] < unitig[i - 1]) status->unsorted = 1;
+    if (unitig[i] < unitig[i - 1]) *unsorted = 1;
 }
 
 template <class T>
@@ -448,8 +448,52 @@ void build_group_offsets(Arena &arena, cudaStream_t st, const MatchSoA &m, Uniti
   MSGPU_LAUNCH("group_bounds", st, group_bounds_kernel<<<grid_for(m.n + 1, 256), 256, 0, st>>>(m.unitig, m.n, uint32_t(unitigs.n), unitigs.grp_off));
 }
 
+void alloc_match_soa(Arena &arena, MatchSoA &s, uint64_t M) {
+  s.n      = M;
+  s.unitig = arena.alloc<uint32_t>(M);
+  s.read   = arena.alloc<uint32_t>(M);
+  s.ir0    = arena.alloc<int32_t>(M);
+  s.ir1    = arena.alloc<int32_t>(M);
+  s.nr0    = arena.alloc<int32_t>(M);
+  s.nr1    = arena.alloc<int32_t>(M);
+  s.score  = arena.alloc<int32_t>(M);
+  s.line   = arena.alloc<uint32_t>(M);
+  s.flags  = arena.alloc<uint8_t>(M);
+  s.rratio = arena.alloc<double>(M);
+}
+
+// Rows arrive in line order.  If they are not already grouped by unitig id (minimap2 emits by query, so they normally
+// are), a stable sort by unitig id groups them and keeps the line order inside a unitig.
+void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &m, uint64_t n_unitigs) {
+  const uint64_t M = m.n;
+  if (M <= 1) return;
+  uint32_t *d_unsorted = arena.alloc<uint32_t>(1);
+  MSGPU_CUDA(cudaMemsetAsync(d_unsorted, 0, sizeof(uint32_t), st));
+  MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, M, d_unsorted));
+  if (!read_back(st, d_unsorted)) return;
+  uint32_t *keys = arena.alloc<uint32_t>(M), *keys2 = arena.alloc<uint32_t>(M);
+  uint32_t *idx = arena.alloc<uint32_t>(M), *idx2 = arena.alloc<uint32_t>(M);
+  int       g = grid_for(M, 256);
+  MSGPU_CUDA(cudaMemcpyAsync(keys, m.unitig, M * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  MSGPU_LAUNCH("iota", st, iota_kernel<<<g, 256, 0, st>>>(idx, M));
+  radix_sort_pairs<uint32_t, uint32_t>(arena, st, keys, idx, keys2, idx2, M, {0, bits_for(n_unitigs ? n_unitigs : 1)});
+  MatchSoA s;
+  alloc_match_soa(arena, s, M);
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.unitig, idx, M, s.unitig));
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.read, idx, M, s.read));
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.ir0, idx, M, s.ir0));
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.ir1, idx, M, s.ir1));
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.nr0, idx, M, s.nr0));
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.nr1, idx, M, s.nr1));
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.score, idx, M, s.score));
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.line, idx, M, s.line));
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.flags, idx, M, s.flags));
+  MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.rratio, idx, M, s.rratio));
+  m = s;
+}
+
 void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
-                ReadTable &reads, UnitigTable &unitigs, MatchSoA &m) {
+                ReadTable &reads, UnitigTable &unitigs, MatchSoA &m, bool drop_last_line) {
   reads = ReadTable{};
   unitigs = UnitigTable{};
   m = MatchSoA{};
@@ -476,8 +520,9 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   MSGPU_LAUNCH("line_index_finish", st, line_index_finish_kernel<<<1, 1, 0, st>>>(d_paf, n_bytes, d_n_nl, line_start, d_nlines));
   uint64_t n_lines = read_back(st, d_nlines);
   *n_lines_out     = n_lines;
-  // BlastFileReader::read(): lines 0 .. lineCount-2 (BlastFileReader.cpp:76)
-  uint64_t n_parse = n_lines ? n_lines - 1 : 0;
+  // BlastFileReader::read(): lines 0 .. lineCount-2 (BlastFileReader.cpp:76).  A shard of a PAF that is not the last
+  // one keeps its last line: only the last line of the whole file is never parsed.
+  uint64_t n_parse = drop_last_line ? (n_lines ? n_lines - 1 : 0) : n_lines;
 
   IngestStatus *d_status = arena.alloc<IngestStatus>(1);
   IngestStatus  h_status{~0ull, 0, 0, 0, 0};
@@ -557,48 +602,11 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   // ---- K5 compaction (+ grouping sort when the PAF is not grouped by unitig)
   exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFSurvivor}, n_parse, rank_a, d_cnt + 2);
   uint64_t M = read_back(st, d_cnt + 2);
-  auto alloc_soa = [&](MatchSoA &s) {
-    s.n      = M;
-    s.unitig = arena.alloc<uint32_t>(M);
-    s.read   = arena.alloc<uint32_t>(M);
-    s.ir0    = arena.alloc<int32_t>(M);
-    s.ir1    = arena.alloc<int32_t>(M);
-    s.nr0    = arena.alloc<int32_t>(M);
-    s.nr1    = arena.alloc<int32_t>(M);
-    s.score  = arena.alloc<int32_t>(M);
-    s.line   = arena.alloc<uint32_t>(M);
-    s.flags  = arena.alloc<uint8_t>(M);
-    s.rratio = arena.alloc<double>(M);
-  };
-  alloc_soa(m);
+  alloc_match_soa(arena, m, M);
   if (n_parse) {
     MSGPU_LAUNCH("compact_matches", st, compact_matches_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f, rank_a, rid_of_line, uid_of_line, m));
   }
-  if (M > 1) {
-    MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, M, d_status));
-  }
-  if (read_back(st, d_status).unsorted) {
-    // stable sort by unitig id keeps the line order inside a unitig (rows are in line order now)
-    uint32_t *keys = arena.alloc<uint32_t>(M), *keys2 = arena.alloc<uint32_t>(M);
-    uint32_t *idx = arena.alloc<uint32_t>(M), *idx2 = arena.alloc<uint32_t>(M);
-    int       g = grid_for(M, 256);
-    MSGPU_CUDA(cudaMemcpyAsync(keys, m.unitig, M * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-    MSGPU_LAUNCH("iota", st, iota_kernel<<<g, 256, 0, st>>>(idx, M));
-    radix_sort_pairs<uint32_t, uint32_t>(arena, st, keys, idx, keys2, idx2, M, {0, bits_for(n_unitigs)});
-    MatchSoA s;
-    alloc_soa(s);
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.unitig, idx, M, s.unitig));
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.read, idx, M, s.read));
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.ir0, idx, M, s.ir0));
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.ir1, idx, M, s.ir1));
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.nr0, idx, M, s.nr0));
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.nr1, idx, M, s.nr1));
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.score, idx, M, s.score));
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.line, idx, M, s.line));
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.flags, idx, M, s.flags));
-    MSGPU_LAUNCH("gather", st, gather_kernel<<<g, 256, 0, st>>>(m.rratio, idx, M, s.rratio));
-    m = s;
-  }
+  group_by_unitig(arena, st, m, n_unitigs);
   build_group_offsets(arena, st, m, unitigs);
 }
 

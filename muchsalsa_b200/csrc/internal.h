@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <string>
 
+#include "../../include/msgpu.h"
 #include "common.cuh"
 
 namespace msgpu {
@@ -54,7 +55,10 @@ struct BuildError {
 
 // ingest.cu : PAF text in HBM -> read table, unitig table (+ group offsets), match SoA   (K1-K5)
 void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
-                ReadTable &reads, UnitigTable &unitigs, MatchSoA &matches);
+                ReadTable &reads, UnitigTable &unitigs, MatchSoA &matches, bool drop_last_line = true);
+void alloc_match_soa(Arena &arena, MatchSoA &s, uint64_t n);
+// stable sort of the rows by unitig id unless they are grouped already
+void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &matches, uint64_t n_unitigs);
 // group offsets for records that arrive already packed (msgpu_build_from_records)
 void build_group_offsets(Arena &arena, cudaStream_t st, const MatchSoA &matches, UnitigTable &unitigs);
 
@@ -71,5 +75,20 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &matches, c
 // picks the variant: fused unless MSGPU_VARIANT=sorted (kept as an independent cross-check of the fused kernel)
 void run_pairing(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs, uint64_t n_reads,
                  EdgeTables &edges, cudaEvent_t ev_pair_done, uint32_t part = 0, uint32_t n_parts = 1);
+
+// shard.cu : multi-GPU construction.  One rank's ingest result travels as a flat blob (header + the arrays below, each
+// section 16-byte aligned); run_shard_merge turns all ranks' blobs into the global read / unitig / match tables.
+struct ShardLayout { // byte offsets of the sections of a blob
+  uint64_t read_nlen, read_line, read_name_off, read_names, unitig_name_off, unitig_names;
+  uint64_t m_unitig, m_read, m_ir0, m_ir1, m_nr0, m_nr1, m_score, m_line, m_rratio, m_flags, total;
+};
+ShardLayout        shard_layout(const msgpu_shard_header &h);
+msgpu_shard_header shard_describe(uint64_t n_lines, const ReadTable &reads, const UnitigTable &unitigs,
+                                  const MatchSoA &matches);
+void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable &reads, const UnitigTable &unitigs,
+                  const MatchSoA &matches, void *dev_blob);
+void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msgpu_shard_header *headers,
+                     const void *const *dev_blobs, uint64_t *n_lines_out, ReadTable &reads, UnitigTable &unitigs,
+                     MatchSoA &matches);
 
 } // namespace msgpu

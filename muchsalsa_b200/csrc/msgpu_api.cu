@@ -113,17 +113,25 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
-// device part of a build: PAF text in HBM -> all tables in HBM
-void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes) {
+// device part of a build: PAF text in HBM -> all tables in HBM.  pair = false: ingest only (one shard of a
+// multi-GPU build); the edge tables stay empty.
+void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes, bool pair = true, bool drop_last_line = true) {
   cudaStream_t st  = ctx->stream;
   ctx->have_result = false;
   ctx->host_valid  = false;
   ctx->arena.reset();
   ctx->profiler.clear();
   MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
-  run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches);
+  run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches, drop_last_line);
   MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
-  run_pairing(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3]);
+  if (pair) {
+    run_pairing(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3]);
+  } else {
+    ctx->edges          = EdgeTables{};
+    ctx->edges.em_begin = ctx->arena.alloc<uint64_t>(1);
+    MSGPU_CUDA(cudaMemsetAsync(ctx->edges.em_begin, 0, sizeof(uint64_t), st));
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[3], st));
+  }
   MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
   MSGPU_CUDA(cudaStreamSynchronize(st));
   ctx->timings.ingest_ms = elapsed(ctx->ev[1], ctx->ev[2]);
@@ -134,13 +142,13 @@ void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes) {
   ctx->have_result = true;
 }
 
-void build_host(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes) {
+void build_host(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes, bool pair = true, bool drop_last_line = true) {
   cudaStream_t st = ctx->stream;
   ctx->input_arena.reset();
   char *d_paf = ctx->input_arena.alloc<char>(n_bytes + 16);
   MSGPU_CUDA(cudaEventRecord(ctx->ev[0], st));
   if (n_bytes) MSGPU_CUDA(cudaMemcpyAsync(d_paf, host_paf, n_bytes, cudaMemcpyHostToDevice, st));
-  build_device(ctx, d_paf, n_bytes);
+  build_device(ctx, d_paf, n_bytes, pair, drop_last_line);
   ctx->timings.h2d_ms = elapsed(ctx->ev[0], ctx->ev[1]);
   ctx->timings.total_ms += ctx->timings.h2d_ms;
 }
@@ -269,6 +277,62 @@ int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t 
     build_group_offsets(ctx->arena, st, m, ctx->unitigs);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
     run_pairing(ctx->arena, st, m, ctx->unitigs, n_reads, ctx->edges, ctx->ev[3]);
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
+    MSGPU_CUDA(cudaStreamSynchronize(st));
+    ctx->timings           = msgpu_timings{};
+    ctx->timings.ingest_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+    ctx->timings.pair_ms   = elapsed(ctx->ev[2], ctx->ev[3]);
+    ctx->timings.merge_ms  = elapsed(ctx->ev[3], ctx->ev[4]);
+    ctx->timings.total_ms  = elapsed(ctx->ev[1], ctx->ev[4]);
+    ctx->have_result       = true;
+  });
+}
+
+int msgpu_shard_ingest_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes, int is_last_shard) {
+  return guarded(ctx, [&] {
+    if (!dev_paf && n_bytes) throw BuildError{MSGPU_ERR_INVALID_ARG, "null PAF buffer"};
+    build_device(ctx, dev_paf, n_bytes, false, is_last_shard != 0);
+  });
+}
+
+int msgpu_shard_ingest_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes, int is_last_shard) {
+  return guarded(ctx, [&] {
+    if (!host_paf && n_bytes) throw BuildError{MSGPU_ERR_INVALID_ARG, "null PAF buffer"};
+    build_host(ctx, host_paf, n_bytes, false, is_last_shard != 0);
+  });
+}
+
+int msgpu_shard_describe(const msgpu_ctx *ctx, msgpu_shard_header *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->have_result || !ctx->reads.name_off) return MSGPU_ERR_NO_RESULT;
+  *out = shard_describe(ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches);
+  return MSGPU_OK;
+}
+
+int msgpu_shard_export(msgpu_ctx *ctx, void *dev_blob, uint64_t capacity) {
+  return guarded(ctx, [&] {
+    if (!ctx->have_result || !ctx->reads.name_off) throw BuildError{MSGPU_ERR_NO_RESULT, "no ingest result to export"};
+    msgpu_shard_header h = shard_describe(ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches);
+    if (!dev_blob || capacity < h.blob_bytes) throw BuildError{MSGPU_ERR_INVALID_ARG, "blob buffer too small"};
+    shard_export(ctx->stream, h, ctx->reads, ctx->unitigs, ctx->matches, dev_blob);
+  });
+}
+
+int msgpu_build_from_shards(msgpu_ctx *ctx, uint32_t n_shards, const msgpu_shard_header *headers,
+                            const void *const *dev_blobs, uint32_t part, uint32_t n_parts) {
+  return guarded(ctx, [&] {
+    if (!n_shards || !headers || !dev_blobs || !n_parts || part >= n_parts)
+      throw BuildError{MSGPU_ERR_INVALID_ARG, "bad shard arguments"};
+    cudaStream_t st  = ctx->stream;
+    ctx->have_result = false;
+    ctx->host_valid  = false;
+    ctx->arena.reset();
+    ctx->profiler.clear();
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
+    run_shard_merge(ctx->arena, st, n_shards, headers, dev_blobs, &ctx->n_lines, ctx->reads, ctx->unitigs,
+                    ctx->matches);
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
+    run_pairing(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3], part, n_parts);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
     MSGPU_CUDA(cudaStreamSynchronize(st));
     ctx->timings           = msgpu_timings{};

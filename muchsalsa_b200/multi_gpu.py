@@ -1,0 +1,120 @@
+"""Multi-GPU graph construction: one process per GPU, `torch.distributed` for the two collectives between the stages
+of the C ABI (include/msgpu.h, "multi-GPU construction").
+
+    rank r:  chunk r of the PAF --msgpu_shard_ingest--> chunk-local tables --msgpu_shard_export--> flat blob
+    all ranks: all-gather(headers), all-gather(blobs)            <- the only bytes that cross NVLink (match records)
+    rank r:  msgpu_build_from_shards(all blobs, part=r, n_parts=N)  -> global read/unitig/match tables (replicated)
+                                                                     + rank r's contiguous slice of the edge tables
+
+The reference is a single process with a thread pool (src/main.cpp:143-157); SURVEY.md §8e derives the sharding: the
+unit of pairing is one unitig's group, the reduction key is the read pair.  Here the rows of the edge table (all edge
+matches whose `first` is one read) are the unit that is partitioned, so every rank needs the whole match table (small)
+and no candidate pair is ever exchanged.
+
+The collectives work on CPU tensors with the `gloo` backend too (tests/test_multi_cpu.py exercises them with two
+processes); everything that touches the GPU goes through muchsalsa_b200.construct.GraphBuilder.
+"""
+from __future__ import annotations
+
+import time
+
+import torch
+
+from . import _lib
+
+HEADER_WORDS = 8  # msgpu_shard_header = 8 x uint64
+
+
+def split_paf(paf: bytes, n: int) -> list[bytes]:
+    """n contiguous chunks of about equal size, cut after a newline.  Concatenated they are the input again."""
+    cuts = [0]
+    for r in range(1, n):
+        want = max(cuts[-1], len(paf) * r // n)
+        nl = paf.find(b"\n", want)
+        cuts.append(len(paf) if nl < 0 else nl + 1)
+    cuts.append(len(paf))
+    return [paf[cuts[i]:cuts[i + 1]] for i in range(n)]
+
+
+def header_to_tensor(h: "_lib.ShardHeader", device) -> torch.Tensor:
+    vals = [int(getattr(h, name)) for name, _ in h._fields_]
+    # uint64 magic does not fit int64 as a positive number: carry the bit pattern
+    vals = [v - (1 << 64) if v >= (1 << 63) else v for v in vals]
+    return torch.tensor(vals, dtype=torch.int64, device=device)
+
+
+def tensor_to_headers(t: torch.Tensor) -> list:
+    out = []
+    for row in t.cpu().tolist():
+        h = _lib.ShardHeader()
+        for (name, _), v in zip(h._fields_, row):
+            setattr(h, name, v + (1 << 64) if v < 0 else v)
+        out.append(h)
+    return out
+
+
+def gather_headers(local: torch.Tensor, world: int, dist) -> torch.Tensor:
+    """[HEADER_WORDS] int64 on every rank -> [world, HEADER_WORDS] (rank order), on the same device."""
+    out = torch.empty(world * HEADER_WORDS, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(out, local)
+    return out.view(world, HEADER_WORDS)
+
+
+def gather_blobs(mine: torch.Tensor, world: int, dist) -> torch.Tensor:
+    """Every rank contributes `mine` (uint8, the same padded length on all ranks) -> [world, len] in rank order."""
+    out = torch.empty(world * mine.numel(), dtype=torch.uint8, device=mine.device)
+    dist.all_gather_into_tensor(out, mine)
+    return out.view(world, mine.numel())
+
+
+class ShardedBuilder:
+    """The N-GPU construction step of one rank.  `dist` is torch.distributed (initialised) or None for world == 1."""
+
+    def __init__(self, builder, rank: int, world: int, dist, device):
+        self.gb, self.rank, self.world, self.dist, self.device = builder, rank, world, dist, device
+        self.exchange_bytes = 0   # bytes this rank received from the others in the last step
+        self.exchange_ms = None   # device time of the blob all-gather of the last step (CUDA events), if on a GPU
+        self._keep = None
+
+    def _exchange(self):
+        gb, world = self.gb, self.world
+        h = gb.shard_header()
+        heads = gather_headers(header_to_tensor(h, self.device), world, self.dist) if world > 1 else \
+            header_to_tensor(h, self.device).view(1, HEADER_WORDS)
+        headers = tensor_to_headers(heads)  # device -> host: the sizes decide the allocations below
+        stride = (max(int(x.blob_bytes) for x in headers) + 255) & ~255
+        mine = torch.empty(stride, dtype=torch.uint8, device=self.device)
+        gb.shard_export(mine.data_ptr(), stride)
+        if world > 1:
+            on_gpu = mine.is_cuda
+            if on_gpu:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            blobs = gather_blobs(mine, world, self.dist)
+            if on_gpu:
+                b.record()
+                self._events = (a, b)
+        else:
+            blobs = mine.view(1, stride)
+        self.exchange_bytes = sum(int(x.blob_bytes) for i, x in enumerate(headers) if i != self.rank)
+        self._keep = (mine, blobs)
+        return headers, [blobs.data_ptr() + s * stride for s in range(world)]
+
+    def build_device(self, dev_ptr: int, n_bytes: int):
+        self.gb.shard_ingest_device(dev_ptr, n_bytes, self.rank == self.world - 1)
+        headers, ptrs = self._exchange()
+        self.gb.build_from_shards(headers, ptrs, self.rank, self.world)
+        return self.gb
+
+    def build_buffer(self, host_buf):
+        self.gb.shard_ingest_buffer(host_buf, self.rank == self.world - 1)
+        headers, ptrs = self._exchange()
+        self.gb.build_from_shards(headers, ptrs, self.rank, self.world)
+        return self.gb
+
+    def last_exchange_ms(self):
+        ev = getattr(self, "_events", None)
+        if not ev:
+            return None
+        ev[1].synchronize()
+        return ev[0].elapsed_time(ev[1])

@@ -60,11 +60,13 @@ def _expand_ranges(lo: np.ndarray, hi: np.ndarray):
     return owner, start + (np.arange(tot, dtype=np.int64) - first)
 
 
-def generate_columns(cfg: SynthConfig, shard: tuple[int, int] | None = None) -> dict:
+def generate_columns(cfg: SynthConfig, shard: tuple[int, int] | None = None, sentinel: bool = True) -> dict:
     """Integer PAF columns of the workload, in file order (grouped by unitig), sentinel line included.
 
     shard=(r, n): keep only the unitigs of the r-th of n contiguous genome slices (multi-GPU input sharding happens at
     unitig boundaries); ids stay global so shards can be compared with the unsharded run.
+    sentinel=False omits the trailing sentinel line: the chunks of ONE file that is split over ranks carry it only on
+    the last chunk (only the last line of the whole file is never parsed).
     """
     rng = np.random.Generator(np.random.PCG64(cfg.seed))
     G = cfg.genome
@@ -152,7 +154,7 @@ def generate_columns(cfg: SynthConfig, shard: tuple[int, int] | None = None) -> 
     # sentinel (dropped by the reader): a copy of the first line, or a dummy when the shard is empty
     for k in cols:
         tail = cols[k][:1] if n else np.array([1000 if k in ("ulen", "rlen", "c3", "c8", "c10") else 0], np.int64)
-        cols[k] = np.concatenate([cols[k], tail]).astype(np.int64)
+        cols[k] = np.concatenate([cols[k], tail] if sentinel else [cols[k]]).astype(np.int64)
     cols["n_unitigs"] = n_u
     cols["n_reads"] = n_r
     # genome geometry, for generate_sequences
@@ -182,10 +184,18 @@ def columns_to_paf(cols: dict, unitig_prefix: str = "u", read_prefix: str = "r")
     return "".join(line.tolist()).encode("ascii")
 
 
-def generate_paf(cfg: SynthConfig | str, shard: tuple[int, int] | None = None) -> bytes:
+def generate_paf(cfg: SynthConfig | str, shard: tuple[int, int] | None = None, sentinel: bool = True) -> bytes:
     if isinstance(cfg, str):
         cfg = CONFIGS[cfg]
-    return columns_to_paf(generate_columns(cfg, shard))
+    return columns_to_paf(generate_columns(cfg, shard, sentinel))
+
+
+def scaled(cfg: SynthConfig | str, factor: int) -> SynthConfig:
+    """The same shape on a `factor` times longer genome (weak scaling: one base-size share per GPU)."""
+    import dataclasses
+    if isinstance(cfg, str):
+        cfg = CONFIGS[cfg]
+    return cfg if factor == 1 else dataclasses.replace(cfg, name=f"{cfg.name}x{factor}", genome=cfg.genome * factor)
 
 
 _COMP = np.arange(256, dtype=np.uint8)

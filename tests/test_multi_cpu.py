@@ -1,0 +1,78 @@
+"""CPU tests of the multi-GPU host logic: PAF chunking and the two collectives of muchsalsa_b200.multi_gpu, run with two
+processes over the gloo backend (the same code path NCCL takes on the GPU box)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from muchsalsa_b200 import _lib, multi_gpu, synth
+
+
+def test_split_paf_is_a_partition_at_line_boundaries():
+    paf = synth.generate_paf("small")
+    for n in (1, 2, 3, 5, 8):
+        chunks = multi_gpu.split_paf(paf, n)
+        assert len(chunks) == n and b"".join(chunks) == paf
+        assert all(c.endswith(b"\n") for c in chunks[:-1] if c)
+    # more ranks than lines: trailing chunks are empty, nothing is lost
+    tiny = b"a\tb\nc\td\n"
+    chunks = multi_gpu.split_paf(tiny, 5)
+    assert b"".join(chunks) == tiny and len(chunks) == 5
+    assert multi_gpu.split_paf(b"", 3) == [b"", b"", b""]
+
+
+def test_header_tensor_round_trip():
+    h = _lib.ShardHeader()
+    for i, (name, _) in enumerate(h._fields_):
+        setattr(h, name, 0x3144524853534d47 if name == "magic" else (1 << 40) + i)
+    h.magic = 0xF144524853534D47  # top bit set: must survive the int64 transport
+    back = multi_gpu.tensor_to_headers(multi_gpu.header_to_tensor(h, "cpu").view(1, -1))[0]
+    assert all(getattr(back, n) == getattr(h, n) for n, _ in h._fields_)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank owns a blob of a different size; sizes travel first, then the padded blobs
+        n_local = 1000 + 777 * rank
+        blob = torch.from_numpy(np.random.default_rng(rank).integers(0, 256, n_local, dtype=np.uint8))
+        h = _lib.ShardHeader()
+        h.magic, h.n_lines, h.n_reads, h.blob_bytes = 0x3144524853534D47, 10 + rank, 5 * rank, n_local
+        heads = multi_gpu.gather_headers(multi_gpu.header_to_tensor(h, "cpu"), world, dist)
+        headers = multi_gpu.tensor_to_headers(heads)
+        stride = (max(int(x.blob_bytes) for x in headers) + 255) & ~255
+        mine = torch.zeros(stride, dtype=torch.uint8)
+        mine[:n_local] = blob
+        allb = multi_gpu.gather_blobs(mine, world, dist)
+        ok = [int(x.n_lines) for x in headers] == [10 + r for r in range(world)]
+        for r in range(world):
+            want = np.random.default_rng(r).integers(0, 256, 1000 + 777 * r, dtype=np.uint8)
+            ok = ok and np.array_equal(allb[r, :int(headers[r].blob_bytes)].numpy(), want)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_variable_size_all_gather_over_gloo_world_2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == [(0, True), (1, True)]

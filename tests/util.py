@@ -178,3 +178,22 @@ def heavy_rows_paf(k0=3000, k1=2500, shared_from=1000, seed=11, small_groups=40)
     rows.sort(key=lambda t: t[0])
     sentinel = L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
     return b"".join(r[1] for r in rows) + sentinel
+
+
+def merge_parts(parts):
+    """Concatenate the per-rank results of a multi-GPU construction (rank order) into one Construction: the global
+    tables are taken from rank 0 (they are replicated), the edge slices are appended."""
+    import copy
+    out = copy.copy(parts[0])
+    out.edge_first = np.concatenate([p.edge_first for p in parts])
+    out.edge_second = np.concatenate([p.edge_second for p in parts])
+    begins, base = [], 0
+    for p in parts:
+        begins.append(p.edge_em_begin[:-1].astype(np.uint64) + np.uint64(base))
+        base += int(p.edge_em_begin[-1])
+    out.edge_em_begin = np.concatenate(begins + [np.array([base], np.uint64)])
+    out.edge_matches = {k: np.concatenate([p.edge_matches[k] for p in parts]) for k in parts[0].edge_matches}
+    out.counts = dict(parts[0].counts)
+    out.counts["n_edges"] = int(out.edge_first.size)
+    out.counts["n_edge_matches"] = base
+    return out
