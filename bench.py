@@ -292,7 +292,7 @@ def run_ours(args):
                            "nvlink_peak_gbs": 770.0}
     gb.close()
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -410,7 +410,16 @@ def run_reference(args):
         os.unlink(path)
 
 
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner there) get stderr instead."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(keep, "w")
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

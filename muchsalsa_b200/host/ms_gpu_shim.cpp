@@ -1,0 +1,123 @@
+// ms_gpu_shim.cpp — see ms_gpu_shim.h.  Replays the flat result of libmsgpu into the reference's objects.
+#include "ms_gpu_shim.h"
+
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "graph/Edge.h"
+#include "graph/Vertex.h"
+
+namespace muchsalsa::gpu {
+
+namespace {
+
+[[noreturn]] void raise(msgpu_ctx *pCtx, int status) {
+  std::string msg = msgpu_last_error(pCtx);
+  switch (status) {
+  case MSGPU_ERR_IO:
+    throw std::runtime_error(msg.empty() ? "Can't open blast file." : msg); // BlastFileAccessor.cpp:44
+  case MSGPU_ERR_INVALID_PAF:
+    throw std::runtime_error("Invalid BLAST file."); // BlastFileReader.cpp:98
+  case MSGPU_ERR_OUT_OF_RANGE:
+    throw std::out_of_range("basic_string_view::substr"); // what strSlice's substr throws, SequenceUtils.cpp:37
+  default:
+    throw std::runtime_error("msgpu: " + msg + " (status " + std::to_string(status) + ")");
+  }
+}
+
+std::string fetchOne(Context &ctx, uint32_t which, unsigned int id, int left, int right, Toggle const direction) {
+  msgpu_seq_req req{which, id, left, right, static_cast<bool>(direction) ? 1u : 0u};
+  uint64_t      bound = 0;
+  if (int rc = msgpu_seq_batch_bound(ctx.get(), &req, 1, &bound); rc != MSGPU_OK) raise(ctx.get(), rc);
+  std::string out(bound, '\0');
+  uint64_t    off[2] = {0, 0};
+  uint8_t     status = 0;
+  if (int rc = msgpu_seq_fetch_batch(ctx.get(), &req, 1, out.data(), bound, off, &status); rc != MSGPU_OK)
+    raise(ctx.get(), rc);
+  if (status != 0) raise(ctx.get(), status == 1 ? MSGPU_ERR_IO : MSGPU_ERR_OUT_OF_RANGE);
+  out.resize(off[1] - off[0]);
+  return out;
+}
+
+} // namespace
+
+Context::Context(int cudaDevice) {
+  if (msgpu_create(cudaDevice, &m_pCtx) != MSGPU_OK || !m_pCtx)
+    throw std::runtime_error("msgpu: no usable CUDA device (the GPU construction path has no CPU fallback)");
+}
+
+Context::~Context() { msgpu_destroy(m_pCtx); }
+
+void constructGraph(Context &ctx, std::string const &pafPath, graph::Graph &graph, matching::MatchMap &matchMap,
+                    Registry &registryNanopore, Registry &registryIllumina) {
+  if (int rc = msgpu_build_from_paf(ctx.get(), pafPath.c_str()); rc != MSGPU_OK) raise(ctx.get(), rc);
+  msgpu_counts c{};
+  msgpu_tables t{};
+  if (int rc = msgpu_result_counts(ctx.get(), &c); rc != MSGPU_OK) raise(ctx.get(), rc);
+  if (int rc = msgpu_result_host(ctx.get(), &t); rc != MSGPU_OK) raise(ctx.get(), rc);
+
+  // Registries: ids are ranks of first appearance, so registering the names in id order reproduces them
+  // (Registry.cpp:36-45 hands out 0, 1, 2, ... in call order).
+  for (uint64_t i = 0; i < c.n_reads; ++i)
+    registryNanopore[std::string(t.read_names + t.read_name_off[i], t.read_names + t.read_name_off[i + 1])];
+  for (uint64_t i = 0; i < c.n_unitigs; ++i)
+    registryIllumina[std::string(t.unitig_names + t.unitig_name_off[i], t.unitig_names + t.unitig_name_off[i + 1])];
+
+  // Vertices: Vertex(id, nanoporeLength, lineIdx) exactly as BlastFileReader.cpp:113-114 builds them.
+  std::vector<graph::Vertex const *> vertices(c.n_reads, nullptr);
+  for (uint64_t i = 0; i < c.n_reads; ++i) {
+    graph.addVertex(std::make_shared<graph::Vertex>(static_cast<unsigned int>(i),
+                                                    static_cast<std::size_t>(t.read_nlen[i]),
+                                                    static_cast<std::size_t>(t.read_line[i])));
+    vertices[i] = graph.getVertex(static_cast<unsigned int>(i));
+  }
+
+  // Vertex matches (BlastFileReader.cpp:116-126, MatchMap.cpp:53-81).
+  for (uint64_t k = 0; k < c.n_matches; ++k) {
+    auto spMatch = std::shared_ptr<matching::VertexMatch>(new matching::VertexMatch{
+        {t.m_nr0[k], t.m_nr1[k]},
+        {t.m_ir0[k], t.m_ir1[k]},
+        t.m_rratio[k],
+        Toggle((t.m_flags[k] & 1) != 0),
+        static_cast<std::size_t>(t.m_score[k]),
+        Toggle((t.m_flags[k] & 2) != 0),
+        static_cast<std::size_t>(t.m_line[k])});
+    matchMap.addVertexMatch(t.m_read[k], t.m_unitig[k], spMatch);
+  }
+
+  // Edges + edge matches (MatchMap.cpp:204-218): edge.first is the vertex with the smaller line index = smaller id.
+  for (uint64_t e = 0; e < c.n_edges; ++e) {
+    auto pair = std::make_pair(gsl::make_not_null(vertices[t.edge_first[e]]),
+                               gsl::make_not_null(vertices[t.edge_second[e]]));
+    graph.addEdge(std::pair<gsl::not_null<graph::Vertex const *> const, gsl::not_null<graph::Vertex const *> const>(
+        pair.first, pair.second));
+    auto const *pEdge = graph.getEdge(pair);
+    for (uint64_t k = t.edge_em_begin[e]; k < t.edge_em_begin[e + 1]; ++k) {
+      auto spMatch = std::shared_ptr<matching::EdgeMatch>(new matching::EdgeMatch{
+          {t.em_ov0[k], t.em_ov1[k]},
+          Toggle((t.em_flags[k] & 1) != 0),
+          t.em_score[k],
+          Toggle((t.em_flags[k] & 2) != 0),
+          static_cast<std::size_t>(t.em_line[k])});
+      matchMap.addEdgeMatch(pEdge, t.em_unitig[k], spMatch);
+    }
+  }
+}
+
+void loadSequences(Context &ctx, std::string const &unitigsPath, std::string const &nanoporePath) {
+  if (int rc = msgpu_seq_load(ctx.get(), unitigsPath.c_str(), nanoporePath.c_str()); rc != MSGPU_OK)
+    raise(ctx.get(), rc);
+}
+
+std::string getIlluminaSequence(Context &ctx, unsigned int illuminaId, int illuminaOverlapLeft,
+                                int illuminaOverlapRight, Toggle const direction) {
+  return fetchOne(ctx, 0, illuminaId, illuminaOverlapLeft, illuminaOverlapRight, direction);
+}
+
+std::string getNanoporeSequence(Context &ctx, unsigned int nanoporeId, int nanoporeRegionLeft,
+                                int nanoporeRegionRight, Toggle const direction) {
+  return fetchOne(ctx, 1, nanoporeId, nanoporeRegionLeft, nanoporeRegionRight, direction);
+}
+
+} // namespace muchsalsa::gpu

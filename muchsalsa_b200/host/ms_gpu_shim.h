@@ -1,0 +1,58 @@
+// ms_gpu_shim.h — the host side of the drop-in: what a MuCHSALSA maintainer adds to libms so that the existing
+// `muchsalsa` binary, pipeline.sh and everything downstream of construction keep working unchanged.
+//
+// It replaces two statements of main() (src/main.cpp:156-157)
+//
+//     blastFileReader.read();          ->   muchsalsa::gpu::constructGraph(ctx, pafPath, graph, matchMap,
+//     matchMap.calculateEdges();                                            registryNanopore, registryIllumina);
+//
+// and backs the two sequence getters of SequenceUtils.h:41-45 with the resident sequence store.  Everything is done
+// through the reference's own PUBLIC API (Registry::operator[], Graph::addVertex / addEdge / getEdge / getVertex,
+// MatchMap::addVertexMatch / addEdgeMatch), so observers, ownership and all downstream kernels see exactly the
+// objects the CPU path would have built.  Errors come back as the reference's own exceptions (std::runtime_error with
+// the reference's messages: BlastFileAccessor.cpp:44, BlastFileReader.cpp:98, SequenceAccessor.cpp:61,110).
+//
+// Compiles against the reference's headers (include/ms) and include/msgpu.h; links libmsgpu.so.  C++20 like libms.
+#pragma once
+
+#include <string>
+
+#include "Registry.h"
+#include "graph/Graph.h"
+#include "matching/MatchMap.h"
+#include "types/Toggle.h"
+
+#include "msgpu.h"
+
+namespace muchsalsa::gpu {
+
+// RAII owner of one msgpu context (= one GPU).  Throws std::runtime_error if no CUDA device is usable: there is no
+// CPU fallback behind this class — a caller that wants one keeps calling BlastFileReader::read() itself.
+class Context {
+public:
+  explicit Context(int cudaDevice = 0);
+  ~Context();
+  Context(Context const &)            = delete;
+  Context &operator=(Context const &) = delete;
+  msgpu_ctx *get() const { return m_pCtx; }
+
+private:
+  msgpu_ctx *m_pCtx = nullptr;
+};
+
+// BlastFileAccessor(path) + BlastFileReader::read() + MatchMap::calculateEdges() (src/main.cpp:153-157).
+void constructGraph(Context &ctx, std::string const &pafPath, muchsalsa::graph::Graph &graph,
+                    muchsalsa::matching::MatchMap &matchMap, muchsalsa::Registry &registryNanopore,
+                    muchsalsa::Registry &registryIllumina);
+
+// SequenceAccessor(...) + buildIndex() (src/main.cpp:161-163): both files indexed and kept resident in HBM; ids
+// continue the numbering of the construction that ran on `ctx`.
+void loadSequences(Context &ctx, std::string const &unitigsPath, std::string const &nanoporePath);
+
+// getIlluminaSequence / getNanoporeSequence (SequenceUtils.cpp:63-85); thread-safe like the reference's.
+std::string getIlluminaSequence(Context &ctx, unsigned int illuminaId, int illuminaOverlapLeft,
+                                int illuminaOverlapRight, muchsalsa::Toggle const direction);
+std::string getNanoporeSequence(Context &ctx, unsigned int nanoporeId, int nanoporeRegionLeft,
+                                int nanoporeRegionRight, muchsalsa::Toggle const direction);
+
+} // namespace muchsalsa::gpu

@@ -201,6 +201,44 @@ class Reference(_Checker):
             if tmp:
                 os.unlink(path)
 
+    @property
+    def has_gpu_shim(self) -> bool:
+        return hasattr(self.lib, "msref_build_gpu")
+
+    def build_gpu(self, paf) -> Tables:
+        """The drop-in check: the reference's own Graph / MatchMap / Registry objects filled by the GPU path through
+        muchsalsa_b200/host/ms_gpu_shim.cpp, dumped by the same code as `build`."""
+        L = self.lib
+        L.msref_build_gpu.argtypes = [C.c_char_p, C.POINTER(_MsTables), C.c_char_p, C.c_uint64]
+        L.msref_build_gpu.restype = C.c_int
+        path, tmp = self._as_path(paf)
+        try:
+            t = _MsTables()
+            err = C.create_string_buffer(512)
+            rc = L.msref_build_gpu(path.encode(), C.byref(t), err, 512)
+            if rc:
+                raise RuntimeError(f"rc={rc}: {err.value.decode(errors='replace')}")
+            out = _to_tables(t)
+            out.times["shim_total"] = t.t_edges
+            self.lib.ms_tables_free(C.byref(t))
+            return out
+        finally:
+            if tmp:
+                os.unlink(path)
+
+    def seq_fetch_gpu(self, unitigs_path, nanopore_path, which: int, name: str, l: int, r: int, direction: bool,
+                      cap: int = 1 << 22):
+        L = self.lib
+        L.msref_seq_fetch_gpu.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_char_p, C.c_uint64]
+        L.msref_seq_fetch_gpu.restype = C.c_int64
+        out = C.create_string_buffer(cap)
+        n = L.msref_seq_fetch_gpu(os.fspath(unitigs_path).encode(), os.fspath(nanopore_path).encode(), which,
+                                  name.encode("latin-1"), l, r, 1 if direction else 0, out, cap)
+        if n == -2:
+            raise RuntimeError("GPU sequence store could not be set up")
+        return None if n < 0 else out.raw[:n]
+
     def strslice(self, s: bytes, i: int, j: int):
         out = C.create_string_buffer(len(s) + 2)
         n = self.lib.msref_strslice(s, len(s), i, j, out)

@@ -39,6 +39,10 @@
 
 #include "ms_tables.h"
 
+#ifdef MSREF_WITH_GPU_SHIM
+#include "ms_gpu_shim.h"
+#endif
+
 namespace {
 
 using clk = std::chrono::steady_clock;
@@ -85,46 +89,12 @@ void ms_tables_free(ms_tables *t) {
   std::memset(t, 0, sizeof(*t));
 }
 
-// Runs BlastFileReader::read() + MatchMap::calculateEdges() on `paf_path` with a
-// `threads`-sized pool (1 = the canonical, deterministic mode) and fills `out`.
-// do_dump = 0 only measures the phase times (used by the CPU baseline).
-int msref_build(const char *paf_path, int threads, int do_dump, ms_tables *out) {
-  using namespace muchsalsa;
-  std::memset(out, 0, sizeof(*out));
-  try {
-    auto pool             = threading::ThreadPool(static_cast<std::size_t>(threads));
-    auto graph            = graph::Graph();
-    auto matchMap         = matching::MatchMap(&pool, &graph);
-    auto registryNanopore = Registry();
-    auto registryIllumina = Registry();
-
-    auto t0         = clk::now();
-    auto bfAccessor = BlastFileAccessor(paf_path);
-    auto t1         = clk::now();
-    auto reader     = BlastFileReader(&pool, &bfAccessor, &graph, &matchMap, &registryNanopore, &registryIllumina);
-    reader.read();
-    auto t2 = clk::now();
-    matchMap.calculateEdges();
-    auto t3      = clk::now();
-    out->t_index = secs(t0, t1);
-    out->t_read  = secs(t1, t2);
-    out->t_edges = secs(t2, t3);
-
-    out->n_reads = graph.getOrder();
-    out->n_edges = graph.getSize();
-    if (!do_dump) {
-      // still report the row counts the baseline rates are quoted on
-      for (auto *pE : graph.getEdges()) {
-        auto const *pEm = matchMap.getEdgeMatches(pE);
-        if (pEm) out->n_em += pEm->size();
-      }
-      for (auto *pV : graph.getVertices()) {
-        auto const *pVm = matchMap.getVertexMatches(pV->getId());
-        if (pVm) out->n_vm += pVm->size();
-      }
-      return 0;
-    }
-
+// Flattens what the reference's objects hold into `out` (canonical orders of ms_tables.h).  Shared by the two ways of
+// filling them: the reference's own read() + calculateEdges(), and the GPU path replayed through ms_gpu_shim.
+static void dump_tables(const char *paf_path, std::size_t line_count, muchsalsa::graph::Graph &graph,
+                        muchsalsa::matching::MatchMap &matchMap, muchsalsa::Registry &registryNanopore,
+                        muchsalsa::Registry &registryIllumina, ms_tables *out) {
+  {
     // ---- vertices, by id
     auto vertices = graph.getVertices();
     std::sort(vertices.begin(), vertices.end(), [](auto *a, auto *b) { return a->getId() < b->getId(); });
@@ -187,7 +157,7 @@ int msref_build(const char *paf_path, int threads, int do_dump, ms_tables *out) 
       NameTable     readNames, unitigNames;
       std::ifstream in(paf_path);
       std::string   line;
-      std::vector<uint8_t> accepted(bfAccessor.getLineCount(), 0);
+      std::vector<uint8_t> accepted(line_count, 0);
       for (auto l : vmline) accepted[l] = 1;
       for (std::size_t li = 0; std::getline(in, line); ++li) {
         if (li >= accepted.size() || !accepted[li]) continue;
@@ -252,12 +222,118 @@ int msref_build(const char *paf_path, int threads, int do_dump, ms_tables *out) 
     out->em_dir        = dup(emDir);
     out->em_prim       = dup(emPrim);
     out->em_line       = dup(emLine);
+  }
+}
+
+// Runs BlastFileReader::read() + MatchMap::calculateEdges() on `paf_path` with a
+// `threads`-sized pool (1 = the canonical, deterministic mode) and fills `out`.
+// do_dump = 0 only measures the phase times (used by the CPU baseline).
+int msref_build(const char *paf_path, int threads, int do_dump, ms_tables *out) {
+  using namespace muchsalsa;
+  std::memset(out, 0, sizeof(*out));
+  try {
+    auto pool             = threading::ThreadPool(static_cast<std::size_t>(threads));
+    auto graph            = graph::Graph();
+    auto matchMap         = matching::MatchMap(&pool, &graph);
+    auto registryNanopore = Registry();
+    auto registryIllumina = Registry();
+
+    auto t0         = clk::now();
+    auto bfAccessor = BlastFileAccessor(paf_path);
+    auto t1         = clk::now();
+    auto reader     = BlastFileReader(&pool, &bfAccessor, &graph, &matchMap, &registryNanopore, &registryIllumina);
+    reader.read();
+    auto t2 = clk::now();
+    matchMap.calculateEdges();
+    auto t3      = clk::now();
+    out->t_index = secs(t0, t1);
+    out->t_read  = secs(t1, t2);
+    out->t_edges = secs(t2, t3);
+
+    out->n_reads = graph.getOrder();
+    out->n_edges = graph.getSize();
+    if (!do_dump) {
+      // still report the row counts the baseline rates are quoted on
+      for (auto *pE : graph.getEdges()) {
+        auto const *pEm = matchMap.getEdgeMatches(pE);
+        if (pEm) out->n_em += pEm->size();
+      }
+      for (auto *pV : graph.getVertices()) {
+        auto const *pVm = matchMap.getVertexMatches(pV->getId());
+        if (pVm) out->n_vm += pVm->size();
+      }
+      return 0;
+    }
+
+    dump_tables(paf_path, bfAccessor.getLineCount(), graph, matchMap, registryNanopore, registryIllumina, out);
     return 0;
   } catch (std::exception const &e) {
     std::fprintf(stderr, "msref_build: %s\n", e.what());
     return 1;
   }
 }
+
+#ifdef MSREF_WITH_GPU_SHIM
+// The drop-in check: the SAME reference objects (Graph, MatchMap, two Registry), filled by the GPU path through the
+// host shim a maintainer would add to libms (muchsalsa_b200/host/ms_gpu_shim.cpp) instead of by read() +
+// calculateEdges(), then dumped by the same code.  Returns 0, 1 (exception; message in err) or 2 (no GPU).
+int msref_build_gpu(const char *paf_path, ms_tables *out, char *err, uint64_t err_cap) {
+  using namespace muchsalsa;
+  std::memset(out, 0, sizeof(*out));
+  auto fail = [&](const char *m, int rc) {
+    if (err && err_cap) std::snprintf(err, err_cap, "%s", m);
+    return rc;
+  };
+  try {
+    std::unique_ptr<gpu::Context> ctx;
+    try {
+      ctx = std::make_unique<gpu::Context>(0);
+    } catch (std::exception const &e) {
+      return fail(e.what(), 2);
+    }
+    auto pool             = threading::ThreadPool(1);
+    auto graph            = graph::Graph();
+    auto matchMap         = matching::MatchMap(&pool, &graph);
+    auto registryNanopore = Registry();
+    auto registryIllumina = Registry();
+    auto t0               = clk::now();
+    gpu::constructGraph(*ctx, paf_path, graph, matchMap, registryNanopore, registryIllumina);
+    out->t_edges = secs(t0, clk::now());
+    out->n_reads = graph.getOrder();
+    out->n_edges = graph.getSize();
+    msgpu_counts c{};
+    msgpu_result_counts(ctx->get(), &c);
+    dump_tables(paf_path, c.n_lines, graph, matchMap, registryNanopore, registryIllumina, out);
+    return 0;
+  } catch (std::exception const &e) {
+    return fail(e.what(), 1);
+  }
+}
+
+// get{Illumina,Nanopore}Sequence through the shim, on a fresh context; returns length, -1 (reference-style exception)
+// or -2 (no GPU / load failure)
+int64_t msref_seq_fetch_gpu(const char *unitigs_path, const char *nanopore_path, int which, const char *name, int l,
+                            int r, int dir, char *out, uint64_t cap) {
+  using namespace muchsalsa;
+  try {
+    gpu::Context ctx(0);
+    gpu::loadSequences(ctx, unitigs_path, nanopore_path);
+    uint32_t id = 0;
+    if (msgpu_seq_id(ctx.get(), static_cast<uint32_t>(which), name, &id) != MSGPU_OK) return -2;
+    try {
+      auto s = which ? gpu::getNanoporeSequence(ctx, id, l, r, Toggle(dir != 0))
+                     : gpu::getIlluminaSequence(ctx, id, l, r, Toggle(dir != 0));
+      if (s.size() <= cap) std::memcpy(out, s.data(), s.size());
+      return static_cast<int64_t>(s.size());
+    } catch (std::out_of_range const &) {
+      return -1;
+    }
+  } catch (std::exception const &) {
+    return -2;
+  }
+}
+#endif
+
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Sequence path: strSlice / getReverseComplement (SequenceUtils.cpp:27-61) and the FASTA/FASTQ store
