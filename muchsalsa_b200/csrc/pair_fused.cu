@@ -278,6 +278,7 @@ struct TileArgs {
   uint2          *records;          // per tile kTileCap slots: (partner row, source | head << 9 | heads before << 10)
   uint2          *tile_cnt;         // per tile: (surviving candidates, run heads)
   unsigned int   *error;
+  uint32_t        wide; // 0: every sort word fits 32 bits for any tile, so the launch carries the small buffers only
 };
 
 struct SrcStage { // the sources of the tile, staged in shared memory (structure of arrays)
@@ -297,12 +298,13 @@ struct TileShared { // everything but the two sort buffers, which follow it in d
   uint32_t smin, smax;
 };
 constexpr size_t kSharedOff = (sizeof(TileShared) + 15) & ~size_t(15);
-constexpr size_t kTileBytes = kSharedOff + 2 * kTileCap * sizeof(unsigned long long);
+constexpr size_t kTileBytesWide   = kSharedOff + 2 * kTileCap * sizeof(unsigned long long);
+constexpr size_t kTileBytesNarrow = kSharedOff + 2 * kTileCap * sizeof(uint32_t);
 
 // Stable LSD radix sort of n words in shared memory on bits [lo, hi); warp w owns a contiguous block of items and
 // ranks it with __match_any_sync + per-warp digit counters, so equal digits keep their order.  Returns the buffer
 // that holds the result.  blockDim.x == kFusedBlock.
-template <class W> __device__ W *cta_radix_sort(TileShared &s, W *in, W *out, uint32_t n, int lo, int hi) {
+template <class W, bool kExpMatch> __device__ W *cta_radix_sort(TileShared &s, W *in, W *out, uint32_t n, int lo, int hi) {
   const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
   const int      kb = hi - lo;
   if (kb <= 0 || n <= 1) return in;
@@ -327,12 +329,18 @@ template <class W> __device__ W *cta_radix_sort(TileShared &s, W *in, W *out, ui
         const W        x     = valid ? in[idx] : W(0);
         const unsigned d     = unsigned(x >> shift) & mask;
         // lanes with the same digit, by one vote per digit bit (cost independent of how many digits are distinct)
-        const unsigned vb = __ballot_sync(0xffffffffu, valid);
-        unsigned       pm = valid ? vb : 0u;
-        for (int bit = 0; bit < b; ++bit) {
-          const bool     on  = (d >> bit) & 1u;
-          const unsigned bal = __ballot_sync(0xffffffffu, on);
-          pm &= on ? bal : ~bal;
+        unsigned pm;
+        if (kExpMatch) {
+          pm = __match_any_sync(0xffffffffu, valid ? d : 256u);
+          pm = valid ? pm : 0u;
+        } else {
+          const unsigned vb = __ballot_sync(0xffffffffu, valid);
+          pm                = valid ? vb : 0u;
+          for (int bit = 0; bit < b; ++bit) { // (fully unrolling this loop was measured slower: spills)
+            const unsigned on  = 0u - ((d >> bit) & 1u);
+            const unsigned bal = __ballot_sync(0xffffffffu, on != 0u);
+            pm &= ~(bal ^ on);
+          }
         }
         word[it] = x;
         peer[it] = pm; // 0 for lanes past the end
@@ -390,7 +398,7 @@ template <class W> __device__ W *cta_radix_sort(TileShared &s, W *in, W *out, ui
 }
 
 // enumerate + sort + heads of one tile, for sort words of type W (32 bits when row + second + slot fit, else 64)
-template <class W>
+template <class W, bool kExpMatch>
 __device__ __forceinline__ void tile_tail(const TileArgs &a, TileShared &s, W *wa, W *wb, uint32_t st_idx,
                                           uint32_t n_src, uint32_t n_ent, int sb, int rb) {
   const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
@@ -423,7 +431,7 @@ __device__ __forceinline__ void tile_tail(const TileArgs &a, TileShared &s, W *w
   __syncthreads();
 
   // ---- sort by (row, second); generation order (= unitig order) breaks ties because the sort is stable
-  W *sorted = cta_radix_sort<W>(s, wa, wb, n_ent, kIdxBits, kIdxBits + sb + rb);
+  W *sorted = cta_radix_sort<W, kExpMatch>(s, wa, wb, n_ent, kIdxBits, kIdxBits + sb + rb);
 
   // ---- run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the key
   // of its pair) but is skipped; the head of a run is its first surviving candidate.
@@ -483,7 +491,7 @@ __device__ __forceinline__ void tile_tail(const TileArgs &a, TileShared &s, W *w
   }
 }
 
-__global__ void __launch_bounds__(kFusedBlock, 2) pair_tiles_kernel(TileArgs a) {
+template <bool kExpMatch> __global__ void __launch_bounds__(kFusedBlock, 2) pair_tiles_kernel(TileArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileShared    &s = *reinterpret_cast<TileShared *>(smem_raw);
   const unsigned t = threadIdx.x, l = t & 31;
@@ -579,10 +587,15 @@ __global__ void __launch_bounds__(kFusedBlock, 2) pair_tiles_kernel(TileArgs a) 
     unsigned char *words = smem_raw + kSharedOff;
     if (sb + rb + kIdxBits <= 32) {
       uint32_t *wa = reinterpret_cast<uint32_t *>(words);
-      tile_tail<uint32_t>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent, sb, rb);
+      tile_tail<uint32_t, kExpMatch>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent, sb, rb);
+    } else if (!a.wide) { // cannot happen: the host sizes the launch from the id width
+      if (t == 0) {
+        *a.error           = 3;
+        a.tile_cnt[st_idx] = make_uint2(0, 0);
+      }
     } else {
       unsigned long long *wa = reinterpret_cast<unsigned long long *>(words);
-      tile_tail<unsigned long long>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent, sb, rb);
+      tile_tail<unsigned long long, kExpMatch>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent, sb, rb);
     }
   }
 }
@@ -620,14 +633,12 @@ __global__ void __launch_bounds__(1024)
 // ---------------------------------------------------------------------------------------------------------------------
 struct EmitArgs {
   const PairRow  *rows;
-  const uint32_t *rd_off, *rd_src, *tile_row;
+  const uint32_t *rd_off, *rd_src, *tile_row, *tile_kind;
   uint32_t        tile_lo, n_tiles;
   const uint2    *records, *tile_cnt;
   const unsigned long long *em_base, *edge_base;
   EdgeTables      out;
 };
-
-constexpr int kEmitBatch = 4; // records in flight per thread: the gathers are latency-bound, so overlap them
 
 __device__ __forceinline__ PairRow ld_row(const PairRow *p) { // two 128-bit read-only loads = one 32-byte sector
   const uint4 *q = reinterpret_cast<const uint4 *>(p);
@@ -644,52 +655,73 @@ __device__ __forceinline__ PairRow ld_row(const PairRow *p) { // two 128-bit rea
   return r;
 }
 
-__global__ void __launch_bounds__(256) pair_emit_rows_kernel(EmitArgs a) {
+constexpr int kEmitBlock = 256;
+constexpr int kEmitBatch = 4; // records in flight per thread: the partner gathers are latency-bound, so overlap them
+
+// One CTA per tile (strided).  The tile's sources (the `first` side of its records, <= 512 rows) are staged in shared
+// memory once; every record then needs ONE dependent gather (its partner's row) after its own coalesced load.
+__global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs a) {
+  __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
+  const unsigned   t = threadIdx.x;
   for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
+    const uint32_t           tile    = a.tile_lo + ti;
     const uint32_t           n_valid = a.tile_cnt[ti].x;
     const unsigned long long em0 = a.em_base[ti], ed0 = a.edge_base[ti];
-    const uint32_t           q0  = a.rd_off[a.tile_row[a.tile_lo + ti]];
-    const uint2             *rec = a.records + uint64_t(ti) * kTileCap;
-    for (uint32_t k0 = threadIdx.x; k0 < n_valid; k0 += blockDim.x * kEmitBatch) {
-      uint2 r[kEmitBatch];
+    const uint32_t           r0 = a.tile_row[tile], q0 = a.rd_off[r0];
+    const uint32_t n_src = (a.tile_kind[tile] ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
+    const uint2   *rec   = a.records + uint64_t(ti) * kTileCap;
+    uint2          r[kEmitBatch];
 #pragma unroll
-      for (int u = 0; u < kEmitBatch; ++u) {
-        const uint32_t k = k0 + u * blockDim.x;
+    for (int u = 0; u < kEmitBatch; ++u) { // the first batch of records travels while the sources are staged
+      const uint32_t k = t + u * kEmitBlock;
+      r[u]             = k < n_valid ? __ldg(rec + k) : make_uint2(0, 0);
+    }
+    __syncthreads(); // previous tile done with the staged sources
+    if (n_valid)
+      for (uint32_t j = t; j < n_src && j < kSrcCap; j += kEmitBlock) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
+        src_lo[j]      = __ldg(q);
+        src_hi[j]      = __ldg(q + 1);
+      }
+    __syncthreads();
+    for (uint32_t k0 = t; k0 < n_valid; k0 += kEmitBlock * kEmitBatch) {
+      PairRow pb[kEmitBatch];
+#pragma unroll
+      for (int u = 0; u < kEmitBatch; ++u) pb[u] = ld_row(a.rows + r[u].x);
+      uint2 cur[kEmitBatch];
+#pragma unroll
+      for (int u = 0; u < kEmitBatch; ++u) { // next batch of records: in flight during the arithmetic below
+        cur[u]           = r[u];
+        const uint32_t k = k0 + (kEmitBatch + u) * kEmitBlock;
         r[u]             = k < n_valid ? __ldg(rec + k) : make_uint2(0, 0);
       }
-      uint32_t qa[kEmitBatch];
-#pragma unroll
-      for (int u = 0; u < kEmitBatch; ++u) qa[u] = __ldg(a.rd_src + q0 + (r[u].y & (kSrcCap - 1)));
-      PairRow pa[kEmitBatch], pb[kEmitBatch];
 #pragma unroll
       for (int u = 0; u < kEmitBatch; ++u) {
-        pa[u] = ld_row(a.rows + qa[u]);
-        pb[u] = ld_row(a.rows + r[u].x);
-      }
-#pragma unroll
-      for (int u = 0; u < kEmitBatch; ++u) {
-        const uint32_t k = k0 + u * blockDim.x;
+        const uint32_t k = k0 + u * kEmitBlock;
         if (k >= n_valid) continue;
-        const int a0 = pa[u].ir0, a1 = pa[u].ir1, b0 = pb[u].ir0, b1 = pb[u].ir1;
-        const int ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
+        const uint32_t j  = cur[u].y & (kSrcCap - 1);
+        const uint4    lo = src_lo[j], hi = src_hi[j];
+        const int      a0 = int32_t(lo.x), a1 = int32_t(lo.y), b0 = pb[u].ir0, b1 = pb[u].ir1;
+        const int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
         // MatchMap.cpp:195-202: score_x * common / len_x for the outer and the inner match, summed.  IEEE addition
         // is commutative, so which of the two is "outer" (the later line) does not change the sum.  No FMA
         // contraction (explicit _rn intrinsics, and the library is built with --fmad=false).
         const double common = double(ov1 - ov0 + 1);
-        const double sa     = double((unsigned long long)(long long)pa[u].score); // size_t widened from int
+        const double sa     = double((unsigned long long)(long long)int32_t(lo.w)); // size_t widened from int
         const double sbb    = double((unsigned long long)(long long)pb[u].score);
         const double sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
         const double sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
+        const uint32_t la = hi.x, fa = hi.y;
         const unsigned long long o = em0 + k;
-        a.out.em_unitig[o] = pa[u].unitig;
+        a.out.em_unitig[o] = hi.z;
         a.out.em_ov0[o]    = ov0;
         a.out.em_ov1[o]    = ov1;
         a.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
-        a.out.em_line[o]   = pa[u].line > pb[u].line ? pa[u].line : pb[u].line; // outer = later line (MatchMap.cpp:218)
-        a.out.em_flags[o]  = uint8_t((((pa[u].flags ^ pb[u].flags) & 1u) ? 0u : 1u) | ((pa[u].flags & pb[u].flags & 2u) ? 2u : 0u));
-        if (r[u].y & (1u << kSrcBits)) {
-          const unsigned long long eo = ed0 + (r[u].y >> (kSrcBits + 1));
-          a.out.first[eo]    = pa[u].read;
+        a.out.em_line[o]   = la > pb[u].line ? la : pb[u].line; // outer = the later line (MatchMap.cpp:218)
+        a.out.em_flags[o]  = uint8_t((((fa ^ pb[u].flags) & 1u) ? 0u : 1u) | ((fa & pb[u].flags & 2u) ? 2u : 0u));
+        if (cur[u].y & (1u << kSrcBits)) {
+          const unsigned long long eo = ed0 + (cur[u].y >> (kSrcBits + 1));
+          a.out.first[eo]    = lo.z;
           a.out.second[eo]   = pb[u].read;
           a.out.em_begin[eo] = o;
         }
@@ -800,12 +832,23 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   if (my_tiles) {
     static bool attr_set = false;
     if (!attr_set) {
-      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileBytes)));
+      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileBytesWide)));
+      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileBytesWide)));
       attr_set = true;
     }
-    int grid = kNumSMs * 2 * 4; // a few waves of two resident CTAs per SM, tiles strided over them
+    // a sort word is (dense row rank, <= 9 bits | second - min second) << 12 | slot: 32 bits are enough for every
+    // tile when read ids have <= 11 bits; otherwise tiles choose per tile and the launch carries the 64-bit buffers
+    int id_bits = 1;
+    while (id_bits < 32 && (1ull << id_bits) < R) ++id_bits;
+    a.wide             = id_bits + kSrcBits + kIdxBits > 32 ? 1u : 0u;
+    const size_t bytes = a.wide ? kTileBytesWide : kTileBytesNarrow;
+    int          grid  = kNumSMs * 2 * 4; // a few waves of two resident CTAs per SM, tiles strided over them
     if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
-    MSGPU_LAUNCH("pair_tiles", st, pair_tiles_kernel<<<grid, kFusedBlock, kTileBytes, st>>>(a));
+    const char *exp_rank = std::getenv("MSGPU_EXP_RANK");
+    if (exp_rank && exp_rank[0] == 'm')
+      MSGPU_LAUNCH("pair_tiles", st, pair_tiles_kernel<true><<<grid, kFusedBlock, bytes, st>>>(a));
+    else
+      MSGPU_LAUNCH("pair_tiles", st, pair_tiles_kernel<false><<<grid, kFusedBlock, bytes, st>>>(a));
   }
   MSGPU_LAUNCH("scan_tiles", st, scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_cnt, my_tiles, em_base, ed_base, totals, e.em_begin));
   if (my_tiles) {
@@ -814,6 +857,7 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
     ea.rd_off    = rd_off;
     ea.rd_src    = rd_src;
     ea.tile_row  = tile_row;
+    ea.tile_kind = tile_kind;
     ea.tile_lo   = tile_lo;
     ea.n_tiles   = my_tiles;
     ea.records   = records;
@@ -823,7 +867,7 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
     ea.out       = e;
     int grid = kNumSMs * 8;
     if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
-    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, 256, 0, st>>>(ea));
+    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
   }
   unsigned long long h_tot[2];
   uint32_t           h_flags[4];

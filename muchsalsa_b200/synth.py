@@ -42,8 +42,10 @@ CONFIGS = {
     "small": SynthConfig("small", 1_500_000, 3.0, 1),
     "ecoli": SynthConfig("ecoli", 4_600_000, 30.0, 2),
     "yeast": SynthConfig("yeast", 12_000_000, 50.0, 3, rep_frac=0.05, rep_kind="geom", rep_mean=5.0, rep_cap=64),
-    "thaliana": SynthConfig("thaliana", 135_000_000, 40.0, 4, rep_frac=0.03, rep_kind="zipf", rep_mean=1.5,
-                            rep_cap=500),
+    # thaliana: few unitigs, but with up to 200 extra loci each (k up to ~9e3 reads on one unitig): ~1e9 candidate
+    # pairs, which is what one B200 holds as a device-resident result (25 B per edge match + 16 B per edge)
+    "thaliana": SynthConfig("thaliana", 135_000_000, 40.0, 4, rep_frac=0.005, rep_kind="zipf", rep_mean=1.5,
+                            rep_cap=200),
     # human: 3.1 Gbp / 30x. ~7e7 lines without repeats; f and m push it towards 1e9. It is sharded
     # across ranks by `generate_columns(..., shard=(rank, world))`, never materialised whole.
     "human": SynthConfig("human", 3_100_000_000, 30.0, 5, rep_frac=0.03, rep_kind="zipf", rep_mean=1.3, rep_cap=4000),
