@@ -31,19 +31,23 @@ constexpr uint64_t kThMatches      = 500;
 
 constexpr uint8_t kFAccepted = 1, kFDir = 2, kFPrim = 4, kFFirstRead = 8, kFFirstUnitig = 16, kFSurvivor = 32;
 
+// Everything the host needs to know about an ingest, kept in device memory and read back ONCE.  All buffers are
+// sized from byte-count bounds (a line with 10 fields has >= 20 bytes), so no count has to reach the host earlier.
 struct IngestStatus {
   unsigned long long first_bad_line; // smallest line index the reference would have thrown on; ~0 = none
-  unsigned           n_accepted;
-  unsigned           collision;
-  unsigned           unsorted;
-  unsigned           pad;
+  unsigned long long n_lines, n_parse;
+  unsigned long long read_name_bytes, unitig_name_bytes;
+  unsigned           n_accepted, collision, unsorted, overflow; // overflow: more lines than n_bytes / 20 (all invalid)
+  unsigned           n_reads, n_unitigs, n_matches, pad;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K1a: line index.  A thread owns 32 consecutive bytes (two aligned 128-bit loads), a block a tile of 8 KB.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kNlBlock = 256;
-constexpr int kNlTile  = kNlBlock * 32;
+constexpr int kNlBlock  = 256;
+constexpr int kNlPieces = 8;                        // a thread owns 8 pieces of 32 bytes, 8 KB apart (coalesced)
+constexpr int kNlPiece  = kNlBlock * 32;            // bytes one sweep of the block covers
+constexpr int kNlTile   = kNlPiece * kNlPieces;     // 64 KB per block
 
 __device__ __forceinline__ unsigned nl_mask4(unsigned w) {
   unsigned y = (__vcmpeq4(w, 0x0a0a0a0au) & 0x80808080u) >> 7; // bit 0/8/16/24 set where the byte is '\n'
@@ -66,39 +70,56 @@ __device__ __forceinline__ unsigned nl_mask32(const uint4 *aligned, uint64_t vb,
 __global__ void __launch_bounds__(kNlBlock)
     newline_count_kernel(const uint4 *__restrict__ aligned, uint64_t mis, uint64_t nv, uint32_t *__restrict__ tile_cnt) {
   __shared__ uint32_t sm[33];
-  uint64_t            vb = uint64_t(blockIdx.x) * kNlTile + uint64_t(threadIdx.x) * 32;
-  uint32_t            c  = __popc(nl_mask32(aligned, vb, mis, nv));
-  uint32_t            total;
+  const uint64_t      base = uint64_t(blockIdx.x) * kNlTile + uint64_t(threadIdx.x) * 32;
+  uint32_t            c    = 0;
+#pragma unroll
+  for (int i = 0; i < kNlPieces; ++i) c += __popc(nl_mask32(aligned, base + uint64_t(i) * kNlPiece, mis, nv));
+  uint32_t total;
   block_exclusive_scan<uint32_t>(c, sm, &total);
   if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
 }
 
-// line_start[k+1] = offset of the byte after the k-th newline
+// line_start[k+1] = offset of the byte after the k-th newline (k < cap_lines; beyond that the file is invalid anyway)
 __global__ void __launch_bounds__(kNlBlock)
     newline_write_kernel(const uint4 *__restrict__ aligned, uint64_t mis, uint64_t nv,
-                         const uint32_t *__restrict__ tile_off, uint64_t *__restrict__ line_start) {
+                         const uint32_t *__restrict__ tile_off, uint64_t cap_lines, uint64_t *__restrict__ line_start) {
   __shared__ uint32_t sm[33];
-  uint64_t            vb = uint64_t(blockIdx.x) * kNlTile + uint64_t(threadIdx.x) * 32;
-  unsigned            m  = nl_mask32(aligned, vb, mis, nv);
-  uint32_t            total;
-  uint32_t            rank = block_exclusive_scan<uint32_t>(__popc(m), sm, &total) + tile_off[blockIdx.x];
-  while (m) {
-    int b = __ffs(m) - 1;
-    m &= m - 1;
-    line_start[uint64_t(rank) + 1] = vb + b - mis + 1;
-    ++rank;
+  const uint64_t      base  = uint64_t(blockIdx.x) * kNlTile + uint64_t(threadIdx.x) * 32;
+  uint32_t            carry = tile_off[blockIdx.x];
+  for (int i = 0; i < kNlPieces; ++i) {
+    const uint64_t vb = base + uint64_t(i) * kNlPiece;
+    unsigned       m  = nl_mask32(aligned, vb, mis, nv);
+    uint32_t       total;
+    uint32_t       rank = carry + block_exclusive_scan<uint32_t>(__popc(m), sm, &total);
+    carry += total;
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (uint64_t(rank) + 1 <= cap_lines) line_start[uint64_t(rank) + 1] = vb + b - mis + 1;
+      ++rank;
+    }
   }
 }
 
 __global__ void line_index_finish_kernel(const char *__restrict__ paf, uint64_t n, const uint32_t *n_newlines,
-                                         uint64_t *line_start, uint64_t *n_lines_out) {
+                                         uint64_t cap_lines, int drop_last_line, uint64_t *line_start,
+                                         IngestStatus *status) {
   // a trailing run of bytes without '\n' is one more line (IO.cpp:92-95); give it a virtual terminator so that
   // length(line i) = line_start[i+1] - line_start[i] - 1 holds for every line
   uint64_t nn   = *n_newlines;
   bool     open = n > 0 && paf[n - 1] != '\n';
+  uint64_t nl   = nn + (open ? 1 : 0);
   line_start[0] = 0;
-  if (open) line_start[nn + 1] = n + 1;
-  *n_lines_out = nn + (open ? 1 : 0);
+  if (nl > cap_lines) { // more lines than a file of n bytes can hold with >= 20 bytes each: some parsed line is invalid
+    status->overflow = 1;
+    nl               = cap_lines;
+  } else if (open) {
+    line_start[nn + 1] = n + 1;
+  }
+  status->n_lines = nn + (open ? 1 : 0);
+  // BlastFileReader::read(): lines 0 .. lineCount-2 (BlastFileReader.cpp:76).  A shard of a PAF that is not the last
+  // one keeps its last line: only the last line of the whole file is never parsed.
+  status->n_parse = drop_last_line ? (nl ? nl - 1 : 0) : nl;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -143,9 +164,10 @@ __device__ __forceinline__ uint64_t name_hash(const char *s, uint32_t n, uint64_
 }
 
 __global__ void __launch_bounds__(256)
-    parse_lines_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ line_start, uint64_t n_parse,
-                       uint64_t seed, LineFields f, IngestStatus *status) {
-  unsigned n_acc = 0;
+    parse_lines_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ line_start, uint64_t seed,
+                       LineFields f, IngestStatus *status) {
+  const uint64_t n_parse = status->n_parse;
+  unsigned       n_acc   = 0;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
     const char *s   = paf + line_start[li];
@@ -213,8 +235,9 @@ struct InternTable {
 };
 
 __global__ void __launch_bounds__(256)
-    intern_insert_kernel(const uint8_t *__restrict__ flags, const uint64_t *__restrict__ hash, uint64_t n_parse,
-                         InternTable t, uint32_t *__restrict__ slot_of_line) {
+    intern_insert_kernel(const uint8_t *__restrict__ flags, const uint64_t *__restrict__ hash,
+                         const IngestStatus *__restrict__ status, InternTable t, uint32_t *__restrict__ slot_of_line) {
+  const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
     if (!(flags[li] & kFAccepted)) continue;
@@ -233,9 +256,10 @@ __global__ void __launch_bounds__(256)
 // every accepted line checks its name against the representative line of its slot and learns whether it is the
 // first appearance of the name
 __global__ void __launch_bounds__(256)
-    intern_verify_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ line_start, uint64_t n_parse,
-                         LineFields f, InternTable rt, const uint32_t *__restrict__ rslot, InternTable ut,
+    intern_verify_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ line_start, LineFields f,
+                         InternTable rt, const uint32_t *__restrict__ rslot, InternTable ut,
                          const uint32_t *__restrict__ uslot, IngestStatus *status) {
+  const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
     uint8_t fl = f.flags[li];
@@ -269,12 +293,14 @@ __global__ void __launch_bounds__(256)
 // the first-appearance lines publish the id of their name (= their rank among first-appearance lines) and fill the
 // vertex / name tables
 __global__ void __launch_bounds__(256)
-    intern_assign_kernel(const uint64_t *__restrict__ line_start, uint64_t n_parse, LineFields f, InternTable rt,
+    intern_assign_kernel(const uint64_t *__restrict__ line_start, const IngestStatus *__restrict__ status,
+                         LineFields f, InternTable rt,
                          const uint32_t *__restrict__ rslot, const uint32_t *__restrict__ rrank, InternTable ut,
                          const uint32_t *__restrict__ uslot, const uint32_t *__restrict__ urank,
                          int32_t *__restrict__ read_nlen, uint32_t *__restrict__ read_line,
                          uint64_t *__restrict__ read_name_src, uint32_t *__restrict__ read_name_len,
                          uint64_t *__restrict__ unitig_name_src, uint32_t *__restrict__ unitig_name_len) {
+  const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
     uint8_t fl = f.flags[li];
@@ -297,8 +323,10 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     gather_names_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ src,
-                        const uint64_t *__restrict__ dst_off, uint64_t n, char *__restrict__ out) {
+                        const uint64_t *__restrict__ dst_off, const unsigned *__restrict__ d_n,
+                        char *__restrict__ out) {
   // one warp per name
+  const uint64_t n = *d_n;
   uint64_t w  = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
   for (; w < n; w += nw) {
@@ -312,10 +340,11 @@ __global__ void __launch_bounds__(256)
 // (two dense ids), so this table needs no verification.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    dedup_insert_kernel(uint64_t n_parse, LineFields f, InternTable rt, const uint32_t *__restrict__ rslot,
-                        InternTable ut, const uint32_t *__restrict__ uslot, InternTable dt,
-                        uint32_t *__restrict__ dslot, uint32_t *__restrict__ rid_of_line,
+    dedup_insert_kernel(const IngestStatus *__restrict__ status, LineFields f, InternTable rt,
+                        const uint32_t *__restrict__ rslot, InternTable ut, const uint32_t *__restrict__ uslot,
+                        InternTable dt, uint32_t *__restrict__ dslot, uint32_t *__restrict__ rid_of_line,
                         uint32_t *__restrict__ uid_of_line) {
+  const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
     if (!(f.flags[li] & kFAccepted)) continue;
@@ -335,8 +364,9 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    dedup_flag_kernel(uint64_t n_parse, uint8_t *__restrict__ flags, InternTable dt,
+    dedup_flag_kernel(const IngestStatus *__restrict__ status, uint8_t *__restrict__ flags, InternTable dt,
                       const uint32_t *__restrict__ dslot) {
+  const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
     uint8_t fl = flags[li];
@@ -348,9 +378,10 @@ __global__ void __launch_bounds__(256)
 // K5: compaction of the surviving lines into the packed match records (line order), rRatio included
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    compact_matches_kernel(uint64_t n_parse, LineFields f, const uint32_t *__restrict__ pos,
+    compact_matches_kernel(const IngestStatus *__restrict__ status, LineFields f, const uint32_t *__restrict__ pos,
                            const uint32_t *__restrict__ rid_of_line, const uint32_t *__restrict__ uid_of_line,
                            MatchSoA m) {
+  const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
     uint8_t fl = f.flags[li];
@@ -372,7 +403,9 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    check_grouped_kernel(const uint32_t *__restrict__ unitig, uint64_t n, uint32_t *unsorted) {
+    check_grouped_kernel(const uint32_t *__restrict__ unitig, const unsigned *__restrict__ d_n, uint64_t n_host,
+                         uint32_t *unsorted) {
+  const uint64_t n = d_n ? uint64_t(*d_n) : n_host;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x + 1; i < n;
        i += uint64_t(gridDim.x) * blockDim.x)
     if (unitig[i] < unitig[i - 1]) *unsorted = 1;
@@ -410,9 +443,9 @@ static uint64_t next_pow2(uint64_t x) {
   return p;
 }
 
-static InternTable make_table(Arena &arena, cudaStream_t st, uint64_t expect) {
+static InternTable make_table(Arena &arena, cudaStream_t st, uint64_t min_slots) {
   InternTable t;
-  uint64_t    cap = next_pow2(expect * 2 + 2);
+  uint64_t    cap = next_pow2(min_slots);
   t.keys          = arena.alloc<unsigned long long>(cap);
   t.minline       = arena.alloc<uint32_t>(cap);
   t.id            = arena.alloc<uint32_t>(cap);
@@ -429,17 +462,24 @@ template <class T> static T read_back(cudaStream_t st, const T *d) {
   return h;
 }
 
-static void build_name_table(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n, const uint64_t *src,
-                             const uint32_t *len, NameTable &out) {
-  out.n        = n;
-  out.name_off = arena.alloc<uint64_t>(n + 1);
-  uint64_t *total = arena.alloc<uint64_t>(1);
-  exclusive_scan<uint64_t>(arena, st, LoadAs<uint32_t, uint64_t>{len}, n, out.name_off, total);
-  MSGPU_CUDA(cudaMemcpyAsync(out.name_off + n, total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-  out.n_bytes = read_back(st, total);
-  out.names   = arena.alloc<char>(out.n_bytes);
-  if (n) {
-    MSGPU_LAUNCH("gather_names", st, gather_names_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(d_paf, src, out.name_off, n, out.names));
+// lengths of the first *d_n names, 0 behind them: lets a scan run over the capacity without knowing the count
+struct NameLen {
+  const uint32_t *len;
+  const unsigned *d_n;
+  __device__ uint64_t operator()(uint64_t i) const { return i < *d_n ? uint64_t(len[i]) : 0ull; }
+};
+
+// name_off[i] = exclusive prefix of the name lengths (entries behind the count repeat the total, so name_off[n] is
+// the total); names gathered from the PAF text.  `cap` bounds the count, `cap_bytes` the total length.
+static void build_name_table(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t cap, uint64_t cap_bytes,
+                             const unsigned *d_n, const uint64_t *src, const uint32_t *len,
+                             unsigned long long *d_total_bytes, NameTable &out) {
+  out.name_off = arena.alloc<uint64_t>(cap + 1);
+  exclusive_scan<uint64_t>(arena, st, NameLen{len, d_n}, cap + 1, out.name_off,
+                           reinterpret_cast<uint64_t *>(d_total_bytes));
+  out.names = arena.alloc<char>(cap_bytes);
+  if (cap) {
+    MSGPU_LAUNCH("gather_names", st, gather_names_kernel<<<grid_for(cap * 32, 256, 2), 256, 0, st>>>(d_paf, src, out.name_off, d_n, out.names));
   }
 }
 
@@ -464,13 +504,15 @@ void alloc_match_soa(Arena &arena, MatchSoA &s, uint64_t M) {
 
 // Rows arrive in line order.  If they are not already grouped by unitig id (minimap2 emits by query, so they normally
 // are), a stable sort by unitig id groups them and keeps the line order inside a unitig.
-void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &m, uint64_t n_unitigs) {
+void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &m, uint64_t n_unitigs, int known_unsorted) {
   const uint64_t M = m.n;
-  if (M <= 1) return;
-  uint32_t *d_unsorted = arena.alloc<uint32_t>(1);
-  MSGPU_CUDA(cudaMemsetAsync(d_unsorted, 0, sizeof(uint32_t), st));
-  MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, M, d_unsorted));
-  if (!read_back(st, d_unsorted)) return;
+  if (M <= 1 || known_unsorted == 0) return;
+  if (known_unsorted < 0) {
+    uint32_t *d_unsorted = arena.alloc<uint32_t>(1);
+    MSGPU_CUDA(cudaMemsetAsync(d_unsorted, 0, sizeof(uint32_t), st));
+    MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, nullptr, M, d_unsorted));
+    if (!read_back(st, d_unsorted)) return;
+  }
   uint32_t *keys = arena.alloc<uint32_t>(M), *keys2 = arena.alloc<uint32_t>(M);
   uint32_t *idx = arena.alloc<uint32_t>(M), *idx2 = arena.alloc<uint32_t>(M);
   int       g = grid_for(M, 256);
@@ -499,6 +541,12 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   m = MatchSoA{};
   *n_lines_out = 0;
 
+  // Capacities from the byte count alone, so that nothing has to come back to the host before the end:
+  //   a line the reader accepts or rejects without throwing has >= 10 tab-separated fields = >= 20 bytes, so a valid
+  //   file of n bytes has <= n / 20 + 1 lines (more lines: some parsed line is invalid, BlastFileReader.cpp:97-98)
+  const uint64_t cap = n_bytes / 20 + 2;
+  if (cap >= 0xfffffff0ull) throw BuildError{MSGPU_ERR_LIMIT, "PAF buffers of 80 GB and more must be split into shards"};
+
   // ---- K1a line index
   uint64_t     mis      = reinterpret_cast<uintptr_t>(d_paf) & 15u;
   const uint4 *aligned  = reinterpret_cast<const uint4 *>(d_paf - mis);
@@ -506,107 +554,92 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   uint64_t     n_tiles  = (nv + kNlTile - 1) / kNlTile;
   uint32_t    *tile_cnt = arena.alloc<uint32_t>(n_tiles + 1);
   uint32_t    *d_n_nl   = arena.alloc<uint32_t>(1);
-  uint64_t    *d_nlines = arena.alloc<uint64_t>(1);
+  IngestStatus *d_status = arena.alloc<IngestStatus>(1);
+  uint64_t    *line_start = arena.alloc<uint64_t>(cap + 2);
   if (n_tiles) {
     MSGPU_LAUNCH("newline_count", st, newline_count_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt));
   }
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{tile_cnt}, n_tiles, tile_cnt, d_n_nl);
-  uint32_t n_newlines = read_back(st, d_n_nl);
-  if (uint64_t(n_newlines) + 2 >= 0xffffffffull) throw BuildError{MSGPU_ERR_LIMIT, "more than 2^32-2 lines in one PAF"};
-  uint64_t *line_start = arena.alloc<uint64_t>(uint64_t(n_newlines) + 2);
   if (n_tiles) {
-    MSGPU_LAUNCH("newline_write", st, newline_write_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt, line_start));
+    MSGPU_LAUNCH("newline_write", st, newline_write_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt, cap, line_start));
   }
-  MSGPU_LAUNCH("line_index_finish", st, line_index_finish_kernel<<<1, 1, 0, st>>>(d_paf, n_bytes, d_n_nl, line_start, d_nlines));
-  uint64_t n_lines = read_back(st, d_nlines);
-  *n_lines_out     = n_lines;
-  // BlastFileReader::read(): lines 0 .. lineCount-2 (BlastFileReader.cpp:76).  A shard of a PAF that is not the last
-  // one keeps its last line: only the last line of the whole file is never parsed.
-  uint64_t n_parse = drop_last_line ? (n_lines ? n_lines - 1 : 0) : n_lines;
-
-  IngestStatus *d_status = arena.alloc<IngestStatus>(1);
-  IngestStatus  h_status{~0ull, 0, 0, 0, 0};
 
   LineFields f;
-  f.c2        = arena.alloc<int32_t>(n_parse);
-  f.ir1       = arena.alloc<int32_t>(n_parse);
-  f.c6        = arena.alloc<int32_t>(n_parse);
-  f.nr0       = arena.alloc<int32_t>(n_parse);
-  f.nr1       = arena.alloc<int32_t>(n_parse);
-  f.c9        = arena.alloc<int32_t>(n_parse);
-  f.rname_rel = arena.alloc<uint32_t>(n_parse);
-  f.rname_len = arena.alloc<uint16_t>(n_parse);
-  f.uname_len = arena.alloc<uint16_t>(n_parse);
-  f.rhash     = arena.alloc<uint64_t>(n_parse);
-  f.uhash     = arena.alloc<uint64_t>(n_parse);
-  f.flags     = arena.alloc<uint8_t>(n_parse);
-  uint32_t *rslot = arena.alloc<uint32_t>(n_parse), *uslot = arena.alloc<uint32_t>(n_parse);
-  uint32_t *dslot = arena.alloc<uint32_t>(n_parse);
-  uint32_t *rid_of_line = arena.alloc<uint32_t>(n_parse), *uid_of_line = arena.alloc<uint32_t>(n_parse);
-  uint32_t *rank_a = arena.alloc<uint32_t>(n_parse), *rank_b = arena.alloc<uint32_t>(n_parse);
-  uint32_t *d_cnt = arena.alloc<uint32_t>(4);
+  f.c2        = arena.alloc<int32_t>(cap);
+  f.ir1       = arena.alloc<int32_t>(cap);
+  f.c6        = arena.alloc<int32_t>(cap);
+  f.nr0       = arena.alloc<int32_t>(cap);
+  f.nr1       = arena.alloc<int32_t>(cap);
+  f.c9        = arena.alloc<int32_t>(cap);
+  f.rname_rel = arena.alloc<uint32_t>(cap);
+  f.rname_len = arena.alloc<uint16_t>(cap);
+  f.uname_len = arena.alloc<uint16_t>(cap);
+  f.rhash     = arena.alloc<uint64_t>(cap);
+  f.uhash     = arena.alloc<uint64_t>(cap);
+  f.flags     = arena.alloc<uint8_t>(cap);
+  uint32_t *rslot = arena.alloc<uint32_t>(cap), *uslot = arena.alloc<uint32_t>(cap);
+  uint32_t *dslot = arena.alloc<uint32_t>(cap);
+  uint32_t *rid_of_line = arena.alloc<uint32_t>(cap), *uid_of_line = arena.alloc<uint32_t>(cap);
+  uint32_t *rank_a = arena.alloc<uint32_t>(cap), *rank_b = arena.alloc<uint32_t>(cap);
+  // ids are handed out to accepted lines only, and an accepted line is longer still (>= 24 bytes): size the id-indexed
+  // tables and the hash tables (load factor <= 2/3 in the worst case, ~1/4 on real PAF) from that
+  const uint64_t cap_acc = n_bytes / 24 + 2;
+  reads.nlen = arena.alloc<int32_t>(cap_acc);
+  reads.line = arena.alloc<uint32_t>(cap_acc);
+  uint64_t *rsrc = arena.alloc<uint64_t>(cap_acc), *usrc = arena.alloc<uint64_t>(cap_acc);
+  uint32_t *rlen = arena.alloc<uint32_t>(cap_acc), *ulen = arena.alloc<uint32_t>(cap_acc);
+  alloc_match_soa(arena, m, cap_acc);
 
-  const int grid_lines = grid_for(n_parse, 256);
-  uint32_t  n_reads = 0, n_unitigs = 0;
-  InternTable rt{}, ut{};
-
+  const int    grid_lines = grid_for(cap, 256);
+  IngestStatus h{};
   for (int attempt = 0;; ++attempt) {
     if (attempt == 4) throw BuildError{MSGPU_ERR_INTERNAL, "name hash collisions persisted over 4 seeds"};
-    MSGPU_CUDA(cudaMemcpyAsync(d_status, &h_status, sizeof(h_status), cudaMemcpyHostToDevice, st));
-    if (n_parse) {
-      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, n_parse,
-                                                     0x243f6a8885a308d3ull * uint64_t(attempt + 1), f, d_status));
-    }
-    IngestStatus s1 = read_back(st, d_status);
-    if (s1.first_bad_line != ~0ull)
-      throw BuildError{MSGPU_ERR_INVALID_PAF, "Invalid BLAST file. (line " + std::to_string(s1.first_bad_line) + ")"};
-    uint64_t n_acc = s1.n_accepted;
+    IngestStatus init{};
+    init.first_bad_line = ~0ull;
+    MSGPU_CUDA(cudaMemcpyAsync(d_status, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    MSGPU_CUDA(cudaMemsetAsync(f.flags, 0, cap, st)); // the scans below run over the capacity
+    MSGPU_LAUNCH("line_index_finish", st, line_index_finish_kernel<<<1, 1, 0, st>>>(d_paf, n_bytes, d_n_nl, cap, drop_last_line ? 1 : 0, line_start, d_status));
+    MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, 0x243f6a8885a308d3ull * uint64_t(attempt + 1), f, d_status));
 
     // ---- K3 interning
-    rt = make_table(arena, st, n_acc);
-    ut = make_table(arena, st, n_acc);
-    if (n_parse) {
-      MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.rhash, n_parse, rt, rslot));
-      MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.uhash, n_parse, ut, uslot));
-      MSGPU_LAUNCH("intern_verify", st, intern_verify_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, n_parse, f, rt, rslot, ut, uslot, d_status));
-    }
-    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstRead}, n_parse, rank_a, d_cnt + 0);
-    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstUnitig}, n_parse, rank_b, d_cnt + 1);
-    IngestStatus s2 = read_back(st, d_status);
-    if (s2.collision) continue; // astronomically rare: two different names with the same 64-bit hash
-    n_reads   = read_back(st, d_cnt + 0);
-    n_unitigs = read_back(st, d_cnt + 1);
-    break;
-  }
-
-  reads.nlen = arena.alloc<int32_t>(n_reads);
-  reads.line = arena.alloc<uint32_t>(n_reads);
-  uint64_t *rsrc = arena.alloc<uint64_t>(n_reads), *usrc = arena.alloc<uint64_t>(n_unitigs);
-  uint32_t *rlen = arena.alloc<uint32_t>(n_reads), *ulen = arena.alloc<uint32_t>(n_unitigs);
-  if (n_parse) {
-    MSGPU_LAUNCH("intern_assign", st, intern_assign_kernel<<<grid_lines, 256, 0, st>>>(line_start, n_parse, f, rt, rslot, rank_a, ut, uslot, rank_b,
+    InternTable rt = make_table(arena, st, cap_acc + cap_acc / 2), ut = make_table(arena, st, cap_acc + cap_acc / 2);
+    MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.rhash, d_status, rt, rslot));
+    MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.uhash, d_status, ut, uslot));
+    MSGPU_LAUNCH("intern_verify", st, intern_verify_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, f, rt, rslot, ut, uslot, d_status));
+    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstRead}, cap, rank_a, &d_status->n_reads);
+    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstUnitig}, cap, rank_b, &d_status->n_unitigs);
+    MSGPU_LAUNCH("intern_assign", st, intern_assign_kernel<<<grid_lines, 256, 0, st>>>(line_start, d_status, f, rt, rslot, rank_a, ut, uslot, rank_b,
                                                      reads.nlen, reads.line, rsrc, rlen, usrc, ulen));
-  }
-  build_name_table(arena, st, d_paf, n_reads, rsrc, rlen, reads);
-  build_name_table(arena, st, d_paf, n_unitigs, usrc, ulen, unitigs);
+    build_name_table(arena, st, d_paf, cap_acc, n_bytes, &d_status->n_reads, rsrc, rlen, &d_status->read_name_bytes, reads);
+    build_name_table(arena, st, d_paf, cap_acc, n_bytes, &d_status->n_unitigs, usrc, ulen, &d_status->unitig_name_bytes, unitigs);
 
-  // ---- K4 dedup
-  uint64_t    n_acc = read_back(st, d_status).n_accepted;
-  InternTable dt    = make_table(arena, st, n_acc);
-  if (n_parse) {
-    MSGPU_LAUNCH("dedup_insert", st, dedup_insert_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line,
-                                                    uid_of_line));
-    MSGPU_LAUNCH("dedup_flag", st, dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f.flags, dt, dslot));
-  }
+    // ---- K4 dedup
+    InternTable dt = make_table(arena, st, cap_acc + cap_acc / 2);
+    MSGPU_LAUNCH("dedup_insert", st, dedup_insert_kernel<<<grid_lines, 256, 0, st>>>(d_status, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line, uid_of_line));
+    MSGPU_LAUNCH("dedup_flag", st, dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(d_status, f.flags, dt, dslot));
 
-  // ---- K5 compaction (+ grouping sort when the PAF is not grouped by unitig)
-  exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFSurvivor}, n_parse, rank_a, d_cnt + 2);
-  uint64_t M = read_back(st, d_cnt + 2);
-  alloc_match_soa(arena, m, M);
-  if (n_parse) {
-    MSGPU_LAUNCH("compact_matches", st, compact_matches_kernel<<<grid_lines, 256, 0, st>>>(n_parse, f, rank_a, rid_of_line, uid_of_line, m));
+    // ---- K5 compaction
+    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFSurvivor}, cap, rank_a, &d_status->n_matches);
+    MSGPU_LAUNCH("compact_matches", st, compact_matches_kernel<<<grid_lines, 256, 0, st>>>(d_status, f, rank_a, rid_of_line, uid_of_line, m));
+    MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(cap_acc, 256, 2), 256, 0, st>>>(m.unitig, &d_status->n_matches, 0, &d_status->unsorted));
+
+    // ---- the one round trip of the ingest
+    h = read_back(st, d_status);
+    if (h.overflow || h.first_bad_line != ~0ull)
+      throw BuildError{MSGPU_ERR_INVALID_PAF,
+                       h.first_bad_line != ~0ull ? "Invalid BLAST file. (line " + std::to_string(h.first_bad_line) + ")"
+                                                 : std::string("Invalid BLAST file. (lines shorter than 10 fields)")};
+    if (!h.collision) break; // else: two different names with the same 64-bit hash (astronomically rare): new seed
   }
-  group_by_unitig(arena, st, m, n_unitigs);
+  if (h.n_lines + 2 >= 0xffffffffull) throw BuildError{MSGPU_ERR_LIMIT, "more than 2^32-2 lines in one PAF"};
+  *n_lines_out    = h.n_lines;
+  reads.n         = h.n_reads;
+  reads.n_bytes   = h.read_name_bytes;
+  unitigs.n       = h.n_unitigs;
+  unitigs.n_bytes = h.unitig_name_bytes;
+  m.n             = h.n_matches;
+  // grouping sort only when the PAF was not grouped by unitig (minimap2 emits by query, so it normally is)
+  group_by_unitig(arena, st, m, h.n_unitigs, h.unsorted ? 1 : 0);
   build_group_offsets(arena, st, m, unitigs);
 }
 

@@ -57,8 +57,9 @@ struct BuildError {
 void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
                 ReadTable &reads, UnitigTable &unitigs, MatchSoA &matches, bool drop_last_line = true);
 void alloc_match_soa(Arena &arena, MatchSoA &s, uint64_t n);
-// stable sort of the rows by unitig id unless they are grouped already
-void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &matches, uint64_t n_unitigs);
+// stable sort of the rows by unitig id unless they are grouped already (known_unsorted: 1 / 0 = the caller has
+// checked, -1 = check here, which costs a round trip to the host)
+void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &matches, uint64_t n_unitigs, int known_unsorted = -1);
 // group offsets for records that arrive already packed (msgpu_build_from_records)
 void build_group_offsets(Arena &arena, cudaStream_t st, const MatchSoA &matches, UnitigTable &unitigs);
 
