@@ -601,6 +601,272 @@ template <bool kExpMatch> __global__ void __launch_bounds__(kFusedBlock, 2) pair
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// K6/K7a, merge variant: the same tile work, ordered by a merge sort that starts from the slices
+// ---------------------------------------------------------------------------------------------------------------------
+// The candidates of a source are generated in slice order and a slice is sorted by read id, so every slice is a sorted
+// run before any sorting happens, and the slices of one row are adjacent.  A word is (second - smin) << 12 | slot:
+// words are unique, and an earlier slice holds smaller slots, so comparing whole words makes every merge stable
+// (candidates of one read pair stay in slice order = unitig order).  Level v merges, inside every row, runs of 2^v
+// slices pairwise.  Each thread produces kMergeV consecutive outputs of the level: one merge-path search on the
+// diagonal of its first output, then a sequential two-way merge — a handful of instructions per element and level,
+// log2(slices per row) levels, one barrier per level.
+constexpr int kMergeV = 9; // outputs per thread and level; odd, so that the per-thread output segments do not collide on banks
+
+struct MergeStage { // the sources of the tile, staged in shared memory
+  uint32_t begin[kSrcCap];    // first partner row of the slice
+  uint32_t base[kSrcCap + 1]; // exclusive prefix of the slice lengths = first candidate slot of the slice
+  int32_t  ir0[kSrcCap], ir1[kSrcCap];
+  uint16_t row_first[kSrcCap], row_end[kSrcCap]; // the sources [row_first, row_end) belong to the same read (row)
+};
+
+struct MergeShared { // everything but the two word buffers, which follow it in dynamic shared memory
+  uint16_t   ent_src[kTileCap]; // slot -> source whose slice owns the slot (| kDropped: failed the overlap test)
+  MergeStage src;
+  uint32_t   scan[33];
+  uint32_t   warp_tot[kFusedWarps];
+  uint32_t   smin, smax, max_row_src;
+};
+constexpr uint16_t kDropped           = 0x8000u;
+constexpr size_t   kMergeOff          = (sizeof(MergeShared) + 15) & ~size_t(15);
+constexpr size_t   kMergeBytesWide    = kMergeOff + 2 * kTileCap * sizeof(unsigned long long);
+constexpr size_t   kMergeBytesNarrow  = kMergeOff + 2 * kTileCap * sizeof(uint32_t);
+
+template <class W>
+__device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W *wa, W *wb, uint32_t st_idx,
+                                           uint32_t n_src, uint32_t n_ent) {
+  const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
+  const uint32_t smin  = s.smin;
+  const uint32_t per   = (n_ent + kFusedBlock - 1) / kFusedBlock;
+  const uint32_t wbase = w * per * 32; // warp w owns slots / positions [wbase, wbase + per * 32)
+
+  // ---- materialise the candidates in generation order (source by source = unitig order inside a row)
+  if (wbase < n_ent) {
+    uint32_t j = 0, hi = n_src; // last source with base <= wbase (empty slices share their base with the next one)
+    while (hi - j > 1) {
+      uint32_t mid = (j + hi) >> 1;
+      if (s.src.base[mid] <= wbase) j = mid; else hi = mid;
+    }
+    for (uint32_t it = 0; it < per; ++it) {
+      const uint32_t e = wbase + it * 32 + l;
+      if (e < n_ent) {
+        while (s.src.base[j + 1] <= e) ++j; // slots grow with `it`, so every lane walks forward only
+        const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
+        const uint32_t sr = a.p_read[ib];
+        const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = a.p_ir0[ib], b1 = a.p_ir1[ib];
+        const int      o0 = a0 > b0 ? a0 : b0, o1 = a1 < b1 ? a1 : b1;
+        const bool     keep = o0 <= o1 && o1 - o0 > kThOverlapF; // MatchMap.cpp:192
+        wa[e]               = (W(sr - smin) << kIdxBits) | W(e);
+        s.ent_src[e]        = uint16_t(j) | (keep ? uint16_t(0) : kDropped);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- merge levels
+  W *in = wa, *out = wb;
+  const uint32_t max_row = s.max_row_src;
+  for (uint32_t lvl = 0; (1u << lvl) < max_row; ++lvl) {
+    const uint32_t G   = 1u << lvl;
+    uint32_t       pos = t * kMergeV;
+    const uint32_t oe  = pos + kMergeV < n_ent ? pos + kMergeV : n_ent;
+    while (pos < oe) {
+      const uint32_t j  = s.ent_src[pos] & (kSrcCap - 1); // slice that owns output position pos
+      const uint32_t rf = s.src.row_first[j], re = s.src.row_end[j];
+      const uint32_t s0 = rf + (((j - rf) >> (lvl + 1)) << (lvl + 1)); // the pair: runs [s0, s1) and [s1, s2)
+      const uint32_t s1 = s0 + G < re ? s0 + G : re, s2 = s0 + 2 * G < re ? s0 + 2 * G : re;
+      const uint32_t a0 = s.src.base[s0], a1 = s.src.base[s1], b1 = s.src.base[s2];
+      const uint32_t seg_end = oe < b1 ? oe : b1;
+      if (a1 == b1 || a0 == a1) { // one side empty: the run is copied
+        for (uint32_t p = pos; p < seg_end; ++p) out[p] = in[p];
+      } else {
+        const uint32_t k  = pos - a0, na = a1 - a0, nb = b1 - a1;
+        uint32_t       lo = k > nb ? k - nb : 0u, hi = k < na ? k : na; // merge path: elements of A among the first k
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (in[a0 + mid] < in[a1 + (k - 1 - mid)]) lo = mid + 1; else hi = mid;
+        }
+        uint32_t ia = a0 + lo, ib = a1 + (k - lo);
+        W        xa = ia < a1 ? in[ia] : W(0), xb = ib < b1 ? in[ib] : W(0);
+        for (uint32_t p = pos; p < seg_end; ++p) {
+          const bool take_a = ib >= b1 || (ia < a1 && xa < xb);
+          out[p]            = take_a ? xa : xb;
+          if (take_a) {
+            ++ia;
+            xa = ia < a1 ? in[ia] : W(0);
+          } else {
+            ++ib;
+            xb = ib < b1 ? in[ib] : W(0);
+          }
+        }
+      }
+      pos = seg_end;
+    }
+    __syncthreads();
+    W *tmp = in;
+    in     = out;
+    out    = tmp;
+  }
+  const W *sorted = in;
+
+  // ---- run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the key
+  // of its pair) but is skipped; the head of a run is its first surviving candidate.
+  uint32_t vmask = 0, hmask = 0, n_v = 0, n_h = 0; // bit `it`: this lane's item of iteration `it` survives / is a head
+  for (uint32_t it = 0; it < per; ++it) {
+    const uint32_t k = wbase + it * 32 + l;
+    bool           ok = false, head = false;
+    if (k < n_ent) {
+      const W x = sorted[k];
+      ok        = !(s.ent_src[uint32_t(x) & (kTileCap - 1)] & kDropped);
+      if (ok) {
+        head = true;
+        const W        key       = x >> kIdxBits;
+        const uint32_t row_start = s.src.base[s.src.row_first[s.ent_src[k] & (kSrcCap - 1)]];
+        for (uint32_t p = k; p > row_start;) {
+          --p;
+          const W y = sorted[p];
+          if ((y >> kIdxBits) != key) break;
+          if (!(s.ent_src[uint32_t(y) & (kTileCap - 1)] & kDropped)) {
+            head = false;
+            break;
+          }
+        }
+      }
+    }
+    vmask |= (ok ? 1u : 0u) << it;
+    hmask |= (head ? 1u : 0u) << it;
+    n_v += __popc(__ballot_sync(0xffffffffu, ok));
+    n_h += __popc(__ballot_sync(0xffffffffu, head));
+  }
+  if (l == 0) s.warp_tot[w] = n_v | (n_h << 16);
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int ww = 0; ww < kFusedWarps; ++ww) {
+    uint32_t c = s.warp_tot[ww];
+    before += ww < int(w) ? c : 0u;
+    total += c;
+  }
+  if (t == 0) a.tile_cnt[st_idx] = make_uint2(total & 0xffffu, total >> 16);
+
+  // ---- the tile's records, compacted, in final order
+  uint2   *rec = a.records + uint64_t(st_idx) * kTileCap;
+  uint32_t pv = before & 0xffffu, ph = before >> 16;
+  for (uint32_t it = 0; it < per; ++it) {
+    const uint32_t k  = wbase + it * 32 + l;
+    const bool     ok = (vmask >> it) & 1u, head = (hmask >> it) & 1u;
+    const unsigned bv = __ballot_sync(0xffffffffu, ok), bh = __ballot_sync(0xffffffffu, head);
+    const unsigned lt = (1u << l) - 1u;
+    if (ok) {
+      const uint32_t e  = uint32_t(sorted[k]) & (kTileCap - 1);
+      const uint32_t j  = s.ent_src[e] & (kSrcCap - 1);
+      const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
+      rec[pv + __popc(bv & lt)] = make_uint2(ib, j | (head ? 1u << kSrcBits : 0u) | ((ph + __popc(bh & lt)) << (kSrcBits + 1)));
+    }
+    pv += __popc(bv);
+    ph += __popc(bh);
+  }
+}
+
+__global__ void __launch_bounds__(kFusedBlock, 2) pair_tiles_merge_kernel(TileArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MergeShared   &s = *reinterpret_cast<MergeShared *>(smem_raw);
+  const unsigned t = threadIdx.x, l = t & 31;
+
+  for (uint32_t tile = a.tile_lo + blockIdx.x; tile < a.tile_hi; tile += gridDim.x) {
+    __syncthreads(); // previous tile fully done with shared memory
+    if (t == 0) {
+      s.smin        = 0xffffffffu;
+      s.smax        = 0;
+      s.max_row_src = 0;
+    }
+    __syncthreads();
+    const uint32_t st_idx = tile - a.tile_lo;
+    const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
+    const uint32_t q0 = a.rd_off[r0];
+    const uint32_t n_src = (kind ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
+    if (n_src > kSrcCap) { // cannot happen: see the planning kernels
+      if (t == 0) {
+        *a.error           = 1;
+        a.tile_cnt[st_idx] = make_uint2(0, 0);
+      }
+      continue;
+    }
+    { // ---- stage the sources (kSrcCap <= blockDim.x: one per thread)
+      const uint32_t j = t;
+      uint32_t       len = 0, lmin = 0xffffffffu, lmax = 0, row_src = 0;
+      if (j < n_src) {
+        const uint32_t q   = a.rd_src[q0 + j];
+        const PairRow  row = a.rows[q];
+        uint32_t       b, e;
+        if (kind) {
+          const uint32_t *sl = a.slices + a.slice_off[r0] + uint64_t(kind - 1) * n_src;
+          b                  = sl[j];
+          e                  = sl[n_src + j];
+          s.src.row_first[j] = 0;
+          s.src.row_end[j]   = uint16_t(n_src);
+          row_src            = n_src;
+        } else {
+          b                  = q + 1;
+          e                  = a.grp_off[row.unitig + 1];
+          const uint32_t f   = a.rd_off[row.read] - q0, g = a.rd_off[row.read + 1] - q0;
+          s.src.row_first[j] = uint16_t(f);
+          s.src.row_end[j]   = uint16_t(g);
+          row_src            = g - f;
+        }
+        len            = e - b;
+        s.src.begin[j] = b;
+        s.src.ir0[j]   = row.ir0;
+        s.src.ir1[j]   = row.ir1;
+        if (len) { // the slice is sorted by read id
+          lmin = a.p_read[b];
+          lmax = a.p_read[e - 1];
+        }
+      }
+      uint32_t tot, ex = block_exclusive_scan<uint32_t>(len, s.scan, &tot);
+      if (j < n_src) s.src.base[j] = ex;
+      if (t == 0) s.src.base[n_src] = tot;
+      for (int d = 16; d > 0; d >>= 1) {
+        uint32_t omin = __shfl_xor_sync(0xffffffffu, lmin, d), omax = __shfl_xor_sync(0xffffffffu, lmax, d);
+        uint32_t orow = __shfl_xor_sync(0xffffffffu, row_src, d);
+        lmin    = omin < lmin ? omin : lmin;
+        lmax    = omax > lmax ? omax : lmax;
+        row_src = orow > row_src ? orow : row_src;
+      }
+      if (l == 0) {
+        if (lmin <= lmax) {
+          atomicMin(&s.smin, lmin);
+          atomicMax(&s.smax, lmax);
+        }
+        atomicMax(&s.max_row_src, row_src);
+      }
+    }
+    __syncthreads();
+    const uint32_t n_ent = s.src.base[n_src];
+    if (n_ent > kTileCap) {
+      if (t == 0) {
+        *a.error           = 2;
+        a.tile_cnt[st_idx] = make_uint2(0, 0);
+      }
+      continue;
+    }
+    const int      sb    = (n_ent && s.smax > s.smin) ? 32 - __clz(s.smax - s.smin) : 0;
+    unsigned char *words = smem_raw + kMergeOff;
+    if (sb + kIdxBits <= 32) {
+      uint32_t *wa = reinterpret_cast<uint32_t *>(words);
+      merge_tail<uint32_t>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent);
+    } else if (!a.wide) { // cannot happen: the host sizes the launch from the id width
+      if (t == 0) {
+        *a.error           = 3;
+        a.tile_cnt[st_idx] = make_uint2(0, 0);
+      }
+    } else {
+      unsigned long long *wa = reinterpret_cast<unsigned long long *>(words);
+      merge_tail<unsigned long long>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // K7b: tile counts -> global offsets of every tile's first edge match and first edge (one CTA; tiles are few)
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
@@ -844,11 +1110,21 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
     const size_t bytes = a.wide ? kTileBytesWide : kTileBytesNarrow;
     int          grid  = kNumSMs * 2 * 4; // a few waves of two resident CTAs per SM, tiles strided over them
     if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
-    const char *exp_rank = std::getenv("MSGPU_EXP_RANK");
-    if (exp_rank && exp_rank[0] == 'm')
-      MSGPU_LAUNCH("pair_tiles", st, pair_tiles_kernel<true><<<grid, kFusedBlock, bytes, st>>>(a));
-    else
+    const char *exp_sort = std::getenv("MSGPU_EXP_SORT");
+    if (exp_sort && exp_sort[0] == 'r') { // radix variant
       MSGPU_LAUNCH("pair_tiles", st, pair_tiles_kernel<false><<<grid, kFusedBlock, bytes, st>>>(a));
+    } else {
+      static bool attr2 = false;
+      if (!attr2) {
+        MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
+        attr2 = true;
+      }
+      // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits
+      a.wide = R > (1ull << (32 - kIdxBits)) ? 1u : 0u;
+      grid   = kNumSMs * (a.wide ? 2 : 3) * 4; // 40 registers, 51 KB (narrow): three resident CTAs per SM
+      if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
+      MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
+    }
   }
   MSGPU_LAUNCH("scan_tiles", st, scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_cnt, my_tiles, em_base, ed_base, totals, e.em_begin));
   if (my_tiles) {
