@@ -40,6 +40,16 @@ public:
     for (auto &s : m_slabs) cudaFree(s.base);
     m_slabs.clear();
     m_used = m_high = 0;
+    if (m_counter) cudaFree(m_counter);
+    m_counter = nullptr;
+  }
+  // a zero-initialised device counter that outlives reset(): kernels that use it leave it at zero again
+  unsigned *counter() {
+    if (!m_counter) {
+      MSGPU_CUDA(cudaMalloc(&m_counter, 256));
+      MSGPU_CUDA(cudaMemset(m_counter, 0, 256));
+    }
+    return m_counter;
   }
   // start a new build: if the previous one spilled into several slabs, replace them by one of the total size
   void reset() {
@@ -83,6 +93,7 @@ private:
   };
   std::vector<Slab> m_slabs;
   size_t            m_used = 0, m_high = 0;
+  unsigned         *m_counter = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -163,62 +163,96 @@ __device__ __forceinline__ uint64_t name_hash(const char *s, uint32_t n, uint64_
   return mix64(h) | 1ull; // 0 is the empty-slot marker
 }
 
-__global__ void __launch_bounds__(256)
-    parse_lines_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ line_start, uint64_t seed,
-                       LineFields f, IngestStatus *status) {
-  const uint64_t n_parse = status->n_parse;
-  unsigned       n_acc   = 0;
-  for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
-       li += uint64_t(gridDim.x) * blockDim.x) {
-    const char *s   = paf + line_start[li];
-    uint64_t    len = line_start[li + 1] - line_start[li] - 1; // getLine() drops the last character of the line
-    // std::getline(iss, token, '\t'): a field exists iff at least one character is left
-    uint32_t fo[10], fl[10];
-    int      ntok = 0;
-    uint64_t p    = 0;
-    while (p < len && ntok < 10) {
-      uint64_t q = p;
-      while (q < len && s[q] != '\t') ++q;
-      fo[ntok] = uint32_t(p);
-      fl[ntok] = uint32_t(q - p);
-      ++ntok;
-      p = q + 1;
-    }
-    uint8_t flags = 0;
-    bool    bad   = ntok < 10; // BlastFileReader.cpp:97 ("Invalid BLAST file.")
-    int     c2 = 0, c3 = 0, c9 = 0, c6 = 0, c7 = 0, c8 = 0;
-    if (!bad)
-      bad = !(dev_stoi(s + fo[2], fl[2], &c2) && dev_stoi(s + fo[3], fl[3], &c3) && dev_stoi(s + fo[9], fl[9], &c9) &&
-              dev_stoi(s + fo[6], fl[6], &c6));
-    if (!bad) {
-      int      ir1     = c3 - 1;
-      int      ilen    = ir1 - c2 + 1;
-      uint64_t matches = uint64_t((long long)c9); // static_cast<std::size_t>(int), BlastFileReader.cpp:102
-      bool     add     = matches >= uint64_t(kMinimumMatches) && ilen >= kMinimumMatches;
-      if (add) {
-        bad = !(dev_stoi(s + fo[7], fl[7], &c7) && dev_stoi(s + fo[8], fl[8], &c8));
-        if (!bad && (fl[5] > 0xffffu || fl[0] > 0xffffu)) bad = true; // names longer than 64 KiB are not supported
-        if (!bad) {
-          flags = kFAccepted;
-          if (fl[4] == 1 && s[fo[4]] == '+') flags |= kFDir;
-          if (ilen >= kThLength && matches >= kThMatches) flags |= kFPrim;
-          f.c2[li]        = c2;
-          f.ir1[li]       = ir1;
-          f.c6[li]        = c6;
-          f.nr0[li]       = c7;
-          f.nr1[li]       = c8 - 1;
-          f.c9[li]        = c9;
-          f.rname_rel[li] = fo[5];
-          f.rname_len[li] = uint16_t(fl[5]);
-          f.uname_len[li] = uint16_t(fl[0]);
-          f.rhash[li]     = name_hash(s + fo[5], fl[5], seed);
-          f.uhash[li]     = name_hash(s + fo[0], fl[0], seed ^ 0x9e3779b97f4a7c15ull);
-          ++n_acc;
-        }
+// the tokenising + std::stoi + filter of one line whose text starts at `s` (shared or global memory)
+__device__ __forceinline__ bool parse_one_line(const char *s, uint64_t len, uint64_t li, uint64_t seed, LineFields &f,
+                                               bool *bad_out) {
+  // std::getline(iss, token, '\t'): a field exists iff at least one character is left
+  uint32_t fo[10], fl[10];
+  int      ntok = 0;
+  uint64_t p    = 0;
+  while (p < len && ntok < 10) {
+    uint64_t q = p;
+    while (q < len && s[q] != '\t') ++q;
+    fo[ntok] = uint32_t(p);
+    fl[ntok] = uint32_t(q - p);
+    ++ntok;
+    p = q + 1;
+  }
+  uint8_t flags = 0;
+  bool    bad   = ntok < 10; // BlastFileReader.cpp:97 ("Invalid BLAST file.")
+  bool    acc   = false;
+  int     c2 = 0, c3 = 0, c9 = 0, c6 = 0, c7 = 0, c8 = 0;
+  if (!bad)
+    bad = !(dev_stoi(s + fo[2], fl[2], &c2) && dev_stoi(s + fo[3], fl[3], &c3) && dev_stoi(s + fo[9], fl[9], &c9) &&
+            dev_stoi(s + fo[6], fl[6], &c6));
+  if (!bad) {
+    int      ir1     = c3 - 1;
+    int      ilen    = ir1 - c2 + 1;
+    uint64_t matches = uint64_t((long long)c9); // static_cast<std::size_t>(int), BlastFileReader.cpp:102
+    bool     add     = matches >= uint64_t(kMinimumMatches) && ilen >= kMinimumMatches;
+    if (add) {
+      bad = !(dev_stoi(s + fo[7], fl[7], &c7) && dev_stoi(s + fo[8], fl[8], &c8));
+      if (!bad && (fl[5] > 0xffffu || fl[0] > 0xffffu)) bad = true; // names longer than 64 KiB are not supported
+      if (!bad) {
+        flags = kFAccepted;
+        if (fl[4] == 1 && s[fo[4]] == '+') flags |= kFDir;
+        if (ilen >= kThLength && matches >= kThMatches) flags |= kFPrim;
+        f.c2[li]        = c2;
+        f.ir1[li]       = ir1;
+        f.c6[li]        = c6;
+        f.nr0[li]       = c7;
+        f.nr1[li]       = c8 - 1;
+        f.c9[li]        = c9;
+        f.rname_rel[li] = fo[5];
+        f.rname_len[li] = uint16_t(fl[5]);
+        f.uname_len[li] = uint16_t(fl[0]);
+        f.rhash[li]     = name_hash(s + fo[5], fl[5], seed);
+        f.uhash[li]     = name_hash(s + fo[0], fl[0], seed ^ 0x9e3779b97f4a7c15ull);
+        acc             = true;
       }
     }
-    if (bad) atomicMin(&status->first_bad_line, (unsigned long long)li);
-    f.flags[li] = flags;
+  }
+  *bad_out    = bad;
+  f.flags[li] = flags;
+  return acc;
+}
+
+// One thread per line, a block per run of 256 consecutive lines.  A thread walks its line byte by byte; straight from
+// global memory that costs one L1 wavefront per lane and byte (32 lanes, 32 different cache lines).  So the block
+// first copies the text of its 256 lines — one contiguous piece of the buffer — into shared memory with coalesced
+// 128-bit loads, when it fits (it does unless lines carry long cg:Z tags; then the lines are read in place).
+constexpr int      kParseBlock = 256;
+constexpr uint32_t kParseStage = 40 * 1024;
+
+__global__ void __launch_bounds__(kParseBlock)
+    parse_lines_kernel(const char *__restrict__ paf, uint64_t n_bytes, const uint64_t *__restrict__ line_start,
+                       uint64_t seed, LineFields f, IngestStatus *status) {
+  __shared__ __align__(16) char stage[kParseStage + 32];
+  const uint64_t n_parse = status->n_parse;
+  unsigned       n_acc   = 0;
+  for (uint64_t l0 = uint64_t(blockIdx.x) * kParseBlock; l0 < n_parse; l0 += uint64_t(gridDim.x) * kParseBlock) {
+    const uint64_t l1 = l0 + kParseBlock < n_parse ? l0 + kParseBlock : n_parse;
+    const uint64_t b0 = line_start[l0];
+    uint64_t       b1 = line_start[l1]; // one past the terminator of the last line of the run
+    if (b1 > n_bytes) b1 = n_bytes;     // the virtual terminator of an unterminated last line
+    const uint64_t a0     = (reinterpret_cast<uintptr_t>(paf) + b0) & 15u; // distance to the 16-byte boundary below
+    const bool     staged = b1 - b0 + a0 <= kParseStage;
+    __syncthreads(); // the previous run is done with the staging buffer
+    if (staged) {
+      const uint4   *src = reinterpret_cast<const uint4 *>(paf + b0 - a0);
+      const uint64_t nv  = (b1 - b0 + a0 + 15) >> 4;
+      for (uint64_t v = threadIdx.x; v < nv; v += kParseBlock) reinterpret_cast<uint4 *>(stage)[v] = ld_stream_u4(src + v);
+    }
+    __syncthreads();
+    const uint64_t li = l0 + threadIdx.x;
+    if (li < l1) {
+      const uint64_t ls  = line_start[li];
+      const uint64_t len = line_start[li + 1] - ls - 1; // getLine() drops the last character of the line
+      const char    *s   = staged ? stage + a0 + (ls - b0) : paf + ls;
+      bool           bad;
+      if (parse_one_line(s, len, li, seed, f, &bad)) ++n_acc;
+      if (bad) atomicMin(&status->first_bad_line, (unsigned long long)li);
+    }
   }
   n_acc = warp_reduce_sum(n_acc);
   if (lane_id() == 0 && n_acc) atomicAdd(&status->n_accepted, n_acc);
@@ -599,7 +633,7 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     MSGPU_CUDA(cudaMemcpyAsync(d_status, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     MSGPU_CUDA(cudaMemsetAsync(f.flags, 0, cap, st)); // the scans below run over the capacity
     MSGPU_LAUNCH("line_index_finish", st, line_index_finish_kernel<<<1, 1, 0, st>>>(d_paf, n_bytes, d_n_nl, cap, drop_last_line ? 1 : 0, line_start, d_status));
-    MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, 0x243f6a8885a308d3ull * uint64_t(attempt + 1), f, d_status));
+    MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, 0x243f6a8885a308d3ull * uint64_t(attempt + 1), f, d_status));
 
     // ---- K3 interning
     InternTable rt = make_table(arena, st, cap_acc + cap_acc / 2), ut = make_table(arena, st, cap_acc + cap_acc / 2);

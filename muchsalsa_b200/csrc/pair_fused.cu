@@ -67,12 +67,50 @@ struct __align__(16) PairRow {
 // pre-pass 1: order every group by read id, build the pair rows, and accumulate per read its number of sources and
 // its number of candidates
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    rank_rows_kernel(MatchSoA m, const uint32_t *__restrict__ grp_off, PairRow *__restrict__ rows,
-                     uint32_t *__restrict__ p_read, int32_t *__restrict__ p_ir0, int32_t *__restrict__ p_ir1,
-                     uint32_t *__restrict__ deg, unsigned long long *__restrict__ wgt) {
+struct RankArgs {
+  MatchSoA            m;
+  const uint32_t     *grp_off;
+  PairRow            *rows;
+  uint32_t           *p_read;
+  int32_t            *p_ir0, *p_ir1;
+  uint32_t           *deg;
+  unsigned long long *wgt;
+  uint32_t           *heavy_list; // matches of groups too long for one thread each
+  unsigned int       *heavy_n;
+};
+constexpr uint32_t kRankHeavy = 512; // groups longer than this are ranked by one warp per match
+
+// match i is the q-th of its group in read order: write its pair row and account its partners to its read
+__device__ __forceinline__ void place_row(const RankArgs &a, uint64_t i, uint32_t u, uint32_t q, uint32_t g1) {
+  const MatchSoA &m = a.m;
+  PairRow         row;
+  row.ir0    = m.ir0[i];
+  row.ir1    = m.ir1[i];
+  row.read   = m.read[i];
+  row.score  = m.score[i];
+  row.line   = m.line[i];
+  row.flags  = m.flags[i];
+  row.unitig = u;
+  row.pad    = 0;
+  a.rows[q]   = row;
+  a.p_read[q] = row.read;
+  a.p_ir0[q]  = row.ir0;
+  a.p_ir1[q]  = row.ir1;
+  const uint32_t len = g1 - q - 1; // partners = the members behind q
+  if (len) {
+    atomicAdd(&a.deg[row.read], 1u);
+    atomicAdd(&a.wgt[row.read], (unsigned long long)len);
+  }
+}
+
+__global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a) {
+  const MatchSoA &m = a.m;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += uint64_t(gridDim.x) * blockDim.x) {
-    const uint32_t u = m.unitig[i], g0 = grp_off[u], g1 = grp_off[u + 1], my = m.read[i];
+    const uint32_t u = m.unitig[i], g0 = a.grp_off[u], g1 = a.grp_off[u + 1], my = m.read[i];
+    if (g1 - g0 > kRankHeavy) { // a repeat: thousands of members; one thread per member would be the tail of the kernel
+      a.heavy_list[atomicAdd(a.heavy_n, 1u)] = uint32_t(i);
+      continue;
+    }
     // reads are unique inside a group (MatchMap.cpp:64-73 keeps one match per (read, unitig)), so the rank is exact
     uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, j = g0;
     for (; j + 4 <= g1; j += 4) {
@@ -82,25 +120,22 @@ __global__ void __launch_bounds__(256)
       r3 += m.read[j + 3] < my;
     }
     for (; j < g1; ++j) r0 += m.read[j] < my;
-    const uint32_t q = g0 + r0 + r1 + r2 + r3;
-    PairRow        row;
-    row.ir0    = m.ir0[i];
-    row.ir1    = m.ir1[i];
-    row.read   = my;
-    row.score  = m.score[i];
-    row.line   = m.line[i];
-    row.flags  = m.flags[i];
-    row.unitig = u;
-    row.pad    = 0;
-    rows[q]    = row;
-    p_read[q]  = my;
-    p_ir0[q]   = row.ir0;
-    p_ir1[q]   = row.ir1;
-    const uint32_t len = g1 - q - 1; // partners = the members behind q
-    if (len) {
-      atomicAdd(&deg[my], 1u);
-      atomicAdd(&wgt[my], (unsigned long long)len);
-    }
+    place_row(a, i, u, g0 + r0 + r1 + r2 + r3, g1);
+  }
+}
+
+// one warp per member of a long group: the lanes share the count
+__global__ void __launch_bounds__(256) rank_rows_heavy_kernel(RankArgs a) {
+  const MatchSoA &m  = a.m;
+  const unsigned  l  = threadIdx.x & 31;
+  const uint64_t  nw = (uint64_t(gridDim.x) * blockDim.x) >> 5, n = *a.heavy_n;
+  for (uint64_t x = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; x < n; x += nw) {
+    const uint64_t i = a.heavy_list[x];
+    const uint32_t u = m.unitig[i], g0 = a.grp_off[u], g1 = a.grp_off[u + 1], my = m.read[i];
+    uint32_t       r = 0;
+    for (uint32_t j = g0 + l; j < g1; j += 32) r += m.read[j] < my;
+    r = warp_reduce_sum(r);
+    if (l == 0) place_row(a, i, u, g0 + r, g1);
   }
 }
 
@@ -238,6 +273,35 @@ __global__ void __launch_bounds__(256)
     const uint32_t q0 = rd_off[r];
     uint32_t      *out = slices + slice_off[r];
     const uint64_t target = uint64_t(j) * plan.sub_cap(r);
+    if (d <= 32) {
+      // one source per lane.  Every probe of the bisection narrows the lane's window [wlo, whi) of positions where
+      // later lower bounds can fall, so the searches get shorter as the bracket [lo, hi] closes.
+      const bool has = l < d;
+      uint32_t   b = 0, e = 0;
+      if (has) {
+        const uint32_t q = rd_src[q0 + l];
+        b                = q + 1;
+        e                = grp_off[rows[q].unitig + 1];
+      }
+      uint32_t wlo = b, whi = e, lo = 0, hi = n_reads; // invariant: C(lo) <= target, wlo = lower bound of lo
+      while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+        const uint32_t pos = has ? lower_bound_u32(p_read, wlo, whi, mid) : 0u;
+        const uint64_t c   = warp_reduce_sum(uint64_t(pos - b));
+        if (c <= target) {
+          lo  = mid;
+          wlo = pos;
+        } else {
+          hi  = mid - 1;
+          whi = pos;
+        }
+      }
+      if (has) {
+        out[uint64_t(j) * d + l] = j == 0 ? b : wlo;
+        if (j == ns - 1) out[uint64_t(ns) * d + l] = e;
+      }
+      continue;
+    }
     // bisection: largest s in [0, n_reads] with C(s) <= target
     uint32_t lo = 0, hi = n_reads; // invariant: C(lo) <= target
     while (lo < hi) {
@@ -607,10 +671,9 @@ template <bool kExpMatch> __global__ void __launch_bounds__(kFusedBlock, 2) pair
 // run before any sorting happens, and the slices of one row are adjacent.  A word is (second - smin) << 12 | slot:
 // words are unique, and an earlier slice holds smaller slots, so comparing whole words makes every merge stable
 // (candidates of one read pair stay in slice order = unitig order).  Level v merges, inside every row, runs of 2^v
-// slices pairwise.  Each thread produces kMergeV consecutive outputs of the level: one merge-path search on the
-// diagonal of its first output, then a sequential two-way merge — a handful of instructions per element and level,
-// log2(slices per row) levels, one barrier per level.
-constexpr int kMergeV = 9; // outputs per thread and level; odd, so that the per-thread output segments do not collide on banks
+// slices pairwise.  Each thread produces ceil(n / 512) consecutive outputs of the level: one merge-path search on
+// the diagonal of its first output, then a sequential two-way merge — a handful of instructions per element and
+// level, log2(slices per row) levels, one barrier per level.
 
 struct MergeStage { // the sources of the tile, staged in shared memory
   uint32_t begin[kSrcCap];    // first partner row of the slice
@@ -667,8 +730,8 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
   const uint32_t max_row = s.max_row_src;
   for (uint32_t lvl = 0; (1u << lvl) < max_row; ++lvl) {
     const uint32_t G   = 1u << lvl;
-    uint32_t       pos = t * kMergeV;
-    const uint32_t oe  = pos + kMergeV < n_ent ? pos + kMergeV : n_ent;
+    uint32_t       pos = t * per; // `per` consecutive outputs per thread: every thread of the block has work
+    const uint32_t oe  = pos + per < n_ent ? pos + per : n_ent;
     while (pos < oe) {
       const uint32_t j  = s.ent_src[pos] & (kSrcCap - 1); // slice that owns output position pos
       const uint32_t rf = s.src.row_first[j], re = s.src.row_end[j];
@@ -1018,7 +1081,13 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   MSGPU_CUDA(cudaMemsetAsync(cursor, 0, (R + 1) * sizeof(uint32_t), st));
   MSGPU_CUDA(cudaMemsetAsync(d_u32, 0, 4 * sizeof(uint32_t), st));
   const int gm = grid_for(M, 256), gr = grid_for(R, 256);
-  if (M) MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<gm, 256, 0, st>>>(m, unitigs.grp_off, rows, p_read, p_ir0, p_ir1, deg, wgt));
+  if (M) {
+    RankArgs ra{m, unitigs.grp_off, rows, p_read, p_ir0, p_ir1, deg, wgt, arena.alloc<uint32_t>(M), d_u32 + 3};
+    // (d_u32[3] doubles as the tile kernels' error flag later: it is reset after this use)
+    MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<gm, 256, 0, st>>>(ra));
+    MSGPU_LAUNCH("rank_rows_heavy", st, rank_rows_heavy_kernel<<<grid_for(M * 32, 256, 4), 256, 0, st>>>(ra));
+    MSGPU_CUDA(cudaMemsetAsync(d_u32 + 3, 0, sizeof(uint32_t), st));
+  }
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{deg}, R, rd_off, d_u32 + 0);
   MSGPU_CUDA(cudaMemcpyAsync(rd_off + R, d_u32 + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
 
