@@ -136,7 +136,8 @@ struct LineFields { // per-line scratch, structure-of-arrays, indexed by line
 
 __device__ __forceinline__ bool dev_isspace(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
-// std::stoi on [s, s+n): false if it would throw (no digits / out of int range)
+// std::stoi on [s, s+n): false if it would throw (no digits / out of int range).  32-bit arithmetic: up to 9
+// significant digits cannot overflow, the 10th is checked once, more are out of range.
 __device__ __forceinline__ bool dev_stoi(const char *s, uint32_t n, int *out) {
   uint32_t i = 0;
   while (i < n && dev_isspace(s[i])) ++i;
@@ -145,22 +146,37 @@ __device__ __forceinline__ bool dev_stoi(const char *s, uint32_t n, int *out) {
     neg = s[i] == '-';
     ++i;
   }
-  if (i >= n || s[i] < '0' || s[i] > '9') return false;
-  long long v = 0;
-  for (; i < n && s[i] >= '0' && s[i] <= '9'; ++i) {
-    v = v * 10 + (s[i] - '0');
-    if (v > 2147483648ll) return false;
-  }
-  if (neg) v = -v;
-  if (v > 2147483647ll || v < -2147483648ll) return false;
-  *out = int(v);
+  if (i >= n) return false;
+  uint32_t d = uint32_t(s[i]) - uint32_t('0');
+  if (d > 9u) return false;
+  uint32_t v = 0, sig = 0; // sig: digits since the first non-zero one
+  do {
+    if (sig == 9) { // the 10th significant digit decides
+      if (v > 214748364u || (v == 214748364u && d > (neg ? 8u : 7u))) return false;
+    } else if (sig > 9) {
+      return false;
+    }
+    v   = v * 10u + d;
+    sig = (sig | v) ? sig + 1 : 0;
+    ++i;
+    if (i >= n) break;
+    d = uint32_t(s[i]) - uint32_t('0');
+  } while (d <= 9u);
+  *out = neg ? int(0u - v) : int(v);
   return true;
 }
 
+// 64-bit name hash from two independent 32-bit multiplicative streams (a 64-bit multiply per byte costs four times
+// as much on this machine); 0 is the empty-slot marker of the tables, so the low bit is forced
 __device__ __forceinline__ uint64_t name_hash(const char *s, uint32_t n, uint64_t seed) {
-  uint64_t h = 1469598103934665603ull ^ seed;
-  for (uint32_t i = 0; i < n; ++i) h = (h ^ (unsigned char)s[i]) * 1099511628211ull;
-  return mix64(h) | 1ull; // 0 is the empty-slot marker
+  uint32_t h1 = 2166136261u ^ uint32_t(seed), h2 = 0x9e3779b9u ^ uint32_t(seed >> 32);
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t c = (unsigned char)s[i];
+    h1               = (h1 ^ c) * 16777619u;
+    h2               = (h2 + c) * 0x85ebca6bu;
+    h2 ^= h2 >> 15;
+  }
+  return mix64((uint64_t(h1) << 32 | h2) ^ (uint64_t(n) << 20)) | 1ull;
 }
 
 // the tokenising + std::stoi + filter of one line whose text starts at `s` (shared or global memory)
