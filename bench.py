@@ -138,13 +138,17 @@ def run_ours(args):
         cfg = synth.scaled(args.workload, world)
         paf = synth.columns_to_paf(synth.generate_columns(cfg, (rank, world), sentinel=(rank == world - 1)))
     n_bytes = len(paf)
+    # ONE explicit stream for everything: the library's kernels, torch's L2 flush and events, and the tensors NCCL
+    # reads and writes.  (Not the default stream: its handle is 0, which the C ABI reads as "the context's own stream";
+    # the flush and the timed work would then run unordered on two streams.)
+    stream = torch.cuda.Stream(dev_t)
+    torch.cuda.set_stream(stream)
     host = torch.frombuffer(bytearray(paf) if n_bytes else bytearray(1), dtype=torch.uint8)[:n_bytes].pin_memory()
     dev = host.cuda()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     gb = GraphBuilder(local)
-    stream = torch.cuda.current_stream()
     gb.set_stream(stream.cuda_stream)
-    sb = multi_gpu.ShardedBuilder(gb, rank, world, dist, dev_t)
+    sb = multi_gpu.ShardedBuilder(gb, rank, world, dist, dev_t, stream)
 
     def barrier():
         if dist is not None:

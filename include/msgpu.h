@@ -60,7 +60,9 @@ int         msgpu_create(int cuda_device, msgpu_ctx **out_ctx);
 void        msgpu_destroy(msgpu_ctx *ctx);
 const char *msgpu_last_error(const msgpu_ctx *ctx);
 int         msgpu_abi_version(void);
-/* All work of the context is enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own stream). */
+/* All work of the context is enqueued on `cuda_stream` (a cudaStream_t; NULL = the context's own non-blocking
+ * stream — note that NULL is also the handle of the legacy default stream, which therefore cannot be selected: a
+ * caller that wants its own work ordered with the context's passes an explicit stream). */
 int         msgpu_set_stream(msgpu_ctx *ctx, void *cuda_stream);
 
 /* ---- construction -------------------------------------------------------------------------------------------------

@@ -89,6 +89,8 @@ class GraphBuilder:
         return self._h
 
     def set_stream(self, cuda_stream: int | None):
+        """A cudaStream_t handle to run on; None / 0 = the context's own (non-blocking) stream.  Note that torch's
+        default stream has handle 0: to share a stream with torch, use an explicit torch.cuda.Stream."""
         self._check(self._lib.msgpu_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
     # ---- construction

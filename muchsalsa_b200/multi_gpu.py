@@ -70,13 +70,30 @@ def gather_blobs(mine: torch.Tensor, world: int, dist) -> torch.Tensor:
 class ShardedBuilder:
     """The N-GPU construction step of one rank.  `dist` is torch.distributed (initialised) or None for world == 1."""
 
-    def __init__(self, builder, rank: int, world: int, dist, device):
+    def __init__(self, builder, rank: int, world: int, dist, device, stream=None):
+        """`stream`: the torch CUDA stream everything of this builder runs on — the library's kernels, the tensors
+        handed to the collectives and (through torch's stream bookkeeping) NCCL's reads and writes of them.  It must
+        not be the default stream: its handle is 0, which the C ABI reads as "the context's own stream", and work on
+        two unrelated streams is not ordered.  None = a new stream."""
         self.gb, self.rank, self.world, self.dist, self.device = builder, rank, world, dist, device
         self.exchange_bytes = 0   # bytes this rank received from the others in the last step
-        self.exchange_ms = None   # device time of the blob all-gather of the last step (CUDA events), if on a GPU
         self._keep = None
+        self.stream = None
+        if torch.device(device).type == "cuda":
+            self.stream = stream if stream is not None else torch.cuda.Stream(device)
+            if self.stream.cuda_stream == 0:
+                raise ValueError("ShardedBuilder needs a non-default CUDA stream")
+            builder.set_stream(self.stream.cuda_stream)
+
+    def _on_stream(self):
+        import contextlib
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
 
     def _exchange(self):
+        with self._on_stream():
+            return self._exchange_on_stream()
+
+    def _exchange_on_stream(self):
         gb, world = self.gb, self.world
         h = gb.shard_header()
         heads = gather_headers(header_to_tensor(h, self.device), world, self.dist) if world > 1 else \
