@@ -258,6 +258,12 @@ def run_ours(args):
             "ms": round(pm_ms, 3), "bytes_written_once": int(strict),
             "achieved_gbs": round(strict / pm_ms / 1e6, 1), "frac": round(strict / pm_ms / 1e6 / peak, 4),
             "survey_8d_bytes": int(survey), "survey_8d_frac": round(survey / pm_ms / 1e6 / peak, 4)}
+        # the whole construction step against SURVEY.md §8(d)'s B_tot (the figure BASELINE.md asks for)
+        step_ms = 1e3 * t_dev / args.steps
+        roof["construction_step"] = {"ms": round(step_ms, 3), "survey_8d_bytes": int(survey),
+                                     "survey_8d_frac": round(survey / step_ms / 1e6 / peak, 4),
+                                     "bytes_written_once": int(strict + n_bytes),
+                                     "frac": round((strict + n_bytes) / step_ms / 1e6 / peak, 4)}
 
     # ---- the reference's CPU path beside it (bounded sample, rank 0 at N = 1 only)
     cpu = cpu_baseline(args.workload) if world == 1 else None

@@ -257,15 +257,15 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *__restrict__
 // value of `second` occurs at most once per source, so C jumps by <= deg and sub-tile j = [s_j, s_j+1) holds fewer
 // than T + deg = kTileCap candidates.  Written out: for every source the row position where each sub-tile begins.
 __global__ void __launch_bounds__(256)
-    split_heavy_kernel(const uint32_t *__restrict__ tile_row, const uint32_t *__restrict__ tile_kind, uint32_t n_tiles,
-                       RowPlan plan, const uint64_t *__restrict__ slice_off, const uint32_t *__restrict__ rd_off,
+    split_heavy_kernel(const uint32_t *__restrict__ tile_row, const uint32_t *__restrict__ tile_kind, uint32_t t_begin,
+                       uint32_t n_tiles, RowPlan plan, const uint64_t *__restrict__ slice_off, const uint32_t *__restrict__ rd_off,
                        const uint32_t *__restrict__ rd_src, const PairRow *__restrict__ rows,
                        const uint32_t *__restrict__ grp_off, const uint32_t *__restrict__ p_read, uint32_t n_reads,
                        uint32_t *__restrict__ slices) {
   const unsigned l  = threadIdx.x & 31;
-  uint64_t       wi = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  uint64_t       wi = t_begin + ((uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
   const uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-  for (; wi < n_tiles; wi += nw) {
+  for (; wi < n_tiles; wi += nw) { // tiles [t_begin, n_tiles)
     const uint32_t kind = tile_kind[wi];
     if (kind == 0) continue;
     const uint32_t r = tile_row[wi], j = kind - 1, d = plan.deg[r], ns = plan.n_sub(r);
@@ -1115,18 +1115,20 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   uint32_t *rd_tmp = arena.alloc<uint32_t>(n_src), *rd_src = arena.alloc<uint32_t>(n_src);
   if (M) MSGPU_LAUNCH("scatter_sources", st, scatter_sources_kernel<<<gm, 256, 0, st>>>(p_read, rows, unitigs.grp_off, M, rd_off, cursor, rd_tmp));
   if (n_src) MSGPU_LAUNCH("order_sources", st, order_sources_kernel<<<grid_for(n_src, 256), 256, 0, st>>>(p_read, rd_off, rd_tmp, n_src, rd_src));
-  uint32_t *slices = arena.alloc<uint32_t>(n_slices);
-  if (n_slices) {
-    MSGPU_LAUNCH("split_heavy", st, split_heavy_kernel<<<grid_for(uint64_t(n_tiles) * 32, 256), 256, 0, st>>>(
-                                        tile_row, tile_kind, n_tiles, plan, slice_off, rd_off, rd_src, rows,
-                                        unitigs.grp_off, p_read, uint32_t(R), slices));
-  }
-
   // ---- this device's share: a contiguous range of tiles (tiles weigh about the same)
   if (n_parts == 0) n_parts = 1;
   const uint32_t tile_lo = uint32_t(uint64_t(n_tiles) * part / n_parts);
   const uint32_t tile_hi = uint32_t(uint64_t(n_tiles) * (part + 1) / n_parts);
   const uint32_t my_tiles = tile_hi - tile_lo;
+  // heavy rows: every sub-tile computes its START boundary; its end boundary is the start of the next sub-tile, so
+  // the range includes one tile past this device's share (a last sub-tile writes the end of its row itself)
+  uint32_t *slices = arena.alloc<uint32_t>(n_slices);
+  if (n_slices && my_tiles) {
+    const uint32_t t_end = tile_hi < n_tiles ? tile_hi + 1 : n_tiles;
+    MSGPU_LAUNCH("split_heavy", st, split_heavy_kernel<<<grid_for(uint64_t(t_end - tile_lo) * 32, 256), 256, 0, st>>>(
+                                        tile_row, tile_kind, tile_lo, t_end, plan, slice_off, rd_off, rd_src, rows,
+                                        unitigs.grp_off, p_read, uint32_t(R), slices));
+  }
   // capacity of the outputs: a tile emits at most kTileCap rows, and never more than there are pairs
   uint64_t cap = uint64_t(my_tiles) * kTileCap;
   if (cap > P) cap = P;

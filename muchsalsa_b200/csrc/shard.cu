@@ -69,13 +69,44 @@ msgpu_shard_header shard_describe(uint64_t n_lines, const ReadTable &reads, cons
   return h;
 }
 
+// all sections of the blob in ONE launch (sixteen cudaMemcpyAsync calls cost more host time than the copy itself)
+struct PackJob {
+  const void *src[16];
+  uint64_t    dst_off[16], bytes[16];
+  int         n;
+};
+
+__global__ void __launch_bounds__(256) pack_blob_kernel(PackJob job, char *__restrict__ blob) {
+  for (int k = 0; k < job.n; ++k) {
+    const char    *src = static_cast<const char *>(job.src[k]);
+    char          *dst = blob + job.dst_off[k];
+    const uint64_t nb  = job.bytes[k];
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) { // sections start 16-byte aligned in the blob
+      const uint64_t nv = nb >> 4;
+      for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += uint64_t(gridDim.x) * blockDim.x)
+        reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+      for (uint64_t i = (nv << 4) + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nb;
+           i += uint64_t(gridDim.x) * blockDim.x)
+        dst[i] = src[i];
+    } else {
+      for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nb; i += uint64_t(gridDim.x) * blockDim.x)
+        dst[i] = src[i];
+    }
+  }
+}
+
 void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable &reads, const UnitigTable &unitigs,
                   const MatchSoA &m, void *dev_blob) {
   const ShardLayout L = shard_layout(h);
   char             *b = static_cast<char *>(dev_blob);
   MSGPU_CUDA(cudaMemcpyAsync(b, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-  auto put = [&](uint64_t off, const void *src, uint64_t bytes) {
-    if (bytes) MSGPU_CUDA(cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyDeviceToDevice, st));
+  PackJob job{};
+  auto    put = [&](uint64_t off, const void *src, uint64_t bytes) {
+    if (!bytes) return;
+    job.src[job.n]     = src;
+    job.dst_off[job.n] = off;
+    job.bytes[job.n]   = bytes;
+    ++job.n;
   };
   const uint64_t R = h.n_reads, U = h.n_unitigs, M = h.n_matches;
   put(L.read_nlen, reads.nlen, R * 4);
@@ -94,6 +125,7 @@ void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable 
   put(L.m_line, m.line, M * 4);
   put(L.m_rratio, m.rratio, M * 8);
   put(L.m_flags, m.flags, M);
+  if (job.n) MSGPU_LAUNCH("pack_blob", st, pack_blob_kernel<<<grid_for(h.blob_bytes / 16 + 1, 256, 2), 256, 0, st>>>(job, b));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -309,53 +341,69 @@ template <class T> static T read_back(cudaStream_t st, const T *d) {
   return h;
 }
 
-// interning of one concatenated name table; returns the number of distinct names, fills gid[entry] and `out`
-static uint32_t merge_names(Arena &arena, cudaStream_t st, const ShardView *d_sh, uint32_t n_shards, int which,
-                            uint64_t n_entries, uint32_t *gid, NameTable &out, int32_t *&read_nlen,
-                            uint32_t *&read_line) {
+struct MergeStatus { // device-resident, read back once per merge
+  unsigned long long name_bytes[2];
+  unsigned           n_ids[2];
+  unsigned           collision, unsorted, n_matches, pad;
+};
+
+struct IdNameLen { // lengths of the first *d_n names, 0 behind them (the scan runs over the capacity)
+  const uint32_t *len;
+  const unsigned *d_n;
+  __device__ uint64_t operator()(uint64_t i) const { return i < *d_n ? uint64_t(len[i]) : 0ull; }
+};
+
+__global__ void __launch_bounds__(256)
+    gather_names_abs_n_kernel(const char *const *__restrict__ src, const uint64_t *__restrict__ dst_off,
+                              const unsigned *__restrict__ d_n, char *__restrict__ out) {
+  const uint64_t n  = *d_n;
+  uint64_t       w  = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; // one warp per name
+  uint64_t       nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  for (; w < n; w += nw) {
+    uint64_t b = dst_off[w], e = dst_off[w + 1];
+    for (uint64_t i = lane_id(); i < e - b; i += 32) out[b + i] = src[w][i];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    shard_check_grouped_kernel(const uint32_t *__restrict__ unitig, const unsigned *__restrict__ d_n,
+                               unsigned *unsorted) {
+  const uint64_t n = *d_n;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x + 1; i < n; i += uint64_t(gridDim.x) * blockDim.x)
+    if (unitig[i] < unitig[i - 1]) *unsorted = 1;
+}
+
+// interning of one concatenated name table: fills gid[entry] and `out`; every size is bounded by the entry count and
+// the name bytes of the headers, so nothing comes back to the host here (counts and the collision flag: `status`)
+static void merge_names(Arena &arena, cudaStream_t st, const ShardView *d_sh, uint32_t n_shards, int which,
+                        uint64_t n_entries, uint64_t name_bytes_bound, uint64_t seed, MergeStatus *d_status,
+                        uint32_t *gid, NameTable &out, int32_t *&read_nlen, uint32_t *&read_line) {
   const char **name_ptr = arena.alloc<const char *>(n_entries);
   uint32_t    *name_len = arena.alloc<uint32_t>(n_entries), *slot = arena.alloc<uint32_t>(n_entries);
   uint32_t    *rank = arena.alloc<uint32_t>(n_entries);
   uint8_t     *first = arena.alloc<uint8_t>(n_entries);
-  uint32_t    *d_flag = arena.alloc<uint32_t>(2);
   const int    g = grid_for(n_entries, 256);
-  EntryTable   t{};
-  uint32_t     n_ids = 0;
-  for (int attempt = 0;; ++attempt) {
-    if (attempt == 4) throw BuildError{MSGPU_ERR_INTERNAL, "name hash collisions persisted over 4 seeds"};
-    t = make_entry_table(arena, st, n_entries);
-    MSGPU_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(uint32_t), st));
-    if (n_entries) {
-      MSGPU_LAUNCH("entry_insert", st, entry_insert_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, which, n_entries, 0x243f6a8885a308d3ull * uint64_t(attempt + 1), t, name_ptr, name_len, slot));
-      MSGPU_LAUNCH("entry_verify", st, entry_verify_kernel<<<g, 256, 0, st>>>(n_entries, t, name_ptr, name_len, slot, first, d_flag));
-    }
-    exclusive_scan<uint32_t>(arena, st, LoadAs<uint8_t, uint32_t>{first}, n_entries, rank, d_flag + 1);
-    uint32_t h[2];
-    MSGPU_CUDA(cudaMemcpyAsync(h, d_flag, sizeof(h), cudaMemcpyDeviceToHost, st));
-    MSGPU_CUDA(cudaStreamSynchronize(st));
-    if (h[0]) continue;
-    n_ids = h[1];
-    break;
-  }
-  const char **id_name_ptr = arena.alloc<const char *>(n_ids);
-  uint32_t    *id_name_len = arena.alloc<uint32_t>(n_ids);
+  EntryTable   t = make_entry_table(arena, st, n_entries);
+  const char **id_name_ptr = arena.alloc<const char *>(n_entries);
+  uint32_t    *id_name_len = arena.alloc<uint32_t>(n_entries);
   if (which == 0) {
-    read_nlen = arena.alloc<int32_t>(n_ids);
-    read_line = arena.alloc<uint32_t>(n_ids);
+    read_nlen = arena.alloc<int32_t>(n_entries);
+    read_line = arena.alloc<uint32_t>(n_entries);
   }
+  if (n_entries) {
+    MSGPU_LAUNCH("entry_insert", st, entry_insert_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, which, n_entries, seed, t, name_ptr, name_len, slot));
+    MSGPU_LAUNCH("entry_verify", st, entry_verify_kernel<<<g, 256, 0, st>>>(n_entries, t, name_ptr, name_len, slot, first, &d_status->collision));
+  }
+  exclusive_scan<uint32_t>(arena, st, LoadAs<uint8_t, uint32_t>{first}, n_entries, rank, &d_status->n_ids[which]);
   if (n_entries) {
     MSGPU_LAUNCH("entry_assign", st, entry_assign_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, which, n_entries, t, slot, first, rank, name_ptr, name_len, id_name_ptr, id_name_len, read_nlen, read_line));
     MSGPU_LAUNCH("entry_gid", st, entry_gid_kernel<<<g, 256, 0, st>>>(n_entries, t, slot, gid));
   }
-  out.n        = n_ids;
-  out.name_off = arena.alloc<uint64_t>(uint64_t(n_ids) + 1);
-  uint64_t *total = arena.alloc<uint64_t>(1);
-  exclusive_scan<uint64_t>(arena, st, LoadAs<uint32_t, uint64_t>{id_name_len}, n_ids, out.name_off, total);
-  MSGPU_CUDA(cudaMemcpyAsync(out.name_off + n_ids, total, sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
-  out.n_bytes = read_back(st, total);
-  out.names   = arena.alloc<char>(out.n_bytes);
-  if (n_ids) MSGPU_LAUNCH("gather_names", st, gather_names_abs_kernel<<<grid_for(uint64_t(n_ids) * 32, 256), 256, 0, st>>>(id_name_ptr, out.name_off, n_ids, out.names));
-  return n_ids;
+  out.name_off = arena.alloc<uint64_t>(n_entries + 1);
+  exclusive_scan<uint64_t>(arena, st, IdNameLen{id_name_len, &d_status->n_ids[which]}, n_entries + 1, out.name_off,
+                           reinterpret_cast<uint64_t *>(&d_status->name_bytes[which]));
+  out.names = arena.alloc<char>(name_bytes_bound);
+  if (n_entries) MSGPU_LAUNCH("gather_names", st, gather_names_abs_n_kernel<<<grid_for(n_entries * 32, 256, 2), 256, 0, st>>>(id_name_ptr, out.name_off, &d_status->n_ids[which], out.names));
 }
 
 void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msgpu_shard_header *headers,
@@ -365,7 +413,7 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
   unitigs = UnitigTable{};
   m       = MatchSoA{};
   std::vector<ShardView> hv(n_shards);
-  uint64_t               rb = 0, ub = 0, mb = 0, lb = 0;
+  uint64_t               rb = 0, ub = 0, mb = 0, lb = 0, rbytes = 0, ubytes = 0;
   for (uint32_t s = 0; s < n_shards; ++s) {
     const msgpu_shard_header &h = headers[s];
     if (h.magic != kShardMagic || h.blob_bytes != shard_layout(h).total)
@@ -400,6 +448,8 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
     ub += h.n_unitigs;
     mb += h.n_matches;
     lb += h.n_lines;
+    rbytes += h.read_name_bytes;
+    ubytes += h.unitig_name_bytes;
   }
   if (lb >= 0xfffffff0ull || rb >= 0xfffffff0ull || mb >= 0xfffffff0ull)
     throw BuildError{MSGPU_ERR_LIMIT, "more than 2^32-16 lines, read entries or matches over all shards"};
@@ -408,27 +458,46 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
   MSGPU_CUDA(cudaMemcpyAsync(d_sh, hv.data(), n_shards * sizeof(ShardView), cudaMemcpyHostToDevice, st));
   MSGPU_CUDA(cudaStreamSynchronize(st)); // hv is pageable host memory
 
-  // ---- global ids
-  uint32_t *gid_r = arena.alloc<uint32_t>(rb), *gid_u = arena.alloc<uint32_t>(ub);
-  int32_t  *no_nlen = nullptr;
-  uint32_t *no_line = nullptr;
-  merge_names(arena, st, d_sh, n_shards, 0, rb, gid_r, reads, reads.nlen, reads.line);
-  merge_names(arena, st, d_sh, n_shards, 1, ub, gid_u, unitigs, no_nlen, no_line);
+  MergeStatus *d_status = arena.alloc<MergeStatus>(1);
+  MergeStatus  h{};
+  for (int attempt = 0;; ++attempt) {
+    if (attempt == 4) throw BuildError{MSGPU_ERR_INTERNAL, "name hash collisions persisted over 4 seeds"};
+    MSGPU_CUDA(cudaMemsetAsync(d_status, 0, sizeof(MergeStatus), st));
+    const uint64_t seed = 0x243f6a8885a308d3ull * uint64_t(attempt + 1);
 
-  // ---- records: renumber, deduplicate across chunks, group by unitig
-  MatchSoA c;
-  alloc_match_soa(arena, c, mb);
-  const int g = grid_for(mb, 256);
-  if (mb) MSGPU_LAUNCH("remap_matches", st, remap_matches_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, mb, gid_r, gid_u, c));
-  EntryTable dt   = make_entry_table(arena, st, mb);
-  uint32_t  *slot = arena.alloc<uint32_t>(mb), *pos = arena.alloc<uint32_t>(mb), *d_m = arena.alloc<uint32_t>(1);
-  if (mb) MSGPU_LAUNCH("dedup_insert", st, shard_dedup_insert_kernel<<<g, 256, 0, st>>>(c, dt, slot));
-  KeepFlag keep{c.line, slot, dt.min_entry};
-  exclusive_scan<uint32_t>(arena, st, keep, mb, pos, d_m);
-  const uint64_t M = read_back(st, d_m);
-  alloc_match_soa(arena, m, M);
-  if (mb) MSGPU_LAUNCH("compact_matches", st, shard_compact_kernel<<<g, 256, 0, st>>>(c, keep, pos, m));
-  group_by_unitig(arena, st, m, unitigs.n);
+    // ---- global ids
+    uint32_t *gid_r = arena.alloc<uint32_t>(rb), *gid_u = arena.alloc<uint32_t>(ub);
+    int32_t  *no_nlen = nullptr;
+    uint32_t *no_line = nullptr;
+    merge_names(arena, st, d_sh, n_shards, 0, rb, rbytes, seed, d_status, gid_r, reads, reads.nlen, reads.line);
+    merge_names(arena, st, d_sh, n_shards, 1, ub, ubytes, seed, d_status, gid_u, unitigs, no_nlen, no_line);
+
+    // ---- records: renumber, deduplicate across chunks (capacity = all records), group by unitig
+    MatchSoA c;
+    alloc_match_soa(arena, c, mb);
+    const int g = grid_for(mb, 256);
+    if (mb) MSGPU_LAUNCH("remap_matches", st, remap_matches_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, mb, gid_r, gid_u, c));
+    EntryTable dt   = make_entry_table(arena, st, mb);
+    uint32_t  *slot = arena.alloc<uint32_t>(mb), *pos = arena.alloc<uint32_t>(mb);
+    if (mb) MSGPU_LAUNCH("dedup_insert", st, shard_dedup_insert_kernel<<<g, 256, 0, st>>>(c, dt, slot));
+    KeepFlag keep{c.line, slot, dt.min_entry};
+    exclusive_scan<uint32_t>(arena, st, keep, mb, pos, &d_status->n_matches);
+    alloc_match_soa(arena, m, mb);
+    if (mb) {
+      MSGPU_LAUNCH("compact_matches", st, shard_compact_kernel<<<g, 256, 0, st>>>(c, keep, pos, m));
+      MSGPU_LAUNCH("check_grouped", st, shard_check_grouped_kernel<<<g, 256, 0, st>>>(m.unitig, &d_status->n_matches, &d_status->unsorted));
+    }
+    // ---- the one round trip of the merge
+    MSGPU_CUDA(cudaMemcpyAsync(&h, d_status, sizeof(h), cudaMemcpyDeviceToHost, st));
+    MSGPU_CUDA(cudaStreamSynchronize(st));
+    if (!h.collision) break;
+  }
+  reads.n         = h.n_ids[0];
+  reads.n_bytes   = h.name_bytes[0];
+  unitigs.n       = h.n_ids[1];
+  unitigs.n_bytes = h.name_bytes[1];
+  m.n             = h.n_matches;
+  group_by_unitig(arena, st, m, unitigs.n, h.unsorted ? 1 : 0);
   build_group_offsets(arena, st, m, unitigs);
 }
 

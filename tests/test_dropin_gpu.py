@@ -20,7 +20,7 @@ def ref(reference):
     return reference
 
 
-@pytest.mark.parametrize("name", ["kat8", "duplicates_ungrouped", "thresholds", "stoi_crlf_tags", "heavy_group"])
+@pytest.mark.parametrize("name", ["kat8", "duplicates_ungrouped", "thresholds", "stoi_crlf_tags", "heavy_group", "long_tags"])
 def test_reference_objects_filled_by_gpu_equal_reference(ref, name):
     paf = util.edge_case_pafs()[name]
     assert tables_equal(ref.build_gpu(paf), ref.build(paf)) == []

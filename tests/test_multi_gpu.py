@@ -41,7 +41,7 @@ def build_sharded(chunks):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 5])
-@pytest.mark.parametrize("name", ["kat8", "duplicates_ungrouped", "thresholds", "heavy_group"])
+@pytest.mark.parametrize("name", ["kat8", "duplicates_ungrouped", "thresholds", "heavy_group", "long_tags"])
 def test_sharded_edge_cases_vs_oracle(oracle, name, n):
     """Chunk boundaries fall inside unitig groups, duplicates of a (read, unitig) pair land in different chunks, a
     name's first appearance and its later ones are seen by different ranks."""

@@ -135,6 +135,18 @@ def edge_case_pafs() -> dict:
             rows.append(L(f"h{u}", ulen, a, b, "+-"[int(rng.integers(0, 2))], f"x{r}", 50000, 1000, 1000 + (b - a),
                           int((b - a) * 0.9)))
     cases["heavy_group"] = b"".join(rows) + sentinel
+    # every line carries a long cg:Z tag (minimap2 -c --eqx, pipeline.sh:175): 256 consecutive lines no longer fit the
+    # parser's shared-memory stage, so the lines are read in place; a few groups of overlapping reads
+    rng = np.random.Generator(np.random.PCG64(9))
+    rows = []
+    for u in range(40):
+        for r in rng.choice(60, int(rng.integers(2, 12)), replace=False):
+            a = int(rng.integers(0, 3000))
+            b = int(a + rng.integers(420, 5000))
+            tag = ("cg:Z:" + "".join(f"{int(x)}=1X" for x in rng.integers(1, 99, 90))).encode()
+            rows.append(L(f"c{u}", 9000, a, b, "+-"[int(rng.integers(0, 2))], f"y{r}", 40000, 50, 50 + (b - a),
+                          int((b - a) * 0.95), extra=("tp:A:P", tag.decode())))
+    cases["long_tags"] = b"".join(rows) + sentinel
     return cases
 
 
