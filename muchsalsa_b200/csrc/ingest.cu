@@ -16,6 +16,7 @@
 // Names are hashed (64 bit) for the open-addressing tables, and every line then compares its name bytes with the
 // representative of its slot; a mismatch (a 64-bit collision) restarts interning with another hash seed.
 #include <algorithm>
+#include <cstdlib>
 
 #include "../../include/msgpu.h"
 #include "internal.h"
@@ -169,6 +170,7 @@ __device__ __forceinline__ bool dev_stoi(const char *s, uint32_t n, int *out) {
 // 64-bit name hash from two independent 32-bit multiplicative streams (a 64-bit multiply per byte costs four times
 // as much on this machine); 0 is the empty-slot marker of the tables, so the low bit is forced
 __device__ __forceinline__ uint64_t name_hash(const char *s, uint32_t n, uint64_t seed) {
+  if (seed == 0) return 1ull; // test hook (MSGPU_TEST_FORCE_COLLISION): every name collides, the verify pass must notice
   uint32_t h1 = 2166136261u ^ uint32_t(seed), h2 = 0x9e3779b9u ^ uint32_t(seed >> 32);
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t c = (unsigned char)s[i];
@@ -649,7 +651,10 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     MSGPU_CUDA(cudaMemcpyAsync(d_status, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     MSGPU_CUDA(cudaMemsetAsync(f.flags, 0, cap, st)); // the scans below run over the capacity
     MSGPU_LAUNCH("line_index_finish", st, line_index_finish_kernel<<<1, 1, 0, st>>>(d_paf, n_bytes, d_n_nl, cap, drop_last_line ? 1 : 0, line_start, d_status));
-    MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, 0x243f6a8885a308d3ull * uint64_t(attempt + 1), f, d_status));
+    // seeds are odd multiples of a constant, never 0; the test hook makes the first attempt collide on purpose
+    const bool     force = attempt == 0 && std::getenv("MSGPU_TEST_FORCE_COLLISION") != nullptr;
+    const uint64_t seed  = force ? 0ull : 0x243f6a8885a308d3ull * uint64_t(attempt + 1);
+    MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
 
     // ---- K3 interning
     InternTable rt = make_table(arena, st, cap_acc + cap_acc / 2), ut = make_table(arena, st, cap_acc + cap_acc / 2);

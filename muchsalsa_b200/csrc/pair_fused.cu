@@ -750,16 +750,15 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
         }
         uint32_t ia = a0 + lo, ib = a1 + (k - lo);
         W        xa = ia < a1 ? in[ia] : W(0), xb = ib < b1 ? in[ib] : W(0);
-        for (uint32_t p = pos; p < seg_end; ++p) {
+        for (uint32_t p = pos; p < seg_end; ++p) { // branch-free step: one select, one reload of the side that moved
           const bool take_a = ib >= b1 || (ia < a1 && xa < xb);
           out[p]            = take_a ? xa : xb;
-          if (take_a) {
-            ++ia;
-            xa = ia < a1 ? in[ia] : W(0);
-          } else {
-            ++ib;
-            xb = ib < b1 ? in[ib] : W(0);
-          }
+          ia += take_a ? 1u : 0u;
+          ib += take_a ? 0u : 1u;
+          const uint32_t nx = take_a ? ia : ib, lim = take_a ? a1 : b1;
+          const W        v  = nx < lim ? in[nx] : W(0);
+          xa                = take_a ? v : xa;
+          xb                = take_a ? xb : v;
         }
       }
       pos = seg_end;
@@ -773,32 +772,41 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
 
   // ---- run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the key
   // of its pair) but is skipped; the head of a run is its first surviving candidate.
+  W        xs[kItems];                             // this lane's sorted words, kept for the record pass
   uint32_t vmask = 0, hmask = 0, n_v = 0, n_h = 0; // bit `it`: this lane's item of iteration `it` survives / is a head
-  for (uint32_t it = 0; it < per; ++it) {
-    const uint32_t k = wbase + it * 32 + l;
-    bool           ok = false, head = false;
-    if (k < n_ent) {
-      const W x = sorted[k];
-      ok        = !(s.ent_src[uint32_t(x) & (kTileCap - 1)] & kDropped);
-      if (ok) {
-        head = true;
-        const W        key       = x >> kIdxBits;
-        const uint32_t row_start = s.src.base[s.src.row_first[s.ent_src[k] & (kSrcCap - 1)]];
-        for (uint32_t p = k; p > row_start;) {
-          --p;
-          const W y = sorted[p];
-          if ((y >> kIdxBits) != key) break;
-          if (!(s.ent_src[uint32_t(y) & (kTileCap - 1)] & kDropped)) {
-            head = false;
-            break;
+#pragma unroll
+  for (int it = 0; it < kItems; ++it) {
+    xs[it] = W(0);
+    if (uint32_t(it) < per) {
+      const uint32_t k = wbase + it * 32 + l;
+      bool           ok = false, head = false;
+      if (k < n_ent) {
+        const W x = sorted[k];
+        xs[it]    = x;
+        ok        = !(s.ent_src[uint32_t(x) & (kTileCap - 1)] & kDropped);
+        if (ok) {
+          head = true;
+          const W key = x >> kIdxBits;
+          // almost always the predecessor has another key: then this is a head and nothing else is looked at
+          if (k > 0 && (sorted[k - 1] >> kIdxBits) == key) {
+            const uint32_t row_start = s.src.base[s.src.row_first[s.ent_src[k] & (kSrcCap - 1)]];
+            for (uint32_t p = k; p > row_start;) {
+              --p;
+              const W y = sorted[p];
+              if ((y >> kIdxBits) != key) break;
+              if (!(s.ent_src[uint32_t(y) & (kTileCap - 1)] & kDropped)) {
+                head = false;
+                break;
+              }
+            }
           }
         }
       }
+      vmask |= (ok ? 1u : 0u) << it;
+      hmask |= (head ? 1u : 0u) << it;
+      n_v += __popc(__ballot_sync(0xffffffffu, ok));
+      n_h += __popc(__ballot_sync(0xffffffffu, head));
     }
-    vmask |= (ok ? 1u : 0u) << it;
-    hmask |= (head ? 1u : 0u) << it;
-    n_v += __popc(__ballot_sync(0xffffffffu, ok));
-    n_h += __popc(__ballot_sync(0xffffffffu, head));
   }
   if (l == 0) s.warp_tot[w] = n_v | (n_h << 16);
   __syncthreads();
@@ -814,23 +822,25 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
   // ---- the tile's records, compacted, in final order
   uint2   *rec = a.records + uint64_t(st_idx) * kTileCap;
   uint32_t pv = before & 0xffffu, ph = before >> 16;
-  for (uint32_t it = 0; it < per; ++it) {
-    const uint32_t k  = wbase + it * 32 + l;
-    const bool     ok = (vmask >> it) & 1u, head = (hmask >> it) & 1u;
-    const unsigned bv = __ballot_sync(0xffffffffu, ok), bh = __ballot_sync(0xffffffffu, head);
-    const unsigned lt = (1u << l) - 1u;
-    if (ok) {
-      const uint32_t e  = uint32_t(sorted[k]) & (kTileCap - 1);
-      const uint32_t j  = s.ent_src[e] & (kSrcCap - 1);
-      const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
-      rec[pv + __popc(bv & lt)] = make_uint2(ib, j | (head ? 1u << kSrcBits : 0u) | ((ph + __popc(bh & lt)) << (kSrcBits + 1)));
+#pragma unroll
+  for (int it = 0; it < kItems; ++it) {
+    if (uint32_t(it) < per) {
+      const bool     ok = (vmask >> it) & 1u, head = (hmask >> it) & 1u;
+      const unsigned bv = __ballot_sync(0xffffffffu, ok), bh = __ballot_sync(0xffffffffu, head);
+      const unsigned lt = (1u << l) - 1u;
+      if (ok) {
+        const uint32_t e  = uint32_t(xs[it]) & (kTileCap - 1);
+        const uint32_t j  = s.ent_src[e] & (kSrcCap - 1);
+        const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
+        rec[pv + __popc(bv & lt)] = make_uint2(ib, j | (head ? 1u << kSrcBits : 0u) | ((ph + __popc(bh & lt)) << (kSrcBits + 1)));
+      }
+      pv += __popc(bv);
+      ph += __popc(bh);
     }
-    pv += __popc(bv);
-    ph += __popc(bh);
   }
 }
 
-__global__ void __launch_bounds__(kFusedBlock, 2) pair_tiles_merge_kernel(TileArgs a) {
+__global__ void __launch_bounds__(kFusedBlock, 3) pair_tiles_merge_kernel(TileArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MergeShared   &s = *reinterpret_cast<MergeShared *>(smem_raw);
   const unsigned t = threadIdx.x, l = t & 31;

@@ -117,3 +117,32 @@ def test_sort_based_variant_agrees_with_fused(builder, monkeypatch):
     srt = util.gpu_to_tables(builder.build_from_buffer(paf).result())
     monkeypatch.delenv("MSGPU_VARIANT")
     assert tables_equal(fused, srt) == []
+
+
+def test_hash_collision_restarts_interning(builder, oracle, monkeypatch):
+    """Names are interned through 64-bit hashes that every line verifies against its slot's representative; a
+    collision restarts the interning with another seed.  The test hook makes the first attempt collide everywhere."""
+    paf = synth.generate_paf("small")
+    monkeypatch.setenv("MSGPU_TEST_FORCE_COLLISION", "1")
+    got = util.gpu_to_tables(builder.build_from_buffer(paf).result())
+    monkeypatch.delenv("MSGPU_TEST_FORCE_COLLISION")
+    assert tables_equal(got, oracle.build(paf)) == []
+
+
+def test_read_with_too_many_partnered_unitigs_is_a_limit_error(builder):
+    """A read that shares more than 512 unitigs with other reads exceeds what one pairing tile stages: the build must
+    fail with MSGPU_ERR_LIMIT (documented in DESIGN.md), not crash or return something wrong."""
+    from muchsalsa_b200.construct import MsGpuError
+    L = util.paf_line
+    rows = []
+    for u in range(600):
+        rows.append(L(f"u{u}", 5000, 0, 3000, "+", "hub", 4000000, u * 3000, u * 3000 + 3000, 2900))
+        rows.append(L(f"u{u}", 5000, 500, 3500, "+", f"p{u}", 9000, 0, 3000, 2900))
+    paf = b"".join(rows) + L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
+    with pytest.raises(MsGpuError) as e:
+        builder.build_from_buffer(paf)
+    assert e.value.status == 6
+    # 500 shared unitigs are fine
+    paf = b"".join(rows[:1000]) + L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
+    c = builder.build_from_buffer(paf).counts()
+    assert c["n_edges"] == 500 and c["n_edge_matches"] == 500
