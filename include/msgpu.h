@@ -171,6 +171,36 @@ int msgpu_result_device(const msgpu_ctx *ctx, msgpu_tables *out);
 /* Copies the result to pinned host memory (once per build; later calls return the same pointers). */
 int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out);
 
+/* ---- chaining + overlaps: the stage that consumes the construction (optional; the tables stay in HBM for it) --------
+ * msgpu_chain_overlaps  replaces, for every edge of the last build, the job chainingAndOverlaps (src/main.cpp:170-178,
+ *                       328-414) = getMaxPairwisePaths (mpp.cpp:145-305, checkCompatibility mpp.cpp:38-142) +
+ *                       getOverlap (ol.cpp:53-101, getOverhangs ol.cpp:31-50): the shadow flag of the edge
+ *                       (Edge::setShadow) and its EdgeOrder list (Edge::appendOrder, Edge.h:49-60) — start / end vertex,
+ *                       leftOffset / rightOffset, containment, integer score, unitig ids of the path, direction, primary.
+ *                       wiggle_room = Application::getWiggleRoom() (default 300, Application.h:132).
+ * Layout: the orders of edge e are edge_n_orders[e] consecutive slots starting at slot edge_em_begin[e] (an edge has
+ * at most as many orders as edge matches), in the order the reference appends them (minus paths, then plus paths).
+ * The unitig ids of the orders of edge e are concatenated, order after order, in ord_ids[edge_em_begin[e] ...];
+ * ord_n_ids[slot] is the path length of the order in `slot`.  baseVertex is always the edge's first vertex.
+ * ord_flags: bit0 startVertex is the edge's first vertex (else the second), bit1 isContained, bit2 direction,
+ * bit3 isPrimary.  Unused slots are zero. */
+typedef struct msgpu_orders {
+  uint64_t        n_edges, n_slots; /* n_slots = n_edge_matches */
+  const uint8_t  *edge_shadow;
+  const uint32_t *edge_n_orders;
+  const double   *ord_left, *ord_right;
+  const uint64_t *ord_score;
+  const uint32_t *ord_n_ids;
+  const uint8_t  *ord_flags;
+  const uint32_t *ord_ids;
+} msgpu_orders;
+
+int msgpu_chain_overlaps(msgpu_ctx *ctx, uint64_t wiggle_room);
+int msgpu_orders_device(const msgpu_ctx *ctx, msgpu_orders *out);
+int msgpu_orders_host(msgpu_ctx *ctx, msgpu_orders *out); /* pinned host copy, valid until the next build / chain */
+/* device time of the last msgpu_chain_overlaps, milliseconds */
+int msgpu_chain_ms(const msgpu_ctx *ctx, float *out);
+
 /* Device time of the stages of the last build, milliseconds (CUDA events on the context's stream). */
 typedef struct msgpu_timings {
   float h2d_ms, ingest_ms, pair_ms, merge_ms, d2h_ms, total_ms;

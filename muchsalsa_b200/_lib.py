@@ -49,6 +49,12 @@ class ShardHeader(C.Structure):
                                           "unitig_name_bytes", "blob_bytes")]
 
 
+class Orders(C.Structure):
+    _fields_ = [("n_edges", C.c_uint64), ("n_slots", C.c_uint64), ("edge_shadow", u8p), ("edge_n_orders", u32p),
+                ("ord_left", f64p), ("ord_right", f64p), ("ord_score", u64p), ("ord_n_ids", u32p), ("ord_flags", u8p),
+                ("ord_ids", u32p)]
+
+
 class SeqReq(C.Structure):
     _fields_ = [("which", C.c_uint32), ("id", C.c_uint32), ("left", C.c_int32), ("right", C.c_int32),
                 ("direction", C.c_uint32)]
@@ -74,6 +80,10 @@ SIGNATURES = {
     "msgpu_result_counts": (C.c_int, [C.c_void_p, C.POINTER(Counts)]),
     "msgpu_result_device": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),
     "msgpu_result_host": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),
+    "msgpu_chain_overlaps": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "msgpu_orders_device": (C.c_int, [C.c_void_p, C.POINTER(Orders)]),
+    "msgpu_orders_host": (C.c_int, [C.c_void_p, C.POINTER(Orders)]),
+    "msgpu_chain_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "msgpu_result_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "msgpu_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "msgpu_profile_read": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -205,6 +205,49 @@ class GraphBuilder:
             matches=m, edge_first=_np(t.edge_first, E, np.uint32), edge_second=_np(t.edge_second, E, np.uint32),
             edge_em_begin=_np(t.edge_em_begin, E + 1, np.uint64), edge_matches=em, timings=self.timings())
 
+    # ---- chaining + overlaps (the stage after construction)
+    def chain_overlaps(self, wiggle_room: int = 300):
+        """chainingAndOverlaps for every edge of the last build (src/main.cpp:328-414)."""
+        self._check(self._lib.msgpu_chain_overlaps(self._h, wiggle_room))
+        return self
+
+    def chain_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.msgpu_chain_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def orders(self) -> dict:
+        """Host copy of the shadow flags and EdgeOrder rows in canonical (compacted) form: edges in table order,
+        orders in the order the reference appends them."""
+        o = _lib.Orders()
+        self._check(self._lib.msgpu_orders_host(self._h, C.byref(o)))
+        E, S = int(o.n_edges), int(o.n_slots)
+        t = self.host_tables()
+        begin = _np(t.edge_em_begin, E + 1, np.uint64).astype(np.int64)
+        n_ord = _np(o.edge_n_orders, E, np.uint32).astype(np.int64)
+        order_begin = np.zeros(E + 1, np.int64)
+        np.cumsum(n_ord, out=order_begin[1:])
+        # slot of every order: edge_em_begin[e] + i
+        edge_of = np.repeat(np.arange(E), n_ord)
+        slot = begin[edge_of] + (np.arange(int(order_begin[-1])) - order_begin[edge_of])
+        flags = _np(o.ord_flags, S, np.uint8)[slot]
+        n_ids = _np(o.ord_n_ids, S, np.uint32)[slot].astype(np.int64)
+        ids_begin = np.zeros(slot.size + 1, np.int64)
+        np.cumsum(n_ids, out=ids_begin[1:])
+        # ids of edge e: ord_ids[edge_em_begin[e] : + sum of its orders' lengths]
+        per_edge = np.zeros(E, np.int64)
+        np.add.at(per_edge, edge_of, n_ids)
+        id_edge = np.repeat(np.arange(E), per_edge)
+        id_first = np.zeros(E + 1, np.int64)
+        np.cumsum(per_edge, out=id_first[1:])
+        id_slot = begin[id_edge] + (np.arange(int(id_first[-1])) - id_first[id_edge])
+        return dict(edge_shadow=_np(o.edge_shadow, E, np.uint8), edge_order_begin=order_begin.astype(np.uint64),
+                    start_is_first=(flags & 1).astype(np.uint8), contained=((flags >> 1) & 1).astype(np.uint8),
+                    direction=((flags >> 2) & 1).astype(np.uint8), primary=((flags >> 3) & 1).astype(np.uint8),
+                    left=_np(o.ord_left, S, np.float64)[slot], right=_np(o.ord_right, S, np.float64)[slot],
+                    score=_np(o.ord_score, S, np.uint64)[slot], ids_begin=ids_begin.astype(np.uint64),
+                    ids=_np(o.ord_ids, S, np.uint32)[id_slot])
+
     # ---- sequences
     def seq_load(self, unitigs_path, nanopore_path):
         self._check(self._lib.msgpu_seq_load(self._h, os.fspath(unitigs_path).encode(),

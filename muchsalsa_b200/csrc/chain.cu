@@ -1,0 +1,530 @@
+// chain.cu — the stage that consumes the edge / edge-match CSR while it is still in HBM: per edge, chain its edge
+// matches into maximal compatible paths and derive the overlap geometry.
+//
+// Replaces, per edge, the job body chainingAndOverlaps (src/main.cpp:328-414) and what it calls:
+//   getMaxPairwisePaths   libms/src/kernel/mpp.cpp:145-305   (checkCompatibility: mpp.cpp:38-142)
+//   getOverlap            libms/src/kernel/ol.cpp:53-101     (getOverhangs: ol.cpp:31-50)
+// and yields what it leaves on the Edge: the shadow flag (Edge.h:241) and the EdgeOrder list (Edge.h:49-60,257-259):
+// start / end vertex, leftOffset / rightOffset (the "relative shifts"), containment, the integer score, the unitig ids
+// of the path, direction and primary flag.
+//
+// One thread per edge (edges are independent; most hold 1-4 edge matches, the dynamic programme is O(n^2) in the edge
+// matches of one direction).  All arithmetic is the reference's, in IEEE double with the same operation order
+// (explicit _rn intrinsics; the library is built with --fmad=false), so offsets and scores are bit-identical.
+//
+// What the reference reads through MatchMap lookups is read here from the tables of the construction:
+//   getEdgeMatch(edge, unitig)     -> the edge's rows of the edge-match table (CSR)
+//   getVertexMatch(read, unitig)   -> binary search for `read` in the unitig's group of the pairing index (groups are
+//                                     ordered by read id), then the public match row through PairRow::orig
+//   getVertexMatches(read)         -> a per-read list of match rows ordered by (nanoporeRange, unitig), built here
+#include <string>
+
+#include "../../include/msgpu.h"
+#include "internal.h"
+#include "scan.cuh"
+
+namespace msgpu {
+
+constexpr int kChainMax = 96; // edge matches of ONE direction on one edge that the per-thread programme holds
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-read match lists ordered by (nanoporeRange.first, nanoporeRange.second, unitig)   [mpp.cpp:253-273]
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    read_degree_kernel(const uint32_t *__restrict__ read, uint64_t n, uint32_t *__restrict__ deg) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
+    atomicAdd(&deg[read[i]], 1u);
+}
+
+__global__ void __launch_bounds__(256)
+    read_scatter_kernel(const uint32_t *__restrict__ read, uint64_t n, const uint32_t *__restrict__ off,
+                        uint32_t *__restrict__ cursor, uint32_t *__restrict__ tmp) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    uint32_t r                             = read[i];
+    tmp[off[r] + atomicAdd(&cursor[r], 1u)] = uint32_t(i);
+  }
+}
+
+__device__ __forceinline__ bool nano_less(const MatchSoA &m, uint32_t a, uint32_t b) { // tuple<pair<int,int>, id> order
+  if (m.nr0[a] != m.nr0[b]) return m.nr0[a] < m.nr0[b];
+  if (m.nr1[a] != m.nr1[b]) return m.nr1[a] < m.nr1[b];
+  return m.unitig[a] < m.unitig[b];
+}
+
+__global__ void __launch_bounds__(256)
+    read_order_kernel(MatchSoA m, const uint32_t *__restrict__ off, const uint32_t *__restrict__ tmp,
+                      uint32_t *__restrict__ list) {
+  for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < m.n; x += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t me = tmp[x], r = m.read[me], lo = off[r], hi = off[r + 1];
+    uint32_t       rank = 0;
+    for (uint32_t p = lo; p < hi; ++p) rank += nano_less(m, tmp[p], me) ? 1u : 0u;
+    list[lo + rank] = me; // (unitig ids are unique inside a read, so the order is total)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the per-edge programme
+// ---------------------------------------------------------------------------------------------------------------------
+struct ChainArgs {
+  MatchSoA        m;
+  const int32_t  *read_nlen;
+  const uint32_t *grp_off;
+  const PairRow  *rows;
+  const uint32_t *p_read;
+  const uint32_t *rm_off, *rm_list; // per-read ordered match lists
+  EdgeTables      e;
+  uint64_t        wiggle;
+  OrderTables     out;
+  unsigned int   *too_long;
+};
+
+struct Vm { // the fields of one VertexMatch the stage reads
+  int    nr0, nr1, ir0, ir1;
+  double rratio;
+  bool   dir;
+};
+
+__device__ __forceinline__ uint32_t find_match_row(const ChainArgs &a, uint32_t unitig, uint32_t read) {
+  uint32_t lo = a.grp_off[unitig], hi = a.grp_off[unitig + 1];
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a.p_read[mid] < read) lo = mid + 1; else hi = mid;
+  }
+  return a.rows[lo].orig;
+}
+
+__device__ __forceinline__ Vm load_vm(const ChainArgs &a, uint32_t row) {
+  Vm v;
+  v.nr0    = a.m.nr0[row];
+  v.nr1    = a.m.nr1[row];
+  v.ir0    = a.m.ir0[row];
+  v.ir1    = a.m.ir1[row];
+  v.rratio = a.m.rratio[row];
+  v.dir    = (a.m.flags[row] & 1) != 0;
+  return v;
+}
+
+// corrected nanopore interval of a vertex match under an edge match (mpp.cpp:50-69)
+__device__ __forceinline__ void corrected_nano(const Vm &v, int ov0, int ov1, double *c0, double *c1) {
+  double ncl = __ddiv_rn(double(ov0 - v.ir0), v.rratio);
+  double ncr = __ddiv_rn(double(v.ir1 - ov1), v.rratio);
+  if (!v.dir) {
+    double t = ncl;
+    ncl      = ncr;
+    ncr      = t;
+  }
+  *c0 = __dadd_rn(double(v.nr0), ncl);
+  *c1 = __dsub_rn(double(v.nr1), ncr);
+}
+
+// nanoCheck of checkCompatibility (mpp.cpp:40-113) for one vertex; returns the `abort` flag
+__device__ __forceinline__ bool nano_check(double a0, double a1, double b0, double b1, int ra0, int ra1, int rb0,
+                                           int rb1, int *orientation, double *diff) {
+  *orientation = 0;
+  *diff        = 0.0;
+  if (a0 <= b1 && b0 <= a1) {
+    if (a0 < b0 && a1 < b1) {
+      *orientation = 2;
+      *diff        = __dadd_rn(__dsub_rn(a1, b0), 1.0);
+    }
+    if (a0 > b0 && a1 > b1) {
+      *orientation = -2;
+      *diff        = __dadd_rn(__dsub_rn(b1, a0), 1.0);
+    }
+  } else if (a0 < b0) {
+    *orientation = 1;
+    *diff        = __dadd_rn(__dsub_rn(b0, a1), 1.0);
+  } else {
+    *orientation = -1;
+    *diff        = __dadd_rn(__dsub_rn(a0, b1), 1.0);
+  }
+  if (ra0 <= rb1 && rb0 <= ra1) {
+    int uco = 0;
+    if (ra0 < rb0 && ra1 < rb1) uco = 2;
+    if (ra0 > rb0 && ra1 > rb1) uco = -2;
+    if ((*orientation < 0 && uco >= 0) || (*orientation > 0 && uco <= 0)) return true;
+  }
+  return false;
+}
+
+// double -> std::size_t as the reference's build does it (path_t's second member, mpp.cpp:34,217,238).  Out of range
+// the conversion is undefined behaviour in C++; x86-64 code (cvttsd2si on d, or on d - 2^63 with the top bit flipped)
+// yields 0 for d >= 2^64 and 2^63 for NaN, where CUDA's cast saturates — only reachable with absurd inputs (a
+// negative match count widened to size_t), but the tables are compared bit for bit.
+__device__ __forceinline__ unsigned long long double_to_size_t(double d) {
+  const double two63 = 9223372036854775808.0;
+  if (d < two63) return d != d ? 0x8000000000000000ull : (unsigned long long)(long long)d;
+  const double t = d - two63;
+  if (t < two63) return (unsigned long long)(long long)t ^ 0x8000000000000000ull;
+  return 0ull;
+}
+
+struct EmState { // per edge match of the direction being chained
+  double c1a, c1b, c2a, c2b; // corrected nanopore intervals on the first / second vertex
+  int    r1a, r1b, r2a, r2b; // nanoporeRange on the first / second vertex
+  double score;
+  uint32_t unitig, row1, row2, k; // k: row of the edge match
+  bool   prim;
+};
+
+struct PathRes { // one entry of getMaxPairwisePaths' result
+  int    tail;   // population entry whose path it is
+  double score;
+  bool   prim;
+};
+
+// getOverhangs (ol.cpp:31-50)
+__device__ __forceinline__ void overhangs(const ChainArgs &a, uint32_t vertex, uint32_t row, int ov0, int ov1,
+                                          double *left, double *right) {
+  const Vm v   = load_vm(a, row);
+  double   ncl = __ddiv_rn(double(ov0 - v.ir0), v.rratio);
+  double   ncr = __ddiv_rn(double(v.ir1 - ov1), v.rratio);
+  if (!v.dir) {
+    double t = ncl;
+    ncl      = ncr;
+    ncr      = t;
+  }
+  *left  = __dadd_rn(double(v.nr0), ncl);
+  *right = __dadd_rn(double(a.read_nlen[vertex] - v.nr1), ncr);
+}
+
+__global__ void __launch_bounds__(128) chain_edges_kernel(ChainArgs a) {
+  const MatchSoA &m = a.m;
+  for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < a.e.n_edges;
+       e += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t v1 = a.e.first[e], v2 = a.e.second[e];
+    const uint64_t k0 = a.e.em_begin[e], k1 = a.e.em_begin[e + 1];
+
+    // results of the two directions: [0] minus (direction false), [1] plus; main.cpp:352-353
+    PathRes  res[2][kChainMax];
+    int      n_res[2] = {0, 0};
+    EmState  st[kChainMax];
+    double   pop[kChainMax];
+    int      pred[kChainMax];
+    // path members per (direction, population entry) are re-derived by walking `pred`; after the first direction is
+    // done its paths are frozen as lists of edge-match rows
+    uint32_t path_rows[2][kChainMax]; // concatenated paths of the results of a direction, in result order
+    int      path_off[2][kChainMax + 1];
+    bool     overflow = false;
+
+    for (int d = 0; d < 2; ++d) {
+      const bool direction = d == 1;
+      // ---- the edge matches of this direction, ordered by (nanoporeRange of the first vertex, unitig): vStart
+      int n = 0;
+      for (uint64_t k = k0; k < k1; ++k) {
+        if (((a.e.em_flags[k] & 1) != 0) != direction) continue;
+        if (n == kChainMax) {
+          overflow = true;
+          break;
+        }
+        EmState s;
+        s.k      = uint32_t(k - k0);
+        s.unitig = a.e.em_unitig[k];
+        s.row1   = find_match_row(a, s.unitig, v1);
+        s.row2   = find_match_row(a, s.unitig, v2);
+        s.score  = a.e.em_score[k];
+        s.prim   = (a.e.em_flags[k] & 2) != 0;
+        const Vm  w1 = load_vm(a, s.row1), w2 = load_vm(a, s.row2);
+        const int ov0 = a.e.em_ov0[k], ov1 = a.e.em_ov1[k];
+        corrected_nano(w1, ov0, ov1, &s.c1a, &s.c1b);
+        corrected_nano(w2, ov0, ov1, &s.c2a, &s.c2b);
+        s.r1a = w1.nr0;
+        s.r1b = w1.nr1;
+        s.r2a = w2.nr0;
+        s.r2b = w2.nr1;
+        // insertion by (r1a, r1b, unitig): std::sort of tuple<pair<int,int>, unsigned> (mpp.cpp:172)
+        int p = n;
+        while (p > 0) {
+          const EmState &q = st[p - 1];
+          const bool     less = s.r1a != q.r1a ? s.r1a < q.r1a : (s.r1b != q.r1b ? s.r1b < q.r1b : s.unitig < q.unitig);
+          if (!less) break;
+          st[p] = q;
+          --p;
+        }
+        st[p] = s;
+        ++n;
+      }
+      path_off[d][0] = 0;
+      if (overflow) break;
+      if (n == 0) continue; // mpp.cpp:151-153
+
+      // ---- the dynamic programme (mpp.cpp:177-199)
+      for (int i = 0; i < n; ++i) {
+        pop[i]  = st[i].score;
+        pred[i] = -1;
+      }
+      for (int k = 0; k + 1 < n; ++k) {
+        for (int l = k + 1; l < n; ++l) {
+          const double score = __dadd_rn(pop[k], st[l].score);
+          if (!(score > pop[l])) continue; // evaluated second in the reference; it has no side effects
+          // checkCompatibility(vStart[k], vStart[l]) — mpp.cpp:38-142
+          int    o1, o2;
+          double d1, d2;
+          bool   abort = nano_check(st[k].c1a, st[k].c1b, st[l].c1a, st[l].c1b, st[k].r1a, st[k].r1b, st[l].r1a,
+                                    st[l].r1b, &o1, &d1);
+          abort |= nano_check(st[k].c2a, st[k].c2b, st[l].c2a, st[l].c2b, st[k].r2a, st[k].r2b, st[l].r2a, st[l].r2b,
+                              &o2, &d2);
+          if (abort) continue;
+          if (!direction) o2 = -o2; // exchange_if(orientation2, -orientation2, !edgeMatch1->direction)
+          bool matching = false;
+          if (o1 == o2 && o1 != 0) {
+            const double mx = d1 > d2 ? d1 : d2, mn = d1 < d2 ? d1 : d2; // std::max / std::min
+            const double df = __dsub_rn(mx, mn);
+            matching = (df <= double(a.wiggle)) || (__ddiv_rn(__dmul_rn(df, 100.0), mx) <= 15.0);
+          } else if ((o1 < 0 && o2 < 0) || (o1 > 0 && o2 > 0)) {
+            matching = __dadd_rn(d1, d2) <= double(a.wiggle);
+          }
+          if (matching) {
+            pop[l]  = score;
+            pred[l] = k;
+          }
+        }
+      }
+
+      // ---- best path (mpp.cpp:201-217), then the disjoint runners-up above 75 % (mpp.cpp:219-243)
+      double max_val = 0.0;
+      int    max_it  = 0;
+      for (int i = 0; i < n; ++i)
+        if (pop[i] > max_val) {
+          max_it  = i;
+          max_val = pop[i];
+        }
+      unsigned long long used[2] = {0ull, 0ull}; // population entries on any accepted path (kChainMax <= 128)
+      int                nr = 0;
+      {
+        bool prim = false;
+        int  len  = 0;
+        for (int i = max_it; i >= 0; i = pred[i]) {
+          prim |= st[i].prim;
+          used[i >> 6] |= 1ull << (i & 63);
+          ++len;
+        }
+        res[d][nr++] = PathRes{max_it, max_val, prim || len > 2};
+      }
+      const double threshold = __dmul_rn(max_val, 0.75);
+      for (int j = 0; j < n; ++j) {
+        if (!(pop[j] > threshold)) continue;
+        bool disjoint = true, prim = false;
+        for (int i = j; i >= 0; i = pred[i]) {
+          disjoint &= !((used[i >> 6] >> (i & 63)) & 1ull);
+          prim |= st[i].prim;
+        }
+        if (!disjoint) continue;
+        for (int i = j; i >= 0; i = pred[i]) used[i >> 6] |= 1ull << (i & 63);
+        res[d][nr++] = PathRes{j, pop[j], prim};
+      }
+
+      // ---- a single primary path may still be a shadow (mpp.cpp:245-302)
+      if (nr == 1 && res[d][0].prim) {
+        const uint32_t s0 = a.rm_off[v1], s1 = a.rm_off[v1 + 1], e0 = a.rm_off[v2], e1 = a.rm_off[v2 + 1];
+        auto start_id = [&](uint32_t i) { return m.unitig[a.rm_list[s0 + i]]; };
+        auto end_id   = [&](uint32_t i) { // vIDsEnd, reversed when !direction (mpp.cpp:273)
+          return m.unitig[a.rm_list[direction ? e0 + i : e1 - 1 - i]];
+        };
+        const uint32_t ns = s1 - s0, ne = e1 - e0;
+        // the path in order: walk back from the tail, then read it forwards
+        int plen = 0;
+        for (int i = res[d][0].tail; i >= 0; i = pred[i]) ++plen;
+        uint32_t front_id = 0, back_id = st[res[d][0].tail].unitig;
+        for (int i = res[d][0].tail; i >= 0; i = pred[i]) front_id = st[i].unitig;
+        if ((start_id(0) != front_id && end_id(0) != front_id) ||
+            (start_id(ns - 1) != back_id && end_id(ne - 1) != back_id)) {
+          res[d][0].prim = false;
+        } else {
+          uint32_t i = 0, j = 0;
+          bool     is_shadow = false;
+          for (int step = 0; step < plen && !is_shadow; ++step) {
+            int node = res[d][0].tail; // the step-th element of the path
+            for (int back = plen - 1 - step; back > 0; --back) node = pred[node];
+            const uint32_t id = st[node].unitig;
+            uint32_t       ps = i;
+            while (ps < ns && start_id(ps) != id) ++ps; // std::find_if from begin + i
+            bool inter = ps > i;
+            i          = ps + 1;
+            uint32_t pe = j;
+            while (pe < ne && end_id(pe) != id) ++pe;
+            inter &= pe > j;
+            j = pe + 1;
+            is_shadow = inter;
+          }
+          if (is_shadow) res[d][0].prim = false;
+        }
+      }
+      n_res[d] = nr;
+
+      // ---- freeze the paths of this direction as edge-match rows (the state arrays are reused by the other one)
+      int w = 0;
+      for (int r = 0; r < nr; ++r) {
+        int len = 0;
+        for (int i = res[d][r].tail; i >= 0; i = pred[i]) ++len;
+        int pos = w + len;
+        for (int i = res[d][r].tail; i >= 0; i = pred[i]) path_rows[d][--pos] = st[i].k;
+        w += len;
+        path_off[d][r + 1] = w;
+        res[d][r].tail     = len; // from here on: the path length
+      }
+    }
+    if (overflow) {
+      *a.too_long            = 1;
+      a.out.edge_n_orders[e] = 0;
+      a.out.edge_shadow[e]   = 0;
+      continue;
+    }
+
+    // ---- chainingAndOverlaps' selection (main.cpp:355-397); keep[] marks the paths that survive
+    bool keep[2][kChainMax];
+    bool has_primary = false, has_multi = false;
+    for (int d = 0; d < 2; ++d)
+      for (int r = 0; r < n_res[d]; ++r) {
+        keep[d][r] = true;
+        has_primary |= res[d][r].prim;
+      }
+    if (has_primary)
+      for (int d = 0; d < 2; ++d)
+        for (int r = 0; r < n_res[d]; ++r) keep[d][r] = res[d][r].prim;
+    for (int d = 0; d < 2; ++d)
+      for (int r = 0; r < n_res[d]; ++r) has_multi |= keep[d][r] && res[d][r].tail > 1;
+    if (has_multi)
+      for (int d = 0; d < 2; ++d)
+        for (int r = 0; r < n_res[d]; ++r) keep[d][r] = keep[d][r] && res[d][r].tail > 1;
+    int  combined = 0;
+    bool first_prim = false, have_first = false;
+    for (int d = 0; d < 2; ++d) // minus first: `!minusPaths.empty() ? minusPaths[0] : plusPaths[0]`
+      for (int r = 0; r < n_res[d]; ++r)
+        if (keep[d][r]) {
+          if (!have_first) {
+            first_prim = res[d][r].prim;
+            have_first = true;
+          }
+          ++combined;
+        }
+    a.out.edge_shadow[e] = combined > 1 ? 1 : (first_prim ? 0 : 1);
+
+    // ---- getOverlap for the minus paths, then the plus paths (main.cpp:399-413, ol.cpp:53-101)
+    uint32_t n_ord = 0, id_w = 0;
+    for (int d = 0; d < 2; ++d) {
+      const bool direction = d == 1;
+      for (int r = 0; r < n_res[d]; ++r) {
+        if (!keep[d][r]) continue;
+        const int      len = res[d][r].tail;
+        const uint32_t *pr = path_rows[d] + path_off[d][r];
+        const uint64_t kf = k0 + pr[0], kl = k0 + pr[len - 1]; // first / last id of the path
+        const uint32_t uf = a.e.em_unitig[kf], ul = a.e.em_unitig[kl];
+        double lf1, rf1, ll1, rl1, lf2, rf2, ll2, rl2; // overhangs of (first id | last id) on (first | second vertex)
+        overhangs(a, v1, find_match_row(a, uf, v1), a.e.em_ov0[kf], a.e.em_ov1[kf], &lf1, &rf1);
+        overhangs(a, v1, find_match_row(a, ul, v1), a.e.em_ov0[kl], a.e.em_ov1[kl], &ll1, &rl1);
+        overhangs(a, v2, find_match_row(a, uf, v2), a.e.em_ov0[kf], a.e.em_ov1[kf], &lf2, &rf2);
+        overhangs(a, v2, find_match_row(a, ul, v2), a.e.em_ov0[kl], a.e.em_ov1[kl], &ll2, &rl2);
+        const double lo1 = lf1, ro1 = rl1;
+        double       lo2 = lf2, ro2 = rl2;
+        if (!direction) {
+          lo2 = rf2;
+          ro2 = ll2;
+        }
+        bool   have = true, start_first = true, contained = true;
+        double left = 0.0, right = 0.0;
+        if (lo1 <= lo2 && ro1 <= ro2) {
+          left  = __dsub_rn(lo2, lo1);
+          right = __dsub_rn(ro2, ro1);
+        } else if (lo1 >= lo2 && ro1 >= ro2) {
+          start_first = false;
+          left        = __dsub_rn(lo1, lo2);
+          right       = __dsub_rn(ro1, ro2);
+        } else if (lo1 > lo2 && ro1 < ro2) {
+          contained = false;
+          left      = __dsub_rn(lo1, lo2);
+          right     = __dsub_rn(ro2, ro1);
+        } else if (lo1 < lo2 && ro1 > ro2) {
+          start_first = false;
+          contained   = false;
+          left        = __dsub_rn(lo2, lo1);
+          right       = __dsub_rn(ro1, ro2);
+        } else {
+          have = false; // NaNs only: the reference's optional stays empty
+        }
+        if (!have) continue;
+        const uint64_t slot = k0 + n_ord;
+        a.out.left[slot]  = left;
+        a.out.right[slot] = right;
+        a.out.score[slot] = double_to_size_t(res[d][r].score);
+        a.out.n_ids[slot] = uint32_t(len);
+        a.out.flags[slot] = uint8_t((start_first ? 1 : 0) | (contained ? 2 : 0) | (direction ? 4 : 0) |
+                                    (res[d][r].prim ? 8 : 0));
+        for (int i = 0; i < len; ++i) a.out.ids[k0 + id_w + i] = a.e.em_unitig[k0 + pr[i]];
+        id_w += uint32_t(len);
+        ++n_ord;
+      }
+    }
+    a.out.edge_n_orders[e] = n_ord;
+  }
+}
+
+void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, const UnitigTable &unitigs,
+                        const MatchSoA &m, const EdgeTables &e, uint64_t wiggle_room, OrderTables &out, float *ms_out) {
+  out = OrderTables{};
+  if (!e.pair_rows || !reads.nlen)
+    throw BuildError{MSGPU_ERR_NO_RESULT, "chaining needs a construction from PAF text by the product pairing variant"};
+  const uint64_t M = m.n, R = reads.n, E = e.n_edges, EM = e.n_em;
+  cudaEvent_t    ev0, ev1;
+  MSGPU_CUDA(cudaEventCreate(&ev0));
+  MSGPU_CUDA(cudaEventCreate(&ev1));
+  MSGPU_CUDA(cudaEventRecord(ev0, st));
+
+  // per-read ordered match lists
+  uint32_t *deg = arena.alloc<uint32_t>(R + 1), *cursor = arena.alloc<uint32_t>(R + 1);
+  uint32_t *rm_off = arena.alloc<uint32_t>(R + 1), *tmp = arena.alloc<uint32_t>(M), *list = arena.alloc<uint32_t>(M);
+  uint32_t *d_tot = arena.alloc<uint32_t>(2);
+  MSGPU_CUDA(cudaMemsetAsync(deg, 0, (R + 1) * sizeof(uint32_t), st));
+  MSGPU_CUDA(cudaMemsetAsync(cursor, 0, (R + 1) * sizeof(uint32_t), st));
+  MSGPU_CUDA(cudaMemsetAsync(d_tot, 0, 2 * sizeof(uint32_t), st));
+  const int gm = grid_for(M, 256);
+  if (M) MSGPU_LAUNCH("read_degree", st, read_degree_kernel<<<gm, 256, 0, st>>>(m.read, M, deg));
+  exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{deg}, R + 1, rm_off, d_tot);
+  if (M) {
+    MSGPU_LAUNCH("read_scatter", st, read_scatter_kernel<<<gm, 256, 0, st>>>(m.read, M, rm_off, cursor, tmp));
+    MSGPU_LAUNCH("read_order", st, read_order_kernel<<<gm, 256, 0, st>>>(m, rm_off, tmp, list));
+  }
+
+  out.edge_shadow   = arena.alloc<uint8_t>(E);
+  out.edge_n_orders = arena.alloc<uint32_t>(E);
+  out.left          = arena.alloc<double>(EM);
+  out.right         = arena.alloc<double>(EM);
+  out.score         = arena.alloc<uint64_t>(EM);
+  out.n_ids         = arena.alloc<uint32_t>(EM);
+  out.ids           = arena.alloc<uint32_t>(EM);
+  out.flags         = arena.alloc<uint8_t>(EM);
+  // slots no order lands in stay zero, so that the host copy is deterministic
+  MSGPU_CUDA(cudaMemsetAsync(out.left, 0, EM * sizeof(double), st));
+  MSGPU_CUDA(cudaMemsetAsync(out.right, 0, EM * sizeof(double), st));
+  MSGPU_CUDA(cudaMemsetAsync(out.score, 0, EM * sizeof(uint64_t), st));
+  MSGPU_CUDA(cudaMemsetAsync(out.n_ids, 0, EM * sizeof(uint32_t), st));
+  MSGPU_CUDA(cudaMemsetAsync(out.ids, 0, EM * sizeof(uint32_t), st));
+  MSGPU_CUDA(cudaMemsetAsync(out.flags, 0, EM, st));
+
+  ChainArgs a;
+  a.m         = m;
+  a.read_nlen = reads.nlen;
+  a.grp_off   = unitigs.grp_off;
+  a.rows      = e.pair_rows;
+  a.p_read    = e.p_read;
+  a.rm_off    = rm_off;
+  a.rm_list   = list;
+  a.e         = e;
+  a.wiggle    = wiggle_room;
+  a.out       = out;
+  a.too_long  = d_tot + 1;
+  if (E) MSGPU_LAUNCH("chain_edges", st, chain_edges_kernel<<<grid_for(E, 128), 128, 0, st>>>(a));
+  MSGPU_CUDA(cudaEventRecord(ev1, st));
+  uint32_t h[2];
+  MSGPU_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(h), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaStreamSynchronize(st));
+  if (ms_out) MSGPU_CUDA(cudaEventElapsedTime(ms_out, ev0, ev1));
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (h[1])
+    throw BuildError{MSGPU_ERR_LIMIT, "an edge holds more than " + std::to_string(kChainMax) +
+                                          " edge matches of one direction (chaining supports up to that many)"};
+  out.valid = true;
+}
+
+} // namespace msgpu

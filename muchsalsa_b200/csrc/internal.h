@@ -35,6 +35,27 @@ struct UnitigTable : NameTable {
   uint32_t *grp_off = nullptr; // n + 1 : matches of unitig u are rows [grp_off[u], grp_off[u+1])
 };
 
+// One match, as the pairing kernels gather it (32 bytes = one L2 sector).  Rows are grouped by unitig and ordered by
+// read id inside a unitig; `orig` is the row of the same match in the public match table (MatchSoA).
+struct __align__(16) PairRow {
+  int32_t  ir0, ir1; // illuminaRange (inclusive)
+  uint32_t read;
+  int32_t  score;
+  uint32_t line, flags, unitig, orig;
+};
+
+// EdgeOrder rows (Edge.h:49-60) + the per-edge shadow flag, as msgpu_chain_overlaps leaves them (see include/msgpu.h)
+struct OrderTables {
+  bool      valid = false;
+  uint8_t  *edge_shadow = nullptr;
+  uint32_t *edge_n_orders = nullptr;
+  double   *left = nullptr, *right = nullptr;
+  uint64_t *score = nullptr;
+  uint32_t *n_ids = nullptr, *ids = nullptr;
+  uint8_t  *flags = nullptr;
+  uint64_t  n_orders = 0;
+};
+
 struct EdgeTables {
   uint64_t  n_pairs = 0;
   uint64_t  n_edges = 0;
@@ -46,6 +67,9 @@ struct EdgeTables {
   double   *em_score = nullptr;
   uint32_t *em_line  = nullptr;
   uint8_t  *em_flags = nullptr;
+  // the pairing's index of the matches (grouped by unitig, by read inside): what the chaining stage looks matches up in
+  const PairRow  *pair_rows = nullptr;
+  const uint32_t *p_read    = nullptr;
 };
 
 struct BuildError {
@@ -91,5 +115,11 @@ void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable 
 void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msgpu_shard_header *headers,
                      const void *const *dev_blobs, uint64_t *n_lines_out, ReadTable &reads, UnitigTable &unitigs,
                      MatchSoA &matches);
+
+// chain.cu : the stage after construction — per edge chaining of its edge matches and the overlap geometry
+// (src/main.cpp:328-414, mpp.cpp:38-305, ol.cpp:31-101) -> shadow flag + EdgeOrder rows
+void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, const UnitigTable &unitigs,
+                        const MatchSoA &matches, const EdgeTables &edges, uint64_t wiggle_room, OrderTables &out,
+                        float *ms_out);
 
 } // namespace msgpu

@@ -63,6 +63,12 @@ struct msgpu_ctx {
   bool         host_valid = false;
   msgpu_tables host_tables{};
 
+  OrderTables  orders; // msgpu_chain_overlaps
+  float        chain_ms = 0.f;
+  PinnedBuf    host_orders;
+  bool         orders_host_valid = false;
+  msgpu_orders host_orders_view{};
+
   SeqStore *seq = nullptr;
   Profiler  profiler;
 };
@@ -119,6 +125,7 @@ void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes, bool pair =
   cudaStream_t st  = ctx->stream;
   ctx->have_result = false;
   ctx->host_valid  = false;
+  ctx->orders      = OrderTables{};
   ctx->arena.reset();
   ctx->profiler.clear();
   MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
@@ -254,6 +261,7 @@ int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t 
     cudaStream_t st  = ctx->stream;
     ctx->have_result = false;
     ctx->host_valid  = false;
+    ctx->orders      = OrderTables{};
     ctx->arena.reset();
     ctx->profiler.clear();
     ctx->reads   = ReadTable{};
@@ -326,6 +334,7 @@ int msgpu_build_from_shards(msgpu_ctx *ctx, uint32_t n_shards, const msgpu_shard
     cudaStream_t st  = ctx->stream;
     ctx->have_result = false;
     ctx->host_valid  = false;
+    ctx->orders      = OrderTables{};
     ctx->arena.reset();
     ctx->profiler.clear();
     MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
@@ -458,6 +467,85 @@ int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out) {
     ctx->host_valid = true;
     *out            = h;
   });
+}
+
+int msgpu_chain_overlaps(msgpu_ctx *ctx, uint64_t wiggle_room) {
+  return guarded(ctx, [&] {
+    if (!ctx->have_result) throw BuildError{MSGPU_ERR_NO_RESULT, "no construction to chain"};
+    ctx->orders            = OrderTables{};
+    ctx->orders_host_valid = false;
+    ctx->profiler.clear();
+    run_chain_overlaps(ctx->arena, ctx->stream, ctx->reads, ctx->unitigs, ctx->matches, ctx->edges, wiggle_room,
+                       ctx->orders, &ctx->chain_ms);
+  });
+}
+
+int msgpu_orders_device(const msgpu_ctx *ctx, msgpu_orders *o) {
+  if (!ctx || !o) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->have_result || !ctx->orders.valid) return MSGPU_ERR_NO_RESULT;
+  o->n_edges       = ctx->edges.n_edges;
+  o->n_slots       = ctx->edges.n_em;
+  o->edge_shadow   = ctx->orders.edge_shadow;
+  o->edge_n_orders = ctx->orders.edge_n_orders;
+  o->ord_left      = ctx->orders.left;
+  o->ord_right     = ctx->orders.right;
+  o->ord_score     = ctx->orders.score;
+  o->ord_n_ids     = ctx->orders.n_ids;
+  o->ord_flags     = ctx->orders.flags;
+  o->ord_ids       = ctx->orders.ids;
+  return MSGPU_OK;
+}
+
+int msgpu_orders_host(msgpu_ctx *ctx, msgpu_orders *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->have_result || !ctx->orders.valid) return MSGPU_ERR_NO_RESULT;
+  if (ctx->orders_host_valid) {
+    *out = ctx->host_orders_view;
+    return MSGPU_OK;
+  }
+  return guarded(ctx, [&] {
+    msgpu_orders d;
+    msgpu_orders_device(ctx, &d);
+    const uint64_t E = d.n_edges, S = d.n_slots;
+    size_t         off = 0;
+    const size_t a_sh = slab_reserve<uint8_t>(off, E), a_no = slab_reserve<uint32_t>(off, E),
+                 a_l = slab_reserve<double>(off, S), a_r = slab_reserve<double>(off, S),
+                 a_sc = slab_reserve<uint64_t>(off, S), a_ni = slab_reserve<uint32_t>(off, S),
+                 a_fl = slab_reserve<uint8_t>(off, S), a_id = slab_reserve<uint32_t>(off, S);
+    char        *slab = static_cast<char *>(ctx->host_orders.get(off + 64));
+    cudaStream_t st   = ctx->stream;
+    auto copy = [&](size_t at, const void *src, size_t bytes) {
+      if (bytes) MSGPU_CUDA(cudaMemcpyAsync(slab + at, src, bytes, cudaMemcpyDeviceToHost, st));
+    };
+    copy(a_sh, d.edge_shadow, E);
+    copy(a_no, d.edge_n_orders, E * 4);
+    copy(a_l, d.ord_left, S * 8);
+    copy(a_r, d.ord_right, S * 8);
+    copy(a_sc, d.ord_score, S * 8);
+    copy(a_ni, d.ord_n_ids, S * 4);
+    copy(a_fl, d.ord_flags, S);
+    copy(a_id, d.ord_ids, S * 4);
+    MSGPU_CUDA(cudaStreamSynchronize(st));
+    msgpu_orders &h = ctx->host_orders_view;
+    h               = d;
+    h.edge_shadow   = reinterpret_cast<const uint8_t *>(slab + a_sh);
+    h.edge_n_orders = reinterpret_cast<const uint32_t *>(slab + a_no);
+    h.ord_left      = reinterpret_cast<const double *>(slab + a_l);
+    h.ord_right     = reinterpret_cast<const double *>(slab + a_r);
+    h.ord_score     = reinterpret_cast<const uint64_t *>(slab + a_sc);
+    h.ord_n_ids     = reinterpret_cast<const uint32_t *>(slab + a_ni);
+    h.ord_flags     = reinterpret_cast<const uint8_t *>(slab + a_fl);
+    h.ord_ids       = reinterpret_cast<const uint32_t *>(slab + a_id);
+    ctx->orders_host_valid = true;
+    *out                   = h;
+  });
+}
+
+int msgpu_chain_ms(const msgpu_ctx *ctx, float *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->orders.valid) return MSGPU_ERR_NO_RESULT;
+  *out = ctx->chain_ms;
+  return MSGPU_OK;
 }
 
 int msgpu_profile_enable(msgpu_ctx *ctx, int enable) {

@@ -54,15 +54,6 @@ constexpr uint32_t kHalfCap    = kTileCap / 2;
 constexpr uint32_t kSrcRatio   = kHalfCap / (kSrcCap / 2); // a source weighs at least this much when tiles are packed
 constexpr int      kItems      = kTileCap / kFusedBlock;   // sort items per thread
 
-// One match, as the pairing kernel gathers it (32 bytes = one L2 sector).  Rows are grouped by unitig and ordered by
-// read id inside a unitig.
-struct __align__(16) PairRow {
-  int32_t  ir0, ir1; // illuminaRange (inclusive)
-  uint32_t read;
-  int32_t  score;
-  uint32_t line, flags, unitig, pad;
-};
-
 // ---------------------------------------------------------------------------------------------------------------------
 // pre-pass 1: order every group by read id, build the pair rows, and accumulate per read its number of sources and
 // its number of candidates
@@ -91,7 +82,7 @@ __device__ __forceinline__ void place_row(const RankArgs &a, uint64_t i, uint32_
   row.line   = m.line[i];
   row.flags  = m.flags[i];
   row.unitig = u;
-  row.pad    = 0;
+  row.orig   = uint32_t(i);
   a.rows[q]   = row;
   a.p_read[q] = row.read;
   a.p_ir0[q]  = row.ir0;
@@ -990,7 +981,7 @@ __device__ __forceinline__ PairRow ld_row(const PairRow *p) { // two 128-bit rea
   r.line   = y.x;
   r.flags  = y.y;
   r.unitig = y.z;
-  r.pad    = 0;
+  r.orig   = y.w;
   return r;
 }
 
@@ -1235,8 +1226,10 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
     throw BuildError{MSGPU_ERR_LIMIT, "a read matches more than " + std::to_string(kSrcCap) + " unitigs with partners"};
   if (h_flags[3])
     throw BuildError{MSGPU_ERR_INTERNAL, "pairing: tile invariant violated (code " + std::to_string(h_flags[3]) + ")"};
-  e.n_em    = h_tot[0];
-  e.n_edges = h_tot[1];
+  e.n_em      = h_tot[0];
+  e.n_edges   = h_tot[1];
+  e.pair_rows = rows; // kept (in the arena) for the stage that follows: msgpu_chain_overlaps
+  e.p_read    = p_read;
 }
 
 void run_pairing(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,

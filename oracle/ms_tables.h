@@ -73,6 +73,27 @@ typedef struct ms_tables {
 
 void ms_tables_free(ms_tables *t);
 
+/* Result of the stage right after construction (src/main.cpp:170-178,328-414: chainingAndOverlaps ->
+ * getMaxPairwisePaths, mpp.cpp:145-305 -> getOverlap, ol.cpp:53-101): per edge its shadow flag and its EdgeOrder
+ * list (Edge.h:49-60), edges in (first, second) order, orders in the order the reference appends them (minus paths,
+ * then plus paths).  baseVertex is always the edge's first vertex and is not dumped. */
+typedef struct ms_orders {
+  uint64_t  n_edges;
+  uint8_t  *edge_shadow;
+  uint64_t *edge_order_begin; /* n_edges + 1 */
+  uint64_t  n_orders;
+  uint8_t  *ord_start_is_first; /* startVertex == Edge::getVertices().first */
+  double   *ord_left, *ord_right;
+  uint8_t  *ord_contained, *ord_direction, *ord_primary;
+  uint64_t *ord_score;
+  uint64_t *ord_ids_begin; /* n_orders + 1 */
+  uint64_t  n_ids;
+  uint32_t *ord_ids;
+  double    t_chain; /* wall-clock seconds of the stage */
+} ms_orders;
+
+void ms_orders_free(ms_orders *o);
+
 #ifdef __cplusplus
 }
 #endif

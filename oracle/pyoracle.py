@@ -46,6 +46,48 @@ class _MsTables(C.Structure):
     ]
 
 
+class _MsOrders(C.Structure):
+    _P = C.POINTER
+    _fields_ = [
+        ("n_edges", C.c_uint64), ("edge_shadow", _P(C.c_uint8)), ("edge_order_begin", _P(C.c_uint64)),
+        ("n_orders", C.c_uint64), ("ord_start_is_first", _P(C.c_uint8)), ("ord_left", _P(C.c_double)),
+        ("ord_right", _P(C.c_double)), ("ord_contained", _P(C.c_uint8)), ("ord_direction", _P(C.c_uint8)),
+        ("ord_primary", _P(C.c_uint8)), ("ord_score", _P(C.c_uint64)), ("ord_ids_begin", _P(C.c_uint64)),
+        ("n_ids", C.c_uint64), ("ord_ids", _P(C.c_uint32)), ("t_chain", C.c_double),
+    ]
+
+
+@dataclass
+class Orders:
+    """Canonical result of chainingAndOverlaps (see oracle/ms_tables.h, ms_orders): per edge a shadow flag and its
+    EdgeOrder list; edges in (first, second) order."""
+    edge_shadow: np.ndarray
+    edge_order_begin: np.ndarray
+    start_is_first: np.ndarray
+    left: np.ndarray
+    right: np.ndarray
+    contained: np.ndarray
+    direction: np.ndarray
+    primary: np.ndarray
+    score: np.ndarray
+    ids_begin: np.ndarray
+    ids: np.ndarray
+    seconds: float = 0.0
+
+
+def orders_equal(a: Orders, b: Orders) -> list:
+    """Names of the fields in which two dumps differ (doubles compared bit for bit)."""
+    bad = []
+    for f in ("edge_shadow", "edge_order_begin", "start_is_first", "left", "right", "contained", "direction",
+              "primary", "score", "ids_begin", "ids"):
+        x, y = getattr(a, f), getattr(b, f)
+        if x.dtype == np.float64:
+            x, y = x.view(np.uint64), np.asarray(y, np.float64).view(np.uint64)
+        if x.shape != y.shape or not np.array_equal(x, y):
+            bad.append(f)
+    return bad
+
+
 @dataclass
 class Tables:
     """Canonical construction result (see oracle/ms_tables.h for the sort orders)."""
@@ -196,6 +238,31 @@ class Reference(_Checker):
                               dict(index=t.t_index, read=t.t_read, edges=t.t_edges, n_reads=int(t.n_reads)))
             out = _to_tables(t)
             self.lib.ms_tables_free(C.byref(t))
+            return out
+        finally:
+            if tmp:
+                os.unlink(path)
+
+    def chain(self, paf, wiggle_room: int = 300) -> Orders:
+        """Construction with one thread, then the reference's chainingAndOverlaps on every edge."""
+        L = self.lib
+        L.msref_chain.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(_MsOrders)]
+        L.msref_chain.restype = C.c_int
+        L.ms_orders_free.argtypes = [C.POINTER(_MsOrders)]
+        L.ms_orders_free.restype = None
+        path, tmp = self._as_path(paf)
+        try:
+            o = _MsOrders()
+            if L.msref_chain(path.encode(), wiggle_room, C.byref(o)):
+                raise RuntimeError("reference threw (see stderr)")
+            E, N, I = int(o.n_edges), int(o.n_orders), int(o.n_ids)
+            out = Orders(_arr(o.edge_shadow, E, np.uint8), _arr(o.edge_order_begin, E + 1, np.uint64),
+                         _arr(o.ord_start_is_first, N, np.uint8), _arr(o.ord_left, N, np.float64),
+                         _arr(o.ord_right, N, np.float64), _arr(o.ord_contained, N, np.uint8),
+                         _arr(o.ord_direction, N, np.uint8), _arr(o.ord_primary, N, np.uint8),
+                         _arr(o.ord_score, N, np.uint64), _arr(o.ord_ids_begin, N + 1, np.uint64),
+                         _arr(o.ord_ids, I, np.uint32), float(o.t_chain))
+            L.ms_orders_free(C.byref(o))
             return out
         finally:
             if tmp:

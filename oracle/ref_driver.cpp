@@ -27,6 +27,7 @@
 
 #include "BlastFileAccessor.h"
 #include "BlastFileReader.h"
+#include "Kernel.h"
 #include "Registry.h"
 #include "SequenceAccessor.h"
 #include "SequenceUtils.h"
@@ -334,6 +335,130 @@ int64_t msref_seq_fetch_gpu(const char *unitigs_path, const char *nanopore_path,
 }
 #endif
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The stage after construction: chainingAndOverlaps (src/main.cpp:328-414) for every edge.  The job body lives in the
+// reference's main.cpp (which cannot be linked: it defines main()), so its control flow is restated here line by line
+// around the reference's OWN getMaxPairwisePaths (mpp.cpp:145-305) and getOverlap (ol.cpp:53-101), which do all the
+// arithmetic.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+void chain_one_edge(muchsalsa::matching::MatchMap &matchMap, muchsalsa::graph::Edge *pEdge, std::size_t wiggleRoom) {
+  using namespace muchsalsa;
+  std::vector<unsigned int> plusIDs, minusIDs;
+  auto const *const         pEdgeMatches = matchMap.getEdgeMatches(pEdge); // main.cpp:334
+  if (!pEdgeMatches) return;
+  for (auto const &[illuminaId, edgeMatch] : *pEdgeMatches) { // main.cpp:341-349
+    if (edgeMatch->direction) plusIDs.push_back(illuminaId); else minusIDs.push_back(illuminaId);
+  }
+  auto minusPaths = getMaxPairwisePaths(matchMap, *pEdge, minusIDs, false, wiggleRoom); // main.cpp:352-353
+  auto plusPaths  = getMaxPairwisePaths(matchMap, *pEdge, plusIDs, true, wiggleRoom);
+  auto isPrim  = [](auto const &p) { return std::get<2>(p); };
+  auto isMulti = [](auto const &p) { return std::get<0>(p).size() > 1; };
+  bool hasPrimary = std::any_of(plusPaths.begin(), plusPaths.end(), isPrim) || // main.cpp:355-361
+                    std::any_of(minusPaths.begin(), minusPaths.end(), isPrim);
+  if (hasPrimary) { // main.cpp:363-371
+    plusPaths.erase(std::remove_if(plusPaths.begin(), plusPaths.end(), [&](auto const &p) { return !isPrim(p); }), plusPaths.end());
+    minusPaths.erase(std::remove_if(minusPaths.begin(), minusPaths.end(), [&](auto const &p) { return !isPrim(p); }), minusPaths.end());
+  }
+  bool hasMulti = std::any_of(plusPaths.begin(), plusPaths.end(), isMulti) || // main.cpp:373-379
+                  std::any_of(minusPaths.begin(), minusPaths.end(), isMulti);
+  if (hasMulti) { // main.cpp:381-389
+    plusPaths.erase(std::remove_if(plusPaths.begin(), plusPaths.end(), [&](auto const &p) { return !isMulti(p); }), plusPaths.end());
+    minusPaths.erase(std::remove_if(minusPaths.begin(), minusPaths.end(), [&](auto const &p) { return !isMulti(p); }), minusPaths.end());
+  }
+  if (plusPaths.size() + minusPaths.size() > 1) { // main.cpp:391-397
+    pEdge->setShadow(true);
+  } else {
+    auto const &path = !minusPaths.empty() ? minusPaths[0] : plusPaths[0];
+    pEdge->setShadow(!std::get<2>(path));
+  }
+  for (auto &p : minusPaths) { // main.cpp:399-405
+    auto o = getOverlap(matchMap, std::get<0>(p), *pEdge, false, std::get<1>(p), std::get<2>(p));
+    if (o.has_value()) pEdge->appendOrder(std::move(o.value()));
+  }
+  for (auto &p : plusPaths) { // main.cpp:407-413
+    auto o = getOverlap(matchMap, std::get<0>(p), *pEdge, true, std::get<1>(p), std::get<2>(p));
+    if (o.has_value()) pEdge->appendOrder(std::move(o.value()));
+  }
+}
+} // namespace
+
+void ms_orders_free(ms_orders *o) {
+  if (!o) return;
+  void *ptrs[] = {o->edge_shadow, o->edge_order_begin, o->ord_start_is_first, o->ord_left,  o->ord_right, o->ord_contained,
+                  o->ord_direction, o->ord_primary,    o->ord_score,          o->ord_ids_begin, o->ord_ids};
+  for (void *p : ptrs) std::free(p);
+  std::memset(o, 0, sizeof(*o));
+}
+
+// construction with one thread (the canonical mode) + chainingAndOverlaps on every edge; edges in (first, second) order
+int msref_chain(const char *paf_path, uint64_t wiggle_room, ms_orders *out) {
+  using namespace muchsalsa;
+  std::memset(out, 0, sizeof(*out));
+  try {
+    auto pool             = threading::ThreadPool(1);
+    auto graph            = graph::Graph();
+    auto matchMap         = matching::MatchMap(&pool, &graph);
+    auto registryNanopore = Registry();
+    auto registryIllumina = Registry();
+    auto bfAccessor       = BlastFileAccessor(paf_path);
+    auto reader = BlastFileReader(&pool, &bfAccessor, &graph, &matchMap, &registryNanopore, &registryIllumina);
+    reader.read();
+    matchMap.calculateEdges();
+    auto edges = graph.getEdges();
+    std::sort(edges.begin(), edges.end(), [](auto *a, auto *b) {
+      auto va = a->getVertices(), vb = b->getVertices();
+      return std::make_pair(va.first->getId(), va.second->getId()) <
+             std::make_pair(vb.first->getId(), vb.second->getId());
+    });
+    auto t0 = clk::now();
+    for (auto *pE : edges) chain_one_edge(matchMap, pE, static_cast<std::size_t>(wiggle_room));
+    out->t_chain = secs(t0, clk::now());
+
+    std::vector<uint8_t>  shadow, sif, cont, dir, prim;
+    std::vector<uint64_t> ob, score, ib;
+    std::vector<double>   left, right;
+    std::vector<uint32_t> ids;
+    for (auto *pE : edges) {
+      auto v = pE->getVertices();
+      shadow.push_back(pE->isShadow() ? 1 : 0);
+      ob.push_back(left.size());
+      for (auto const &o : pE->getEdgeOrders()) {
+        if (o.baseVertex != v.first) throw std::runtime_error("baseVertex is not the first vertex");
+        sif.push_back(o.startVertex == v.first ? 1 : 0);
+        left.push_back(o.leftOffset);
+        right.push_back(o.rightOffset);
+        cont.push_back(static_cast<bool>(o.isContained) ? 1 : 0);
+        dir.push_back(static_cast<bool>(o.direction) ? 1 : 0);
+        prim.push_back(static_cast<bool>(o.isPrimary) ? 1 : 0);
+        score.push_back(o.score);
+        ib.push_back(ids.size());
+        for (auto u : o.ids) ids.push_back(u);
+      }
+    }
+    ob.push_back(left.size());
+    ib.push_back(ids.size());
+    out->n_edges            = edges.size();
+    out->edge_shadow        = dup(shadow);
+    out->edge_order_begin   = dup(ob);
+    out->n_orders           = left.size();
+    out->ord_start_is_first = dup(sif);
+    out->ord_left           = dup(left);
+    out->ord_right          = dup(right);
+    out->ord_contained      = dup(cont);
+    out->ord_direction      = dup(dir);
+    out->ord_primary        = dup(prim);
+    out->ord_score          = dup(score);
+    out->ord_ids_begin      = dup(ib);
+    out->n_ids              = ids.size();
+    out->ord_ids            = dup(ids);
+    return 0;
+  } catch (std::exception const &e) {
+    std::fprintf(stderr, "msref_chain: %s\n", e.what());
+    return 1;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Sequence path: strSlice / getReverseComplement (SequenceUtils.cpp:27-61) and the FASTA/FASTQ store
