@@ -265,6 +265,15 @@ def run_ours(args):
                                      "bytes_written_once": int(strict + n_bytes),
                                      "frac": round((strict + n_bytes) / step_ms / 1e6 / peak, 4)}
 
+    # ---- the stage that consumes the tables while they are in HBM (chaining + overlaps per edge);
+    # reported beside the metric, not part of it.  Device time from the library's own events.
+    chain_ms = []
+    for _ in range(min(args.steps, 3)):
+        step_device()
+        gb.chain_overlaps(300)
+        chain_ms.append(gb.chain_ms())
+    chain_t = reduce(sum(chain_ms) / len(chain_ms), "MAX")
+
     # ---- the reference's CPU path beside it (bounded sample, rank 0 at N = 1 only)
     cpu = cpu_baseline(args.workload) if world == 1 else None
 
@@ -293,6 +302,11 @@ def run_ours(args):
         "kernels": {k: {kk: round(vv, 3) for kk, vv in v.items()} for k, v in top[:12]},
         "variant": os.environ.get("MSGPU_VARIANT", "default"),
     }
+    out["chain_overlaps"] = {
+        "what": "per-edge max pairwise paths + overlap geometry (src/main.cpp:328-414, mpp.cpp, ol.cpp) on the "
+                "device-resident edge tables; bit-exact vs the reference (tests/test_chain_gpu.py)",
+        "ms": round(chain_t, 3), "edges_per_s": n_edges / chain_t * 1e3,
+        "cpu_reference": (cpu or {}).get("chain")}
     if world > 1:
         x = [v for v in xch_ms if v is not None]
         x_ms = reduce(sum(x) / len(x), "MAX") if x else None
@@ -355,7 +369,16 @@ def cpu_baseline(workload, steps=1):
                     best = (t, r1)
             res, threads = best[1], 1
         t = res["t_index"] + res["t_read"] + res["t_edges"]
-        return {"value": res["n_vm"] / t, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+        chain = None
+        try:  # the stage after construction on the same sample (1 thread; edges are independent jobs in the reference)
+            p = subprocess.run([cli, path, "1", "chain"], capture_output=True, text=True, timeout=1800)
+            if p.returncode == 0:
+                c = json.loads(p.stdout.strip().splitlines()[-1])
+                chain = {"edges_per_s": c["n_edges"] / c["t_chain"], "seconds": round(c["t_chain"], 3), "cores": 1,
+                         "edges": c["n_edges"], "sample": sample}
+        except Exception as e:  # the baseline must not take the bench down
+            chain = {"error": repr(e)}
+        return {"chain": chain, "value": res["n_vm"] / t, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
                 "seconds": round(t, 3), "edges_per_s": res["n_edges"] / t, "edge_matches_per_s": res["n_em"] / t,
                 "phases_s": {k: res[k] for k in ("t_index", "t_read", "t_edges")},
                 "rows": {k: res[k] for k in ("n_reads", "n_vm", "n_edges", "n_em")}, "host_cpus": ncpu, "note": note}

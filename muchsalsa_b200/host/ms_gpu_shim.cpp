@@ -105,6 +105,40 @@ void constructGraph(Context &ctx, std::string const &pafPath, graph::Graph &grap
   }
 }
 
+void chainAndOverlaps(Context &ctx, graph::Graph &graph, std::size_t wiggleRoom) {
+  if (int rc = msgpu_chain_overlaps(ctx.get(), wiggleRoom); rc != MSGPU_OK) raise(ctx.get(), rc);
+  msgpu_counts c{};
+  msgpu_tables t{};
+  msgpu_orders o{};
+  if (int rc = msgpu_result_counts(ctx.get(), &c); rc != MSGPU_OK) raise(ctx.get(), rc);
+  if (int rc = msgpu_result_host(ctx.get(), &t); rc != MSGPU_OK) raise(ctx.get(), rc);
+  if (int rc = msgpu_orders_host(ctx.get(), &o); rc != MSGPU_OK) raise(ctx.get(), rc);
+  for (uint64_t e = 0; e < c.n_edges; ++e) {
+    auto const *const pFirst  = graph.getVertex(t.edge_first[e]);
+    auto const *const pSecond = graph.getVertex(t.edge_second[e]);
+    auto *const       pEdge =
+        graph.getEdge(std::make_pair(gsl::make_not_null(pFirst), gsl::make_not_null(pSecond)));
+    pEdge->setShadow(o.edge_shadow[e] != 0);
+    uint64_t idAt = t.edge_em_begin[e]; // the ids of the edge's orders are concatenated from its first slot on
+    for (uint32_t i = 0; i < o.edge_n_orders[e]; ++i) {
+      uint64_t const slot        = t.edge_em_begin[e] + i;
+      bool const     startIsFirst = (o.ord_flags[slot] & 1) != 0;
+      std::vector<unsigned int> ids(o.ord_ids + idAt, o.ord_ids + idAt + o.ord_n_ids[slot]);
+      idAt += o.ord_n_ids[slot];
+      pEdge->appendOrder(graph::EdgeOrder{startIsFirst ? pFirst : pSecond,
+                                          startIsFirst ? pSecond : pFirst,
+                                          o.ord_left[slot],
+                                          o.ord_right[slot],
+                                          Toggle((o.ord_flags[slot] & 2) != 0),
+                                          pFirst, // baseVertex is always the edge's first vertex (ol.cpp:81-97)
+                                          static_cast<std::size_t>(o.ord_score[slot]),
+                                          std::move(ids),
+                                          Toggle((o.ord_flags[slot] & 4) != 0),
+                                          Toggle((o.ord_flags[slot] & 8) != 0)});
+    }
+  }
+}
+
 void loadSequences(Context &ctx, std::string const &unitigsPath, std::string const &nanoporePath) {
   if (int rc = msgpu_seq_load(ctx.get(), unitigsPath.c_str(), nanoporePath.c_str()); rc != MSGPU_OK)
     raise(ctx.get(), rc);

@@ -45,6 +45,11 @@ void constructGraph(Context &ctx, std::string const &pafPath, muchsalsa::graph::
                     muchsalsa::matching::MatchMap &matchMap, muchsalsa::Registry &registryNanopore,
                     muchsalsa::Registry &registryIllumina);
 
+// The stage right after construction, for every edge of the graph built by constructGraph on `ctx`: replaces the
+// ThreadPool loop over chainingAndOverlaps jobs (src/main.cpp:170-178, 328-414).  Sets Edge::setShadow and appends the
+// EdgeOrders exactly as getMaxPairwisePaths (mpp.cpp) + getOverlap (ol.cpp) would.
+void chainAndOverlaps(Context &ctx, muchsalsa::graph::Graph &graph, std::size_t wiggleRoom);
+
 // SequenceAccessor(...) + buildIndex() (src/main.cpp:161-163): both files indexed and kept resident in HBM; ids
 // continue the numbering of the construction that ran on `ctx`.
 void loadSequences(Context &ctx, std::string const &unitigsPath, std::string const &nanoporePath);

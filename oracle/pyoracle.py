@@ -255,18 +255,44 @@ class Reference(_Checker):
             o = _MsOrders()
             if L.msref_chain(path.encode(), wiggle_room, C.byref(o)):
                 raise RuntimeError("reference threw (see stderr)")
-            E, N, I = int(o.n_edges), int(o.n_orders), int(o.n_ids)
-            out = Orders(_arr(o.edge_shadow, E, np.uint8), _arr(o.edge_order_begin, E + 1, np.uint64),
-                         _arr(o.ord_start_is_first, N, np.uint8), _arr(o.ord_left, N, np.float64),
-                         _arr(o.ord_right, N, np.float64), _arr(o.ord_contained, N, np.uint8),
-                         _arr(o.ord_direction, N, np.uint8), _arr(o.ord_primary, N, np.uint8),
-                         _arr(o.ord_score, N, np.uint64), _arr(o.ord_ids_begin, N + 1, np.uint64),
-                         _arr(o.ord_ids, I, np.uint32), float(o.t_chain))
+            out = self._orders(o)
             L.ms_orders_free(C.byref(o))
             return out
         finally:
             if tmp:
                 os.unlink(path)
+
+    def chain_gpu(self, paf, wiggle_room: int = 300) -> Orders:
+        """Construction AND chaining by the GPU path through the host shim (constructGraph + chainAndOverlaps of
+        muchsalsa_b200/host/ms_gpu_shim.cpp) into the reference's own Graph / Edge objects, dumped like `chain`."""
+        L = self.lib
+        L.msref_chain_gpu.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(_MsOrders), C.c_char_p, C.c_uint64]
+        L.msref_chain_gpu.restype = C.c_int
+        L.ms_orders_free.argtypes = [C.POINTER(_MsOrders)]
+        L.ms_orders_free.restype = None
+        path, tmp = self._as_path(paf)
+        try:
+            o = _MsOrders()
+            err = C.create_string_buffer(512)
+            rc = L.msref_chain_gpu(path.encode(), wiggle_room, C.byref(o), err, 512)
+            if rc:
+                raise RuntimeError(f"rc={rc}: {err.value.decode(errors='replace')}")
+            out = self._orders(o)
+            L.ms_orders_free(C.byref(o))
+            return out
+        finally:
+            if tmp:
+                os.unlink(path)
+
+    @staticmethod
+    def _orders(o) -> Orders:
+        E, N, I = int(o.n_edges), int(o.n_orders), int(o.n_ids)
+        return Orders(_arr(o.edge_shadow, E, np.uint8), _arr(o.edge_order_begin, E + 1, np.uint64),
+                      _arr(o.ord_start_is_first, N, np.uint8), _arr(o.ord_left, N, np.float64),
+                      _arr(o.ord_right, N, np.float64), _arr(o.ord_contained, N, np.uint8),
+                      _arr(o.ord_direction, N, np.uint8), _arr(o.ord_primary, N, np.uint8),
+                      _arr(o.ord_score, N, np.uint64), _arr(o.ord_ids_begin, N + 1, np.uint64),
+                      _arr(o.ord_ids, I, np.uint32), float(o.t_chain))
 
     @property
     def has_gpu_shim(self) -> bool:

@@ -311,6 +311,46 @@ int msref_build_gpu(const char *paf_path, ms_tables *out, char *err, uint64_t er
   }
 }
 
+namespace {
+void dump_orders(std::vector<muchsalsa::graph::Edge *> const &edges, ms_orders *out); // defined with msref_chain
+}
+// construction AND chaining through the shim (constructGraph + chainAndOverlaps), dumped like msref_chain
+int msref_chain_gpu(const char *paf_path, uint64_t wiggle_room, ms_orders *out, char *err, uint64_t err_cap) {
+  using namespace muchsalsa;
+  std::memset(out, 0, sizeof(*out));
+  auto fail = [&](const char *m, int rc) {
+    if (err && err_cap) std::snprintf(err, err_cap, "%s", m);
+    return rc;
+  };
+  try {
+    std::unique_ptr<gpu::Context> ctx;
+    try {
+      ctx = std::make_unique<gpu::Context>(0);
+    } catch (std::exception const &e) {
+      return fail(e.what(), 2);
+    }
+    auto pool             = threading::ThreadPool(1);
+    auto graph            = graph::Graph();
+    auto matchMap         = matching::MatchMap(&pool, &graph);
+    auto registryNanopore = Registry();
+    auto registryIllumina = Registry();
+    gpu::constructGraph(*ctx, paf_path, graph, matchMap, registryNanopore, registryIllumina);
+    auto t0 = clk::now();
+    gpu::chainAndOverlaps(*ctx, graph, static_cast<std::size_t>(wiggle_room));
+    out->t_chain = secs(t0, clk::now());
+    auto edges   = graph.getEdges();
+    std::sort(edges.begin(), edges.end(), [](auto *a, auto *b) {
+      auto va = a->getVertices(), vb = b->getVertices();
+      return std::make_pair(va.first->getId(), va.second->getId()) <
+             std::make_pair(vb.first->getId(), vb.second->getId());
+    });
+    dump_orders(edges, out);
+    return 0;
+  } catch (std::exception const &e) {
+    return fail(e.what(), 1);
+  }
+}
+
 // get{Illumina,Nanopore}Sequence through the shim, on a fresh context; returns length, -1 (reference-style exception)
 // or -2 (no GPU / load failure)
 int64_t msref_seq_fetch_gpu(const char *unitigs_path, const char *nanopore_path, int which, const char *name, int l,
@@ -384,6 +424,49 @@ void chain_one_edge(muchsalsa::matching::MatchMap &matchMap, muchsalsa::graph::E
 }
 } // namespace
 
+namespace {
+// flattens the shadow flags and EdgeOrder lists of `edges` (already in (first, second) order) into `out`
+void dump_orders(std::vector<muchsalsa::graph::Edge *> const &edges, ms_orders *out) {
+    std::vector<uint8_t>  shadow, sif, cont, dir, prim;
+  std::vector<uint64_t> ob, score, ib;
+  std::vector<double>   left, right;
+  std::vector<uint32_t> ids;
+  for (auto *pE : edges) {
+    auto v = pE->getVertices();
+    shadow.push_back(pE->isShadow() ? 1 : 0);
+    ob.push_back(left.size());
+    for (auto const &o : pE->getEdgeOrders()) {
+      if (o.baseVertex != v.first) throw std::runtime_error("baseVertex is not the first vertex");
+      sif.push_back(o.startVertex == v.first ? 1 : 0);
+      left.push_back(o.leftOffset);
+      right.push_back(o.rightOffset);
+      cont.push_back(static_cast<bool>(o.isContained) ? 1 : 0);
+      dir.push_back(static_cast<bool>(o.direction) ? 1 : 0);
+      prim.push_back(static_cast<bool>(o.isPrimary) ? 1 : 0);
+      score.push_back(o.score);
+      ib.push_back(ids.size());
+      for (auto u : o.ids) ids.push_back(u);
+    }
+  }
+  ob.push_back(left.size());
+  ib.push_back(ids.size());
+  out->n_edges            = edges.size();
+  out->edge_shadow        = dup(shadow);
+  out->edge_order_begin   = dup(ob);
+  out->n_orders           = left.size();
+  out->ord_start_is_first = dup(sif);
+  out->ord_left           = dup(left);
+  out->ord_right          = dup(right);
+  out->ord_contained      = dup(cont);
+  out->ord_direction      = dup(dir);
+  out->ord_primary        = dup(prim);
+  out->ord_score          = dup(score);
+  out->ord_ids_begin      = dup(ib);
+  out->n_ids              = ids.size();
+  out->ord_ids            = dup(ids);
+}
+} // namespace
+
 void ms_orders_free(ms_orders *o) {
   if (!o) return;
   void *ptrs[] = {o->edge_shadow, o->edge_order_begin, o->ord_start_is_first, o->ord_left,  o->ord_right, o->ord_contained,
@@ -416,43 +499,7 @@ int msref_chain(const char *paf_path, uint64_t wiggle_room, ms_orders *out) {
     for (auto *pE : edges) chain_one_edge(matchMap, pE, static_cast<std::size_t>(wiggle_room));
     out->t_chain = secs(t0, clk::now());
 
-    std::vector<uint8_t>  shadow, sif, cont, dir, prim;
-    std::vector<uint64_t> ob, score, ib;
-    std::vector<double>   left, right;
-    std::vector<uint32_t> ids;
-    for (auto *pE : edges) {
-      auto v = pE->getVertices();
-      shadow.push_back(pE->isShadow() ? 1 : 0);
-      ob.push_back(left.size());
-      for (auto const &o : pE->getEdgeOrders()) {
-        if (o.baseVertex != v.first) throw std::runtime_error("baseVertex is not the first vertex");
-        sif.push_back(o.startVertex == v.first ? 1 : 0);
-        left.push_back(o.leftOffset);
-        right.push_back(o.rightOffset);
-        cont.push_back(static_cast<bool>(o.isContained) ? 1 : 0);
-        dir.push_back(static_cast<bool>(o.direction) ? 1 : 0);
-        prim.push_back(static_cast<bool>(o.isPrimary) ? 1 : 0);
-        score.push_back(o.score);
-        ib.push_back(ids.size());
-        for (auto u : o.ids) ids.push_back(u);
-      }
-    }
-    ob.push_back(left.size());
-    ib.push_back(ids.size());
-    out->n_edges            = edges.size();
-    out->edge_shadow        = dup(shadow);
-    out->edge_order_begin   = dup(ob);
-    out->n_orders           = left.size();
-    out->ord_start_is_first = dup(sif);
-    out->ord_left           = dup(left);
-    out->ord_right          = dup(right);
-    out->ord_contained      = dup(cont);
-    out->ord_direction      = dup(dir);
-    out->ord_primary        = dup(prim);
-    out->ord_score          = dup(score);
-    out->ord_ids_begin      = dup(ib);
-    out->n_ids              = ids.size();
-    out->ord_ids            = dup(ids);
+    dump_orders(edges, out);
     return 0;
   } catch (std::exception const &e) {
     std::fprintf(stderr, "msref_chain: %s\n", e.what());
@@ -560,6 +607,14 @@ int main(int argc, char **argv) {
   if (argc < 3) {
     std::fprintf(stderr, "usage: %s <paf> <threads>\n", argv[0]);
     return 2;
+  }
+  if (argc >= 4 && std::string(argv[3]) == "chain") { // `msref_cli <paf> 1 chain`: also time chainingAndOverlaps
+    ms_orders o;
+    int       rc = msref_chain(argv[1], 300, &o);
+    if (rc) return rc;
+    std::printf("{\"threads\": 1, \"t_chain\": %.6f, \"n_edges\": %llu, \"n_orders\": %llu}\n", o.t_chain,
+                (unsigned long long)o.n_edges, (unsigned long long)o.n_orders);
+    return 0;
   }
   ms_tables t;
   int       rc = msref_build(argv[1], std::atoi(argv[2]), 0, &t);

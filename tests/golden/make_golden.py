@@ -55,6 +55,15 @@ def seq_cases():
             ("odd_fasta_reads", odd_fa, odd_fa, False), ("synth_small", u[:24000], n[:60000], False)]
 
 
+def orders_digest(o) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("edge_shadow", "edge_order_begin", "start_is_first", "left", "right", "contained", "direction", "primary",
+              "score", "ids_begin", "ids"):
+        h.update(np.ascontiguousarray(getattr(o, f)).tobytes())
+    return h.hexdigest()
+
+
 def main():
     R = Reference()
     # the reference's own fixtures (data, not code) travel with the repo so the GPU box can load them
@@ -78,6 +87,10 @@ def main():
             cfg = dataclasses.replace(synth.CONFIGS[name], shuffle_groups=shuffled)
             t = R.build(synth.generate_paf(cfg))
             digests[name + ("_shuffled" if shuffled else "")] = dict(digest=tables_digest(t), counts=t.counts)
+            if not shuffled and name != "yeast":  # the stage after construction (chainingAndOverlaps), same inputs
+                o = R.chain(synth.generate_paf(cfg))
+                digests[name].update(orders_digest=orders_digest(o), orders=int(o.left.size),
+                                     shadow_edges=int(o.edge_shadow.sum()))
             print(name, shuffled, t.counts, flush=True)
     for k, v in old.items():
         digests.setdefault(k, v)

@@ -8,7 +8,7 @@ import pytest
 
 import util
 from muchsalsa_b200 import synth
-from oracle.pyoracle import tables_digest, tables_equal
+from oracle.pyoracle import orders_equal, tables_digest, tables_equal
 
 pytestmark = pytest.mark.gpu
 
@@ -55,3 +55,16 @@ def test_sequence_getters_through_the_shim(ref, tmp_path):
                 assert ref.seq_fetch_gpu(up, np_, which, name, l, r, d) == want
     finally:
         h.close()
+
+
+@pytest.mark.parametrize("name", ["kat8", "duplicates_ungrouped", "heavy_group", "long_tags"])
+def test_reference_edges_chained_by_gpu_equal_reference(ref, name):
+    """Edge::isShadow() and Edge::getEdgeOrders() of the reference's own Edge objects after the shim's
+    chainAndOverlaps, against the reference's own chainingAndOverlaps (src/main.cpp:328-414)."""
+    paf = util.edge_case_pafs()[name]
+    assert orders_equal(ref.chain_gpu(paf), ref.chain(paf)) == []
+
+
+def test_reference_edges_chained_by_gpu_small(ref):
+    paf = synth.generate_paf("small")
+    assert orders_equal(ref.chain_gpu(paf), ref.chain(paf)) == []

@@ -11,12 +11,12 @@ import torch
 import util
 from muchsalsa_b200 import multi_gpu, synth
 from muchsalsa_b200.construct import GraphBuilder
-from oracle.pyoracle import tables_digest, tables_equal
+from oracle.pyoracle import Orders, orders_equal, tables_digest, tables_equal
 
 pytestmark = pytest.mark.gpu
 
 
-def build_sharded(chunks):
+def build_sharded(chunks, chain=False):
     """chunks: the rank-ordered pieces of one PAF.  Returns the merged Construction."""
     n = len(chunks)
     ranks = [GraphBuilder(0) for _ in range(n)]
@@ -34,6 +34,8 @@ def build_sharded(chunks):
         for r, gb in enumerate(ranks):
             gb.build_from_shards(headers, [b.data_ptr() for b in blobs], r, n)
             parts.append(gb.result())
+            if chain:
+                parts[-1].orders = gb.chain_overlaps(300).orders()
         return util.merge_parts(parts), parts
     finally:
         for gb in ranks:
@@ -85,3 +87,23 @@ def test_sharded_builder_world_1_equals_plain_build(builder):
         sb = multi_gpu.ShardedBuilder(gb, 0, 1, None, torch.device("cuda", 0))
         sharded = util.gpu_to_tables(sb.build_buffer(paf).result())
     assert tables_equal(plain, sharded) == []
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_sharded_chain_vs_reference(reference, n):
+    """Every rank chains the edges of its own slice (it holds the whole match table); the slices' orders appended in
+    rank order are the reference's."""
+    paf = util.edge_case_pafs()["heavy_group"] if n == 3 else synth.generate_paf("small")
+    _, parts = build_sharded(multi_gpu.split_paf(paf, n), chain=True)
+    keys = ("start_is_first", "left", "right", "contained", "direction", "primary", "score", "ids")
+    cat = {k: np.concatenate([p.orders[k] for p in parts]) for k in keys}
+    cat["edge_shadow"] = np.concatenate([p.orders["edge_shadow"] for p in parts])
+    ob, ib, o0, i0 = [], [], 0, 0
+    for p in parts:
+        ob.append(p.orders["edge_order_begin"][:-1].astype(np.int64) + o0)
+        ib.append(p.orders["ids_begin"][:-1].astype(np.int64) + i0)
+        o0 += int(p.orders["edge_order_begin"][-1])
+        i0 += int(p.orders["ids_begin"][-1])
+    cat["edge_order_begin"] = np.concatenate(ob + [np.array([o0])]).astype(np.uint64)
+    cat["ids_begin"] = np.concatenate(ib + [np.array([i0])]).astype(np.uint64)
+    assert orders_equal(Orders(**cat), reference.chain(paf)) == []

@@ -122,3 +122,27 @@ def test_oracle_sequences_vs_golden(oracle, label):
     for which, id_, l, r, direction, want in g["fetch"]:
         got = oracle.seq_fetch(by_id[which][id_], l, r, direction)
         assert (None if got is None else got.decode("latin-1")) == want, (label, which, id_, l, r, direction)
+
+
+def test_reference_chain_known_answer(reference):
+    """chainingAndOverlaps of the reference on the SURVEY §8c known-answer PAF (values recorded here; they pin the
+    driver that the GPU chaining tests compare against)."""
+    o = reference.chain(util.kat8_paf())
+    assert o.edge_shadow.tolist() == [0, 1, 1] and o.edge_order_begin.tolist() == [0, 1, 2, 4]
+    assert o.left.tolist() == [10401.0, 2600.0, 16001.0, 900.0] and o.right.tolist() == [15401.0, 600.0, 13001.0, 2100.0]
+    assert o.start_is_first.tolist() == [0, 1, 0, 1] and o.contained.tolist() == [0, 0, 0, 1]
+    assert o.score.tolist() == [3800, 573, 1670, 3215] and o.primary.tolist() == [1, 0, 0, 0]
+    assert o.ids.tolist() == [0, 0, 0, 1] and o.direction.tolist() == [0, 1, 0, 1]
+
+
+def test_reference_chain_small_digest(reference):
+    import hashlib
+    from muchsalsa_b200 import synth
+    o = reference.chain(synth.generate_paf("small"))
+    h = hashlib.sha256()
+    for f in ("edge_shadow", "edge_order_begin", "start_is_first", "left", "right", "contained", "direction", "primary",
+              "score", "ids_begin", "ids"):
+        h.update(np.ascontiguousarray(getattr(o, f)).tobytes())
+    g = util.load_golden("digests.json")["small"]
+    assert o.left.size == g["orders"] == 1465 and int(o.edge_shadow.sum()) == g["shadow_edges"] == 39
+    assert h.hexdigest() == g["orders_digest"]
