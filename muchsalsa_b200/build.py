@@ -25,6 +25,9 @@ NVCC_FLAGS = [
 ]
 
 
+NVCC_FLAGS += os.environ.get("MSGPU_NVCC_EXTRA", "").split()  # development experiments only (e.g. -DMSGPU_IDX_BITS=13)
+
+
 def _nvcc() -> str:
     for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if c and (os.path.sep not in c or os.path.exists(c)):

@@ -15,8 +15,16 @@
 // What the reference reads through MatchMap lookups is read here from the tables of the construction:
 //   getEdgeMatch(edge, unitig)     -> the edge's rows of the edge-match table (CSR)
 //   getVertexMatch(read, unitig)   -> binary search for `read` in the unitig's group of the pairing index (groups are
-//                                     ordered by read id), then the public match row through PairRow::orig
-//   getVertexMatches(read)         -> a per-read list of match rows ordered by (nanoporeRange, unitig), built here
+//                                     ordered by read id), done ONCE per edge match by chain_rows_kernel (every edge
+//                                     in parallel, no other state), which leaves the two positions next to the edge
+//                                     match; the fields come from a 32-byte row (one L2 sector) in pairing order
+//   getVertexMatches(read)         -> a per-read list of unitig ids ordered by (nanoporeRange, unitig), built here
+//
+// Three launches share the per-edge programme.  74 % of the edges at yeast scale hold ONE edge match: for them the
+// dynamic programme is the identity and chain_single_kernel does the whole job in registers.  Edges with 2..8 edge
+// matches go to the programme instantiated with 8-entry state arrays (they stay in L1), the rest to the 96-entry
+// instantiation; the two lists are filled by warp-aggregated appends, and every result is written at a position that
+// depends on the edge alone, so the output does not depend on the order of the lists.
 #include <string>
 
 #include "../../include/msgpu.h"
@@ -25,7 +33,31 @@
 
 namespace msgpu {
 
-constexpr int kChainMax = 96; // edge matches of ONE direction on one edge that the per-thread programme holds
+constexpr int kChainMax   = 96; // edge matches of ONE direction on one edge that the per-thread programme holds
+constexpr int kChainSmall = 8;  // edges with at most this many edge matches run the small instantiation
+
+// the fields of one VertexMatch the stage reads, in pairing order (grouped by unitig, by read id inside): 32 bytes
+struct __align__(16) VmRow {
+  int32_t  nr0, nr1, ir0, ir1;
+  double   rratio;
+  uint32_t flags, unitig;
+};
+
+__global__ void __launch_bounds__(256)
+    build_vm_rows_kernel(MatchSoA m, const PairRow *__restrict__ rows, VmRow *__restrict__ vm) {
+  for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < m.n; q += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t i = rows[q].orig;
+    VmRow          v;
+    v.nr0    = m.nr0[i];
+    v.nr1    = m.nr1[i];
+    v.ir0    = m.ir0[i];
+    v.ir1    = m.ir1[i];
+    v.rratio = m.rratio[i];
+    v.flags  = m.flags[i];
+    v.unitig = m.unitig[i];
+    vm[q]    = v;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // per-read match lists ordered by (nanoporeRange.first, nanoporeRange.second, unitig)   [mpp.cpp:253-273]
@@ -53,12 +85,12 @@ __device__ __forceinline__ bool nano_less(const MatchSoA &m, uint32_t a, uint32_
 
 __global__ void __launch_bounds__(256)
     read_order_kernel(MatchSoA m, const uint32_t *__restrict__ off, const uint32_t *__restrict__ tmp,
-                      uint32_t *__restrict__ list) {
+                      uint32_t *__restrict__ list_unitig) {
   for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < m.n; x += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t me = tmp[x], r = m.read[me], lo = off[r], hi = off[r + 1];
     uint32_t       rank = 0;
     for (uint32_t p = lo; p < hi; ++p) rank += nano_less(m, tmp[p], me) ? 1u : 0u;
-    list[lo + rank] = me; // (unitig ids are unique inside a read, so the order is total)
+    list_unitig[lo + rank] = m.unitig[me]; // (unitig ids are unique inside a read, so the order is total)
   }
 }
 
@@ -66,16 +98,18 @@ __global__ void __launch_bounds__(256)
 // the per-edge programme
 // ---------------------------------------------------------------------------------------------------------------------
 struct ChainArgs {
-  MatchSoA        m;
   const int32_t  *read_nlen;
   const uint32_t *grp_off;
-  const PairRow  *rows;
   const uint32_t *p_read;
-  const uint32_t *rm_off, *rm_list; // per-read ordered match lists
+  const VmRow    *vm;               // match fields in pairing order
+  const uint32_t *em_row1, *em_row2; // per edge match: position of the first / second vertex's match in `vm`
+  const uint32_t *rm_off, *rm_unitig; // per read: its unitig ids ordered by (nanoporeRange, unitig)
   EdgeTables      e;
   uint64_t        wiggle;
   OrderTables     out;
   unsigned int   *too_long;
+  uint32_t       *list_in, *list_out; // edges handed from one launch to the next
+  unsigned int   *n_in, *n_out;
 };
 
 struct Vm { // the fields of one VertexMatch the stage reads
@@ -84,24 +118,58 @@ struct Vm { // the fields of one VertexMatch the stage reads
   bool   dir;
 };
 
-__device__ __forceinline__ uint32_t find_match_row(const ChainArgs &a, uint32_t unitig, uint32_t read) {
-  uint32_t lo = a.grp_off[unitig], hi = a.grp_off[unitig + 1];
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (a.p_read[mid] < read) lo = mid + 1; else hi = mid;
-  }
-  return a.rows[lo].orig;
+__device__ __forceinline__ Vm load_vm(const ChainArgs &a, uint32_t pos) { // two 128-bit loads = one 32-byte sector
+  const uint4 *q = reinterpret_cast<const uint4 *>(a.vm + pos);
+  const uint4  x = __ldg(q), y = __ldg(q + 1);
+  Vm           v;
+  v.nr0    = int32_t(x.x);
+  v.nr1    = int32_t(x.y);
+  v.ir0    = int32_t(x.z);
+  v.ir1    = int32_t(x.w);
+  v.rratio = __hiloint2double(int(y.y), int(y.x));
+  v.dir    = (y.z & 1u) != 0;
+  return v;
 }
 
-__device__ __forceinline__ Vm load_vm(const ChainArgs &a, uint32_t row) {
-  Vm v;
-  v.nr0    = a.m.nr0[row];
-  v.nr1    = a.m.nr1[row];
-  v.ir0    = a.m.ir0[row];
-  v.ir1    = a.m.ir1[row];
-  v.rratio = a.m.rratio[row];
-  v.dir    = (a.m.flags[row] & 1) != 0;
-  return v;
+// getVertexMatch(read, unitig) for both vertices of every edge match: one thread per edge, nothing but the searches
+// (the group of a unitig is ordered by read id and first < second, so the second search starts behind the first hit)
+__global__ void __launch_bounds__(256)
+    chain_rows_kernel(EdgeTables e, const uint32_t *__restrict__ grp_off, const uint32_t *__restrict__ p_read,
+                      uint32_t *__restrict__ em_row1, uint32_t *__restrict__ em_row2) {
+  for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < e.n_edges;
+       x += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t v1 = e.first[x], v2 = e.second[x];
+    const uint64_t k0 = e.em_begin[x], k1 = e.em_begin[x + 1];
+    for (uint64_t k = k0; k < k1; ++k) {
+      const uint32_t u  = e.em_unitig[k];
+      const uint32_t g1 = grp_off[u + 1];
+      uint32_t       lo = grp_off[u], hi = g1;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p_read[mid] < v1) lo = mid + 1; else hi = mid;
+      }
+      em_row1[k] = lo;
+      ++lo;
+      hi = g1;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (p_read[mid] < v2) lo = mid + 1; else hi = mid;
+      }
+      em_row2[k] = lo;
+    }
+  }
+}
+
+// appends `x` to a list for the lanes that ask for it: one atomic per warp
+__device__ __forceinline__ void warp_append(bool want, uint32_t x, uint32_t *list, unsigned int *n) {
+  const unsigned act  = __activemask();
+  const unsigned mask = __ballot_sync(act, want);
+  if (!mask) return;
+  const unsigned l = threadIdx.x & 31, lead = __ffs(mask) - 1;
+  unsigned       base = 0;
+  if (l == lead) base = atomicAdd(n, unsigned(__popc(mask)));
+  base = __shfl_sync(act, base, lead);
+  if (want) list[base + __popc(mask & ((1u << l) - 1u))] = x;
 }
 
 // corrected nanopore interval of a vertex match under an edge match (mpp.cpp:50-69)
@@ -174,9 +242,9 @@ struct PathRes { // one entry of getMaxPairwisePaths' result
 };
 
 // getOverhangs (ol.cpp:31-50)
-__device__ __forceinline__ void overhangs(const ChainArgs &a, uint32_t vertex, uint32_t row, int ov0, int ov1,
+__device__ __forceinline__ void overhangs(const ChainArgs &a, uint32_t vertex, uint32_t pos, int ov0, int ov1,
                                           double *left, double *right) {
-  const Vm v   = load_vm(a, row);
+  const Vm v   = load_vm(a, pos);
   double   ncl = __ddiv_rn(double(ov0 - v.ir0), v.rratio);
   double   ncr = __ddiv_rn(double(v.ir1 - ov1), v.rratio);
   if (!v.dir) {
@@ -188,23 +256,22 @@ __device__ __forceinline__ void overhangs(const ChainArgs &a, uint32_t vertex, u
   *right = __dadd_rn(double(a.read_nlen[vertex] - v.nr1), ncr);
 }
 
-__global__ void __launch_bounds__(128) chain_edges_kernel(ChainArgs a) {
-  const MatchSoA &m = a.m;
-  for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < a.e.n_edges;
-       e += uint64_t(gridDim.x) * blockDim.x) {
+// the whole job of one edge, with state arrays of kCap entries per direction
+template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainArgs &a, uint64_t e) {
+  {
     const uint32_t v1 = a.e.first[e], v2 = a.e.second[e];
     const uint64_t k0 = a.e.em_begin[e], k1 = a.e.em_begin[e + 1];
 
     // results of the two directions: [0] minus (direction false), [1] plus; main.cpp:352-353
-    PathRes  res[2][kChainMax];
+    PathRes  res[2][kCap];
     int      n_res[2] = {0, 0};
-    EmState  st[kChainMax];
-    double   pop[kChainMax];
-    int      pred[kChainMax];
+    EmState  st[kCap];
+    double   pop[kCap];
+    int      pred[kCap];
     // path members per (direction, population entry) are re-derived by walking `pred`; after the first direction is
     // done its paths are frozen as lists of edge-match rows
-    uint32_t path_rows[2][kChainMax]; // concatenated paths of the results of a direction, in result order
-    int      path_off[2][kChainMax + 1];
+    uint32_t path_rows[2][kCap]; // concatenated paths of the results of a direction, in result order
+    int      path_off[2][kCap + 1];
     bool     overflow = false;
 
     for (int d = 0; d < 2; ++d) {
@@ -213,15 +280,15 @@ __global__ void __launch_bounds__(128) chain_edges_kernel(ChainArgs a) {
       int n = 0;
       for (uint64_t k = k0; k < k1; ++k) {
         if (((a.e.em_flags[k] & 1) != 0) != direction) continue;
-        if (n == kChainMax) {
+        if (n == kCap) {
           overflow = true;
           break;
         }
         EmState s;
         s.k      = uint32_t(k - k0);
         s.unitig = a.e.em_unitig[k];
-        s.row1   = find_match_row(a, s.unitig, v1);
-        s.row2   = find_match_row(a, s.unitig, v2);
+        s.row1   = a.em_row1[k];
+        s.row2   = a.em_row2[k];
         s.score  = a.e.em_score[k];
         s.prim   = (a.e.em_flags[k] & 2) != 0;
         const Vm  w1 = load_vm(a, s.row1), w2 = load_vm(a, s.row2);
@@ -289,7 +356,7 @@ __global__ void __launch_bounds__(128) chain_edges_kernel(ChainArgs a) {
           max_it  = i;
           max_val = pop[i];
         }
-      unsigned long long used[2] = {0ull, 0ull}; // population entries on any accepted path (kChainMax <= 128)
+      unsigned long long used[2] = {0ull, 0ull}; // population entries on any accepted path (kCap <= 128)
       int                nr = 0;
       {
         bool prim = false;
@@ -317,9 +384,9 @@ __global__ void __launch_bounds__(128) chain_edges_kernel(ChainArgs a) {
       // ---- a single primary path may still be a shadow (mpp.cpp:245-302)
       if (nr == 1 && res[d][0].prim) {
         const uint32_t s0 = a.rm_off[v1], s1 = a.rm_off[v1 + 1], e0 = a.rm_off[v2], e1 = a.rm_off[v2 + 1];
-        auto start_id = [&](uint32_t i) { return m.unitig[a.rm_list[s0 + i]]; };
+        auto start_id = [&](uint32_t i) { return a.rm_unitig[s0 + i]; };
         auto end_id   = [&](uint32_t i) { // vIDsEnd, reversed when !direction (mpp.cpp:273)
-          return m.unitig[a.rm_list[direction ? e0 + i : e1 - 1 - i]];
+          return a.rm_unitig[direction ? e0 + i : e1 - 1 - i];
         };
         const uint32_t ns = s1 - s0, ne = e1 - e0;
         // the path in order: walk back from the tail, then read it forwards
@@ -368,11 +435,11 @@ __global__ void __launch_bounds__(128) chain_edges_kernel(ChainArgs a) {
       *a.too_long            = 1;
       a.out.edge_n_orders[e] = 0;
       a.out.edge_shadow[e]   = 0;
-      continue;
+      return;
     }
 
     // ---- chainingAndOverlaps' selection (main.cpp:355-397); keep[] marks the paths that survive
-    bool keep[2][kChainMax];
+    bool keep[2][kCap];
     bool has_primary = false, has_multi = false;
     for (int d = 0; d < 2; ++d)
       for (int r = 0; r < n_res[d]; ++r) {
@@ -409,12 +476,11 @@ __global__ void __launch_bounds__(128) chain_edges_kernel(ChainArgs a) {
         const int      len = res[d][r].tail;
         const uint32_t *pr = path_rows[d] + path_off[d][r];
         const uint64_t kf = k0 + pr[0], kl = k0 + pr[len - 1]; // first / last id of the path
-        const uint32_t uf = a.e.em_unitig[kf], ul = a.e.em_unitig[kl];
         double lf1, rf1, ll1, rl1, lf2, rf2, ll2, rl2; // overhangs of (first id | last id) on (first | second vertex)
-        overhangs(a, v1, find_match_row(a, uf, v1), a.e.em_ov0[kf], a.e.em_ov1[kf], &lf1, &rf1);
-        overhangs(a, v1, find_match_row(a, ul, v1), a.e.em_ov0[kl], a.e.em_ov1[kl], &ll1, &rl1);
-        overhangs(a, v2, find_match_row(a, uf, v2), a.e.em_ov0[kf], a.e.em_ov1[kf], &lf2, &rf2);
-        overhangs(a, v2, find_match_row(a, ul, v2), a.e.em_ov0[kl], a.e.em_ov1[kl], &ll2, &rl2);
+        overhangs(a, v1, a.em_row1[kf], a.e.em_ov0[kf], a.e.em_ov1[kf], &lf1, &rf1);
+        overhangs(a, v1, a.em_row1[kl], a.e.em_ov0[kl], a.e.em_ov1[kl], &ll1, &rl1);
+        overhangs(a, v2, a.em_row2[kf], a.e.em_ov0[kf], a.e.em_ov1[kf], &lf2, &rf2);
+        overhangs(a, v2, a.em_row2[kl], a.e.em_ov0[kl], a.e.em_ov1[kl], &ll2, &rl2);
         const double lo1 = lf1, ro1 = rl1;
         double       lo2 = lf2, ro2 = rl2;
         if (!direction) {
@@ -456,6 +522,98 @@ __global__ void __launch_bounds__(128) chain_edges_kernel(ChainArgs a) {
       }
     }
     a.out.edge_n_orders[e] = n_ord;
+  }
+}
+
+// Edges with ONE edge match (the common case).  With a single candidate getMaxPairwisePaths' programme is the
+// identity: the population is the match's own score (mpp.cpp:177-181), the maximum search starts from 0.0 so a
+// non-positive score yields 0 (mpp.cpp:201-208), the only runner-up shares the entry and is dropped (mpp.cpp:219-243),
+// the shadow test walks a path of length one (mpp.cpp:245-302), chainingAndOverlaps' filters keep the single path
+// (main.cpp:355-397) and the order comes from one getOverlap (ol.cpp:53-101).  Everything else is handed on.
+__global__ void __launch_bounds__(256) chain_single_kernel(ChainArgs a) {
+  for (uint64_t base = uint64_t(blockIdx.x) * blockDim.x; base < a.e.n_edges; base += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t e    = base + threadIdx.x;
+    const bool     live = e < a.e.n_edges;
+    uint64_t       k0 = 0, k1 = 0;
+    if (live) {
+      k0 = a.e.em_begin[e];
+      k1 = a.e.em_begin[e + 1];
+    }
+    warp_append(live && k1 - k0 != 1, uint32_t(e), a.list_out, a.n_out);
+    if (!live || k1 - k0 != 1) continue;
+    const uint32_t v1 = a.e.first[e], v2 = a.e.second[e];
+    const uint8_t  fl = a.e.em_flags[k0];
+    const bool     direction = (fl & 1) != 0;
+    bool           prim      = (fl & 2) != 0;
+    const uint32_t id        = a.e.em_unitig[k0];
+    const double   sc        = a.e.em_score[k0];
+    const double   max_val   = sc > 0.0 ? sc : 0.0;
+    if (prim) { // mpp.cpp:245-302 for a path of one id
+      const uint32_t s0 = a.rm_off[v1], ns = a.rm_off[v1 + 1] - s0, e0 = a.rm_off[v2], ne = a.rm_off[v2 + 1] - e0;
+      auto start_id = [&](uint32_t i) { return a.rm_unitig[s0 + i]; };
+      auto end_id   = [&](uint32_t i) { return a.rm_unitig[direction ? e0 + i : e0 + ne - 1 - i]; };
+      if ((start_id(0) != id && end_id(0) != id) || (start_id(ns - 1) != id && end_id(ne - 1) != id)) {
+        prim = false;
+      } else {
+        uint32_t ps = 0, pe = 0;
+        while (ps < ns && start_id(ps) != id) ++ps;
+        while (pe < ne && end_id(pe) != id) ++pe;
+        if (ps > 0 && pe > 0) prim = false;
+      }
+    }
+    a.out.edge_shadow[e] = prim ? 0 : 1;
+    const int ov0 = a.e.em_ov0[k0], ov1 = a.e.em_ov1[k0];
+    double    l1, r1, l2, r2;
+    overhangs(a, v1, a.em_row1[k0], ov0, ov1, &l1, &r1);
+    overhangs(a, v2, a.em_row2[k0], ov0, ov1, &l2, &r2);
+    const double lo1 = l1, ro1 = r1, lo2 = direction ? l2 : r2, ro2 = direction ? r2 : l2;
+    bool   have = true, start_first = true, contained = true;
+    double left = 0.0, right = 0.0;
+    if (lo1 <= lo2 && ro1 <= ro2) {
+      left  = __dsub_rn(lo2, lo1);
+      right = __dsub_rn(ro2, ro1);
+    } else if (lo1 >= lo2 && ro1 >= ro2) {
+      start_first = false;
+      left        = __dsub_rn(lo1, lo2);
+      right       = __dsub_rn(ro1, ro2);
+    } else if (lo1 > lo2 && ro1 < ro2) {
+      contained = false;
+      left      = __dsub_rn(lo1, lo2);
+      right     = __dsub_rn(ro2, ro1);
+    } else if (lo1 < lo2 && ro1 > ro2) {
+      start_first = false;
+      contained   = false;
+      left        = __dsub_rn(lo2, lo1);
+      right       = __dsub_rn(ro1, ro2);
+    } else {
+      have = false; // NaNs only
+    }
+    if (have) {
+      a.out.left[k0]  = left;
+      a.out.right[k0] = right;
+      a.out.score[k0] = double_to_size_t(max_val);
+      a.out.n_ids[k0] = 1;
+      a.out.flags[k0] = uint8_t((start_first ? 1 : 0) | (contained ? 2 : 0) | (direction ? 4 : 0) | (prim ? 8 : 0));
+      a.out.ids[k0]   = id;
+    }
+    a.out.edge_n_orders[e] = have ? 1u : 0u;
+  }
+}
+
+// the edges of a list through the programme with kCap-entry arrays; longer edges are handed on (kHandOn)
+template <int kCap, bool kHandOn> __global__ void __launch_bounds__(128) chain_list_kernel(ChainArgs a) {
+  const uint64_t n = *a.n_in;
+  for (uint64_t base = uint64_t(blockIdx.x) * blockDim.x; base < n; base += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t x    = base + threadIdx.x;
+    const bool     live = x < n;
+    const uint32_t e    = live ? a.list_in[x] : 0u;
+    bool           mine = live;
+    if (kHandOn) {
+      const bool big = live && a.e.em_begin[e + 1] - a.e.em_begin[e] > uint64_t(kCap);
+      warp_append(big, e, a.list_out, a.n_out);
+      mine = live && !big;
+    }
+    if (mine) chain_one_edge<kCap>(a, e);
   }
 }
 
@@ -501,19 +659,48 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
   MSGPU_CUDA(cudaMemsetAsync(out.ids, 0, EM * sizeof(uint32_t), st));
   MSGPU_CUDA(cudaMemsetAsync(out.flags, 0, EM, st));
 
+  // match fields in pairing order, and the position of both vertices' matches for every edge match
+  VmRow    *vm      = arena.alloc<VmRow>(M);
+  uint32_t *em_row1 = arena.alloc<uint32_t>(EM), *em_row2 = arena.alloc<uint32_t>(EM);
+  if (M) MSGPU_LAUNCH("build_vm_rows", st, build_vm_rows_kernel<<<gm, 256, 0, st>>>(m, e.pair_rows, vm));
+  if (E) MSGPU_LAUNCH("chain_rows", st, chain_rows_kernel<<<grid_for(E, 256, 64), 256, 0, st>>>(e, unitigs.grp_off, e.p_read, em_row1, em_row2));
+
+  if (E >= 0xffffffffull) throw BuildError{MSGPU_ERR_LIMIT, "chaining supports < 2^32 edges per device"};
+  uint32_t     *multi = arena.alloc<uint32_t>(E), *big = arena.alloc<uint32_t>(E);
+  unsigned int *d_cnt = arena.alloc<unsigned int>(2);
+  MSGPU_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned int), st));
+
   ChainArgs a;
-  a.m         = m;
   a.read_nlen = reads.nlen;
   a.grp_off   = unitigs.grp_off;
-  a.rows      = e.pair_rows;
   a.p_read    = e.p_read;
+  a.vm        = vm;
+  a.em_row1   = em_row1;
+  a.em_row2   = em_row2;
   a.rm_off    = rm_off;
-  a.rm_list   = list;
+  a.rm_unitig = list;
   a.e         = e;
   a.wiggle    = wiggle_room;
   a.out       = out;
   a.too_long  = d_tot + 1;
-  if (E) MSGPU_LAUNCH("chain_edges", st, chain_edges_kernel<<<grid_for(E, 128), 128, 0, st>>>(a));
+  if (E) {
+    a.list_in  = nullptr;
+    a.n_in     = nullptr;
+    a.list_out = multi;
+    a.n_out    = d_cnt + 0;
+    MSGPU_LAUNCH("chain_single", st, chain_single_kernel<<<grid_for(E, 256, 64), 256, 0, st>>>(a));
+    // the lists are sized on the device; the grids are bounded by E and stride over what is there
+    a.list_in  = multi;
+    a.n_in     = d_cnt + 0;
+    a.list_out = big;
+    a.n_out    = d_cnt + 1;
+    MSGPU_LAUNCH("chain_small", st, (chain_list_kernel<kChainSmall, true><<<grid_for(E, 128, 16), 128, 0, st>>>(a)));
+    a.list_in  = big;
+    a.n_in     = d_cnt + 1;
+    a.list_out = nullptr;
+    a.n_out    = nullptr;
+    MSGPU_LAUNCH("chain_large", st, (chain_list_kernel<kChainMax, false><<<grid_for(E, 128, 4), 128, 0, st>>>(a)));
+  }
   MSGPU_CUDA(cudaEventRecord(ev1, st));
   uint32_t h[2];
   MSGPU_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -42,6 +42,30 @@ public:
     m_used = m_high = 0;
     if (m_counter) cudaFree(m_counter);
     m_counter = nullptr;
+    if (m_scan_state) cudaFree(m_scan_state);
+    m_scan_state       = nullptr;
+    m_scan_state_bytes = 0;
+  }
+  // Status words of the single-pass scans (scan.cuh): a region that outlives reset() and that nothing else writes.
+  // Every call hands out the next epoch; flags written under an older epoch read as "not ready", so the region is
+  // cleared only when it grows or when the 16-bit epoch wraps.
+  void *scan_state(size_t bytes, cudaStream_t st, unsigned *epoch) {
+    if (bytes > m_scan_state_bytes) {
+      if (m_scan_state) {
+        MSGPU_CUDA(cudaStreamSynchronize(st));
+        cudaFree(m_scan_state);
+      }
+      m_scan_state_bytes = bytes < (size_t(1) << 20) ? (size_t(1) << 20) : bytes * 2;
+      MSGPU_CUDA(cudaMalloc(&m_scan_state, m_scan_state_bytes));
+      MSGPU_CUDA(cudaMemsetAsync(m_scan_state, 0, m_scan_state_bytes, st));
+      m_epoch = 0;
+    }
+    if (++m_epoch >= (1u << 16)) {
+      MSGPU_CUDA(cudaMemsetAsync(m_scan_state, 0, m_scan_state_bytes, st));
+      m_epoch = 1;
+    }
+    *epoch = m_epoch;
+    return m_scan_state;
   }
   // a zero-initialised device counter that outlives reset(): kernels that use it leave it at zero again
   unsigned *counter() {
@@ -94,6 +118,9 @@ private:
   std::vector<Slab> m_slabs;
   size_t            m_used = 0, m_high = 0;
   unsigned         *m_counter = nullptr;
+  void             *m_scan_state = nullptr;
+  size_t            m_scan_state_bytes = 0;
+  unsigned          m_epoch = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -47,12 +47,16 @@ constexpr int kThOverlapF = 100; // MatchMap.cpp:41
 
 constexpr int      kFusedBlock = 512;
 constexpr int      kFusedWarps = kFusedBlock / 32;
-constexpr int      kIdxBits    = 12;
+#ifndef MSGPU_IDX_BITS
+#define MSGPU_IDX_BITS 12
+#endif
+constexpr int      kIdxBits    = MSGPU_IDX_BITS;
 constexpr uint32_t kTileCap    = 1u << kIdxBits; // candidates per tile
 constexpr uint32_t kSrcCap     = 512;            // sources per tile
 constexpr uint32_t kHalfCap    = kTileCap / 2;
 constexpr uint32_t kSrcRatio   = kHalfCap / (kSrcCap / 2); // a source weighs at least this much when tiles are packed
 constexpr int      kItems      = kTileCap / kFusedBlock;   // sort items per thread
+constexpr int      kMergeCtas  = kIdxBits <= 12 ? 3 : 2;    // resident CTAs of the merge kernel per SM (narrow words)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // pre-pass 1: order every group by read id, build the pair rows, and accumulate per read its number of sources and
@@ -546,7 +550,7 @@ __device__ __forceinline__ void tile_tail(const TileArgs &a, TileShared &s, W *w
   }
 }
 
-template <bool kExpMatch> __global__ void __launch_bounds__(kFusedBlock, 2) pair_tiles_kernel(TileArgs a) {
+template <bool kExpMatch> __global__ void __launch_bounds__(kFusedBlock, kIdxBits <= 12 ? 2 : 1) pair_tiles_kernel(TileArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileShared    &s = *reinterpret_cast<TileShared *>(smem_raw);
   const unsigned t = threadIdx.x, l = t & 31;
@@ -831,7 +835,7 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
   }
 }
 
-__global__ void __launch_bounds__(kFusedBlock, 3) pair_tiles_merge_kernel(TileArgs a) {
+__global__ void __launch_bounds__(kFusedBlock, kMergeCtas) pair_tiles_merge_kernel(TileArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MergeShared   &s = *reinterpret_cast<MergeShared *>(smem_raw);
   const unsigned t = threadIdx.x, l = t & 31;
@@ -1193,7 +1197,7 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
       }
       // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits
       a.wide = R > (1ull << (32 - kIdxBits)) ? 1u : 0u;
-      grid   = kNumSMs * (a.wide ? 2 : 3) * 4; // 40 registers, 51 KB (narrow): three resident CTAs per SM
+      grid   = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * 4; // 40 registers, 51 KB (narrow): three resident CTAs per SM
       if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
       MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
     }
