@@ -267,13 +267,16 @@ def run_ours(args):
 
     # ---- the stage that consumes the tables while they are in HBM (chaining + overlaps per edge);
     # reported beside the metric, not part of it.  Device time from the library's own events.
-    chain_ms = []
+    chain_ms, filter_ms = [], []
     for it in range(min(args.steps, 3) + 1):
         step_device()
         gb.chain_overlaps(300)
+        gb.edge_filters(300)
         if it:  # the first call grows the arena (cudaMalloc inside the timed span): warm-up
             chain_ms.append(gb.chain_ms())
+            filter_ms.append(gb.edge_filters_ms())
     chain_t = reduce(sum(chain_ms) / len(chain_ms), "MAX")
+    filter_t = reduce(sum(filter_ms) / len(filter_ms), "MAX")
 
     # ---- the reference's CPU path beside it (bounded sample, rank 0 at N = 1 only)
     cpu = cpu_baseline(args.workload) if world == 1 else None
@@ -308,6 +311,12 @@ def run_ours(args):
                 "device-resident edge tables; bit-exact vs the reference (tests/test_chain_gpu.py)",
         "ms": round(chain_t, 3), "edges_per_s": n_edges / chain_t * 1e3,
         "cpu_reference": (cpu or {}).get("chain")}
+    out["edge_filters"] = {
+        "what": "per-edge findContractionEdges (+ sanityCheck), findDeletableEdges, computeBitweight "
+                "(src/main.cpp:416-460, 534-573, sc.cpp) on the device-resident order tables; identical to the "
+                "reference (tests/test_filters_gpu.py)",
+        "ms": round(filter_t, 3), "edges_per_s": n_edges / filter_t * 1e3,
+        "cpu_reference": ((cpu or {}).get("chain") or {}).get("filters")}
     if world > 1:
         x = [v for v in xch_ms if v is not None]
         x_ms = reduce(sum(x) / len(x), "MAX") if x else None
@@ -376,7 +385,9 @@ def cpu_baseline(workload, steps=1):
             if p.returncode == 0:
                 c = json.loads(p.stdout.strip().splitlines()[-1])
                 chain = {"edges_per_s": c["n_edges"] / c["t_chain"], "seconds": round(c["t_chain"], 3), "cores": 1,
-                         "edges": c["n_edges"], "sample": sample}
+                         "edges": c["n_edges"], "sample": sample,
+                         "filters": {"edges_per_s": c["n_edges"] / max(c["t_filters"], 1e-9),
+                                     "seconds": round(c["t_filters"], 3)}}
         except Exception as e:  # the baseline must not take the bench down
             chain = {"error": repr(e)}
         return {"chain": chain, "value": res["n_vm"] / t, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,

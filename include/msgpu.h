@@ -201,6 +201,34 @@ int msgpu_orders_host(msgpu_ctx *ctx, msgpu_orders *out); /* pinned host copy, v
 /* device time of the last msgpu_chain_overlaps, milliseconds */
 int msgpu_chain_ms(const msgpu_ctx *ctx, float *out);
 
+/* ---- per-edge passes after chaining (optional; they read the orders of the last msgpu_chain_overlaps in HBM) ---------
+ * msgpu_edge_filters  replaces, for every edge, the job bodies
+ *   findContractionEdges (src/main.cpp:416-460, with sanityCheck of libms/src/kernel/sc.cpp:29-88):
+ *       contraction_order[e] = index, among the orders of edge e, of the first contained primary order whose start
+ *       vertex passes the sanity test against every non-shadow neighbour edge; -1 if none (the edge is not a
+ *       contraction edge).  The value the reference stores is &order, i.e. orders[index].
+ *   findDeletableEdges (src/main.cpp:534-550): the contained orders are dropped (Edge::replaceOrders);
+ *       n_kept_orders[e] = orders left, in their old relative order (they are the slots with ord_flags bit1 clear);
+ *       deletable[e] = 1 iff none is left.
+ *   computeBitweight (src/main.cpp:552-573) on the orders that are left: weight[e] (Edge::setWeight, 0 if untouched)
+ *       and consensus[e] = 'a' e_POS / 'b' e_NEG / 'c' e_NONE (Direction.h:41).
+ * The bookkeeping between these jobs (findContractionTargets, findDeletableVertices, contract: main.cpp:462-531) stays
+ * on the host: it depends on the iteration order of a pointer-keyed unordered_map.  Deleting vertices in between
+ * removes edges but does not change the verdict on an edge that survives. */
+typedef struct msgpu_edge_filter_tables {
+  uint64_t        n_edges;
+  const int32_t  *contraction_order;
+  const uint8_t  *deletable;
+  const uint32_t *n_kept_orders;
+  const uint64_t *weight;
+  const uint8_t  *consensus;
+} msgpu_edge_filter_tables;
+
+int msgpu_edge_filters(msgpu_ctx *ctx, uint64_t wiggle_room);
+int msgpu_edge_filters_device(const msgpu_ctx *ctx, msgpu_edge_filter_tables *out);
+int msgpu_edge_filters_host(msgpu_ctx *ctx, msgpu_edge_filter_tables *out); /* pinned host copy */
+int msgpu_edge_filters_ms(const msgpu_ctx *ctx, float *out); /* device time of the last msgpu_edge_filters, ms */
+
 /* Device time of the stages of the last build, milliseconds (CUDA events on the context's stream). */
 typedef struct msgpu_timings {
   float h2d_ms, ingest_ms, pair_ms, merge_ms, d2h_ms, total_ms;

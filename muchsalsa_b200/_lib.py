@@ -55,6 +55,11 @@ class Orders(C.Structure):
                 ("ord_ids", u32p)]
 
 
+class EdgeFilters(C.Structure):
+    _fields_ = [("n_edges", C.c_uint64), ("contraction_order", C.POINTER(C.c_int32)), ("deletable", u8p),
+                ("n_kept_orders", u32p), ("weight", u64p), ("consensus", u8p)]
+
+
 class SeqReq(C.Structure):
     _fields_ = [("which", C.c_uint32), ("id", C.c_uint32), ("left", C.c_int32), ("right", C.c_int32),
                 ("direction", C.c_uint32)]
@@ -84,6 +89,10 @@ SIGNATURES = {
     "msgpu_orders_device": (C.c_int, [C.c_void_p, C.POINTER(Orders)]),
     "msgpu_orders_host": (C.c_int, [C.c_void_p, C.POINTER(Orders)]),
     "msgpu_chain_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "msgpu_edge_filters": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "msgpu_edge_filters_device": (C.c_int, [C.c_void_p, C.POINTER(EdgeFilters)]),
+    "msgpu_edge_filters_host": (C.c_int, [C.c_void_p, C.POINTER(EdgeFilters)]),
+    "msgpu_edge_filters_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "msgpu_result_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "msgpu_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "msgpu_profile_read": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -248,6 +248,27 @@ class GraphBuilder:
                     score=_np(o.ord_score, S, np.uint64)[slot], ids_begin=ids_begin.astype(np.uint64),
                     ids=_np(o.ord_ids, S, np.uint32)[id_slot])
 
+    # ---- per-edge passes after chaining
+    def edge_filters(self, wiggle_room: int = 300):
+        """findContractionEdges, findDeletableEdges and computeBitweight for every edge of the last chaining
+        (src/main.cpp:416-460, 534-573)."""
+        self._check(self._lib.msgpu_edge_filters(self._h, wiggle_room))
+        return self
+
+    def edge_filters_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.msgpu_edge_filters_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def filters(self) -> dict:
+        """Host copy of the per-edge verdicts, edges in table order."""
+        f = _lib.EdgeFilters()
+        self._check(self._lib.msgpu_edge_filters_host(self._h, C.byref(f)))
+        E = int(f.n_edges)
+        return dict(contraction_order=_np(f.contraction_order, E, np.int32), deletable=_np(f.deletable, E, np.uint8),
+                    n_kept_orders=_np(f.n_kept_orders, E, np.uint32), weight=_np(f.weight, E, np.uint64),
+                    consensus=_np(f.consensus, E, np.uint8))
+
     # ---- sequences
     def seq_load(self, unitigs_path, nanopore_path):
         self._check(self._lib.msgpu_seq_load(self._h, os.fspath(unitigs_path).encode(),

@@ -56,6 +56,17 @@ struct OrderTables {
   uint64_t  n_orders = 0;
 };
 
+// per-edge verdicts of the passes that follow chaining (filter.cu; see msgpu_edge_filters in include/msgpu.h)
+struct FilterTables {
+  bool      valid   = false;
+  uint64_t  n_edges = 0;
+  int32_t  *contraction = nullptr;
+  uint8_t  *deletable   = nullptr;
+  uint32_t *n_kept      = nullptr;
+  uint64_t *weight      = nullptr;
+  uint8_t  *consensus   = nullptr;
+};
+
 struct EdgeTables {
   uint64_t  n_pairs = 0;
   uint64_t  n_edges = 0;
@@ -121,5 +132,10 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
 void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, const UnitigTable &unitigs,
                         const MatchSoA &matches, const EdgeTables &edges, uint64_t wiggle_room, OrderTables &out,
                         float *ms_out);
+
+// filter.cu : the per-edge passes after chaining — findContractionEdges (+ sanityCheck), findDeletableEdges,
+// computeBitweight (src/main.cpp:416-460, 534-573, sc.cpp:29-88)
+void run_edge_filters(Arena &arena, cudaStream_t st, uint64_t n_reads, const EdgeTables &edges, const OrderTables &orders,
+                      uint64_t wiggle_room, FilterTables &out, float *ms_out);
 
 } // namespace msgpu

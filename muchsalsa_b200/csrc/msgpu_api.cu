@@ -69,6 +69,12 @@ struct msgpu_ctx {
   bool         orders_host_valid = false;
   msgpu_orders host_orders_view{};
 
+  FilterTables             filters; // msgpu_edge_filters
+  float                    filter_ms = 0.f;
+  PinnedBuf                host_filters;
+  bool                     filters_host_valid = false;
+  msgpu_edge_filter_tables host_filters_view{};
+
   SeqStore *seq = nullptr;
   Profiler  profiler;
 };
@@ -126,6 +132,7 @@ void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes, bool pair =
   ctx->have_result = false;
   ctx->host_valid  = false;
   ctx->orders      = OrderTables{};
+    ctx->filters     = FilterTables{};
   ctx->arena.reset();
   ctx->profiler.clear();
   MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
@@ -262,6 +269,7 @@ int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t 
     ctx->have_result = false;
     ctx->host_valid  = false;
     ctx->orders      = OrderTables{};
+    ctx->filters     = FilterTables{};
     ctx->arena.reset();
     ctx->profiler.clear();
     ctx->reads   = ReadTable{};
@@ -335,6 +343,7 @@ int msgpu_build_from_shards(msgpu_ctx *ctx, uint32_t n_shards, const msgpu_shard
     ctx->have_result = false;
     ctx->host_valid  = false;
     ctx->orders      = OrderTables{};
+    ctx->filters     = FilterTables{};
     ctx->arena.reset();
     ctx->profiler.clear();
     MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
@@ -472,8 +481,10 @@ int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out) {
 int msgpu_chain_overlaps(msgpu_ctx *ctx, uint64_t wiggle_room) {
   return guarded(ctx, [&] {
     if (!ctx->have_result) throw BuildError{MSGPU_ERR_NO_RESULT, "no construction to chain"};
-    ctx->orders            = OrderTables{};
-    ctx->orders_host_valid = false;
+    ctx->orders             = OrderTables{};
+    ctx->orders_host_valid  = false;
+    ctx->filters            = FilterTables{};
+    ctx->filters_host_valid = false;
     ctx->profiler.clear();
     run_chain_overlaps(ctx->arena, ctx->stream, ctx->reads, ctx->unitigs, ctx->matches, ctx->edges, wiggle_room,
                        ctx->orders, &ctx->chain_ms);
@@ -545,6 +556,75 @@ int msgpu_chain_ms(const msgpu_ctx *ctx, float *out) {
   if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
   if (!ctx->orders.valid) return MSGPU_ERR_NO_RESULT;
   *out = ctx->chain_ms;
+  return MSGPU_OK;
+}
+
+int msgpu_edge_filters(msgpu_ctx *ctx, uint64_t wiggle_room) {
+  return guarded(ctx, [&] {
+    if (!ctx->have_result || !ctx->orders.valid)
+      throw BuildError{MSGPU_ERR_NO_RESULT, "the edge filters need msgpu_chain_overlaps first"};
+    ctx->filters            = FilterTables{};
+    ctx->filters_host_valid = false;
+    ctx->profiler.clear();
+    run_edge_filters(ctx->arena, ctx->stream, ctx->reads.n, ctx->edges, ctx->orders, wiggle_room, ctx->filters,
+                     &ctx->filter_ms);
+  });
+}
+
+int msgpu_edge_filters_device(const msgpu_ctx *ctx, msgpu_edge_filter_tables *o) {
+  if (!ctx || !o) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->have_result || !ctx->filters.valid) return MSGPU_ERR_NO_RESULT;
+  o->n_edges           = ctx->filters.n_edges;
+  o->contraction_order = ctx->filters.contraction;
+  o->deletable         = ctx->filters.deletable;
+  o->n_kept_orders     = ctx->filters.n_kept;
+  o->weight            = ctx->filters.weight;
+  o->consensus         = ctx->filters.consensus;
+  return MSGPU_OK;
+}
+
+int msgpu_edge_filters_host(msgpu_ctx *ctx, msgpu_edge_filter_tables *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->have_result || !ctx->filters.valid) return MSGPU_ERR_NO_RESULT;
+  if (ctx->filters_host_valid) {
+    *out = ctx->host_filters_view;
+    return MSGPU_OK;
+  }
+  return guarded(ctx, [&] {
+    msgpu_edge_filter_tables d;
+    msgpu_edge_filters_device(ctx, &d);
+    const uint64_t E   = d.n_edges;
+    size_t         off = 0;
+    const size_t a_c = slab_reserve<int32_t>(off, E), a_d = slab_reserve<uint8_t>(off, E),
+                 a_k = slab_reserve<uint32_t>(off, E), a_w = slab_reserve<uint64_t>(off, E),
+                 a_s = slab_reserve<uint8_t>(off, E);
+    char        *slab = static_cast<char *>(ctx->host_filters.get(off + 64));
+    cudaStream_t st   = ctx->stream;
+    auto copy = [&](size_t at, const void *src, size_t bytes) {
+      if (bytes) MSGPU_CUDA(cudaMemcpyAsync(slab + at, src, bytes, cudaMemcpyDeviceToHost, st));
+    };
+    copy(a_c, d.contraction_order, E * 4);
+    copy(a_d, d.deletable, E);
+    copy(a_k, d.n_kept_orders, E * 4);
+    copy(a_w, d.weight, E * 8);
+    copy(a_s, d.consensus, E);
+    MSGPU_CUDA(cudaStreamSynchronize(st));
+    msgpu_edge_filter_tables &h = ctx->host_filters_view;
+    h                   = d;
+    h.contraction_order = reinterpret_cast<const int32_t *>(slab + a_c);
+    h.deletable         = reinterpret_cast<const uint8_t *>(slab + a_d);
+    h.n_kept_orders     = reinterpret_cast<const uint32_t *>(slab + a_k);
+    h.weight            = reinterpret_cast<const uint64_t *>(slab + a_w);
+    h.consensus         = reinterpret_cast<const uint8_t *>(slab + a_s);
+    ctx->filters_host_valid = true;
+    *out                    = h;
+  });
+}
+
+int msgpu_edge_filters_ms(const msgpu_ctx *ctx, float *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  if (!ctx->filters.valid) return MSGPU_ERR_NO_RESULT;
+  *out = ctx->filter_ms;
   return MSGPU_OK;
 }
 

@@ -94,6 +94,22 @@ typedef struct ms_orders {
 
 void ms_orders_free(ms_orders *o);
 
+/* Per-edge verdicts of the jobs that follow chaining (src/main.cpp:416-460, 534-573), edges in (first, second) order:
+ * the order findContractionEdges selects (index into the edge's order list BEFORE filtering, -1 none), whether
+ * findDeletableEdges marks the edge, the orders it leaves, and what computeBitweight then sets. */
+typedef struct ms_filters {
+  uint64_t  n_edges;
+  int32_t  *contraction_order;
+  uint8_t  *deletable;
+  uint32_t *n_kept_orders;
+  uint64_t *weight;
+  uint8_t  *consensus; /* Direction::Enum as char: 'a' e_POS, 'b' e_NEG, 'c' e_NONE */
+  double    t_filters; /* wall-clock seconds of the three passes */
+  double    t_chain;   /* wall-clock seconds of chainingAndOverlaps before them */
+} ms_filters;
+
+void ms_filters_free(ms_filters *f);
+
 #ifdef __cplusplus
 }
 #endif

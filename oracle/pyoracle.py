@@ -57,6 +57,18 @@ class _MsOrders(C.Structure):
     ]
 
 
+class _MsFilters(C.Structure):
+    _P = C.POINTER
+    _fields_ = [
+        ("n_edges", C.c_uint64), ("contraction_order", _P(C.c_int32)), ("deletable", _P(C.c_uint8)),
+        ("n_kept_orders", _P(C.c_uint32)), ("weight", _P(C.c_uint64)), ("consensus", _P(C.c_uint8)),
+        ("t_filters", C.c_double), ("t_chain", C.c_double),
+    ]
+
+
+FILTER_FIELDS = ("contraction_order", "deletable", "n_kept_orders", "weight", "consensus")
+
+
 @dataclass
 class Orders:
     """Canonical result of chainingAndOverlaps (see oracle/ms_tables.h, ms_orders): per edge a shadow flag and its
@@ -257,6 +269,30 @@ class Reference(_Checker):
                 raise RuntimeError("reference threw (see stderr)")
             out = self._orders(o)
             L.ms_orders_free(C.byref(o))
+            return out
+        finally:
+            if tmp:
+                os.unlink(path)
+
+    def filters(self, paf, wiggle_room: int = 300) -> dict:
+        """Construction + chaining as in `chain`, then the reference's per-edge jobs findContractionEdges,
+        findDeletableEdges and computeBitweight (src/main.cpp:416-460, 534-573; sanityCheck is the reference's own
+        sc.cpp).  Returns the FILTER_FIELDS arrays (edges in (first, second) order) and `seconds`."""
+        L = self.lib
+        L.msref_filters.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(_MsFilters)]
+        L.msref_filters.restype = C.c_int
+        L.ms_filters_free.argtypes = [C.POINTER(_MsFilters)]
+        L.ms_filters_free.restype = None
+        path, tmp = self._as_path(paf)
+        try:
+            f = _MsFilters()
+            if L.msref_filters(path.encode(), wiggle_room, C.byref(f)):
+                raise RuntimeError("reference threw (see stderr)")
+            E = int(f.n_edges)
+            out = dict(contraction_order=_arr(f.contraction_order, E, np.int32), deletable=_arr(f.deletable, E, np.uint8),
+                       n_kept_orders=_arr(f.n_kept_orders, E, np.uint32), weight=_arr(f.weight, E, np.uint64),
+                       consensus=_arr(f.consensus, E, np.uint8), seconds=float(f.t_filters))
+            L.ms_filters_free(C.byref(f))
             return out
         finally:
             if tmp:

@@ -17,6 +17,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
+#include <map>
 #include <memory>
 #include <numeric>
 #include <string>
@@ -508,6 +510,114 @@ int msref_chain(const char *paf_path, uint64_t wiggle_room, ms_orders *out) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// The per-edge jobs after chaining: findContractionEdges (src/main.cpp:416-460), findDeletableEdges (main.cpp:534-550)
+// and computeBitweight (main.cpp:552-573).  Like chainingAndOverlaps their bodies live in main.cpp, so the control flow
+// is restated around the reference's OWN sanityCheck (sc.cpp:29-88), Graph::getNeighbors / hasEdge / getVertex and
+// Edge::replaceOrders / setWeight / setConsensusDirection.  The jobs in between (contraction bookkeeping and vertex
+// deletion, main.cpp:462-531) are not run: they only remove edges and do not change the verdict on the others.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+int contraction_order_of(muchsalsa::graph::Graph &graph, muchsalsa::graph::Edge const *pEdge, std::size_t wiggleRoom) {
+  using namespace muchsalsa;
+  auto const &edgeOrders = pEdge->getEdgeOrders();
+  for (auto const &order : edgeOrders) { // main.cpp:421
+    if (order.isContained && order.isPrimary) {
+      auto       isSane    = true;
+      auto const neighbors = graph.getNeighbors(order.startVertex);
+      auto const edges     = std::map<unsigned int, graph::Edge *>(std::begin(neighbors), std::end(neighbors));
+      for (auto const &[targetId, pSubedge] : edges) { // main.cpp:427-448
+        auto const *const pTargetVertex = graph.getVertex(targetId);
+        if (targetId == order.endVertex->getId() || pSubedge->isShadow()) continue;
+        isSane &= graph.hasEdge(std::make_pair(order.endVertex, pTargetVertex));
+        if (!isSane) break;
+        isSane &= sanityCheck(graph, *order.startVertex, *order.endVertex, *pTargetVertex, order, wiggleRoom);
+        if (!isSane) break;
+      }
+      if (isSane) return static_cast<int>(&order - edgeOrders.data()); // main.cpp:450-457 stores &order
+    }
+  }
+  return -1;
+}
+} // namespace
+
+void ms_filters_free(ms_filters *f) {
+  if (!f) return;
+  void *ptrs[] = {f->contraction_order, f->deletable, f->n_kept_orders, f->weight, f->consensus};
+  for (void *p : ptrs) std::free(p);
+  std::memset(f, 0, sizeof(*f));
+}
+
+// construction (one thread) + chainingAndOverlaps + the three per-edge jobs; edges in (first, second) order
+int msref_filters(const char *paf_path, uint64_t wiggle_room, ms_filters *out) {
+  using namespace muchsalsa;
+  std::memset(out, 0, sizeof(*out));
+  try {
+    auto pool             = threading::ThreadPool(1);
+    auto graph            = graph::Graph();
+    auto matchMap         = matching::MatchMap(&pool, &graph);
+    auto registryNanopore = Registry();
+    auto registryIllumina = Registry();
+    auto bfAccessor       = BlastFileAccessor(paf_path);
+    auto reader = BlastFileReader(&pool, &bfAccessor, &graph, &matchMap, &registryNanopore, &registryIllumina);
+    reader.read();
+    matchMap.calculateEdges();
+    auto edges = graph.getEdges();
+    std::sort(edges.begin(), edges.end(), [](auto *a, auto *b) {
+      auto va = a->getVertices(), vb = b->getVertices();
+      return std::make_pair(va.first->getId(), va.second->getId()) <
+             std::make_pair(vb.first->getId(), vb.second->getId());
+    });
+    auto const wiggle = static_cast<std::size_t>(wiggle_room);
+    auto       tc     = clk::now();
+    for (auto *pE : edges) chain_one_edge(matchMap, pE, wiggle);
+    out->t_chain = secs(tc, clk::now());
+
+    std::vector<int32_t>  contraction;
+    std::vector<uint8_t>  deletable, consensus;
+    std::vector<uint32_t> kept;
+    std::vector<uint64_t> weight;
+    auto                  t0 = clk::now();
+    for (auto *pE : edges) contraction.push_back(contraction_order_of(graph, pE, wiggle));
+    for (auto *pE : edges) { // findDeletableEdges, main.cpp:534-550
+      std::vector<graph::EdgeOrder> filteredOrders;
+      std::remove_copy_if(std::begin(pE->getEdgeOrders()), std::end(pE->getEdgeOrders()),
+                          std::back_inserter(filteredOrders), [](auto const &order) { return order.isContained; });
+      deletable.push_back(filteredOrders.empty() ? 1 : 0);
+      pE->replaceOrders(std::move(filteredOrders));
+    }
+    for (auto *pE : edges) { // computeBitweight, main.cpp:552-573
+      auto const &orders = pE->getEdgeOrders();
+      if (!orders.empty()) {
+        if (pE->isShadow()) {
+          auto const initial   = orders[0].direction;
+          auto const findOther = std::find_if(orders.begin(), orders.end(), [&](auto const &order) {
+                                   return order.direction != initial;
+                                 }) != orders.end();
+          if (!findOther) pE->setConsensusDirection(orders[0].direction);
+        } else {
+          pE->setWeight(orders[0].score);
+          pE->setConsensusDirection(orders[0].direction);
+        }
+      }
+      kept.push_back(static_cast<uint32_t>(orders.size()));
+      weight.push_back(pE->getWeight());
+      consensus.push_back(static_cast<uint8_t>(pE->getConsensusDirection()));
+    }
+    out->t_filters         = secs(t0, clk::now());
+    out->n_edges           = edges.size();
+    out->contraction_order = dup(contraction);
+    out->deletable         = dup(deletable);
+    out->n_kept_orders     = dup(kept);
+    out->weight            = dup(weight);
+    out->consensus         = dup(consensus);
+    return 0;
+  } catch (std::exception const &e) {
+    std::fprintf(stderr, "msref_filters: %s\n", e.what());
+    return 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Sequence path: strSlice / getReverseComplement (SequenceUtils.cpp:27-61) and the FASTA/FASTQ store
 // (SequenceAccessor.cpp:54-231) + get{Illumina,Nanopore}Sequence (SequenceUtils.cpp:63-85).
 // ---------------------------------------------------------------------------------------------------------------------
@@ -608,12 +718,12 @@ int main(int argc, char **argv) {
     std::fprintf(stderr, "usage: %s <paf> <threads>\n", argv[0]);
     return 2;
   }
-  if (argc >= 4 && std::string(argv[3]) == "chain") { // `msref_cli <paf> 1 chain`: also time chainingAndOverlaps
-    ms_orders o;
-    int       rc = msref_chain(argv[1], 300, &o);
+  if (argc >= 4 && std::string(argv[3]) == "chain") { // `msref_cli <paf> 1 chain`: time the stages after construction
+    ms_filters f;
+    int        rc = msref_filters(argv[1], 300, &f);
     if (rc) return rc;
-    std::printf("{\"threads\": 1, \"t_chain\": %.6f, \"n_edges\": %llu, \"n_orders\": %llu}\n", o.t_chain,
-                (unsigned long long)o.n_edges, (unsigned long long)o.n_orders);
+    std::printf("{\"threads\": 1, \"t_chain\": %.6f, \"t_filters\": %.6f, \"n_edges\": %llu}\n", f.t_chain, f.t_filters,
+                (unsigned long long)f.n_edges);
     return 0;
   }
   ms_tables t;

@@ -64,6 +64,15 @@ def orders_digest(o) -> str:
     return h.hexdigest()
 
 
+def filters_digest(f) -> str:
+    import hashlib
+    from oracle.pyoracle import FILTER_FIELDS
+    h = hashlib.sha256()
+    for k in FILTER_FIELDS:
+        h.update(np.ascontiguousarray(f[k]).tobytes())
+    return h.hexdigest()
+
+
 def main():
     R = Reference()
     # the reference's own fixtures (data, not code) travel with the repo so the GPU box can load them
@@ -74,6 +83,11 @@ def main():
     cases = {name: tables_json(R.build(paf)) for name, paf in util.edge_case_pafs().items()}
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         json.dump(cases, f)
+
+    # known-answer vector of the per-edge jobs after chaining on the SURVEY.md §8c PAF
+    fl = R.filters(util.kat8_paf())
+    with open(os.path.join(HERE, "filters_kat8.json"), "w") as f:
+        json.dump({k: fl[k].tolist() for k in ("contraction_order", "deletable", "n_kept_orders", "weight", "consensus")}, f)
 
     digests = {}
     names = ["small", "ecoli"] + (["yeast"] if "--yeast" in sys.argv else [])
@@ -91,6 +105,10 @@ def main():
                 o = R.chain(synth.generate_paf(cfg))
                 digests[name].update(orders_digest=orders_digest(o), orders=int(o.left.size),
                                      shadow_edges=int(o.edge_shadow.sum()))
+                fl = R.filters(synth.generate_paf(cfg))  # the per-edge jobs after chaining
+                digests[name].update(filters_digest=filters_digest(fl),
+                                     contraction_edges=int((fl["contraction_order"] >= 0).sum()),
+                                     deletable_edges=int(fl["deletable"].sum()))
             print(name, shuffled, t.counts, flush=True)
     for k, v in old.items():
         digests.setdefault(k, v)

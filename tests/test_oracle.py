@@ -146,3 +146,27 @@ def test_reference_chain_small_digest(reference):
     g = util.load_golden("digests.json")["small"]
     assert o.left.size == g["orders"] == 1465 and int(o.edge_shadow.sum()) == g["shadow_edges"] == 39
     assert h.hexdigest() == g["orders_digest"]
+
+
+def test_reference_filters_known_answer(reference):
+    """findContractionEdges / findDeletableEdges / computeBitweight of the reference on the SURVEY §8c known-answer
+    PAF against the vector committed under tests/golden (pins the GPU test of the same name)."""
+    from oracle.pyoracle import FILTER_FIELDS
+    f = reference.filters(util.kat8_paf())
+    g = util.load_golden("filters_kat8.json")
+    for k in FILTER_FIELDS:
+        assert f[k].tolist() == g[k], k
+    # r1-r2 is the only non-shadow edge: weight = its order's score, direction negative; r1-r3 / r2-r3 are shadows
+    assert f["weight"].tolist() == [3800, 0, 0] and bytes(f["consensus"].tolist()) == b"bab"
+
+
+def test_reference_filters_small_digest(reference):
+    import hashlib
+    from oracle.pyoracle import FILTER_FIELDS
+    f = reference.filters(synth.generate_paf("small"))
+    g = util.load_golden("digests.json")["small"]
+    h = hashlib.sha256()
+    for k in FILTER_FIELDS:
+        h.update(np.ascontiguousarray(f[k]).tobytes())
+    assert h.hexdigest() == g["filters_digest"]
+    assert int((f["contraction_order"] >= 0).sum()) == g["contraction_edges"] > 0
