@@ -139,6 +139,67 @@ void chainAndOverlaps(Context &ctx, graph::Graph &graph, std::size_t wiggleRoom)
   }
 }
 
+namespace {
+struct FilterView {
+  msgpu_counts             c{};
+  msgpu_tables             t{};
+  msgpu_edge_filter_tables f{};
+};
+
+FilterView filterView(Context &ctx) {
+  FilterView v;
+  if (int rc = msgpu_result_counts(ctx.get(), &v.c); rc != MSGPU_OK) raise(ctx.get(), rc);
+  if (int rc = msgpu_result_host(ctx.get(), &v.t); rc != MSGPU_OK) raise(ctx.get(), rc);
+  if (int rc = msgpu_edge_filters_host(ctx.get(), &v.f); rc != MSGPU_OK) raise(ctx.get(), rc);
+  return v;
+}
+
+// the edge of table row e if both vertices and the edge are still in the graph
+graph::Edge *liveEdge(graph::Graph &graph, msgpu_tables const &t, uint64_t e) {
+  auto const *const pFirst  = graph.getVertex(t.edge_first[e]);
+  auto const *const pSecond = graph.getVertex(t.edge_second[e]);
+  if (pFirst == nullptr || pSecond == nullptr) return nullptr;
+  return graph.getEdge(std::make_pair(gsl::make_not_null(pFirst), gsl::make_not_null(pSecond)));
+}
+} // namespace
+
+void findContractionEdges(Context &ctx, graph::Graph &graph, std::size_t wiggleRoom,
+                          std::unordered_map<graph::Edge const *, graph::EdgeOrder const *> &contractionEdges) {
+  if (int rc = msgpu_edge_filters(ctx.get(), wiggleRoom); rc != MSGPU_OK) raise(ctx.get(), rc);
+  auto const v = filterView(ctx);
+  for (uint64_t e = 0; e < v.c.n_edges; ++e) {
+    if (v.f.contraction_order[e] < 0) continue;
+    auto const *const pEdge = liveEdge(graph, v.t, e);
+    if (pEdge == nullptr) continue;
+    contractionEdges.insert({pEdge, &pEdge->getEdgeOrders()[static_cast<std::size_t>(v.f.contraction_order[e])]});
+  }
+}
+
+void findDeletableEdges(Context &ctx, graph::Graph &graph, std::set<graph::Edge const *> &deletableEdges) {
+  auto const v = filterView(ctx);
+  for (uint64_t e = 0; e < v.c.n_edges; ++e) {
+    auto *const pEdge = liveEdge(graph, v.t, e);
+    if (pEdge == nullptr) continue;
+    std::vector<graph::EdgeOrder> kept; // the slots with isContained clear, in their old order (main.cpp:536-538)
+    kept.reserve(v.f.n_kept_orders[e]);
+    for (auto const &order : pEdge->getEdgeOrders())
+      if (!order.isContained) kept.push_back(order);
+    if (v.f.deletable[e] != 0) deletableEdges.insert(pEdge);
+    pEdge->replaceOrders(std::move(kept));
+  }
+}
+
+void computeBitweights(Context &ctx, graph::Graph &graph) {
+  auto const v = filterView(ctx);
+  for (uint64_t e = 0; e < v.c.n_edges; ++e) {
+    auto *const pEdge = liveEdge(graph, v.t, e);
+    if (pEdge == nullptr) continue;
+    if (v.f.consensus[e] == 'c') continue;          // untouched: weight 0, e_NONE (Edge.cpp:32-33)
+    if (!pEdge->isShadow()) pEdge->setWeight(static_cast<std::size_t>(v.f.weight[e])); // main.cpp:568
+    pEdge->setConsensusDirection(v.f.consensus[e] == 'a');
+  }
+}
+
 void loadSequences(Context &ctx, std::string const &unitigsPath, std::string const &nanoporePath) {
   if (int rc = msgpu_seq_load(ctx.get(), unitigsPath.c_str(), nanoporePath.c_str()); rc != MSGPU_OK)
     raise(ctx.get(), rc);

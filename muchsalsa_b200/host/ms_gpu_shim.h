@@ -15,7 +15,9 @@
 // Compiles against the reference's headers (include/ms) and include/msgpu.h; links libmsgpu.so.  C++20 like libms.
 #pragma once
 
+#include <set>
 #include <string>
+#include <unordered_map>
 
 #include "Registry.h"
 #include "graph/Graph.h"
@@ -49,6 +51,23 @@ void constructGraph(Context &ctx, std::string const &pafPath, muchsalsa::graph::
 // ThreadPool loop over chainingAndOverlaps jobs (src/main.cpp:170-178, 328-414).  Sets Edge::setShadow and appends the
 // EdgeOrders exactly as getMaxPairwisePaths (mpp.cpp) + getOverlap (ol.cpp) would.
 void chainAndOverlaps(Context &ctx, muchsalsa::graph::Graph &graph, std::size_t wiggleRoom);
+
+// The per-edge jobs that follow, computed on the GPU in one call from the orders chainAndOverlaps left in HBM, then
+// applied at the three places main() runs them:
+//   findContractionEdges   replaces the job loop of src/main.cpp:181-191 (job body 416-460, sanityCheck of sc.cpp):
+//                          fills `contractionEdges` with {edge, &order} exactly like the reference's map.  Call it
+//                          right after chainAndOverlaps, while the graph is complete; it runs msgpu_edge_filters.
+//   findDeletableEdges     replaces src/main.cpp:247-256 (job body 534-550): drops the contained orders of every edge
+//                          still in the graph (Edge::replaceOrders) and collects the edges left without orders.
+//   computeBitweights      replaces src/main.cpp:263-270 (job body 552-573): Edge::setWeight / setConsensusDirection
+//                          for every edge still in the graph.
+// Vertices and edges the host deleted in between (main.cpp:193-245, 258-260) are skipped: the verdict on an edge
+// depends on its own orders only.
+void findContractionEdges(Context &ctx, muchsalsa::graph::Graph &graph, std::size_t wiggleRoom,
+                          std::unordered_map<muchsalsa::graph::Edge const *, muchsalsa::graph::EdgeOrder const *> &contractionEdges);
+void findDeletableEdges(Context &ctx, muchsalsa::graph::Graph &graph,
+                        std::set<muchsalsa::graph::Edge const *> &deletableEdges);
+void computeBitweights(Context &ctx, muchsalsa::graph::Graph &graph);
 
 // SequenceAccessor(...) + buildIndex() (src/main.cpp:161-163): both files indexed and kept resident in HBM; ids
 // continue the numbering of the construction that ran on `ctx`.

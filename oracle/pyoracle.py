@@ -298,6 +298,32 @@ class Reference(_Checker):
             if tmp:
                 os.unlink(path)
 
+    def filters_gpu(self, paf, wiggle_room: int = 300) -> dict:
+        """Like `filters`, but construction, chaining and the per-edge jobs run on the GPU and are applied to the
+        reference's own Graph / Edge objects through the host shim (findContractionEdges, findDeletableEdges,
+        computeBitweights of muchsalsa_b200/host/ms_gpu_shim.cpp); dumped from those objects."""
+        L = self.lib
+        L.msref_filters_gpu.argtypes = [C.c_char_p, C.c_uint64, C.POINTER(_MsFilters), C.c_char_p, C.c_uint64]
+        L.msref_filters_gpu.restype = C.c_int
+        L.ms_filters_free.argtypes = [C.POINTER(_MsFilters)]
+        L.ms_filters_free.restype = None
+        path, tmp = self._as_path(paf)
+        try:
+            f = _MsFilters()
+            err = C.create_string_buffer(512)
+            rc = L.msref_filters_gpu(path.encode(), wiggle_room, C.byref(f), err, 512)
+            if rc:
+                raise RuntimeError(f"rc={rc}: {err.value.decode(errors='replace')}")
+            E = int(f.n_edges)
+            out = dict(contraction_order=_arr(f.contraction_order, E, np.int32), deletable=_arr(f.deletable, E, np.uint8),
+                       n_kept_orders=_arr(f.n_kept_orders, E, np.uint32), weight=_arr(f.weight, E, np.uint64),
+                       consensus=_arr(f.consensus, E, np.uint8))
+            L.ms_filters_free(C.byref(f))
+            return out
+        finally:
+            if tmp:
+                os.unlink(path)
+
     def chain_gpu(self, paf, wiggle_room: int = 300) -> Orders:
         """Construction AND chaining by the GPU path through the host shim (constructGraph + chainAndOverlaps of
         muchsalsa_b200/host/ms_gpu_shim.cpp) into the reference's own Graph / Edge objects, dumped like `chain`."""

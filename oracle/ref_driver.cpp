@@ -21,6 +21,7 @@
 #include <map>
 #include <memory>
 #include <numeric>
+#include <set>
 #include <string>
 #include <string_view>
 #include <tuple>
@@ -347,6 +348,66 @@ int msref_chain_gpu(const char *paf_path, uint64_t wiggle_room, ms_orders *out, 
              std::make_pair(vb.first->getId(), vb.second->getId());
     });
     dump_orders(edges, out);
+    return 0;
+  } catch (std::exception const &e) {
+    return fail(e.what(), 1);
+  }
+}
+
+// Construction, chaining AND the per-edge jobs by the GPU path through the host shim into the reference's own objects;
+// dumped from the Edge objects like msref_filters does.
+int msref_filters_gpu(const char *paf_path, uint64_t wiggle_room, ms_filters *out, char *err, uint64_t err_cap) {
+  using namespace muchsalsa;
+  std::memset(out, 0, sizeof(*out));
+  auto fail = [&](const char *m, int rc) {
+    if (err && err_cap) std::snprintf(err, err_cap, "%s", m);
+    return rc;
+  };
+  try {
+    std::unique_ptr<gpu::Context> ctx;
+    try {
+      ctx = std::make_unique<gpu::Context>(0);
+    } catch (std::exception const &e) {
+      return fail(e.what(), 2);
+    }
+    auto pool             = threading::ThreadPool(1);
+    auto graph            = graph::Graph();
+    auto matchMap         = matching::MatchMap(&pool, &graph);
+    auto registryNanopore = Registry();
+    auto registryIllumina = Registry();
+    gpu::constructGraph(*ctx, paf_path, graph, matchMap, registryNanopore, registryIllumina);
+    gpu::chainAndOverlaps(*ctx, graph, static_cast<std::size_t>(wiggle_room));
+    std::unordered_map<graph::Edge const *, graph::EdgeOrder const *> contractionEdges;
+    gpu::findContractionEdges(*ctx, graph, static_cast<std::size_t>(wiggle_room), contractionEdges);
+    auto edges = graph.getEdges();
+    std::sort(edges.begin(), edges.end(), [](auto *a, auto *b) {
+      auto va = a->getVertices(), vb = b->getVertices();
+      return std::make_pair(va.first->getId(), va.second->getId()) <
+             std::make_pair(vb.first->getId(), vb.second->getId());
+    });
+    std::vector<int32_t> contraction;
+    for (auto *pE : edges) { // before the orders are replaced: the map points into the unfiltered lists
+      auto it = contractionEdges.find(pE);
+      contraction.push_back(it == contractionEdges.end() ? -1 : static_cast<int32_t>(it->second - pE->getEdgeOrders().data()));
+    }
+    std::set<graph::Edge const *> deletableEdges;
+    gpu::findDeletableEdges(*ctx, graph, deletableEdges);
+    gpu::computeBitweights(*ctx, graph);
+    std::vector<uint8_t>  deletable, consensus;
+    std::vector<uint32_t> kept;
+    std::vector<uint64_t> weight;
+    for (auto *pE : edges) {
+      deletable.push_back(deletableEdges.count(pE) ? 1 : 0);
+      kept.push_back(static_cast<uint32_t>(pE->getEdgeOrders().size()));
+      weight.push_back(pE->getWeight());
+      consensus.push_back(static_cast<uint8_t>(pE->getConsensusDirection()));
+    }
+    out->n_edges           = edges.size();
+    out->contraction_order = dup(contraction);
+    out->deletable         = dup(deletable);
+    out->n_kept_orders     = dup(kept);
+    out->weight            = dup(weight);
+    out->consensus         = dup(consensus);
     return 0;
   } catch (std::exception const &e) {
     return fail(e.what(), 1);

@@ -68,3 +68,15 @@ def test_reference_edges_chained_by_gpu_equal_reference(ref, name):
 def test_reference_edges_chained_by_gpu_small(ref):
     paf = synth.generate_paf("small")
     assert orders_equal(ref.chain_gpu(paf), ref.chain(paf)) == []
+
+
+@pytest.mark.parametrize("name", ["kat8", "duplicates_ungrouped", "heavy_group", "small"])
+def test_reference_edges_filtered_by_gpu_equal_reference(ref, name):
+    """The contraction-edge map, Edge::getEdgeOrders() after replaceOrders, Edge::getWeight() and
+    getConsensusDirection() of the reference's own objects after the shim's findContractionEdges / findDeletableEdges /
+    computeBitweights, against the reference's own job bodies (src/main.cpp:416-460, 534-573)."""
+    import numpy as np
+    from oracle.pyoracle import FILTER_FIELDS
+    paf = synth.generate_paf("small") if name == "small" else util.edge_case_pafs()[name]
+    got, want = ref.filters_gpu(paf), ref.filters(paf)
+    assert [k for k in FILTER_FIELDS if not np.array_equal(got[k], want[k])] == []
