@@ -94,22 +94,32 @@ def make_workload(name, shard=None):
 #   M kept matches, EM edge matches, E edges, P candidate pairs, B PAF bytes
 # ---------------------------------------------------------------------------------------------------------------------
 def kernel_bytes(name, c, paf_bytes):
+    """Algorithmic bytes of one launch, two ways: (survey, strict).
+
+    survey: SURVEY.md §8(d)'s fixed record sizes (R_m = R_e = 40 B) x the units the launch processes — the numerator
+            the roofline is quoted on, so that a path that re-reads or re-sorts scores lower, not higher.  The product
+            variant splits K6 + K7 over two kernels: pair_tiles does K6 (every match read once, every surviving
+            candidate produced once: R_m*M + R_e*EM) and K7's pass over the candidates into edge-grouped order
+            (R_e*EM); pair_emit_rows does K7's write of the ordered edge matches and the edge table (R_e*EM + 12*E).
+            Together: R_m*M + 3*R_e*EM + 12*E = §8(d)'s K6 + K7.
+    strict: the bytes THIS implementation has to move at least (actual record sizes, everything touched once); the
+            tile kernel keeps the candidates in shared memory, so its strict figure is far below the survey's."""
     M, EM, E = c["n_matches"], c["n_edge_matches"], c["n_edges"]
+    L = c["n_lines"]
     table = {
         # sort-based variant
-        "radix_scatter": 2 * 12 * EM,            # (key u64 + index u32) read once + written once per digit pass
-        "radix_hist": 8 * EM,                    # keys read once
-        "pair_emit": 29 * M + 33 * EM,           # match fields read once; key + payload of each kept pair written once
-        "pair_count": 12 * M,                    # unitig ranges + read ids read once (pairing happens on chip)
-        "gather_sorted": (12 + 25 + 25 + 1) * EM,
-        "write_edges": 9 * EM + 16 * E,
-        # product variant (pair_fused.cu): the tile kernel reads every match once (32 B row + 12 B of columns) and
-        # writes one 8 B record per edge match; the emit kernel reads the records and writes the tables once
-        "pair_tiles": 44 * M + 8 * EM,
-        "pair_emit_rows": 8 * EM + 32 * M + 25 * EM + 16 * E,
-        # ingest
-        "parse_lines": paf_bytes + 8 * c["n_lines"] + 50 * c["n_lines"],
-        "newline_count": paf_bytes, "newline_write": paf_bytes + 8 * c["n_lines"],
+        "radix_scatter": (2 * 12 * EM,) * 2,       # (key u64 + index u32) read once + written once per digit pass
+        "radix_hist": (8 * EM,) * 2,               # keys read once
+        "pair_emit": (40 * M + 40 * EM, 29 * M + 33 * EM),
+        "pair_count": (12 * M,) * 2,
+        "gather_sorted": (80 * EM, (12 + 25 + 25 + 1) * EM),
+        "write_edges": (12 * E, 9 * EM + 16 * E),
+        # product variant (pair_fused.cu)
+        "pair_tiles": (40 * M + 80 * EM, 44 * M + 8 * EM),
+        "pair_emit_rows": (40 * EM + 12 * E, 8 * EM + 32 * M + 25 * EM + 16 * E),
+        # ingest: text read once + one packed record per line (§8(d): file bytes + R_m per record written)
+        "parse_lines": (paf_bytes + 40 * L, paf_bytes + 58 * L),
+        "newline_count": (paf_bytes,) * 2, "newline_write": (paf_bytes + 8 * L,) * 2,
     }
     return table.get(name)
 
@@ -227,6 +237,9 @@ def run_ours(args):
             a[0] += n
             a[1] += t
     gb.profile(False)
+    flush.zero_()
+    step_device()  # one more plain step: its phase times (library events, no per-launch events) feed the roofline
+    torch.cuda.synchronize()
     per_kernel = {k: {"launches_per_step": n / args.steps, "ms_per_step": t / args.steps, "us_per_launch": 1e3 * t / n}
                   for k, (n, t) in agg.items()}
     top = sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_per_step"])
@@ -236,28 +249,35 @@ def run_ours(args):
         b = kernel_bytes(name, counts, n_bytes)
         if b is None:
             continue
-        achieved = b / (st["us_per_launch"] * 1e-6) / 1e9
+        b_survey, b_strict = b
+        achieved = b_survey / (st["us_per_launch"] * 1e-6) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(args.workload, {}).get(name)
         roof = {"kernel": name, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(b), "us_per_launch": round(st["us_per_launch"], 2),
+                "algorithmic_bytes_per_launch": int(b_survey),
+                "algorithmic_bytes_definition": "SURVEY.md §8(d) record sizes (40 B per match / edge match, 12 B per "
+                                                "edge) x units per launch; see DESIGN.md §4",
+                "strict_bytes_per_launch": int(b_strict),
+                "strict_frac": round(b_strict / (st["us_per_launch"] * 1e-6) / 1e9 / peak, 4),
+                "us_per_launch": round(st["us_per_launch"], 2),
                 "share_of_step": round(st["ms_per_step"] / sum(v["ms_per_step"] for v in per_kernel.values()), 3)}
         break
-    # the whole pairing + merge (K6 + K7: plan, tile sort, tile scan, emit) against the bytes it must move
-    pm_kernels = ("rank_rows", "scatter_sources", "order_sources", "write_tiles", "split_heavy", "pair_tiles",
-                  "scan_tiles", "pair_emit_rows")
-    pm_ms = sum(per_kernel[k]["ms_per_step"] for k in pm_kernels if k in per_kernel)
+    # the whole pairing + merge (K6 + K7: plan, tile sort, tile scans, emit) against the bytes it must move; device
+    # time of the two phases from the library's own events
+    tm = gb.timings()
+    pm_ms = tm["pair_ms"] + tm["merge_ms"]
     if roof is not None and pm_ms > 0:
         M, EM, E = counts["n_matches"], counts["n_edge_matches"], counts["n_edges"]
         strict = 29 * M + 25 * EM + 16 * E                     # every match once, every edge match + edge once
-        survey = 3 * 40 * M + 3 * 40 * EM + 12 * E             # SURVEY.md §8(d) B_tot (sort-shaped passes)
+        survey = 40 * M + 3 * 40 * EM + 12 * E                 # K6 + K7
         roof["pairing_and_merge"] = {
             "ms": round(pm_ms, 3), "bytes_written_once": int(strict),
             "achieved_gbs": round(strict / pm_ms / 1e6, 1), "frac": round(strict / pm_ms / 1e6 / peak, 4),
             "survey_8d_bytes": int(survey), "survey_8d_frac": round(survey / pm_ms / 1e6 / peak, 4)}
+        survey = 3 * 40 * M + 3 * 40 * EM + 12 * E             # SURVEY.md §8(d) B_tot of the whole construction
         # the whole construction step against SURVEY.md §8(d)'s B_tot (the figure BASELINE.md asks for)
         step_ms = 1e3 * t_dev / args.steps
         roof["construction_step"] = {"ms": round(step_ms, 3), "survey_8d_bytes": int(survey),

@@ -62,6 +62,7 @@ public:
     }
     if (++m_epoch >= (1u << 16)) {
       MSGPU_CUDA(cudaMemsetAsync(m_scan_state, 0, m_scan_state_bytes, st));
+      MSGPU_CUDA(cudaMemsetAsync(counter() + 8, 0, 32 * sizeof(unsigned), st)); // the scans' ring of ticket counters
       m_epoch = 1;
     }
     *epoch = m_epoch;
@@ -70,8 +71,8 @@ public:
   // a zero-initialised device counter that outlives reset(): kernels that use it leave it at zero again
   unsigned *counter() {
     if (!m_counter) {
-      MSGPU_CUDA(cudaMalloc(&m_counter, 256));
-      MSGPU_CUDA(cudaMemset(m_counter, 0, 256));
+      MSGPU_CUDA(cudaMalloc(&m_counter, 512)); // [0..7] kernels' own counters, [8..39] ticket ring of the scans
+      MSGPU_CUDA(cudaMemset(m_counter, 0, 512));
     }
     return m_counter;
   }

@@ -521,14 +521,13 @@ struct NameLen {
   __device__ uint64_t operator()(uint64_t i) const { return i < *d_n ? uint64_t(len[i]) : 0ull; }
 };
 
-// name_off[i] = exclusive prefix of the name lengths (entries behind the count repeat the total, so name_off[n] is
-// the total); names gathered from the PAF text.  `cap` bounds the count, `cap_bytes` the total length.
+// name_off[i] = exclusive prefix of the name lengths for i <= count (name_off[count] is the total); names gathered from the PAF text.  `cap` bounds the count, `cap_bytes` the total length.
 static void build_name_table(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t cap, uint64_t cap_bytes,
                              const unsigned *d_n, const uint64_t *src, const uint32_t *len,
                              unsigned long long *d_total_bytes, NameTable &out) {
   out.name_off = arena.alloc<uint64_t>(cap + 1);
   exclusive_scan<uint64_t>(arena, st, NameLen{len, d_n}, cap + 1, out.name_off,
-                           reinterpret_cast<uint64_t *>(d_total_bytes));
+                           reinterpret_cast<uint64_t *>(d_total_bytes), ScanLive{d_n, nullptr, 1}); // name_off[0 .. n]
   out.names = arena.alloc<char>(cap_bytes);
   if (cap) {
     MSGPU_LAUNCH("gather_names", st, gather_names_kernel<<<grid_for(cap * 32, 256, 2), 256, 0, st>>>(d_paf, src, out.name_off, d_n, out.names));
@@ -656,13 +655,14 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     const uint64_t seed  = force ? 0ull : 0x243f6a8885a308d3ull * uint64_t(attempt + 1);
     MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
 
+    const ScanLive live_lines{nullptr, &d_status->n_lines, 0}; // the per-line scans stop at the actual line count
     // ---- K3 interning
     InternTable rt = make_table(arena, st, cap_acc + cap_acc / 2), ut = make_table(arena, st, cap_acc + cap_acc / 2);
     MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.rhash, d_status, rt, rslot));
     MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.uhash, d_status, ut, uslot));
     MSGPU_LAUNCH("intern_verify", st, intern_verify_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, f, rt, rslot, ut, uslot, d_status));
-    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstRead}, cap, rank_a, &d_status->n_reads);
-    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstUnitig}, cap, rank_b, &d_status->n_unitigs);
+    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstRead}, cap, rank_a, &d_status->n_reads, live_lines);
+    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstUnitig}, cap, rank_b, &d_status->n_unitigs, live_lines);
     MSGPU_LAUNCH("intern_assign", st, intern_assign_kernel<<<grid_lines, 256, 0, st>>>(line_start, d_status, f, rt, rslot, rank_a, ut, uslot, rank_b,
                                                      reads.nlen, reads.line, rsrc, rlen, usrc, ulen));
     build_name_table(arena, st, d_paf, cap_acc, n_bytes, &d_status->n_reads, rsrc, rlen, &d_status->read_name_bytes, reads);
@@ -674,7 +674,7 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     MSGPU_LAUNCH("dedup_flag", st, dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(d_status, f.flags, dt, dslot));
 
     // ---- K5 compaction
-    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFSurvivor}, cap, rank_a, &d_status->n_matches);
+    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFSurvivor}, cap, rank_a, &d_status->n_matches, live_lines);
     MSGPU_LAUNCH("compact_matches", st, compact_matches_kernel<<<grid_lines, 256, 0, st>>>(d_status, f, rank_a, rid_of_line, uid_of_line, m));
     MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(cap_acc, 256, 2), 256, 0, st>>>(m.unitig, &d_status->n_matches, 0, &d_status->unsorted));
 

@@ -734,9 +734,8 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
       const uint32_t s1 = s0 + G < re ? s0 + G : re, s2 = s0 + 2 * G < re ? s0 + 2 * G : re;
       const uint32_t a0 = s.src.base[s0], a1 = s.src.base[s1], b1 = s.src.base[s2];
       const uint32_t seg_end = oe < b1 ? oe : b1;
-      if (a1 == b1 || a0 == a1) { // one side empty: the run is copied
-        for (uint32_t p = pos; p < seg_end; ++p) out[p] = in[p];
-      } else {
+      { // (a run whose partner is empty takes the same path: the search interval is empty and one side never wins,
+        //  so the lanes of a warp that copy and the lanes that merge do not serialise)
         const uint32_t k  = pos - a0, na = a1 - a0, nb = b1 - a1;
         uint32_t       lo = k > nb ? k - nb : 0u, hi = k < na ? k : na; // merge path: elements of A among the first k
         while (lo < hi) {
@@ -935,32 +934,16 @@ __global__ void __launch_bounds__(kFusedBlock, kMergeCtas) pair_tiles_merge_kern
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K7b: tile counts -> global offsets of every tile's first edge match and first edge (one CTA; tiles are few)
+// K7b: tile counts -> global offsets of every tile's first edge match and first edge (two single-pass scans)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-    scan_tiles_kernel(const uint2 *__restrict__ tile_cnt, uint32_t n_tiles, unsigned long long *__restrict__ em_base,
-                      unsigned long long *__restrict__ edge_base, unsigned long long *__restrict__ totals,
-                      uint64_t *__restrict__ em_begin) {
-  __shared__ unsigned long long sm[33];
-  unsigned long long            carry_v = 0, carry_h = 0;
-  for (uint32_t c0 = 0; c0 < n_tiles; c0 += blockDim.x) {
-    const uint32_t i = c0 + threadIdx.x;
-    const uint2    c = i < n_tiles ? tile_cnt[i] : make_uint2(0, 0);
-    // both counts are <= 4096 per tile and a chunk has 1024 tiles: pack them into one 64-bit scan
-    unsigned long long tot, ex = block_exclusive_scan<unsigned long long>((unsigned long long)c.x | ((unsigned long long)c.y << 32), sm, &tot);
-    if (i < n_tiles) {
-      em_base[i]   = carry_v + (ex & 0xffffffffull);
-      edge_base[i] = carry_h + (ex >> 32);
-    }
-    carry_v += tot & 0xffffffffull;
-    carry_h += tot >> 32;
-  }
-  if (threadIdx.x == 0) {
-    totals[0]         = carry_v;
-    totals[1]         = carry_h;
-    em_begin[carry_h] = carry_v; // closes the CSR
-  }
-}
+struct TileValid { // surviving candidates of a tile
+  const uint2 *cnt;
+  __device__ unsigned long long operator()(uint64_t i) const { return cnt[i].x; }
+};
+struct TileHeads { // run heads (= edges) of a tile
+  const uint2 *cnt;
+  __device__ unsigned long long operator()(uint64_t i) const { return cnt[i].y; }
+};
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K7c: every record becomes one edge match (and, for run heads, one edge) at its final position
@@ -970,7 +953,7 @@ struct EmitArgs {
   const uint32_t *rd_off, *rd_src, *tile_row, *tile_kind;
   uint32_t        tile_lo, n_tiles;
   const uint2    *records, *tile_cnt;
-  const unsigned long long *em_base, *edge_base;
+  const unsigned long long *em_base, *edge_base, *totals; // totals: (edge matches, edges) of this launch
   EdgeTables      out;
 };
 
@@ -997,6 +980,7 @@ constexpr int kEmitBatch = 4; // records in flight per thread: the partner gathe
 __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs a) {
   __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
   const unsigned   t = threadIdx.x;
+  if (blockIdx.x == 0 && t == 0) a.out.em_begin[a.totals[1]] = a.totals[0]; // closes the CSR
   for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
     const uint32_t           tile    = a.tile_lo + ti;
     const uint32_t           n_valid = a.tile_cnt[ti].x;
@@ -1202,7 +1186,9 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
       MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
     }
   }
-  MSGPU_LAUNCH("scan_tiles", st, scan_tiles_kernel<<<1, 1024, 0, st>>>(tile_cnt, my_tiles, em_base, ed_base, totals, e.em_begin));
+  exclusive_scan<unsigned long long>(arena, st, TileValid{tile_cnt}, my_tiles, em_base, totals + 0);
+  exclusive_scan<unsigned long long>(arena, st, TileHeads{tile_cnt}, my_tiles, ed_base, totals + 1);
+  if (!my_tiles) MSGPU_CUDA(cudaMemsetAsync(e.em_begin, 0, sizeof(uint64_t), st)); // an empty CSR: em_begin[0] = 0
   if (my_tiles) {
     EmitArgs ea;
     ea.rows      = rows;
@@ -1216,6 +1202,7 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
     ea.tile_cnt  = tile_cnt;
     ea.em_base   = em_base;
     ea.edge_base = ed_base;
+    ea.totals    = totals;
     ea.out       = e;
     int grid = kNumSMs * 8;
     if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
