@@ -35,6 +35,7 @@ namespace msgpu {
 
 constexpr int kChainMax   = 96; // edge matches of ONE direction on one edge that the per-thread programme holds
 constexpr int kChainSmall = 8;  // edges with at most this many edge matches run the small instantiation
+constexpr int kChainTiny  = 4;  // ... and these the smallest one: its state stays in L1 / L2
 
 // the fields of one VertexMatch the stage reads, in pairing order (grouped by unitig, by read id inside): 32 bytes
 struct __align__(16) VmRow {
@@ -231,7 +232,8 @@ struct EmState { // per edge match of the direction being chained
   double c1a, c1b, c2a, c2b; // corrected nanopore intervals on the first / second vertex
   int    r1a, r1b, r2a, r2b; // nanoporeRange on the first / second vertex
   double score;
-  uint32_t unitig, row1, row2, k; // k: row of the edge match
+  uint32_t unitig;
+  uint16_t k; // row of the edge match inside its edge
   bool   prim;
 };
 
@@ -285,13 +287,11 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
           break;
         }
         EmState s;
-        s.k      = uint32_t(k - k0);
+        s.k      = uint16_t(k - k0);
         s.unitig = a.e.em_unitig[k];
-        s.row1   = a.em_row1[k];
-        s.row2   = a.em_row2[k];
         s.score  = a.e.em_score[k];
         s.prim   = (a.e.em_flags[k] & 2) != 0;
-        const Vm  w1 = load_vm(a, s.row1), w2 = load_vm(a, s.row2);
+        const Vm  w1 = load_vm(a, a.em_row1[k]), w2 = load_vm(a, a.em_row2[k]);
         const int ov0 = a.e.em_ov0[k], ov1 = a.e.em_ov1[k];
         corrected_nano(w1, ov0, ov1, &s.c1a, &s.c1b);
         corrected_nano(w2, ov0, ov1, &s.c2a, &s.c2b);
@@ -667,8 +667,8 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
 
   if (E >= 0xffffffffull) throw BuildError{MSGPU_ERR_LIMIT, "chaining supports < 2^32 edges per device"};
   uint32_t     *multi = arena.alloc<uint32_t>(E), *big = arena.alloc<uint32_t>(E);
-  unsigned int *d_cnt = arena.alloc<unsigned int>(2);
-  MSGPU_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned int), st));
+  unsigned int *d_cnt = arena.alloc<unsigned int>(4);
+  MSGPU_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned int), st));
 
   ChainArgs a;
   a.read_nlen = reads.nlen;
@@ -694,9 +694,14 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
     a.n_in     = d_cnt + 0;
     a.list_out = big;
     a.n_out    = d_cnt + 1;
-    MSGPU_LAUNCH("chain_small", st, (chain_list_kernel<kChainSmall, true><<<grid_for(E, 128, 16), 128, 0, st>>>(a)));
+    MSGPU_LAUNCH("chain_tiny", st, (chain_list_kernel<kChainTiny, true><<<grid_for(E, 128, 16), 128, 0, st>>>(a)));
     a.list_in  = big;
     a.n_in     = d_cnt + 1;
+    a.list_out = multi;
+    a.n_out    = d_cnt + 2;
+    MSGPU_LAUNCH("chain_small", st, (chain_list_kernel<kChainSmall, true><<<grid_for(E, 128, 16), 128, 0, st>>>(a)));
+    a.list_in  = multi;
+    a.n_in     = d_cnt + 2;
     a.list_out = nullptr;
     a.n_out    = nullptr;
     MSGPU_LAUNCH("chain_large", st, (chain_list_kernel<kChainMax, false><<<grid_for(E, 128, 4), 128, 0, st>>>(a)));
