@@ -73,7 +73,6 @@ struct RankArgs {
   uint32_t           *heavy_list; // matches of groups too long for one thread each
   unsigned int       *heavy_n;
 };
-constexpr uint32_t kRankHeavy = 512; // groups longer than this are ranked by one warp per match
 
 // match i is the q-th of its group in read order: write its pair row and account its partners to its read
 __device__ __forceinline__ void place_row(const RankArgs &a, uint64_t i, uint32_t u, uint32_t q, uint32_t g1) {
@@ -98,24 +97,80 @@ __device__ __forceinline__ void place_row(const RankArgs &a, uint64_t i, uint32_
   }
 }
 
-__global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a) {
+// Bitonic sort of n = 2^x keys (padded with ~0) in shared memory by `nthreads` cooperating threads (a warp or a CTA)
+template <bool kCta> __device__ __forceinline__ void bitonic_sort_shared(unsigned long long *keys, uint32_t n, uint32_t tid,
+                                                                        uint32_t nthreads) {
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = tid; t < (n >> 1); t += nthreads) {
+        const uint32_t i  = ((t & ~(j - 1)) << 1) | (t & (j - 1)); // the pair (i, i + j), bit j of i clear
+        const bool     up = (i & k) == 0;
+        const unsigned long long x = keys[i], y = keys[i + j];
+        if ((x > y) == up) {
+          keys[i]     = y;
+          keys[i + j] = x;
+        }
+      }
+      if (kCta) __syncthreads(); else __syncwarp();
+    }
+  }
+}
+
+constexpr uint32_t kSortWarpMax = 128;  // groups up to this size: one warp sorts them
+constexpr uint32_t kSortCtaMax  = 4096; // ... up to this size: one CTA; longer ones are ranked by counting (below)
+
+// One warp per group: the keys (read id << 32 | row of the match) are sorted in shared memory, then lane by lane the
+// matches are placed at their position in read order.  Reads are unique inside a group (MatchMap.cpp:64-73 keeps one
+// match per (read, unitig)), so the order is total.  Groups too long for a warp go to `big_groups`.
+__global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a, uint32_t n_groups, uint32_t *__restrict__ big_groups,
+                                                        unsigned int *__restrict__ n_big) {
+  __shared__ unsigned long long sm[256 / 32][kSortWarpMax];
   const MatchSoA &m = a.m;
-  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += uint64_t(gridDim.x) * blockDim.x) {
-    const uint32_t u = m.unitig[i], g0 = a.grp_off[u], g1 = a.grp_off[u + 1], my = m.read[i];
-    if (g1 - g0 > kRankHeavy) { // a repeat: thousands of members; one thread per member would be the tail of the kernel
-      a.heavy_list[atomicAdd(a.heavy_n, 1u)] = uint32_t(i);
+  const unsigned  l = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint64_t  nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  unsigned long long *keys = sm[w];
+  for (uint64_t u = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; u < n_groups; u += nw) {
+    const uint32_t g0 = a.grp_off[u], g1 = a.grp_off[u + 1], k = g1 - g0;
+    if (k == 0) continue;
+    if (k > kSortWarpMax) {
+      if (l == 0) big_groups[atomicAdd(n_big, 1u)] = uint32_t(u);
       continue;
     }
-    // reads are unique inside a group (MatchMap.cpp:64-73 keeps one match per (read, unitig)), so the rank is exact
-    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, j = g0;
-    for (; j + 4 <= g1; j += 4) {
-      r0 += m.read[j] < my;
-      r1 += m.read[j + 1] < my;
-      r2 += m.read[j + 2] < my;
-      r3 += m.read[j + 3] < my;
+    uint32_t n = 2;
+    while (n < k) n <<= 1;
+    for (uint32_t i = l; i < n; i += 32)
+      keys[i] = i < k ? ((unsigned long long)m.read[g0 + i] << 32 | (g0 + i)) : ~0ull;
+    __syncwarp();
+    bitonic_sort_shared<false>(keys, n, l, 32);
+    for (uint32_t j = l; j < k; j += 32) place_row(a, uint32_t(keys[j]), uint32_t(u), g0 + j, g1);
+    __syncwarp();
+  }
+}
+
+// One CTA per longer group; groups beyond kSortCtaMax hand their members to the counting kernel
+__global__ void __launch_bounds__(256) rank_rows_cta_kernel(RankArgs a, const uint32_t *__restrict__ big_groups,
+                                                            const unsigned int *__restrict__ n_big) {
+  extern __shared__ __align__(16) unsigned long long keys_cta[];
+  const MatchSoA &m = a.m;
+  const uint32_t  nb = *n_big;
+  for (uint32_t x = blockIdx.x; x < nb; x += gridDim.x) {
+    const uint32_t u = big_groups[x], g0 = a.grp_off[u], g1 = a.grp_off[u + 1], k = g1 - g0;
+    if (k > kSortCtaMax) {
+      __shared__ unsigned int base;
+      if (threadIdx.x == 0) base = atomicAdd(a.heavy_n, k);
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) a.heavy_list[base + i] = g0 + i;
+      __syncthreads();
+      continue;
     }
-    for (; j < g1; ++j) r0 += m.read[j] < my;
-    place_row(a, i, u, g0 + r0 + r1 + r2 + r3, g1);
+    uint32_t n = 2;
+    while (n < k) n <<= 1;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+      keys_cta[i] = i < k ? ((unsigned long long)m.read[g0 + i] << 32 | (g0 + i)) : ~0ull;
+    __syncthreads();
+    bitonic_sort_shared<true>(keys_cta, n, threadIdx.x, blockDim.x);
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) place_row(a, uint32_t(keys_cta[j]), u, g0 + j, g1);
+    __syncthreads();
   }
 }
 
@@ -1073,8 +1128,14 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   if (M) {
     RankArgs ra{m, unitigs.grp_off, rows, p_read, p_ir0, p_ir1, deg, wgt, arena.alloc<uint32_t>(M), d_u32 + 3};
     // (d_u32[3] doubles as the tile kernels' error flag later: it is reset after this use)
-    MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<gm, 256, 0, st>>>(ra));
+    // groups ordered by read id: a warp sorts a short group, a CTA a longer one, the longest are ranked by counting
+    const uint32_t U = uint32_t(unitigs.n);
+    uint32_t      *big_groups = arena.alloc<uint32_t>(U + 1);
+    MSGPU_CUDA(cudaMemsetAsync(d_u32 + 2, 0, sizeof(uint32_t), st)); // (the too-many-sources flag is set later)
+    MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<grid_for(uint64_t(U) * 32, 256), 256, 0, st>>>(ra, U, big_groups, d_u32 + 2));
+    MSGPU_LAUNCH("rank_rows_cta", st, rank_rows_cta_kernel<<<kNumSMs * 6, 256, kSortCtaMax * sizeof(unsigned long long), st>>>(ra, big_groups, d_u32 + 2));
     MSGPU_LAUNCH("rank_rows_heavy", st, rank_rows_heavy_kernel<<<grid_for(M * 32, 256, 4), 256, 0, st>>>(ra));
+    MSGPU_CUDA(cudaMemsetAsync(d_u32 + 2, 0, sizeof(uint32_t), st));
     MSGPU_CUDA(cudaMemsetAsync(d_u32 + 3, 0, sizeof(uint32_t), st));
   }
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{deg}, R, rd_off, d_u32 + 0);

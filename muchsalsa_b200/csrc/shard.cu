@@ -237,10 +237,14 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    entry_gid_kernel(uint64_t n_entries, EntryTable t, const uint32_t *__restrict__ slot, uint32_t *__restrict__ gid) {
+    entry_gid_kernel(uint64_t n_entries, EntryTable t, const uint32_t *__restrict__ slot, uint32_t *__restrict__ gid,
+                     const uint8_t *__restrict__ first, uint8_t *__restrict__ shared /* may be null */) {
   for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n_entries;
-       e += uint64_t(gridDim.x) * blockDim.x)
-    gid[e] = t.id[slot[e]];
+       e += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t id = t.id[slot[e]];
+    gid[e]            = id;
+    if (shared && !first[e]) shared[id] = 1; // the name occurs in more than one shard
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -277,10 +281,18 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// per (unitig, read) keep the record with the smallest global line (MatchMap.cpp:64-73) — across chunks this time
+// per (unitig, read) keep the record with the smallest global line (MatchMap.cpp:64-73) — across chunks this time.
+// Every chunk is deduplicated already, so only the records of unitigs that occur in several chunks (the groups cut
+// by a chunk boundary, or everything if the PAF is not grouped) can have a duplicate: the others skip the table.
+constexpr uint32_t kNoSlot = 0xffffffffu;
 __global__ void __launch_bounds__(256)
-    shard_dedup_insert_kernel(MatchSoA c, EntryTable t, uint32_t *__restrict__ slot) {
+    shard_dedup_insert_kernel(MatchSoA c, EntryTable t, const uint8_t *__restrict__ shared_unitig,
+                              uint32_t *__restrict__ slot) {
   for (uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < c.n; g += uint64_t(gridDim.x) * blockDim.x) {
+    if (!shared_unitig[c.unitig[g]]) {
+      slot[g] = kNoSlot;
+      continue;
+    }
     unsigned long long key = ((unsigned long long)c.unitig[g] << 32 | c.read[g]) + 1ull;
     uint64_t           q   = mix64(key) & t.mask;
     for (;;) {
@@ -295,7 +307,10 @@ __global__ void __launch_bounds__(256)
 
 struct KeepFlag {
   const uint32_t *line, *slot, *min_line;
-  __device__ uint32_t operator()(uint64_t g) const { return min_line[slot[g]] == line[g] ? 1u : 0u; }
+  __device__ uint32_t operator()(uint64_t g) const {
+    const uint32_t q = slot[g];
+    return (q == kNoSlot || min_line[q] == line[g]) ? 1u : 0u;
+  }
 };
 
 __global__ void __launch_bounds__(256)
@@ -377,7 +392,8 @@ __global__ void __launch_bounds__(256)
 // the name bytes of the headers, so nothing comes back to the host here (counts and the collision flag: `status`)
 static void merge_names(Arena &arena, cudaStream_t st, const ShardView *d_sh, uint32_t n_shards, int which,
                         uint64_t n_entries, uint64_t name_bytes_bound, uint64_t seed, MergeStatus *d_status,
-                        uint32_t *gid, NameTable &out, int32_t *&read_nlen, uint32_t *&read_line) {
+                        uint32_t *gid, NameTable &out, int32_t *&read_nlen, uint32_t *&read_line,
+                        uint8_t *shared = nullptr /* per global id: 1 iff the name occurs in several shards */) {
   const char **name_ptr = arena.alloc<const char *>(n_entries);
   uint32_t    *name_len = arena.alloc<uint32_t>(n_entries), *slot = arena.alloc<uint32_t>(n_entries);
   uint32_t    *rank = arena.alloc<uint32_t>(n_entries);
@@ -397,7 +413,7 @@ static void merge_names(Arena &arena, cudaStream_t st, const ShardView *d_sh, ui
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint8_t, uint32_t>{first}, n_entries, rank, &d_status->n_ids[which]);
   if (n_entries) {
     MSGPU_LAUNCH("entry_assign", st, entry_assign_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, which, n_entries, t, slot, first, rank, name_ptr, name_len, id_name_ptr, id_name_len, read_nlen, read_line));
-    MSGPU_LAUNCH("entry_gid", st, entry_gid_kernel<<<g, 256, 0, st>>>(n_entries, t, slot, gid));
+    MSGPU_LAUNCH("entry_gid", st, entry_gid_kernel<<<g, 256, 0, st>>>(n_entries, t, slot, gid, first, shared));
   }
   out.name_off = arena.alloc<uint64_t>(n_entries + 1);
   exclusive_scan<uint64_t>(arena, st, IdNameLen{id_name_len, &d_status->n_ids[which]}, n_entries + 1, out.name_off,
@@ -470,7 +486,9 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
     int32_t  *no_nlen = nullptr;
     uint32_t *no_line = nullptr;
     merge_names(arena, st, d_sh, n_shards, 0, rb, rbytes, seed, d_status, gid_r, reads, reads.nlen, reads.line);
-    merge_names(arena, st, d_sh, n_shards, 1, ub, ubytes, seed, d_status, gid_u, unitigs, no_nlen, no_line);
+    uint8_t *shared_u = arena.alloc<uint8_t>(ub + 1);
+    MSGPU_CUDA(cudaMemsetAsync(shared_u, 0, ub + 1, st));
+    merge_names(arena, st, d_sh, n_shards, 1, ub, ubytes, seed, d_status, gid_u, unitigs, no_nlen, no_line, shared_u);
 
     // ---- records: renumber, deduplicate across chunks (capacity = all records), group by unitig
     MatchSoA c;
@@ -479,7 +497,7 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
     if (mb) MSGPU_LAUNCH("remap_matches", st, remap_matches_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, mb, gid_r, gid_u, c));
     EntryTable dt   = make_entry_table(arena, st, mb);
     uint32_t  *slot = arena.alloc<uint32_t>(mb), *pos = arena.alloc<uint32_t>(mb);
-    if (mb) MSGPU_LAUNCH("dedup_insert", st, shard_dedup_insert_kernel<<<g, 256, 0, st>>>(c, dt, slot));
+    if (mb) MSGPU_LAUNCH("dedup_insert", st, shard_dedup_insert_kernel<<<g, 256, 0, st>>>(c, dt, shared_u, slot));
     KeepFlag keep{c.line, slot, dt.min_entry};
     exclusive_scan<uint32_t>(arena, st, keep, mb, pos, &d_status->n_matches);
     alloc_match_soa(arena, m, mb);
