@@ -56,7 +56,7 @@ constexpr uint32_t kSrcCap     = 512;            // sources per tile
 constexpr uint32_t kHalfCap    = kTileCap / 2;
 constexpr uint32_t kSrcRatio   = kHalfCap / (kSrcCap / 2); // a source weighs at least this much when tiles are packed
 constexpr int      kItems      = kTileCap / kFusedBlock;   // sort items per thread
-constexpr int      kMergeCtas  = kIdxBits <= 12 ? 3 : 2;    // resident CTAs of the merge kernel per SM (narrow words)
+constexpr int      kMergeCtas  = kIdxBits <= 12 ? 4 : 2;    // resident CTAs of the merge kernel per SM (narrow words)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // pre-pass 1: order every group by read id, build the pair rows, and accumulate per read its number of sources and

@@ -108,6 +108,14 @@ def test_heavy_rows_vs_oracle(builder, oracle):
     assert got.counts["em"] > 4_000_000
 
 
+def test_group_longer_than_the_cta_sort_vs_oracle(builder, oracle):
+    """A unitig matched by 4 500 reads: its group is too long for the shared-memory sorts of rank_rows (warp: 128,
+    CTA: 4096) and is ranked by the counting kernel; next to it groups of every other size class."""
+    paf = util.heavy_rows_paf(k0=4500, k1=700, shared_from=4200, seed=5, small_groups=60)
+    got = _same(builder, oracle, paf)
+    assert got.counts["em"] > 2_000_000
+
+
 def test_sort_based_variant_agrees_with_fused(builder, monkeypatch):
     """The sort-based pairing (global radix sort of the candidate stream) is an independent implementation of the
     same tables: both variants must agree bit for bit."""
