@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Small end-to-end exercise of every kernel of the library for compute-sanitizer (memcheck / racecheck):
-construction from PAF (grouped and shuffled), heavy rows, a 3-rank sharded build, the sequence store."""
+construction from PAF (grouped and shuffled), heavy rows, chaining + edge filters, a 3-rank sharded build, the
+sequence store."""
 import os
 import sys
 
@@ -22,6 +23,10 @@ heavy = util.heavy_rows_paf(k0=1500, k1=1200, shared_from=500, small_groups=10)
 with GraphBuilder(0) as gb:
     for name, paf in (("small", small), ("shuffled", shuffled), ("heavy", heavy), ("kat8", util.kat8_paf())):
         print(name, gb.build_from_buffer(paf).counts(), flush=True)
+        gb.chain_overlaps(300).edge_filters(300)  # the stages after construction: chain.cu, filter.cu
+        f = gb.filters()
+        print("  orders", int(gb.orders()["left"].size), "contraction edges", int((f["contraction_order"] >= 0).sum()),
+              flush=True)
     ufa, nfa = synth.generate_sequences("small")
     gb.seq_load_buffers(ufa[:30000], nfa[:30000], False)
     uid = gb.seq_id(0, "u0")
