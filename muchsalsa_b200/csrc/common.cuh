@@ -42,33 +42,35 @@ public:
     m_used = m_high = 0;
     if (m_counter) cudaFree(m_counter);
     m_counter = nullptr;
-    if (m_scan_state) cudaFree(m_scan_state);
-    m_scan_state       = nullptr;
-    m_scan_state_bytes = 0;
+    for (int k = 0; k < 4; ++k) {
+      if (m_scan_state[k]) cudaFree(m_scan_state[k]);
+      m_scan_state[k]       = nullptr;
+      m_scan_state_bytes[k] = 0;
+    }
   }
-  // Status words of the single-pass scans (scan.cuh): a region that outlives reset() and that nothing else writes.
-  // Every call hands out the next epoch; flags written under an older epoch read as "not ready", so the region is
-  // cleared only when it grows or when the 16-bit epoch wraps.
-  void *scan_state(size_t bytes, cudaStream_t st, unsigned *epoch) {
-    if (bytes > m_scan_state_bytes) {
-      if (m_scan_state) {
+  // Status words of the single-pass scans (scan.cuh): regions that outlive reset() and that nothing else writes, one
+  // per slot (up to four scans run concurrently in one launch).  Every call hands out the next epoch; flags written
+  // under an older epoch read as "not ready", so a region is cleared only when it grows or when the 16-bit epoch wraps.
+  void *scan_state(int slot, size_t bytes, cudaStream_t st, unsigned *epoch) {
+    if (bytes > m_scan_state_bytes[slot]) {
+      if (m_scan_state[slot]) {
         MSGPU_CUDA(cudaStreamSynchronize(st));
-        cudaFree(m_scan_state);
+        cudaFree(m_scan_state[slot]);
       }
-      m_scan_state_bytes = bytes < (size_t(1) << 20) ? (size_t(1) << 20) : bytes * 2;
-      MSGPU_CUDA(cudaMalloc(&m_scan_state, m_scan_state_bytes));
-      MSGPU_CUDA(cudaMemsetAsync(m_scan_state, 0, m_scan_state_bytes, st));
-      m_epoch = 0;
+      m_scan_state_bytes[slot] = bytes < (size_t(1) << 18) ? (size_t(1) << 18) : bytes * 2;
+      MSGPU_CUDA(cudaMalloc(&m_scan_state[slot], m_scan_state_bytes[slot]));
+      MSGPU_CUDA(cudaMemsetAsync(m_scan_state[slot], 0, m_scan_state_bytes[slot], st));
     }
     if (++m_epoch >= (1u << 16)) {
-      MSGPU_CUDA(cudaMemsetAsync(m_scan_state, 0, m_scan_state_bytes, st));
+      for (int k = 0; k < 4; ++k)
+        if (m_scan_state[k]) MSGPU_CUDA(cudaMemsetAsync(m_scan_state[k], 0, m_scan_state_bytes[k], st));
       MSGPU_CUDA(cudaMemsetAsync(counter() + 8, 0, 32 * sizeof(unsigned), st)); // the scans' ring of ticket counters
       m_epoch = 1;
     }
     *epoch = m_epoch;
-    return m_scan_state;
+    return m_scan_state[slot];
   }
-  // a zero-initialised device counter that outlives reset(): kernels that use it leave it at zero again
+  // zero-initialised device counters that outlive reset(): kernels that use them leave them at zero again
   unsigned *counter() {
     if (!m_counter) {
       MSGPU_CUDA(cudaMalloc(&m_counter, 512)); // [0..7] kernels' own counters, [8..39] ticket ring of the scans
@@ -119,8 +121,8 @@ private:
   std::vector<Slab> m_slabs;
   size_t            m_used = 0, m_high = 0;
   unsigned         *m_counter = nullptr;
-  void             *m_scan_state = nullptr;
-  size_t            m_scan_state_bytes = 0;
+  void             *m_scan_state[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t            m_scan_state_bytes[4] = {0, 0, 0, 0};
   unsigned          m_epoch = 0;
 };
 

@@ -521,16 +521,30 @@ struct NameLen {
   __device__ uint64_t operator()(uint64_t i) const { return i < *d_n ? uint64_t(len[i]) : 0ull; }
 };
 
-// name_off[i] = exclusive prefix of the name lengths for i <= count (name_off[count] is the total); names gathered from the PAF text.  `cap` bounds the count, `cap_bytes` the total length.
-static void build_name_table(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t cap, uint64_t cap_bytes,
-                             const unsigned *d_n, const uint64_t *src, const uint32_t *len,
-                             unsigned long long *d_total_bytes, NameTable &out) {
-  out.name_off = arena.alloc<uint64_t>(cap + 1);
-  exclusive_scan<uint64_t>(arena, st, NameLen{len, d_n}, cap + 1, out.name_off,
-                           reinterpret_cast<uint64_t *>(d_total_bytes), ScanLive{d_n, nullptr, 1}); // name_off[0 .. n]
-  out.names = arena.alloc<char>(cap_bytes);
-  if (cap) {
-    MSGPU_LAUNCH("gather_names", st, gather_names_kernel<<<grid_for(cap * 32, 256, 2), 256, 0, st>>>(d_paf, src, out.name_off, d_n, out.names));
+// name_off[i] = exclusive prefix of the name lengths for i <= count (name_off[count] is the total); names gathered
+// from the PAF text.  `cap` bounds the counts, `cap_bytes` the total lengths.  Both tables at once: their two scans
+// share a launch.
+struct NameJob {
+  const unsigned     *d_n;
+  const uint64_t     *src;
+  const uint32_t     *len;
+  unsigned long long *d_total_bytes;
+  NameTable          *out;
+};
+static void build_name_tables(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t cap, uint64_t cap_bytes,
+                              const NameJob &a, const NameJob &b) {
+  a.out->name_off = arena.alloc<uint64_t>(cap + 1);
+  b.out->name_off = arena.alloc<uint64_t>(cap + 1);
+  run_scans(arena, st,
+            scan_job<uint64_t>(arena, st, 0, NameLen{a.len, a.d_n}, cap + 1, a.out->name_off,
+                               reinterpret_cast<uint64_t *>(a.d_total_bytes), ScanLive{a.d_n, nullptr, 1}),
+            scan_job<uint64_t>(arena, st, 1, NameLen{b.len, b.d_n}, cap + 1, b.out->name_off,
+                               reinterpret_cast<uint64_t *>(b.d_total_bytes), ScanLive{b.d_n, nullptr, 1}));
+  for (const NameJob *j : {&a, &b}) {
+    j->out->names = arena.alloc<char>(cap_bytes);
+    if (cap) {
+      MSGPU_LAUNCH("gather_names", st, gather_names_kernel<<<grid_for(cap * 32, 256, 2), 256, 0, st>>>(d_paf, j->src, j->out->name_off, j->d_n, j->out->names));
+    }
   }
 }
 
@@ -661,12 +675,14 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.rhash, d_status, rt, rslot));
     MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.uhash, d_status, ut, uslot));
     MSGPU_LAUNCH("intern_verify", st, intern_verify_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, f, rt, rslot, ut, uslot, d_status));
-    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstRead}, cap, rank_a, &d_status->n_reads, live_lines);
-    exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFFirstUnitig}, cap, rank_b, &d_status->n_unitigs, live_lines);
+    run_scans(arena, st,
+              scan_job<uint32_t>(arena, st, 0, FlagBit<uint32_t>{f.flags, kFFirstRead}, cap, rank_a, &d_status->n_reads, live_lines),
+              scan_job<uint32_t>(arena, st, 1, FlagBit<uint32_t>{f.flags, kFFirstUnitig}, cap, rank_b, &d_status->n_unitigs, live_lines));
     MSGPU_LAUNCH("intern_assign", st, intern_assign_kernel<<<grid_lines, 256, 0, st>>>(line_start, d_status, f, rt, rslot, rank_a, ut, uslot, rank_b,
                                                      reads.nlen, reads.line, rsrc, rlen, usrc, ulen));
-    build_name_table(arena, st, d_paf, cap_acc, n_bytes, &d_status->n_reads, rsrc, rlen, &d_status->read_name_bytes, reads);
-    build_name_table(arena, st, d_paf, cap_acc, n_bytes, &d_status->n_unitigs, usrc, ulen, &d_status->unitig_name_bytes, unitigs);
+    build_name_tables(arena, st, d_paf, cap_acc, n_bytes,
+                      NameJob{&d_status->n_reads, rsrc, rlen, &d_status->read_name_bytes, &reads},
+                      NameJob{&d_status->n_unitigs, usrc, ulen, &d_status->unitig_name_bytes, &unitigs});
 
     // ---- K4 dedup
     InternTable dt = make_table(arena, st, cap_acc + cap_acc / 2);

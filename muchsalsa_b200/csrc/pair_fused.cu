@@ -1138,19 +1138,19 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
     MSGPU_CUDA(cudaMemsetAsync(d_u32 + 2, 0, sizeof(uint32_t), st));
     MSGPU_CUDA(cudaMemsetAsync(d_u32 + 3, 0, sizeof(uint32_t), st));
   }
-  exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{deg}, R, rd_off, d_u32 + 0);
-  MSGPU_CUDA(cudaMemcpyAsync(rd_off + R, d_u32 + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-
-  // ---- tile planning
+  // ---- tile planning: four independent scans over the reads in one launch (source offsets, clipped row weights,
+  // slice-table offsets, the pair count), then the tile index, which needs the weights' prefix
   RowPlan   plan{deg, wgt};
-  uint64_t *prefix = arena.alloc<uint64_t>(R + 1);
-  exclusive_scan<uint64_t>(arena, st, ClippedWeight{plan}, R, prefix, (uint64_t *)nullptr);
-  TileCount tc{plan, prefix};
+  uint64_t *prefix = arena.alloc<uint64_t>(R + 1), *slice_off = arena.alloc<uint64_t>(R + 1);
   uint32_t *tile_idx = arena.alloc<uint32_t>(R + 1);
+  MSGPU_CUDA(cudaMemsetAsync(d_u64, 0, 4 * sizeof(uint64_t), st)); // (totals of empty scans)
+  run_scans(arena, st, scan_job<uint32_t>(arena, st, 0, LoadAs<uint32_t, uint32_t>{deg}, R, rd_off, d_u32 + 0),
+            scan_job<uint64_t>(arena, st, 1, ClippedWeight{plan}, R, prefix, (uint64_t *)nullptr),
+            scan_job<uint64_t>(arena, st, 2, SliceCount{plan}, R, slice_off, d_u64 + 0),
+            scan_job<uint64_t>(arena, st, 3, WeightOf{wgt}, R, (uint64_t *)nullptr, d_u64 + 1));
+  MSGPU_CUDA(cudaMemcpyAsync(rd_off + R, d_u32 + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  TileCount tc{plan, prefix};
   exclusive_scan<uint32_t>(arena, st, tc, R, tile_idx, d_u32 + 1);
-  uint64_t *slice_off = arena.alloc<uint64_t>(R + 1);
-  exclusive_scan<uint64_t>(arena, st, SliceCount{plan}, R, slice_off, d_u64 + 0);
-  exclusive_scan<uint64_t>(arena, st, WeightOf{wgt}, R, (uint64_t *)nullptr, d_u64 + 1);
   uint32_t h32[4];
   uint64_t h64[4];
   MSGPU_CUDA(cudaMemcpyAsync(h32, d_u32, sizeof(h32), cudaMemcpyDeviceToHost, st));
@@ -1247,8 +1247,9 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
       MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
     }
   }
-  exclusive_scan<unsigned long long>(arena, st, TileValid{tile_cnt}, my_tiles, em_base, totals + 0);
-  exclusive_scan<unsigned long long>(arena, st, TileHeads{tile_cnt}, my_tiles, ed_base, totals + 1);
+  MSGPU_CUDA(cudaMemsetAsync(totals, 0, 2 * sizeof(unsigned long long), st));
+  run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{tile_cnt}, my_tiles, em_base, totals + 0),
+            scan_job<unsigned long long>(arena, st, 1, TileHeads{tile_cnt}, my_tiles, ed_base, totals + 1));
   if (!my_tiles) MSGPU_CUDA(cudaMemsetAsync(e.em_begin, 0, sizeof(uint64_t), st)); // an empty CSR: em_begin[0] = 0
   if (my_tiles) {
     EmitArgs ea;

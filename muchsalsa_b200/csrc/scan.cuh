@@ -36,27 +36,40 @@ struct ScanLive { // live = min(n, *p32 or *p64 (whichever is set) + extra); bot
   uint64_t                  extra = 0;
 };
 
-template <class T, class InFn>
-__global__ void __launch_bounds__(kScanBlock)
-    scan_onepass_kernel(InFn in, uint64_t n_cap, ScanLive live, T *out /* may alias the input; may be null */,
-                        T *__restrict__ total_out, unsigned long long *state, unsigned epoch,
-                        unsigned *counters /* ring of ticket counters, one per epoch */) {
+// One scan of a launch: what to scan and where its status words and ticket counter live
+template <class T, class InFn> struct ScanJob {
+  using value_type = T;
+  InFn                in;
+  uint64_t            n_cap;
+  ScanLive            live;
+  T                  *out;       // may alias the input; may be null
+  T                  *total_out; // device; may be null
+  unsigned long long *state;
+  unsigned            epoch;
+};
+
+// the work of one block of one scan; blocks past the scan's tiles (a launch is sized for its longest scan) leave
+template <class Job> __device__ __forceinline__ void scan_block(const Job &job, unsigned *counters) {
+  using T = typename Job::value_type;
   constexpr int       kWarps = kScanBlock / 32;
   __shared__ unsigned s_tile;
   __shared__ uint64_t s_n;
-  __shared__ T        w_tot[kWarps]; // warp totals of the tile, then their exclusive prefix
+  __shared__ T        w_tot[kWarps]; // warp totals of the tile
   __shared__ T        w_sum[kWarps];
   __shared__ unsigned w_inc[kWarps];
+  const uint64_t n_tiles_cap = (job.n_cap + kScanTile - 1) / kScanTile;
+  if (blockIdx.x >= n_tiles_cap) return;
+  const unsigned epoch = job.epoch;
   const unsigned l = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     // the ticket counter of this scan; the slot half a ring ahead is cleared for a later scan (scans on one stream
-    // are ordered, so nobody is using it)
-    s_tile = atomicAdd(&counters[epoch & 31u], 1u);
+    // are ordered, so nobody is using it).  A one-tile scan needs no ticket.
+    s_tile = n_tiles_cap > 1 ? atomicAdd(&counters[epoch & 31u], 1u) : 0u;
     if (blockIdx.x == 0) counters[(epoch + 16u) & 31u] = 0u;
-    uint64_t n = n_cap;
-    if (live.p32 || live.p64) {
-      const uint64_t c = (live.p32 ? uint64_t(*live.p32) : uint64_t(*live.p64)) + live.extra;
-      n                = c < n_cap ? c : n_cap;
+    uint64_t n = job.n_cap;
+    if (job.live.p32 || job.live.p64) {
+      const uint64_t c = (job.live.p32 ? uint64_t(*job.live.p32) : uint64_t(*job.live.p64)) + job.live.extra;
+      n                = c < job.n_cap ? c : job.n_cap;
     }
     s_n = n;
   }
@@ -72,7 +85,7 @@ __global__ void __launch_bounds__(kScanBlock)
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
     const uint64_t i = wbase + uint64_t(j) * 32 + l;
-    v[j]             = i < n ? in(i) : T(0);
+    v[j]             = i < n ? job.in(i) : T(0);
   }
   T carry = 0; // exclusive prefix inside the warp's run
 #pragma unroll
@@ -91,69 +104,114 @@ __global__ void __launch_bounds__(kScanBlock)
     wex += ww < int(w) ? c : T(0);
     total += c;
   }
-  volatile unsigned long long *vs  = state;
-  const unsigned long long     tag = (unsigned long long)(epoch & kScanEpochMask) << 2;
-  if ((unsigned long long)total >> (64 - kScanValShift)) __trap();
-  if (threadIdx.x == 0) vs[tile] = ((unsigned long long)total << kScanValShift) | tag | (tile == 0 ? 2ull : 1ull);
   T prefix = 0;
-  if (tile > 0) {
-    long long hi = (long long)tile - 1; // window = tiles hi, hi-1, ..., hi-(kScanBlock-1)
-    while (true) {
-      const long long    p    = hi - (long long)threadIdx.x;
-      unsigned long long word = 0;
-      if (p >= 0) {
-        word = vs[p];
-        while ((word & (kScanEpochMask << 2)) != tag || (word & 3ull) == 0ull) {
-          __nanosleep(32);
+  if (last_tile > 0) { // several live tiles: publish, look back
+    volatile unsigned long long *vs  = job.state;
+    const unsigned long long     tag = (unsigned long long)(epoch & kScanEpochMask) << 2;
+    if ((unsigned long long)total >> (64 - kScanValShift)) __trap();
+    if (threadIdx.x == 0) vs[tile] = ((unsigned long long)total << kScanValShift) | tag | (tile == 0 ? 2ull : 1ull);
+    if (tile > 0) {
+      long long hi = (long long)tile - 1; // window = tiles hi, hi-1, ..., hi-(kScanBlock-1)
+      while (true) {
+        const long long    p    = hi - (long long)threadIdx.x;
+        unsigned long long word = 0;
+        if (p >= 0) {
           word = vs[p];
+          while ((word & (kScanEpochMask << 2)) != tag || (word & 3ull) == 0ull) {
+            __nanosleep(32);
+            word = vs[p];
+          }
         }
-      }
-      const bool     is_incl = p >= 0 && (word & 3ull) == 2ull;
-      const unsigned im      = __ballot_sync(0xffffffffu, is_incl);
-      const unsigned stop    = im ? unsigned(__ffs(im) - 1) : 32u; // nearest predecessor with an inclusive prefix
-      T              x       = (p >= 0 && l <= stop) ? T(word >> kScanValShift) : T(0);
-      x                      = warp_reduce_sum(x);
-      if (l == 0) {
-        w_sum[w] = x;
-        w_inc[w] = im != 0u;
-      }
-      __syncthreads();
-      bool done = false;
+        const bool     is_incl = p >= 0 && (word & 3ull) == 2ull;
+        const unsigned im      = __ballot_sync(0xffffffffu, is_incl);
+        const unsigned stop    = im ? unsigned(__ffs(im) - 1) : 32u; // nearest predecessor with an inclusive prefix
+        T              x       = (p >= 0 && l <= stop) ? T(word >> kScanValShift) : T(0);
+        x                      = warp_reduce_sum(x);
+        if (l == 0) {
+          w_sum[w] = x;
+          w_inc[w] = im != 0u;
+        }
+        __syncthreads();
+        bool done = false;
 #pragma unroll
-      for (int ww = 0; ww < kWarps; ++ww) {
-        if (!done) prefix += w_sum[ww];
-        done = done || w_inc[ww] != 0u;
+        for (int ww = 0; ww < kWarps; ++ww) {
+          if (!done) prefix += w_sum[ww];
+          done = done || w_inc[ww] != 0u;
+        }
+        __syncthreads();
+        if (done || hi - kScanBlock < 0) break;
+        hi -= kScanBlock;
       }
-      __syncthreads();
-      if (done || hi - kScanBlock < 0) break;
-      hi -= kScanBlock;
+      if ((unsigned long long)(prefix + total) >> (64 - kScanValShift)) __trap();
+      if (threadIdx.x == 0) vs[tile] = ((unsigned long long)(prefix + total) << kScanValShift) | tag | 2ull;
     }
-    if ((unsigned long long)(prefix + total) >> (64 - kScanValShift)) __trap();
-    if (threadIdx.x == 0) vs[tile] = ((unsigned long long)(prefix + total) << kScanValShift) | tag | 2ull;
   }
-  if (threadIdx.x == 0 && tile == last_tile && total_out) *total_out = prefix + total;
-  if (out) {
+  if (threadIdx.x == 0 && tile == last_tile && job.total_out) *job.total_out = prefix + total;
+  if (job.out) {
     const T off = prefix + wex;
 #pragma unroll
     for (int j = 0; j < kScanItems; ++j) {
       const uint64_t i = wbase + uint64_t(j) * 32 + l;
-      if (i < n) out[i] = off + v[j];
+      if (i < n) job.out[i] = off + v[j];
     }
   }
 }
 
-// out[i] = sum_{j<i} in(j) for i < n; *total_out (device) = sum of all.  `out` may be null (total only).
-// n == 0 is allowed (total = 0).  With `live`, see above: outputs exist for i < live only.
+// up to four independent scans in ONE launch (blockIdx.y picks the scan): they cost the latency of one
+template <class J0> __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, unsigned *counters) {
+  scan_block(j0, counters);
+}
+template <class J0, class J1> __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, J1 j1, unsigned *counters) {
+  if (blockIdx.y == 0) scan_block(j0, counters); else scan_block(j1, counters);
+}
+template <class J0, class J1, class J2, class J3>
+__global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, J1 j1, J2 j2, J3 j3, unsigned *counters) {
+  if (blockIdx.y == 0) scan_block(j0, counters);
+  else if (blockIdx.y == 1) scan_block(j1, counters);
+  else if (blockIdx.y == 2) scan_block(j2, counters);
+  else scan_block(j3, counters);
+}
+
+// Prepares a job: out[i] = sum_{j<i} in(j) for i < n; *total_out (device) = sum of all.  `out` may be null (total
+// only).  With `live`, see above: outputs exist for i < live only.  `slot` = which of the (up to four) concurrent
+// scans of the coming launch this is; each gets its own status words and epoch.
+template <class T, class InFn>
+ScanJob<T, InFn> scan_job(Arena &arena, cudaStream_t st, int slot, InFn in, uint64_t n, T *out, T *total_out,
+                          ScanLive live = ScanLive{}) {
+  const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  unsigned       epoch   = 0;
+  auto *state = static_cast<unsigned long long *>(arena.scan_state(slot, n_tiles * sizeof(unsigned long long), st, &epoch));
+  return ScanJob<T, InFn>{in, n, live, out, total_out, state, epoch};
+}
+inline unsigned scan_grid(uint64_t n) { return unsigned((n + kScanTile - 1) / kScanTile); }
+
+template <class J0> void run_scans(Arena &arena, cudaStream_t st, const J0 &j0) {
+  if (!j0.n_cap) return;
+  MSGPU_LAUNCH("scan", st, scan_kernel<J0><<<scan_grid(j0.n_cap), kScanBlock, 0, st>>>(j0, arena.counter() + 8));
+}
+template <class J0, class J1> void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1) {
+  const uint64_t n = j0.n_cap > j1.n_cap ? j0.n_cap : j1.n_cap;
+  if (!n) return;
+  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1><<<dim3(scan_grid(n), 2), kScanBlock, 0, st>>>(j0, j1, arena.counter() + 8)));
+}
+template <class J0, class J1, class J2, class J3>
+void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1, const J2 &j2, const J3 &j3) {
+  uint64_t n = j0.n_cap;
+  n          = j1.n_cap > n ? j1.n_cap : n;
+  n          = j2.n_cap > n ? j2.n_cap : n;
+  n          = j3.n_cap > n ? j3.n_cap : n;
+  if (!n) return;
+  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1, J2, J3><<<dim3(scan_grid(n), 4), kScanBlock, 0, st>>>(j0, j1, j2, j3, arena.counter() + 8)));
+}
+
+// a single scan.  n == 0 is allowed (total = 0).
 template <class T, class InFn>
 void exclusive_scan(Arena &arena, cudaStream_t st, InFn in, uint64_t n, T *out, T *total_out, ScanLive live = ScanLive{}) {
   if (n == 0) {
     if (total_out) MSGPU_CUDA(cudaMemsetAsync(total_out, 0, sizeof(T), st));
     return;
   }
-  const uint64_t      n_tiles = (n + kScanTile - 1) / kScanTile;
-  unsigned            epoch   = 0;
-  unsigned long long *state   = static_cast<unsigned long long *>(arena.scan_state(n_tiles * sizeof(unsigned long long), st, &epoch));
-  MSGPU_LAUNCH("scan", st, scan_onepass_kernel<T, InFn><<<(unsigned)n_tiles, kScanBlock, 0, st>>>(in, n, live, out, total_out, state, epoch, arena.counter() + 8));
+  run_scans(arena, st, scan_job<T, InFn>(arena, st, 0, in, n, out, total_out, live));
 }
 
 // common input functors
