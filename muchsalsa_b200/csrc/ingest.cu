@@ -286,9 +286,14 @@ struct InternTable {
   uint64_t            mask;
 };
 
+// (both registries in one launch: blockIdx.y = 0 reads, 1 unitigs)
 __global__ void __launch_bounds__(256)
-    intern_insert_kernel(const uint8_t *__restrict__ flags, const uint64_t *__restrict__ hash,
-                         const IngestStatus *__restrict__ status, InternTable t, uint32_t *__restrict__ slot_of_line) {
+    intern_insert_kernel(const uint8_t *__restrict__ flags, const uint64_t *__restrict__ rhash,
+                         const uint64_t *__restrict__ uhash, const IngestStatus *__restrict__ status, InternTable rt,
+                         InternTable ut, uint32_t *__restrict__ rslot, uint32_t *__restrict__ uslot) {
+  const uint64_t *__restrict__ hash = blockIdx.y ? uhash : rhash;
+  const InternTable t               = blockIdx.y ? ut : rt;
+  uint32_t *__restrict__ slot_of_line = blockIdx.y ? uslot : rslot;
   const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
@@ -495,16 +500,20 @@ static uint64_t next_pow2(uint64_t x) {
   return p;
 }
 
-static InternTable make_table(Arena &arena, cudaStream_t st, uint64_t min_slots) {
-  InternTable t;
-  uint64_t    cap = next_pow2(min_slots);
-  t.keys          = arena.alloc<unsigned long long>(cap);
-  t.minline       = arena.alloc<uint32_t>(cap);
-  t.id            = arena.alloc<uint32_t>(cap);
-  t.mask          = cap - 1;
-  MSGPU_CUDA(cudaMemsetAsync(t.keys, 0, cap * sizeof(unsigned long long), st));
-  MSGPU_CUDA(cudaMemsetAsync(t.minline, 0xff, cap * sizeof(uint32_t), st));
-  return t;
+// the three open-addressing tables of an ingest (reads, unitigs, (unitig, read) keys), same capacity each; their keys
+// are one allocation and their min-line words another, so two memsets initialise all of them
+static void make_tables(Arena &arena, cudaStream_t st, uint64_t min_slots, InternTable (&t)[3]) {
+  const uint64_t      cap     = next_pow2(min_slots);
+  unsigned long long *keys    = arena.alloc<unsigned long long>(3 * cap);
+  uint32_t           *minline = arena.alloc<uint32_t>(3 * cap);
+  for (int k = 0; k < 3; ++k) {
+    t[k].keys    = keys + k * cap;
+    t[k].minline = minline + k * cap;
+    t[k].id      = arena.alloc<uint32_t>(cap);
+    t[k].mask    = cap - 1;
+  }
+  MSGPU_CUDA(cudaMemsetAsync(keys, 0, 3 * cap * sizeof(unsigned long long), st));
+  MSGPU_CUDA(cudaMemsetAsync(minline, 0xff, 3 * cap * sizeof(uint32_t), st));
 }
 
 template <class T> static T read_back(cudaStream_t st, const T *d) {
@@ -671,9 +680,10 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
 
     const ScanLive live_lines{nullptr, &d_status->n_lines, 0}; // the per-line scans stop at the actual line count
     // ---- K3 interning
-    InternTable rt = make_table(arena, st, cap_acc + cap_acc / 2), ut = make_table(arena, st, cap_acc + cap_acc / 2);
-    MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.rhash, d_status, rt, rslot));
-    MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<grid_lines, 256, 0, st>>>(f.flags, f.uhash, d_status, ut, uslot));
+    InternTable tables[3];
+    make_tables(arena, st, cap_acc + cap_acc / 2, tables);
+    const InternTable rt = tables[0], ut = tables[1], dt = tables[2];
+    MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<dim3(grid_lines, 2), 256, 0, st>>>(f.flags, f.rhash, f.uhash, d_status, rt, ut, rslot, uslot));
     MSGPU_LAUNCH("intern_verify", st, intern_verify_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, f, rt, rslot, ut, uslot, d_status));
     run_scans(arena, st,
               scan_job<uint32_t>(arena, st, 0, FlagBit<uint32_t>{f.flags, kFFirstRead}, cap, rank_a, &d_status->n_reads, live_lines),
@@ -685,7 +695,6 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
                       NameJob{&d_status->n_unitigs, usrc, ulen, &d_status->unitig_name_bytes, &unitigs});
 
     // ---- K4 dedup
-    InternTable dt = make_table(arena, st, cap_acc + cap_acc / 2);
     MSGPU_LAUNCH("dedup_insert", st, dedup_insert_kernel<<<grid_lines, 256, 0, st>>>(d_status, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line, uid_of_line));
     MSGPU_LAUNCH("dedup_flag", st, dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(d_status, f.flags, dt, dslot));
 

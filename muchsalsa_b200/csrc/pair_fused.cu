@@ -1114,36 +1114,36 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   PairRow  *rows   = arena.alloc<PairRow>(M);
   uint32_t *p_read = arena.alloc<uint32_t>(M);
   int32_t  *p_ir0 = arena.alloc<int32_t>(M), *p_ir1 = arena.alloc<int32_t>(M);
-  uint32_t           *deg    = arena.alloc<uint32_t>(R + 1);
-  unsigned long long *wgt    = arena.alloc<unsigned long long>(R + 1);
-  uint32_t           *cursor = arena.alloc<uint32_t>(R + 1);
+  // everything that must start at zero lives in one block, cleared by one memset: per-read counters, the flags and
+  // counters of the kernels, the totals of the scans
+  const size_t z_deg = 0, z_cursor = z_deg + (R + 1) * sizeof(uint32_t), z_wgt = ((z_cursor + (R + 1) * sizeof(uint32_t)) + 7) & ~size_t(7);
+  const size_t z_u32 = z_wgt + (R + 1) * sizeof(unsigned long long), z_u64 = z_u32 + 8 * sizeof(uint32_t);
+  const size_t z_tot = z_u64 + 4 * sizeof(uint64_t), z_end = z_tot + 2 * sizeof(unsigned long long);
+  char        *zero  = arena.alloc<char>(z_end);
+  MSGPU_CUDA(cudaMemsetAsync(zero, 0, z_end, st));
+  uint32_t           *deg    = reinterpret_cast<uint32_t *>(zero + z_deg);
+  uint32_t           *cursor = reinterpret_cast<uint32_t *>(zero + z_cursor);
+  unsigned long long *wgt    = reinterpret_cast<unsigned long long *>(zero + z_wgt);
+  uint32_t           *d_u32  = reinterpret_cast<uint32_t *>(zero + z_u32); // [0] sources [1] tiles [2] too many sources
+                                                                           // [3] tile error [4] big groups [5] heavy matches
+  uint64_t           *d_u64  = reinterpret_cast<uint64_t *>(zero + z_u64);
+  unsigned long long *totals = reinterpret_cast<unsigned long long *>(zero + z_tot);
   uint32_t           *rd_off = arena.alloc<uint32_t>(R + 1);
-  uint32_t           *d_u32  = arena.alloc<uint32_t>(4);
-  uint64_t           *d_u64  = arena.alloc<uint64_t>(4);
-  MSGPU_CUDA(cudaMemsetAsync(deg, 0, (R + 1) * sizeof(uint32_t), st));
-  MSGPU_CUDA(cudaMemsetAsync(wgt, 0, (R + 1) * sizeof(unsigned long long), st));
-  MSGPU_CUDA(cudaMemsetAsync(cursor, 0, (R + 1) * sizeof(uint32_t), st));
-  MSGPU_CUDA(cudaMemsetAsync(d_u32, 0, 4 * sizeof(uint32_t), st));
   const int gm = grid_for(M, 256), gr = grid_for(R, 256);
   if (M) {
-    RankArgs ra{m, unitigs.grp_off, rows, p_read, p_ir0, p_ir1, deg, wgt, arena.alloc<uint32_t>(M), d_u32 + 3};
-    // (d_u32[3] doubles as the tile kernels' error flag later: it is reset after this use)
+    RankArgs ra{m, unitigs.grp_off, rows, p_read, p_ir0, p_ir1, deg, wgt, arena.alloc<uint32_t>(M), d_u32 + 5};
     // groups ordered by read id: a warp sorts a short group, a CTA a longer one, the longest are ranked by counting
     const uint32_t U = uint32_t(unitigs.n);
     uint32_t      *big_groups = arena.alloc<uint32_t>(U + 1);
-    MSGPU_CUDA(cudaMemsetAsync(d_u32 + 2, 0, sizeof(uint32_t), st)); // (the too-many-sources flag is set later)
-    MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<grid_for(uint64_t(U) * 32, 256), 256, 0, st>>>(ra, U, big_groups, d_u32 + 2));
-    MSGPU_LAUNCH("rank_rows_cta", st, rank_rows_cta_kernel<<<kNumSMs * 6, 256, kSortCtaMax * sizeof(unsigned long long), st>>>(ra, big_groups, d_u32 + 2));
+    MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<grid_for(uint64_t(U) * 32, 256), 256, 0, st>>>(ra, U, big_groups, d_u32 + 4));
+    MSGPU_LAUNCH("rank_rows_cta", st, rank_rows_cta_kernel<<<kNumSMs * 6, 256, kSortCtaMax * sizeof(unsigned long long), st>>>(ra, big_groups, d_u32 + 4));
     MSGPU_LAUNCH("rank_rows_heavy", st, rank_rows_heavy_kernel<<<grid_for(M * 32, 256, 4), 256, 0, st>>>(ra));
-    MSGPU_CUDA(cudaMemsetAsync(d_u32 + 2, 0, sizeof(uint32_t), st));
-    MSGPU_CUDA(cudaMemsetAsync(d_u32 + 3, 0, sizeof(uint32_t), st));
   }
   // ---- tile planning: four independent scans over the reads in one launch (source offsets, clipped row weights,
   // slice-table offsets, the pair count), then the tile index, which needs the weights' prefix
   RowPlan   plan{deg, wgt};
   uint64_t *prefix = arena.alloc<uint64_t>(R + 1), *slice_off = arena.alloc<uint64_t>(R + 1);
   uint32_t *tile_idx = arena.alloc<uint32_t>(R + 1);
-  MSGPU_CUDA(cudaMemsetAsync(d_u64, 0, 4 * sizeof(uint64_t), st)); // (totals of empty scans)
   run_scans(arena, st, scan_job<uint32_t>(arena, st, 0, LoadAs<uint32_t, uint32_t>{deg}, R, rd_off, d_u32 + 0),
             scan_job<uint64_t>(arena, st, 1, ClippedWeight{plan}, R, prefix, (uint64_t *)nullptr),
             scan_job<uint64_t>(arena, st, 2, SliceCount{plan}, R, slice_off, d_u64 + 0),
@@ -1196,7 +1196,6 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   uint2              *tile_cnt = arena.alloc<uint2>(uint64_t(my_tiles) + 1);
   unsigned long long *em_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
   unsigned long long *ed_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
-  unsigned long long *totals  = arena.alloc<unsigned long long>(2);
 
   TileArgs a;
   a.rows      = rows;
@@ -1247,7 +1246,6 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
       MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
     }
   }
-  MSGPU_CUDA(cudaMemsetAsync(totals, 0, 2 * sizeof(unsigned long long), st));
   run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{tile_cnt}, my_tiles, em_base, totals + 0),
             scan_job<unsigned long long>(arena, st, 1, TileHeads{tile_cnt}, my_tiles, ed_base, totals + 1));
   if (!my_tiles) MSGPU_CUDA(cudaMemsetAsync(e.em_begin, 0, sizeof(uint64_t), st)); // an empty CSR: em_begin[0] = 0
