@@ -67,6 +67,26 @@ def gather_blobs(mine: torch.Tensor, world: int, dist) -> torch.Tensor:
     return out.view(world, mine.numel())
 
 
+HEADER_BYTES = HEADER_WORDS * 8
+
+
+def gather_one_shot(h: "_lib.ShardHeader", write_blob, stride: int, world: int, dist, device):
+    """The exchange as ONE collective: every rank contributes [header | blob] padded to `stride` bytes (the same
+    value on every rank, a multiple of 256).  `write_blob(dst_tensor)` fills the blob part; it is not called when this
+    rank's blob does not fit.  Returns (headers, gathered [world, stride] tensor, ok): ok is False iff some rank's
+    blob did not fit — every rank sees the same headers, so every rank reaches the same verdict and can fall back to
+    the two-collective path together."""
+    buf = torch.empty(stride, dtype=torch.uint8, device=device)
+    buf[:HEADER_BYTES] = header_to_tensor(h, device).view(torch.uint8)
+    if int(h.blob_bytes) + HEADER_BYTES <= stride:
+        write_blob(buf[HEADER_BYTES:])
+    out = gather_blobs(buf, world, dist) if world > 1 else buf.view(1, stride)
+    heads = out[:, :HEADER_BYTES].contiguous().view(torch.int64).view(world, HEADER_WORDS)
+    headers = tensor_to_headers(heads)  # device -> host: the one synchronisation of the exchange
+    ok = all(int(x.blob_bytes) + HEADER_BYTES <= stride for x in headers)
+    return headers, out, ok
+
+
 class ShardedBuilder:
     """The N-GPU construction step of one rank.  `dist` is torch.distributed (initialised) or None for world == 1."""
 
@@ -96,26 +116,47 @@ class ShardedBuilder:
     def _exchange_on_stream(self):
         gb, world = self.gb, self.world
         h = gb.shard_header()
+        stride = getattr(self, "_stride", None)
+        if stride is not None:
+            # steady state: the stride that fitted every rank last time (plus slack) — ONE collective, one host sync
+            ev = self._timer()
+            headers, blobs, ok = gather_one_shot(
+                h, lambda dst: gb.shard_export(dst.data_ptr(), dst.numel()), stride, world, self.dist, self.device)
+            if ok:
+                self._stop(ev)
+                self.exchange_bytes = sum(int(x.blob_bytes) for i, x in enumerate(headers) if i != self.rank)
+                self._keep = blobs
+                return headers, [blobs.data_ptr() + s * stride + HEADER_BYTES for s in range(world)]
+        # first step, or a blob outgrew the stride: sizes first, then the padded blobs
         heads = gather_headers(header_to_tensor(h, self.device), world, self.dist) if world > 1 else \
             header_to_tensor(h, self.device).view(1, HEADER_WORDS)
         headers = tensor_to_headers(heads)  # device -> host: the sizes decide the allocations below
-        stride = (max(int(x.blob_bytes) for x in headers) + 255) & ~255
+        biggest = max(int(x.blob_bytes) for x in headers)
+        stride = (biggest + 255) & ~255
+        self._stride = (biggest + biggest // 8 + HEADER_BYTES + 255) & ~255  # what the next steps try
         mine = torch.empty(stride, dtype=torch.uint8, device=self.device)
         gb.shard_export(mine.data_ptr(), stride)
         if world > 1:
-            on_gpu = mine.is_cuda
-            if on_gpu:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
+            ev = self._timer()
             blobs = gather_blobs(mine, world, self.dist)
-            if on_gpu:
-                b.record()
-                self._events = (a, b)
+            self._stop(ev)
         else:
             blobs = mine.view(1, stride)
         self.exchange_bytes = sum(int(x.blob_bytes) for i, x in enumerate(headers) if i != self.rank)
         self._keep = (mine, blobs)
         return headers, [blobs.data_ptr() + s * stride for s in range(world)]
+
+    def _timer(self):
+        if self.stream is None or self.world == 1:
+            return None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        return (a, b)
+
+    def _stop(self, ev):
+        if ev is not None:
+            ev[1].record()
+            self._events = ev
 
     def build_device(self, dev_ptr: int, n_bytes: int):
         self.gb.shard_ingest_device(dev_ptr, n_bytes, self.rank == self.world - 1)

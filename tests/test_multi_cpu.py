@@ -59,6 +59,19 @@ def _worker(rank, world, port, q):
         for r in range(world):
             want = np.random.default_rng(r).integers(0, 256, 1000 + 777 * r, dtype=np.uint8)
             ok = ok and np.array_equal(allb[r, :int(headers[r].blob_bytes)].numpy(), want)
+        # the one-collective form: [header | blob] padded to a stride every rank agrees on
+        def write(dst):
+            dst[:n_local] = blob
+        stride = (max(int(x.blob_bytes) for x in headers) + multi_gpu.HEADER_BYTES + 255) & ~255
+        hs, out, fits = multi_gpu.gather_one_shot(h, write, stride, world, dist, "cpu")
+        ok = ok and fits and [int(x.n_reads) for x in hs] == [5 * r for r in range(world)]
+        for r in range(world):
+            want = np.random.default_rng(r).integers(0, 256, 1000 + 777 * r, dtype=np.uint8)
+            got = out[r, multi_gpu.HEADER_BYTES:multi_gpu.HEADER_BYTES + int(hs[r].blob_bytes)]
+            ok = ok and np.array_equal(got.numpy(), want)
+        # a stride that is too small for the last rank: every rank must see that
+        _, _, fits = multi_gpu.gather_one_shot(h, write, 1024 + 256, world, dist, "cpu")
+        ok = ok and not fits
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
