@@ -190,15 +190,27 @@ __global__ void __launch_bounds__(256) rank_rows_heavy_kernel(RankArgs a) {
 }
 
 // pre-pass 2: per read the list of its sources (positions in the pair rows), in unitig order
+// (multi-GPU: a device needs the lists of the rows of its own tiles only — `rows_of` names them)
+struct RowRange {
+  const uint32_t *tile_row; // null: every row
+  uint32_t        t_first, t_last, n_reads; // rows tile_row[t_first] .. tile_row[t_last] (inclusive)
+  __device__ uint32_t lo() const { return tile_row ? tile_row[t_first] : 0u; }
+  __device__ uint32_t hi() const { // exclusive
+    if (!tile_row) return n_reads;
+    const uint32_t r = tile_row[t_last] + 1u;
+    return r < n_reads ? r : n_reads;
+  }
+};
+
 __global__ void __launch_bounds__(256)
     scatter_sources_kernel(const uint32_t *__restrict__ p_read, const PairRow *__restrict__ rows,
                            const uint32_t *__restrict__ grp_off, uint64_t n, const uint32_t *__restrict__ rd_off,
-                           uint32_t *__restrict__ cursor, uint32_t *__restrict__ rd_tmp) {
+                           uint32_t *__restrict__ cursor, uint32_t *__restrict__ rd_tmp, RowRange rows_of) {
+  const uint32_t r_lo = rows_of.lo(), r_hi = rows_of.hi();
   for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < n; q += uint64_t(gridDim.x) * blockDim.x) {
-    if (grp_off[rows[q].unitig + 1] - uint32_t(q) - 1 > 0) {
-      uint32_t r                                    = p_read[q];
-      rd_tmp[rd_off[r] + atomicAdd(&cursor[r], 1u)] = uint32_t(q);
-    }
+    const uint32_t r = p_read[q];
+    if (r < r_lo || r >= r_hi) continue;
+    if (grp_off[rows[q].unitig + 1] - uint32_t(q) - 1 > 0) rd_tmp[rd_off[r] + atomicAdd(&cursor[r], 1u)] = uint32_t(q);
   }
 }
 
@@ -206,8 +218,10 @@ __global__ void __launch_bounds__(256)
 // = unitig order, which makes the candidate stream of a tile deterministic
 __global__ void __launch_bounds__(256)
     order_sources_kernel(const uint32_t *__restrict__ p_read, const uint32_t *__restrict__ rd_off,
-                         const uint32_t *__restrict__ rd_tmp, uint64_t n_src, uint32_t *__restrict__ rd_src) {
-  for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < n_src;
+                         const uint32_t *__restrict__ rd_tmp, uint64_t n_src, uint32_t *__restrict__ rd_src,
+                         RowRange rows_of) {
+  const uint64_t x_lo = rd_off[rows_of.lo()], x_hi = rd_off[rows_of.hi()]; // (rd_off has n_reads + 1 entries)
+  for (uint64_t x = x_lo + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < x_hi && x < n_src;
        x += uint64_t(gridDim.x) * blockDim.x) {
     uint32_t me = rd_tmp[x];
     uint32_t r  = p_read[me];
@@ -1163,13 +1177,16 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   uint32_t *tile_row = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1), *tile_kind = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1);
   if (R) MSGPU_LAUNCH("write_tiles", st, write_tiles_kernel<<<gr, 256, 0, st>>>(tc, tile_idx, R, n_tiles, tile_row, tile_kind, d_u32 + 2));
   uint32_t *rd_tmp = arena.alloc<uint32_t>(n_src), *rd_src = arena.alloc<uint32_t>(n_src);
-  if (M) MSGPU_LAUNCH("scatter_sources", st, scatter_sources_kernel<<<gm, 256, 0, st>>>(p_read, rows, unitigs.grp_off, M, rd_off, cursor, rd_tmp));
-  if (n_src) MSGPU_LAUNCH("order_sources", st, order_sources_kernel<<<grid_for(n_src, 256), 256, 0, st>>>(p_read, rd_off, rd_tmp, n_src, rd_src));
   // ---- this device's share: a contiguous range of tiles (tiles weigh about the same)
   if (n_parts == 0) n_parts = 1;
   const uint32_t tile_lo = uint32_t(uint64_t(n_tiles) * part / n_parts);
   const uint32_t tile_hi = uint32_t(uint64_t(n_tiles) * (part + 1) / n_parts);
   const uint32_t my_tiles = tile_hi - tile_lo;
+  // source lists: of every row on one device, of the rows of this device's tiles (+ the one after) on several
+  RowRange rows_of{nullptr, 0u, 0u, uint32_t(R)};
+  if (n_parts > 1) rows_of = RowRange{tile_row, tile_lo, tile_hi < n_tiles ? tile_hi : n_tiles, uint32_t(R)};
+  if (M) MSGPU_LAUNCH("scatter_sources", st, scatter_sources_kernel<<<gm, 256, 0, st>>>(p_read, rows, unitigs.grp_off, M, rd_off, cursor, rd_tmp, rows_of));
+  if (n_src) MSGPU_LAUNCH("order_sources", st, order_sources_kernel<<<grid_for(n_src, 256), 256, 0, st>>>(p_read, rd_off, rd_tmp, n_src, rd_src, rows_of));
   // heavy rows: every sub-tile computes its START boundary; its end boundary is the start of the next sub-tile, so
   // the range includes one tile past this device's share (a last sub-tile writes the end of its row itself)
   uint32_t *slices = arena.alloc<uint32_t>(n_slices);
