@@ -141,7 +141,8 @@ __device__ __forceinline__ bool dev_isspace(char c) { return c == ' ' || (c >= '
 // significant digits cannot overflow, the 10th is checked once, more are out of range.
 __device__ __forceinline__ bool dev_stoi(const char *s, uint32_t n, int *out) {
   uint32_t i = 0;
-  while (i < n && dev_isspace(s[i])) ++i;
+  if (n && (unsigned char)s[0] <= ' ')  // leading white space is rare: one compare on the common path
+    while (i < n && dev_isspace(s[i])) ++i;
   bool neg = false;
   if (i < n && (s[i] == '+' || s[i] == '-')) {
     neg = s[i] == '-';
@@ -150,6 +151,22 @@ __device__ __forceinline__ bool dev_stoi(const char *s, uint32_t n, int *out) {
   if (i >= n) return false;
   uint32_t d = uint32_t(s[i]) - uint32_t('0');
   if (d > 9u) return false;
+  // common path: at most 9 digits cannot overflow and need no bookkeeping
+  {
+    uint32_t v = 0, j = i, nd = 0;
+    do {
+      v = v * 10u + d;
+      ++j;
+      ++nd;
+      if (j >= n) break;
+      d = uint32_t(s[j]) - uint32_t('0');
+    } while (d <= 9u && nd < 9u);
+    if (j >= n || d > 9u) { // the number ended within 9 digits
+      *out = neg ? int(0u - v) : int(v);
+      return true;
+    }
+    d = uint32_t(s[i]) - uint32_t('0'); // 10 digits or more: the exact walk below, from the first digit
+  }
   uint32_t v = 0, sig = 0; // sig: digits since the first non-zero one
   do {
     if (sig == 9) { // the 10th significant digit decides
@@ -185,16 +202,26 @@ __device__ __forceinline__ uint64_t name_hash(const char *s, uint32_t n, uint64_
 __device__ __forceinline__ bool parse_one_line(const char *s, uint64_t len, uint64_t li, uint64_t seed, LineFields &f,
                                                bool *bad_out) {
   // std::getline(iss, token, '\t'): a field exists iff at least one character is left
-  uint32_t fo[10], fl[10];
-  int      ntok = 0;
-  uint64_t p    = 0;
-  while (p < len && ntok < 10) {
-    uint64_t q = p;
-    while (q < len && s[q] != '\t') ++q;
-    fo[ntok] = uint32_t(p);
-    fl[ntok] = uint32_t(q - p);
-    ++ntok;
-    p = q + 1;
+  // (the loop over the ten fields is unrolled so that fo / fl stay in registers; lines of 4 GiB and more do not exist
+  //  on this path: the whole buffer is below 80 GB and a line is counted in 32 bits)
+  uint32_t       fo[10], fl[10];
+  int            ntok = 0;
+  const uint32_t n    = len < 0xfffffff0ull ? uint32_t(len) : 0xfffffff0u;
+  uint32_t       p    = 0;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    fo[k] = 0;
+    fl[k] = 0;
+    if (p < n) {
+      uint32_t q = p;
+      while (q < n && s[q] != '\t') ++q;
+      fo[k] = p;
+      fl[k] = q - p;
+      ntok  = k + 1;
+      p     = q + 1;
+    } else {
+      p = 0xffffffffu; // no further field
+    }
   }
   uint8_t flags = 0;
   bool    bad   = ntok < 10; // BlastFileReader.cpp:97 ("Invalid BLAST file.")

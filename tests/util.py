@@ -122,6 +122,14 @@ def edge_case_pafs() -> dict:
         b"u1\t5000\t2500\t5000\t+\tr3\t18000\t0\t2500\t450 \t2500\t60\r\n",
         b"u1\t5000\t2500\t5000\t-\tr4\t-5\t0\t2500\t-1\t2500\t60\r\n",   # negative matches widen to a huge size_t
         sentinel])
+    # std::stoi at the edges of int: INT_MAX as a read length, -INT_MAX-1 as a match count, ten and more digits made
+    # of leading zeros (the fast path of the device parser handles up to nine digits; these take the exact one)
+    cases["stoi_ten_digits"] = b"".join([
+        b"u1\t5000\t0000000000\t00000003000\t+\tr1\t2147483647\t100\t3100\t2900\t3000\t60\n",
+        b"u1\t5000\t1000\t4000\t-\tr2\t0000000000015000\t500\t3500\t-2147483648\t3000\t60\n",
+        b"u1\t5000\t2500\t5000\t+\tr3\t18000\t000000000\t0000002500\t450\t2500\t60\n",
+        b"u1\t5000\t2400\t5000\t+\tr4\t999999999\t1\t2601\t1234567890\t2600\t60\n",
+        sentinel])
     # one heavy unitig: k = 120 reads -> 7 140 pairs in one group, plus small groups around it
     rng = np.random.Generator(np.random.PCG64(7))
     rows = []
@@ -159,6 +167,8 @@ def invalid_pafs() -> dict:
         "too_few_fields": good + b"u1\t5000\t0\t3000\t+\tr1\t20000\t100\t3100\n" + sentinel,
         "empty_line": good + b"\n" + sentinel,
         "not_a_number": good + b"u1\t5000\tabc\t3000\t+\tr1\t20000\t100\t3100\t2900\t3000\t60\n" + sentinel,
+        "int_overflow_by_one": good + b"u1\t5000\t0\t3000\t+\tr1\t2147483648\t100\t3100\t2900\t3000\t60\n" + sentinel,
+        "int_underflow_by_one": good + b"u1\t5000\t0\t3000\t+\tr1\t20000\t100\t3100\t-2147483649\t3000\t60\n" + sentinel,
         "int_overflow": good + b"u1\t5000\t0\t99999999999\t+\tr1\t20000\t100\t3100\t2900\t3000\t60\n" + sentinel,
         "bad_read_coord_on_accepted": good + b"u1\t5000\t0\t3000\t+\tr1\t20000\t\t3100\t2900\t3000\t60\n" + sentinel,
     }
