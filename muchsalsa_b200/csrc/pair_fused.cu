@@ -118,6 +118,7 @@ template <bool kCta> __device__ __forceinline__ void bitonic_sort_shared(unsigne
 
 constexpr uint32_t kSortWarpMax = 128;  // groups up to this size: one warp sorts them
 constexpr uint32_t kSortCtaMax  = 4096; // ... up to this size: one CTA; longer ones are ranked by counting (below)
+constexpr uint32_t kCountCtaMax = 1024; // inside the CTA kernel: groups up to this size are ranked by counting
 
 // One warp per group: the keys (read id << 32 | row of the match) are sorted in shared memory, then lane by lane the
 // matches are placed at their position in read order.  Reads are unique inside a group (MatchMap.cpp:64-73 keeps one
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a, uint32_t n_g
 }
 
 // One CTA per longer group; groups beyond kSortCtaMax hand their members to the counting kernel
-__global__ void __launch_bounds__(256) rank_rows_cta_kernel(RankArgs a, const uint32_t *__restrict__ big_groups,
+__global__ void __launch_bounds__(1024) rank_rows_cta_kernel(RankArgs a, const uint32_t *__restrict__ big_groups,
                                                             const unsigned int *__restrict__ n_big) {
   extern __shared__ __align__(16) unsigned long long keys_cta[];
   const MatchSoA &m = a.m;
@@ -160,6 +161,28 @@ __global__ void __launch_bounds__(256) rank_rows_cta_kernel(RankArgs a, const ui
       if (threadIdx.x == 0) base = atomicAdd(a.heavy_n, k);
       __syncthreads();
       for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) a.heavy_list[base + i] = g0 + i;
+      __syncthreads();
+      continue;
+    }
+    if (k <= kCountCtaMax) {
+      // a group of a few hundred matches: every thread counts, for its members, the smaller read ids among all of
+      // them (k^2 compares served by shared-memory broadcasts, no barrier per step) — cheaper here than ~50 stages
+      // of a sorting network with a barrier each
+      uint32_t *ids = reinterpret_cast<uint32_t *>(keys_cta);
+      for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) ids[i] = m.read[g0 + i];
+      __syncthreads();
+      for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
+        const uint32_t my = ids[j];
+        uint32_t       r0 = 0, r1 = 0, r2 = 0, r3 = 0, i = 0;
+        for (; i + 4 <= k; i += 4) {
+          r0 += ids[i] < my;
+          r1 += ids[i + 1] < my;
+          r2 += ids[i + 2] < my;
+          r3 += ids[i + 3] < my;
+        }
+        for (; i < k; ++i) r0 += ids[i] < my;
+        place_row(a, g0 + j, u, g0 + r0 + r1 + r2 + r3, g1);
+      }
       __syncthreads();
       continue;
     }
@@ -1150,7 +1173,7 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
     const uint32_t U = uint32_t(unitigs.n);
     uint32_t      *big_groups = arena.alloc<uint32_t>(U + 1);
     MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<grid_for(uint64_t(U) * 32, 256), 256, 0, st>>>(ra, U, big_groups, d_u32 + 4));
-    MSGPU_LAUNCH("rank_rows_cta", st, rank_rows_cta_kernel<<<kNumSMs * 6, 256, kSortCtaMax * sizeof(unsigned long long), st>>>(ra, big_groups, d_u32 + 4));
+    MSGPU_LAUNCH("rank_rows_cta", st, rank_rows_cta_kernel<<<kNumSMs * 2, 1024, kSortCtaMax * sizeof(unsigned long long), st>>>(ra, big_groups, d_u32 + 4));
     MSGPU_LAUNCH("rank_rows_heavy", st, rank_rows_heavy_kernel<<<grid_for(M * 32, 256, 4), 256, 0, st>>>(ra));
   }
   // ---- tile planning: four independent scans over the reads in one launch (source offsets, clipped row weights,

@@ -118,7 +118,6 @@ template <class Job> __device__ __forceinline__ void scan_block(const Job &job, 
         if (p >= 0) {
           word = vs[p];
           while ((word & (kScanEpochMask << 2)) != tag || (word & 3ull) == 0ull) {
-            __nanosleep(32);
             word = vs[p];
           }
         }
