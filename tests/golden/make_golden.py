@@ -101,7 +101,7 @@ def main():
             cfg = dataclasses.replace(synth.CONFIGS[name], shuffle_groups=shuffled)
             t = R.build(synth.generate_paf(cfg))
             digests[name + ("_shuffled" if shuffled else "")] = dict(digest=tables_digest(t), counts=t.counts)
-            if not shuffled and name != "yeast":  # the stage after construction (chainingAndOverlaps), same inputs
+            if not shuffled:  # the stages after construction, same inputs (yeast: ~10 min of the reference's CPU time)
                 o = R.chain(synth.generate_paf(cfg))
                 digests[name].update(orders_digest=orders_digest(o), orders=int(o.left.size),
                                      shadow_edges=int(o.edge_shadow.sum()))

@@ -68,3 +68,27 @@ def test_filters_need_the_orders(builder):
     with pytest.raises(MsGpuError) as e:
         builder.edge_filters()
     assert e.value.status == 7
+
+
+def test_chain_and_filters_at_yeast_scale_match_the_reference_digests(builder):
+    """BASELINE.json's metric configuration at full size (3.0e7 edges): the shadow flags, the EdgeOrder rows and the
+    per-edge verdicts hash to the digests recorded from the reference (tests/golden/make_golden.py --yeast; about ten
+    minutes of the reference's CPU time, so it is recorded once and not re-run here)."""
+    g = util.load_golden("digests.json").get("yeast", {})
+    if "orders_digest" not in g or "filters_digest" not in g:
+        pytest.skip("yeast-scale digests of the stages after construction not recorded")
+    from oracle.pyoracle import Orders
+    paf = synth.generate_paf("yeast")
+    builder.build_from_buffer(paf).chain_overlaps(300).edge_filters(300)
+    o = Orders(**builder.orders())
+    h = hashlib.sha256()
+    for f in ("edge_shadow", "edge_order_begin", "start_is_first", "left", "right", "contained", "direction",
+              "primary", "score", "ids_begin", "ids"):
+        h.update(np.ascontiguousarray(getattr(o, f)).tobytes())
+    assert h.hexdigest() == g["orders_digest"] and o.left.size == g["orders"]
+    got = builder.filters()
+    h = hashlib.sha256()
+    for k in FILTER_FIELDS:
+        h.update(np.ascontiguousarray(got[k]).tobytes())
+    assert h.hexdigest() == g["filters_digest"]
+    assert int((got["contraction_order"] >= 0).sum()) == g["contraction_edges"]
