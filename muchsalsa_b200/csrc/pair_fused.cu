@@ -389,6 +389,52 @@ __global__ void __launch_bounds__(256)
       }
       continue;
     }
+    if (d <= 128) {
+      // up to four sources per lane, each with its own shrinking window (the arrays are unrolled into registers)
+      uint32_t b[4], e[4], wlo[4], whi[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t a = l + 32u * i;
+        b[i] = e[i] = 0;
+        if (a < d) {
+          const uint32_t q = rd_src[q0 + a];
+          b[i]             = q + 1;
+          e[i]             = grp_off[rows[q].unitig + 1];
+        }
+        wlo[i] = b[i];
+        whi[i] = e[i];
+      }
+      uint32_t lo = 0, hi = n_reads; // invariant: C(lo) <= target, wlo = lower bounds of lo
+      while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+        uint32_t       pos[4];
+        uint64_t       c = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          pos[i] = (l + 32u * i < d) ? lower_bound_u32(p_read, wlo[i], whi[i], mid) : 0u;
+          c += pos[i] - b[i];
+        }
+        c = warp_reduce_sum(c);
+        if (c <= target) {
+          lo = mid;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) wlo[i] = pos[i];
+        } else {
+          hi = mid - 1;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) whi[i] = pos[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t a = l + 32u * i;
+        if (a < d) {
+          out[uint64_t(j) * d + a] = j == 0 ? b[i] : wlo[i];
+          if (j == ns - 1) out[uint64_t(ns) * d + a] = e[i];
+        }
+      }
+      continue;
+    }
     // bisection: largest s in [0, n_reads] with C(s) <= target
     uint32_t lo = 0, hi = n_reads; // invariant: C(lo) <= target
     while (lo < hi) {
