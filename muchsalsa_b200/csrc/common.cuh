@@ -42,6 +42,8 @@ public:
     m_used = m_high = 0;
     if (m_counter) cudaFree(m_counter);
     m_counter = nullptr;
+    if (m_host_scratch) cudaFreeHost(m_host_scratch);
+    m_host_scratch = nullptr;
     for (int k = 0; k < 4; ++k) {
       if (m_scan_state[k]) cudaFree(m_scan_state[k]);
       m_scan_state[k]       = nullptr;
@@ -69,6 +71,12 @@ public:
     }
     *epoch = m_epoch;
     return m_scan_state[slot];
+  }
+  // a small pinned host buffer for the few words a stage reads back (a pageable destination makes the copy take the
+  // driver's staging path); valid until the next call
+  void *host_scratch() {
+    if (!m_host_scratch) MSGPU_CUDA(cudaMallocHost(&m_host_scratch, 1024));
+    return m_host_scratch;
   }
   // zero-initialised device counters that outlive reset(): kernels that use them leave them at zero again
   unsigned *counter() {
@@ -121,6 +129,7 @@ private:
   std::vector<Slab> m_slabs;
   size_t            m_used = 0, m_high = 0;
   unsigned         *m_counter = nullptr;
+  void             *m_host_scratch = nullptr;
   void             *m_scan_state[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t            m_scan_state_bytes[4] = {0, 0, 0, 0};
   unsigned          m_epoch = 0;

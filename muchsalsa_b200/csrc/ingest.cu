@@ -543,11 +543,14 @@ static void make_tables(Arena &arena, cudaStream_t st, uint64_t min_slots, Inter
   MSGPU_CUDA(cudaMemsetAsync(minline, 0xff, 3 * cap * sizeof(uint32_t), st));
 }
 
-template <class T> static T read_back(cudaStream_t st, const T *d) {
-  T h;
-  MSGPU_CUDA(cudaMemcpyAsync(&h, d, sizeof(T), cudaMemcpyDeviceToHost, st));
+template <class T> static T read_back(Arena &arena, cudaStream_t st, const T *d) {
+  static_assert(sizeof(T) <= 1024, "host scratch");
+  void *h = arena.host_scratch(); // pinned: the copy is a plain DMA, not the driver's staging path
+  MSGPU_CUDA(cudaMemcpyAsync(h, d, sizeof(T), cudaMemcpyDeviceToHost, st));
   MSGPU_CUDA(cudaStreamSynchronize(st));
-  return h;
+  T out;
+  memcpy(&out, h, sizeof(T));
+  return out;
 }
 
 // lengths of the first *d_n names, 0 behind them: lets a scan run over the capacity without knowing the count
@@ -612,7 +615,7 @@ void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &m, uint64_t n_unit
     uint32_t *d_unsorted = arena.alloc<uint32_t>(1);
     MSGPU_CUDA(cudaMemsetAsync(d_unsorted, 0, sizeof(uint32_t), st));
     MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, nullptr, M, d_unsorted));
-    if (!read_back(st, d_unsorted)) return;
+    if (!read_back(arena, st, d_unsorted)) return;
   }
   uint32_t *keys = arena.alloc<uint32_t>(M), *keys2 = arena.alloc<uint32_t>(M);
   uint32_t *idx = arena.alloc<uint32_t>(M), *idx2 = arena.alloc<uint32_t>(M);
@@ -731,7 +734,7 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(cap_acc, 256, 2), 256, 0, st>>>(m.unitig, &d_status->n_matches, 0, &d_status->unsorted));
 
     // ---- the one round trip of the ingest
-    h = read_back(st, d_status);
+    h = read_back(arena, st, d_status);
     if (h.overflow || h.first_bad_line != ~0ull)
       throw BuildError{MSGPU_ERR_INVALID_PAF,
                        h.first_bad_line != ~0ull ? "Invalid BLAST file. (line " + std::to_string(h.first_bad_line) + ")"

@@ -1234,10 +1234,11 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   MSGPU_CUDA(cudaMemcpyAsync(rd_off + R, d_u32 + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   TileCount tc{plan, prefix};
   exclusive_scan<uint32_t>(arena, st, tc, R, tile_idx, d_u32 + 1);
-  uint32_t h32[4];
-  uint64_t h64[4];
-  MSGPU_CUDA(cudaMemcpyAsync(h32, d_u32, sizeof(h32), cudaMemcpyDeviceToHost, st));
-  MSGPU_CUDA(cudaMemcpyAsync(h64, d_u64, sizeof(h64), cudaMemcpyDeviceToHost, st));
+  // one copy of the adjacent counter words (d_u32[0..7], d_u64[0..3], totals[0..1]) into pinned memory
+  char *h_words = static_cast<char *>(arena.host_scratch());
+  MSGPU_CUDA(cudaMemcpyAsync(h_words, zero + z_u32, z_end - z_u32, cudaMemcpyDeviceToHost, st));
+  const uint32_t *h32 = reinterpret_cast<const uint32_t *>(h_words);
+  const uint64_t *h64 = reinterpret_cast<const uint64_t *>(h_words + (z_u64 - z_u32));
   MSGPU_CUDA(cudaStreamSynchronize(st));
   const uint32_t n_src = h32[0], n_tiles = h32[1];
   const uint64_t n_slices = h64[0], P = h64[1]; // P = sum k(k-1)/2: every unordered pair is one suffix member
@@ -1354,10 +1355,9 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
     if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
     MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
   }
-  unsigned long long h_tot[2];
-  uint32_t           h_flags[4];
-  MSGPU_CUDA(cudaMemcpyAsync(h_tot, totals, sizeof(h_tot), cudaMemcpyDeviceToHost, st));
-  MSGPU_CUDA(cudaMemcpyAsync(h_flags, d_u32, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaMemcpyAsync(h_words, zero + z_u32, z_end - z_u32, cudaMemcpyDeviceToHost, st));
+  const uint32_t           *h_flags = reinterpret_cast<const uint32_t *>(h_words);
+  const unsigned long long *h_tot   = reinterpret_cast<const unsigned long long *>(h_words + (z_tot - z_u32));
   MSGPU_CUDA(cudaStreamSynchronize(st));
   if (h_flags[2])
     throw BuildError{MSGPU_ERR_LIMIT, "a read matches more than " + std::to_string(kSrcCap) + " unitigs with partners"};
