@@ -72,10 +72,11 @@ public:
     *epoch = m_epoch;
     return m_scan_state[slot];
   }
+  static constexpr size_t kHostScratch = 16384;
   // a small pinned host buffer for the few words a stage reads back (a pageable destination makes the copy take the
   // driver's staging path); valid until the next call
   void *host_scratch() {
-    if (!m_host_scratch) MSGPU_CUDA(cudaMallocHost(&m_host_scratch, 1024));
+    if (!m_host_scratch) MSGPU_CUDA(cudaMallocHost(&m_host_scratch, kHostScratch));
     return m_host_scratch;
   }
   // zero-initialised device counters that outlive reset(): kernels that use them leave them at zero again

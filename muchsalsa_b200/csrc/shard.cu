@@ -471,8 +471,16 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
     throw BuildError{MSGPU_ERR_LIMIT, "more than 2^32-16 lines, read entries or matches over all shards"};
   *n_lines_out = lb;
   ShardView *d_sh = arena.alloc<ShardView>(n_shards);
-  MSGPU_CUDA(cudaMemcpyAsync(d_sh, hv.data(), n_shards * sizeof(ShardView), cudaMemcpyHostToDevice, st));
-  MSGPU_CUDA(cudaStreamSynchronize(st)); // hv is pageable host memory
+  if (n_shards * sizeof(ShardView) + 256 <= Arena::kHostScratch) {
+    // through the second part of the pinned scratch buffer: no synchronisation (the first 256 bytes are where the
+    // status comes back at the end of the merge, after this copy in stream order)
+    char *pin = static_cast<char *>(arena.host_scratch()) + 256;
+    memcpy(pin, hv.data(), n_shards * sizeof(ShardView));
+    MSGPU_CUDA(cudaMemcpyAsync(d_sh, pin, n_shards * sizeof(ShardView), cudaMemcpyHostToDevice, st));
+  } else {
+    MSGPU_CUDA(cudaMemcpyAsync(d_sh, hv.data(), n_shards * sizeof(ShardView), cudaMemcpyHostToDevice, st));
+    MSGPU_CUDA(cudaStreamSynchronize(st)); // hv is pageable host memory
+  }
 
   MergeStatus *d_status = arena.alloc<MergeStatus>(1);
   MergeStatus  h{};
@@ -506,8 +514,11 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
       MSGPU_LAUNCH("check_grouped", st, shard_check_grouped_kernel<<<g, 256, 0, st>>>(m.unitig, &d_status->n_matches, &d_status->unsorted));
     }
     // ---- the one round trip of the merge
-    MSGPU_CUDA(cudaMemcpyAsync(&h, d_status, sizeof(h), cudaMemcpyDeviceToHost, st));
+    static_assert(sizeof(MergeStatus) <= 256, "host scratch layout");
+    void *pinned = arena.host_scratch();
+    MSGPU_CUDA(cudaMemcpyAsync(pinned, d_status, sizeof(h), cudaMemcpyDeviceToHost, st));
     MSGPU_CUDA(cudaStreamSynchronize(st));
+    memcpy(&h, pinned, sizeof(h));
     if (!h.collision) break;
   }
   reads.n         = h.n_ids[0];
