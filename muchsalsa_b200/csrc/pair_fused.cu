@@ -872,23 +872,26 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
       const uint32_t s1 = s0 + G < re ? s0 + G : re, s2 = s0 + 2 * G < re ? s0 + 2 * G : re;
       const uint32_t a0 = s.src.base[s0], a1 = s.src.base[s1], b1 = s.src.base[s2];
       const uint32_t seg_end = oe < b1 ? oe : b1;
-      { // (a run whose partner is empty takes the same path: the search interval is empty and one side never wins,
-        //  so the lanes of a warp that copy and the lanes that merge do not serialise)
+      if (a1 == b1 || a0 == a1) { // one side empty: the run is copied
+        for (uint32_t p = pos; p < seg_end; ++p) out[p] = in[p];
+      } else {
         const uint32_t k  = pos - a0, na = a1 - a0, nb = b1 - a1;
         uint32_t       lo = k > nb ? k - nb : 0u, hi = k < na ? k : na; // merge path: elements of A among the first k
         while (lo < hi) {
           const uint32_t mid = (lo + hi) >> 1;
           if (in[a0 + mid] < in[a1 + (k - 1 - mid)]) lo = mid + 1; else hi = mid;
         }
+        // An exhausted run reads as ~0, which no word equals (the host gives 32-bit words only to read-id ranges
+        // below 2^20 - 1, and 64-bit words have their top bits clear), so one compare decides a step.
         uint32_t ia = a0 + lo, ib = a1 + (k - lo);
-        W        xa = ia < a1 ? in[ia] : W(0), xb = ib < b1 ? in[ib] : W(0);
+        W        xa = ia < a1 ? in[ia] : ~W(0), xb = ib < b1 ? in[ib] : ~W(0);
         for (uint32_t p = pos; p < seg_end; ++p) { // branch-free step: one select, one reload of the side that moved
-          const bool take_a = ib >= b1 || (ia < a1 && xa < xb);
+          const bool take_a = xa < xb;
           out[p]            = take_a ? xa : xb;
           ia += take_a ? 1u : 0u;
           ib += take_a ? 0u : 1u;
           const uint32_t nx = take_a ? ia : ib, lim = take_a ? a1 : b1;
-          const W        v  = nx < lim ? in[nx] : W(0);
+          const W        v  = nx < lim ? in[nx] : ~W(0);
           xa                = take_a ? v : xa;
           xb                = take_a ? xb : v;
         }
@@ -1054,9 +1057,10 @@ __global__ void __launch_bounds__(kFusedBlock, kMergeCtas) pair_tiles_merge_kern
       }
       continue;
     }
-    const int      sb    = (n_ent && s.smax > s.smin) ? 32 - __clz(s.smax - s.smin) : 0;
+    // 32-bit words when (second - min second) << 12 | slot fits AND can never be all ones (the merge's end marker)
+    const uint32_t range = (n_ent && s.smax > s.smin) ? s.smax - s.smin : 0u;
     unsigned char *words = smem_raw + kMergeOff;
-    if (sb + kIdxBits <= 32) {
+    if (range < (1u << (32 - kIdxBits)) - 1u) {
       uint32_t *wa = reinterpret_cast<uint32_t *>(words);
       merge_tail<uint32_t>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent);
     } else if (!a.wide) { // cannot happen: the host sizes the launch from the id width
@@ -1327,7 +1331,7 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
         attr2 = true;
       }
       // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits
-      a.wide = R > (1ull << (32 - kIdxBits)) ? 1u : 0u;
+      a.wide = R > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)
       grid   = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * 4; // 40 registers, 51 KB (narrow): three resident CTAs per SM
       if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
       MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
