@@ -102,9 +102,9 @@ void build_group_offsets(Arena &arena, cudaStream_t st, const MatchSoA &matches,
 void run_pairing_sorted(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs,
                         uint64_t n_reads, EdgeTables &edges, cudaEvent_t ev_pair_done);
 
-// pair_fused.cu : the product variant — ONE persistent kernel (per-row tiles sorted in shared memory, ordered output
-// through a decoupled look-back).  `part` of `n_parts`: this device handles that contiguous share of the tiles, and its
-// tables are that slice of the global result (multi-GPU); 0 of 1 = everything.
+// pair_fused.cu : the product variant — per-row tiles sorted in shared memory (pair_tiles), offsets by two scans,
+// tables written once in final order (pair_emit_rows).  `part` of `n_parts`: this device handles that contiguous share
+// of the tiles, and its tables are that slice of the global result (multi-GPU); 0 of 1 = everything.
 void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs,
                        uint64_t n_reads, EdgeTables &edges, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts);
 

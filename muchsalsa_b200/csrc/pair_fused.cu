@@ -18,11 +18,12 @@
 //     heavier than a tile (a read that crosses a high-multiplicity repeat) is split into sub-tiles by VALUE RANGES of
 //     `second`: the boundaries are found by bisection on the merged rank over the row's sorted suffixes, so every
 //     sub-tile is bounded, no edge straddles two sub-tiles and the sub-tiles of a row are in output order.
-//   * pair_tiles_kernel, one CTA per tile, no dependency between tiles: stage the sources, enumerate the candidates
-//     into shared memory, radix-sort them there by (row, second) — stable, and candidates are generated in unitig
-//     order, so rows of one edge come out by unitig — find the run heads (= edges) and write the tile's surviving
-//     candidates as compact 8-byte records (partner row, source, head flag, heads before) plus two counts.
-//   * scan_tiles_kernel turns the per-tile counts into the global offset of every tile's first edge match and edge.
+//   * pair_tiles_merge_kernel, one CTA per tile, no dependency between tiles: stage the sources, enumerate the
+//     candidates into shared memory, merge-sort them there by (row, second) starting from the slices, which are
+//     sorted runs already — stable, and candidates are generated in unitig order, so rows of one edge come out by
+//     unitig — find the run heads (= edges) and write the tile's surviving candidates as compact 8-byte records
+//     (partner row, source, head flag, heads before) plus two counts.
+//   * two single-pass scans turn the per-tile counts into the global offset of every tile's first edge match and edge.
 //   * pair_emit_rows_kernel, embarrassingly parallel: each record gathers its two matches (one 32-byte sector each),
 //     evaluates the reference's score expression in IEEE double and writes the edge match — and, for a run head, the
 //     edge and its CSR offset — exactly once, coalesced, in (first, second, unitig) order.
@@ -458,7 +459,6 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------------------------------
 // K6/K7a: one CTA per tile — enumerate, sort in shared memory, find run heads, write the tile's compact records
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr uint16_t kNoSource = 0xffffu; // candidate failed the overlap test
 constexpr int      kSrcBits  = 9;       // kSrcCap == 1 << kSrcBits
 static_assert(kSrcCap == (1u << kSrcBits), "record packing");
 
@@ -478,327 +478,8 @@ struct TileArgs {
   uint32_t        wide; // 0: every sort word fits 32 bits for any tile, so the launch carries the small buffers only
 };
 
-struct SrcStage { // the sources of the tile, staged in shared memory (structure of arrays)
-  uint32_t begin[kSrcCap];    // first partner row
-  uint32_t base[kSrcCap + 1]; // exclusive prefix of the slice lengths = first candidate slot
-  int32_t  ir0[kSrcCap], ir1[kSrcCap];
-  uint16_t row_local[kSrcCap]; // dense rank of the source's read inside the tile
-};
-
-struct TileShared { // everything but the two sort buffers, which follow it in dynamic shared memory
-  uint16_t ent_j[kTileCap]; // candidate slot -> source (kNoSource: failed the overlap test)
-  SrcStage src;
-  uint32_t warp_cnt[kFusedWarps][256];
-  uint32_t bin_base[256];
-  uint32_t scan[33];
-  uint32_t warp_tot[kFusedWarps];
-  uint32_t smin, smax;
-};
-constexpr size_t kSharedOff = (sizeof(TileShared) + 15) & ~size_t(15);
-constexpr size_t kTileBytesWide   = kSharedOff + 2 * kTileCap * sizeof(unsigned long long);
-constexpr size_t kTileBytesNarrow = kSharedOff + 2 * kTileCap * sizeof(uint32_t);
-
-// Stable LSD radix sort of n words in shared memory on bits [lo, hi); warp w owns a contiguous block of items and
-// ranks it with __match_any_sync + per-warp digit counters, so equal digits keep their order.  Returns the buffer
-// that holds the result.  blockDim.x == kFusedBlock.
-template <class W, bool kExpMatch> __device__ W *cta_radix_sort(TileShared &s, W *in, W *out, uint32_t n, int lo, int hi) {
-  const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
-  const int      kb = hi - lo;
-  if (kb <= 0 || n <= 1) return in;
-  const int      n_pass = (kb + 7) / 8, bits = (kb + n_pass - 1) / n_pass;
-  const uint32_t per    = (n + kFusedBlock - 1) / kFusedBlock; // items per thread in this tile
-  const uint32_t wbase  = w * per * 32;
-  for (int shift = lo; shift < hi; shift += bits) {
-    const int      b    = hi - shift < bits ? hi - shift : bits;
-    const unsigned mask = (1u << b) - 1u;
-    for (uint32_t z = t; z < kFusedWarps * 256; z += kFusedBlock) (&s.warp_cnt[0][0])[z] = 0;
-    __syncthreads();
-    W        word[kItems];
-    unsigned peer[kItems];
-    // peers of every item first (independent, so the votes pipeline), then the serial counter updates
-#pragma unroll
-    for (int it = 0; it < kItems; ++it) {
-      word[it] = W(0);
-      peer[it] = 0;
-      if (uint32_t(it) < per) {
-        const uint32_t idx   = wbase + it * 32 + l;
-        const bool     valid = idx < n;
-        const W        x     = valid ? in[idx] : W(0);
-        const unsigned d     = unsigned(x >> shift) & mask;
-        // lanes with the same digit, by one vote per digit bit (cost independent of how many digits are distinct)
-        unsigned pm;
-        if (kExpMatch) {
-          pm = __match_any_sync(0xffffffffu, valid ? d : 256u);
-          pm = valid ? pm : 0u;
-        } else {
-          const unsigned vb = __ballot_sync(0xffffffffu, valid);
-          pm                = valid ? vb : 0u;
-          for (int bit = 0; bit < b; ++bit) { // (fully unrolling this loop was measured slower: spills)
-            const unsigned on  = 0u - ((d >> bit) & 1u);
-            const unsigned bal = __ballot_sync(0xffffffffu, on != 0u);
-            pm &= ~(bal ^ on);
-          }
-        }
-        word[it] = x;
-        peer[it] = pm; // 0 for lanes past the end
-      }
-    }
-    uint16_t rank[kItems];
-#pragma unroll
-    for (int it = 0; it < kItems; ++it) {
-      if (uint32_t(it) < per) {
-        const unsigned pm   = peer[it];
-        const unsigned d    = unsigned(word[it] >> shift) & mask;
-        const unsigned lead = pm ? unsigned(__ffs(pm) - 1) : l;
-        uint32_t       old  = 0;
-        if (pm && l == lead) {
-          old              = s.warp_cnt[w][d];
-          s.warp_cnt[w][d] = old + __popc(pm);
-        }
-        old      = __shfl_sync(0xffffffffu, old, lead);
-        rank[it] = uint16_t(old + __popc(pm & ((1u << l) - 1u)));
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    { // thread t < 256 owns digit t: exclusive prefix over the warps, then over the digits
-      uint32_t sum = 0;
-      if (t < 256) {
-#pragma unroll
-        for (int ww = 0; ww < kFusedWarps; ++ww) {
-          uint32_t c        = s.warp_cnt[ww][t];
-          s.warp_cnt[ww][t] = sum;
-          sum += c;
-        }
-      }
-      uint32_t total;
-      uint32_t ex = block_exclusive_scan<uint32_t>(sum, s.scan, &total);
-      if (t < 256) s.bin_base[t] = ex;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < kItems; ++it) {
-      if (uint32_t(it) < per) {
-        uint32_t idx = wbase + it * 32 + l;
-        if (idx < n) {
-          unsigned d = unsigned(word[it] >> shift) & mask;
-          out[s.bin_base[d] + s.warp_cnt[w][d] + rank[it]] = word[it];
-        }
-      }
-    }
-    __syncthreads();
-    W *tmp = in;
-    in     = out;
-    out    = tmp;
-  }
-  return in;
-}
-
-// enumerate + sort + heads of one tile, for sort words of type W (32 bits when row + second + slot fit, else 64)
-template <class W, bool kExpMatch>
-__device__ __forceinline__ void tile_tail(const TileArgs &a, TileShared &s, W *wa, W *wb, uint32_t st_idx,
-                                          uint32_t n_src, uint32_t n_ent, int sb, int rb) {
-  const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
-  const uint32_t smin  = s.smin;
-  const uint32_t per   = (n_ent + kFusedBlock - 1) / kFusedBlock;
-  const uint32_t wbase = w * per * 32; // warp w owns slots / sorted positions [wbase, wbase + per * 32)
-
-  // ---- materialise the candidates in generation order (source by source = unitig order inside a row)
-  if (wbase < n_ent) {
-    uint32_t j = 0, hi = n_src; // last source with base <= wbase (empty slices share their base with the next one)
-    while (hi - j > 1) {
-      uint32_t mid = (j + hi) >> 1;
-      if (s.src.base[mid] <= wbase) j = mid; else hi = mid;
-    }
-    for (uint32_t it = 0; it < per; ++it) {
-      const uint32_t e = wbase + it * 32 + l;
-      if (e < n_ent) {
-        while (s.src.base[j + 1] <= e) ++j; // slots grow with `it`, so every lane walks forward only
-        const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
-        const uint32_t sr = a.p_read[ib];
-        const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = a.p_ir0[ib], b1 = a.p_ir1[ib];
-        const int      o0 = a0 > b0 ? a0 : b0, o1 = a1 < b1 ? a1 : b1;
-        const bool     keep = o0 <= o1 && o1 - o0 > kThOverlapF; // MatchMap.cpp:192
-        const W        key  = (W(s.src.row_local[j]) << sb) | W(sr - smin);
-        wa[e]               = (key << kIdxBits) | W(e);
-        s.ent_j[e]          = keep ? uint16_t(j) : kNoSource;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- sort by (row, second); generation order (= unitig order) breaks ties because the sort is stable
-  W *sorted = cta_radix_sort<W, kExpMatch>(s, wa, wb, n_ent, kIdxBits, kIdxBits + sb + rb);
-
-  // ---- run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the key
-  // of its pair) but is skipped; the head of a run is its first surviving candidate.
-  uint32_t vmask = 0, hmask = 0, n_v = 0, n_h = 0; // bit `it`: this lane's item of iteration `it` survives / is a head
-  for (uint32_t it = 0; it < per; ++it) {
-    const uint32_t k = wbase + it * 32 + l;
-    bool           ok = false, head = false;
-    if (k < n_ent) {
-      const W x = sorted[k];
-      ok        = s.ent_j[uint32_t(x) & (kTileCap - 1)] != kNoSource;
-      if (ok) {
-        head        = true;
-        const W key = x >> kIdxBits;
-        for (uint32_t p = k; p > 0;) {
-          --p;
-          const W y = sorted[p];
-          if ((y >> kIdxBits) != key) break;
-          if (s.ent_j[uint32_t(y) & (kTileCap - 1)] != kNoSource) {
-            head = false;
-            break;
-          }
-        }
-      }
-    }
-    vmask |= (ok ? 1u : 0u) << it;
-    hmask |= (head ? 1u : 0u) << it;
-    n_v += __popc(__ballot_sync(0xffffffffu, ok));
-    n_h += __popc(__ballot_sync(0xffffffffu, head));
-  }
-  if (l == 0) s.warp_tot[w] = n_v | (n_h << 16);
-  __syncthreads();
-  uint32_t before = 0, total = 0;
-#pragma unroll
-  for (int ww = 0; ww < kFusedWarps; ++ww) {
-    uint32_t c = s.warp_tot[ww];
-    before += ww < int(w) ? c : 0u;
-    total += c;
-  }
-  if (t == 0) a.tile_cnt[st_idx] = make_uint2(total & 0xffffu, total >> 16);
-
-  // ---- the tile's records, compacted, in final order
-  uint2   *rec = a.records + uint64_t(st_idx) * kTileCap;
-  uint32_t pv = before & 0xffffu, ph = before >> 16;
-  for (uint32_t it = 0; it < per; ++it) {
-    const uint32_t k    = wbase + it * 32 + l;
-    const bool     ok   = (vmask >> it) & 1u, head = (hmask >> it) & 1u;
-    const unsigned bv   = __ballot_sync(0xffffffffu, ok), bh = __ballot_sync(0xffffffffu, head);
-    const unsigned lt   = (1u << l) - 1u;
-    if (ok) {
-      const uint32_t e  = uint32_t(sorted[k]) & (kTileCap - 1);
-      const uint32_t j  = s.ent_j[e];
-      const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
-      rec[pv + __popc(bv & lt)] = make_uint2(ib, j | (head ? 1u << kSrcBits : 0u) | ((ph + __popc(bh & lt)) << (kSrcBits + 1)));
-    }
-    pv += __popc(bv);
-    ph += __popc(bh);
-  }
-}
-
-template <bool kExpMatch> __global__ void __launch_bounds__(kFusedBlock, kIdxBits <= 12 ? 2 : 1) pair_tiles_kernel(TileArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileShared    &s = *reinterpret_cast<TileShared *>(smem_raw);
-  const unsigned t = threadIdx.x, l = t & 31;
-
-  for (uint32_t tile = a.tile_lo + blockIdx.x; tile < a.tile_hi; tile += gridDim.x) {
-    __syncthreads(); // previous tile fully done with shared memory
-    if (t == 0) {
-      s.smin = 0xffffffffu;
-      s.smax = 0;
-    }
-    __syncthreads();
-    const uint32_t st_idx = tile - a.tile_lo;
-    const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
-    const uint32_t q0 = a.rd_off[r0];
-    const uint32_t n_src = (kind ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
-    // a tile that violates its capacity invariant (cannot happen: see the planning kernels) reports the error and
-    // contributes nothing
-    if (n_src > kSrcCap) {
-      if (t == 0) {
-        *a.error            = 1;
-        a.tile_cnt[st_idx] = make_uint2(0, 0);
-      }
-      continue;
-    }
-
-    // ---- stage the sources; slice = the partners this tile takes from each source
-    {
-      const uint32_t *sl0 = nullptr, *sl1 = nullptr;
-      if (kind) {
-        sl0 = a.slices + a.slice_off[r0] + uint64_t(kind - 1) * n_src;
-        sl1 = sl0 + n_src;
-      }
-      uint32_t lmin = 0xffffffffu, lmax = 0, carry_len = 0, carry_row = 0;
-      for (uint32_t c0 = 0; c0 < n_src; c0 += kFusedBlock) {
-        const uint32_t j = c0 + t;
-        uint32_t       len = 0, newrow = 0;
-        if (j < n_src) {
-          const uint32_t q   = a.rd_src[q0 + j];
-          const PairRow  row = a.rows[q];
-          uint32_t       b, e;
-          if (kind) {
-            b = sl0[j];
-            e = sl1[j];
-          } else {
-            b = q + 1;
-            e = a.grp_off[row.unitig + 1];
-          }
-          len            = e - b;
-          s.src.begin[j] = b;
-          s.src.ir0[j]   = row.ir0;
-          s.src.ir1[j]   = row.ir1;
-          if (len) { // the slice is sorted by read id
-            uint32_t f = a.p_read[b], g = a.p_read[e - 1];
-            lmin       = f < lmin ? f : lmin;
-            lmax       = g > lmax ? g : lmax;
-          }
-          newrow = (j > 0 && a.p_read[a.rd_src[q0 + j - 1]] != row.read) ? 1u : 0u;
-        }
-        // a chunk holds <= 256 sources; slice lengths are scanned in 32 bits and the new-row flags ride in the top
-        // byte-and-a-bit only when the lengths cannot reach them (planned tiles hold <= 4096 candidates)
-        uint32_t tot, ex = block_exclusive_scan<uint32_t>(len, s.scan, &tot);
-        uint32_t tot_row, ex_row = block_exclusive_scan<uint32_t>(newrow, s.scan, &tot_row);
-        if (j < n_src) {
-          s.src.base[j]      = carry_len + ex;
-          s.src.row_local[j] = uint16_t(carry_row + ex_row + newrow);
-        }
-        carry_len += tot;
-        carry_row += tot_row;
-      }
-      if (t == 0) s.src.base[n_src] = carry_len;
-      for (int d = 16; d > 0; d >>= 1) {
-        uint32_t omin = __shfl_xor_sync(0xffffffffu, lmin, d), omax = __shfl_xor_sync(0xffffffffu, lmax, d);
-        lmin = omin < lmin ? omin : lmin;
-        lmax = omax > lmax ? omax : lmax;
-      }
-      if (l == 0 && lmin <= lmax) {
-        atomicMin(&s.smin, lmin);
-        atomicMax(&s.smax, lmax);
-      }
-    }
-    __syncthreads();
-    const uint32_t n_ent  = s.src.base[n_src];
-    const uint32_t n_rows = n_src ? uint32_t(s.src.row_local[n_src - 1]) + 1u : 0u;
-    if (n_ent > kTileCap) {
-      if (t == 0) {
-        *a.error            = 2;
-        a.tile_cnt[st_idx] = make_uint2(0, 0);
-      }
-      continue;
-    }
-    const int sb = (n_ent && s.smax > s.smin) ? 32 - __clz(s.smax - s.smin) : 0;
-    const int rb = n_rows > 1 ? 32 - __clz(n_rows - 1) : 0;
-    unsigned char *words = smem_raw + kSharedOff;
-    if (sb + rb + kIdxBits <= 32) {
-      uint32_t *wa = reinterpret_cast<uint32_t *>(words);
-      tile_tail<uint32_t, kExpMatch>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent, sb, rb);
-    } else if (!a.wide) { // cannot happen: the host sizes the launch from the id width
-      if (t == 0) {
-        *a.error           = 3;
-        a.tile_cnt[st_idx] = make_uint2(0, 0);
-      }
-    } else {
-      unsigned long long *wa = reinterpret_cast<unsigned long long *>(words);
-      tile_tail<unsigned long long, kExpMatch>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent, sb, rb);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// K6/K7a, merge variant: the same tile work, ordered by a merge sort that starts from the slices
+// K6/K7a: the tile kernel — candidates ordered by a merge sort that starts from the slices
 // ---------------------------------------------------------------------------------------------------------------------
 // The candidates of a source are generated in slice order and a slice is sorted by read id, so every slice is a sorted
 // run before any sorting happens, and the slices of one row are adjacent.  A word is (second - smin) << 12 | slot:
@@ -1309,33 +990,16 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   if (my_tiles) {
     static bool attr_set = false;
     if (!attr_set) {
-      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileBytesWide)));
-      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTileBytesWide)));
+      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
       attr_set = true;
     }
-    // a sort word is (dense row rank, <= 9 bits | second - min second) << 12 | slot: 32 bits are enough for every
-    // tile when read ids have <= 11 bits; otherwise tiles choose per tile and the launch carries the 64-bit buffers
-    int id_bits = 1;
-    while (id_bits < 32 && (1ull << id_bits) < R) ++id_bits;
-    a.wide             = id_bits + kSrcBits + kIdxBits > 32 ? 1u : 0u;
-    const size_t bytes = a.wide ? kTileBytesWide : kTileBytesNarrow;
-    int          grid  = kNumSMs * 2 * 4; // a few waves of two resident CTAs per SM, tiles strided over them
+    // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits; otherwise
+    // tiles choose per tile and the launch carries the 64-bit buffers
+    a.wide = R > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)
+    // 32 registers, 51 KB (narrow): four resident CTAs per SM; a few waves of them, tiles strided over the grid
+    int grid = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * 4;
     if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
-    const char *exp_sort = std::getenv("MSGPU_EXP_SORT");
-    if (exp_sort && exp_sort[0] == 'r') { // radix variant
-      MSGPU_LAUNCH("pair_tiles", st, pair_tiles_kernel<false><<<grid, kFusedBlock, bytes, st>>>(a));
-    } else {
-      static bool attr2 = false;
-      if (!attr2) {
-        MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
-        attr2 = true;
-      }
-      // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits
-      a.wide = R > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)
-      grid   = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * 4; // 40 registers, 51 KB (narrow): three resident CTAs per SM
-      if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
-      MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
-    }
+    MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
   }
   run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{tile_cnt}, my_tiles, em_base, totals + 0),
             scan_job<unsigned long long>(arena, st, 1, TileHeads{tile_cnt}, my_tiles, ed_base, totals + 1));
