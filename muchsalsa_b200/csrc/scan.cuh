@@ -1,11 +1,12 @@
 // scan.cuh — device-wide exclusive prefix sum in ONE launch (single pass, decoupled look-back), hand-written.
 //
-// The arrays scanned on this path are per-line, per-match, per-read or per-unitig: tens to hundreds of tiles, so what a
-// scan costs is its launches, not its bytes.  One kernel: a block takes a ticket (tiles are numbered in the order blocks
-// start, so a tile only ever waits for tiles that are already running), reduces its 2048 items, publishes the tile
-// aggregate, looks back over its predecessors' aggregates / inclusive prefixes with one warp, publishes its own
-// inclusive prefix and writes its outputs.  Every input value is evaluated once.  Input values come from a functor so
-// flags packed in bytes / derived counts need no staging array.
+// The arrays scanned on this path are per-line, per-match, per-read or per-unitig: one to a few hundred tiles, so what
+// a scan costs is its latency, not its bytes.  One kernel: a block takes a ticket (tiles are numbered in the order
+// blocks start, so a tile only ever waits for tiles that are already running), reduces its 8192 items (a warp owns
+// 512 consecutive ones, lane-striped, so every load and store is one contiguous run), publishes the tile aggregate,
+// looks back over its predecessors' aggregates / inclusive prefixes, publishes its own inclusive prefix and writes
+// its outputs.  Every input value is evaluated once.  Input values come from a functor so flags packed in bytes /
+// derived counts need no staging array.  Up to four independent scans share one launch (blockIdx.y picks the scan).
 //
 // The per-tile status words live in a region of the arena that outlives reset() and is used by scans only.  A status
 // is ONE 64-bit word — value << 18 | epoch << 2 | state (1: tile aggregate, 2: inclusive prefix) — so a single load
@@ -13,8 +14,7 @@
 // the word: stale words read as "not ready" and no launch is spent on clearing them.  Sums must stay below 2^46
 // (7e13; the largest quantity scanned here is the pair count, ~1e11 at human scale); a larger one traps.
 // The look-back window is the whole block (512 predecessors per round trip) and a tile holds 8192 items, so the scans of
-// this path (at most a few hundred tiles) resolve in one round trip after their own reduce; pollers back off with
-// nanosleep so that they do not crowd out the tiles that are still reducing.
+// this path (at most a few hundred tiles) resolve in one round trip after their own reduce.
 // `live` (optional): a count in device memory; items at index >= live contribute nothing and their outputs are not
 // written, tiles entirely behind it retire at once.  Lets a scan be launched over a capacity bound when the actual
 // count is only known on the device.
@@ -25,7 +25,7 @@
 namespace msgpu {
 
 constexpr int      kScanBlock     = 512;
-constexpr int      kScanItems     = 16; // contiguous items per thread
+constexpr int      kScanItems     = 16; // items per thread (lane-striped inside the warp's run of 512)
 constexpr int      kScanTile      = kScanBlock * kScanItems;
 constexpr int      kScanValShift  = 18;
 constexpr unsigned kScanEpochMask = 0xffffu;
