@@ -49,7 +49,7 @@ ShardLayout shard_layout(const msgpu_shard_header &h) {
   L.m_nr1           = take(M * 4);
   L.m_score         = take(M * 4);
   L.m_line          = take(M * 4);
-  L.m_rratio        = take(M * 8);
+  L.m_rratio        = take(0); // not sent: rRatio is recomputed from the ranges, bit for bit (BlastFileReader.cpp:118-119)
   L.m_flags         = take(M);
   L.total           = o;
   return L;
@@ -123,7 +123,6 @@ void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable 
   put(L.m_nr1, m.nr1, M * 4);
   put(L.m_score, m.score, M * 4);
   put(L.m_line, m.line, M * 4);
-  put(L.m_rratio, m.rratio, M * 8);
   put(L.m_flags, m.flags, M);
   if (job.n) MSGPU_LAUNCH("pack_blob", st, pack_blob_kernel<<<grid_for(h.blob_bytes / 16 + 1, 256, 2), 256, 0, st>>>(job, b));
 }
@@ -277,7 +276,9 @@ __global__ void __launch_bounds__(256)
     c.score[g]  = v.m_score[k];
     c.line[g]   = uint32_t(v.m_line[k] + v.line_base);
     c.flags[g]  = v.m_flags[k];
-    c.rratio[g] = v.m_rratio[k];
+    // rRatio = double(illuminaLength) / double(c8 - c7) (BlastFileReader.cpp:118-119): the same division the ingest
+    // did on the same integers, so it travels as those integers only
+    c.rratio[g] = __ddiv_rn(double(v.m_ir1[k] - v.m_ir0[k] + 1), double(v.m_nr1[k] - v.m_nr0[k] + 1));
   }
 }
 
