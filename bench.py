@@ -142,11 +142,7 @@ def run_ours(args):
 
     # ---- workload: at N ranks the genome is N times longer and rank r holds the r-th contiguous chunk of the PAF
     # (weak scaling: every GPU adds one base-size share; reads and unitigs of a boundary region meet in the merge)
-    if world == 1:
-        paf = make_workload(args.workload)
-    else:
-        cfg = synth.scaled(args.workload, world)
-        paf = synth.columns_to_paf(synth.generate_columns(cfg, (rank, world), sentinel=(rank == world - 1)))
+    paf = synth.rank_chunk(args.workload, rank, world)
     n_bytes = len(paf)
     # ONE explicit stream for everything: the library's kernels, torch's L2 flush and events, and the tensors NCCL
     # reads and writes.  (Not the default stream: its handle is 0, which the C ABI reads as "the context's own stream";
@@ -189,6 +185,7 @@ def run_ours(args):
     counts = gb.counts()
     torch.cuda.synchronize()
     barrier()
+    parity = check_parity(gb, args.workload, rank, world, dist)
 
     # ---- timed region 1: device-resident throughput (CUDA events on the library's stream, max over ranks)
     sampler = ClockSampler(local)
@@ -291,12 +288,17 @@ def run_ours(args):
     for it in range(min(args.steps, 3) + 1):
         step_device()
         gb.chain_overlaps(300)
-        gb.edge_filters(300)
+        if world == 1:  # the contraction test needs the whole edge table on one device (msgpu.h: msgpu_edge_filters)
+            gb.edge_filters(300)
         if it:  # the first call grows the arena (cudaMalloc inside the timed span): warm-up
             chain_ms.append(gb.chain_ms())
-            filter_ms.append(gb.edge_filters_ms())
+            if world == 1:
+                filter_ms.append(gb.edge_filters_ms())
     chain_t = reduce(sum(chain_ms) / len(chain_ms), "MAX")
-    filter_t = reduce(sum(filter_ms) / len(filter_ms), "MAX")
+    filter_t = sum(filter_ms) / len(filter_ms) if filter_ms else None
+
+    # ---- K8: the resident sequence store + batched slice / reverse complement (rank 0 at N = 1)
+    sequence = bench_sequences(gb, args.workload, stream) if world == 1 and not args.no_sequence else None
 
     # ---- the reference's CPU path beside it (bounded sample, rank 0 at N = 1 only)
     cpu = cpu_baseline(args.workload) if world == 1 else None
@@ -310,8 +312,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32 keys + f64 scores",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}-scale synthetic PAF x{world} (muchsalsa_b200.synth, seed fixed; at N "
-                               "GPUs the genome is N times longer and rank r holds the r-th chunk of the PAF)",
+        "config": {"workload": workload_label(args.workload, world),
                    "paf_bytes": int(bytes_h2d), "lines": counts["n_lines"], "kept_matches": counts["n_matches"],
                    "reads": counts["n_reads"], "unitigs": counts["n_unitigs"], "pairs": counts["n_pairs"],
                    "edges": int(n_edges), "edge_matches": int(n_em),
@@ -331,12 +332,19 @@ def run_ours(args):
                 "device-resident edge tables; bit-exact vs the reference (tests/test_chain_gpu.py)",
         "ms": round(chain_t, 3), "edges_per_s": n_edges / chain_t * 1e3,
         "cpu_reference": (cpu or {}).get("chain")}
-    out["edge_filters"] = {
-        "what": "per-edge findContractionEdges (+ sanityCheck), findDeletableEdges, computeBitweight "
-                "(src/main.cpp:416-460, 534-573, sc.cpp) on the device-resident order tables; identical to the "
-                "reference (tests/test_filters_gpu.py)",
-        "ms": round(filter_t, 3), "edges_per_s": n_edges / filter_t * 1e3,
-        "cpu_reference": ((cpu or {}).get("chain") or {}).get("filters")}
+    out["parity"] = parity["ok"]
+    out["parity_detail"] = parity
+    if filter_t is not None:
+        out["edge_filters"] = {
+            "what": "per-edge findContractionEdges (+ sanityCheck), findDeletableEdges, computeBitweight "
+                    "(src/main.cpp:416-460, 534-573, sc.cpp) on the device-resident order tables; identical to the "
+                    "reference (tests/test_filters_gpu.py)",
+            "ms": round(filter_t, 3), "edges_per_s": n_edges / filter_t * 1e3,
+            "cpu_reference": ((cpu or {}).get("chain") or {}).get("filters")}
+    else:
+        out["edge_filters"] = {"skipped": "needs the whole edge table on one device; every rank holds one slice"}
+    if sequence is not None:
+        out["sequence"] = sequence
     if world > 1:
         x = [v for v in xch_ms if v is not None]
         x_ms = reduce(sum(x) / len(x), "MAX") if x else None
@@ -349,6 +357,166 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def check_parity(gb, workload, rank, world, dist):
+    """Is what the timed steps build the reference's result?  Every rank digests its slice of the edge tables on the
+    device (msgpu_result_digest: order-independent sums + invariant violations); the sums over the ranks must equal
+    the digest recorded from the CPU checkers for the same PAF (tests/golden/sum_digests.json, written by
+    tests/golden/make_sum_digests.py), and the slices' key ranges must follow each other in rank order."""
+    import torch
+    d = gb.digest()
+    keys = ("n_edges", "n_edge_matches", "edge_sum", "em_sum", "violations")
+    lo_hi = [(d[k] & 0xffffffff, d[k] >> 32) for k in keys]
+    v = [x for pair in lo_hi for x in pair] + [d["first_key"] >> 32, d["first_key"] & 0xffffffff,
+                                               d["last_key"] >> 32, d["last_key"] & 0xffffffff]
+    t = torch.tensor(v, dtype=torch.int64, device="cuda")
+    if dist is not None:
+        allv = torch.empty(world * t.numel(), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allv, t)
+        allv = allv.view(world, -1).cpu().tolist()
+    else:
+        allv = [t.cpu().tolist()]
+    tot = {}
+    for i, k in enumerate(keys):  # 32-bit halves summed exactly, recombined mod 2^64
+        lo, hi = sum(r[2 * i] for r in allv), sum(r[2 * i + 1] for r in allv)
+        tot[k] = (lo + (hi << 32)) & ((1 << 64) - 1)
+    ordered, prev = True, -1
+    for r in allv:
+        first, last = (r[10] << 32) | r[11], (r[12] << 32) | r[13]
+        if (r[0] + (r[1] << 32)) == 0:
+            continue  # an empty slice
+        ordered = ordered and prev < first <= last
+        prev = last
+    gp = os.path.join(ROOT, "tests", "golden", "sum_digests.json")
+    gold = json.load(open(gp)).get(f"{workload}x{world}") if os.path.exists(gp) else None
+    out = {"digest": {k: tot[k] for k in keys}, "slices_in_key_order": ordered, "golden": None, "ok": None}
+    if gold is not None:
+        same = all(tot[k] == gold[k] for k in ("n_edges", "n_edge_matches", "edge_sum", "em_sum"))
+        out["golden"] = f"tests/golden/sum_digests.json[{workload}x{world}] (recorded from the {gold['source']})"
+        out["ok"] = bool(same and ordered and tot["violations"] == 0)
+    else:
+        out["note"] = "no golden digest for this workload: invariants only"
+        out["invariants_ok"] = bool(ordered and tot["violations"] == 0)
+    return out
+
+
+def bench_sequences(gb, workload, stream, n_req=1 << 20):
+    """K8 (d): load both sequence files into the resident store, then one batch of n_req
+    requests shaped like assemblePath's (ap.cpp:352-579: flanks of 50-5000 bases of reads and unitigs, half of them
+    reverse complemented) through msgpu_seq_fetch_batch_device (everything in HBM) and through the host-buffer entry;
+    the reference's get{Illumina,Nanopore}Sequence loop on a bounded sample of the same requests beside it."""
+    import numpy as np
+    import torch
+    from muchsalsa_b200 import synth
+    if workload not in ("small", "ecoli", "yeast"):
+        return None
+    ufa, nfa = synth.generate_sequences(workload)
+    t0 = time.perf_counter()
+    gb.seq_load_buffers(ufa, nfa, False)
+    load_s = time.perf_counter() - t0
+    g = synth.generate_columns(synth.CONFIGS[workload])["_geom"]
+    rng = np.random.Generator(np.random.PCG64(99))
+    which = (rng.random(n_req) < 0.8).astype(np.uint32)  # mostly read flanks, some unitig anchors
+    idx = np.where(which == 1, rng.integers(0, g["rlen"].size, n_req), rng.integers(0, g["ulen"].size, n_req))
+    names_r, names_u = g["rname"], np.arange(g["ulen"].size)
+    # sequence ids continue the numbering of the last build; resolve by name like the shim does
+    rid = np.array([gb.seq_id(1, f"r{int(x)}") for x in names_r], np.uint32)
+    uid = np.array([gb.seq_id(0, f"u{int(x)}") for x in names_u], np.uint32)
+    ids = np.where(which == 1, rid[np.minimum(idx, rid.size - 1)], uid[np.minimum(idx, uid.size - 1)]).astype(np.uint32)
+    length = np.where(which == 1, g["rlen"][np.minimum(idx, g["rlen"].size - 1)],
+                      g["ulen"][np.minimum(idx, g["ulen"].size - 1)]).astype(np.int64)
+    want = rng.integers(50, 5001, n_req)
+    left = (rng.random(n_req) * np.maximum(length - want, 1)).astype(np.int64)
+    right = np.minimum(left + want - 2, length - 1)  # get*Sequence returns bases left .. right + 1 inclusive
+    reqs = np.stack([which, ids, left.astype(np.uint32), right.astype(np.uint32),
+                     (rng.random(n_req) < 0.5).astype(np.uint32)], axis=1).astype(np.uint32)
+    d_reqs = torch.from_numpy(reqs.view(np.int32)).cuda()
+    bound = int(np.minimum(want, length).sum()) + 64
+    d_out = torch.empty(bound, dtype=torch.uint8, device="cuda")
+    d_off = torch.empty(n_req + 1, dtype=torch.int64, device="cuda")
+    d_st = torch.empty(n_req, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def run():
+        gb.seq_fetch_batch_device(d_reqs.data_ptr(), n_req, d_out.data_ptr(), bound, d_off.data_ptr(), d_st.data_ptr())
+
+    for _ in range(3):
+        run()
+    bases = int(d_off[-1].item())
+    ms = []
+    for _ in range(5):
+        flush.zero_()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        run()
+        b.record(stream)
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    gb.profile(True)
+    flush.zero_()
+    run()
+    ks = gb.kernel_stats()
+    gb.profile(False)
+    peak, peak_src = peaks()
+    copy_ms = ks.get("slice_copy", (1, float("nan")))[1]
+    dev_ms = sum(ms) / len(ms)
+    # host-buffer entry (requests and output in host memory, copies inside the timed region)
+    h_out, h_off, h_st = np.empty(bound, np.uint8), np.empty(n_req + 1, np.uint64), np.empty(n_req, np.uint8)
+    gb.seq_fetch_batch_host(reqs, h_out, h_off, h_st)
+    t0 = time.perf_counter()
+    gb.seq_fetch_batch_host(reqs, h_out, h_off, h_st)
+    host_s = time.perf_counter() - t0
+    ok = bool((d_st == 0).all().item()) and int(h_off[-1]) == bases
+    out = {"what": "msgpu_seq_load_buffers + msgpu_seq_fetch_batch(_device): strSlice / getReverseComplement / "
+                   "get{Illumina,Nanopore}Sequence (SequenceUtils.cpp:27-85) over the store resident in HBM",
+           "store_bytes": len(ufa) + len(nfa), "load_s": round(load_s, 3), "requests": n_req, "bases": bases,
+           "request_shape": "80 % read flanks / 20 % unitig anchors, 50-5000 bases, half reverse complemented",
+           "device_ms": round(dev_ms, 3), "bases_per_s": bases / dev_ms * 1e3,
+           "host_buffers_ms": round(host_s * 1e3, 3), "host_buffers_bases_per_s": bases / host_s,
+           "all_requests_ok": ok,
+           "roofline": {"kernel": "slice_copy", "bound": "hbm", "algorithmic_bytes_per_launch": 2 * bases,
+                        "us_per_launch": round(copy_ms * 1e3, 2), "achieved": round(2 * bases / copy_ms / 1e6, 1),
+                        "peak": peak, "unit": "GB/s", "frac": round(2 * bases / copy_ms / 1e6 / peak, 4),
+                        "peak_source": peak_src, "definition": "SURVEY.md §8(d): requested bases x (1 read + 1 write)"},
+           "kernels_ms": {k: round(v[1], 4) for k, v in ks.items()}}
+    # the reference numbers sequences in file order when no PAF primed its registries: same requests, its ids
+    reqs_ref = reqs.copy()
+    reqs_ref[:, 1] = idx.astype(np.uint32)
+    out["cpu_reference"] = seq_cpu_baseline(ufa, nfa, reqs_ref)
+    return out
+
+
+def seq_cpu_baseline(ufa, nfa, reqs, n_sample=20000):
+    """The reference's own loop (oracle/_ref/msref_cli seq: SequenceAccessor + get*Sequence, unmodified) on the first
+    n_sample requests of the same batch, 1 thread and all host threads (the accessor serialises on a mutex per file)."""
+    cli = os.path.join(ROOT, "oracle", "_ref", "msref_cli")
+    if not os.path.exists(cli):
+        return {"unavailable": "oracle/_ref/msref_cli not built"}
+    import numpy as np
+    td = tempfile.mkdtemp(prefix="msseq_")
+    try:
+        pu, pn, pr = os.path.join(td, "u.fa"), os.path.join(td, "n.fa"), os.path.join(td, "reqs.bin")
+        open(pu, "wb").write(ufa)
+        open(pn, "wb").write(nfa)
+        sample = reqs[:n_sample].copy()
+        open(pr, "wb").write(sample.astype(np.int32).tobytes())
+        res = {}
+        for threads in sorted({1, os.cpu_count() or 1}):
+            p = subprocess.run([cli, "seq", pu, pn, pr, str(threads)], capture_output=True, text=True, timeout=900)
+            if p.returncode != 0:
+                res[f"threads_{threads}"] = {"error": p.returncode}
+                continue
+            r = json.loads(p.stdout.strip().splitlines()[-1])
+            res[f"threads_{threads}"] = {"bases_per_s": r["bases"] / r["seconds"], "seconds": round(r["seconds"], 3),
+                                         "requests": r["requests"], "bases": r["bases"]}
+        res["sample"] = f"first {len(sample)} requests of the batch"
+        res["kind"] = "reference"
+        return res
+    finally:
+        import shutil
+        shutil.rmtree(td, ignore_errors=True)
 
 
 def result_bytes(c, gb):
@@ -383,21 +551,21 @@ def cpu_baseline(workload, steps=1):
         if not os.path.exists(cli):
             return cpu_baseline_port(paf, sample)
         ncpu = os.cpu_count() or 1
-        multi, rc = _run_ref_cli(path, ncpu) if ncpu > 1 else (None, 0)
-        res, threads, note = multi, ncpu, None
-        if multi is None:
-            note = (f"reference with {ncpu} threads exited with status {rc} (data race on the adjacency list, "
-                    "Graph.cpp:96-116 vs 212-230); timed with 1 thread, its only reliable mode")
-            best = None
-            for _ in range(steps):
-                r1, rc1 = _run_ref_cli(path, 1)
-                if r1 is None:
-                    return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
-                            "note": f"reference failed with status {rc1}"}
-                t = r1["t_index"] + r1["t_read"] + r1["t_edges"]
-                if best is None or t < best[0]:
-                    best = (t, r1)
-            res, threads = best[1], 1
+        r1, rc1 = _run_ref_cli(path, 1)
+        if r1 is None:
+            return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
+                    "note": f"reference failed with status {rc1}"}
+        res, threads, note = r1, 1, None
+        if ncpu > 1:  # all host threads: the reference either exits -11 (race on the adjacency list) or crawls on its locks
+            multi, rc = _run_ref_cli(path, ncpu)
+            if multi is None:
+                note = (f"reference with {ncpu} threads exited with status {rc} (data race on the adjacency list, "
+                        "Graph.cpp:96-116 vs 212-230); timed with 1 thread, its only reliable mode")
+            else:
+                tn, t1 = (sum(x[k] for k in ("t_index", "t_read", "t_edges")) for x in (multi, r1))
+                note = f"1 thread {t1:.2f} s, {ncpu} threads {tn:.2f} s on this sample; the faster is reported"
+                if tn < t1:
+                    res, threads = multi, ncpu
         t = res["t_index"] + res["t_read"] + res["t_edges"]
         chain = None
         try:  # the stage after construction on the same sample (1 thread; edges are independent jobs in the reference)
@@ -429,26 +597,81 @@ def cpu_baseline_port(paf, sample):
             "seconds": round(dt, 3), "edges_per_s": c["edges"] / dt, "note": "oracle/_ref absent: timed the C port"}
 
 
+def workload_label(workload, world):
+    return (f"{workload}-scale synthetic PAF x{world} (muchsalsa_b200.synth, seed fixed; at N GPUs the genome is N "
+            "times longer and rank r holds the r-th chunk of the PAF)")
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on this box's host cores, same metric."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref/msref_cli = the unmodified
+    reference sources compiled by oracle/Makefile: BlastFileAccessor + BlastFileReader::read() +
+    MatchMap::calculateEdges()) on this box's host cores, on OUR arm's config.
+
+    Every timed step builds the WHOLE workload when K steps of it fit the time budget (MSGPU_REF_BUDGET_S, default
+    1500 s: yeast at N = 1 does, ~45 s per step on one core); otherwise the largest 1/d unitig shard of it that fits
+    (yeast x N at N > 1, thaliana, human) and `cpu_baseline.sample` says so.  The rate is per kept match either way.
+    The reference is only reliable with one worker thread (it races on the adjacency list and exits -11 with more);
+    that is probed ONCE, on a small shard, not per step.  Warm-up steps run on the small shard too: a fresh CPU
+    process has no state to warm beyond the page cache and the clocks."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    shard = CPU_SAMPLE.get(args.workload)
-    paf = make_workload(args.workload, shard)
-    with tempfile.NamedTemporaryFile(suffix=".paf", delete=False) as f:
+    from muchsalsa_b200 import synth
+    world = max(1, args.gpus)
+    cfg = synth.scaled(args.workload, world)
+    budget = float(os.environ.get("MSGPU_REF_BUDGET_S", "1500"))
+    ncpu = os.cpu_count() or 1
+
+    def write(paf):
+        f = tempfile.NamedTemporaryFile(suffix=".paf", delete=False)
         f.write(paf)
-        path = f.name
+        f.close()
+        return f.name
+
+    probe_d = {"small": 1, "ecoli": 1}.get(args.workload, 24 * world)
+    probe_path = write(synth.columns_to_paf(synth.generate_columns(cfg, (0, probe_d) if probe_d > 1 else None)))
+    paths = [probe_path]
     try:
-        ncpu = os.cpu_count() or 1
-        threads, note = ncpu, None
-        probe, rc = _run_ref_cli(path, ncpu) if ncpu > 1 else (None, 0)
-        if probe is None:
-            threads = 1
-            note = (f"{ncpu} threads: exit status {rc} (unlocked adjacency-list reads race the writer, "
-                    "Graph.cpp:96-116 vs 212-230); 1 thread is the reference's only reliable mode")
-        for _ in range(args.warmup):
-            _run_ref_cli(path, threads)
+        # thread count: whichever of {1, all host threads} is faster on the probe shard — with more than one thread the
+        # reference either exits -11 (unlocked adjacency-list reads race the writer, Graph.cpp:96-116 vs 212-230) or
+        # crawls on its four global locks
+        t0 = time.perf_counter()
+        r, rc = _run_ref_cli(probe_path, 1)
+        probe_s = time.perf_counter() - t0
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/msref_cli failed (status {rc})"}))
+            return
+        t1 = r["t_index"] + r["t_read"] + r["t_edges"]
+        threads, note = 1, None
+        if ncpu > 1:
+            t0 = time.perf_counter()
+            multi, rc = _run_ref_cli(probe_path, ncpu)
+            multi_s = time.perf_counter() - t0
+            if multi is None:
+                note = (f"{ncpu} threads: exit status {rc} (data race on the adjacency list); 1 thread is the "
+                        "reference's only reliable mode")
+            else:
+                tn = multi["t_index"] + multi["t_read"] + multi["t_edges"]
+                note = f"probe shard: 1 thread {t1:.2f} s, {ncpu} threads {tn:.2f} s; timed with the faster"
+                if tn < t1:
+                    threads, probe_s = ncpu, multi_s
+        for _ in range(max(0, args.warmup - 1)):
+            _run_ref_cli(probe_path, threads)
+        # the largest share of the workload whose K steps fit the budget
+        est_full = probe_s * probe_d * 1.2
+        d = 1
+        while args.steps * est_full / d > budget and d < probe_d:
+            d += 1
+        if d == 1:
+            paf = b"".join(synth.rank_chunk(args.workload, rr, world) for rr in range(world))
+            sample = "whole workload"
+        elif d >= probe_d:
+            paf, sample = None, f"unitig shard 0 of {probe_d} of the workload"
+        else:
+            paf = synth.columns_to_paf(synth.generate_columns(cfg, (0, d)))
+            sample = f"unitig shard 0 of {d} of the workload"
+        path = probe_path if paf is None else write(paf)
+        paths.append(path)
         tot, rows = 0.0, None
         for _ in range(args.steps):
             r, rc = _run_ref_cli(path, threads)
@@ -458,21 +681,33 @@ def run_reference(args):
             tot += r["t_index"] + r["t_read"] + r["t_edges"]
             rows = r
         value = rows["n_vm"] * args.steps / tot
-        sample = "whole workload" if shard is None else f"unitig shard {shard[0]} of {shard[1]} of the workload"
+        config = {"workload": workload_label(args.workload, world)}
+        gp = os.path.join(ROOT, "tests", "golden", "sum_digests.json")
+        gold = json.load(open(gp)).get(f"{args.workload}x{world}") if os.path.exists(gp) else None
+        if d == 1:
+            config.update(kept_matches=rows["n_vm"], reads=rows["n_reads"], edges=rows["n_edges"],
+                          edge_matches=rows["n_em"])
+        elif gold:
+            config.update(kept_matches=gold["n_matches"], reads=gold["n_reads"], edges=gold["n_edges"],
+                          edge_matches=gold["n_edge_matches"])
         out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32 keys + f64 scores",
-               "data": "synthetic",
-               "config": {"workload": f"{args.workload}-scale synthetic PAF (muchsalsa_b200.synth, seed fixed)",
-                          "sample": sample, "kept_matches": rows["n_vm"], "edges": rows["n_edges"],
-                          "edge_matches": rows["n_em"]},
+               "data": "synthetic", "config": config,
                "edges_per_s": rows["n_edges"] * args.steps / tot,
+               "edge_matches_per_s": rows["n_em"] * args.steps / tot,
                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
-                                "sample": sample, "host_cpus": ncpu, "note": note},
+                                "sample": sample, "host_cpus": ncpu, "note": note,
+                                "rows_per_step": {k: rows[k] for k in ("n_reads", "n_vm", "n_edges", "n_em")},
+                                "warmup_on": f"unitig shard 0 of {probe_d}" if probe_d > 1 else "whole workload"},
                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     finally:
-        os.unlink(path)
+        for p in set(paths):
+            try:
+                os.unlink(p)
+            except OSError:
+                pass
 
 
 def _claim_stdout():
@@ -491,6 +726,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MSGPU_WORKLOAD", "yeast"))
+    ap.add_argument("--no-sequence", action="store_true", help="skip the K8 (sequence store) block")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -171,6 +171,24 @@ int msgpu_result_device(const msgpu_ctx *ctx, msgpu_tables *out);
 /* Copies the result to pinned host memory (once per build; later calls return the same pointers). */
 int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out);
 
+/* ---- digest: an order-independent checksum of the edge / edge-match tables, computed in HBM -------------------------
+ * The reference has no counterpart (it never serialises Graph / MatchMap); this is how results too large to download
+ * are compared: the digests of the slices of a multi-GPU build (or of the chunks of a chunked build) ADD UP, mod 2^64,
+ * to the digest of the one-GPU build and to the digest of the reference's tables (tests/golden/digests.json).
+ * With mix(x) = splitmix64's finaliser (x ^= x >> 30; x *= 0xbf58476d1ce4e5b9; x ^= x >> 27; x *= 0x94d049bb133111eb;
+ * x ^= x >> 31), for every edge match of edge (first, second)
+ *   h = mix(flags + 0x9e3779b97f4a7c15); h = mix(h ^ bits(score)); h = mix(h ^ (u32(ov1) << 32 | line));
+ *   h = mix(h ^ (unitig << 32 | u32(ov0))); em_sum += mix(h ^ (first << 32 | second))
+ * and for every edge   edge_sum += mix(mix(n_edge_matches_of_the_edge + 0xd1b54a32d192ed03) ^ (first << 32 | second)).
+ * violations counts rows that break an invariant of the tables: first < second, (first, second) strictly increasing,
+ * edge_em_begin strictly increasing from 0 to n_edge_matches, unitigs strictly increasing inside an edge,
+ * ov1 - ov0 > 100 (MatchMap.cpp:192).  first_key / last_key = (first << 32 | second) of the first / last edge of the
+ * slice (~0 / 0 when empty): consecutive slices of a multi-GPU build must satisfy last_key(r) < first_key(r + 1). */
+typedef struct msgpu_digest {
+  uint64_t n_edges, n_edge_matches, edge_sum, em_sum, first_key, last_key, violations;
+} msgpu_digest;
+int msgpu_result_digest(msgpu_ctx *ctx, msgpu_digest *out);
+
 /* ---- chaining + overlaps: the stage that consumes the construction (optional; the tables stay in HBM for it) --------
  * msgpu_chain_overlaps  replaces, for every edge of the last build, the job chainingAndOverlaps (src/main.cpp:170-178,
  *                       328-414) = getMaxPairwisePaths (mpp.cpp:145-305, checkCompatibility mpp.cpp:38-142) +

@@ -30,6 +30,11 @@ class Tables(C.Structure):
     ]
 
 
+class Digest(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in
+                ("n_edges", "n_edge_matches", "edge_sum", "em_sum", "first_key", "last_key", "violations")]
+
+
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "ingest_ms", "pair_ms", "merge_ms", "d2h_ms", "total_ms")]
 
@@ -85,6 +90,7 @@ SIGNATURES = {
     "msgpu_result_counts": (C.c_int, [C.c_void_p, C.POINTER(Counts)]),
     "msgpu_result_device": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),
     "msgpu_result_host": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),
+    "msgpu_result_digest": (C.c_int, [C.c_void_p, C.POINTER(Digest)]),
     "msgpu_chain_overlaps": (C.c_int, [C.c_void_p, C.c_uint64]),
     "msgpu_orders_device": (C.c_int, [C.c_void_p, C.POINTER(Orders)]),
     "msgpu_orders_host": (C.c_int, [C.c_void_p, C.POINTER(Orders)]),

@@ -205,6 +205,13 @@ class GraphBuilder:
             matches=m, edge_first=_np(t.edge_first, E, np.uint32), edge_second=_np(t.edge_second, E, np.uint32),
             edge_em_begin=_np(t.edge_em_begin, E + 1, np.uint64), edge_matches=em, timings=self.timings())
 
+    def digest(self) -> dict:
+        """Order-independent checksum + invariant violations of the edge tables, computed on the device
+        (msgpu_result_digest); the digests of slices / chunks add up mod 2^64."""
+        d = _lib.Digest()
+        self._check(self._lib.msgpu_result_digest(self._h, C.byref(d)))
+        return {k: int(getattr(d, k)) for k, _ in d._fields_}
+
     # ---- chaining + overlaps (the stage after construction)
     def chain_overlaps(self, wiggle_room: int = 300):
         """chainingAndOverlaps for every edge of the last build (src/main.cpp:328-414)."""
@@ -306,6 +313,51 @@ class GraphBuilder:
             raise MsGpuError(rc, "msgpu_seq_fetch_batch failed")
         raw = out.raw
         return [None if st[i] else raw[off[i]:off[i + 1]] for i in range(n)]
+
+
+    def seq_fetch_batch_device(self, dev_reqs: int, n: int, dev_out: int, capacity: int, dev_out_off: int,
+                               dev_status: int):
+        """msgpu_seq_fetch_batch_device: every buffer resident in HBM (device pointers as ints)."""
+        self._check(self._lib.msgpu_seq_fetch_batch_device(self._h, C.c_void_p(dev_reqs), n, C.c_void_p(dev_out),
+                                                           capacity, C.c_void_p(dev_out_off), C.c_void_p(dev_status)))
+        return self
+
+    def seq_fetch_batch_host(self, reqs: np.ndarray, out: np.ndarray, off: np.ndarray, status: np.ndarray):
+        """msgpu_seq_fetch_batch on caller-owned numpy buffers: reqs [n, 5] uint32 (which, id, left, right, direction),
+        out uint8 [capacity], off uint64 [n + 1], status uint8 [n]."""
+        n = int(reqs.shape[0])
+        rc = self._lib.msgpu_seq_fetch_batch(self._h, C.cast(reqs.ctypes.data, C.POINTER(_lib.SeqReq)), n,
+                                             C.c_void_p(out.ctypes.data), int(out.size),
+                                             C.cast(off.ctypes.data, _lib.u64p), C.cast(status.ctypes.data, _lib.u8p))
+        if rc != 0:
+            raise MsGpuError(rc, "msgpu_seq_fetch_batch failed")
+        return self
+
+
+class _DeviceSpan:
+    """A device pointer + length as a __cuda_array_interface__ object (v2), so torch / cupy can wrap it without a
+    copy.  The memory belongs to the library: valid until the next build on the context."""
+
+    def __init__(self, ptr: int, n: int, typestr: str, keep=None):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._keep = keep
+
+
+_TYPESTR = {"u1": "|u1", "i4": "<i4", "u4": "<u4", "i8": "<i8", "u8": "<u8", "f8": "<f8"}
+
+
+def device_view(ptr, n: int, kind: str):
+    """torch tensor over `n` elements of library-owned device memory (kind: u1 i4 u4 i8 u8 f8; unsigned 32/64-bit
+    columns are viewed as the signed type of the same width, which torch can index with).  Host plumbing for tests
+    and bench.py — nothing is copied."""
+    import torch
+    addr = C.cast(ptr, C.c_void_p).value if not isinstance(ptr, int) else ptr
+    if not addr or n == 0:
+        return torch.zeros(0, dtype={"u1": torch.uint8, "i4": torch.int32, "u4": torch.int32, "i8": torch.int64,
+                                     "u8": torch.int64, "f8": torch.float64}[kind], device="cuda")
+    signed = {"u4": "i4", "u8": "i8"}.get(kind, kind)
+    return torch.as_tensor(_DeviceSpan(addr, n, _TYPESTR[signed]), device="cuda")
 
 
 def _host_ptr(buf):

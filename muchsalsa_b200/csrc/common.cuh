@@ -53,7 +53,15 @@ public:
   // Status words of the single-pass scans (scan.cuh): regions that outlive reset() and that nothing else writes, one
   // per slot (up to four scans run concurrently in one launch).  Every call hands out the next epoch; flags written
   // under an older epoch read as "not ready", so a region is cleared only when it grows or when the 16-bit epoch wraps.
-  void *scan_state(int slot, size_t bytes, cudaStream_t st, unsigned *epoch) {
+  // Tickets: a scan of `n_tickets` tiles numbers them in the order its blocks start, from ONE counter per slot that
+  // only ever grows; the host knows how many tickets every earlier scan of the slot took (exactly one per tile), so
+  // a scan subtracts that base and nothing ever has to be cleared — a scan that is prepared but never launched, or
+  // one with a single tile, takes no ticket and leaves the bookkeeping untouched (unsigned wrap-around is harmless).
+  void *scan_state(int slot, size_t bytes, cudaStream_t st, unsigned *epoch, unsigned n_tickets, unsigned **ticket,
+                   unsigned *ticket_base) {
+    *ticket      = counter() + 8 + slot;
+    *ticket_base = m_ticket_base[slot];
+    m_ticket_base[slot] += n_tickets;
     if (bytes > m_scan_state_bytes[slot]) {
       if (m_scan_state[slot]) {
         MSGPU_CUDA(cudaStreamSynchronize(st));
@@ -66,7 +74,6 @@ public:
     if (++m_epoch >= (1u << 16)) {
       for (int k = 0; k < 4; ++k)
         if (m_scan_state[k]) MSGPU_CUDA(cudaMemsetAsync(m_scan_state[k], 0, m_scan_state_bytes[k], st));
-      MSGPU_CUDA(cudaMemsetAsync(counter() + 8, 0, 32 * sizeof(unsigned), st)); // the scans' ring of ticket counters
       m_epoch = 1;
     }
     *epoch = m_epoch;
@@ -82,7 +89,7 @@ public:
   // zero-initialised device counters that outlive reset(): kernels that use them leave them at zero again
   unsigned *counter() {
     if (!m_counter) {
-      MSGPU_CUDA(cudaMalloc(&m_counter, 512)); // [0..7] kernels' own counters, [8..39] ticket ring of the scans
+      MSGPU_CUDA(cudaMalloc(&m_counter, 512)); // [0..7] kernels' own counters, [8..11] ticket counters of the scans
       MSGPU_CUDA(cudaMemset(m_counter, 0, 512));
     }
     return m_counter;
@@ -134,6 +141,7 @@ private:
   void             *m_scan_state[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t            m_scan_state_bytes[4] = {0, 0, 0, 0};
   unsigned          m_epoch = 0;
+  unsigned          m_ticket_base[4] = {0, 0, 0, 0};
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

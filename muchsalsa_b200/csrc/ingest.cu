@@ -130,7 +130,7 @@ __global__ void line_index_finish_kernel(const char *__restrict__ paf, uint64_t 
 struct LineFields { // per-line scratch, structure-of-arrays, indexed by line
   int32_t  *c2, *ir1, *c6, *nr0, *nr1, *c9;
   uint32_t *rname_rel; // offset of the read name (field 5) from the line start
-  uint16_t *rname_len, *uname_len;
+  uint32_t *rname_len, *uname_len;
   uint64_t *rhash, *uhash;
   uint8_t  *flags;
 };
@@ -237,7 +237,6 @@ __device__ __forceinline__ bool parse_one_line(const char *s, uint64_t len, uint
     bool     add     = matches >= uint64_t(kMinimumMatches) && ilen >= kMinimumMatches;
     if (add) {
       bad = !(dev_stoi(s + fo[7], fl[7], &c7) && dev_stoi(s + fo[8], fl[8], &c8));
-      if (!bad && (fl[5] > 0xffffu || fl[0] > 0xffffu)) bad = true; // names longer than 64 KiB are not supported
       if (!bad) {
         flags = kFAccepted;
         if (fl[4] == 1 && s[fo[4]] == '+') flags |= kFDir;
@@ -249,8 +248,8 @@ __device__ __forceinline__ bool parse_one_line(const char *s, uint64_t len, uint
         f.nr1[li]       = c8 - 1;
         f.c9[li]        = c9;
         f.rname_rel[li] = fo[5];
-        f.rname_len[li] = uint16_t(fl[5]);
-        f.uname_len[li] = uint16_t(fl[0]);
+        f.rname_len[li] = fl[5];
+        f.uname_len[li] = fl[0];
         f.rhash[li]     = name_hash(s + fo[5], fl[5], seed);
         f.uhash[li]     = name_hash(s + fo[0], fl[0], seed ^ 0x9e3779b97f4a7c15ull);
         acc             = true;
@@ -676,8 +675,8 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   f.nr1       = arena.alloc<int32_t>(cap);
   f.c9        = arena.alloc<int32_t>(cap);
   f.rname_rel = arena.alloc<uint32_t>(cap);
-  f.rname_len = arena.alloc<uint16_t>(cap);
-  f.uname_len = arena.alloc<uint16_t>(cap);
+  f.rname_len = arena.alloc<uint32_t>(cap);
+  f.uname_len = arena.alloc<uint32_t>(cap);
   f.rhash     = arena.alloc<uint64_t>(cap);
   f.uhash     = arena.alloc<uint64_t>(cap);
   f.flags     = arena.alloc<uint8_t>(cap);
@@ -685,9 +684,10 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   uint32_t *dslot = arena.alloc<uint32_t>(cap);
   uint32_t *rid_of_line = arena.alloc<uint32_t>(cap), *uid_of_line = arena.alloc<uint32_t>(cap);
   uint32_t *rank_a = arena.alloc<uint32_t>(cap), *rank_b = arena.alloc<uint32_t>(cap);
-  // ids are handed out to accepted lines only, and an accepted line is longer still (>= 24 bytes): size the id-indexed
-  // tables and the hash tables (load factor <= 2/3 in the worst case, ~1/4 on real PAF) from that
-  const uint64_t cap_acc = n_bytes / 24 + 2;
+  // ids are handed out to accepted lines only; the shortest line the filter accepts is 20 bytes as well (std::getline
+  // takes empty fields: "\t\t0\t400\t\t\t1\t0\t1\t400\n" — both names and the strand empty), so the id-indexed tables,
+  // the match table and the hash tables (load factor <= 2/3 in the worst case, ~1/4 on real PAF) share the line bound
+  const uint64_t cap_acc = cap;
   reads.nlen = arena.alloc<int32_t>(cap_acc);
   reads.line = arena.alloc<uint32_t>(cap_acc);
   uint64_t *rsrc = arena.alloc<uint64_t>(cap_acc), *usrc = arena.alloc<uint64_t>(cap_acc);

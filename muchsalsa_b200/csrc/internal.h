@@ -127,6 +127,9 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
                      const void *const *dev_blobs, uint64_t *n_lines_out, ReadTable &reads, UnitigTable &unitigs,
                      MatchSoA &matches);
 
+// digest.cu : order-independent checksum + structural invariants of the edge tables, in HBM
+void run_digest(Arena &arena, cudaStream_t st, const EdgeTables &edges, msgpu_digest *out);
+
 // chain.cu : the stage after construction — per edge chaining of its edge matches and the overlap geometry
 // (src/main.cpp:328-414, mpp.cpp:38-305, ol.cpp:31-101) -> shadow flag + EdgeOrder rows
 void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, const UnitigTable &unitigs,

@@ -50,6 +50,7 @@ struct msgpu_ctx {
   std::string  error;
 
   bool          have_result = false;
+  uint32_t      n_parts     = 1; // > 1: the edge tables of the last build are one slice of a multi-GPU build
   uint64_t      n_lines     = 0;
   ReadTable     reads;
   UnitigTable   unitigs;
@@ -131,8 +132,9 @@ void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes, bool pair =
   cudaStream_t st  = ctx->stream;
   ctx->have_result = false;
   ctx->host_valid  = false;
+  ctx->n_parts     = 1;
   ctx->orders      = OrderTables{};
-    ctx->filters     = FilterTables{};
+  ctx->filters     = FilterTables{};
   ctx->arena.reset();
   ctx->profiler.clear();
   MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
@@ -272,6 +274,7 @@ int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t 
     ctx->filters     = FilterTables{};
     ctx->arena.reset();
     ctx->profiler.clear();
+    ctx->n_parts = 1;
     ctx->reads   = ReadTable{};
     ctx->unitigs = UnitigTable{};
     ctx->reads.n = n_reads;
@@ -350,6 +353,7 @@ int msgpu_build_from_shards(msgpu_ctx *ctx, uint32_t n_shards, const msgpu_shard
     run_shard_merge(ctx->arena, st, n_shards, headers, dev_blobs, &ctx->n_lines, ctx->reads, ctx->unitigs,
                     ctx->matches);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
+    ctx->n_parts = n_parts;
     run_pairing(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3], part, n_parts);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
     MSGPU_CUDA(cudaStreamSynchronize(st));
@@ -478,6 +482,14 @@ int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out) {
   });
 }
 
+int msgpu_result_digest(msgpu_ctx *ctx, msgpu_digest *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  return guarded(ctx, [&] {
+    if (!ctx->have_result) throw BuildError{MSGPU_ERR_NO_RESULT, "no construction to digest"};
+    run_digest(ctx->arena, ctx->stream, ctx->edges, out);
+  });
+}
+
 int msgpu_chain_overlaps(msgpu_ctx *ctx, uint64_t wiggle_room) {
   return guarded(ctx, [&] {
     if (!ctx->have_result) throw BuildError{MSGPU_ERR_NO_RESULT, "no construction to chain"};
@@ -563,6 +575,13 @@ int msgpu_edge_filters(msgpu_ctx *ctx, uint64_t wiggle_room) {
   return guarded(ctx, [&] {
     if (!ctx->have_result || !ctx->orders.valid)
       throw BuildError{MSGPU_ERR_NO_RESULT, "the edge filters need msgpu_chain_overlaps first"};
+    // findContractionEdges looks at the edges AROUND the start vertex of an order and at the third edge of every
+    // triangle (main.cpp:432-443): on one slice of a multi-GPU build those rows live on other ranks, hasEdge would
+    // answer "no" and the verdict would flip.  Refuse instead of answering wrongly.
+    if (ctx->n_parts > 1)
+      throw BuildError{MSGPU_ERR_LIMIT,
+                       "msgpu_edge_filters needs the whole edge table on one device; this context holds one slice of " +
+                           std::to_string(ctx->n_parts) + " (multi-GPU build)"};
     ctx->filters            = FilterTables{};
     ctx->filters_host_valid = false;
     ctx->profiler.clear();
@@ -748,6 +767,7 @@ int msgpu_seq_fetch_batch_device(msgpu_ctx *ctx, const msgpu_seq_req *dev_reqs, 
                                  uint64_t *dev_out_off, uint8_t *dev_status) {
   return guarded(ctx, [&] {
     if (!ctx->seq) throw BuildError{MSGPU_ERR_NO_RESULT, "no sequence store loaded"};
+    ctx->profiler.clear(); // per-kernel times of THIS batch (msgpu_profile_read)
     seq_fetch_device(ctx->seq, ctx->stream, dev_reqs, n, dev_out, cap, dev_out_off, dev_status);
   });
 }

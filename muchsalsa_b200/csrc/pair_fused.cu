@@ -988,11 +988,9 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   a.error     = d_u32 + 3;
   if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st)); // planning done; what follows is "merge" time
   if (my_tiles) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
-      attr_set = true;
-    }
+    // the opt-in is an attribute of the function ON THE CURRENT DEVICE: set it before every launch (a context per
+    // GPU in one process is supported, and the call costs less than a microsecond)
+    MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
     // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits; otherwise
     // tiles choose per tile and the launch carries the 64-bit buffers
     a.wide = R > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)

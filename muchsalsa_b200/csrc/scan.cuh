@@ -46,10 +46,12 @@ template <class T, class InFn> struct ScanJob {
   T                  *total_out; // device; may be null
   unsigned long long *state;
   unsigned            epoch;
+  unsigned           *ticket;      // the slot's ticket counter (grows forever) ...
+  unsigned            ticket_base; // ... and its value when this scan starts (host bookkeeping, Arena::scan_state)
 };
 
 // the work of one block of one scan; blocks past the scan's tiles (a launch is sized for its longest scan) leave
-template <class Job> __device__ __forceinline__ void scan_block(const Job &job, unsigned *counters) {
+template <class Job> __device__ __forceinline__ void scan_block(const Job &job) {
   using T = typename Job::value_type;
   constexpr int       kWarps = kScanBlock / 32;
   __shared__ unsigned s_tile;
@@ -62,10 +64,9 @@ template <class Job> __device__ __forceinline__ void scan_block(const Job &job, 
   const unsigned epoch = job.epoch;
   const unsigned l = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    // the ticket counter of this scan; the slot half a ring ahead is cleared for a later scan (scans on one stream
-    // are ordered, so nobody is using it).  A one-tile scan needs no ticket.
-    s_tile = n_tiles_cap > 1 ? atomicAdd(&counters[epoch & 31u], 1u) : 0u;
-    if (blockIdx.x == 0) counters[(epoch + 16u) & 31u] = 0u;
+    // tiles are numbered in the order blocks start; every block of a multi-tile scan takes exactly one ticket, which
+    // is what the host adds to the slot's base for the next scan.  A one-tile scan needs no ticket.
+    s_tile = n_tiles_cap > 1 ? atomicAdd(job.ticket, 1u) - job.ticket_base : 0u;
     uint64_t n = job.n_cap;
     if (job.live.p32 || job.live.p64) {
       const uint64_t c = (job.live.p32 ? uint64_t(*job.live.p32) : uint64_t(*job.live.p64)) + job.live.extra;
@@ -157,18 +158,16 @@ template <class Job> __device__ __forceinline__ void scan_block(const Job &job, 
 }
 
 // up to four independent scans in ONE launch (blockIdx.y picks the scan): they cost the latency of one
-template <class J0> __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, unsigned *counters) {
-  scan_block(j0, counters);
-}
-template <class J0, class J1> __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, J1 j1, unsigned *counters) {
-  if (blockIdx.y == 0) scan_block(j0, counters); else scan_block(j1, counters);
+template <class J0> __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0) { scan_block(j0); }
+template <class J0, class J1> __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, J1 j1) {
+  if (blockIdx.y == 0) scan_block(j0); else scan_block(j1);
 }
 template <class J0, class J1, class J2, class J3>
-__global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, J1 j1, J2 j2, J3 j3, unsigned *counters) {
-  if (blockIdx.y == 0) scan_block(j0, counters);
-  else if (blockIdx.y == 1) scan_block(j1, counters);
-  else if (blockIdx.y == 2) scan_block(j2, counters);
-  else scan_block(j3, counters);
+__global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, J1 j1, J2 j2, J3 j3) {
+  if (blockIdx.y == 0) scan_block(j0);
+  else if (blockIdx.y == 1) scan_block(j1);
+  else if (blockIdx.y == 2) scan_block(j2);
+  else scan_block(j3);
 }
 
 // Prepares a job: out[i] = sum_{j<i} in(j) for i < n; *total_out (device) = sum of all.  `out` may be null (total
@@ -178,20 +177,23 @@ template <class T, class InFn>
 ScanJob<T, InFn> scan_job(Arena &arena, cudaStream_t st, int slot, InFn in, uint64_t n, T *out, T *total_out,
                           ScanLive live = ScanLive{}) {
   const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
-  unsigned       epoch   = 0;
-  auto *state = static_cast<unsigned long long *>(arena.scan_state(slot, n_tiles * sizeof(unsigned long long), st, &epoch));
-  return ScanJob<T, InFn>{in, n, live, out, total_out, state, epoch};
+  unsigned       epoch = 0, *ticket = nullptr, ticket_base = 0;
+  // the launch covers this scan's tiles whenever it happens at all (run_scans sizes the grid for the longest job and
+  // skips the launch only when every job is empty), so a multi-tile scan takes exactly n_tiles tickets
+  auto *state = static_cast<unsigned long long *>(arena.scan_state(
+      slot, n_tiles * sizeof(unsigned long long), st, &epoch, n_tiles > 1 ? unsigned(n_tiles) : 0u, &ticket, &ticket_base));
+  return ScanJob<T, InFn>{in, n, live, out, total_out, state, epoch, ticket, ticket_base};
 }
 inline unsigned scan_grid(uint64_t n) { return unsigned((n + kScanTile - 1) / kScanTile); }
 
 template <class J0> void run_scans(Arena &arena, cudaStream_t st, const J0 &j0) {
   if (!j0.n_cap) return;
-  MSGPU_LAUNCH("scan", st, scan_kernel<J0><<<scan_grid(j0.n_cap), kScanBlock, 0, st>>>(j0, arena.counter() + 8));
+  MSGPU_LAUNCH("scan", st, scan_kernel<J0><<<scan_grid(j0.n_cap), kScanBlock, 0, st>>>(j0));
 }
 template <class J0, class J1> void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1) {
   const uint64_t n = j0.n_cap > j1.n_cap ? j0.n_cap : j1.n_cap;
   if (!n) return;
-  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1><<<dim3(scan_grid(n), 2), kScanBlock, 0, st>>>(j0, j1, arena.counter() + 8)));
+  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1><<<dim3(scan_grid(n), 2), kScanBlock, 0, st>>>(j0, j1)));
 }
 template <class J0, class J1, class J2, class J3>
 void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1, const J2 &j2, const J3 &j3) {
@@ -200,7 +202,7 @@ void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1, const 
   n          = j2.n_cap > n ? j2.n_cap : n;
   n          = j3.n_cap > n ? j3.n_cap : n;
   if (!n) return;
-  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1, J2, J3><<<dim3(scan_grid(n), 4), kScanBlock, 0, st>>>(j0, j1, j2, j3, arena.counter() + 8)));
+  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1, J2, J3><<<dim3(scan_grid(n), 4), kScanBlock, 0, st>>>(j0, j1, j2, j3)));
 }
 
 // a single scan.  n == 0 is allowed (total = 0).

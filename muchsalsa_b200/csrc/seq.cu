@@ -275,28 +275,80 @@ struct WindowCount {
   __device__ uint64_t operator()(uint64_t i) const { return w[i].count; }
 };
 
-// One warp per request.  Forward: straight copy.  Reverse complement: out[k] = comp(src[count-1-k]).
-// src_sel(i) picks the source text of request i (0 / 1 = unitigs / reads for the store; always 0 for caller text).
+// complement of four packed bytes: only upper-case A<->T (0x41 ^ 0x54 = 0x15) and C<->G (0x43 ^ 0x47 = 0x04) change
+__device__ __forceinline__ uint32_t complement4(uint32_t w) {
+  const uint32_t at = __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x54545454u);
+  const uint32_t cg = __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u);
+  return w ^ (at & 0x15151515u) ^ (cg & 0x04040404u);
+}
+
+// the 16 bytes that start at the (arbitrarily aligned) address p: two aligned 128-bit loads + funnel shifts.  Every
+// lane of a warp works on the same request, so the misalignment is warp-uniform and the switch does not diverge.
+__device__ __forceinline__ uint4 load16_unaligned(const char *p) {
+  const uintptr_t a   = reinterpret_cast<uintptr_t>(p);
+  const uint4    *q   = reinterpret_cast<const uint4 *>(a & ~uintptr_t(15));
+  const unsigned  off = unsigned(a & 15u);
+  const uint4     x   = __ldg(q);
+  if (off == 0) return x;
+  const uint4    y  = __ldg(q + 1); // holds `off` of the wanted bytes, so it lies inside the text
+  const unsigned sh = (off & 3u) * 8u;
+  uint32_t       a0, a1, a2, a3, a4;
+  switch (off >> 2) {
+  case 0: a0 = x.x, a1 = x.y, a2 = x.z, a3 = x.w, a4 = y.x; break;
+  case 1: a0 = x.y, a1 = x.z, a2 = x.w, a3 = y.x, a4 = y.y; break;
+  case 2: a0 = x.z, a1 = x.w, a2 = y.x, a3 = y.y, a4 = y.z; break;
+  default: a0 = x.w, a1 = y.x, a2 = y.y, a3 = y.z, a4 = y.w; break;
+  }
+  return make_uint4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh),
+                    __funnelshift_r(a3, a4, sh));
+}
+
+// One warp per request.  Forward: out[k] = src[k].  Reverse complement: out[k] = comp(src[count-1-k])
+// (SequenceUtils.cpp:41-61).  The bulk moves as aligned 128-bit stores — lane l writes 16 output bytes per step, read
+// from the (generally misaligned) source with two aligned 128-bit loads; in reverse the 16 bytes are byte-reversed and
+// complemented four at a time in registers.  The few bytes before the first / after the last aligned output vector
+// go one per lane.  src_sel(i) picks the source text of request i (0 / 1 = unitigs / reads for the store; always 0
+// for caller text).
 template <class SrcSel, class RevSel>
 __global__ void __launch_bounds__(256)
     slice_copy_kernel(SrcSel src_sel, RevSel rev_sel, const Window *__restrict__ win,
                       const uint64_t *__restrict__ out_off, uint64_t n, uint64_t cap, char *__restrict__ out,
                       uint8_t *__restrict__ status) {
-  uint64_t w  = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  uint64_t       w  = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  const unsigned l  = lane_id();
   for (; w < n; w += nw) {
-    Window   q = win[w];
-    uint64_t o = out_off[w];
+    const Window   q = win[w];
+    const uint64_t o = out_off[w];
     if (q.count == 0) continue;
     if (o + q.count > cap) {
-      if (lane_id() == 0) status[w] = 2;
+      if (l == 0) status[w] = 2;
       continue;
     }
-    const char *src = src_sel(w) + q.src;
-    if (!rev_sel(w)) {
-      for (uint64_t k = lane_id(); k < q.count; k += 32) out[o + k] = src[k];
+    const char    *src = src_sel(w) + q.src;
+    char          *dst = out + o;
+    const bool     rev = rev_sel(w);
+    uint64_t       head = (16u - unsigned(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u; // bytes before the first aligned vector
+    if (head > q.count) head = q.count;
+    const uint64_t nvec = (q.count - head) >> 4, tail0 = head + (nvec << 4);
+    if (!rev) {
+      if (l < head) dst[l] = src[l];
+      for (uint64_t v = l; v < nvec; v += 32)
+        *reinterpret_cast<uint4 *>(dst + head + (v << 4)) = load16_unaligned(src + head + (v << 4));
+      if (tail0 + l < q.count) dst[tail0 + l] = src[tail0 + l];
     } else {
-      for (uint64_t k = lane_id(); k < q.count; k += 32) out[o + k] = complement(src[q.count - 1 - k]);
+      const char *end = src + q.count; // out[k] = comp(end[-1 - k])
+      if (l < head) dst[l] = complement(end[-1 - int64_t(l)]);
+      for (uint64_t v = l; v < nvec; v += 32) {
+        const uint4 t = load16_unaligned(end - head - ((v + 1) << 4));
+        uint4       r;
+        r.x = complement4(__byte_perm(t.w, 0u, 0x0123u));
+        r.y = complement4(__byte_perm(t.z, 0u, 0x0123u));
+        r.z = complement4(__byte_perm(t.y, 0u, 0x0123u));
+        r.w = complement4(__byte_perm(t.x, 0u, 0x0123u));
+        *reinterpret_cast<uint4 *>(dst + head + (v << 4)) = r;
+      }
+      if (tail0 + l < q.count) dst[tail0 + l] = complement(end[-1 - int64_t(tail0 + l)]);
     }
   }
 }

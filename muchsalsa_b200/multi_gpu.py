@@ -26,12 +26,17 @@ HEADER_WORDS = 8  # msgpu_shard_header = 8 x uint64
 
 
 def split_paf(paf: bytes, n: int) -> list[bytes]:
-    """n contiguous chunks of about equal size, cut after a newline.  Concatenated they are the input again."""
+    """n contiguous chunks of about equal size, cut after a newline.  Concatenated they are the input again.
+
+    The LAST chunk always holds the last line of the file (earlier chunks may be empty for tiny inputs): the rank that
+    ingests it with is_last_shard=1 is the one that drops that line, as BlastFileReader::read() does
+    (BlastFileReader.cpp:76) — a last line parsed by an earlier rank would be a line the reference never sees."""
+    last_line = paf.rfind(b"\n", 0, max(len(paf) - 1, 0)) + 1  # where the last line starts
     cuts = [0]
     for r in range(1, n):
         want = max(cuts[-1], len(paf) * r // n)
         nl = paf.find(b"\n", want)
-        cuts.append(len(paf) if nl < 0 else nl + 1)
+        cuts.append(min(len(paf) if nl < 0 else nl + 1, last_line))
     cuts.append(len(paf))
     return [paf[cuts[i]:cuts[i + 1]] for i in range(n)]
 

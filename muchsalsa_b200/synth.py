@@ -19,7 +19,8 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-__all__ = ["SynthConfig", "CONFIGS", "generate_columns", "columns_to_paf", "generate_paf", "generate_sequences"]
+__all__ = ["SynthConfig", "CONFIGS", "generate_columns", "columns_to_paf", "generate_paf", "generate_sequences",
+           "rank_chunk", "scaled"]
 
 
 @dataclass(frozen=True)
@@ -198,6 +199,16 @@ def scaled(cfg: SynthConfig | str, factor: int) -> SynthConfig:
     if isinstance(cfg, str):
         cfg = CONFIGS[cfg]
     return cfg if factor == 1 else dataclasses.replace(cfg, name=f"{cfg.name}x{factor}", genome=cfg.genome * factor)
+
+
+def rank_chunk(workload: str, rank: int, world: int) -> bytes:
+    """Chunk `rank` of the `world`-rank weak-scaling workload: the genome is `world` times longer and rank r holds the
+    unitigs of the r-th contiguous genome slice; only the last chunk carries the sentinel line.  The chunks
+    concatenated in rank order are ONE PAF (the one whose digest tests/golden/sum_digests.json records); for
+    world == 1 this is generate_paf(workload)."""
+    if world == 1:
+        return generate_paf(workload)
+    return columns_to_paf(generate_columns(scaled(workload, world), (rank, world), sentinel=(rank == world - 1)))
 
 
 _COMP = np.arange(256, dtype=np.uint8)

@@ -190,6 +190,45 @@ def tables_digest(t: Tables) -> str:
     return h.hexdigest()
 
 
+def _mix64(x: np.ndarray) -> np.ndarray:
+    """splitmix64's finaliser on uint64 arrays (wrap-around arithmetic) — the mix of include/msgpu.h, msgpu_digest."""
+    x = x.astype(np.uint64, copy=True)
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xbf58476d1ce4e5b9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94d049bb133111eb)
+        x ^= x >> np.uint64(31)
+    return x
+
+
+def tables_sum_digest(t: Tables) -> dict:
+    """The order-independent digest of include/msgpu.h (msgpu_digest), restated in numpy on the checker's tables:
+    what msgpu_result_digest must return for the same construction, and what the digests of the slices of a multi-GPU
+    build (or the chunks of a chunked one) must add up to mod 2^64."""
+    u64 = np.uint64
+    E = int(t.edge_first.size)
+    b = t.edge_em_begin.astype(np.int64)
+    n_per = np.diff(b)
+    first = np.repeat(t.edge_first.astype(u64), n_per)
+    second = np.repeat(t.edge_second.astype(u64), n_per)
+    em = t.em
+    flags = (em["dir"].astype(u64) & u64(1)) | ((em["prim"].astype(u64) & u64(1)) << u64(1))
+    with np.errstate(over="ignore"):
+        h = _mix64(flags + u64(0x9e3779b97f4a7c15))
+        h = _mix64(h ^ np.ascontiguousarray(em["score"], np.float64).view(u64))
+        h = _mix64(h ^ ((em["ov1"].astype(np.int64).astype(u64) & u64(0xffffffff)) << u64(32)
+                        | (em["line"].astype(u64) & u64(0xffffffff))))
+        h = _mix64(h ^ (em["unitig"].astype(u64) << u64(32) | (em["ov0"].astype(np.int64).astype(u64) & u64(0xffffffff))))
+        h = _mix64(h ^ (first << u64(32) | second))
+        em_sum = int(h.sum(dtype=u64)) if h.size else 0
+        key = t.edge_first.astype(u64) << u64(32) | t.edge_second.astype(u64)
+        he = _mix64(_mix64(n_per.astype(u64) + u64(0xd1b54a32d192ed03)) ^ key)
+        edge_sum = int(he.sum(dtype=u64)) if E else 0
+    return dict(n_edges=E, n_edge_matches=int(b[-1]) if b.size else 0, edge_sum=edge_sum, em_sum=em_sum,
+                first_key=int(key[0]) if E else (1 << 64) - 1, last_key=int(key[-1]) if E else 0, violations=0)
+
+
 class _Checker:
     so_path = ""
     prefix = ""

@@ -26,6 +26,7 @@
 #include <string_view>
 #include <tuple>
 #include <unordered_map>
+#include <thread>
 #include <vector>
 
 #include "BlastFileAccessor.h"
@@ -766,6 +767,36 @@ int64_t msref_seq_fetch(msref_seq *h, int which, uint32_t id, int l, int r, int 
   }
 }
 
+// The reference's own fetch loop, timed: request i = (which, id, left, right, direction) as five int32; `threads`
+// std::threads split the batch the way main()'s pool threads call get*Sequence concurrently (src/main.cpp:645-653;
+// the accessor serialises them on one mutex per file, SequenceAccessor.cpp:56,131-137).  Returns the bases fetched.
+uint64_t msref_seq_bench(msref_seq *h, const int32_t *reqs, uint64_t n, int threads, double *seconds) {
+  if (threads < 1) threads = 1;
+  std::vector<uint64_t>    bases(size_t(threads), 0);
+  std::vector<std::thread> pool;
+  auto                     t0 = clk::now();
+  for (int t = 0; t < threads; ++t) {
+    pool.emplace_back([&, t] {
+      uint64_t b = 0;
+      for (uint64_t i = uint64_t(t); i < n; i += uint64_t(threads)) {
+        const int32_t *q = reqs + 5 * i;
+        try {
+          auto s = q[0] ? muchsalsa::getNanoporeSequence(*h->acc, uint32_t(q[1]), q[2], q[3], muchsalsa::Toggle(q[4] != 0))
+                        : muchsalsa::getIlluminaSequence(*h->acc, uint32_t(q[1]), q[2], q[3], muchsalsa::Toggle(q[4] != 0));
+          b += s.size();
+        } catch (std::exception const &) {
+        }
+      }
+      bases[size_t(t)] = b;
+    });
+  }
+  for (auto &th : pool) th.join();
+  *seconds = secs(t0, clk::now());
+  uint64_t total = 0;
+  for (auto b : bases) total += b;
+  return total;
+}
+
 } // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -778,6 +809,23 @@ int main(int argc, char **argv) {
   if (argc < 3) {
     std::fprintf(stderr, "usage: %s <paf> <threads>\n", argv[0]);
     return 2;
+  }
+  if (argc >= 6 && std::string(argv[1]) == "seq") { // `msref_cli seq <unitigs.fa> <nanopore.fx> <requests.bin> <threads>`
+    msref_seq *h = msref_seq_open(argv[3], argv[2], nullptr, nullptr);
+    if (!h) return 3;
+    std::FILE *f = std::fopen(argv[4], "rb");
+    if (!f) return 4;
+    std::vector<int32_t> reqs;
+    int32_t              buf[5 * 1024];
+    size_t               got;
+    while ((got = std::fread(buf, sizeof(int32_t) * 5, 1024, f)) > 0) reqs.insert(reqs.end(), buf, buf + 5 * got);
+    std::fclose(f);
+    double   t     = 0;
+    uint64_t bases = msref_seq_bench(h, reqs.data(), reqs.size() / 5, std::atoi(argv[5]), &t);
+    std::printf("{\"threads\": %d, \"requests\": %llu, \"bases\": %llu, \"seconds\": %.6f}\n", std::atoi(argv[5]),
+                (unsigned long long)(reqs.size() / 5), (unsigned long long)bases, t);
+    msref_seq_close(h);
+    return 0;
   }
   if (argc >= 4 && std::string(argv[3]) == "chain") { // `msref_cli <paf> 1 chain`: time the stages after construction
     ms_filters f;
