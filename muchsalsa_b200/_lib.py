@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmsgpu.so")
+# MSGPU_LIB: development only — another build of the same library (A/B of compile-time constants on the GPU box)
+LIB_PATH = os.environ.get("MSGPU_LIB") or os.path.join(HERE, "libmsgpu.so")
 
 u8p, u32p, i32p, u64p, f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_int32, C.c_uint64, C.c_double))
 

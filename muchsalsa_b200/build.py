@@ -84,5 +84,28 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(tag: str, extra_flags: list[str]) -> str:
+    """Development only: a second copy of the library compiled with extra nvcc flags (-D...), as libmsgpu_<tag>.so —
+    selected on the GPU box with MSGPU_LIB=... for A/B measurements of compile-time constants."""
+    out = os.path.join(HERE, f"libmsgpu_{tag}.so")
+    objdir = os.path.join(HERE, f".obj_{tag}")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in _sources():
+        obj = os.path.join(objdir, os.path.basename(src).replace(".cu", ".o"))
+        procs.append((obj, subprocess.Popen([_nvcc(), *NVCC_FLAGS, *extra_flags, "-c", src, "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for obj, p in procs:
+        out_text, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(out_text)
+    subprocess.run([_nvcc(), "-shared", "-o", out, *[o for o, _ in procs], "-cudart", "static"], check=True)
+    return out
+
+
 if __name__ == "__main__":
-    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

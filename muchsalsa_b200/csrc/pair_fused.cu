@@ -58,6 +58,10 @@ constexpr uint32_t kHalfCap    = kTileCap / 2;
 constexpr uint32_t kSrcRatio   = kHalfCap / (kSrcCap / 2); // a source weighs at least this much when tiles are packed
 constexpr int      kItems      = kTileCap / kFusedBlock;   // sort items per thread
 constexpr int      kMergeCtas  = kIdxBits <= 12 ? 4 : 2;    // resident CTAs of the merge kernel per SM (narrow words)
+#ifndef MSGPU_FUSED_CTAS
+#define MSGPU_FUSED_CTAS 3
+#endif
+constexpr int      kFusedCtas  = MSGPU_FUSED_CTAS;          // ... of the fused kernel (its emission phase needs registers)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // pre-pass 1: order every group by read id, build the pair rows, and accumulate per read its number of sources and
@@ -502,21 +506,25 @@ struct MergeShared { // everything but the two word buffers, which follow it in 
   uint32_t   scan[33];
   uint32_t   warp_tot[kFusedWarps];
   uint32_t   smin, smax, max_row_src;
+  // the fused kernel: ticket of the current tile, look-back scratch, the tile's exclusive output offsets
+  uint32_t           cur_tile, lb_inc[kFusedWarps];
+  unsigned long long lb_sum[kFusedWarps], em_excl, edge_excl;
 };
 constexpr uint16_t kDropped           = 0x8000u;
 constexpr size_t   kMergeOff          = (sizeof(MergeShared) + 15) & ~size_t(15);
 constexpr size_t   kMergeBytesWide    = kMergeOff + 2 * kTileCap * sizeof(unsigned long long);
 constexpr size_t   kMergeBytesNarrow  = kMergeOff + 2 * kTileCap * sizeof(uint32_t);
 
+// materialise the candidates in generation order (source by source = unitig order inside a row); returns this
+// thread's number of candidates that pass the overlap test
 template <class W>
-__device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W *wa, W *wb, uint32_t st_idx,
-                                           uint32_t n_src, uint32_t n_ent) {
+__device__ __forceinline__ uint32_t enumerate_candidates(const TileArgs &a, MergeShared &s, W *wa, uint32_t n_src,
+                                                         uint32_t n_ent) {
   const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
   const uint32_t smin  = s.smin;
   const uint32_t per   = (n_ent + kFusedBlock - 1) / kFusedBlock;
   const uint32_t wbase = w * per * 32; // warp w owns slots / positions [wbase, wbase + per * 32)
-
-  // ---- materialise the candidates in generation order (source by source = unitig order inside a row)
+  uint32_t       kept  = 0;
   if (wbase < n_ent) {
     uint32_t j = 0, hi = n_src; // last source with base <= wbase (empty slices share their base with the next one)
     while (hi - j > 1) {
@@ -534,12 +542,19 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
         const bool     keep = o0 <= o1 && o1 - o0 > kThOverlapF; // MatchMap.cpp:192
         wa[e]               = (W(sr - smin) << kIdxBits) | W(e);
         s.ent_src[e]        = uint16_t(j) | (keep ? uint16_t(0) : kDropped);
+        kept += keep ? 1u : 0u;
       }
     }
   }
-  __syncthreads();
+  return kept;
+}
 
-  // ---- merge levels
+// the merge levels; returns the buffer that holds the sorted words (the other one is free afterwards).  Starts and
+// ends with a barrier.
+template <class W> __device__ __forceinline__ W *merge_levels(MergeShared &s, W *wa, W *wb, uint32_t n_ent) {
+  const unsigned t   = threadIdx.x;
+  const uint32_t per = (n_ent + kFusedBlock - 1) / kFusedBlock;
+  __syncthreads();
   W *in = wa, *out = wb;
   const uint32_t max_row = s.max_row_src;
   for (uint32_t lvl = 0; (1u << lvl) < max_row; ++lvl) {
@@ -584,7 +599,17 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
     in     = out;
     out    = tmp;
   }
-  const W *sorted = in;
+  return in;
+}
+
+template <class W>
+__device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W *wa, W *wb, uint32_t st_idx,
+                                           uint32_t n_src, uint32_t n_ent) {
+  const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
+  const uint32_t per   = (n_ent + kFusedBlock - 1) / kFusedBlock;
+  const uint32_t wbase = w * per * 32; // warp w owns slots / positions [wbase, wbase + per * 32)
+  enumerate_candidates<W>(a, s, wa, n_src, n_ent);
+  const W *sorted = merge_levels<W>(s, wa, wb, n_ent);
 
   // ---- run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the key
   // of its pair) but is skipped; the head of a run is its first surviving candidate.
@@ -756,6 +781,339 @@ __global__ void __launch_bounds__(kFusedBlock, kMergeCtas) pair_tiles_merge_kern
   }
 }
 
+__device__ __forceinline__ PairRow ld_row(const PairRow *p) { // two 128-bit read-only loads = one 32-byte sector
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4        x = __ldg(q), y = __ldg(q + 1);
+  PairRow      r;
+  r.ir0    = int32_t(x.x);
+  r.ir1    = int32_t(x.y);
+  r.read   = x.z;
+  r.score  = int32_t(x.w);
+  r.line   = y.x;
+  r.flags  = y.y;
+  r.unitig = y.z;
+  r.orig   = y.w;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K6 + K7 in ONE kernel: enumerate, sort in shared memory, and write the edge matches and edges at their final
+// positions — no intermediate records, no separate emission kernel.
+//
+// What a tile needs from the tiles before it are two running sums: surviving candidates (where its edge matches start)
+// and run heads (where its edges start).  Both travel through decoupled look-back chains, one status word per tile and
+// chain (value << 2 | state; 1 = the tile's own count, 2 = inclusive prefix).  Tiles are taken in ticket order, so
+// every predecessor of a running tile is running or done.  What makes the look-backs (almost) free is WHEN they
+// happen:
+//   * a tile knows its surviving-candidate count right after the enumeration and publishes it then; it needs the
+//     prefix only after its sort — by then every predecessor has long published (they started earlier);
+//   * its head count exists only after the sort; it is published then, but the prefix is not needed before the edge
+//     matches have been written (the gathers, the f64 score, six column stores: a third of a tile's life) — again the
+//     predecessors, which started earlier, have passed their own sorts by then.
+// (The first one-kernel version of round 1 looked back for both sums right after the sort and lost 27 % of its stall
+//  samples waiting for ~300 in-flight predecessors to finish sorting.)
+// The whole block looks back at once (512 predecessors per round trip), so a chain normally costs one L2 round trip.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FusedArgs {
+  TileArgs            t;
+  unsigned int       *ticket;            // zero before the launch
+  unsigned long long *st_em, *st_edge;   // status words of the launch's tiles, zero before the launch
+  unsigned long long  em_value_base;     // added to the em_begin VALUES (rows of earlier chunks of the same slice)
+  unsigned long long *totals;            // [0] edge matches, [1] edges of this launch (written by the last tile)
+  EdgeTables          out;               // indexed from the launch's first edge match / edge
+};
+
+// exclusive prefix of `tile` over the chain `st` (all threads of the block call it; two barriers per round)
+__device__ __forceinline__ unsigned long long block_lookback(volatile unsigned long long *st, uint32_t tile, MergeShared &s) {
+  const unsigned     t = threadIdx.x, l = t & 31, w = t >> 5;
+  unsigned long long prefix = 0;
+  long long          hi     = (long long)tile - 1;
+  while (true) {
+    const long long    p    = hi - (long long)t;
+    unsigned long long word = 2ull; // before the first tile: an inclusive prefix of zero
+    if (p >= 0) {
+      word = st[p];
+      while ((word & 3ull) == 0ull) word = st[p];
+    }
+    const unsigned im   = __ballot_sync(0xffffffffu, (word & 3ull) == 2ull);
+    const unsigned stop = im ? unsigned(__ffs(im) - 1) : 32u; // nearest predecessor of this warp's window with a prefix
+    unsigned long long x = l <= stop ? (word >> 2) : 0ull;
+    x                    = warp_reduce_sum(x);
+    if (l == 0) {
+      s.lb_sum[w] = x;
+      s.lb_inc[w] = im != 0u;
+    }
+    __syncthreads();
+    bool done = false;
+#pragma unroll
+    for (int ww = 0; ww < kFusedWarps; ++ww) {
+      if (!done) prefix += s.lb_sum[ww];
+      done = done || s.lb_inc[ww] != 0u;
+    }
+    __syncthreads();
+    if (done) break;
+    hi -= kFusedBlock;
+  }
+  return prefix;
+}
+
+template <class W>
+__device__ __forceinline__ void fused_tail(const FusedArgs &fa, MergeShared &s, W *wa, W *wb, uint32_t st_idx,
+                                           uint32_t n_src, uint32_t n_ent, uint32_t q0, bool last_tile) {
+  const TileArgs &a = fa.t;
+  const unsigned  t = threadIdx.x, w = t >> 5, l = t & 31;
+  const uint32_t  per   = (n_ent + kFusedBlock - 1) / kFusedBlock;
+  const uint32_t  wbase = w * per * 32;
+  volatile unsigned long long *st_em = fa.st_em, *st_edge = fa.st_edge;
+
+  // ---- enumerate; the tile's surviving-candidate count is known (and published) before the sort
+  uint32_t kept = enumerate_candidates<W>(a, s, wa, n_src, n_ent);
+  kept          = warp_reduce_sum(kept);
+  if (l == 0) s.warp_tot[w] = kept;
+  __syncthreads();
+  uint32_t n_valid = 0;
+#pragma unroll
+  for (int ww = 0; ww < kFusedWarps; ++ww) n_valid += s.warp_tot[ww];
+  if (t == 0) st_em[st_idx] = ((unsigned long long)n_valid << 2) | (st_idx ? 1ull : 2ull); // tile 0: already a prefix
+
+  const W *sorted = merge_levels<W>(s, wa, wb, n_ent); // (starts with the barrier that protects warp_tot)
+  W       *spare  = sorted == wa ? wb : wa;
+
+  // ---- run heads = edges of this tile (a candidate that failed the overlap test stays in its run but is skipped)
+  uint32_t vmask = 0, hmask = 0, n_v = 0, n_h = 0;
+#pragma unroll
+  for (int it = 0; it < kItems; ++it) {
+    if (uint32_t(it) < per) {
+      const uint32_t k = wbase + it * 32 + l;
+      bool           ok = false, head = false;
+      if (k < n_ent) {
+        const W x = sorted[k];
+        ok        = !(s.ent_src[uint32_t(x) & (kTileCap - 1)] & kDropped);
+        if (ok) {
+          head = true;
+          const W key = x >> kIdxBits;
+          if (k > 0 && (sorted[k - 1] >> kIdxBits) == key) {
+            const uint32_t row_start = s.src.base[s.src.row_first[s.ent_src[k] & (kSrcCap - 1)]];
+            for (uint32_t p = k; p > row_start;) {
+              --p;
+              const W y = sorted[p];
+              if ((y >> kIdxBits) != key) break;
+              if (!(s.ent_src[uint32_t(y) & (kTileCap - 1)] & kDropped)) {
+                head = false;
+                break;
+              }
+            }
+          }
+        }
+      }
+      vmask |= (ok ? 1u : 0u) << it;
+      hmask |= (head ? 1u : 0u) << it;
+      n_v += __popc(__ballot_sync(0xffffffffu, ok));
+      n_h += __popc(__ballot_sync(0xffffffffu, head));
+    }
+  }
+  if (l == 0) s.warp_tot[w] = n_v | (n_h << 16);
+  // the sources' remaining fields (score, line, unitig, read, flags) go where the sort no longer needs the space
+  uint4    *ex    = reinterpret_cast<uint4 *>(spare);
+  uint32_t *ex_fl = reinterpret_cast<uint32_t *>(ex + kSrcCap);
+  if (t < n_src) {
+    const PairRow row = ld_row(a.rows + a.rd_src[q0 + t]);
+    ex[t]             = make_uint4(uint32_t(row.score), row.line, row.unitig, row.read);
+    ex_fl[t]          = row.flags;
+  }
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int ww = 0; ww < kFusedWarps; ++ww) {
+    const uint32_t c = s.warp_tot[ww];
+    before += ww < int(w) ? c : 0u;
+    total += c;
+  }
+  const uint32_t n_heads = total >> 16;
+  if (t == 0) st_edge[st_idx] = ((unsigned long long)n_heads << 2) | (st_idx ? 1ull : 2ull);
+
+  // ---- where this tile's edge matches start: every predecessor published its count before ITS sort
+  const unsigned long long em_excl = st_idx ? block_lookback(st_em, st_idx, s) : 0ull;
+  if (t == 0 && st_idx) st_em[st_idx] = ((em_excl + n_valid) << 2) | 2ull;
+
+  // ---- the edge matches, at their final positions
+  const unsigned lt = (1u << l) - 1u;
+  const uint32_t smin = s.smin;
+  {
+    uint32_t pv = before & 0xffffu;
+#pragma unroll 1
+    for (uint32_t it = 0; it < per; ++it) {
+      {
+        const bool     ok = (vmask >> it) & 1u;
+        const unsigned bv = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const uint32_t e  = uint32_t(sorted[wbase + it * 32 + l]) & (kTileCap - 1);
+          const uint32_t j  = s.ent_src[e] & (kSrcCap - 1);
+          const PairRow  pb = ld_row(a.rows + (s.src.begin[j] + (e - s.src.base[j])));
+          const uint4    sx = ex[j];
+          const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = pb.ir0, b1 = pb.ir1;
+          const int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
+          // MatchMap.cpp:195-202: score_x * common / len_x for the outer and the inner match, summed (IEEE addition
+          // commutes, so which of the two is "outer" does not change the sum); no FMA contraction
+          const double common = double(ov1 - ov0 + 1);
+          const double sa     = double((unsigned long long)(long long)int32_t(sx.x)); // size_t widened from int
+          const double sbb    = double((unsigned long long)(long long)pb.score);
+          const double sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
+          const double sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
+          const uint32_t fa_  = ex_fl[j];
+          const unsigned long long o = em_excl + pv + __popc(bv & lt);
+          fa.out.em_unitig[o] = sx.z;
+          fa.out.em_ov0[o]    = ov0;
+          fa.out.em_ov1[o]    = ov1;
+          fa.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
+          fa.out.em_line[o]   = sx.y > pb.line ? sx.y : pb.line; // outer = the later line (MatchMap.cpp:218)
+          fa.out.em_flags[o]  = uint8_t((((fa_ ^ pb.flags) & 1u) ? 0u : 1u) | ((fa_ & pb.flags & 2u) ? 2u : 0u));
+        }
+        pv += __popc(bv);
+      }
+    }
+  }
+
+  // ---- where its edges start: the predecessors, which started earlier, are past their sorts by now
+  const unsigned long long edge_excl = st_idx ? block_lookback(st_edge, st_idx, s) : 0ull;
+  if (t == 0 && st_idx) st_edge[st_idx] = ((edge_excl + n_heads) << 2) | 2ull;
+  {
+    uint32_t pv = before & 0xffffu, ph = before >> 16;
+#pragma unroll 1
+    for (uint32_t it = 0; it < per; ++it) {
+      {
+        const bool     ok = (vmask >> it) & 1u, head = (hmask >> it) & 1u;
+        const unsigned bv = __ballot_sync(0xffffffffu, ok), bh = __ballot_sync(0xffffffffu, head);
+        if (head) {
+          const W        x  = sorted[wbase + it * 32 + l];
+          const uint32_t j  = s.ent_src[uint32_t(x) & (kTileCap - 1)] & (kSrcCap - 1);
+          const unsigned long long eo = edge_excl + ph + __popc(bh & lt);
+          fa.out.first[eo]    = ex[j].w;
+          fa.out.second[eo]   = uint32_t(x >> kIdxBits) + smin;
+          fa.out.em_begin[eo] = fa.em_value_base + em_excl + pv + __popc(bv & lt);
+        }
+        pv += __popc(bv);
+        ph += __popc(bh);
+      }
+    }
+  }
+  if (last_tile && t == 0) { // closes the CSR and reports the totals of the launch
+    fa.totals[0]                            = em_excl + n_valid;
+    fa.totals[1]                            = edge_excl + n_heads;
+    fa.out.em_begin[edge_excl + n_heads]    = fa.em_value_base + em_excl + n_valid;
+  }
+}
+
+// kWide = false: every sort word of the launch fits 32 bits (read ids below 2^20), the 64-bit path is not compiled in
+template <bool kWide>
+__global__ void __launch_bounds__(kFusedBlock, kWide ? (kFusedCtas > 2 ? 2 : kFusedCtas) : kFusedCtas)
+    pair_tiles_fused_kernel(FusedArgs fa) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MergeShared    &s = *reinterpret_cast<MergeShared *>(smem_raw);
+  const TileArgs &a = fa.t;
+  const unsigned  t = threadIdx.x, l = t & 31;
+  const uint32_t  n_tiles = a.tile_hi - a.tile_lo;
+
+  while (true) {
+    __syncthreads(); // previous tile fully done with shared memory
+    if (t == 0) {
+      s.cur_tile    = atomicAdd(fa.ticket, 1u); // ticket order = start order: predecessors are running or done
+      s.smin        = 0xffffffffu;
+      s.smax        = 0;
+      s.max_row_src = 0;
+    }
+    __syncthreads();
+    const uint32_t st_idx = s.cur_tile;
+    if (st_idx >= n_tiles) break;
+    const uint32_t tile = a.tile_lo + st_idx;
+    const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
+    const uint32_t q0 = a.rd_off[r0];
+    uint32_t       n_src = (kind ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
+    if (n_src > kSrcCap) { // cannot happen (see the planning kernels); the tile still has to publish its (zero) counts
+      if (t == 0) *a.error = 1;
+      n_src = 0;
+    }
+    { // ---- stage the sources (kSrcCap <= blockDim.x: one per thread)
+      const uint32_t j = t;
+      uint32_t       len = 0, lmin = 0xffffffffu, lmax = 0, row_src = 0;
+      if (j < n_src) {
+        const uint32_t q   = a.rd_src[q0 + j];
+        const PairRow  row = a.rows[q];
+        uint32_t       b, e;
+        if (kind) {
+          const uint32_t *sl = a.slices + a.slice_off[r0] + uint64_t(kind - 1) * n_src;
+          b                  = sl[j];
+          e                  = sl[n_src + j];
+          s.src.row_first[j] = 0;
+          s.src.row_end[j]   = uint16_t(n_src);
+          row_src            = n_src;
+        } else {
+          b                  = q + 1;
+          e                  = a.grp_off[row.unitig + 1];
+          const uint32_t f   = a.rd_off[row.read] - q0, g = a.rd_off[row.read + 1] - q0;
+          s.src.row_first[j] = uint16_t(f);
+          s.src.row_end[j]   = uint16_t(g);
+          row_src            = g - f;
+        }
+        len            = e - b;
+        s.src.begin[j] = b;
+        s.src.ir0[j]   = row.ir0;
+        s.src.ir1[j]   = row.ir1;
+        if (len) { // the slice is sorted by read id
+          lmin = a.p_read[b];
+          lmax = a.p_read[e - 1];
+        }
+      }
+      uint32_t tot, ex = block_exclusive_scan<uint32_t>(len, s.scan, &tot);
+      if (j < n_src) s.src.base[j] = ex;
+      if (t == 0) s.src.base[n_src] = tot;
+      for (int d = 16; d > 0; d >>= 1) {
+        uint32_t omin = __shfl_xor_sync(0xffffffffu, lmin, d), omax = __shfl_xor_sync(0xffffffffu, lmax, d);
+        uint32_t orow = __shfl_xor_sync(0xffffffffu, row_src, d);
+        lmin    = omin < lmin ? omin : lmin;
+        lmax    = omax > lmax ? omax : lmax;
+        row_src = orow > row_src ? orow : row_src;
+      }
+      if (l == 0) {
+        if (lmin <= lmax) {
+          atomicMin(&s.smin, lmin);
+          atomicMax(&s.smax, lmax);
+        }
+        atomicMax(&s.max_row_src, row_src);
+      }
+    }
+    __syncthreads();
+    uint32_t n_ent = s.src.base[n_src];
+    __syncthreads(); // (everybody has read base[n_src] before an error path may overwrite it)
+    if (n_ent > kTileCap) { // cannot happen; publish zero counts and go on
+      if (t == 0) {
+        *a.error      = 2;
+        s.src.base[0] = 0;
+      }
+      n_src = 0;
+      n_ent = 0;
+      __syncthreads();
+    }
+    const bool     last  = st_idx + 1 == n_tiles;
+    const uint32_t range = (n_ent && s.smax > s.smin) ? s.smax - s.smin : 0u;
+    unsigned char *words = smem_raw + kMergeOff;
+    if (range < (1u << (32 - kIdxBits)) - 1u || !kWide) {
+      if (!(range < (1u << (32 - kIdxBits)) - 1u)) { // cannot happen: the host sizes the launch from the id width
+        if (t == 0) *a.error = 3;
+        n_src = 0;
+        n_ent = 0;
+      }
+      uint32_t *wa = reinterpret_cast<uint32_t *>(words);
+      fused_tail<uint32_t>(fa, s, wa, wa + kTileCap, st_idx, n_src, n_ent, q0, last);
+    } else if (kWide) {
+      unsigned long long *wa = reinterpret_cast<unsigned long long *>(words);
+      fused_tail<unsigned long long>(fa, s, wa, wa + kTileCap, st_idx, n_src, n_ent, q0, last);
+    }
+  }
+}
+template __global__ void pair_tiles_fused_kernel<false>(FusedArgs);
+template __global__ void pair_tiles_fused_kernel<true>(FusedArgs);
+
 // ---------------------------------------------------------------------------------------------------------------------
 // K7b: tile counts -> global offsets of every tile's first edge match and first edge (two single-pass scans)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -780,20 +1138,6 @@ struct EmitArgs {
   EdgeTables      out;
 };
 
-__device__ __forceinline__ PairRow ld_row(const PairRow *p) { // two 128-bit read-only loads = one 32-byte sector
-  const uint4 *q = reinterpret_cast<const uint4 *>(p);
-  uint4        x = __ldg(q), y = __ldg(q + 1);
-  PairRow      r;
-  r.ir0    = int32_t(x.x);
-  r.ir1    = int32_t(x.y);
-  r.read   = x.z;
-  r.score  = int32_t(x.w);
-  r.line   = y.x;
-  r.flags  = y.y;
-  r.unitig = y.z;
-  r.orig   = y.w;
-  return r;
-}
 
 constexpr int kEmitBlock = 256;
 constexpr int kEmitBatch = 4; // records in flight per thread: the partner gathers are latency-bound, so overlap them
@@ -867,6 +1211,110 @@ __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs 
           a.out.em_begin[eo] = o;
         }
       }
+    }
+  }
+}
+
+// One edge match from its record: the partner's row and the tile's staged source row -> the six column values
+struct EmRow {
+  uint32_t unitig, line, second;
+  int32_t  ov0, ov1;
+  double   score;
+  uint8_t  flags;
+};
+__device__ __forceinline__ EmRow make_em_row(const uint4 lo, const uint4 hi, const PairRow &pb) {
+  EmRow     r;
+  const int a0 = int32_t(lo.x), a1 = int32_t(lo.y), b0 = pb.ir0, b1 = pb.ir1;
+  r.ov0 = a0 > b0 ? a0 : b0;
+  r.ov1 = a1 < b1 ? a1 : b1;
+  // MatchMap.cpp:195-202 (see pair_emit_rows_kernel): no FMA contraction, the sum commutes
+  const double common = double(r.ov1 - r.ov0 + 1);
+  const double sa     = double((unsigned long long)(long long)int32_t(lo.w));
+  const double sbb    = double((unsigned long long)(long long)pb.score);
+  const double sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
+  const double sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
+  r.score  = __dadd_rn(sc_a, sc_b);
+  r.unitig = hi.z;
+  r.line   = hi.x > pb.line ? hi.x : pb.line; // outer = the later line (MatchMap.cpp:218)
+  r.flags  = uint8_t((((hi.y ^ pb.flags) & 1u) ? 0u : 1u) | ((hi.y & pb.flags & 2u) ? 2u : 0u));
+  r.second = pb.read;
+  return r;
+}
+
+// The same emission with 128-bit column stores: a thread owns FOUR consecutive output rows whose global position is
+// a multiple of four, so every 32-bit column takes one aligned 16-byte store per thread (512 contiguous bytes per
+// warp), the score column two, the flag column one 4-byte store — 7 store instructions for what the scalar kernel
+// does in 24.  The rows before the first / after the last aligned quad of a tile (< 4 each) go one per thread.
+__global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_vec_kernel(EmitArgs a) {
+  __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
+  const unsigned   t = threadIdx.x;
+  if (blockIdx.x == 0 && t == 0) a.out.em_begin[a.totals[1]] = a.totals[0]; // closes the CSR
+  for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
+    const uint32_t           tile    = a.tile_lo + ti;
+    const uint32_t           n_valid = a.tile_cnt[ti].x;
+    const unsigned long long em0 = a.em_base[ti], ed0 = a.edge_base[ti];
+    const uint32_t           r0 = a.tile_row[tile], q0 = a.rd_off[r0];
+    const uint32_t n_src = (a.tile_kind[tile] ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
+    const uint2   *rec   = a.records + uint64_t(ti) * kTileCap;
+    __syncthreads(); // previous tile done with the staged sources
+    if (n_valid)
+      for (uint32_t j = t; j < n_src && j < kSrcCap; j += kEmitBlock) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
+        src_lo[j]      = __ldg(q);
+        src_hi[j]      = __ldg(q + 1);
+      }
+    __syncthreads();
+    uint32_t lead = (4u - uint32_t(em0 & 3ull)) & 3u; // rows before the first aligned quad
+    if (lead > n_valid) lead = n_valid;
+    const uint32_t n_quads = (n_valid - lead) >> 2, tail0 = lead + (n_quads << 2);
+    auto edge_of = [&](uint2 rc, const EmRow &r, unsigned long long o) {
+      if (rc.y & (1u << kSrcBits)) {
+        const unsigned long long eo = ed0 + (rc.y >> (kSrcBits + 1));
+        a.out.first[eo]    = src_lo[rc.y & (kSrcCap - 1)].z;
+        a.out.second[eo]   = r.second;
+        a.out.em_begin[eo] = o;
+      }
+    };
+    for (uint32_t q = t; q < n_quads; q += kEmitBlock) {
+      const uint32_t k = lead + (q << 2);
+      uint2          rc[4];
+      PairRow        pb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rc[u] = __ldg(rec + k + u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pb[u] = ld_row(a.rows + rc[u].x);
+      EmRow r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t j = rc[u].y & (kSrcCap - 1);
+        r[u]             = make_em_row(src_lo[j], src_hi[j], pb[u]);
+      }
+      const unsigned long long o = em0 + k; // a multiple of 4
+      *reinterpret_cast<uint4 *>(a.out.em_unitig + o) = make_uint4(r[0].unitig, r[1].unitig, r[2].unitig, r[3].unitig);
+      *reinterpret_cast<int4 *>(a.out.em_ov0 + o)     = make_int4(r[0].ov0, r[1].ov0, r[2].ov0, r[3].ov0);
+      *reinterpret_cast<int4 *>(a.out.em_ov1 + o)     = make_int4(r[0].ov1, r[1].ov1, r[2].ov1, r[3].ov1);
+      *reinterpret_cast<double2 *>(a.out.em_score + o)     = make_double2(r[0].score, r[1].score);
+      *reinterpret_cast<double2 *>(a.out.em_score + o + 2) = make_double2(r[2].score, r[3].score);
+      *reinterpret_cast<uint4 *>(a.out.em_line + o)   = make_uint4(r[0].line, r[1].line, r[2].line, r[3].line);
+      *reinterpret_cast<uchar4 *>(a.out.em_flags + o) = make_uchar4(r[0].flags, r[1].flags, r[2].flags, r[3].flags);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) edge_of(rc[u], r[u], o + u);
+    }
+    // the (< 4 + < 4) rows around the aligned quads
+    const uint32_t n_rest = lead + (n_valid - tail0);
+    if (t < n_rest) {
+      const uint32_t k  = t < lead ? t : tail0 + (t - lead);
+      const uint2    rc = __ldg(rec + k);
+      const uint32_t j  = rc.y & (kSrcCap - 1);
+      const EmRow    r  = make_em_row(src_lo[j], src_hi[j], ld_row(a.rows + rc.x));
+      const unsigned long long o = em0 + k;
+      a.out.em_unitig[o] = r.unitig;
+      a.out.em_ov0[o]    = r.ov0;
+      a.out.em_ov1[o]    = r.ov1;
+      a.out.em_score[o]  = r.score;
+      a.out.em_line[o]   = r.line;
+      a.out.em_flags[o]  = r.flags;
+      edge_of(rc, r, o);
     }
   }
 }
@@ -964,10 +1412,14 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   e.second    = arena.alloc<uint32_t>(cap);
   e.em_begin  = arena.alloc<uint64_t>(cap + 1);
 
-  uint2              *records  = arena.alloc<uint2>(uint64_t(my_tiles) * kTileCap);
-  uint2              *tile_cnt = arena.alloc<uint2>(uint64_t(my_tiles) + 1);
-  unsigned long long *em_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
-  unsigned long long *ed_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
+  // The product is the two-kernel form (tile kernel -> compact records -> two scans -> emission kernel).
+  // MSGPU_VARIANT=fused selects the ONE-kernel form (enumerate, sort, write the tables; offsets by two look-back
+  // chains): bit-identical tables, measured slower at yeast scale (1.56 ms vs 0.75 + 0.50 ms; 21 % of its stall samples
+  // sit behind the look-back for the edge offsets — a tile waits for the slowest sort among ~440 tiles in flight —
+  // and its emission phase runs at 40 registers / 3 CTAs per SM): profiles/r2_ncu_pair_tiles_fused_onekernel_yeast.txt.
+  // Kept as the A/B the design decision rests on.
+  const char *variant = std::getenv("MSGPU_VARIANT");
+  const bool  split   = !(variant && std::string(variant) == "fused");
 
   TileArgs a;
   a.rows      = rows;
@@ -983,26 +1435,53 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   a.slices    = slices;
   a.tile_lo   = tile_lo;
   a.tile_hi   = tile_hi;
-  a.records   = records;
-  a.tile_cnt  = tile_cnt;
+  a.records   = nullptr;
+  a.tile_cnt  = nullptr;
   a.error     = d_u32 + 3;
+  // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits; otherwise
+  // tiles choose per tile and the launch carries the 64-bit buffers
+  a.wide = R > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)
   if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st)); // planning done; what follows is "merge" time
-  if (my_tiles) {
+  if (!my_tiles) {
+    MSGPU_CUDA(cudaMemsetAsync(e.em_begin, 0, sizeof(uint64_t), st)); // an empty CSR: em_begin[0] = 0
+  } else if (!split) {
+    unsigned long long *status = arena.alloc<unsigned long long>(2 * uint64_t(my_tiles));
+    MSGPU_CUDA(cudaMemsetAsync(status, 0, 2 * uint64_t(my_tiles) * sizeof(unsigned long long), st));
+    FusedArgs fa;
+    fa.t             = a;
+    fa.ticket        = d_u32 + 6; // (zeroed with the block above)
+    fa.st_em         = status;
+    fa.st_edge       = status + my_tiles;
+    fa.em_value_base = 0;
+    fa.totals        = totals;
+    fa.out           = e;
     // the opt-in is an attribute of the function ON THE CURRENT DEVICE: set it before every launch (a context per
     // GPU in one process is supported, and the call costs less than a microsecond)
+    if (a.wide) {
+      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
+      int grid = kNumSMs * (kFusedCtas > 2 ? 2 : kFusedCtas);
+      if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
+      MSGPU_LAUNCH("pair_tiles_fused", st, pair_tiles_fused_kernel<true><<<grid, kFusedBlock, kMergeBytesWide, st>>>(fa));
+    } else {
+      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesNarrow)));
+      int grid = kNumSMs * kFusedCtas; // persistent: one CTA per resident slot, tiles by ticket
+      if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
+      MSGPU_LAUNCH("pair_tiles_fused", st, pair_tiles_fused_kernel<false><<<grid, kFusedBlock, kMergeBytesNarrow, st>>>(fa));
+    }
+  } else {
+    uint2              *records  = arena.alloc<uint2>(uint64_t(my_tiles) * kTileCap);
+    uint2              *tile_cnt = arena.alloc<uint2>(uint64_t(my_tiles) + 1);
+    unsigned long long *em_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
+    unsigned long long *ed_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
+    a.records  = records;
+    a.tile_cnt = tile_cnt;
     MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
-    // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits; otherwise
-    // tiles choose per tile and the launch carries the 64-bit buffers
-    a.wide = R > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)
     // 32 registers, 51 KB (narrow): four resident CTAs per SM; a few waves of them, tiles strided over the grid
     int grid = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * 4;
     if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
     MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
-  }
-  run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{tile_cnt}, my_tiles, em_base, totals + 0),
-            scan_job<unsigned long long>(arena, st, 1, TileHeads{tile_cnt}, my_tiles, ed_base, totals + 1));
-  if (!my_tiles) MSGPU_CUDA(cudaMemsetAsync(e.em_begin, 0, sizeof(uint64_t), st)); // an empty CSR: em_begin[0] = 0
-  if (my_tiles) {
+    run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{tile_cnt}, my_tiles, em_base, totals + 0),
+              scan_job<unsigned long long>(arena, st, 1, TileHeads{tile_cnt}, my_tiles, ed_base, totals + 1));
     EmitArgs ea;
     ea.rows      = rows;
     ea.rd_off    = rd_off;
@@ -1017,9 +1496,14 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
     ea.edge_base = ed_base;
     ea.totals    = totals;
     ea.out       = e;
-    int grid = kNumSMs * 8;
+    grid         = kNumSMs * 8;
     if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
-    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
+    // 128-bit column stores need the output columns 16-byte aligned (arena allocations are 256-byte aligned)
+    const char *emit = std::getenv("MSGPU_EMIT");
+    if (emit && std::string(emit) == "scalar")
+      MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
+    else
+      MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_vec_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
   }
   MSGPU_CUDA(cudaMemcpyAsync(h_words, zero + z_u32, z_end - z_u32, cudaMemcpyDeviceToHost, st));
   const uint32_t           *h_flags = reinterpret_cast<const uint32_t *>(h_words);

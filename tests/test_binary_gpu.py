@@ -1,0 +1,85 @@
+"""The REAL `muchsalsa` executable with the GPU path wired in (oracle/make_binary.py applies INTEGRATION.md §2 to a
+scratch copy of the reference's main.cpp and links the reference's own objects + the host shim + libmsgpu.so), run
+end to end on config 1 with the argv pipeline.sh passes (pipeline.sh:179).
+
+What "identical output" can mean here: the reference binary is NOT deterministic even with one worker thread —
+ThreadPool(1) runs a main-queue and a sub-queue thread (ThreadPool.cpp:84-89), assembly indices come from an atomic
+counter and three jobs share pointer-keyed containers — so two runs of the unmodified CPU path on the same input give
+different bytes.  Measured in the build container (6 runs, ASLR off): the record ORDER and the numbering in the names
+differ every time, and the CONTENT (the multiset of sequences of temp_1.target.fa / temp_1.query.fa, the rows of
+temp_1.align.paf without the two name columns) takes one of two values.  The test therefore compares content: the
+GPU path's output must be one of the outcomes the CPU path produces (tests/golden/binary_small.json holds the ones
+recorded in the build container; the CPU runs of the test session are added to the set).
+The binary is built in the build container (it needs /root/reference) and travels to the GPU box in oracle/_ref/."""
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+import util
+from muchsalsa_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "_ref", "muchsalsa")
+
+
+def _inputs(tmp_path, workload):
+    (tmp_path / "in.paf").write_bytes(synth.generate_paf(workload))
+    ufa, nfa = synth.generate_sequences(workload)
+    (tmp_path / "unitigs.fa").write_bytes(ufa)
+    (tmp_path / "nanopore.fa").write_bytes(nfa)
+
+
+def _fasta_content(b: bytes):
+    return sorted(rec.partition(b"\n")[2].replace(b"\n", b"") for rec in b.split(b">")[1:])
+
+
+def canonical(out_dir) -> dict:
+    """Order- and numbering-independent content of the three output files."""
+    h = lambda rows: hashlib.sha256(b"|".join(rows)).hexdigest()
+    paf = []
+    for line in (out_dir / "temp_1.align.paf").read_bytes().split(b"\n"):
+        if line:
+            c = line.split(b"\t")
+            paf.append(b"\t".join(c[1:5] + c[6:]))  # without the query / target names (they carry the numbering)
+    return {"target": h(_fasta_content((out_dir / "temp_1.target.fa").read_bytes())),
+            "query": h(_fasta_content((out_dir / "temp_1.query.fa").read_bytes())), "paf": h(sorted(paf)),
+            "target_bytes": len((out_dir / "temp_1.target.fa").read_bytes())}
+
+
+def _run(tmp_path, tag, env_extra):
+    out = tmp_path / f"out_{tag}"
+    out.mkdir()
+    env = {k: v for k, v in os.environ.items() if k not in ("MUCHSALSA_GPU", "MUCHSALSA_GPU_STAGES")}
+    env.update(env_extra)
+    p = subprocess.run([EXE, str(tmp_path / "in.paf"), str(tmp_path / "unitigs.fa"), str(tmp_path / "nanopore.fa"),
+                        str(out), "1"], capture_output=True, text=True, env=env, timeout=1200)
+    assert p.returncode == 0 and "Finished assembly" in p.stdout and "Exception" not in p.stderr, (p.stdout, p.stderr)
+    return canonical(out)
+
+
+def _key(c):
+    return (c["target"], c["query"], c["paf"])
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/muchsalsa not built (needs /root/reference)")
+def test_cpu_path_of_the_binary_gives_a_recorded_outcome(tmp_path):
+    """Not a GPU test: without MUCHSALSA_GPU the binary is the reference, statement for statement."""
+    _inputs(tmp_path, "small")
+    known = {tuple(v) for v in util.load_golden("binary_small.json")["outcomes"]}
+    assert _key(_run(tmp_path, "cpu", {})) in known
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stages", [False, True])
+def test_binary_output_with_the_gpu_path_is_an_outcome_of_the_cpu_path(tmp_path, stages):
+    assert os.path.exists(EXE), "oracle/_ref/muchsalsa missing: run python oracle/make_binary.py in the build container"
+    _inputs(tmp_path, "small")
+    known = {tuple(v) for v in util.load_golden("binary_small.json")["outcomes"]}
+    known |= {_key(_run(tmp_path, f"cpu{i}", {})) for i in range(3)}
+    env = {"MUCHSALSA_GPU": "0", **({"MUCHSALSA_GPU_STAGES": "1"} if stages else {})}
+    for i in range(3):
+        got = _run(tmp_path, f"gpu{i}", env)
+        assert got["target_bytes"] > 1_000_000  # 20 contigs, 1.39 Mbp of a 1.5 Mbp genome
+        assert _key(got) in known, f"run {i}: content differs from every outcome of the reference's own path"

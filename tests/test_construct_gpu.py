@@ -127,6 +127,18 @@ def test_sort_based_variant_agrees_with_fused(builder, monkeypatch):
     assert tables_equal(fused, srt) == []
 
 
+def test_one_kernel_variant_agrees_with_the_two_kernel_product(builder, monkeypatch):
+    """MSGPU_VARIANT=fused writes the tables from ONE kernel (offsets through two decoupled look-back chains) instead
+    of tile kernel -> records -> scans -> emission kernel.  Same tables, bit for bit — also on rows larger than a
+    tile, whose sub-tiles chain through the look-back.  (Measured slower; kept as the A/B)"""
+    for paf in (synth.generate_paf("ecoli"), util.heavy_rows_paf()):
+        two = util.gpu_to_tables(builder.build_from_buffer(paf).result())
+        monkeypatch.setenv("MSGPU_VARIANT", "fused")
+        one = util.gpu_to_tables(builder.build_from_buffer(paf).result())
+        monkeypatch.delenv("MSGPU_VARIANT")
+        assert tables_equal(one, two) == []
+
+
 def test_hash_collision_restarts_interning(builder, oracle, monkeypatch):
     """Names are interned through 64-bit hashes that every line verifies against its slot's representative; a
     collision restarts the interning with another seed.  The test hook makes the first attempt collide everywhere."""
