@@ -189,6 +189,42 @@ typedef struct msgpu_digest {
 } msgpu_digest;
 int msgpu_result_digest(msgpu_ctx *ctx, msgpu_digest *out);
 
+/* ---- chunked construction: the edge tables produced piece by piece -------------------------------------------------
+ * For results larger than HBM (config 5: 10^11 edge matches do not fit eight GPUs) and for consumers that stream.
+ * The reference materialises everything in two hash maps (Graph::m_adjacencyList, MatchMap::m_edgeMatches); nothing
+ * there corresponds to this, it is what lets the same tables exist at sizes the reference cannot reach.
+ *
+ * msgpu_set_chunk_tiles(ctx, n)   n > 0: the builds that follow stop after planning the pairing; the edge / edge-match
+ *                      tables are then produced by msgpu_chunk_next, `n` pairing tiles (<= 4096 candidate pairs each)
+ *                      at a time, in (first, second) order, into two alternating sets of device buffers.  0 (default):
+ *                      the whole result is materialised by the build.
+ * msgpu_chunk_next     the next chunk.  Its pointers stay valid until the NEXT call of msgpu_chunk_next (the chunk after
+ *                      it is already being computed into the other buffer set while the caller works on this one;
+ *                      work the caller queues on the context's stream is ordered before that buffer is reused).  MSGPU_ERR_NO_RESULT when every chunk has
+ *                      been delivered.  edge_em_begin holds n_edges + 1 values that continue the slice: [0] == em_base;
+ *                      the edge-match columns are indexed from the chunk's own first row (value - em_base).
+ *                      msgpu_result_counts reports the rows delivered so far.
+ * msgpu_chunk_digest   msgpu_digest of the chunk last delivered; the chunks' sums add up to the digest of the whole.
+ * msgpu_result_host    with chunking on and no chunk taken yet, it drains the chunks itself and downloads each one on a
+ *                      second stream while the next is computed: the same host tables as without chunking, with the
+ *                      copy overlapping the pairing.  chain / filter stages need the resident form. */
+typedef struct msgpu_chunk {
+  uint64_t        index;
+  uint64_t        n_edges, n_edge_matches; /* rows of this chunk */
+  uint64_t        edge_base, em_base;      /* rows of the slice before this chunk */
+  int             last;                    /* non-zero: no chunk follows */
+  const uint32_t *edge_first, *edge_second;
+  const uint64_t *edge_em_begin;
+  const uint32_t *em_unitig;
+  const int32_t  *em_ov0, *em_ov1;
+  const double   *em_score;
+  const uint32_t *em_line;
+  const uint8_t  *em_flags;
+} msgpu_chunk;
+int msgpu_set_chunk_tiles(msgpu_ctx *ctx, uint32_t tiles_per_chunk);
+int msgpu_chunk_next(msgpu_ctx *ctx, msgpu_chunk *out);
+int msgpu_chunk_digest(msgpu_ctx *ctx, msgpu_digest *out);
+
 /* ---- chaining + overlaps: the stage that consumes the construction (optional; the tables stay in HBM for it) --------
  * msgpu_chain_overlaps  replaces, for every edge of the last build, the job chainingAndOverlaps (src/main.cpp:170-178,
  *                       328-414) = getMaxPairwisePaths (mpp.cpp:145-305, checkCompatibility mpp.cpp:38-142) +

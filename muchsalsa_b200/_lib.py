@@ -36,6 +36,13 @@ class Digest(C.Structure):
                 ("n_edges", "n_edge_matches", "edge_sum", "em_sum", "first_key", "last_key", "violations")]
 
 
+class Chunk(C.Structure):
+    _fields_ = [("index", C.c_uint64), ("n_edges", C.c_uint64), ("n_edge_matches", C.c_uint64),
+                ("edge_base", C.c_uint64), ("em_base", C.c_uint64), ("last", C.c_int),
+                ("edge_first", u32p), ("edge_second", u32p), ("edge_em_begin", u64p), ("em_unitig", u32p),
+                ("em_ov0", i32p), ("em_ov1", i32p), ("em_score", f64p), ("em_line", u32p), ("em_flags", u8p)]
+
+
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "ingest_ms", "pair_ms", "merge_ms", "d2h_ms", "total_ms")]
 
@@ -91,6 +98,9 @@ SIGNATURES = {
     "msgpu_result_counts": (C.c_int, [C.c_void_p, C.POINTER(Counts)]),
     "msgpu_result_device": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),
     "msgpu_result_host": (C.c_int, [C.c_void_p, C.POINTER(Tables)]),
+    "msgpu_set_chunk_tiles": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "msgpu_chunk_next": (C.c_int, [C.c_void_p, C.POINTER(Chunk)]),
+    "msgpu_chunk_digest": (C.c_int, [C.c_void_p, C.POINTER(Digest)]),
     "msgpu_result_digest": (C.c_int, [C.c_void_p, C.POINTER(Digest)]),
     "msgpu_chain_overlaps": (C.c_int, [C.c_void_p, C.c_uint64]),
     "msgpu_orders_device": (C.c_int, [C.c_void_p, C.POINTER(Orders)]),

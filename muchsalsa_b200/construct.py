@@ -205,6 +205,27 @@ class GraphBuilder:
             matches=m, edge_first=_np(t.edge_first, E, np.uint32), edge_second=_np(t.edge_second, E, np.uint32),
             edge_em_begin=_np(t.edge_em_begin, E + 1, np.uint64), edge_matches=em, timings=self.timings())
 
+    # ---- chunked construction (results larger than HBM; downloads overlapped with the pairing)
+    def set_chunk_tiles(self, tiles_per_chunk: int):
+        """> 0: the builds that follow stop after planning; chunk_next() / host_tables() produce the edge tables
+        piece by piece.  0: resident (default)."""
+        self._check(self._lib.msgpu_set_chunk_tiles(self._h, int(tiles_per_chunk)))
+        return self
+
+    def chunk_next(self):
+        """The next chunk (a _lib.Chunk with device pointers), or None when every chunk has been delivered."""
+        c = _lib.Chunk()
+        rc = self._lib.msgpu_chunk_next(self._h, C.byref(c))
+        if rc == 7:
+            return None
+        self._check(rc)
+        return c
+
+    def chunk_digest(self) -> dict:
+        d = _lib.Digest()
+        self._check(self._lib.msgpu_chunk_digest(self._h, C.byref(d)))
+        return {k: int(getattr(d, k)) for k, _ in d._fields_}
+
     def digest(self) -> dict:
         """Order-independent checksum + invariant violations of the edge tables, computed on the device
         (msgpu_result_digest); the digests of slices / chunks add up mod 2^64."""

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) digest_kernel(EdgeTables e, DigestAcc *ac
   unsigned long long es = 0, ms = 0, bad = 0;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < e.n_edges; i += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t f = e.first[i], s = e.second[i];
-    const uint64_t b0 = e.em_begin[i], b1 = e.em_begin[i + 1];
+    const uint64_t b0 = e.em_begin[i] - e.em_value_base, b1 = e.em_begin[i + 1] - e.em_value_base; // column indices
     if (!(f < s)) ++bad;                                  // Edge::getVertices(): first = the smaller line index = id
     if (!(b1 > b0) || b1 > e.n_em) ++bad;                 // an edge exists iff it has >= 1 edge match
     if (i > 0) {                                          // strictly increasing (first, second): every pair once

@@ -81,6 +81,31 @@ struct EdgeTables {
   // the pairing's index of the matches (grouped by unitig, by read inside): what the chaining stage looks matches up in
   const PairRow  *pair_rows = nullptr;
   const uint32_t *p_read    = nullptr;
+  // chunked emission: the em_begin VALUES of a chunk continue the slice (first = rows of the earlier chunks), while
+  // the columns are indexed from the chunk's own first row
+  uint64_t em_value_base = 0;
+};
+
+// What the planning of a pairing leaves behind (all pointers into the build arena): the matches ordered for pairing,
+// the per-read source lists and the tile table.  Tiles [tile_lo, tile_hi) are this device's share.
+struct PairPlan {
+  bool            valid = false;
+  const PairRow  *rows = nullptr;
+  const uint32_t *p_read = nullptr;
+  const int32_t  *p_ir0 = nullptr, *p_ir1 = nullptr;
+  const uint32_t *grp_off = nullptr, *rd_off = nullptr, *rd_src = nullptr, *tile_row = nullptr, *tile_kind = nullptr;
+  const uint64_t *slice_off = nullptr;
+  const uint32_t *slices = nullptr;
+  uint32_t       *flags = nullptr; // device: [2] a read with too many sources, [3] tile invariant violated
+  uint64_t        n_reads = 0, n_pairs = 0;
+  uint32_t        n_tiles = 0, tile_lo = 0, tile_hi = 0;
+};
+
+// scratch of one emission (a range of tiles): compact records, per-tile counts and offsets, totals
+struct PairScratch {
+  uint32_t            max_tiles = 0;
+  uint2              *records = nullptr, *tile_cnt = nullptr;
+  unsigned long long *em_base = nullptr, *ed_base = nullptr, *status = nullptr, *totals = nullptr;
 };
 
 struct BuildError {
@@ -106,7 +131,19 @@ void run_pairing_sorted(Arena &arena, cudaStream_t st, const MatchSoA &matches, 
 // tables written once in final order (pair_emit_rows).  `part` of `n_parts`: this device handles that contiguous share
 // of the tiles, and its tables are that slice of the global result (multi-GPU); 0 of 1 = everything.
 void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs,
-                       uint64_t n_reads, EdgeTables &edges, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts);
+                       uint64_t n_reads, EdgeTables &edges, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts,
+                       PairPlan *plan_out);
+// the same in pieces, for chunked emission (msgpu_chunk_next): plan once, then emit ranges of tiles
+void     pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs, uint64_t n_reads,
+                      uint32_t part, uint32_t n_parts, PairPlan &plan);
+void     pairing_scratch_alloc(Arena &arena, uint32_t max_tiles, PairScratch &sc);
+uint64_t pairing_rows_bound(const PairPlan &plan, uint32_t n_tiles);
+void     pairing_outputs_alloc(Arena &arena, uint64_t cap, EdgeTables &e);
+void     pairing_tiles(Arena &arena, cudaStream_t st, const PairPlan &plan, uint32_t t_lo, uint32_t t_hi, PairScratch &sc);
+void     pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &plan, uint32_t t_lo, uint32_t t_hi, PairScratch &sc,
+                      EdgeTables &e, uint64_t em_value_base);
+void     pairing_finish(Arena &arena, cudaStream_t st, const PairPlan &plan, const PairScratch &sc, uint64_t *n_em,
+                        uint64_t *n_edges);
 
 // picks the variant: fused unless MSGPU_VARIANT=sorted (kept as an independent cross-check of the fused kernel)
 void run_pairing(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs, uint64_t n_reads,

@@ -76,6 +76,26 @@ struct msgpu_ctx {
   bool                     filters_host_valid = false;
   msgpu_edge_filter_tables host_filters_view{};
 
+  // chunked emission (msgpu_set_chunk_tiles / msgpu_chunk_next)
+  struct Chunks {
+    bool        active = false; // the last build stopped after planning; chunks are being delivered
+    PairPlan    plan;
+    PairScratch sc[2];
+    EdgeTables  out[2];
+    uint32_t    next_tile = 0;         // first tile whose "tiles" half has not been launched
+    int         cur = -1;              // buffer set whose tiles half is in flight and rows half is not (-1: none left)
+    uint32_t    cur_lo = 0, cur_hi = 0;
+    uint64_t    index = 0, em_base = 0, edge_base = 0;
+    bool        taken = false;         // a chunk has been delivered to the caller
+    EdgeTables  last;                  // the chunk last delivered (for msgpu_chunk_digest)
+    bool        have_last = false;
+    cudaEvent_t rows_done = nullptr;
+  } chunks;
+  uint32_t     chunk_tiles = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t  copy_done[2]{};
+  bool         copy_pending[2] = {false, false}; // a download of that buffer set is in flight on copy_stream
+
   SeqStore *seq = nullptr;
   Profiler  profiler;
 };
@@ -126,6 +146,92 @@ float elapsed(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
+// pairing of a build: whole (resident) or, with chunking on, planned only — the chunks follow through
+// msgpu_chunk_next / msgpu_result_host
+void pair_or_plan(msgpu_ctx *ctx, uint32_t part, uint32_t n_parts) {
+  cudaStream_t st = ctx->stream;
+  {
+    cudaEvent_t keep  = ctx->chunks.rows_done; // the event outlives the builds
+    ctx->chunks       = msgpu_ctx::Chunks{};
+    ctx->chunks.rows_done = keep;
+  }
+  if (!ctx->chunk_tiles) {
+    pair_or_plan(ctx, part, n_parts);
+    return;
+  }
+  auto &c = ctx->chunks;
+  pairing_plan(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, part, n_parts, c.plan);
+  ctx->edges           = EdgeTables{};
+  ctx->edges.n_pairs   = c.plan.n_pairs;
+  ctx->edges.pair_rows = c.plan.rows;
+  ctx->edges.p_read    = c.plan.p_read;
+  const uint32_t my_tiles = c.plan.tile_hi - c.plan.tile_lo;
+  const uint32_t per      = ctx->chunk_tiles < my_tiles ? ctx->chunk_tiles : (my_tiles ? my_tiles : 1u);
+  const uint64_t cap      = pairing_rows_bound(c.plan, per);
+  for (int b = 0; b < 2; ++b) {
+    pairing_scratch_alloc(ctx->arena, per, c.sc[b]);
+    pairing_outputs_alloc(ctx->arena, cap, c.out[b]);
+  }
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[3], st));
+  c.active    = true;
+  c.next_tile = c.plan.tile_lo;
+  // the tiles half of the first chunk starts right away
+  c.cur_lo = c.next_tile;
+  c.cur_hi = c.cur_lo + per < c.plan.tile_hi ? c.cur_lo + per : c.plan.tile_hi;
+  pairing_tiles(ctx->arena, st, c.plan, c.cur_lo, c.cur_hi, c.sc[0]);
+  c.next_tile = c.cur_hi;
+  c.cur       = 0;
+}
+
+// delivers the next chunk into `e` (device tables of the chunk); false when there is none left
+bool next_chunk(msgpu_ctx *ctx, EdgeTables &e, uint64_t *index, bool *last) {
+  auto &c = ctx->chunks;
+  if (!c.active || c.cur < 0) return false;
+  cudaStream_t st = ctx->stream;
+  if (!ctx->chunks.rows_done) MSGPU_CUDA(cudaEventCreateWithFlags(&ctx->chunks.rows_done, cudaEventDisableTiming));
+  const int      b  = c.cur;
+  const uint32_t lo = c.cur_lo, hi = c.cur_hi;
+  if (ctx->copy_pending[b]) { // msgpu_result_host is still downloading the chunk that used this buffer set
+    MSGPU_CUDA(cudaStreamWaitEvent(st, ctx->copy_done[b], 0));
+    ctx->copy_pending[b] = false;
+  }
+  pairing_rows(ctx->arena, st, c.plan, lo, hi, c.sc[b], c.out[b], c.em_base);
+  // the counts of this chunk travel to pinned memory behind its rows; the tiles half of the NEXT chunk is queued
+  // before the host waits, so the GPU keeps sorting while the caller works on this chunk
+  char *h = static_cast<char *>(ctx->arena.host_scratch());
+  MSGPU_CUDA(cudaMemcpyAsync(h, c.plan.flags, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaMemcpyAsync(h + 64, c.sc[b].totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaEventRecord(c.rows_done, st));
+  if (c.next_tile < c.plan.tile_hi) {
+    const uint32_t per = c.sc[1 - b].max_tiles;
+    c.cur_lo           = c.next_tile;
+    c.cur_hi           = c.cur_lo + per < c.plan.tile_hi ? c.cur_lo + per : c.plan.tile_hi;
+    pairing_tiles(ctx->arena, st, c.plan, c.cur_lo, c.cur_hi, c.sc[1 - b]);
+    c.next_tile = c.cur_hi;
+    c.cur       = 1 - b;
+  } else {
+    c.cur = -1;
+  }
+  MSGPU_CUDA(cudaEventSynchronize(c.rows_done));
+  const uint32_t           *h_flags = reinterpret_cast<const uint32_t *>(h);
+  const unsigned long long *h_tot   = reinterpret_cast<const unsigned long long *>(h + 64);
+  if (h_flags[2]) throw BuildError{MSGPU_ERR_LIMIT, "a read matches more than 512 unitigs with partners"};
+  if (h_flags[3]) throw BuildError{MSGPU_ERR_INTERNAL, "pairing: tile invariant violated (code " + std::to_string(h_flags[3]) + ")"};
+  e         = c.out[b];
+  e.n_em    = h_tot[0];
+  e.n_edges = h_tot[1];
+  e.n_pairs = c.plan.n_pairs;
+  *index    = c.index++;
+  *last     = c.cur < 0;
+  c.em_base += e.n_em;
+  c.edge_base += e.n_edges;
+  ctx->edges.n_em    = c.em_base; // rows delivered so far (msgpu_result_counts)
+  ctx->edges.n_edges = c.edge_base;
+  c.last      = e;
+  c.have_last = true;
+  return true;
+}
+
 // device part of a build: PAF text in HBM -> all tables in HBM.  pair = false: ingest only (one shard of a
 // multi-GPU build); the edge tables stay empty.
 void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes, bool pair = true, bool drop_last_line = true) {
@@ -141,8 +247,9 @@ void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes, bool pair =
   run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches, drop_last_line);
   MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
   if (pair) {
-    run_pairing(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3]);
+    pair_or_plan(ctx, 0, 1);
   } else {
+    ctx->chunks.active  = false;
     ctx->edges          = EdgeTables{};
     ctx->edges.em_begin = ctx->arena.alloc<uint64_t>(1);
     MSGPU_CUDA(cudaMemsetAsync(ctx->edges.em_begin, 0, sizeof(uint64_t), st));
@@ -210,6 +317,10 @@ void msgpu_destroy(msgpu_ctx *ctx) {
   DeviceGuard g(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   seq_destroy(ctx->seq);
+  if (ctx->chunks.rows_done) cudaEventDestroy(ctx->chunks.rows_done);
+  for (auto &e : ctx->copy_done)
+    if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto &e : ctx->ev)
     if (e) cudaEventDestroy(e);
   ctx->arena.release();
@@ -295,7 +406,7 @@ int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t 
     MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
     build_group_offsets(ctx->arena, st, m, ctx->unitigs);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
-    run_pairing(ctx->arena, st, m, ctx->unitigs, n_reads, ctx->edges, ctx->ev[3]);
+    pair_or_plan(ctx, 0, 1);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
     MSGPU_CUDA(cudaStreamSynchronize(st));
     ctx->timings           = msgpu_timings{};
@@ -420,10 +531,15 @@ int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out) {
   }
   return guarded(ctx, [&] {
     cudaStream_t st = ctx->stream;
+    const bool   chunked = ctx->chunks.active;
+    if (chunked && ctx->chunks.taken)
+      throw BuildError{MSGPU_ERR_NO_RESULT, "chunks of this build were already taken with msgpu_chunk_next"};
     msgpu_tables d;
     msgpu_result_device(ctx, &d);
-    const uint64_t R = ctx->reads.n, U = ctx->unitigs.n, M = ctx->matches.n, E = ctx->edges.n_edges,
-                   EM = ctx->edges.n_em;
+    const uint64_t R = ctx->reads.n, U = ctx->unitigs.n, M = ctx->matches.n;
+    // chunked: the row counts are not known yet; lay the slab out for what the device's tiles can produce at most
+    const uint64_t cap_rows = chunked ? pairing_rows_bound(ctx->chunks.plan, ctx->chunks.plan.tile_hi - ctx->chunks.plan.tile_lo) : 0;
+    const uint64_t E = chunked ? cap_rows : ctx->edges.n_edges, EM = chunked ? cap_rows : ctx->edges.n_em;
     const bool have_names = ctx->reads.name_off != nullptr;
     // lay every table out in one pinned slab
     size_t off = 0;
@@ -458,6 +574,7 @@ int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out) {
     add(d.m_score, M, &h.m_score);
     add(d.m_line, M, &h.m_line);
     add(d.m_flags, M, &h.m_flags);
+    const size_t n_small = copies.size(); // what follows are the edge / edge-match columns
     add(d.edge_first, E, &h.edge_first);
     add(d.edge_second, E, &h.edge_second);
     add(d.edge_em_begin, E + 1, &h.edge_em_begin);
@@ -468,17 +585,104 @@ int msgpu_result_host(msgpu_ctx *ctx, msgpu_tables *out) {
     add(d.em_line, EM, &h.em_line);
     add(d.em_flags, EM, &h.em_flags);
     char *slab = static_cast<char *>(ctx->host_result.get(off + 64));
-    MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
-    for (auto &c : copies) {
-      *c.dst = slab + c.at;
-      if (c.bytes) MSGPU_CUDA(cudaMemcpyAsync(slab + c.at, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
+    for (auto &c : copies) *c.dst = slab + c.at;
+    if (!chunked) {
+      MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
+      for (auto &c : copies)
+        if (c.bytes) MSGPU_CUDA(cudaMemcpyAsync(slab + c.at, c.src, c.bytes, cudaMemcpyDeviceToHost, st));
+      MSGPU_CUDA(cudaEventRecord(ctx->ev[5], st));
+      MSGPU_CUDA(cudaStreamSynchronize(st));
+      ctx->timings.d2h_ms = elapsed(ctx->ev[4], ctx->ev[5]);
+    } else {
+      // Chunks are downloaded on a second stream while the next ones are computed: the rows half of chunk c + 2
+      // waits (on the device) for the download of chunk c, which used the same buffer set.
+      if (!ctx->copy_stream) MSGPU_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (auto &e : ctx->copy_done)
+        if (!e) MSGPU_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      cudaStream_t cs = ctx->copy_stream;
+      MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st)); // everything queued so far (the plan, the read / match tables)
+      MSGPU_CUDA(cudaStreamWaitEvent(cs, ctx->ev[4], 0));
+      for (size_t i = 0; i < n_small; ++i)
+        if (copies[i].bytes)
+          MSGPU_CUDA(cudaMemcpyAsync(slab + copies[i].at, copies[i].src, copies[i].bytes, cudaMemcpyDeviceToHost, cs));
+      auto at = [](const void *hp) { return static_cast<char *>(const_cast<void *>(hp)); };
+      EdgeTables e;
+      uint64_t   index = 0;
+      bool       last  = false;
+      int        b     = ctx->chunks.cur; // buffer set of the chunk about to be delivered
+      uint64_t   eb = 0, mb = 0;
+      ctx->copy_pending[0] = ctx->copy_pending[1] = false;
+      while (next_chunk(ctx, e, &index, &last)) {
+        auto put = [&](char *dst, const void *src, size_t bytes) {
+          if (bytes) MSGPU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, cs));
+        };
+        put(at(h.edge_first) + eb * 4, e.first, e.n_edges * 4);
+        put(at(h.edge_second) + eb * 4, e.second, e.n_edges * 4);
+        put(at(h.edge_em_begin) + eb * 8, e.em_begin, (e.n_edges + 1) * 8);
+        put(at(h.em_unitig) + mb * 4, e.em_unitig, e.n_em * 4);
+        put(at(h.em_ov0) + mb * 4, e.em_ov0, e.n_em * 4);
+        put(at(h.em_ov1) + mb * 4, e.em_ov1, e.n_em * 4);
+        put(at(h.em_score) + mb * 8, e.em_score, e.n_em * 8);
+        put(at(h.em_line) + mb * 4, e.em_line, e.n_em * 4);
+        put(at(h.em_flags) + mb, e.em_flags, e.n_em);
+        MSGPU_CUDA(cudaEventRecord(ctx->copy_done[b], cs));
+        ctx->copy_pending[b] = true;
+        eb += e.n_edges;
+        mb += e.n_em;
+        b = ctx->chunks.cur;
+      }
+      MSGPU_CUDA(cudaStreamSynchronize(cs));
+      MSGPU_CUDA(cudaStreamSynchronize(st));
+      ctx->copy_pending[0] = ctx->copy_pending[1] = false;
+      ctx->chunks.taken = false; // (the chunks went to the host tables, not to the caller)
+      ctx->timings.d2h_ms = 0.f;
     }
-    MSGPU_CUDA(cudaEventRecord(ctx->ev[5], st));
-    MSGPU_CUDA(cudaStreamSynchronize(st));
-    ctx->timings.d2h_ms = elapsed(ctx->ev[4], ctx->ev[5]);
     ctx->timings.total_ms += ctx->timings.d2h_ms;
     ctx->host_valid = true;
     *out            = h;
+  });
+}
+
+int msgpu_set_chunk_tiles(msgpu_ctx *ctx, uint32_t tiles_per_chunk) {
+  if (!ctx) return MSGPU_ERR_INVALID_ARG;
+  ctx->chunk_tiles = tiles_per_chunk;
+  return MSGPU_OK;
+}
+
+int msgpu_chunk_next(msgpu_ctx *ctx, msgpu_chunk *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  return guarded(ctx, [&] {
+    if (!ctx->have_result || !ctx->chunks.active) throw BuildError{MSGPU_ERR_NO_RESULT, "no chunked build in progress"};
+    EdgeTables e;
+    uint64_t   index = 0;
+    bool       last  = false;
+    const uint64_t em_base = ctx->chunks.em_base, edge_base = ctx->chunks.edge_base;
+    if (!next_chunk(ctx, e, &index, &last)) throw BuildError{MSGPU_ERR_NO_RESULT, "every chunk has been delivered"};
+    ctx->chunks.taken = true;
+    std::memset(out, 0, sizeof(*out));
+    out->index          = index;
+    out->n_edges        = e.n_edges;
+    out->n_edge_matches = e.n_em;
+    out->edge_base      = edge_base;
+    out->em_base        = em_base;
+    out->last           = last ? 1 : 0;
+    out->edge_first     = e.first;
+    out->edge_second    = e.second;
+    out->edge_em_begin  = e.em_begin;
+    out->em_unitig      = e.em_unitig;
+    out->em_ov0         = e.em_ov0;
+    out->em_ov1         = e.em_ov1;
+    out->em_score       = e.em_score;
+    out->em_line        = e.em_line;
+    out->em_flags       = e.em_flags;
+  });
+}
+
+int msgpu_chunk_digest(msgpu_ctx *ctx, msgpu_digest *out) {
+  if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
+  return guarded(ctx, [&] {
+    if (!ctx->chunks.active || !ctx->chunks.have_last) throw BuildError{MSGPU_ERR_NO_RESULT, "no chunk delivered yet"};
+    run_digest(ctx->arena, ctx->stream, ctx->chunks.last, out);
   });
 }
 
@@ -486,6 +690,7 @@ int msgpu_result_digest(msgpu_ctx *ctx, msgpu_digest *out) {
   if (!ctx || !out) return MSGPU_ERR_INVALID_ARG;
   return guarded(ctx, [&] {
     if (!ctx->have_result) throw BuildError{MSGPU_ERR_NO_RESULT, "no construction to digest"};
+    if (ctx->chunks.active) throw BuildError{MSGPU_ERR_NO_RESULT, "chunked build: use msgpu_chunk_digest per chunk"};
     run_digest(ctx->arena, ctx->stream, ctx->edges, out);
   });
 }
@@ -493,6 +698,7 @@ int msgpu_result_digest(msgpu_ctx *ctx, msgpu_digest *out) {
 int msgpu_chain_overlaps(msgpu_ctx *ctx, uint64_t wiggle_room) {
   return guarded(ctx, [&] {
     if (!ctx->have_result) throw BuildError{MSGPU_ERR_NO_RESULT, "no construction to chain"};
+    if (ctx->chunks.active) throw BuildError{MSGPU_ERR_NO_RESULT, "the chaining stage needs the resident edge tables (chunking is on)"};
     ctx->orders             = OrderTables{};
     ctx->orders_host_valid  = false;
     ctx->filters            = FilterTables{};

@@ -1135,6 +1135,7 @@ struct EmitArgs {
   uint32_t        tile_lo, n_tiles;
   const uint2    *records, *tile_cnt;
   const unsigned long long *em_base, *edge_base, *totals; // totals: (edge matches, edges) of this launch
+  unsigned long long em_value_base; // added to the em_begin VALUES (rows of earlier chunks of the same slice)
   EdgeTables      out;
 };
 
@@ -1147,7 +1148,7 @@ constexpr int kEmitBatch = 4; // records in flight per thread: the partner gathe
 __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs a) {
   __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
   const unsigned   t = threadIdx.x;
-  if (blockIdx.x == 0 && t == 0) a.out.em_begin[a.totals[1]] = a.totals[0]; // closes the CSR
+  if (blockIdx.x == 0 && t == 0) a.out.em_begin[a.totals[1]] = a.em_value_base + a.totals[0]; // closes the CSR
   for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
     const uint32_t           tile    = a.tile_lo + ti;
     const uint32_t           n_valid = a.tile_cnt[ti].x;
@@ -1208,120 +1209,20 @@ __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs 
           const unsigned long long eo = ed0 + (cur[u].y >> (kSrcBits + 1));
           a.out.first[eo]    = lo.z;
           a.out.second[eo]   = pb[u].read;
-          a.out.em_begin[eo] = o;
+          a.out.em_begin[eo] = a.em_value_base + o;
         }
       }
     }
   }
 }
 
-// One edge match from its record: the partner's row and the tile's staged source row -> the six column values
-struct EmRow {
-  uint32_t unitig, line, second;
-  int32_t  ov0, ov1;
-  double   score;
-  uint8_t  flags;
-};
-__device__ __forceinline__ EmRow make_em_row(const uint4 lo, const uint4 hi, const PairRow &pb) {
-  EmRow     r;
-  const int a0 = int32_t(lo.x), a1 = int32_t(lo.y), b0 = pb.ir0, b1 = pb.ir1;
-  r.ov0 = a0 > b0 ? a0 : b0;
-  r.ov1 = a1 < b1 ? a1 : b1;
-  // MatchMap.cpp:195-202 (see pair_emit_rows_kernel): no FMA contraction, the sum commutes
-  const double common = double(r.ov1 - r.ov0 + 1);
-  const double sa     = double((unsigned long long)(long long)int32_t(lo.w));
-  const double sbb    = double((unsigned long long)(long long)pb.score);
-  const double sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
-  const double sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
-  r.score  = __dadd_rn(sc_a, sc_b);
-  r.unitig = hi.z;
-  r.line   = hi.x > pb.line ? hi.x : pb.line; // outer = the later line (MatchMap.cpp:218)
-  r.flags  = uint8_t((((hi.y ^ pb.flags) & 1u) ? 0u : 1u) | ((hi.y & pb.flags & 2u) ? 2u : 0u));
-  r.second = pb.read;
-  return r;
-}
-
-// The same emission with 128-bit column stores: a thread owns FOUR consecutive output rows whose global position is
-// a multiple of four, so every 32-bit column takes one aligned 16-byte store per thread (512 contiguous bytes per
-// warp), the score column two, the flag column one 4-byte store — 7 store instructions for what the scalar kernel
-// does in 24.  The rows before the first / after the last aligned quad of a tile (< 4 each) go one per thread.
-__global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_vec_kernel(EmitArgs a) {
-  __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
-  const unsigned   t = threadIdx.x;
-  if (blockIdx.x == 0 && t == 0) a.out.em_begin[a.totals[1]] = a.totals[0]; // closes the CSR
-  for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
-    const uint32_t           tile    = a.tile_lo + ti;
-    const uint32_t           n_valid = a.tile_cnt[ti].x;
-    const unsigned long long em0 = a.em_base[ti], ed0 = a.edge_base[ti];
-    const uint32_t           r0 = a.tile_row[tile], q0 = a.rd_off[r0];
-    const uint32_t n_src = (a.tile_kind[tile] ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
-    const uint2   *rec   = a.records + uint64_t(ti) * kTileCap;
-    __syncthreads(); // previous tile done with the staged sources
-    if (n_valid)
-      for (uint32_t j = t; j < n_src && j < kSrcCap; j += kEmitBlock) {
-        const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
-        src_lo[j]      = __ldg(q);
-        src_hi[j]      = __ldg(q + 1);
-      }
-    __syncthreads();
-    uint32_t lead = (4u - uint32_t(em0 & 3ull)) & 3u; // rows before the first aligned quad
-    if (lead > n_valid) lead = n_valid;
-    const uint32_t n_quads = (n_valid - lead) >> 2, tail0 = lead + (n_quads << 2);
-    auto edge_of = [&](uint2 rc, const EmRow &r, unsigned long long o) {
-      if (rc.y & (1u << kSrcBits)) {
-        const unsigned long long eo = ed0 + (rc.y >> (kSrcBits + 1));
-        a.out.first[eo]    = src_lo[rc.y & (kSrcCap - 1)].z;
-        a.out.second[eo]   = r.second;
-        a.out.em_begin[eo] = o;
-      }
-    };
-    for (uint32_t q = t; q < n_quads; q += kEmitBlock) {
-      const uint32_t k = lead + (q << 2);
-      uint2          rc[4];
-      PairRow        pb[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) rc[u] = __ldg(rec + k + u);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) pb[u] = ld_row(a.rows + rc[u].x);
-      EmRow r[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t j = rc[u].y & (kSrcCap - 1);
-        r[u]             = make_em_row(src_lo[j], src_hi[j], pb[u]);
-      }
-      const unsigned long long o = em0 + k; // a multiple of 4
-      *reinterpret_cast<uint4 *>(a.out.em_unitig + o) = make_uint4(r[0].unitig, r[1].unitig, r[2].unitig, r[3].unitig);
-      *reinterpret_cast<int4 *>(a.out.em_ov0 + o)     = make_int4(r[0].ov0, r[1].ov0, r[2].ov0, r[3].ov0);
-      *reinterpret_cast<int4 *>(a.out.em_ov1 + o)     = make_int4(r[0].ov1, r[1].ov1, r[2].ov1, r[3].ov1);
-      *reinterpret_cast<double2 *>(a.out.em_score + o)     = make_double2(r[0].score, r[1].score);
-      *reinterpret_cast<double2 *>(a.out.em_score + o + 2) = make_double2(r[2].score, r[3].score);
-      *reinterpret_cast<uint4 *>(a.out.em_line + o)   = make_uint4(r[0].line, r[1].line, r[2].line, r[3].line);
-      *reinterpret_cast<uchar4 *>(a.out.em_flags + o) = make_uchar4(r[0].flags, r[1].flags, r[2].flags, r[3].flags);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) edge_of(rc[u], r[u], o + u);
-    }
-    // the (< 4 + < 4) rows around the aligned quads
-    const uint32_t n_rest = lead + (n_valid - tail0);
-    if (t < n_rest) {
-      const uint32_t k  = t < lead ? t : tail0 + (t - lead);
-      const uint2    rc = __ldg(rec + k);
-      const uint32_t j  = rc.y & (kSrcCap - 1);
-      const EmRow    r  = make_em_row(src_lo[j], src_hi[j], ld_row(a.rows + rc.x));
-      const unsigned long long o = em0 + k;
-      a.out.em_unitig[o] = r.unitig;
-      a.out.em_ov0[o]    = r.ov0;
-      a.out.em_ov1[o]    = r.ov1;
-      a.out.em_score[o]  = r.score;
-      a.out.em_line[o]   = r.line;
-      a.out.em_flags[o]  = r.flags;
-      edge_of(rc, r, o);
-    }
-  }
-}
-
-void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
-                       EdgeTables &e, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts) {
-  e = EdgeTables{};
+// ---------------------------------------------------------------------------------------------------------------------
+// host side: planning (everything up to the tile table) and emission of a range of tiles, so that a result can be
+// produced whole (resident) or chunk by chunk (results larger than HBM, downloads overlapped with the pairing)
+// ---------------------------------------------------------------------------------------------------------------------
+void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
+                  uint32_t part, uint32_t n_parts, PairPlan &pl) {
+  pl = PairPlan{};
   const uint64_t M = m.n, R = n_reads;
   if (R >= 0xfffffff0ull || M >= 0xfffffff0ull)
     throw BuildError{MSGPU_ERR_LIMIT, "pairing supports < 2^32 reads and matches per device"};
@@ -1331,10 +1232,10 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   uint32_t *p_read = arena.alloc<uint32_t>(M);
   int32_t  *p_ir0 = arena.alloc<int32_t>(M), *p_ir1 = arena.alloc<int32_t>(M);
   // everything that must start at zero lives in one block, cleared by one memset: per-read counters, the flags and
-  // counters of the kernels, the totals of the scans
+  // counters of the kernels
   const size_t z_deg = 0, z_cursor = z_deg + (R + 1) * sizeof(uint32_t), z_wgt = ((z_cursor + (R + 1) * sizeof(uint32_t)) + 7) & ~size_t(7);
   const size_t z_u32 = z_wgt + (R + 1) * sizeof(unsigned long long), z_u64 = z_u32 + 8 * sizeof(uint32_t);
-  const size_t z_tot = z_u64 + 4 * sizeof(uint64_t), z_end = z_tot + 2 * sizeof(unsigned long long);
+  const size_t z_end = z_u64 + 4 * sizeof(uint64_t);
   char        *zero  = arena.alloc<char>(z_end);
   MSGPU_CUDA(cudaMemsetAsync(zero, 0, z_end, st));
   uint32_t           *deg    = reinterpret_cast<uint32_t *>(zero + z_deg);
@@ -1343,7 +1244,6 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   uint32_t           *d_u32  = reinterpret_cast<uint32_t *>(zero + z_u32); // [0] sources [1] tiles [2] too many sources
                                                                            // [3] tile error [4] big groups [5] heavy matches
   uint64_t           *d_u64  = reinterpret_cast<uint64_t *>(zero + z_u64);
-  unsigned long long *totals = reinterpret_cast<unsigned long long *>(zero + z_tot);
   uint32_t           *rd_off = arena.alloc<uint32_t>(R + 1);
   const int gm = grid_for(M, 256), gr = grid_for(R, 256);
   if (M) {
@@ -1367,7 +1267,7 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   MSGPU_CUDA(cudaMemcpyAsync(rd_off + R, d_u32 + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
   TileCount tc{plan, prefix};
   exclusive_scan<uint32_t>(arena, st, tc, R, tile_idx, d_u32 + 1);
-  // one copy of the adjacent counter words (d_u32[0..7], d_u64[0..3], totals[0..1]) into pinned memory
+  // one copy of the adjacent counter words (d_u32[0..7], d_u64[0..3]) into pinned memory
   char *h_words = static_cast<char *>(arena.host_scratch());
   MSGPU_CUDA(cudaMemcpyAsync(h_words, zero + z_u32, z_end - z_u32, cudaMemcpyDeviceToHost, st));
   const uint32_t *h32 = reinterpret_cast<const uint32_t *>(h_words);
@@ -1375,7 +1275,6 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   MSGPU_CUDA(cudaStreamSynchronize(st));
   const uint32_t n_src = h32[0], n_tiles = h32[1];
   const uint64_t n_slices = h64[0], P = h64[1]; // P = sum k(k-1)/2: every unordered pair is one suffix member
-  e.n_pairs = P;
 
   uint32_t *tile_row = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1), *tile_kind = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1);
   if (R) MSGPU_LAUNCH("write_tiles", st, write_tiles_kernel<<<gr, 256, 0, st>>>(tc, tile_idx, R, n_tiles, tile_row, tile_kind, d_u32 + 2));
@@ -1399,9 +1298,43 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
                                         tile_row, tile_kind, tile_lo, t_end, plan, slice_off, rd_off, rd_src, rows,
                                         unitigs.grp_off, p_read, uint32_t(R), slices));
   }
-  // capacity of the outputs: a tile emits at most kTileCap rows, and never more than there are pairs
-  uint64_t cap = uint64_t(my_tiles) * kTileCap;
-  if (cap > P) cap = P;
+  pl.rows      = rows;
+  pl.p_read    = p_read;
+  pl.p_ir0     = p_ir0;
+  pl.p_ir1     = p_ir1;
+  pl.grp_off   = unitigs.grp_off;
+  pl.rd_off    = rd_off;
+  pl.rd_src    = rd_src;
+  pl.tile_row  = tile_row;
+  pl.tile_kind = tile_kind;
+  pl.slice_off = slice_off;
+  pl.slices    = slices;
+  pl.flags     = d_u32;
+  pl.n_reads   = R;
+  pl.n_pairs   = P;
+  pl.n_tiles   = n_tiles;
+  pl.tile_lo   = tile_lo;
+  pl.tile_hi   = tile_hi;
+  pl.valid     = true;
+}
+
+// scratch of one emission: the compact records of its tiles, their counts and offsets, the totals (device)
+void pairing_scratch_alloc(Arena &arena, uint32_t max_tiles, PairScratch &sc) {
+  sc.max_tiles = max_tiles;
+  sc.records   = arena.alloc<uint2>(uint64_t(max_tiles) * kTileCap);
+  sc.tile_cnt  = arena.alloc<uint2>(uint64_t(max_tiles) + 1);
+  sc.em_base   = arena.alloc<unsigned long long>(uint64_t(max_tiles) + 1);
+  sc.ed_base   = arena.alloc<unsigned long long>(uint64_t(max_tiles) + 1);
+  sc.status    = arena.alloc<unsigned long long>(2 * uint64_t(max_tiles) + 2);
+  sc.totals    = arena.alloc<unsigned long long>(4); // [0] edge matches [1] edges [2] ticket of the one-kernel variant
+}
+
+uint64_t pairing_rows_bound(const PairPlan &pl, uint32_t n_tiles) { // output rows a range of tiles can produce at most
+  const uint64_t cap = uint64_t(n_tiles) * kTileCap;
+  return cap < pl.n_pairs ? cap : pl.n_pairs;
+}
+
+void pairing_outputs_alloc(Arena &arena, uint64_t cap, EdgeTables &e) {
   e.em_unitig = arena.alloc<uint32_t>(cap);
   e.em_ov0    = arena.alloc<int32_t>(cap);
   e.em_ov1    = arena.alloc<int32_t>(cap);
@@ -1411,7 +1344,9 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   e.first     = arena.alloc<uint32_t>(cap);
   e.second    = arena.alloc<uint32_t>(cap);
   e.em_begin  = arena.alloc<uint64_t>(cap + 1);
+}
 
+static bool one_kernel_variant() {
   // The product is the two-kernel form (tile kernel -> compact records -> two scans -> emission kernel).
   // MSGPU_VARIANT=fused selects the ONE-kernel form (enumerate, sort, write the tables; offsets by two look-back
   // chains): bit-identical tables, measured slower at yeast scale (1.56 ms vs 0.75 + 0.50 ms; 21 % of its stall samples
@@ -1419,104 +1354,147 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   // and its emission phase runs at 40 registers / 3 CTAs per SM): profiles/r2_ncu_pair_tiles_fused_onekernel_yeast.txt.
   // Kept as the A/B the design decision rests on.
   const char *variant = std::getenv("MSGPU_VARIANT");
-  const bool  split   = !(variant && std::string(variant) == "fused");
+  return variant && std::string(variant) == "fused";
+}
 
+static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, const PairScratch &sc) {
   TileArgs a;
-  a.rows      = rows;
-  a.p_read    = p_read;
-  a.p_ir0     = p_ir0;
-  a.p_ir1     = p_ir1;
-  a.grp_off   = unitigs.grp_off;
-  a.rd_off    = rd_off;
-  a.rd_src    = rd_src;
-  a.tile_row  = tile_row;
-  a.tile_kind = tile_kind;
-  a.slice_off = slice_off;
-  a.slices    = slices;
-  a.tile_lo   = tile_lo;
-  a.tile_hi   = tile_hi;
-  a.records   = nullptr;
-  a.tile_cnt  = nullptr;
-  a.error     = d_u32 + 3;
+  a.rows      = pl.rows;
+  a.p_read    = pl.p_read;
+  a.p_ir0     = pl.p_ir0;
+  a.p_ir1     = pl.p_ir1;
+  a.grp_off   = pl.grp_off;
+  a.rd_off    = pl.rd_off;
+  a.rd_src    = pl.rd_src;
+  a.tile_row  = pl.tile_row;
+  a.tile_kind = pl.tile_kind;
+  a.slice_off = pl.slice_off;
+  a.slices    = pl.slices;
+  a.tile_lo   = t_lo;
+  a.tile_hi   = t_hi;
+  a.records   = sc.records;
+  a.tile_cnt  = sc.tile_cnt;
+  a.error     = pl.flags + 3;
   // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits; otherwise
   // tiles choose per tile and the launch carries the 64-bit buffers
-  a.wide = R > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)
-  if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st)); // planning done; what follows is "merge" time
-  if (!my_tiles) {
-    MSGPU_CUDA(cudaMemsetAsync(e.em_begin, 0, sizeof(uint64_t), st)); // an empty CSR: em_begin[0] = 0
-  } else if (!split) {
-    unsigned long long *status = arena.alloc<unsigned long long>(2 * uint64_t(my_tiles));
-    MSGPU_CUDA(cudaMemsetAsync(status, 0, 2 * uint64_t(my_tiles) * sizeof(unsigned long long), st));
+  a.wide = pl.n_reads > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)
+  return a;
+}
+
+// First half of the emission of tiles [t_lo, t_hi): enumerate + sort every tile into compact records, then the two
+// scans that turn the tiles' counts into row offsets.  Needs nothing from earlier ranges, so the tiles of the next
+// chunk can run while the rows of this one are consumed.  Asynchronous; sc.totals (device) = the range's row counts.
+void pairing_tiles(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, PairScratch &sc) {
+  const uint32_t n = t_hi - t_lo;
+  if (n > sc.max_tiles) throw BuildError{MSGPU_ERR_INTERNAL, "pairing: emission scratch too small"};
+  MSGPU_CUDA(cudaMemsetAsync(sc.totals, 0, 4 * sizeof(unsigned long long), st));
+  if (!n || one_kernel_variant()) return;
+  const TileArgs a = tile_args(pl, t_lo, t_hi, sc);
+  // (the shared-memory opt-in is an attribute of the function ON THE CURRENT DEVICE: set before every launch — a
+  //  context per GPU in one process is supported, and the call costs less than a microsecond)
+  MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
+  // 32 registers, 51 KB (narrow): four resident CTAs per SM; a few waves of them, tiles strided over the grid
+  int grid = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * 4;
+  if (uint32_t(grid) > n) grid = int(n);
+  MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
+  run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{sc.tile_cnt}, n, sc.em_base, sc.totals + 0),
+            scan_job<unsigned long long>(arena, st, 1, TileHeads{sc.tile_cnt}, n, sc.ed_base, sc.totals + 1));
+}
+
+// Second half: the records of the range -> the columns of `e` (indexed from the range's first edge match / edge; the
+// em_begin VALUES start at em_value_base = the rows of the earlier ranges of the same slice).  Asynchronous.
+void pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, PairScratch &sc,
+                  EdgeTables &e, uint64_t em_value_base) {
+  (void)arena;
+  const uint32_t n = t_hi - t_lo;
+  e.em_value_base  = em_value_base;
+  if (!n) {
+    MSGPU_CUDA(cudaMemcpyAsync(e.em_begin, &e.em_value_base, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); // empty CSR
+    return;
+  }
+  if (one_kernel_variant()) {
+    const TileArgs a = tile_args(pl, t_lo, t_hi, sc);
+    MSGPU_CUDA(cudaMemsetAsync(sc.status, 0, 2 * uint64_t(n) * sizeof(unsigned long long), st));
     FusedArgs fa;
     fa.t             = a;
-    fa.ticket        = d_u32 + 6; // (zeroed with the block above)
-    fa.st_em         = status;
-    fa.st_edge       = status + my_tiles;
-    fa.em_value_base = 0;
-    fa.totals        = totals;
+    fa.ticket        = reinterpret_cast<unsigned int *>(sc.totals + 2);
+    fa.st_em         = sc.status;
+    fa.st_edge       = sc.status + n;
+    fa.em_value_base = em_value_base;
+    fa.totals        = sc.totals;
     fa.out           = e;
-    // the opt-in is an attribute of the function ON THE CURRENT DEVICE: set it before every launch (a context per
-    // GPU in one process is supported, and the call costs less than a microsecond)
     if (a.wide) {
       MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
       int grid = kNumSMs * (kFusedCtas > 2 ? 2 : kFusedCtas);
-      if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
+      if (uint32_t(grid) > n) grid = int(n);
       MSGPU_LAUNCH("pair_tiles_fused", st, pair_tiles_fused_kernel<true><<<grid, kFusedBlock, kMergeBytesWide, st>>>(fa));
     } else {
       MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesNarrow)));
       int grid = kNumSMs * kFusedCtas; // persistent: one CTA per resident slot, tiles by ticket
-      if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
+      if (uint32_t(grid) > n) grid = int(n);
       MSGPU_LAUNCH("pair_tiles_fused", st, pair_tiles_fused_kernel<false><<<grid, kFusedBlock, kMergeBytesNarrow, st>>>(fa));
     }
-  } else {
-    uint2              *records  = arena.alloc<uint2>(uint64_t(my_tiles) * kTileCap);
-    uint2              *tile_cnt = arena.alloc<uint2>(uint64_t(my_tiles) + 1);
-    unsigned long long *em_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
-    unsigned long long *ed_base = arena.alloc<unsigned long long>(uint64_t(my_tiles) + 1);
-    a.records  = records;
-    a.tile_cnt = tile_cnt;
-    MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
-    // 32 registers, 51 KB (narrow): four resident CTAs per SM; a few waves of them, tiles strided over the grid
-    int grid = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * 4;
-    if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
-    MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
-    run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{tile_cnt}, my_tiles, em_base, totals + 0),
-              scan_job<unsigned long long>(arena, st, 1, TileHeads{tile_cnt}, my_tiles, ed_base, totals + 1));
-    EmitArgs ea;
-    ea.rows      = rows;
-    ea.rd_off    = rd_off;
-    ea.rd_src    = rd_src;
-    ea.tile_row  = tile_row;
-    ea.tile_kind = tile_kind;
-    ea.tile_lo   = tile_lo;
-    ea.n_tiles   = my_tiles;
-    ea.records   = records;
-    ea.tile_cnt  = tile_cnt;
-    ea.em_base   = em_base;
-    ea.edge_base = ed_base;
-    ea.totals    = totals;
-    ea.out       = e;
-    grid         = kNumSMs * 8;
-    if (uint32_t(grid) > my_tiles) grid = int(my_tiles);
-    // 128-bit column stores need the output columns 16-byte aligned (arena allocations are 256-byte aligned)
-    const char *emit = std::getenv("MSGPU_EMIT");
-    if (emit && std::string(emit) == "scalar")
-      MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
-    else
-      MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_vec_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
+    return;
   }
-  MSGPU_CUDA(cudaMemcpyAsync(h_words, zero + z_u32, z_end - z_u32, cudaMemcpyDeviceToHost, st));
-  const uint32_t           *h_flags = reinterpret_cast<const uint32_t *>(h_words);
-  const unsigned long long *h_tot   = reinterpret_cast<const unsigned long long *>(h_words + (z_tot - z_u32));
+  EmitArgs ea;
+  ea.rows          = pl.rows;
+  ea.rd_off        = pl.rd_off;
+  ea.rd_src        = pl.rd_src;
+  ea.tile_row      = pl.tile_row;
+  ea.tile_kind     = pl.tile_kind;
+  ea.tile_lo       = t_lo;
+  ea.n_tiles       = n;
+  ea.records       = sc.records;
+  ea.tile_cnt      = sc.tile_cnt;
+  ea.em_base       = sc.em_base;
+  ea.edge_base     = sc.ed_base;
+  ea.totals        = sc.totals;
+  ea.em_value_base = em_value_base;
+  ea.out           = e;
+  int grid         = kNumSMs * 8;
+  if (uint32_t(grid) > n) grid = int(n);
+  // (measured and not kept, round 2: the same emission with four consecutive rows per thread and 128-bit column
+  //  stores — 0.75 ms instead of 0.49 ms at yeast scale, profiles/r2_ab_emit_vec_vs_scalar_and_fused.log: the kernel is
+  //  bound by the latency of its gathers, and a thread that owns a quad serialises four of them behind one another
+  //  where four strided records keep four independent chains in flight)
+  MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
+}
+
+// reads the row counts of the last emission and the error flags of the plan (one round trip); throws on the
+// shapes the kernels refuse
+void pairing_finish(Arena &arena, cudaStream_t st, const PairPlan &pl, const PairScratch &sc, uint64_t *n_em,
+                    uint64_t *n_edges) {
+  char *h = static_cast<char *>(arena.host_scratch());
+  MSGPU_CUDA(cudaMemcpyAsync(h, pl.flags, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaMemcpyAsync(h + 64, sc.totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   MSGPU_CUDA(cudaStreamSynchronize(st));
+  const uint32_t           *h_flags = reinterpret_cast<const uint32_t *>(h);
+  const unsigned long long *h_tot   = reinterpret_cast<const unsigned long long *>(h + 64);
   if (h_flags[2])
     throw BuildError{MSGPU_ERR_LIMIT, "a read matches more than " + std::to_string(kSrcCap) + " unitigs with partners"};
   if (h_flags[3])
     throw BuildError{MSGPU_ERR_INTERNAL, "pairing: tile invariant violated (code " + std::to_string(h_flags[3]) + ")"};
-  e.n_em      = h_tot[0];
-  e.n_edges   = h_tot[1];
-  e.pair_rows = rows; // kept (in the arena) for the stage that follows: msgpu_chain_overlaps
-  e.p_read    = p_read;
+  *n_em    = h_tot[0];
+  *n_edges = h_tot[1];
+}
+
+void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
+                       EdgeTables &e, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts, PairPlan *plan_out) {
+  e = EdgeTables{};
+  PairPlan pl;
+  pairing_plan(arena, st, m, unitigs, n_reads, part, n_parts, pl);
+  e.n_pairs = pl.n_pairs;
+  const uint32_t my_tiles = pl.tile_hi - pl.tile_lo;
+  pairing_outputs_alloc(arena, pairing_rows_bound(pl, my_tiles), e);
+  PairScratch sc;
+  pairing_scratch_alloc(arena, my_tiles, sc);
+  if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st)); // planning done; what follows is "merge" time
+  pairing_tiles(arena, st, pl, pl.tile_lo, pl.tile_hi, sc);
+  pairing_rows(arena, st, pl, pl.tile_lo, pl.tile_hi, sc, e, 0);
+  pairing_finish(arena, st, pl, sc, &e.n_em, &e.n_edges);
+  e.pair_rows = pl.rows; // kept (in the arena) for the stage that follows: msgpu_chain_overlaps
+  e.p_read    = pl.p_read;
+  if (plan_out) *plan_out = pl;
 }
 
 void run_pairing(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
@@ -1525,7 +1503,7 @@ void run_pairing(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigT
   if (v && std::string(v) == "sorted" && n_parts <= 1)
     run_pairing_sorted(arena, st, m, unitigs, n_reads, e, ev_pair_done);
   else
-    run_pairing_fused(arena, st, m, unitigs, n_reads, e, ev_pair_done, part, n_parts);
+    run_pairing_fused(arena, st, m, unitigs, n_reads, e, ev_pair_done, part, n_parts, nullptr);
 }
 
 } // namespace msgpu
