@@ -209,7 +209,9 @@ def run_ours(args):
     launches = gb.launch_count() - launches0
     t_dev = reduce(sum(ms) / 1e3, "MAX")
 
-    # ---- timed region 2: end to end through the C ABI with host buffers
+    # ---- timed region 2: end to end through the C ABI with host buffers.  The edge tables are produced in chunks of
+    # `--e2e-chunk-tiles` pairing tiles so that msgpu_result_host downloads one chunk while the next is paired
+    gb.set_chunk_tiles(args.e2e_chunk_tiles)
     for _ in range(2):
         step_e2e()
     torch.cuda.synchronize()
@@ -221,6 +223,7 @@ def run_ours(args):
     barrier()
     t_e2e = reduce(time.perf_counter() - t0, "MAX")
     stage = gb.timings()
+    gb.set_chunk_tiles(0)
     clocks = sampler.summary()
 
     # ---- per-kernel durations (CUDA events around every launch) for the roofline
@@ -352,6 +355,258 @@ def run_ours(args):
                            "bytes_received_per_rank": sb.exchange_bytes, "ms": x_ms,
                            "gbs_per_rank": (sb.exchange_bytes / x_ms / 1e6) if x_ms else None,
                            "nvlink_peak_gbs": 770.0}
+    gb.close()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+BIG_WORKLOADS = ("thaliana", "human")  # generated on the GPU, built chunk by chunk, compared on a unitig sample
+
+
+def run_ours_big(args):
+    """thaliana / human: results that do not fit the host (thaliana: 60 GB) or the GPUs (human: 10^11 edge matches).
+    Same step as run_ours, except that
+      * the workload is generated and formatted on the GPU (muchsalsa_b200.synth_gpu),
+      * the edge tables are produced chunk by chunk (msgpu_set_chunk_tiles / msgpu_chunk_next) into two alternating
+        buffer sets; a step has delivered every chunk when its clock stops,
+      * parity = on-device invariants + digests of every chunk, and a comparison BY NAME with the CPU checker on a
+        deterministic sample of the unitigs (oracle/sampled.py)."""
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev_t = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev_t)
+    from muchsalsa_b200 import multi_gpu, synth, synth_gpu
+    from muchsalsa_b200.construct import GraphBuilder
+    from oracle import sampled
+
+    cfg = synth.CONFIGS[args.workload]
+    t_gen = time.perf_counter()
+    cols = synth_gpu.generate_columns_torch(cfg, (rank, world) if world > 1 else None, sentinel=(rank == world - 1),
+                                            device=dev_t)
+    n_lines_local = int(cols["unitig"].numel())
+    # ---- the sample: unitigs whose NAME hashes to 0 mod `sample_mod`; their lines go to the CPU checker
+    uniq = torch.unique(cols["unitig"][:n_lines_local - (1 if rank == world - 1 else 0)]).cpu().numpy()
+    picked = np.array([u for u in uniq if sampled.unitig_in_sample(b"u%d" % u, args.sample_mod)], np.int64)
+    body = n_lines_local - (1 if rank == world - 1 else 0)  # the sentinel is the file's last line: never parsed
+    in_s = torch.isin(cols["unitig"][:body], torch.from_numpy(picked).to(dev_t))
+    sub_idx = torch.nonzero(in_s).squeeze(1)
+    sub_cols = {k: v[:body][sub_idx] for k, v in cols.items() if torch.is_tensor(v)}
+    sub_lines = synth_gpu.columns_to_paf_torch(sub_cols).cpu().numpy().tobytes().split(b"\n")[:-1] if sub_idx.numel() else []
+    sub_local = sub_idx.cpu().numpy()
+    dev = synth_gpu.columns_to_paf_torch(cols)
+    n_bytes = int(dev.numel())
+    del cols, sub_cols, in_s, sub_idx
+    torch.cuda.empty_cache()
+    t_gen = time.perf_counter() - t_gen
+
+    stream = torch.cuda.Stream(dev_t)
+    torch.cuda.set_stream(stream)
+    host = dev.cpu().pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    gb = GraphBuilder(local)
+    gb.set_stream(stream.cuda_stream)
+    gb.set_chunk_tiles(args.chunk_tiles)
+    sb = multi_gpu.ShardedBuilder(gb, rank, world, dist, dev_t, stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def reduce(x, op):
+        if dist is None:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
+
+    def drain(consumer=None):
+        n = 0
+        while True:
+            c = gb.chunk_next()
+            if c is None:
+                return n
+            n += 1
+            if consumer is not None:
+                consumer(c)
+
+    def step(from_host=False):
+        if world == 1:
+            gb.build_from_buffer(host) if from_host else gb.build_from_device(dev.data_ptr(), n_bytes)
+        else:
+            sb.build_buffer(host) if from_host else sb.build_device(dev.data_ptr(), n_bytes)
+        return drain()
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        n_chunks = step()
+    counts = gb.counts()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = gb.launch_count()
+    ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        step()
+        b.record(stream)
+        b.synchronize()
+        ms.append(a.elapsed_time(b))
+    torch.cuda.synchronize()
+    barrier()
+    launches = gb.launch_count() - launches0
+    t_dev = reduce(sum(ms) / 1e3, "MAX")
+    # end to end: the PAF travels from pinned host memory inside the timed region; what comes back per step are the
+    # per-chunk row counts (the tables themselves are larger than host memory can take at these sizes)
+    step(True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(True)
+    torch.cuda.synchronize()
+    barrier()
+    t_e2e = reduce(time.perf_counter() - t0, "MAX")
+    clocks = sampler.summary()
+
+    # ---- per-kernel times of one step (events around every launch)
+    gb.profile(True)
+    step()
+    ks = gb.kernel_stats()
+    gb.profile(False)
+    per_kernel = {k: {"launches_per_step": n, "ms_per_step": t, "us_per_launch": 1e3 * t / max(n, 1)} for k, (n, t) in ks.items()}
+    top = sorted(per_kernel.items(), key=lambda kv: -kv[1]["ms_per_step"])
+
+    # ---- verification pass (not timed): digest + invariants of every chunk, rows of the sampled unitigs
+    c0 = gb.counts()
+    U = c0["n_unitigs"]
+    t = gb.device_tables()
+    un = sampled.device_name_table(t.unitig_name_off, t.unitig_names, U)
+    member = torch.from_numpy(np.array([sampled.unitig_in_sample(x, args.sample_mod) for x in un], np.bool_)).cuda()
+    dig = {"n_edges": 0, "n_edge_matches": 0, "edge_sum": 0, "em_sum": 0, "violations": 0}
+    keys_in_order, prev_key, rows, first_key, last_key = True, -1, [], (1 << 64) - 1, 0
+
+    def consume(c):
+        nonlocal keys_in_order, prev_key, first_key, last_key
+        d = gb.chunk_digest()
+        for k in dig:
+            dig[k] = (dig[k] + d[k]) & ((1 << 64) - 1)
+        if d["n_edges"]:
+            keys_in_order = keys_in_order and prev_key < d["first_key"]
+            prev_key = d["last_key"]
+            first_key, last_key = min(first_key, d["first_key"]), max(last_key, d["last_key"])
+        rows.append(sampled.sample_rows_of_chunk(c, member))
+
+    if world == 1:
+        gb.build_from_device(dev.data_ptr(), n_bytes)
+    else:
+        sb.build_device(dev.data_ptr(), n_bytes)
+    drain(consume)
+    final = gb.counts()
+    mine = sampled.concat_rows(rows)
+    rn = sampled.device_name_table(t.read_name_off, t.read_names, c0["n_reads"])
+    got = sampled.canon_from_ids(mine, rn, un)
+    # totals over the ranks; every rank's slice must follow the previous one's
+    vec = [dig[k] & 0xffffffff for k in dig] + [dig[k] >> 32 for k in dig] + \
+          [first_key >> 32, first_key & 0xffffffff, last_key >> 32, last_key & 0xffffffff, n_lines_local, int(keys_in_order)]
+    tv = torch.tensor(vec, dtype=torch.int64, device="cuda")
+    if dist is not None:
+        allv = torch.empty(world * tv.numel(), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allv, tv)
+        allv = allv.view(world, -1).cpu().tolist()
+    else:
+        allv = [tv.cpu().tolist()]
+    nk = len(dig)
+    tot = {k: (sum(r[i] for r in allv) + (sum(r[nk + i] for r in allv) << 32)) & ((1 << 64) - 1) for i, k in enumerate(dig)}
+    ordered, prev = all(r[2 * nk + 5] for r in allv), -1
+    for r in allv:
+        fk, lk = (r[2 * nk] << 32) | r[2 * nk + 1], (r[2 * nk + 2] << 32) | r[2 * nk + 3]
+        if lk == 0 and fk == (1 << 64) - 1:
+            continue
+        ordered = ordered and prev < fk
+        prev = lk
+    line_base = sum(r[2 * nk + 4] for r in allv[:rank])
+    payload = (got, sub_lines, (sub_local + line_base))
+    if dist is not None:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(payload, gathered, dst=0)
+    else:
+        gathered = [payload]
+    sample = None
+    if rank == 0:
+        from oracle.pyoracle import Oracle
+        g_all = np.sort(np.concatenate([g[0] for g in gathered]), order=["lo", "hi", "u"])
+        lines = [ln for g in gathered for ln in g[1]]
+        orig = np.concatenate([np.asarray(g[2], np.int64) for g in gathered]) if lines else np.zeros(0, np.int64)
+        t0 = time.perf_counter()
+        want = sampled.checker_records_for_lines(Oracle(), lines, orig)
+        sample = {"unitigs_sampled": int(sum(len(set(ln[:ln.find(b"\t")] for ln in g[1])) for g in gathered)),
+                  "lines": len(lines), "edge_matches_gpu": int(g_all.size), "edge_matches_checker": int(want.size),
+                  "identical_by_name": bool(sampled.records_equal(g_all, want)),
+                  "checker": "oracle/libms_oracle.so (pinned on the reference by tests/test_oracle.py)",
+                  "checker_seconds": round(time.perf_counter() - t0, 2), "modulus": args.sample_mod}
+    M_tot = counts["n_matches"]  # global (the match tables are replicated)
+    parity = {"digest": tot, "slices_in_key_order": bool(ordered), "sampled": sample,
+              "ok": bool(tot["violations"] == 0 and ordered and (sample is None or sample["identical_by_name"]))}
+    peak, peak_src = peaks()
+    EM, E = tot["n_edge_matches"], tot["n_edges"]
+    roof = None
+    for name, st in top:
+        cnt = {"n_matches": M_tot, "n_edge_matches": EM // world, "n_edges": E // world, "n_lines": counts["n_lines"]}
+        bts = kernel_bytes(name, cnt, n_bytes)
+        if bts is None:
+            continue
+        roof = {"kernel": name, "bound": "hbm", "achieved": round(bts[0] / (st["ms_per_step"] * 1e-3) / 1e9, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(bts[0] / (st["ms_per_step"] * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_step_this_rank": int(bts[0]),
+                "strict_frac": round(bts[1] / (st["ms_per_step"] * 1e-3) / 1e9 / peak, 4),
+                "launches_per_step": st["launches_per_step"], "ms_per_step": round(st["ms_per_step"], 3),
+                "share_of_step": round(st["ms_per_step"] / sum(v["ms_per_step"] for v in per_kernel.values()), 3),
+                "note": "summed over the chunks of one step on rank 0 (CUDA events around every launch)"}
+        break
+    step_ms = 1e3 * t_dev / args.steps
+    survey = 3 * 40 * M_tot + 3 * 40 * EM + 12 * E
+    if roof is not None:
+        roof["construction_step"] = {"ms": round(step_ms, 3), "survey_8d_bytes": int(survey),
+                                     "survey_8d_frac_of_n_gpus": round(survey / step_ms / 1e6 / (peak * world), 4)}
+    cpu = cpu_baseline(args.workload) if world == 1 else None
+    out = {"metric": METRIC, "value": M_tot * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "i32 keys + f64 scores", "data": "synthetic",
+           "config": {"workload": f"{args.workload}-scale synthetic PAF (muchsalsa_b200.synth_gpu: G = {cfg.genome:,} bp, "
+                                  f"{cfg.coverage:g}x, repeats {cfg.rep_frac:g} x {cfg.rep_kind}({cfg.rep_mean:g}) capped "
+                                  f"{cfg.rep_cap}; ONE workload split over the ranks by unitig range)",
+                      "paf_bytes": int(reduce(n_bytes, "SUM")), "lines": int(sum(r[2 * nk + 4] for r in allv)),
+                      "kept_matches": M_tot, "reads": counts["n_reads"], "unitigs": counts["n_unitigs"],
+                      "pairs": int(reduce(counts["n_pairs"], "MAX")), "edges": E, "edge_matches": EM,
+                      "chunk_tiles": args.chunk_tiles, "chunks_per_step_rank0": n_chunks,
+                      "l2": "flushed between steps (256 MiB memset)", "generated_in_s": round(t_gen, 1)},
+           "edges_per_s": E * args.steps / t_dev, "edge_matches_per_s": EM * args.steps / t_dev,
+           "e2e": {"value": M_tot * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(reduce(n_bytes, "SUM")),
+                   "d2h_bytes_per_step": int(reduce(n_chunks * 80, "SUM")), "ms_per_step": 1e3 * t_e2e / args.steps,
+                   "note": "PAF from pinned host memory; the tables are consumed on the device chunk by chunk, the "
+                           "per-chunk row counts return to the host"},
+           "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+           "kernels": {k: {kk: round(vv, 3) for kk, vv in v.items()} for k, v in top[:12]},
+           "parity": parity["ok"], "parity_detail": parity,
+           "device_mem_gb": round((torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 1e9, 1)}
+    if world > 1:
+        out["exchange"] = {"bytes_received_per_rank": sb.exchange_bytes, "ms": sb.last_exchange_ms()}
     gb.close()
     if rank == 0:
         print(json.dumps(out), flush=True)
@@ -727,9 +982,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("MSGPU_WORKLOAD", "yeast"))
     ap.add_argument("--no-sequence", action="store_true", help="skip the K8 (sequence store) block")
+    ap.add_argument("--chunk-tiles", type=int, default=65536, help="thaliana / human: pairing tiles per chunk")
+    ap.add_argument("--e2e-chunk-tiles", type=int, default=2048,
+                    help="the e2e leg downloads the edge tables chunk by chunk, overlapped with the pairing; 0 = resident")
+    ap.add_argument("--sample-mod", type=int, default=512, help="thaliana / human: 1 unitig in this many is compared "
+                                                                  "with the CPU checker by name")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in BIG_WORKLOADS:
+        run_ours_big(args)
     else:
         run_ours(args)
 

@@ -184,8 +184,8 @@ class GraphBuilder:
         return t
 
     def result(self) -> Construction:
+        t = self.host_tables()  # (a chunked build learns its row counts while the chunks are downloaded)
         c = self.counts()
-        t = self.host_tables()
         R, U, M, E, EM = c["n_reads"], c["n_unitigs"], c["n_matches"], c["n_edges"], c["n_edge_matches"]
         m = dict(unitig=_np(t.m_unitig, M, np.uint32), read=_np(t.m_read, M, np.uint32),
                  nr0=_np(t.m_nr0, M, np.int32), nr1=_np(t.m_nr1, M, np.int32), ir0=_np(t.m_ir0, M, np.int32),

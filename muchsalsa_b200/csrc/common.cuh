@@ -128,6 +128,24 @@ public:
     return alloc<T>(n);
   }
   size_t high_water() const { return m_high; }
+  // Stack discipline for temporaries: everything allocated after mark() is given back by release_to() — the memory
+  // is reused by later allocations of the same build.  Stream order makes this safe without synchronisation: the
+  // kernels that used the temporaries were enqueued before the kernels that will reuse their memory.
+  struct Mark {
+    size_t n_slabs, used_last, used_total;
+  };
+  Mark mark() const { return Mark{m_slabs.size(), m_slabs.empty() ? 0 : m_slabs.back().used, m_used}; }
+  void release_to(const Mark &m) {
+    if (m.n_slabs == 0) {
+      for (auto &s : m_slabs) s.used = 0;
+    } else {
+      for (size_t i = m.n_slabs; i < m_slabs.size(); ++i) m_slabs[i].used = 0;
+      // (alloc() fills the first slab that has room, so earlier slabs may have grown too: only the slab that was last
+      //  at mark time can be rolled back exactly; allocations that landed in older slabs stay until reset())
+      if (m_slabs[m.n_slabs - 1].used > m.used_last) m_slabs[m.n_slabs - 1].used = m.used_last;
+    }
+    m_used = m.used_total;
+  }
 
 private:
   struct Slab {

@@ -156,7 +156,7 @@ void pair_or_plan(msgpu_ctx *ctx, uint32_t part, uint32_t n_parts) {
     ctx->chunks.rows_done = keep;
   }
   if (!ctx->chunk_tiles) {
-    pair_or_plan(ctx, part, n_parts);
+    run_pairing(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3], part, n_parts);
     return;
   }
   auto &c = ctx->chunks;

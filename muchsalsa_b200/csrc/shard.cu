@@ -499,7 +499,11 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
     MSGPU_CUDA(cudaMemsetAsync(shared_u, 0, ub + 1, st));
     merge_names(arena, st, d_sh, n_shards, 1, ub, ubytes, seed, d_status, gid_u, unitigs, no_nlen, no_line, shared_u);
 
-    // ---- records: renumber, deduplicate across chunks (capacity = all records), group by unitig
+    // ---- records: renumber, deduplicate across chunks (capacity = all records), group by unitig.  The final table is
+    // allocated first; everything after the mark is scratch of the merge and is handed back before the pairing
+    // allocates (at 10^8 .. 10^9 records the scratch — a second record table, the dedup table — is the larger part)
+    alloc_match_soa(arena, m, mb);
+    const Arena::Mark scratch = arena.mark();
     MatchSoA c;
     alloc_match_soa(arena, c, mb);
     const int g = grid_for(mb, 256);
@@ -509,7 +513,6 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
     if (mb) MSGPU_LAUNCH("dedup_insert", st, shard_dedup_insert_kernel<<<g, 256, 0, st>>>(c, dt, shared_u, slot));
     KeepFlag keep{c.line, slot, dt.min_entry};
     exclusive_scan<uint32_t>(arena, st, keep, mb, pos, &d_status->n_matches);
-    alloc_match_soa(arena, m, mb);
     if (mb) {
       MSGPU_LAUNCH("compact_matches", st, shard_compact_kernel<<<g, 256, 0, st>>>(c, keep, pos, m));
       MSGPU_LAUNCH("check_grouped", st, shard_check_grouped_kernel<<<g, 256, 0, st>>>(m.unitig, &d_status->n_matches, &d_status->unsorted));
@@ -520,6 +523,7 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
     MSGPU_CUDA(cudaMemcpyAsync(pinned, d_status, sizeof(h), cudaMemcpyDeviceToHost, st));
     MSGPU_CUDA(cudaStreamSynchronize(st));
     memcpy(&h, pinned, sizeof(h));
+    arena.release_to(scratch);
     if (!h.collision) break;
   }
   reads.n         = h.n_ids[0];
