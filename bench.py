@@ -391,6 +391,9 @@ def run_ours_big(args):
     from oracle import sampled
 
     cfg = synth.CONFIGS[args.workload]
+    if args.genome_scale != 1.0:  # development: the same shape on a shorter genome
+        import dataclasses
+        cfg = dataclasses.replace(cfg, name=f"{cfg.name}*{args.genome_scale:g}", genome=int(cfg.genome * args.genome_scale))
     t_gen = time.perf_counter()
     cols = synth_gpu.generate_columns_torch(cfg, (rank, world) if world > 1 else None, sentinel=(rank == world - 1),
                                             device=dev_t)
@@ -584,7 +587,7 @@ def run_ours_big(args):
     if roof is not None:
         roof["construction_step"] = {"ms": round(step_ms, 3), "survey_8d_bytes": int(survey),
                                      "survey_8d_frac_of_n_gpus": round(survey / step_ms / 1e6 / (peak * world), 4)}
-    cpu = cpu_baseline(args.workload) if world == 1 else None
+    cpu = cpu_baseline(args.workload) if world == 1 and args.genome_scale == 1.0 else None
     out = {"metric": METRIC, "value": M_tot * args.steps / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": warm, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "i32 keys + f64 scores", "data": "synthetic",
@@ -983,6 +986,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("MSGPU_WORKLOAD", "yeast"))
     ap.add_argument("--no-sequence", action="store_true", help="skip the K8 (sequence store) block")
     ap.add_argument("--chunk-tiles", type=int, default=65536, help="thaliana / human: pairing tiles per chunk")
+    ap.add_argument("--genome-scale", type=float, default=1.0, help="thaliana / human: scale the genome (development)")
     ap.add_argument("--e2e-chunk-tiles", type=int, default=2048,
                     help="the e2e leg downloads the edge tables chunk by chunk, overlapped with the pairing; 0 = resident")
     ap.add_argument("--sample-mod", type=int, default=512, help="thaliana / human: 1 unitig in this many is compared "

@@ -215,4 +215,64 @@ std::string getNanoporeSequence(Context &ctx, unsigned int nanoporeId, int nanop
   return fetchOne(ctx, 1, nanoporeId, nanoporeRegionLeft, nanoporeRegionRight, direction);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// SequenceBatch
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+thread_local SequenceBatch *t_pActiveBatch = nullptr;
+}
+
+SequenceBatch *SequenceBatch::active() { return t_pActiveBatch; }
+
+SequenceBatch::~SequenceBatch() {
+  if (t_pActiveBatch == this) t_pActiveBatch = nullptr;
+}
+
+void SequenceBatch::begin(Mode mode) {
+  if (t_pActiveBatch != nullptr) throw std::logic_error("SequenceBatch: another batch is active on this thread");
+  m_mode   = mode;
+  m_cursor = 0;
+  if (mode == Mode::e_RECORD) m_requests.clear();
+  t_pActiveBatch = this;
+}
+
+void SequenceBatch::end() {
+  t_pActiveBatch = nullptr;
+  m_mode         = Mode::e_IDLE;
+}
+
+void SequenceBatch::fetch() {
+  auto const n = m_requests.size();
+  m_offsets.assign(n + 1, 0);
+  m_status.assign(n, 0);
+  uint64_t bound = 0;
+  if (int rc = msgpu_seq_batch_bound(m_ctx.get(), m_requests.data(), n, &bound); rc != MSGPU_OK) raise(m_ctx.get(), rc);
+  m_data.assign(bound, '\0');
+  if (n == 0) return;
+  if (int rc = msgpu_seq_fetch_batch(m_ctx.get(), m_requests.data(), n, m_data.data(), bound, m_offsets.data(),
+                                     m_status.data());
+      rc != MSGPU_OK)
+    raise(m_ctx.get(), rc);
+}
+
+std::string SequenceBatch::get(unsigned int which, unsigned int id, int left, int right, Toggle const direction) {
+  msgpu_seq_req const req{which, id, left, right, static_cast<bool>(direction) ? 1u : 0u};
+  if (m_mode == Mode::e_RECORD) {
+    // the length the reference's strSlice(record, left, right + 1) would have (SequenceUtils.cpp:27-38), from the index
+    uint64_t bytes = 0;
+    if (int rc = msgpu_seq_batch_bound(m_ctx.get(), &req, 1, &bytes); rc != MSGPU_OK) raise(m_ctx.get(), rc);
+    m_requests.push_back(req);
+    return std::string(bytes, 'N');
+  }
+  if (m_mode != Mode::e_REPLAY || m_cursor >= m_requests.size())
+    throw std::logic_error("SequenceBatch: replay asked for more sequences than were recorded");
+  auto const &rec = m_requests[m_cursor];
+  if (rec.which != req.which || rec.id != req.id || rec.left != req.left || rec.right != req.right ||
+      rec.direction != req.direction)
+    throw std::logic_error("SequenceBatch: the replay pass diverged from the recorded pass");
+  auto const i = m_cursor++;
+  if (m_status[i] != 0) raise(m_ctx.get(), m_status[i] == 1 ? MSGPU_ERR_IO : MSGPU_ERR_OUT_OF_RANGE);
+  return m_data.substr(m_offsets[i], m_offsets[i + 1] - m_offsets[i]);
+}
+
 } // namespace muchsalsa::gpu

@@ -18,6 +18,7 @@
 #include <set>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "Registry.h"
 #include "graph/Graph.h"
@@ -78,5 +79,63 @@ std::string getIlluminaSequence(Context &ctx, unsigned int illuminaId, int illum
                                 int illuminaOverlapRight, muchsalsa::Toggle const direction);
 std::string getNanoporeSequence(Context &ctx, unsigned int nanoporeId, int nanoporeRegionLeft,
                                 int nanoporeRegionRight, muchsalsa::Toggle const direction);
+
+// The sequence fetches of ONE assemblePath call as ONE batch.  assemblePath issues its fetches one
+// by one (ap.cpp:352-579: getSequenceLeft/RightOfAnchor, getAnchorSequence, getSequenceBetweenAnchors; :1288-1301 the
+// contain elements), and what it does with a fetched sequence depends on its LENGTH only (append, slice, reverse
+// complement, write) — never on its bytes.  So the call is run twice:
+//   record  with the getters answering placeholder strings of exactly the length the reference would return (the
+//           lengths come from the index, no sequence byte is touched) while every request is logged; the pass writes
+//           to a null OutputWriter and a scratch Id2OverlapMap, its other arguments are const;
+//   fetch   ONE msgpu_seq_fetch_batch for everything the path needs;
+//   replay  with the getters handing out the fetched sequences in the recorded order — this pass produces the output.
+// While a batch is active on a thread (thread-local, like the reference's per-job state), the two getters of
+// SequenceUtils.cpp:63-85 forward to it: the two-line change INTEGRATION.md §6 shows.
+class SequenceBatch {
+public:
+  explicit SequenceBatch(Context &ctx) : m_ctx(ctx) {}
+  ~SequenceBatch();
+  SequenceBatch(SequenceBatch const &)            = delete;
+  SequenceBatch &operator=(SequenceBatch const &) = delete;
+
+  static SequenceBatch *active(); // the batch the calling thread is recording / replaying, or nullptr
+  template <class Fn> void record(Fn &&pass) {
+    begin(Mode::e_RECORD);
+    try {
+      pass();
+    } catch (...) {
+      end();
+      throw;
+    }
+    end();
+  }
+  void fetch(); // one msgpu_seq_fetch_batch for the recorded requests
+  template <class Fn> void replay(Fn &&pass) {
+    begin(Mode::e_REPLAY);
+    try {
+      pass();
+    } catch (...) {
+      end();
+      throw;
+    }
+    end();
+  }
+  // what the getters call while the batch is active (which: 0 = unitig / illumina, 1 = nanopore)
+  std::string get(unsigned int which, unsigned int id, int left, int right, muchsalsa::Toggle const direction);
+  std::size_t size() const { return m_requests.size(); }
+
+private:
+  enum class Mode { e_IDLE, e_RECORD, e_REPLAY };
+  void begin(Mode mode);
+  void end();
+
+  Context                  &m_ctx;
+  Mode                      m_mode = Mode::e_IDLE;
+  std::vector<msgpu_seq_req> m_requests;
+  std::vector<uint64_t>     m_offsets;
+  std::vector<uint8_t>      m_status;
+  std::string               m_data;
+  std::size_t               m_cursor = 0;
+};
 
 } // namespace muchsalsa::gpu

@@ -8,7 +8,9 @@ What a maintainer would do by hand, done by script so that 
   2. the eight `T const *const` container element types libstdc++ rejects lose their inner const (the reference is
      built with libc++, which accepts them: src/main.cpp:211,212,247,486,495,541,597, kernel/cc.cpp:46; the
      `std::any_cast<Edge const *const>` of main.cpp:418 is legal and stays),
-  3. main() gets the INTEGRATION.md §2 change: with MUCHSALSA_GPU=<device> in the environment the two statements
+  3. main() gets the INTEGRATION.md §2 change (and, for the sequence fetches, the §6 change: MUCHSALSA_GPU_SEQ=1 loads
+     the two sequence files into the resident store and runs every assemblePath call as record -> one batched fetch ->
+     replay; the two getters of a COPY of SequenceUtils.cpp forward to the active batch — oracle/binary_patch/*.inc): with MUCHSALSA_GPU=<device> in the environment the two statements
      `blastFileReader.read(); matchMap.calculateEdges();` (src/main.cpp:156-157) are replaced by
      `muchsalsa::gpu::constructGraph(...)`; with MUCHSALSA_GPU_STAGES=1 in addition the job loops over
      chainingAndOverlaps / findContractionEdges / findDeletableEdges / computeBitweight (src/main.cpp:170-191,
@@ -89,6 +91,39 @@ def patch_main(src: str) -> str:
     return src
 
 
+def _inc(name: str) -> str:
+    return open(os.path.join(HERE, "binary_patch", name)).read()
+
+
+def patch_sequence_utils(src: str) -> str:
+    """while a SequenceBatch is active on the calling thread, the two getters forward to it."""
+    assert '#include "SequenceUtils.h"' in src
+    src = src.replace('#include "SequenceUtils.h"', '#include "SequenceUtils.h"\n\n#include "ms_gpu_shim.h"', 1)
+    for which, name in ((0, "getIlluminaSequence"), (1, "getNanoporeSequence")):
+        m = re.search(r"std::string muchsalsa::%s\(([^)]*)\)\s*\{\n" % name, src)
+        assert m, f"{name} has moved"
+        args = [a.strip().split()[-1].lstrip("&*") for a in m.group(1).split(",")]  # parameter names, in order
+        call = ("  if (auto *const pBatch = muchsalsa::gpu::SequenceBatch::active()) {\n"
+                f"    return pBatch->get({which}U, {args[1]}, {args[2]}, {args[3]}, {args[4]});\n  }}\n")
+        src = src[:m.end()] + call + src[m.end():]
+    return src
+
+
+def patch_main_sequences(src: str) -> str:
+    """MUCHSALSA_GPU_SEQ=1 (with MUCHSALSA_GPU): the sequence files go to the resident store and every assemblePath call
+    fetches what it needs as ONE batch (record pass -> msgpu_seq_fetch_batch -> replay pass; SequenceBatch)."""
+    old = "    sequenceAccessor.buildIndex();\n"
+    assert old in src
+    src = src.replace(old, old + _inc("load_sequences_gpu.inc"), 1)
+    decl = "void assemblePathsSub(gsl::not_null<Job const *> pJob);"
+    assert decl in src
+    src = src.replace(decl, decl + "\n\n#include <cstdio>\nstatic muchsalsa::gpu::Context *g_pGpuSeqCtx = nullptr; "
+                                  "// set when the sequence store is on the GPU", 1)
+    old = "    Id2OverlapMap id2OverlapMap;\n    muchsalsa::assemblePath(\n          &id2OverlapMap,\n"
+    assert old in src
+    return src.replace(old, _inc("assemble_sub_gpu.inc"), 1)
+
+
 def main():
     build = os.environ.get("MSBIN_BUILD", "/tmp/msbin_build")
     os.makedirs(build, exist_ok=True)
@@ -96,7 +131,10 @@ def main():
     subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)  # the reference's objects + the shim object
     for f in ("Application.cpp", "Application.h", "TrackingAllocator.cpp", "TrackingAllocator.h"):
         open(os.path.join(build, f), "w").write(open(os.path.join(REF, "src", f)).read())
-    open(os.path.join(build, "main.cpp"), "w").write(patch_main(open(os.path.join(REF, "src", "main.cpp")).read()))
+    open(os.path.join(build, "main.cpp"), "w").write(
+        patch_main_sequences(patch_main(open(os.path.join(REF, "src", "main.cpp")).read())))
+    open(os.path.join(build, "SequenceUtils.cpp"), "w").write(
+        patch_sequence_utils(open(os.path.join(REF, "libms", "src", "SequenceUtils.cpp")).read()))
     cc = open(os.path.join(REF, "libms", "src", "kernel", "cc.cpp")).read()
     cc, n = re.subn(r"(std::deque<muchsalsa::graph::Vertex const \*)const>", r"\1>", cc)
     assert n == 1
@@ -107,7 +145,8 @@ def main():
              f"-I{REF}/include", f"-I{REF}/include/ms", f"-I{PKG}/host", f"-I{ROOT}/include", f"-I{build}"]
     objs = []
     units = [(os.path.join(build, f), f.replace(".cpp", ".o")) for f in ("main.cpp", "Application.cpp",
-                                                                          "TrackingAllocator.cpp", "cc.cpp")]
+                                                                          "TrackingAllocator.cpp", "cc.cpp",
+                                                                          "SequenceUtils.cpp")]
     units += [(os.path.join(REF, "libms", "src", u + ".cpp"), "bin_" + u.replace("/", "_") + ".o")
               for u in ("kernel/mst", "kernel/dg", "kernel/lg", "kernel/ap", "OutputWriter", "Kernel", "Util")]
     procs = []
@@ -118,7 +157,7 @@ def main():
     if any(p.wait() for p in procs):
         raise SystemExit("compilation failed")
     ref_objs = [os.path.join(OUT, "obj", f) for f in sorted(os.listdir(os.path.join(OUT, "obj")))
-                if f.endswith(".o") and f not in ("ref_driver.o",)]
+                if f.endswith(".o") and f not in ("ref_driver.o", "SequenceUtils.o")]  # (the patched copy replaces it)
     exe = os.path.join(OUT, "muchsalsa")
     subprocess.run([cxx, "-pthread", "-o", exe, *objs, *ref_objs, f"-L{PKG}", "-lmsgpu",
                     "-Wl,-rpath,$ORIGIN/../../muchsalsa_b200"], check=True)

@@ -51,7 +51,7 @@ def canonical(out_dir) -> dict:
 def _run(tmp_path, tag, env_extra):
     out = tmp_path / f"out_{tag}"
     out.mkdir()
-    env = {k: v for k, v in os.environ.items() if k not in ("MUCHSALSA_GPU", "MUCHSALSA_GPU_STAGES")}
+    env = {k: v for k, v in os.environ.items() if not k.startswith("MUCHSALSA_GPU")}
     env.update(env_extra)
     p = subprocess.run([EXE, str(tmp_path / "in.paf"), str(tmp_path / "unitigs.fa"), str(tmp_path / "nanopore.fa"),
                         str(out), "1"], capture_output=True, text=True, env=env, timeout=1200)
@@ -72,13 +72,21 @@ def test_cpu_path_of_the_binary_gives_a_recorded_outcome(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("stages", [False, True])
-def test_binary_output_with_the_gpu_path_is_an_outcome_of_the_cpu_path(tmp_path, stages):
+@pytest.mark.parametrize("mode", ["construction", "stages", "sequences", "everything"])
+def test_binary_output_with_the_gpu_path_is_an_outcome_of_the_cpu_path(tmp_path, mode):
+    """construction: main.cpp:156-157 on the GPU.  stages: also the job loops over chainingAndOverlaps /
+    findContractionEdges / findDeletableEdges / computeBitweight.  sequences: also the sequence store resident in HBM
+    and every assemblePath call fetching its sequences as ONE batch (record -> msgpu_seq_fetch_batch -> replay,
+    SURVEY.md §8 f2).  everything: all of them."""
     assert os.path.exists(EXE), "oracle/_ref/muchsalsa missing: run python oracle/make_binary.py in the build container"
     _inputs(tmp_path, "small")
     known = {tuple(v) for v in util.load_golden("binary_small.json")["outcomes"]}
     known |= {_key(_run(tmp_path, f"cpu{i}", {})) for i in range(3)}
-    env = {"MUCHSALSA_GPU": "0", **({"MUCHSALSA_GPU_STAGES": "1"} if stages else {})}
+    env = {"MUCHSALSA_GPU": "0"}
+    if mode in ("stages", "everything"):
+        env["MUCHSALSA_GPU_STAGES"] = "1"
+    if mode in ("sequences", "everything"):
+        env["MUCHSALSA_GPU_SEQ"] = "1"
     for i in range(3):
         got = _run(tmp_path, f"gpu{i}", env)
         assert got["target_bytes"] > 1_000_000  # 20 contigs, 1.39 Mbp of a 1.5 Mbp genome
