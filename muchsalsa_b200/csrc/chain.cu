@@ -108,9 +108,14 @@ struct ChainArgs {
   EdgeTables      e;
   uint64_t        wiggle;
   OrderTables     out;
-  unsigned int   *too_long;
   uint32_t       *list_in, *list_out; // edges handed from one launch to the next
   unsigned int   *n_in, *n_out;
+  // edges with more edge matches of one direction than the largest fast instantiation holds: listed by chain_large,
+  // done by chain_huge with their state in a global scratch slab
+  uint32_t           *huge_list;
+  unsigned int       *n_huge;
+  unsigned long long *huge_em, *huge_cursor;
+  char               *huge_scratch;
 };
 
 struct Vm { // the fields of one VertexMatch the stage reads
@@ -233,7 +238,7 @@ struct EmState { // per edge match of the direction being chained
   int    r1a, r1b, r2a, r2b; // nanoporeRange on the first / second vertex
   double score;
   uint32_t unitig;
-  uint16_t k; // row of the edge match inside its edge
+  uint32_t k; // row of the edge match inside its edge
   bool   prim;
 };
 
@@ -258,23 +263,81 @@ __device__ __forceinline__ void overhangs(const ChainArgs &a, uint32_t vertex, u
   *right = __dadd_rn(double(a.read_nlen[vertex] - v.nr1), ncr);
 }
 
-// the whole job of one edge, with state arrays of kCap entries per direction
-template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainArgs &a, uint64_t e) {
+// State of the per-edge programme.  kCap > 0: arrays of kCap entries per direction in the thread's local memory (the
+// fast instantiations).  kCap == 0: the same arrays carved out of a global scratch slab, sized by the edge itself —
+// the fallback for edges with more edge matches of one direction than the largest fast instantiation holds (two long
+// reads that share hundreds of unitigs), so that no input the reference accepts is refused.
+template <int kCap> struct ChainStore {
+  PathRes            res[2 * kCap];
+  EmState            st[kCap];
+  double             pop[kCap];
+  int                pred[kCap];
+  uint32_t           path_rows[2 * kCap];
+  int                path_off[2 * (kCap + 1)];
+  bool               keep[2 * kCap];
+  unsigned long long used[(kCap + 63) / 64];
+  __device__ __forceinline__ int  cap() const { return kCap; }
+  __device__ __forceinline__ void bind(char *, int) {}
+};
+template <> struct ChainStore<0> {
+  PathRes            *res;
+  EmState            *st;
+  double             *pop;
+  int                *pred;
+  uint32_t           *path_rows;
+  int                *path_off;
+  bool               *keep;
+  unsigned long long *used;
+  int                 n;
+  __device__ __forceinline__ int cap() const { return n; }
+  __host__ __device__ static size_t bytes(size_t cap) { // every section 8-byte aligned
+    auto up = [](size_t x) { return (x + 7) & ~size_t(7); };
+    return up(2 * cap * sizeof(PathRes)) + up(cap * sizeof(EmState)) + up(cap * sizeof(double)) + up(cap * sizeof(int)) +
+           up(2 * cap * sizeof(uint32_t)) + up(2 * (cap + 1) * sizeof(int)) + up(2 * cap) + up(((cap + 63) / 64) * 8);
+  }
+  __device__ __forceinline__ void bind(char *p, int cap) {
+    auto up = [](size_t x) { return (x + 7) & ~size_t(7); };
+    n   = cap;
+    res = reinterpret_cast<PathRes *>(p);
+    p += up(2 * size_t(cap) * sizeof(PathRes));
+    st = reinterpret_cast<EmState *>(p);
+    p += up(size_t(cap) * sizeof(EmState));
+    pop = reinterpret_cast<double *>(p);
+    p += up(size_t(cap) * sizeof(double));
+    pred = reinterpret_cast<int *>(p);
+    p += up(size_t(cap) * sizeof(int));
+    path_rows = reinterpret_cast<uint32_t *>(p);
+    p += up(2 * size_t(cap) * sizeof(uint32_t));
+    path_off = reinterpret_cast<int *>(p);
+    p += up(2 * (size_t(cap) + 1) * sizeof(int));
+    keep = reinterpret_cast<bool *>(p);
+    p += up(2 * size_t(cap));
+    used = reinterpret_cast<unsigned long long *>(p);
+  }
+};
+
+// the whole job of one edge, with state arrays of kCap entries per direction (kCap == 0: of as many as the edge has
+// edge matches, in `scratch`)
+template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainArgs &a, uint64_t e, char *scratch = nullptr) {
   {
     const uint32_t v1 = a.e.first[e], v2 = a.e.second[e];
     const uint64_t k0 = a.e.em_begin[e], k1 = a.e.em_begin[e + 1];
 
+    ChainStore<kCap> S;
+    S.bind(scratch, int(k1 - k0));
+    const int cap = S.cap();
     // results of the two directions: [0] minus (direction false), [1] plus; main.cpp:352-353
-    PathRes  res[2][kCap];
-    int      n_res[2] = {0, 0};
-    EmState  st[kCap];
-    double   pop[kCap];
-    int      pred[kCap];
+    PathRes            *res  = S.res;       // res[d * cap + r]
+    int                 n_res[2] = {0, 0};
+    EmState            *st   = S.st;
+    double             *pop  = S.pop;
+    int                *pred = S.pred;
     // path members per (direction, population entry) are re-derived by walking `pred`; after the first direction is
     // done its paths are frozen as lists of edge-match rows
-    uint32_t path_rows[2][kCap]; // concatenated paths of the results of a direction, in result order
-    int      path_off[2][kCap + 1];
-    bool     overflow = false;
+    uint32_t           *path_rows = S.path_rows; // [d * cap + i]: concatenated paths of a direction, in result order
+    int                *path_off  = S.path_off;  // [d * (cap + 1) + r]
+    unsigned long long *used      = S.used;
+    bool                overflow  = false;
 
     for (int d = 0; d < 2; ++d) {
       const bool direction = d == 1;
@@ -282,12 +345,12 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
       int n = 0;
       for (uint64_t k = k0; k < k1; ++k) {
         if (((a.e.em_flags[k] & 1) != 0) != direction) continue;
-        if (n == kCap) {
+        if (n == cap) {
           overflow = true;
           break;
         }
         EmState s;
-        s.k      = uint16_t(k - k0);
+        s.k      = uint32_t(k - k0);
         s.unitig = a.e.em_unitig[k];
         s.score  = a.e.em_score[k];
         s.prim   = (a.e.em_flags[k] & 2) != 0;
@@ -311,7 +374,7 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
         st[p] = s;
         ++n;
       }
-      path_off[d][0] = 0;
+      path_off[d * (cap + 1)] = 0;
       if (overflow) break;
       if (n == 0) continue; // mpp.cpp:151-153
 
@@ -356,8 +419,8 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
           max_it  = i;
           max_val = pop[i];
         }
-      unsigned long long used[2] = {0ull, 0ull}; // population entries on any accepted path (kCap <= 128)
-      int                nr = 0;
+      for (int i = 0; i < (n + 63) / 64; ++i) used[i] = 0ull; // population entries on any accepted path
+      int nr = 0;
       {
         bool prim = false;
         int  len  = 0;
@@ -366,7 +429,7 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
           used[i >> 6] |= 1ull << (i & 63);
           ++len;
         }
-        res[d][nr++] = PathRes{max_it, max_val, prim || len > 2};
+        res[d * cap + nr++] = PathRes{max_it, max_val, prim || len > 2};
       }
       const double threshold = __dmul_rn(max_val, 0.75);
       for (int j = 0; j < n; ++j) {
@@ -378,11 +441,11 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
         }
         if (!disjoint) continue;
         for (int i = j; i >= 0; i = pred[i]) used[i >> 6] |= 1ull << (i & 63);
-        res[d][nr++] = PathRes{j, pop[j], prim};
+        res[d * cap + nr++] = PathRes{j, pop[j], prim};
       }
 
       // ---- a single primary path may still be a shadow (mpp.cpp:245-302)
-      if (nr == 1 && res[d][0].prim) {
+      if (nr == 1 && res[d * cap].prim) {
         const uint32_t s0 = a.rm_off[v1], s1 = a.rm_off[v1 + 1], e0 = a.rm_off[v2], e1 = a.rm_off[v2 + 1];
         auto start_id = [&](uint32_t i) { return a.rm_unitig[s0 + i]; };
         auto end_id   = [&](uint32_t i) { // vIDsEnd, reversed when !direction (mpp.cpp:273)
@@ -391,17 +454,17 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
         const uint32_t ns = s1 - s0, ne = e1 - e0;
         // the path in order: walk back from the tail, then read it forwards
         int plen = 0;
-        for (int i = res[d][0].tail; i >= 0; i = pred[i]) ++plen;
-        uint32_t front_id = 0, back_id = st[res[d][0].tail].unitig;
-        for (int i = res[d][0].tail; i >= 0; i = pred[i]) front_id = st[i].unitig;
+        for (int i = res[d * cap].tail; i >= 0; i = pred[i]) ++plen;
+        uint32_t front_id = 0, back_id = st[res[d * cap].tail].unitig;
+        for (int i = res[d * cap].tail; i >= 0; i = pred[i]) front_id = st[i].unitig;
         if ((start_id(0) != front_id && end_id(0) != front_id) ||
             (start_id(ns - 1) != back_id && end_id(ne - 1) != back_id)) {
-          res[d][0].prim = false;
+          res[d * cap].prim = false;
         } else {
           uint32_t i = 0, j = 0;
           bool     is_shadow = false;
           for (int step = 0; step < plen && !is_shadow; ++step) {
-            int node = res[d][0].tail; // the step-th element of the path
+            int node = res[d * cap].tail; // the step-th element of the path
             for (int back = plen - 1 - step; back > 0; --back) node = pred[node];
             const uint32_t id = st[node].unitig;
             uint32_t       ps = i;
@@ -414,7 +477,7 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
             j = pe + 1;
             is_shadow = inter;
           }
-          if (is_shadow) res[d][0].prim = false;
+          if (is_shadow) res[d * cap].prim = false;
         }
       }
       n_res[d] = nr;
@@ -423,44 +486,45 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
       int w = 0;
       for (int r = 0; r < nr; ++r) {
         int len = 0;
-        for (int i = res[d][r].tail; i >= 0; i = pred[i]) ++len;
+        for (int i = res[d * cap + r].tail; i >= 0; i = pred[i]) ++len;
         int pos = w + len;
-        for (int i = res[d][r].tail; i >= 0; i = pred[i]) path_rows[d][--pos] = st[i].k;
+        for (int i = res[d * cap + r].tail; i >= 0; i = pred[i]) path_rows[d * cap + --pos] = st[i].k;
         w += len;
-        path_off[d][r + 1] = w;
-        res[d][r].tail     = len; // from here on: the path length
+        path_off[d * (cap + 1) + r + 1] = w;
+        res[d * cap + r].tail           = len; // from here on: the path length
       }
     }
-    if (overflow) {
-      *a.too_long            = 1;
+    if (overflow) { // more edge matches of one direction than this instantiation holds: the fallback takes the edge
+      a.huge_list[atomicAdd(a.n_huge, 1u)] = uint32_t(e);
+      atomicAdd(a.huge_em, (unsigned long long)(k1 - k0));
       a.out.edge_n_orders[e] = 0;
       a.out.edge_shadow[e]   = 0;
       return;
     }
 
     // ---- chainingAndOverlaps' selection (main.cpp:355-397); keep[] marks the paths that survive
-    bool keep[2][kCap];
-    bool has_primary = false, has_multi = false;
+    bool *keep = S.keep; // keep[d * cap + r]
+    bool  has_primary = false, has_multi = false;
     for (int d = 0; d < 2; ++d)
       for (int r = 0; r < n_res[d]; ++r) {
-        keep[d][r] = true;
-        has_primary |= res[d][r].prim;
+        keep[d * cap + r] = true;
+        has_primary |= res[d * cap + r].prim;
       }
     if (has_primary)
       for (int d = 0; d < 2; ++d)
-        for (int r = 0; r < n_res[d]; ++r) keep[d][r] = res[d][r].prim;
+        for (int r = 0; r < n_res[d]; ++r) keep[d * cap + r] = res[d * cap + r].prim;
     for (int d = 0; d < 2; ++d)
-      for (int r = 0; r < n_res[d]; ++r) has_multi |= keep[d][r] && res[d][r].tail > 1;
+      for (int r = 0; r < n_res[d]; ++r) has_multi |= keep[d * cap + r] && res[d * cap + r].tail > 1;
     if (has_multi)
       for (int d = 0; d < 2; ++d)
-        for (int r = 0; r < n_res[d]; ++r) keep[d][r] = keep[d][r] && res[d][r].tail > 1;
+        for (int r = 0; r < n_res[d]; ++r) keep[d * cap + r] = keep[d * cap + r] && res[d * cap + r].tail > 1;
     int  combined = 0;
     bool first_prim = false, have_first = false;
     for (int d = 0; d < 2; ++d) // minus first: `!minusPaths.empty() ? minusPaths[0] : plusPaths[0]`
       for (int r = 0; r < n_res[d]; ++r)
-        if (keep[d][r]) {
+        if (keep[d * cap + r]) {
           if (!have_first) {
-            first_prim = res[d][r].prim;
+            first_prim = res[d * cap + r].prim;
             have_first = true;
           }
           ++combined;
@@ -472,9 +536,9 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
     for (int d = 0; d < 2; ++d) {
       const bool direction = d == 1;
       for (int r = 0; r < n_res[d]; ++r) {
-        if (!keep[d][r]) continue;
-        const int      len = res[d][r].tail;
-        const uint32_t *pr = path_rows[d] + path_off[d][r];
+        if (!keep[d * cap + r]) continue;
+        const int      len = res[d * cap + r].tail;
+        const uint32_t *pr = path_rows + d * cap + path_off[d * (cap + 1) + r];
         const uint64_t kf = k0 + pr[0], kl = k0 + pr[len - 1]; // first / last id of the path
         double lf1, rf1, ll1, rl1, lf2, rf2, ll2, rl2; // overhangs of (first id | last id) on (first | second vertex)
         overhangs(a, v1, a.em_row1[kf], a.e.em_ov0[kf], a.e.em_ov1[kf], &lf1, &rf1);
@@ -512,10 +576,10 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
         const uint64_t slot = k0 + n_ord;
         a.out.left[slot]  = left;
         a.out.right[slot] = right;
-        a.out.score[slot] = double_to_size_t(res[d][r].score);
+        a.out.score[slot] = double_to_size_t(res[d * cap + r].score);
         a.out.n_ids[slot] = uint32_t(len);
         a.out.flags[slot] = uint8_t((start_first ? 1 : 0) | (contained ? 2 : 0) | (direction ? 4 : 0) |
-                                    (res[d][r].prim ? 8 : 0));
+                                    (res[d * cap + r].prim ? 8 : 0));
         for (int i = 0; i < len; ++i) a.out.ids[k0 + id_w + i] = a.e.em_unitig[k0 + pr[i]];
         id_w += uint32_t(len);
         ++n_ord;
@@ -617,6 +681,17 @@ template <int kCap, bool kHandOn> __global__ void __launch_bounds__(128) chain_l
   }
 }
 
+// the fallback: one thread per listed edge, state arrays sized by the edge in the scratch slab (slow — the dynamic
+// programme is quadratic in the edge matches of a direction and runs on one thread — but nothing is refused)
+__global__ void __launch_bounds__(64) chain_huge_kernel(ChainArgs a, uint32_t n_huge) {
+  for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < n_huge; x += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t e   = a.huge_list[x];
+    const uint64_t n   = a.e.em_begin[e + 1] - a.e.em_begin[e];
+    const uint64_t off = atomicAdd(a.huge_cursor, (unsigned long long)ChainStore<0>::bytes(n));
+    chain_one_edge<0>(a, e, a.huge_scratch + off);
+  }
+}
+
 void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, const UnitigTable &unitigs,
                         const MatchSoA &m, const EdgeTables &e, uint64_t wiggle_room, OrderTables &out, float *ms_out) {
   out = OrderTables{};
@@ -669,6 +744,10 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
   uint32_t     *multi = arena.alloc<uint32_t>(E), *big = arena.alloc<uint32_t>(E);
   unsigned int *d_cnt = arena.alloc<unsigned int>(4);
   MSGPU_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned int), st));
+  // an edge reaches the fallback only with more than kChainMax edge matches, so at most EM / (kChainMax + 1) edges do
+  uint32_t           *huge_list = arena.alloc<uint32_t>(EM / (kChainMax + 1) + 1);
+  unsigned long long *d_huge    = arena.alloc<unsigned long long>(4); // [0] edges listed [1] their edge matches [2] cursor
+  MSGPU_CUDA(cudaMemsetAsync(d_huge, 0, 4 * sizeof(unsigned long long), st));
 
   ChainArgs a;
   a.read_nlen = reads.nlen;
@@ -682,7 +761,11 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
   a.e         = e;
   a.wiggle    = wiggle_room;
   a.out       = out;
-  a.too_long  = d_tot + 1;
+  a.huge_list    = huge_list;
+  a.n_huge       = reinterpret_cast<unsigned int *>(d_huge);
+  a.huge_em      = d_huge + 1;
+  a.huge_cursor  = d_huge + 2;
+  a.huge_scratch = nullptr;
   if (E) {
     a.list_in  = nullptr;
     a.n_in     = nullptr;
@@ -706,16 +789,20 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
     a.n_out    = nullptr;
     MSGPU_LAUNCH("chain_large", st, (chain_list_kernel<kChainMax, false><<<grid_for(E, 128, 4), 128, 0, st>>>(a)));
   }
+  unsigned long long *h_huge = static_cast<unsigned long long *>(arena.host_scratch());
+  MSGPU_CUDA(cudaMemcpyAsync(h_huge, d_huge, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaStreamSynchronize(st));
+  const uint32_t n_huge = uint32_t(h_huge[0] & 0xffffffffull);
+  if (n_huge) { // rare: edges beyond the fast instantiations, one thread each over a scratch slab sized by the edges
+    const uint64_t huge_em = h_huge[1];
+    a.huge_scratch = arena.alloc<char>(152 * huge_em + 128 * uint64_t(n_huge));
+    MSGPU_LAUNCH("chain_huge", st, chain_huge_kernel<<<grid_for(n_huge, 64, 8), 64, 0, st>>>(a, n_huge));
+  }
   MSGPU_CUDA(cudaEventRecord(ev1, st));
-  uint32_t h[2];
-  MSGPU_CUDA(cudaMemcpyAsync(h, d_tot, sizeof(h), cudaMemcpyDeviceToHost, st));
   MSGPU_CUDA(cudaStreamSynchronize(st));
   if (ms_out) MSGPU_CUDA(cudaEventElapsedTime(ms_out, ev0, ev1));
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
-  if (h[1])
-    throw BuildError{MSGPU_ERR_LIMIT, "an edge holds more than " + std::to_string(kChainMax) +
-                                          " edge matches of one direction (chaining supports up to that many)"};
   out.valid = true;
 }
 

@@ -222,6 +222,10 @@ namespace {
 thread_local SequenceBatch *t_pActiveBatch = nullptr;
 }
 
+std::string SequenceBatch::keyOf(msgpu_seq_req const &req) {
+  return std::string(reinterpret_cast<char const *>(&req), sizeof(req)); // five 32-bit words, no padding
+}
+
 SequenceBatch *SequenceBatch::active() { return t_pActiveBatch; }
 
 SequenceBatch::~SequenceBatch() {
@@ -248,6 +252,8 @@ void SequenceBatch::fetch() {
   uint64_t bound = 0;
   if (int rc = msgpu_seq_batch_bound(m_ctx.get(), m_requests.data(), n, &bound); rc != MSGPU_OK) raise(m_ctx.get(), rc);
   m_data.assign(bound, '\0');
+  m_index.clear();
+  for (std::size_t i = 0; i < n; ++i) m_index.emplace(keyOf(m_requests[i]), i);
   if (n == 0) return;
   if (int rc = msgpu_seq_fetch_batch(m_ctx.get(), m_requests.data(), n, m_data.data(), bound, m_offsets.data(),
                                      m_status.data());
@@ -264,13 +270,15 @@ std::string SequenceBatch::get(unsigned int which, unsigned int id, int left, in
     m_requests.push_back(req);
     return std::string(bytes, 'N');
   }
-  if (m_mode != Mode::e_REPLAY || m_cursor >= m_requests.size())
-    throw std::logic_error("SequenceBatch: replay asked for more sequences than were recorded");
-  auto const &rec = m_requests[m_cursor];
-  if (rec.which != req.which || rec.id != req.id || rec.left != req.left || rec.right != req.right ||
-      rec.direction != req.direction)
-    throw std::logic_error("SequenceBatch: the replay pass diverged from the recorded pass");
-  auto const i = m_cursor++;
+  if (m_mode != Mode::e_REPLAY) throw std::logic_error("SequenceBatch: get() outside record / replay");
+  // Served by KEY, not by position: assemblePath walks containers keyed by pointers to objects it allocates itself
+  // (its anchor graph), so two passes over the same path can ask for the same sequences in a different order.
+  auto const it = m_index.find(keyOf(req));
+  if (it == m_index.end()) { // not seen while recording (cannot happen for a pure function of the lengths): fetch it now
+    ++m_misses;
+    return fetchOne(m_ctx, which, id, left, right, direction);
+  }
+  auto const i = it->second;
   if (m_status[i] != 0) raise(m_ctx.get(), m_status[i] == 1 ? MSGPU_ERR_IO : MSGPU_ERR_OUT_OF_RANGE);
   return m_data.substr(m_offsets[i], m_offsets[i + 1] - m_offsets[i]);
 }

@@ -88,7 +88,9 @@ std::string getNanoporeSequence(Context &ctx, unsigned int nanoporeId, int nanop
 //           lengths come from the index, no sequence byte is touched) while every request is logged; the pass writes
 //           to a null OutputWriter and a scratch Id2OverlapMap, its other arguments are const;
 //   fetch   ONE msgpu_seq_fetch_batch for everything the path needs;
-//   replay  with the getters handing out the fetched sequences in the recorded order — this pass produces the output.
+//   replay  with the getters handing out the fetched sequences, looked up by request (assemblePath iterates containers
+//           keyed by pointers to objects it allocates itself, so two passes may ask in a different order) — this pass
+//           produces the output.
 // While a batch is active on a thread (thread-local, like the reference's per-job state), the two getters of
 // SequenceUtils.cpp:63-85 forward to it: the two-line change INTEGRATION.md §6 shows.
 class SequenceBatch {
@@ -123,6 +125,7 @@ public:
   // what the getters call while the batch is active (which: 0 = unitig / illumina, 1 = nanopore)
   std::string get(unsigned int which, unsigned int id, int left, int right, muchsalsa::Toggle const direction);
   std::size_t size() const { return m_requests.size(); }
+  std::size_t misses() const { return m_misses; } // replayed requests that had not been recorded (fetched singly)
 
 private:
   enum class Mode { e_IDLE, e_RECORD, e_REPLAY };
@@ -135,7 +138,9 @@ private:
   std::vector<uint64_t>     m_offsets;
   std::vector<uint8_t>      m_status;
   std::string               m_data;
-  std::size_t               m_cursor = 0;
+  std::size_t               m_cursor = 0, m_misses = 0;
+  std::unordered_map<std::string, std::size_t> m_index; // request -> position in the batch
+  static std::string keyOf(msgpu_seq_req const &req);
 };
 
 } // namespace muchsalsa::gpu

@@ -64,3 +64,26 @@ def test_chain_needs_a_construction(reference):
         with pytest.raises(MsGpuError) as e:
             gb.chain_overlaps()
         assert e.value.status == 7
+
+
+def long_shared_reads_paf(n_unitigs=150):
+    """Two long reads that share `n_unitigs` unitigs (a third shares most of them on the other strand): one edge holds
+    more edge matches of ONE direction than the largest fast instantiation of the per-edge programme (96)."""
+    L = util.paf_line
+    rows = []
+    for u in range(n_unitigs):
+        a = u * 2600
+        rows.append(L(f"u{u}", 2400, 0, 2200, "+", "longA", 500000, a + 100, a + 2300, 2100))
+        rows.append(L(f"u{u}", 2400, 100, 2400, "+", "longB", 480000, a + 40, a + 2340, 2150))
+        if u % 5 != 0:
+            rows.append(L(f"u{u}", 2400, 50, 2300, "-", "longC", 470000, 460000 - a, 462250 - a, 2000))
+    return b"".join(rows) + L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
+
+
+def test_chain_edge_with_more_matches_than_the_fast_paths_hold(builder, reference):
+    """The reference chains any number of shared unitigs (mpp.cpp:145-305 works on vectors); edges beyond the 96-entry
+    instantiation go to the fallback whose state lives in a global scratch slab — same orders, bit for bit."""
+    paf = long_shared_reads_paf()
+    got, want = _gpu_orders(builder, paf), reference.chain(paf)
+    assert orders_equal(got, want) == []
+    assert int(np.diff(got.ids_begin.astype(np.int64)).max()) > 96  # a path longer than the old limit
