@@ -96,6 +96,8 @@ struct PairPlan {
   const uint32_t *grp_off = nullptr, *rd_off = nullptr, *rd_src = nullptr, *tile_row = nullptr, *tile_kind = nullptr;
   const uint64_t *slice_off = nullptr;
   const uint32_t *slices = nullptr;
+  const uint32_t *wide_list = nullptr; // tiles (sub-tiles of rows with 513 .. 4095 sources) for the wide instantiation
+  uint32_t        n_wide = 0;
   uint32_t       *flags = nullptr; // device: [2] a read with too many sources, [3] tile invariant violated
   uint64_t        n_reads = 0, n_pairs = 0;
   uint32_t        n_tiles = 0, tile_lo = 0, tile_hi = 0;

@@ -215,7 +215,7 @@ bool next_chunk(msgpu_ctx *ctx, EdgeTables &e, uint64_t *index, bool *last) {
   MSGPU_CUDA(cudaEventSynchronize(c.rows_done));
   const uint32_t           *h_flags = reinterpret_cast<const uint32_t *>(h);
   const unsigned long long *h_tot   = reinterpret_cast<const unsigned long long *>(h + 64);
-  if (h_flags[2]) throw BuildError{MSGPU_ERR_LIMIT, "a read matches more than 512 unitigs with partners"};
+  if (h_flags[2]) throw BuildError{MSGPU_ERR_LIMIT, "a read shares 4096 or more unitigs with other reads"};
   if (h_flags[3]) throw BuildError{MSGPU_ERR_INTERNAL, "pairing: tile invariant violated (code " + std::to_string(h_flags[3]) + ")"};
   e         = c.out[b];
   e.n_em    = h_tot[0];

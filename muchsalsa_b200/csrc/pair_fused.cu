@@ -53,15 +53,13 @@ constexpr int      kFusedWarps = kFusedBlock / 32;
 #endif
 constexpr int      kIdxBits    = MSGPU_IDX_BITS;
 constexpr uint32_t kTileCap    = 1u << kIdxBits; // candidates per tile
-constexpr uint32_t kSrcCap     = 512;            // sources per tile
+constexpr uint32_t kSrcCap     = 512;            // sources per tile (the product instantiation of the tile kernel)
+constexpr int      kSrcBitsWide = 12;            // ... of the instantiation for rows with more sources: up to 4095 — an
+constexpr uint32_t kSrcCapWide = 1u << kSrcBitsWide; // edge cannot hold more edge matches than a tile holds candidates
 constexpr uint32_t kHalfCap    = kTileCap / 2;
 constexpr uint32_t kSrcRatio   = kHalfCap / (kSrcCap / 2); // a source weighs at least this much when tiles are packed
 constexpr int      kItems      = kTileCap / kFusedBlock;   // sort items per thread
 constexpr int      kMergeCtas  = kIdxBits <= 12 ? 4 : 2;    // resident CTAs of the merge kernel per SM (narrow words)
-#ifndef MSGPU_FUSED_CTAS
-#define MSGPU_FUSED_CTAS 3
-#endif
-constexpr int      kFusedCtas  = MSGPU_FUSED_CTAS;          // ... of the fused kernel (its emission phase needs registers)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // pre-pass 1: order every group by read id, build the pair rows, and accumulate per read its number of sources and
@@ -287,12 +285,19 @@ struct ClippedWeight {
 struct TileCount {
   RowPlan         p;
   const uint64_t *prefix;
+  unsigned int   *n_wide; // out: sub-tiles of rows with more sources than the product tile kernel stages (the scan
+                          // evaluates every row exactly once, so the count rides along)
   __device__ bool start(uint64_t r) const {
     if (r == 0) return true;
     if (prefix[r] / kHalfCap != prefix[r - 1] / kHalfCap) return true;
     return p.heavy(r - 1);
   }
-  __device__ uint32_t operator()(uint64_t r) const { return p.heavy(r) ? p.n_sub(r) : (start(r) ? 1u : 0u); }
+  __device__ uint32_t operator()(uint64_t r) const {
+    if (!p.heavy(r)) return start(r) ? 1u : 0u;
+    const uint32_t ns = p.n_sub(r);
+    if (p.deg[r] > kSrcCap && p.deg[r] < kSrcCapWide) atomicAdd(n_wide, ns);
+    return ns;
+  }
 };
 
 // slice table entries of a heavy row: (n_sub + 1) boundaries x deg sources
@@ -311,16 +316,21 @@ struct WeightOf {
 __global__ void __launch_bounds__(256)
     write_tiles_kernel(TileCount tc, const uint32_t *__restrict__ tile_idx, uint64_t n_reads, uint32_t n_tiles,
                        uint32_t *__restrict__ tile_row, uint32_t *__restrict__ tile_kind,
-                       uint32_t *__restrict__ too_many_sources) {
+                       uint32_t *__restrict__ too_many_sources, uint32_t *__restrict__ wide_list,
+                       unsigned int *__restrict__ wide_cursor) {
   for (uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n_reads;
        r += uint64_t(gridDim.x) * blockDim.x) {
-    if (tc.p.deg[r] > kSrcCap) *too_many_sources = 1;
+    if (tc.p.deg[r] >= kSrcCapWide) *too_many_sources = 1; // an edge of such a row could outgrow a tile
     uint32_t t = tile_idx[r];
     if (tc.p.heavy(r)) {
       uint32_t ns = tc.p.n_sub(r);
       for (uint32_t j = 0; j < ns; ++j) {
         tile_row[t + j]  = uint32_t(r);
         tile_kind[t + j] = 1 + j;
+      }
+      if (tc.p.deg[r] > kSrcCap && tc.p.deg[r] < kSrcCapWide) { // its sub-tiles go to the many-sources instantiation
+        const uint32_t w = atomicAdd(wide_cursor, ns);
+        for (uint32_t j = 0; j < ns; ++j) wide_list[w + j] = t + j;
       }
     } else if (tc.start(r)) {
       tile_row[t]  = uint32_t(r);
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(256)
     const uint32_t kind = tile_kind[wi];
     if (kind == 0) continue;
     const uint32_t r = tile_row[wi], j = kind - 1, d = plan.deg[r], ns = plan.n_sub(r);
-    if (d > kSrcCap) continue; // reported by write_tiles_kernel; the build fails with MSGPU_ERR_LIMIT
+    if (d >= kSrcCapWide) continue; // reported by write_tiles_kernel; the build fails with MSGPU_ERR_LIMIT
     const uint32_t q0 = rd_off[r];
     uint32_t      *out = slices + slice_off[r];
     const uint64_t target = uint64_t(j) * plan.sub_cap(r);
@@ -464,7 +474,8 @@ __global__ void __launch_bounds__(256)
 // K6/K7a: one CTA per tile — enumerate, sort in shared memory, find run heads, write the tile's compact records
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int      kSrcBits  = 9;       // kSrcCap == 1 << kSrcBits
-static_assert(kSrcCap == (1u << kSrcBits), "record packing");
+static_assert(kSrcCap == (1u << kSrcBits), "staging capacity");
+constexpr int      kRecSrcBits = kSrcBitsWide; // a record carries its source in this many bits, whichever kernel wrote it
 
 struct TileArgs {
   const PairRow  *rows;
@@ -476,7 +487,9 @@ struct TileArgs {
   const uint64_t *slice_off;
   const uint32_t *slices;
   uint32_t        tile_lo, tile_hi; // this launch processes tiles [tile_lo, tile_hi)
-  uint2          *records;          // per tile kTileCap slots: (partner row, source | head << 9 | heads before << 10)
+  uint2          *records;          // per tile kTileCap slots: (partner row, source | head << 12 | heads before << 13)
+  const uint32_t *wide_list;        // the instantiation for many sources: the tiles it takes (those inside the range)
+  uint32_t        n_wide;
   uint2          *tile_cnt;         // per tile: (surviving candidates, run heads)
   unsigned int   *error;
   uint32_t        wide; // 0: every sort word fits 32 bits for any tile, so the launch carries the small buffers only
@@ -493,32 +506,34 @@ struct TileArgs {
 // the diagonal of its first output, then a sequential two-way merge — a handful of instructions per element and
 // level, log2(slices per row) levels, one barrier per level.
 
-struct MergeStage { // the sources of the tile, staged in shared memory
-  uint32_t begin[kSrcCap];    // first partner row of the slice
-  uint32_t base[kSrcCap + 1]; // exclusive prefix of the slice lengths = first candidate slot of the slice
-  int32_t  ir0[kSrcCap], ir1[kSrcCap];
-  uint16_t row_first[kSrcCap], row_end[kSrcCap]; // the sources [row_first, row_end) belong to the same read (row)
+template <int kSB> struct MergeStage { // the sources of the tile, staged in shared memory (up to 1 << kSB of them)
+  static constexpr uint32_t kCap = 1u << kSB;
+  uint32_t begin[kCap];    // first partner row of the slice
+  uint32_t base[kCap + 1]; // exclusive prefix of the slice lengths = first candidate slot of the slice
+  int32_t  ir0[kCap], ir1[kCap];
+  uint16_t row_first[kCap], row_end[kCap]; // the sources [row_first, row_end) belong to the same read (row)
 };
 
-struct MergeShared { // everything but the two word buffers, which follow it in dynamic shared memory
-  uint16_t   ent_src[kTileCap]; // slot -> source whose slice owns the slot (| kDropped: failed the overlap test)
-  MergeStage src;
-  uint32_t   scan[33];
-  uint32_t   warp_tot[kFusedWarps];
-  uint32_t   smin, smax, max_row_src;
-  // the fused kernel: ticket of the current tile, look-back scratch, the tile's exclusive output offsets
-  uint32_t           cur_tile, lb_inc[kFusedWarps];
-  unsigned long long lb_sum[kFusedWarps], em_excl, edge_excl;
+template <int kSB> struct MergeShared { // everything but the two word buffers, which follow it in dynamic shared memory
+  static constexpr uint32_t kSrcMask = (1u << kSB) - 1u;
+  uint16_t        ent_src[kTileCap]; // slot -> source whose slice owns the slot (| kDropped: failed the overlap test)
+  MergeStage<kSB> src;
+  uint32_t        scan[33];
+  uint32_t        warp_tot[kFusedWarps];
+  uint32_t        smin, smax, max_row_src;
 };
-constexpr uint16_t kDropped           = 0x8000u;
-constexpr size_t   kMergeOff          = (sizeof(MergeShared) + 15) & ~size_t(15);
-constexpr size_t   kMergeBytesWide    = kMergeOff + 2 * kTileCap * sizeof(unsigned long long);
-constexpr size_t   kMergeBytesNarrow  = kMergeOff + 2 * kTileCap * sizeof(uint32_t);
+constexpr uint16_t kDropped = 0x8000u;
+template <int kSB> constexpr size_t merge_off() { return (sizeof(MergeShared<kSB>) + 15) & ~size_t(15); }
+template <int kSB> constexpr size_t merge_bytes(bool wide_words) {
+  return merge_off<kSB>() + 2 * kTileCap * (wide_words ? sizeof(unsigned long long) : sizeof(uint32_t));
+}
+constexpr size_t kMergeBytesWide   = merge_bytes<kSrcBits>(true);
+constexpr size_t kMergeBytesNarrow = merge_bytes<kSrcBits>(false);
 
 // materialise the candidates in generation order (source by source = unitig order inside a row); returns this
 // thread's number of candidates that pass the overlap test
-template <class W>
-__device__ __forceinline__ uint32_t enumerate_candidates(const TileArgs &a, MergeShared &s, W *wa, uint32_t n_src,
+template <class W, int kSB>
+__device__ __forceinline__ uint32_t enumerate_candidates(const TileArgs &a, MergeShared<kSB> &s, W *wa, uint32_t n_src,
                                                          uint32_t n_ent) {
   const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
   const uint32_t smin  = s.smin;
@@ -551,7 +566,8 @@ __device__ __forceinline__ uint32_t enumerate_candidates(const TileArgs &a, Merg
 
 // the merge levels; returns the buffer that holds the sorted words (the other one is free afterwards).  Starts and
 // ends with a barrier.
-template <class W> __device__ __forceinline__ W *merge_levels(MergeShared &s, W *wa, W *wb, uint32_t n_ent) {
+template <class W, int kSB>
+__device__ __forceinline__ W *merge_levels(MergeShared<kSB> &s, W *wa, W *wb, uint32_t n_ent) {
   const unsigned t   = threadIdx.x;
   const uint32_t per = (n_ent + kFusedBlock - 1) / kFusedBlock;
   __syncthreads();
@@ -562,7 +578,7 @@ template <class W> __device__ __forceinline__ W *merge_levels(MergeShared &s, W 
     uint32_t       pos = t * per; // `per` consecutive outputs per thread: every thread of the block has work
     const uint32_t oe  = pos + per < n_ent ? pos + per : n_ent;
     while (pos < oe) {
-      const uint32_t j  = s.ent_src[pos] & (kSrcCap - 1); // slice that owns output position pos
+      const uint32_t j  = s.ent_src[pos] & MergeShared<kSB>::kSrcMask; // slice that owns output position pos
       const uint32_t rf = s.src.row_first[j], re = s.src.row_end[j];
       const uint32_t s0 = rf + (((j - rf) >> (lvl + 1)) << (lvl + 1)); // the pair: runs [s0, s1) and [s1, s2)
       const uint32_t s1 = s0 + G < re ? s0 + G : re, s2 = s0 + 2 * G < re ? s0 + 2 * G : re;
@@ -602,14 +618,15 @@ template <class W> __device__ __forceinline__ W *merge_levels(MergeShared &s, W 
   return in;
 }
 
-template <class W>
-__device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W *wa, W *wb, uint32_t st_idx,
+template <class W, int kSB>
+__device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared<kSB> &s, W *wa, W *wb, uint32_t st_idx,
                                            uint32_t n_src, uint32_t n_ent) {
+  constexpr uint32_t kSrcMask = MergeShared<kSB>::kSrcMask;
   const unsigned t = threadIdx.x, w = t >> 5, l = t & 31;
   const uint32_t per   = (n_ent + kFusedBlock - 1) / kFusedBlock;
   const uint32_t wbase = w * per * 32; // warp w owns slots / positions [wbase, wbase + per * 32)
-  enumerate_candidates<W>(a, s, wa, n_src, n_ent);
-  const W *sorted = merge_levels<W>(s, wa, wb, n_ent);
+  enumerate_candidates<W, kSB>(a, s, wa, n_src, n_ent);
+  const W *sorted = merge_levels<W, kSB>(s, wa, wb, n_ent);
 
   // ---- run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the key
   // of its pair) but is skipped; the head of a run is its first surviving candidate.
@@ -630,7 +647,7 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
           const W key = x >> kIdxBits;
           // almost always the predecessor has another key: then this is a head and nothing else is looked at
           if (k > 0 && (sorted[k - 1] >> kIdxBits) == key) {
-            const uint32_t row_start = s.src.base[s.src.row_first[s.ent_src[k] & (kSrcCap - 1)]];
+            const uint32_t row_start = s.src.base[s.src.row_first[s.ent_src[k] & kSrcMask]];
             for (uint32_t p = k; p > row_start;) {
               --p;
               const W y = sorted[p];
@@ -671,9 +688,9 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
       const unsigned lt = (1u << l) - 1u;
       if (ok) {
         const uint32_t e  = uint32_t(xs[it]) & (kTileCap - 1);
-        const uint32_t j  = s.ent_src[e] & (kSrcCap - 1);
+        const uint32_t j  = s.ent_src[e] & kSrcMask;
         const uint32_t ib = s.src.begin[j] + (e - s.src.base[j]);
-        rec[pv + __popc(bv & lt)] = make_uint2(ib, j | (head ? 1u << kSrcBits : 0u) | ((ph + __popc(bh & lt)) << (kSrcBits + 1)));
+        rec[pv + __popc(bv & lt)] = make_uint2(ib, j | (head ? 1u << kRecSrcBits : 0u) | ((ph + __popc(bh & lt)) << (kRecSrcBits + 1)));
       }
       pv += __popc(bv);
       ph += __popc(bh);
@@ -681,12 +698,21 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared &s, W 
   }
 }
 
-__global__ void __launch_bounds__(kFusedBlock, kMergeCtas) pair_tiles_merge_kernel(TileArgs a) {
+// kSB = kSrcBits: the product — every tile of the range whose sources fit 512 (all of them, unless a read shares more
+// unitigs with partners than that).  kSB = kSrcBitsWide: the tiles of `wide_list` (sub-tiles of rows with 513 .. 4095
+// sources: a read that crosses that many shared unitigs is rare but legal input), one resident CTA per SM.
+template <int kSB>
+__global__ void __launch_bounds__(kFusedBlock, kSB == kSrcBits ? kMergeCtas : 1) pair_tiles_merge_kernel(TileArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  MergeShared   &s = *reinterpret_cast<MergeShared *>(smem_raw);
-  const unsigned t = threadIdx.x, l = t & 31;
+  MergeShared<kSB>  &s = *reinterpret_cast<MergeShared<kSB> *>(smem_raw);
+  const unsigned     t = threadIdx.x, l = t & 31;
+  constexpr uint32_t kCap    = 1u << kSB;
+  constexpr bool     kIsWide = kSB != kSrcBits;
+  const uint32_t     n_items = kIsWide ? a.n_wide : a.tile_hi - a.tile_lo;
 
-  for (uint32_t tile = a.tile_lo + blockIdx.x; tile < a.tile_hi; tile += gridDim.x) {
+  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t tile = kIsWide ? a.wide_list[item] : a.tile_lo + item;
+    if (kIsWide && (tile < a.tile_lo || tile >= a.tile_hi)) continue; // (a chunk takes the listed tiles of its range)
     __syncthreads(); // previous tile fully done with shared memory
     if (t == 0) {
       s.smin        = 0xffffffffu;
@@ -698,16 +724,19 @@ __global__ void __launch_bounds__(kFusedBlock, kMergeCtas) pair_tiles_merge_kern
     const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
     const uint32_t q0 = a.rd_off[r0];
     const uint32_t n_src = (kind ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
-    if (n_src > kSrcCap) { // cannot happen: see the planning kernels
+    if (!kIsWide && n_src > kCap) continue; // a sub-tile of a row with many sources: the wide instantiation takes it
+    if (n_src > kCap) {                     // cannot happen: the planning refuses rows with more sources than that
       if (t == 0) {
         *a.error           = 1;
         a.tile_cnt[st_idx] = make_uint2(0, 0);
       }
       continue;
     }
-    { // ---- stage the sources (kSrcCap <= blockDim.x: one per thread)
-      const uint32_t j = t;
-      uint32_t       len = 0, lmin = 0xffffffffu, lmax = 0, row_src = 0;
+    // ---- stage the sources, blockDim.x at a time (one pass for the product instantiation)
+    uint32_t carry = 0, lmin = 0xffffffffu, lmax = 0, row_src = 0;
+    for (uint32_t j0 = 0; j0 < n_src || j0 == 0; j0 += kFusedBlock) {
+      const uint32_t j   = j0 + t;
+      uint32_t       len = 0;
       if (j < n_src) {
         const uint32_t q   = a.rd_src[q0 + j];
         const PairRow  row = a.rows[q];
@@ -725,34 +754,36 @@ __global__ void __launch_bounds__(kFusedBlock, kMergeCtas) pair_tiles_merge_kern
           const uint32_t f   = a.rd_off[row.read] - q0, g = a.rd_off[row.read + 1] - q0;
           s.src.row_first[j] = uint16_t(f);
           s.src.row_end[j]   = uint16_t(g);
-          row_src            = g - f;
+          row_src            = g - f > row_src ? g - f : row_src;
         }
         len            = e - b;
         s.src.begin[j] = b;
         s.src.ir0[j]   = row.ir0;
         s.src.ir1[j]   = row.ir1;
         if (len) { // the slice is sorted by read id
-          lmin = a.p_read[b];
-          lmax = a.p_read[e - 1];
+          const uint32_t x0 = a.p_read[b], x1 = a.p_read[e - 1];
+          lmin = x0 < lmin ? x0 : lmin;
+          lmax = x1 > lmax ? x1 : lmax;
         }
       }
       uint32_t tot, ex = block_exclusive_scan<uint32_t>(len, s.scan, &tot);
-      if (j < n_src) s.src.base[j] = ex;
-      if (t == 0) s.src.base[n_src] = tot;
-      for (int d = 16; d > 0; d >>= 1) {
-        uint32_t omin = __shfl_xor_sync(0xffffffffu, lmin, d), omax = __shfl_xor_sync(0xffffffffu, lmax, d);
-        uint32_t orow = __shfl_xor_sync(0xffffffffu, row_src, d);
-        lmin    = omin < lmin ? omin : lmin;
-        lmax    = omax > lmax ? omax : lmax;
-        row_src = orow > row_src ? orow : row_src;
+      if (j < n_src) s.src.base[j] = carry + ex;
+      carry += tot;
+    }
+    if (t == 0) s.src.base[n_src] = carry;
+    for (int d = 16; d > 0; d >>= 1) {
+      uint32_t omin = __shfl_xor_sync(0xffffffffu, lmin, d), omax = __shfl_xor_sync(0xffffffffu, lmax, d);
+      uint32_t orow = __shfl_xor_sync(0xffffffffu, row_src, d);
+      lmin    = omin < lmin ? omin : lmin;
+      lmax    = omax > lmax ? omax : lmax;
+      row_src = orow > row_src ? orow : row_src;
+    }
+    if (l == 0) {
+      if (lmin <= lmax) {
+        atomicMin(&s.smin, lmin);
+        atomicMax(&s.smax, lmax);
       }
-      if (l == 0) {
-        if (lmin <= lmax) {
-          atomicMin(&s.smin, lmin);
-          atomicMax(&s.smax, lmax);
-        }
-        atomicMax(&s.max_row_src, row_src);
-      }
+      atomicMax(&s.max_row_src, row_src);
     }
     __syncthreads();
     const uint32_t n_ent = s.src.base[n_src];
@@ -765,10 +796,10 @@ __global__ void __launch_bounds__(kFusedBlock, kMergeCtas) pair_tiles_merge_kern
     }
     // 32-bit words when (second - min second) << 12 | slot fits AND can never be all ones (the merge's end marker)
     const uint32_t range = (n_ent && s.smax > s.smin) ? s.smax - s.smin : 0u;
-    unsigned char *words = smem_raw + kMergeOff;
+    unsigned char *words = smem_raw + merge_off<kSB>();
     if (range < (1u << (32 - kIdxBits)) - 1u) {
       uint32_t *wa = reinterpret_cast<uint32_t *>(words);
-      merge_tail<uint32_t>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent);
+      merge_tail<uint32_t, kSB>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent);
     } else if (!a.wide) { // cannot happen: the host sizes the launch from the id width
       if (t == 0) {
         *a.error           = 3;
@@ -776,7 +807,7 @@ __global__ void __launch_bounds__(kFusedBlock, kMergeCtas) pair_tiles_merge_kern
       }
     } else {
       unsigned long long *wa = reinterpret_cast<unsigned long long *>(words);
-      merge_tail<unsigned long long>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent);
+      merge_tail<unsigned long long, kSB>(a, s, wa, wa + kTileCap, st_idx, n_src, n_ent);
     }
   }
 }
@@ -795,324 +826,6 @@ __device__ __forceinline__ PairRow ld_row(const PairRow *p) { // two 128-bit rea
   r.orig   = y.w;
   return r;
 }
-
-// ---------------------------------------------------------------------------------------------------------------------
-// K6 + K7 in ONE kernel: enumerate, sort in shared memory, and write the edge matches and edges at their final
-// positions — no intermediate records, no separate emission kernel.
-//
-// What a tile needs from the tiles before it are two running sums: surviving candidates (where its edge matches start)
-// and run heads (where its edges start).  Both travel through decoupled look-back chains, one status word per tile and
-// chain (value << 2 | state; 1 = the tile's own count, 2 = inclusive prefix).  Tiles are taken in ticket order, so
-// every predecessor of a running tile is running or done.  What makes the look-backs (almost) free is WHEN they
-// happen:
-//   * a tile knows its surviving-candidate count right after the enumeration and publishes it then; it needs the
-//     prefix only after its sort — by then every predecessor has long published (they started earlier);
-//   * its head count exists only after the sort; it is published then, but the prefix is not needed before the edge
-//     matches have been written (the gathers, the f64 score, six column stores: a third of a tile's life) — again the
-//     predecessors, which started earlier, have passed their own sorts by then.
-// (The first one-kernel version of round 1 looked back for both sums right after the sort and lost 27 % of its stall
-//  samples waiting for ~300 in-flight predecessors to finish sorting.)
-// The whole block looks back at once (512 predecessors per round trip), so a chain normally costs one L2 round trip.
-// ---------------------------------------------------------------------------------------------------------------------
-struct FusedArgs {
-  TileArgs            t;
-  unsigned int       *ticket;            // zero before the launch
-  unsigned long long *st_em, *st_edge;   // status words of the launch's tiles, zero before the launch
-  unsigned long long  em_value_base;     // added to the em_begin VALUES (rows of earlier chunks of the same slice)
-  unsigned long long *totals;            // [0] edge matches, [1] edges of this launch (written by the last tile)
-  EdgeTables          out;               // indexed from the launch's first edge match / edge
-};
-
-// exclusive prefix of `tile` over the chain `st` (all threads of the block call it; two barriers per round)
-__device__ __forceinline__ unsigned long long block_lookback(volatile unsigned long long *st, uint32_t tile, MergeShared &s) {
-  const unsigned     t = threadIdx.x, l = t & 31, w = t >> 5;
-  unsigned long long prefix = 0;
-  long long          hi     = (long long)tile - 1;
-  while (true) {
-    const long long    p    = hi - (long long)t;
-    unsigned long long word = 2ull; // before the first tile: an inclusive prefix of zero
-    if (p >= 0) {
-      word = st[p];
-      while ((word & 3ull) == 0ull) word = st[p];
-    }
-    const unsigned im   = __ballot_sync(0xffffffffu, (word & 3ull) == 2ull);
-    const unsigned stop = im ? unsigned(__ffs(im) - 1) : 32u; // nearest predecessor of this warp's window with a prefix
-    unsigned long long x = l <= stop ? (word >> 2) : 0ull;
-    x                    = warp_reduce_sum(x);
-    if (l == 0) {
-      s.lb_sum[w] = x;
-      s.lb_inc[w] = im != 0u;
-    }
-    __syncthreads();
-    bool done = false;
-#pragma unroll
-    for (int ww = 0; ww < kFusedWarps; ++ww) {
-      if (!done) prefix += s.lb_sum[ww];
-      done = done || s.lb_inc[ww] != 0u;
-    }
-    __syncthreads();
-    if (done) break;
-    hi -= kFusedBlock;
-  }
-  return prefix;
-}
-
-template <class W>
-__device__ __forceinline__ void fused_tail(const FusedArgs &fa, MergeShared &s, W *wa, W *wb, uint32_t st_idx,
-                                           uint32_t n_src, uint32_t n_ent, uint32_t q0, bool last_tile) {
-  const TileArgs &a = fa.t;
-  const unsigned  t = threadIdx.x, w = t >> 5, l = t & 31;
-  const uint32_t  per   = (n_ent + kFusedBlock - 1) / kFusedBlock;
-  const uint32_t  wbase = w * per * 32;
-  volatile unsigned long long *st_em = fa.st_em, *st_edge = fa.st_edge;
-
-  // ---- enumerate; the tile's surviving-candidate count is known (and published) before the sort
-  uint32_t kept = enumerate_candidates<W>(a, s, wa, n_src, n_ent);
-  kept          = warp_reduce_sum(kept);
-  if (l == 0) s.warp_tot[w] = kept;
-  __syncthreads();
-  uint32_t n_valid = 0;
-#pragma unroll
-  for (int ww = 0; ww < kFusedWarps; ++ww) n_valid += s.warp_tot[ww];
-  if (t == 0) st_em[st_idx] = ((unsigned long long)n_valid << 2) | (st_idx ? 1ull : 2ull); // tile 0: already a prefix
-
-  const W *sorted = merge_levels<W>(s, wa, wb, n_ent); // (starts with the barrier that protects warp_tot)
-  W       *spare  = sorted == wa ? wb : wa;
-
-  // ---- run heads = edges of this tile (a candidate that failed the overlap test stays in its run but is skipped)
-  uint32_t vmask = 0, hmask = 0, n_v = 0, n_h = 0;
-#pragma unroll
-  for (int it = 0; it < kItems; ++it) {
-    if (uint32_t(it) < per) {
-      const uint32_t k = wbase + it * 32 + l;
-      bool           ok = false, head = false;
-      if (k < n_ent) {
-        const W x = sorted[k];
-        ok        = !(s.ent_src[uint32_t(x) & (kTileCap - 1)] & kDropped);
-        if (ok) {
-          head = true;
-          const W key = x >> kIdxBits;
-          if (k > 0 && (sorted[k - 1] >> kIdxBits) == key) {
-            const uint32_t row_start = s.src.base[s.src.row_first[s.ent_src[k] & (kSrcCap - 1)]];
-            for (uint32_t p = k; p > row_start;) {
-              --p;
-              const W y = sorted[p];
-              if ((y >> kIdxBits) != key) break;
-              if (!(s.ent_src[uint32_t(y) & (kTileCap - 1)] & kDropped)) {
-                head = false;
-                break;
-              }
-            }
-          }
-        }
-      }
-      vmask |= (ok ? 1u : 0u) << it;
-      hmask |= (head ? 1u : 0u) << it;
-      n_v += __popc(__ballot_sync(0xffffffffu, ok));
-      n_h += __popc(__ballot_sync(0xffffffffu, head));
-    }
-  }
-  if (l == 0) s.warp_tot[w] = n_v | (n_h << 16);
-  // the sources' remaining fields (score, line, unitig, read, flags) go where the sort no longer needs the space
-  uint4    *ex    = reinterpret_cast<uint4 *>(spare);
-  uint32_t *ex_fl = reinterpret_cast<uint32_t *>(ex + kSrcCap);
-  if (t < n_src) {
-    const PairRow row = ld_row(a.rows + a.rd_src[q0 + t]);
-    ex[t]             = make_uint4(uint32_t(row.score), row.line, row.unitig, row.read);
-    ex_fl[t]          = row.flags;
-  }
-  __syncthreads();
-  uint32_t before = 0, total = 0;
-#pragma unroll
-  for (int ww = 0; ww < kFusedWarps; ++ww) {
-    const uint32_t c = s.warp_tot[ww];
-    before += ww < int(w) ? c : 0u;
-    total += c;
-  }
-  const uint32_t n_heads = total >> 16;
-  if (t == 0) st_edge[st_idx] = ((unsigned long long)n_heads << 2) | (st_idx ? 1ull : 2ull);
-
-  // ---- where this tile's edge matches start: every predecessor published its count before ITS sort
-  const unsigned long long em_excl = st_idx ? block_lookback(st_em, st_idx, s) : 0ull;
-  if (t == 0 && st_idx) st_em[st_idx] = ((em_excl + n_valid) << 2) | 2ull;
-
-  // ---- the edge matches, at their final positions
-  const unsigned lt = (1u << l) - 1u;
-  const uint32_t smin = s.smin;
-  {
-    uint32_t pv = before & 0xffffu;
-#pragma unroll 1
-    for (uint32_t it = 0; it < per; ++it) {
-      {
-        const bool     ok = (vmask >> it) & 1u;
-        const unsigned bv = __ballot_sync(0xffffffffu, ok);
-        if (ok) {
-          const uint32_t e  = uint32_t(sorted[wbase + it * 32 + l]) & (kTileCap - 1);
-          const uint32_t j  = s.ent_src[e] & (kSrcCap - 1);
-          const PairRow  pb = ld_row(a.rows + (s.src.begin[j] + (e - s.src.base[j])));
-          const uint4    sx = ex[j];
-          const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = pb.ir0, b1 = pb.ir1;
-          const int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
-          // MatchMap.cpp:195-202: score_x * common / len_x for the outer and the inner match, summed (IEEE addition
-          // commutes, so which of the two is "outer" does not change the sum); no FMA contraction
-          const double common = double(ov1 - ov0 + 1);
-          const double sa     = double((unsigned long long)(long long)int32_t(sx.x)); // size_t widened from int
-          const double sbb    = double((unsigned long long)(long long)pb.score);
-          const double sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
-          const double sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
-          const uint32_t fa_  = ex_fl[j];
-          const unsigned long long o = em_excl + pv + __popc(bv & lt);
-          fa.out.em_unitig[o] = sx.z;
-          fa.out.em_ov0[o]    = ov0;
-          fa.out.em_ov1[o]    = ov1;
-          fa.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
-          fa.out.em_line[o]   = sx.y > pb.line ? sx.y : pb.line; // outer = the later line (MatchMap.cpp:218)
-          fa.out.em_flags[o]  = uint8_t((((fa_ ^ pb.flags) & 1u) ? 0u : 1u) | ((fa_ & pb.flags & 2u) ? 2u : 0u));
-        }
-        pv += __popc(bv);
-      }
-    }
-  }
-
-  // ---- where its edges start: the predecessors, which started earlier, are past their sorts by now
-  const unsigned long long edge_excl = st_idx ? block_lookback(st_edge, st_idx, s) : 0ull;
-  if (t == 0 && st_idx) st_edge[st_idx] = ((edge_excl + n_heads) << 2) | 2ull;
-  {
-    uint32_t pv = before & 0xffffu, ph = before >> 16;
-#pragma unroll 1
-    for (uint32_t it = 0; it < per; ++it) {
-      {
-        const bool     ok = (vmask >> it) & 1u, head = (hmask >> it) & 1u;
-        const unsigned bv = __ballot_sync(0xffffffffu, ok), bh = __ballot_sync(0xffffffffu, head);
-        if (head) {
-          const W        x  = sorted[wbase + it * 32 + l];
-          const uint32_t j  = s.ent_src[uint32_t(x) & (kTileCap - 1)] & (kSrcCap - 1);
-          const unsigned long long eo = edge_excl + ph + __popc(bh & lt);
-          fa.out.first[eo]    = ex[j].w;
-          fa.out.second[eo]   = uint32_t(x >> kIdxBits) + smin;
-          fa.out.em_begin[eo] = fa.em_value_base + em_excl + pv + __popc(bv & lt);
-        }
-        pv += __popc(bv);
-        ph += __popc(bh);
-      }
-    }
-  }
-  if (last_tile && t == 0) { // closes the CSR and reports the totals of the launch
-    fa.totals[0]                            = em_excl + n_valid;
-    fa.totals[1]                            = edge_excl + n_heads;
-    fa.out.em_begin[edge_excl + n_heads]    = fa.em_value_base + em_excl + n_valid;
-  }
-}
-
-// kWide = false: every sort word of the launch fits 32 bits (read ids below 2^20), the 64-bit path is not compiled in
-template <bool kWide>
-__global__ void __launch_bounds__(kFusedBlock, kWide ? (kFusedCtas > 2 ? 2 : kFusedCtas) : kFusedCtas)
-    pair_tiles_fused_kernel(FusedArgs fa) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  MergeShared    &s = *reinterpret_cast<MergeShared *>(smem_raw);
-  const TileArgs &a = fa.t;
-  const unsigned  t = threadIdx.x, l = t & 31;
-  const uint32_t  n_tiles = a.tile_hi - a.tile_lo;
-
-  while (true) {
-    __syncthreads(); // previous tile fully done with shared memory
-    if (t == 0) {
-      s.cur_tile    = atomicAdd(fa.ticket, 1u); // ticket order = start order: predecessors are running or done
-      s.smin        = 0xffffffffu;
-      s.smax        = 0;
-      s.max_row_src = 0;
-    }
-    __syncthreads();
-    const uint32_t st_idx = s.cur_tile;
-    if (st_idx >= n_tiles) break;
-    const uint32_t tile = a.tile_lo + st_idx;
-    const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
-    const uint32_t q0 = a.rd_off[r0];
-    uint32_t       n_src = (kind ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
-    if (n_src > kSrcCap) { // cannot happen (see the planning kernels); the tile still has to publish its (zero) counts
-      if (t == 0) *a.error = 1;
-      n_src = 0;
-    }
-    { // ---- stage the sources (kSrcCap <= blockDim.x: one per thread)
-      const uint32_t j = t;
-      uint32_t       len = 0, lmin = 0xffffffffu, lmax = 0, row_src = 0;
-      if (j < n_src) {
-        const uint32_t q   = a.rd_src[q0 + j];
-        const PairRow  row = a.rows[q];
-        uint32_t       b, e;
-        if (kind) {
-          const uint32_t *sl = a.slices + a.slice_off[r0] + uint64_t(kind - 1) * n_src;
-          b                  = sl[j];
-          e                  = sl[n_src + j];
-          s.src.row_first[j] = 0;
-          s.src.row_end[j]   = uint16_t(n_src);
-          row_src            = n_src;
-        } else {
-          b                  = q + 1;
-          e                  = a.grp_off[row.unitig + 1];
-          const uint32_t f   = a.rd_off[row.read] - q0, g = a.rd_off[row.read + 1] - q0;
-          s.src.row_first[j] = uint16_t(f);
-          s.src.row_end[j]   = uint16_t(g);
-          row_src            = g - f;
-        }
-        len            = e - b;
-        s.src.begin[j] = b;
-        s.src.ir0[j]   = row.ir0;
-        s.src.ir1[j]   = row.ir1;
-        if (len) { // the slice is sorted by read id
-          lmin = a.p_read[b];
-          lmax = a.p_read[e - 1];
-        }
-      }
-      uint32_t tot, ex = block_exclusive_scan<uint32_t>(len, s.scan, &tot);
-      if (j < n_src) s.src.base[j] = ex;
-      if (t == 0) s.src.base[n_src] = tot;
-      for (int d = 16; d > 0; d >>= 1) {
-        uint32_t omin = __shfl_xor_sync(0xffffffffu, lmin, d), omax = __shfl_xor_sync(0xffffffffu, lmax, d);
-        uint32_t orow = __shfl_xor_sync(0xffffffffu, row_src, d);
-        lmin    = omin < lmin ? omin : lmin;
-        lmax    = omax > lmax ? omax : lmax;
-        row_src = orow > row_src ? orow : row_src;
-      }
-      if (l == 0) {
-        if (lmin <= lmax) {
-          atomicMin(&s.smin, lmin);
-          atomicMax(&s.smax, lmax);
-        }
-        atomicMax(&s.max_row_src, row_src);
-      }
-    }
-    __syncthreads();
-    uint32_t n_ent = s.src.base[n_src];
-    __syncthreads(); // (everybody has read base[n_src] before an error path may overwrite it)
-    if (n_ent > kTileCap) { // cannot happen; publish zero counts and go on
-      if (t == 0) {
-        *a.error      = 2;
-        s.src.base[0] = 0;
-      }
-      n_src = 0;
-      n_ent = 0;
-      __syncthreads();
-    }
-    const bool     last  = st_idx + 1 == n_tiles;
-    const uint32_t range = (n_ent && s.smax > s.smin) ? s.smax - s.smin : 0u;
-    unsigned char *words = smem_raw + kMergeOff;
-    if (range < (1u << (32 - kIdxBits)) - 1u || !kWide) {
-      if (!(range < (1u << (32 - kIdxBits)) - 1u)) { // cannot happen: the host sizes the launch from the id width
-        if (t == 0) *a.error = 3;
-        n_src = 0;
-        n_ent = 0;
-      }
-      uint32_t *wa = reinterpret_cast<uint32_t *>(words);
-      fused_tail<uint32_t>(fa, s, wa, wa + kTileCap, st_idx, n_src, n_ent, q0, last);
-    } else if (kWide) {
-      unsigned long long *wa = reinterpret_cast<unsigned long long *>(words);
-      fused_tail<unsigned long long>(fa, s, wa, wa + kTileCap, st_idx, n_src, n_ent, q0, last);
-    }
-  }
-}
-template __global__ void pair_tiles_fused_kernel<false>(FusedArgs);
-template __global__ void pair_tiles_fused_kernel<true>(FusedArgs);
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K7b: tile counts -> global offsets of every tile's first edge match and first edge (two single-pass scans)
@@ -1163,8 +876,9 @@ __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs 
       r[u]             = k < n_valid ? __ldg(rec + k) : make_uint2(0, 0);
     }
     __syncthreads(); // previous tile done with the staged sources
-    if (n_valid)
-      for (uint32_t j = t; j < n_src && j < kSrcCap; j += kEmitBlock) {
+    const bool staged = n_src <= kSrcCap; // (rows with more sources: their rows are read in place, one more gather)
+    if (n_valid && staged)
+      for (uint32_t j = t; j < n_src; j += kEmitBlock) {
         const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
         src_lo[j]      = __ldg(q);
         src_hi[j]      = __ldg(q + 1);
@@ -1185,8 +899,16 @@ __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs 
       for (int u = 0; u < kEmitBatch; ++u) {
         const uint32_t k = k0 + u * kEmitBlock;
         if (k >= n_valid) continue;
-        const uint32_t j  = cur[u].y & (kSrcCap - 1);
-        const uint4    lo = src_lo[j], hi = src_hi[j];
+        const uint32_t j  = cur[u].y & ((1u << kRecSrcBits) - 1u);
+        uint4          lo, hi;
+        if (staged) {
+          lo = src_lo[j];
+          hi = src_hi[j];
+        } else {
+          const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
+          lo             = __ldg(q);
+          hi             = __ldg(q + 1);
+        }
         const int      a0 = int32_t(lo.x), a1 = int32_t(lo.y), b0 = pb[u].ir0, b1 = pb[u].ir1;
         const int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
         // MatchMap.cpp:195-202: score_x * common / len_x for the outer and the inner match, summed.  IEEE addition
@@ -1205,8 +927,8 @@ __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs 
         a.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
         a.out.em_line[o]   = la > pb[u].line ? la : pb[u].line; // outer = the later line (MatchMap.cpp:218)
         a.out.em_flags[o]  = uint8_t((((fa ^ pb[u].flags) & 1u) ? 0u : 1u) | ((fa & pb[u].flags & 2u) ? 2u : 0u));
-        if (cur[u].y & (1u << kSrcBits)) {
-          const unsigned long long eo = ed0 + (cur[u].y >> (kSrcBits + 1));
+        if (cur[u].y & (1u << kRecSrcBits)) {
+          const unsigned long long eo = ed0 + (cur[u].y >> (kRecSrcBits + 1));
           a.out.first[eo]    = lo.z;
           a.out.second[eo]   = pb[u].read;
           a.out.em_begin[eo] = a.em_value_base + o;
@@ -1243,6 +965,7 @@ void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const Unitig
   unsigned long long *wgt    = reinterpret_cast<unsigned long long *>(zero + z_wgt);
   uint32_t           *d_u32  = reinterpret_cast<uint32_t *>(zero + z_u32); // [0] sources [1] tiles [2] too many sources
                                                                            // [3] tile error [4] big groups [5] heavy matches
+                                                                           // [6] tiles with > 512 sources [7] cursor of their list
   uint64_t           *d_u64  = reinterpret_cast<uint64_t *>(zero + z_u64);
   uint32_t           *rd_off = arena.alloc<uint32_t>(R + 1);
   const int gm = grid_for(M, 256), gr = grid_for(R, 256);
@@ -1265,7 +988,7 @@ void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const Unitig
             scan_job<uint64_t>(arena, st, 2, SliceCount{plan}, R, slice_off, d_u64 + 0),
             scan_job<uint64_t>(arena, st, 3, WeightOf{wgt}, R, (uint64_t *)nullptr, d_u64 + 1));
   MSGPU_CUDA(cudaMemcpyAsync(rd_off + R, d_u32 + 0, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-  TileCount tc{plan, prefix};
+  TileCount tc{plan, prefix, d_u32 + 6};
   exclusive_scan<uint32_t>(arena, st, tc, R, tile_idx, d_u32 + 1);
   // one copy of the adjacent counter words (d_u32[0..7], d_u64[0..3]) into pinned memory
   char *h_words = static_cast<char *>(arena.host_scratch());
@@ -1273,11 +996,12 @@ void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const Unitig
   const uint32_t *h32 = reinterpret_cast<const uint32_t *>(h_words);
   const uint64_t *h64 = reinterpret_cast<const uint64_t *>(h_words + (z_u64 - z_u32));
   MSGPU_CUDA(cudaStreamSynchronize(st));
-  const uint32_t n_src = h32[0], n_tiles = h32[1];
+  const uint32_t n_src = h32[0], n_tiles = h32[1], n_wide = h32[6];
   const uint64_t n_slices = h64[0], P = h64[1]; // P = sum k(k-1)/2: every unordered pair is one suffix member
 
   uint32_t *tile_row = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1), *tile_kind = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1);
-  if (R) MSGPU_LAUNCH("write_tiles", st, write_tiles_kernel<<<gr, 256, 0, st>>>(tc, tile_idx, R, n_tiles, tile_row, tile_kind, d_u32 + 2));
+  uint32_t *wide_list = arena.alloc<uint32_t>(uint64_t(n_wide) + 1);
+  if (R) MSGPU_LAUNCH("write_tiles", st, write_tiles_kernel<<<gr, 256, 0, st>>>(tc, tile_idx, R, n_tiles, tile_row, tile_kind, d_u32 + 2, wide_list, d_u32 + 7));
   uint32_t *rd_tmp = arena.alloc<uint32_t>(n_src), *rd_src = arena.alloc<uint32_t>(n_src);
   // ---- this device's share: a contiguous range of tiles (tiles weigh about the same)
   if (n_parts == 0) n_parts = 1;
@@ -1309,6 +1033,8 @@ void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const Unitig
   pl.tile_kind = tile_kind;
   pl.slice_off = slice_off;
   pl.slices    = slices;
+  pl.wide_list = wide_list;
+  pl.n_wide    = n_wide;
   pl.flags     = d_u32;
   pl.n_reads   = R;
   pl.n_pairs   = P;
@@ -1346,17 +1072,6 @@ void pairing_outputs_alloc(Arena &arena, uint64_t cap, EdgeTables &e) {
   e.em_begin  = arena.alloc<uint64_t>(cap + 1);
 }
 
-static bool one_kernel_variant() {
-  // The product is the two-kernel form (tile kernel -> compact records -> two scans -> emission kernel).
-  // MSGPU_VARIANT=fused selects the ONE-kernel form (enumerate, sort, write the tables; offsets by two look-back
-  // chains): bit-identical tables, measured slower at yeast scale (1.56 ms vs 0.75 + 0.50 ms; 21 % of its stall samples
-  // sit behind the look-back for the edge offsets — a tile waits for the slowest sort among ~440 tiles in flight —
-  // and its emission phase runs at 40 registers / 3 CTAs per SM): profiles/r2_ncu_pair_tiles_fused_onekernel_yeast.txt.
-  // Kept as the A/B the design decision rests on.
-  const char *variant = std::getenv("MSGPU_VARIANT");
-  return variant && std::string(variant) == "fused";
-}
-
 static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, const PairScratch &sc) {
   TileArgs a;
   a.rows      = pl.rows;
@@ -1374,6 +1089,8 @@ static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, cons
   a.tile_hi   = t_hi;
   a.records   = sc.records;
   a.tile_cnt  = sc.tile_cnt;
+  a.wide_list = pl.wide_list;
+  a.n_wide    = pl.n_wide;
   a.error     = pl.flags + 3;
   // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits; otherwise
   // tiles choose per tile and the launch carries the 64-bit buffers
@@ -1388,15 +1105,21 @@ void pairing_tiles(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t
   const uint32_t n = t_hi - t_lo;
   if (n > sc.max_tiles) throw BuildError{MSGPU_ERR_INTERNAL, "pairing: emission scratch too small"};
   MSGPU_CUDA(cudaMemsetAsync(sc.totals, 0, 4 * sizeof(unsigned long long), st));
-  if (!n || one_kernel_variant()) return;
+  if (!n) return;
   const TileArgs a = tile_args(pl, t_lo, t_hi, sc);
   // (the shared-memory opt-in is an attribute of the function ON THE CURRENT DEVICE: set before every launch — a
   //  context per GPU in one process is supported, and the call costs less than a microsecond)
-  MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
+  MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel<kSrcBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
   // 32 registers, 51 KB (narrow): four resident CTAs per SM; a few waves of them, tiles strided over the grid
   int grid = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * 4;
   if (uint32_t(grid) > n) grid = int(n);
-  MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
+  MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<kSrcBits><<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
+  if (pl.n_wide) { // sub-tiles of rows with 513 .. 4095 sources (skipped above): the same kernel staged for that many
+    const size_t bytes = merge_bytes<kSrcBitsWide>(a.wide != 0);
+    MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel<kSrcBitsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(merge_bytes<kSrcBitsWide>(true))));
+    int gw = pl.n_wide < uint32_t(kNumSMs) ? int(pl.n_wide) : kNumSMs;
+    MSGPU_LAUNCH("pair_tiles_wide", st, pair_tiles_merge_kernel<kSrcBitsWide><<<gw, kFusedBlock, bytes, st>>>(a));
+  }
   run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{sc.tile_cnt}, n, sc.em_base, sc.totals + 0),
             scan_job<unsigned long long>(arena, st, 1, TileHeads{sc.tile_cnt}, n, sc.ed_base, sc.totals + 1));
 }
@@ -1410,30 +1133,6 @@ void pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_
   e.em_value_base  = em_value_base;
   if (!n) {
     MSGPU_CUDA(cudaMemcpyAsync(e.em_begin, &e.em_value_base, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); // empty CSR
-    return;
-  }
-  if (one_kernel_variant()) {
-    const TileArgs a = tile_args(pl, t_lo, t_hi, sc);
-    MSGPU_CUDA(cudaMemsetAsync(sc.status, 0, 2 * uint64_t(n) * sizeof(unsigned long long), st));
-    FusedArgs fa;
-    fa.t             = a;
-    fa.ticket        = reinterpret_cast<unsigned int *>(sc.totals + 2);
-    fa.st_em         = sc.status;
-    fa.st_edge       = sc.status + n;
-    fa.em_value_base = em_value_base;
-    fa.totals        = sc.totals;
-    fa.out           = e;
-    if (a.wide) {
-      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
-      int grid = kNumSMs * (kFusedCtas > 2 ? 2 : kFusedCtas);
-      if (uint32_t(grid) > n) grid = int(n);
-      MSGPU_LAUNCH("pair_tiles_fused", st, pair_tiles_fused_kernel<true><<<grid, kFusedBlock, kMergeBytesWide, st>>>(fa));
-    } else {
-      MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesNarrow)));
-      int grid = kNumSMs * kFusedCtas; // persistent: one CTA per resident slot, tiles by ticket
-      if (uint32_t(grid) > n) grid = int(n);
-      MSGPU_LAUNCH("pair_tiles_fused", st, pair_tiles_fused_kernel<false><<<grid, kFusedBlock, kMergeBytesNarrow, st>>>(fa));
-    }
     return;
   }
   EmitArgs ea;
@@ -1471,7 +1170,8 @@ void pairing_finish(Arena &arena, cudaStream_t st, const PairPlan &pl, const Pai
   const uint32_t           *h_flags = reinterpret_cast<const uint32_t *>(h);
   const unsigned long long *h_tot   = reinterpret_cast<const unsigned long long *>(h + 64);
   if (h_flags[2])
-    throw BuildError{MSGPU_ERR_LIMIT, "a read matches more than " + std::to_string(kSrcCap) + " unitigs with partners"};
+    throw BuildError{MSGPU_ERR_LIMIT, "a read shares " + std::to_string(kSrcCapWide) + " or more unitigs with other reads (one "
+                                      "edge of it could hold more edge matches than a pairing tile holds candidates)"};
   if (h_flags[3])
     throw BuildError{MSGPU_ERR_INTERNAL, "pairing: tile invariant violated (code " + std::to_string(h_flags[3]) + ")"};
   *n_em    = h_tot[0];

@@ -127,18 +127,6 @@ def test_sort_based_variant_agrees_with_fused(builder, monkeypatch):
     assert tables_equal(fused, srt) == []
 
 
-def test_one_kernel_variant_agrees_with_the_two_kernel_product(builder, monkeypatch):
-    """MSGPU_VARIANT=fused writes the tables from ONE kernel (offsets through two decoupled look-back chains) instead
-    of tile kernel -> records -> scans -> emission kernel.  Same tables, bit for bit — also on rows larger than a
-    tile, whose sub-tiles chain through the look-back.  (Measured slower; kept as the A/B)"""
-    for paf in (synth.generate_paf("ecoli"), util.heavy_rows_paf()):
-        two = util.gpu_to_tables(builder.build_from_buffer(paf).result())
-        monkeypatch.setenv("MSGPU_VARIANT", "fused")
-        one = util.gpu_to_tables(builder.build_from_buffer(paf).result())
-        monkeypatch.delenv("MSGPU_VARIANT")
-        assert tables_equal(one, two) == []
-
-
 def test_hash_collision_restarts_interning(builder, oracle, monkeypatch):
     """Names are interned through 64-bit hashes that every line verifies against its slot's representative; a
     collision restarts the interning with another seed.  The test hook makes the first attempt collide everywhere."""
@@ -149,20 +137,34 @@ def test_hash_collision_restarts_interning(builder, oracle, monkeypatch):
     assert tables_equal(got, oracle.build(paf)) == []
 
 
-def test_read_with_too_many_partnered_unitigs_is_a_limit_error(builder):
-    """A read that shares more than 512 unitigs with other reads exceeds what one pairing tile stages: the build must
-    fail with MSGPU_ERR_LIMIT (documented in DESIGN.md), not crash or return something wrong."""
-    from muchsalsa_b200.construct import MsGpuError
+def long_read_paf(n_unitigs, n_partners=3):
+    """A very long read (`hub`) that shares `n_unitigs` unitigs with other reads: every unitig is also matched by one
+    of `n_partners` long reads (so single edges hold hundreds of edge matches) and every third one by a short read."""
     L = util.paf_line
     rows = []
-    for u in range(600):
-        rows.append(L(f"u{u}", 5000, 0, 3000, "+", "hub", 4000000, u * 3000, u * 3000 + 3000, 2900))
-        rows.append(L(f"u{u}", 5000, 500, 3500, "+", f"p{u}", 9000, 0, 3000, 2900))
-    paf = b"".join(rows) + L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
+    for u in range(n_unitigs):
+        a = u * 3000
+        rows.append(L(f"u{u}", 5000, 0, 3000, "+", "hub", 20_000_000, a, a + 3000, 2900))
+        rows.append(L(f"u{u}", 5000, 500, 3500, "+-"[u % 2], f"long{u % n_partners}", 15_000_000, a + 200, a + 3200, 2800))
+        if u % 3 == 0:
+            rows.append(L(f"u{u}", 5000, 1000, 4000, "+", f"p{u}", 9000, 0, 3000, 2700))
+    return b"".join(rows) + L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
+
+
+@pytest.mark.parametrize("n_unitigs", [600, 1500, 4000])
+def test_read_that_shares_more_unitigs_than_a_product_tile_stages(builder, oracle, n_unitigs):
+    """The product tile kernel stages 512 sources; a read that shares more unitigs with partners (an ultra-long read:
+    legal input, the reference has no such notion) is paired by the instantiation staged for up to 4095 sources — one
+    edge then holds up to that many edge matches.  Bit-exact with the oracle."""
+    paf = long_read_paf(n_unitigs)
+    got = _same(builder, oracle, paf)
+    assert int(np.diff(got.edge_em_begin.astype(np.int64)).max()) >= n_unitigs // 3
+
+
+def test_read_with_4096_shared_unitigs_is_the_limit(builder):
+    """An edge cannot hold more edge matches than a pairing tile holds candidates (4096): a read sharing that many
+    unitigs with partners (>= 10 Mb of read) is refused with MSGPU_ERR_LIMIT — not a crash, not a wrong answer."""
+    from muchsalsa_b200.construct import MsGpuError
     with pytest.raises(MsGpuError) as e:
-        builder.build_from_buffer(paf)
+        builder.build_from_buffer(long_read_paf(4100))
     assert e.value.status == 6
-    # 500 shared unitigs are fine
-    paf = b"".join(rows[:1000]) + L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
-    c = builder.build_from_buffer(paf).counts()
-    assert c["n_edges"] == 500 and c["n_edge_matches"] == 500
