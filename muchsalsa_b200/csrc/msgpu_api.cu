@@ -465,7 +465,7 @@ int msgpu_build_from_shards(msgpu_ctx *ctx, uint32_t n_shards, const msgpu_shard
                     ctx->matches);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
     ctx->n_parts = n_parts;
-    run_pairing(ctx->arena, st, ctx->matches, ctx->unitigs, ctx->reads.n, ctx->edges, ctx->ev[3], part, n_parts);
+    pair_or_plan(ctx, part, n_parts);
     MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
     MSGPU_CUDA(cudaStreamSynchronize(st));
     ctx->timings           = msgpu_timings{};
