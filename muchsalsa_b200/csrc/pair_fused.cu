@@ -938,6 +938,111 @@ __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs 
   }
 }
 
+// The same emission with the tile's records brought into shared memory by ONE bulk copy (cp.async.bulk — the 1-D form of
+// the TMA unit, SASS UBLKCP — completing on an mbarrier) instead of coalesced per-thread loads: a tile's records are one
+// contiguous, 16-byte aligned run, the shape bulk copies want.  The A/B the north star asks for ("staged via TMA");
+// selected with MSGPU_EMIT=bulk, result in DESIGN.md §4.  (The candidates of the tile kernel are NOT such a shape:
+// a source's partner slice starts at an arbitrary 4-byte offset of three separate columns, and staging 4096
+// candidates x 12 bytes would take the shared memory that buys the kernel its four resident CTAs.)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_bulk_kernel(EmitArgs a) {
+  __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
+  __shared__ __align__(8) unsigned long long bar;
+  extern __shared__ __align__(16) unsigned char bulk_raw[];
+  uint2           *recs = reinterpret_cast<uint2 *>(bulk_raw); // kTileCap records
+  const unsigned   t = threadIdx.x;
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  if (blockIdx.x == 0 && t == 0) a.out.em_begin[a.totals[1]] = a.em_value_base + a.totals[0]; // closes the CSR
+  for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
+    const uint32_t           tile    = a.tile_lo + ti;
+    const uint32_t           n_valid = a.tile_cnt[ti].x;
+    const unsigned long long em0 = a.em_base[ti], ed0 = a.edge_base[ti];
+    const uint32_t           r0 = a.tile_row[tile], q0 = a.rd_off[r0];
+    const uint32_t n_src = (a.tile_kind[tile] ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
+    const uint2   *rec   = a.records + uint64_t(ti) * kTileCap;
+    __syncthreads(); // previous tile done with the records and the staged sources
+    if (t == 0 && n_valid) {
+      const uint32_t bytes = (n_valid * uint32_t(sizeof(uint2)) + 15u) & ~15u; // (a tile's slots are 32 KB: in bounds)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_addr(recs)),
+                   "l"(rec), "r"(bytes), "r"(smem_addr(&bar))
+                   : "memory");
+    }
+    const bool staged = n_src <= kSrcCap;
+    if (n_valid && staged)
+      for (uint32_t j = t; j < n_src; j += kEmitBlock) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
+        src_lo[j]      = __ldg(q);
+        src_hi[j]      = __ldg(q + 1);
+      }
+    __syncthreads();
+    if (n_valid) { // every thread waits for the copy (hardware sleep, not a poll)
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_addr(&bar)), "r"(phase)
+                     : "memory");
+      phase ^= 1u;
+    }
+    for (uint32_t k0 = t; k0 < n_valid; k0 += kEmitBlock * kEmitBatch) {
+      uint2   cur[kEmitBatch];
+      PairRow pb[kEmitBatch];
+#pragma unroll
+      for (int u = 0; u < kEmitBatch; ++u) {
+        const uint32_t k = k0 + u * kEmitBlock;
+        cur[u]           = k < n_valid ? recs[k] : make_uint2(0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kEmitBatch; ++u) pb[u] = ld_row(a.rows + cur[u].x);
+#pragma unroll
+      for (int u = 0; u < kEmitBatch; ++u) {
+        const uint32_t k = k0 + u * kEmitBlock;
+        if (k >= n_valid) continue;
+        const uint32_t j = cur[u].y & ((1u << kRecSrcBits) - 1u);
+        uint4          lo, hi;
+        if (staged) {
+          lo = src_lo[j];
+          hi = src_hi[j];
+        } else {
+          const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
+          lo             = __ldg(q);
+          hi             = __ldg(q + 1);
+        }
+        const int a0 = int32_t(lo.x), a1 = int32_t(lo.y), b0 = pb[u].ir0, b1 = pb[u].ir1;
+        const int ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
+        const double common = double(ov1 - ov0 + 1); // MatchMap.cpp:195-202, as in pair_emit_rows_kernel
+        const double sa     = double((unsigned long long)(long long)int32_t(lo.w));
+        const double sbb    = double((unsigned long long)(long long)pb[u].score);
+        const double sc_a   = __ddiv_rn(__dmul_rn(sa, common), double(a1 - a0 + 1));
+        const double sc_b   = __ddiv_rn(__dmul_rn(sbb, common), double(b1 - b0 + 1));
+        const uint32_t la = hi.x, fa = hi.y;
+        const unsigned long long o = em0 + k;
+        a.out.em_unitig[o] = hi.z;
+        a.out.em_ov0[o]    = ov0;
+        a.out.em_ov1[o]    = ov1;
+        a.out.em_score[o]  = __dadd_rn(sc_a, sc_b);
+        a.out.em_line[o]   = la > pb[u].line ? la : pb[u].line;
+        a.out.em_flags[o]  = uint8_t((((fa ^ pb[u].flags) & 1u) ? 0u : 1u) | ((fa & pb[u].flags & 2u) ? 2u : 0u));
+        if (cur[u].y & (1u << kRecSrcBits)) {
+          const unsigned long long eo = ed0 + (cur[u].y >> (kRecSrcBits + 1));
+          a.out.first[eo]    = lo.z;
+          a.out.second[eo]   = pb[u].read;
+          a.out.em_begin[eo] = a.em_value_base + o;
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host side: planning (everything up to the tile table) and emission of a range of tiles, so that a result can be
 // produced whole (resident) or chunk by chunk (results larger than HBM, downloads overlapped with the pairing)
@@ -1156,6 +1261,13 @@ void pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_
   //  stores — 0.75 ms instead of 0.49 ms at yeast scale, profiles/r2_ab_emit_vec_vs_scalar_and_fused.log: the kernel is
   //  bound by the latency of its gathers, and a thread that owns a quad serialises four of them behind one another
   //  where four strided records keep four independent chains in flight)
+  const char *emit = std::getenv("MSGPU_EMIT");
+  if (emit && std::string(emit) == "bulk") { // the TMA-staged A/B (see pair_emit_rows_bulk_kernel)
+    const int bytes = int(kTileCap * sizeof(uint2));
+    MSGPU_CUDA(cudaFuncSetAttribute(pair_emit_rows_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_bulk_kernel<<<grid, kEmitBlock, bytes, st>>>(ea));
+    return;
+  }
   MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
 }
 

@@ -6,4 +6,5 @@ for w in ${WORKLOADS:-yeast}; do
     [ -e "$lib" ] || continue
     echo "== $lib $w"; MSGPU_LIB=$PWD/$lib python scripts/quick_step.py $w 2>&1 | tail -3
   done
+  echo "== MSGPU_EMIT=bulk $w"; MSGPU_EMIT=bulk python scripts/quick_step.py $w 2>&1 | tail -3
 done
