@@ -940,8 +940,8 @@ __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs 
 
 // The same emission with the tile's records brought into shared memory by ONE bulk copy (cp.async.bulk — the 1-D form of
 // the TMA unit, SASS UBLKCP — completing on an mbarrier) instead of coalesced per-thread loads: a tile's records are one
-// contiguous, 16-byte aligned run, the shape bulk copies want.  The A/B the north star asks for ("staged via TMA");
-// selected with MSGPU_EMIT=bulk, result in DESIGN.md §4.  (The candidates of the tile kernel are NOT such a shape:
+// contiguous, 16-byte aligned run, the shape bulk copies want.  The north star's "staged via TMA", measured against the
+// per-thread form (MSGPU_EMIT=scalar) and adopted: DESIGN.md §4.  (The candidates of the tile kernel are NOT such a shape:
 // a source's partner slice starts at an arbitrary 4-byte offset of three separate columns, and staging 4096
 // candidates x 12 bytes would take the shared memory that buys the kernel its four resident CTAs.)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -1261,14 +1261,16 @@ void pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_
   //  stores — 0.75 ms instead of 0.49 ms at yeast scale, profiles/r2_ab_emit_vec_vs_scalar_and_fused.log: the kernel is
   //  bound by the latency of its gathers, and a thread that owns a quad serialises four of them behind one another
   //  where four strided records keep four independent chains in flight)
+  // The product stages a tile's records with one bulk copy (pair_emit_rows_bulk_kernel: 0.482 ms against 0.506 ms at
+  // yeast scale, profiles/r2_ab_emit_bulk_vs_scalar_yeast.log); MSGPU_EMIT=scalar keeps the per-thread loads as the A/B.
   const char *emit = std::getenv("MSGPU_EMIT");
-  if (emit && std::string(emit) == "bulk") { // the TMA-staged A/B (see pair_emit_rows_bulk_kernel)
-    const int bytes = int(kTileCap * sizeof(uint2));
-    MSGPU_CUDA(cudaFuncSetAttribute(pair_emit_rows_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_bulk_kernel<<<grid, kEmitBlock, bytes, st>>>(ea));
+  if (emit && std::string(emit) == "scalar") {
+    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
     return;
   }
-  MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
+  const int bytes = int(kTileCap * sizeof(uint2));
+  MSGPU_CUDA(cudaFuncSetAttribute(pair_emit_rows_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_bulk_kernel<<<grid, kEmitBlock, bytes, st>>>(ea));
 }
 
 // reads the row counts of the last emission and the error flags of the plan (one round trip); throws on the

@@ -6,5 +6,5 @@ for w in ${WORKLOADS:-yeast}; do
     [ -e "$lib" ] || continue
     echo "== $lib $w"; MSGPU_LIB=$PWD/$lib python scripts/quick_step.py $w 2>&1 | tail -3
   done
-  echo "== MSGPU_EMIT=bulk $w"; MSGPU_EMIT=bulk python scripts/quick_step.py $w 2>&1 | tail -3
+  echo "== MSGPU_EMIT=scalar $w"; MSGPU_EMIT=scalar python scripts/quick_step.py $w 2>&1 | tail -3
 done

@@ -127,12 +127,12 @@ def test_sort_based_variant_agrees_with_fused(builder, monkeypatch):
     assert tables_equal(fused, srt) == []
 
 
-def test_bulk_copy_emission_variant_agrees_with_the_product(builder, monkeypatch):
-    """MSGPU_EMIT=bulk brings a tile's records into shared memory with one cp.async.bulk (the TMA unit's 1-D copy) on
-    an mbarrier instead of per-thread loads — the A/B of DESIGN.md §4.  Same tables, bit for bit."""
+def test_per_thread_emission_variant_agrees_with_the_product(builder, monkeypatch):
+    """The product brings a tile's records into shared memory with one cp.async.bulk (the TMA unit's 1-D copy) on an
+    mbarrier; MSGPU_EMIT=scalar loads them per thread — the A/B of DESIGN.md §4.  Same tables, bit for bit."""
     for paf in (synth.generate_paf("ecoli"), util.heavy_rows_paf()):
         want = util.gpu_to_tables(builder.build_from_buffer(paf).result())
-        monkeypatch.setenv("MSGPU_EMIT", "bulk")
+        monkeypatch.setenv("MSGPU_EMIT", "scalar")
         got = util.gpu_to_tables(builder.build_from_buffer(paf).result())
         monkeypatch.delenv("MSGPU_EMIT")
         assert tables_equal(got, want) == []
