@@ -76,6 +76,27 @@ int msgpu_build_from_paf(msgpu_ctx *ctx, const char *paf_path);
 int msgpu_build_from_paf_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes);
 int msgpu_build_from_paf_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes);
 
+/* ---- the scrubber's anchor graph ---------------------------------------------------------------------
+ * msgpu_anchor_graph_from_paf_*  replaces the loop of pipeline/scrubber_bfs.py:57-114 — the pre-filter that decides
+ * which nanopore reads reach the assembler — on the same PAF columns: the same per-unitig read pairing as
+ * calculateEdges, with the scrubber's rules instead of BlastFileReader's:
+ *   - a line is line.rstrip().split("\t"); a line with ONE field is skipped; 2..8 fields, or a field 1 2 3 6 7 8 that
+ *     Python's int() rejects, are MSGPU_ERR_INVALID_PAF (the script dies with IndexError / ValueError); digit-group
+ *     underscores and values beyond 32 bits, which int() accepts, are reported as invalid too
+ *   - EVERY line is read (no last-line drop); a line is accepted iff c3 - c2 >= 500 (scrubber_bfs.py:85)
+ *   - reads (graph nodes) and anchors are numbered by first accepted appearance; read_nlen = field 6 of that line
+ *   - per (read, anchor) the first accepted line is kept (scrubber_bfs.py:97-98); the match table holds these rows in
+ *     LINE order with RAW ranges: m_nr0 / m_nr1 = (s_2, e_2) as the script stores them, m_ir0 / m_ir1 = (s_1, e_1),
+ *     m_score = field 1 (the anchor's length), m_flags bit0 = strand '+'
+ *   - an edge joins two reads kept in the same BLOCK of consecutive kept rows naming one anchor
+ *     (scrubber_bfs.py:103-113); there is no overlap test
+ * Result: the usual tables.  edge_first / edge_second are the graph's edges (each pair once, first < second).  The
+ * edge-match rows list, per edge, the blocks that produced it (em_unitig = the block's anchor; the other columns carry
+ * what the pairing kernels compute and mean nothing to the scrubber).  msgpu_chain_overlaps / msgpu_edge_filters do
+ * not apply to this graph (MSGPU_ERR_NO_RESULT). */
+int msgpu_anchor_graph_from_paf_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes);
+int msgpu_anchor_graph_from_paf_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes);
+
 /* Packed structure-of-arrays match records (the result of ingest, = the VertexMatch rows of MatchMap.h:51-59 plus
  * their ids), grouped by unitig and ordered by line inside a unitig.  Device pointers.
  * flags: bit0 = direction ('+'), bit1 = isPrimary. */

@@ -88,6 +88,8 @@ SIGNATURES = {
     "msgpu_build_from_paf": (C.c_int, [C.c_void_p, C.c_char_p]),
     "msgpu_build_from_paf_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "msgpu_build_from_paf_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "msgpu_anchor_graph_from_paf_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "msgpu_anchor_graph_from_paf_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "msgpu_build_from_records": (C.c_int, [C.c_void_p, C.POINTER(MatchSoA), C.c_uint32, C.c_uint32]),
     "msgpu_shard_ingest_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "msgpu_shard_ingest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),

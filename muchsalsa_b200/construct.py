@@ -109,6 +109,17 @@ class GraphBuilder:
         self._check(self._lib.msgpu_build_from_paf_device(self._h, C.c_void_p(dev_ptr), n_bytes))
         return self
 
+    def anchor_graph_from_buffer(self, buf):
+        """The scrubber's anchor graph (pipeline/scrubber_bfs.py:57-114) of a PAF in host memory; see include/msgpu.h."""
+        ptr, n, keep = _host_ptr(buf)
+        self._keep = keep
+        self._check(self._lib.msgpu_anchor_graph_from_paf_buffer(self._h, C.c_void_p(ptr), n))
+        return self
+
+    def anchor_graph_from_device(self, dev_ptr: int, n_bytes: int):
+        self._check(self._lib.msgpu_anchor_graph_from_paf_device(self._h, C.c_void_p(dev_ptr), n_bytes))
+        return self
+
     def build_from_records(self, rec: dict, n_reads: int, n_unitigs: int):
         """rec: dict of torch CUDA tensors (unitig, read, ir0, ir1, nr0, nr1, score, line, flags)."""
         soa = _lib.MatchSoA()

@@ -261,6 +261,90 @@ __device__ __forceinline__ bool parse_one_line(const char *s, uint64_t len, uint
   return acc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The pipeline's scrubber reads the same PAF with other rules (pipeline/scrubber_bfs.py:57-100):
+//   line.rstrip().split("\t")            trailing white space is not part of the line; a line with ONE field is skipped
+//   linetemp[0..8], int() of 1 2 3 6 7 8  fewer than nine fields -> IndexError, a non-integer -> ValueError (both: invalid)
+//   e_1 - s_1 >= 500                      the only accept rule (unitig span; no match count, no last-line drop)
+// Ranges are kept RAW here ((s_2, e_2) is what the script stores, scrubber_bfs.py:100), and int() is Python's: optional
+// white space on both sides, an optional sign, digits — nothing may follow (std::stoi stops at the first non-digit).
+// Python's digit-group underscores ("1_000") and values beyond 32 bits are reported as invalid.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool py_isspace(char c) { return c == ' ' || (c >= '\t' && c <= '\r') || (c >= 0x1c && c <= 0x1f); }
+
+__device__ __forceinline__ bool dev_pyint(const char *s, uint32_t n, int *out) {
+  uint32_t i = 0;
+  while (i < n && py_isspace(s[i])) ++i;
+  while (n > i && py_isspace(s[n - 1])) --n;
+  bool neg = false;
+  if (i < n && (s[i] == '+' || s[i] == '-')) {
+    neg = s[i] == '-';
+    ++i;
+  }
+  if (i >= n) return false;
+  unsigned long long v = 0;
+  for (; i < n; ++i) {
+    const uint32_t d = uint32_t(s[i]) - uint32_t('0');
+    if (d > 9u) return false;
+    v = v * 10ull + d;
+    if (v > 2147483648ull) return false; // beyond int: not representable in the tables
+  }
+  if (!neg && v > 2147483647ull) return false;
+  *out = neg ? int(0ll - (long long)v) : int(v);
+  return true;
+}
+
+__device__ __forceinline__ bool parse_one_line_scrubber(const char *s, uint64_t len, uint64_t li, uint64_t seed,
+                                                        LineFields &f, bool *bad_out) {
+  uint32_t n = len < 0xfffffff0ull ? uint32_t(len) : 0xfffffff0u;
+  while (n && py_isspace(s[n - 1])) --n; // str.rstrip()
+  uint32_t fo[9], fl[9];
+  int      ntok = 0;
+  uint32_t p    = 0;
+  bool     more = n > 0; // split("\t"): one field per tab, plus one (an empty line is one empty field: skipped below)
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    fo[k] = 0;
+    fl[k] = 0;
+    if (more) {
+      uint32_t q = p;
+      while (q < n && s[q] != '\t') ++q;
+      fo[k] = p;
+      fl[k] = q - p;
+      ntok  = k + 1;
+      more  = q < n; // a tab follows (the stripped line cannot END in a tab, so another field does)
+      p     = q + 1;
+    }
+  }
+  uint8_t flags = 0;
+  bool    bad = false, acc = false;
+  if (ntok >= 2) { // (one field: the line is skipped, scrubber_bfs.py:76-77)
+    int len_1 = 0, len_2 = 0, s_1 = 0, s_2 = 0, e_1 = 0, e_2 = 0;
+    bad = ntok < 9 || !(dev_pyint(s + fo[1], fl[1], &len_1) && dev_pyint(s + fo[6], fl[6], &len_2) &&
+                        dev_pyint(s + fo[2], fl[2], &s_1) && dev_pyint(s + fo[7], fl[7], &s_2) &&
+                        dev_pyint(s + fo[3], fl[3], &e_1) && dev_pyint(s + fo[8], fl[8], &e_2));
+    if (!bad && (long long)e_1 - (long long)s_1 >= 500ll) { // threshold_length, scrubber_bfs.py:50,85
+      flags = kFAccepted;
+      if (fl[4] == 1 && s[fo[4]] == '+') flags |= kFDir;
+      f.c2[li]        = s_1;
+      f.ir1[li]       = e_1;
+      f.c6[li]        = len_2;
+      f.nr0[li]       = s_2;
+      f.nr1[li]       = e_2;
+      f.c9[li]        = len_1;
+      f.rname_rel[li] = fo[5];
+      f.rname_len[li] = fl[5];
+      f.uname_len[li] = fl[0];
+      f.rhash[li]     = name_hash(s + fo[5], fl[5], seed);
+      f.uhash[li]     = name_hash(s + fo[0], fl[0], seed ^ 0x9e3779b97f4a7c15ull);
+      acc             = true;
+    }
+  }
+  *bad_out    = bad;
+  f.flags[li] = flags;
+  return acc;
+}
+
 // One thread per line, a block per run of 256 consecutive lines.  A thread walks its line byte by byte; straight from
 // global memory that costs one L1 wavefront per lane and byte (32 lanes, 32 different cache lines).  So the block
 // first copies the text of its 256 lines — one contiguous piece of the buffer — into shared memory with coalesced
@@ -268,6 +352,7 @@ __device__ __forceinline__ bool parse_one_line(const char *s, uint64_t len, uint
 constexpr int      kParseBlock = 256;
 constexpr uint32_t kParseStage = 40 * 1024;
 
+template <bool kScrubber>
 __global__ void __launch_bounds__(kParseBlock)
     parse_lines_kernel(const char *__restrict__ paf, uint64_t n_bytes, const uint64_t *__restrict__ line_start,
                        uint64_t seed, LineFields f, IngestStatus *status) {
@@ -294,7 +379,7 @@ __global__ void __launch_bounds__(kParseBlock)
       const uint64_t len = line_start[li + 1] - ls - 1; // getLine() drops the last character of the line
       const char    *s   = staged ? stage + a0 + (ls - b0) : paf + ls;
       bool           bad;
-      if (parse_one_line(s, len, li, seed, f, &bad)) ++n_acc;
+      if (kScrubber ? parse_one_line_scrubber(s, len, li, seed, f, &bad) : parse_one_line(s, len, li, seed, f, &bad)) ++n_acc;
       if (bad) atomicMin(&status->first_bad_line, (unsigned long long)li);
     }
   }
@@ -520,6 +605,38 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// The scrubber pairs the reads of a BLOCK: consecutive processed lines that name the same anchor
+// (scrubber_bfs.py:103-113).  Records are in line order; a record starts a block iff its anchor differs from its
+// predecessor's.
+struct BlockStart {
+  const uint32_t *unitig;
+  __device__ uint32_t operator()(uint64_t i) const { return (i == 0 || unitig[i] != unitig[i - 1]) ? 1u : 0u; }
+};
+__global__ void __launch_bounds__(256)
+    block_ids_kernel(const uint32_t *__restrict__ unitig, uint64_t n, const uint32_t *__restrict__ before,
+                     uint32_t *__restrict__ block, uint32_t *__restrict__ block_unitig) {
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const bool     start = i == 0 || unitig[i] != unitig[i - 1];
+    const uint32_t b     = before[i] + (start ? 1u : 0u) - 1u;
+    block[i]             = b;
+    if (start) block_unitig[b] = unitig[i];
+  }
+}
+
+template <class T> static T read_back(Arena &arena, cudaStream_t st, const T *d);
+
+uint64_t run_scrubber_blocks(Arena &arena, cudaStream_t st, const MatchSoA &m, uint32_t **block_out,
+                             uint32_t **block_unitig_out) {
+  const uint64_t M = m.n;
+  uint32_t *before = arena.alloc<uint32_t>(M + 1), *block = arena.alloc<uint32_t>(M + 1);
+  uint32_t *block_unitig = arena.alloc<uint32_t>(M + 1), *d_n = arena.alloc<uint32_t>(1);
+  exclusive_scan<uint32_t>(arena, st, BlockStart{m.unitig}, M, before, d_n);
+  if (M) MSGPU_LAUNCH("block_ids", st, block_ids_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, M, before, block, block_unitig));
+  *block_out        = block;
+  *block_unitig_out = block_unitig;
+  return uint64_t(read_back(arena, st, d_n));
+}
+
 static uint64_t next_pow2(uint64_t x) {
   uint64_t p = 1024;
   while (p < x) p <<= 1;
@@ -638,7 +755,7 @@ void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &m, uint64_t n_unit
 }
 
 void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
-                ReadTable &reads, UnitigTable &unitigs, MatchSoA &m, bool drop_last_line) {
+                ReadTable &reads, UnitigTable &unitigs, MatchSoA &m, bool drop_last_line, bool scrubber) {
   reads = ReadTable{};
   unitigs = UnitigTable{};
   m = MatchSoA{};
@@ -706,7 +823,10 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     // seeds are odd multiples of a constant, never 0; the test hook makes the first attempt collide on purpose
     const bool     force = attempt == 0 && std::getenv("MSGPU_TEST_FORCE_COLLISION") != nullptr;
     const uint64_t seed  = force ? 0ull : 0x243f6a8885a308d3ull * uint64_t(attempt + 1);
-    MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
+    if (scrubber)
+      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<true><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
+    else
+      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<false><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
 
     const ScanLive live_lines{nullptr, &d_status->n_lines, 0}; // the per-line scans stop at the actual line count
     // ---- K3 interning
@@ -748,6 +868,7 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   unitigs.n       = h.n_unitigs;
   unitigs.n_bytes = h.unitig_name_bytes;
   m.n             = h.n_matches;
+  if (scrubber) return; // records stay in line order: the scrubber pairs blocks of consecutive lines (run_scrubber_blocks)
   // grouping sort only when the PAF was not grouped by unitig (minimap2 emits by query, so it normally is)
   group_by_unitig(arena, st, m, h.n_unitigs, h.unsorted ? 1 : 0);
   build_group_offsets(arena, st, m, unitigs);

@@ -99,6 +99,7 @@ struct PairPlan {
   const uint32_t *wide_list = nullptr; // tiles (sub-tiles of rows with 513 .. 4095 sources) for the wide instantiation
   uint32_t        n_wide = 0;
   uint32_t       *flags = nullptr; // device: [2] a read with too many sources, [3] tile invariant violated
+  bool            no_overlap_test = false; // the scrubber's pairing keeps every pair of a group
   uint64_t        n_reads = 0, n_pairs = 0;
   uint32_t        n_tiles = 0, tile_lo = 0, tile_hi = 0;
 };
@@ -117,7 +118,11 @@ struct BuildError {
 
 // ingest.cu : PAF text in HBM -> read table, unitig table (+ group offsets), match SoA   (K1-K5)
 void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
-                ReadTable &reads, UnitigTable &unitigs, MatchSoA &matches, bool drop_last_line = true);
+                ReadTable &reads, UnitigTable &unitigs, MatchSoA &matches, bool drop_last_line = true,
+                bool scrubber = false);
+// scrubber mode: block id of every record (records in line order) + the anchor of every block; returns the block count
+uint64_t run_scrubber_blocks(Arena &arena, cudaStream_t st, const MatchSoA &matches, uint32_t **block_out,
+                             uint32_t **block_unitig_out);
 void alloc_match_soa(Arena &arena, MatchSoA &s, uint64_t n);
 // stable sort of the rows by unitig id unless they are grouped already (known_unsorted: 1 / 0 = the caller has
 // checked, -1 = check here, which costs a round trip to the host)
@@ -134,10 +139,10 @@ void run_pairing_sorted(Arena &arena, cudaStream_t st, const MatchSoA &matches, 
 // of the tiles, and its tables are that slice of the global result (multi-GPU); 0 of 1 = everything.
 void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs,
                        uint64_t n_reads, EdgeTables &edges, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts,
-                       PairPlan *plan_out);
+                       PairPlan *plan_out, bool no_overlap_test = false);
 // the same in pieces, for chunked emission (msgpu_chunk_next): plan once, then emit ranges of tiles
 void     pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &matches, const UnitigTable &unitigs, uint64_t n_reads,
-                      uint32_t part, uint32_t n_parts, PairPlan &plan);
+                      uint32_t part, uint32_t n_parts, PairPlan &plan, bool no_overlap_test = false);
 void     pairing_scratch_alloc(Arena &arena, uint32_t max_tiles, PairScratch &sc);
 uint64_t pairing_rows_bound(const PairPlan &plan, uint32_t n_tiles);
 void     pairing_outputs_alloc(Arena &arena, uint64_t cap, EdgeTables &e);

@@ -375,6 +375,76 @@ int msgpu_build_from_paf(msgpu_ctx *ctx, const char *paf_path) {
   });
 }
 
+namespace {
+__global__ void __launch_bounds__(256)
+    block_to_anchor_kernel(uint32_t *__restrict__ em_unitig, uint64_t n, const uint32_t *__restrict__ block_unitig) {
+  for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += uint64_t(gridDim.x) * blockDim.x)
+    em_unitig[k] = block_unitig[em_unitig[k]];
+}
+
+// the scrubber's anchor graph (pipeline/scrubber_bfs.py:57-114) from PAF text in HBM
+void anchor_graph_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes) {
+  cudaStream_t st  = ctx->stream;
+  ctx->have_result = false;
+  ctx->host_valid  = false;
+  ctx->n_parts     = 1;
+  ctx->orders      = OrderTables{};
+  ctx->filters     = FilterTables{};
+  {
+    cudaEvent_t keep      = ctx->chunks.rows_done;
+    ctx->chunks           = msgpu_ctx::Chunks{};
+    ctx->chunks.rows_done = keep;
+  }
+  ctx->arena.reset();
+  ctx->profiler.clear();
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
+  run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches, false, true);
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
+  // groups = blocks of consecutive processed lines naming the same anchor; every pair of a block is an edge
+  uint32_t *block = nullptr, *block_unitig = nullptr;
+  const uint64_t n_blocks = run_scrubber_blocks(ctx->arena, st, ctx->matches, &block, &block_unitig);
+  MatchSoA by_block = ctx->matches;
+  by_block.unitig   = block;
+  UnitigTable blocks;
+  blocks.n = n_blocks;
+  build_group_offsets(ctx->arena, st, by_block, blocks);
+  run_pairing_fused(ctx->arena, st, by_block, blocks, ctx->reads.n, ctx->edges, ctx->ev[3], 0, 1, nullptr, true);
+  if (ctx->edges.n_em)
+    MSGPU_LAUNCH("block_to_anchor", st, block_to_anchor_kernel<<<grid_for(ctx->edges.n_em, 256), 256, 0, st>>>(
+                                            ctx->edges.em_unitig, ctx->edges.n_em, block_unitig));
+  ctx->edges.pair_rows = nullptr; // (the stages after construction do not apply to this graph)
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
+  MSGPU_CUDA(cudaStreamSynchronize(st));
+  ctx->timings           = msgpu_timings{};
+  ctx->timings.ingest_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  ctx->timings.pair_ms   = elapsed(ctx->ev[2], ctx->ev[3]);
+  ctx->timings.merge_ms  = elapsed(ctx->ev[3], ctx->ev[4]);
+  ctx->timings.total_ms  = elapsed(ctx->ev[1], ctx->ev[4]);
+  ctx->have_result       = true;
+}
+} // namespace
+
+int msgpu_anchor_graph_from_paf_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes) {
+  return guarded(ctx, [&] {
+    if (!dev_paf && n_bytes) throw BuildError{MSGPU_ERR_INVALID_ARG, "null PAF buffer"};
+    anchor_graph_device(ctx, dev_paf, n_bytes);
+  });
+}
+
+int msgpu_anchor_graph_from_paf_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes) {
+  return guarded(ctx, [&] {
+    if (!host_paf && n_bytes) throw BuildError{MSGPU_ERR_INVALID_ARG, "null PAF buffer"};
+    cudaStream_t st = ctx->stream;
+    ctx->input_arena.reset();
+    char *d_paf = ctx->input_arena.alloc<char>(n_bytes + 16);
+    MSGPU_CUDA(cudaEventRecord(ctx->ev[0], st));
+    if (n_bytes) MSGPU_CUDA(cudaMemcpyAsync(d_paf, host_paf, n_bytes, cudaMemcpyHostToDevice, st));
+    anchor_graph_device(ctx, d_paf, n_bytes);
+    ctx->timings.h2d_ms = elapsed(ctx->ev[0], ctx->ev[1]);
+    ctx->timings.total_ms += ctx->timings.h2d_ms;
+  });
+}
+
 int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t n_reads, uint32_t n_unitigs) {
   return guarded(ctx, [&] {
     if (!r) throw BuildError{MSGPU_ERR_INVALID_ARG, "null records"};

@@ -493,6 +493,7 @@ struct TileArgs {
   uint2          *tile_cnt;         // per tile: (surviving candidates, run heads)
   unsigned int   *error;
   uint32_t        wide; // 0: every sort word fits 32 bits for any tile, so the launch carries the small buffers only
+  uint32_t        no_overlap_test; // the scrubber's pairing: every pair of a group is kept (scrubber_bfs.py:109-113)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -554,7 +555,7 @@ __device__ __forceinline__ uint32_t enumerate_candidates(const TileArgs &a, Merg
         const uint32_t sr = a.p_read[ib];
         const int      a0 = s.src.ir0[j], a1 = s.src.ir1[j], b0 = a.p_ir0[ib], b1 = a.p_ir1[ib];
         const int      o0 = a0 > b0 ? a0 : b0, o1 = a1 < b1 ? a1 : b1;
-        const bool     keep = o0 <= o1 && o1 - o0 > kThOverlapF; // MatchMap.cpp:192
+        const bool     keep = (o0 <= o1 && o1 - o0 > kThOverlapF) || a.no_overlap_test; // MatchMap.cpp:192
         wa[e]               = (W(sr - smin) << kIdxBits) | W(e);
         s.ent_src[e]        = uint16_t(j) | (keep ? uint16_t(0) : kDropped);
         kept += keep ? 1u : 0u;
@@ -734,8 +735,10 @@ __global__ void __launch_bounds__(kFusedBlock, kSB == kSrcBits ? kMergeCtas : 1)
     }
     // ---- stage the sources, blockDim.x at a time (one pass for the product instantiation)
     uint32_t carry = 0, lmin = 0xffffffffu, lmax = 0, row_src = 0;
-    for (uint32_t j0 = 0; j0 < n_src || j0 == 0; j0 += kFusedBlock) {
-      const uint32_t j   = j0 + t;
+#pragma unroll
+    for (uint32_t pass = 0; pass < kCap / kFusedBlock; ++pass) { // (exactly one pass in the product instantiation)
+      if (pass && pass * kFusedBlock >= n_src) break;
+      const uint32_t j   = pass * kFusedBlock + t;
       uint32_t       len = 0;
       if (j < n_src) {
         const uint32_t q   = a.rd_src[q0 + j];
@@ -1048,8 +1051,9 @@ __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_bulk_kernel(Emit
 // produced whole (resident) or chunk by chunk (results larger than HBM, downloads overlapped with the pairing)
 // ---------------------------------------------------------------------------------------------------------------------
 void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
-                  uint32_t part, uint32_t n_parts, PairPlan &pl) {
+                  uint32_t part, uint32_t n_parts, PairPlan &pl, bool no_overlap_test) {
   pl = PairPlan{};
+  pl.no_overlap_test = no_overlap_test;
   const uint64_t M = m.n, R = n_reads;
   if (R >= 0xfffffff0ull || M >= 0xfffffff0ull)
     throw BuildError{MSGPU_ERR_LIMIT, "pairing supports < 2^32 reads and matches per device"};
@@ -1200,6 +1204,7 @@ static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, cons
   // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits; otherwise
   // tiles choose per tile and the launch carries the 64-bit buffers
   a.wide = pl.n_reads > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)
+  a.no_overlap_test = pl.no_overlap_test ? 1u : 0u;
   return a;
 }
 
@@ -1293,10 +1298,11 @@ void pairing_finish(Arena &arena, cudaStream_t st, const PairPlan &pl, const Pai
 }
 
 void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigTable &unitigs, uint64_t n_reads,
-                       EdgeTables &e, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts, PairPlan *plan_out) {
+                       EdgeTables &e, cudaEvent_t ev_pair_done, uint32_t part, uint32_t n_parts, PairPlan *plan_out,
+                       bool no_overlap_test) {
   e = EdgeTables{};
   PairPlan pl;
-  pairing_plan(arena, st, m, unitigs, n_reads, part, n_parts, pl);
+  pairing_plan(arena, st, m, unitigs, n_reads, part, n_parts, pl, no_overlap_test);
   e.n_pairs = pl.n_pairs;
   const uint32_t my_tiles = pl.tile_hi - pl.tile_lo;
   pairing_outputs_alloc(arena, pairing_rows_bound(pl, my_tiles), e);
@@ -1317,7 +1323,7 @@ void run_pairing(Arena &arena, cudaStream_t st, const MatchSoA &m, const UnitigT
   if (v && std::string(v) == "sorted" && n_parts <= 1)
     run_pairing_sorted(arena, st, m, unitigs, n_reads, e, ev_pair_done);
   else
-    run_pairing_fused(arena, st, m, unitigs, n_reads, e, ev_pair_done, part, n_parts, nullptr);
+    run_pairing_fused(arena, st, m, unitigs, n_reads, e, ev_pair_done, part, n_parts, nullptr, false);
 }
 
 } // namespace msgpu
