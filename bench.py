@@ -617,6 +617,11 @@ def run_ours_big(args):
         dist.destroy_process_group()
 
 
+def _traffic(workload, kernel):
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(tp)).get(workload, {}).get(kernel) if os.path.exists(tp) else None
+
+
 def check_parity(gb, workload, rank, world, dist):
     """Is what the timed steps build the reference's result?  Every rank digests its slice of the edge tables on the
     device (msgpu_result_digest: order-independent sums + invariant violations); the sums over the ranks must equal
@@ -735,6 +740,8 @@ def bench_sequences(gb, workload, stream, n_req=1 << 20):
            "host_buffers_ms": round(host_s * 1e3, 3), "host_buffers_bases_per_s": bases / host_s,
            "all_requests_ok": ok,
            "roofline": {"kernel": "slice_copy", "bound": "hbm", "algorithmic_bytes_per_launch": 2 * bases,
+                        "traffic": _traffic(workload, "slice_copy"),
+                        "traffic_note": "ncu capture of scripts/profile_seq.py (read-flank requests only: 2.48e9 bases)",
                         "us_per_launch": round(copy_ms * 1e3, 2), "achieved": round(2 * bases / copy_ms / 1e6, 1),
                         "peak": peak, "unit": "GB/s", "frac": round(2 * bases / copy_ms / 1e6 / peak, 4),
                         "peak_source": peak_src, "definition": "SURVEY.md §8(d): requested bases x (1 read + 1 write)"},

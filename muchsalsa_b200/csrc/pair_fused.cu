@@ -725,7 +725,10 @@ __global__ void __launch_bounds__(kFusedBlock, kSB == kSrcBits ? kMergeCtas : 1)
     const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
     const uint32_t q0 = a.rd_off[r0];
     const uint32_t n_src = (kind ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
-    if (!kIsWide && n_src > kCap) continue; // a sub-tile of a row with many sources: the wide instantiation takes it
+    if (!kIsWide && n_src > kCap) { // a sub-tile of a row with many sources: the wide instantiation takes it ...
+      if (n_src >= kSrcCapWide && t == 0) a.tile_cnt[st_idx] = make_uint2(0, 0); // ... unless the build is refused
+      continue;                                                                  // (write_tiles_kernel flags the row)
+    }
     if (n_src > kCap) {                     // cannot happen: the planning refuses rows with more sources than that
       if (t == 0) {
         *a.error           = 1;
