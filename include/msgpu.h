@@ -97,6 +97,35 @@ int msgpu_build_from_paf_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_by
 int msgpu_anchor_graph_from_paf_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes);
 int msgpu_anchor_graph_from_paf_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes);
 
+/* ---- the unitig filter's coverage profiles -----------------------------------------------------------
+ * Replaces the two passes of pipeline/unitig_filter.py over its PAF (the pre-filter that removes over-covered unitigs
+ * and cuts the peaks out of the rest).  Rules of the script, not BlastFileReader's: every line counts (no accept rule,
+ * no skipped line, no last-line drop); a line is line.rstrip().split("\t") and needs fields 0..6 with 1, 2, 3, 6
+ * integers for Python's int() (else MSGPU_ERR_INVALID_PAF, as for positions outside the unitig: IndexError).
+ *   msgpu_unitig_coverage_from_paf_*   pass 1 (unitig_filter.py:34-75).  Per BLOCK of consecutive lines naming one
+ *                  unitig, in file order: block_unitig (id = rank of first appearance; names through
+ *                  msgpu_result_host: unitig_names), block_n_reads (distinct reads), block_len (the unitig length of the
+ *                  block's first line) and block_max_cov = the maximum over the unitig's positions of the number of
+ *                  reads covering it, a read counting ONCE per block (its first line there; c2 .. c3 - 1 inclusive).
+ *   msgpu_unitig_coverage_cut          pass 2 (unitig_filter.py:102-176) for the cut-offs the caller derives from pass 1
+ *                  (:83-97): block_outlier[b] = 1 iff the maximum of the LAST block of b's unitig is > cutoff; such a
+ *                  block is profiled again with ALL its lines and cut into the maximal runs of positions with coverage
+ *                  <= q3 that are >= 500 long: fragments (frag_block, frag_start, frag_end inclusive), in file order.
+ * Pointers are pinned host memory, valid until the next build on the context. */
+typedef struct msgpu_coverage {
+  uint64_t        n_blocks;
+  const uint32_t *block_unitig, *block_n_reads, *block_len, *block_max_cov;
+} msgpu_coverage;
+typedef struct msgpu_fragments {
+  uint64_t        n_blocks, n_fragments;
+  const uint8_t  *block_outlier;
+  const uint32_t *frag_block;
+  const int32_t  *frag_start, *frag_end;
+} msgpu_fragments;
+int msgpu_unitig_coverage_from_paf_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes, msgpu_coverage *out);
+int msgpu_unitig_coverage_from_paf_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes, msgpu_coverage *out);
+int msgpu_unitig_coverage_cut(msgpu_ctx *ctx, double cutoff, double q3, msgpu_fragments *out);
+
 /* Packed structure-of-arrays match records (the result of ingest, = the VertexMatch rows of MatchMap.h:51-59 plus
  * their ids), grouped by unitig and ordered by line inside a unitig.  Device pointers.
  * flags: bit0 = direction ('+'), bit1 = isPrimary. */

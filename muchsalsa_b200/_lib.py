@@ -43,6 +43,16 @@ class Chunk(C.Structure):
                 ("em_ov0", i32p), ("em_ov1", i32p), ("em_score", f64p), ("em_line", u32p), ("em_flags", u8p)]
 
 
+class Coverage(C.Structure):
+    _fields_ = [("n_blocks", C.c_uint64), ("block_unitig", u32p), ("block_n_reads", u32p), ("block_len", u32p),
+                ("block_max_cov", u32p)]
+
+
+class Fragments(C.Structure):
+    _fields_ = [("n_blocks", C.c_uint64), ("n_fragments", C.c_uint64), ("block_outlier", u8p), ("frag_block", u32p),
+                ("frag_start", i32p), ("frag_end", i32p)]
+
+
 class Timings(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "ingest_ms", "pair_ms", "merge_ms", "d2h_ms", "total_ms")]
 
@@ -90,6 +100,9 @@ SIGNATURES = {
     "msgpu_build_from_paf_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "msgpu_anchor_graph_from_paf_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "msgpu_anchor_graph_from_paf_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "msgpu_unitig_coverage_from_paf_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Coverage)]),
+    "msgpu_unitig_coverage_from_paf_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Coverage)]),
+    "msgpu_unitig_coverage_cut": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.POINTER(Fragments)]),
     "msgpu_build_from_records": (C.c_int, [C.c_void_p, C.POINTER(MatchSoA), C.c_uint32, C.c_uint32]),
     "msgpu_shard_ingest_buffer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "msgpu_shard_ingest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),

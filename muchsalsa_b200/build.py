@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libmsgpu.so")
 STAMP = os.path.join(HERE, ".libmsgpu.stamp")
 
-SOURCES = ["msgpu_api.cu", "ingest.cu", "pair_sort.cu", "pair_fused.cu", "chain.cu", "filter.cu", "shard.cu", "seq.cu", "digest.cu"]
+SOURCES = ["msgpu_api.cu", "ingest.cu", "pair_sort.cu", "pair_fused.cu", "chain.cu", "filter.cu", "shard.cu", "seq.cu", "digest.cu", "coverage.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "--fmad=false",  # the score arithmetic must not be contracted into FMAs (bit-exact doubles, MatchMap.cpp:195-202)

@@ -120,6 +120,25 @@ class GraphBuilder:
         self._check(self._lib.msgpu_anchor_graph_from_paf_device(self._h, C.c_void_p(dev_ptr), n_bytes))
         return self
 
+    def unitig_coverage_from_buffer(self, buf) -> dict:
+        """Pass 1 of the unitig filter (pipeline/unitig_filter.py:34-75): per block of consecutive lines naming one
+        unitig its unitig id, distinct reads, length and maximum coverage (numpy copies); see include/msgpu.h."""
+        ptr, n, keep = _host_ptr(buf)
+        self._keep = keep
+        c = _lib.Coverage()
+        self._check(self._lib.msgpu_unitig_coverage_from_paf_buffer(self._h, C.c_void_p(ptr), n, C.byref(c)))
+        B = int(c.n_blocks)
+        return dict(block_unitig=_np(c.block_unitig, B, np.uint32), block_n_reads=_np(c.block_n_reads, B, np.uint32),
+                    block_len=_np(c.block_len, B, np.uint32), block_max_cov=_np(c.block_max_cov, B, np.uint32))
+
+    def unitig_coverage_cut(self, cutoff: float, q3: float) -> dict:
+        """Pass 2 (unitig_filter.py:102-176): outlier flag per block and the fragments of the outlier blocks."""
+        f = _lib.Fragments()
+        self._check(self._lib.msgpu_unitig_coverage_cut(self._h, float(cutoff), float(q3), C.byref(f)))
+        B, F = int(f.n_blocks), int(f.n_fragments)
+        return dict(block_outlier=_np(f.block_outlier, B, np.uint8), frag_block=_np(f.frag_block, F, np.uint32),
+                    frag_start=_np(f.frag_start, F, np.int32), frag_end=_np(f.frag_end, F, np.int32))
+
     def build_from_records(self, rec: dict, n_reads: int, n_unitigs: int):
         """rec: dict of torch CUDA tensors (unitig, read, ir0, ir1, nr0, nr1, score, line, flags)."""
         soa = _lib.MatchSoA()

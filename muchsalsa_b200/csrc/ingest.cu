@@ -345,6 +345,57 @@ __device__ __forceinline__ bool parse_one_line_scrubber(const char *s, uint64_t 
   return acc;
 }
 
+// The pipeline's unitig filter reads the PAF with yet other rules (pipeline/unitig_filter.py:42-50): every line counts
+// (no accept rule, no skipped lines), fields 0, 1, 2, 3, 5, 6 must exist (IndexError otherwise) and 1, 2, 3, 6 must be
+// integers for Python's int().  Kept per line: illuminaStart = c2, illuminaEnd = c3 - 1, the unitig length (field 1).
+__device__ __forceinline__ bool parse_one_line_coverage(const char *s, uint64_t len, uint64_t li, uint64_t seed,
+                                                        LineFields &f, bool *bad_out) {
+  uint32_t n = len < 0xfffffff0ull ? uint32_t(len) : 0xfffffff0u;
+  while (n && py_isspace(s[n - 1])) --n; // str.rstrip()
+  uint32_t fo[7], fl[7];
+  int      ntok = 0;
+  uint32_t p    = 0;
+  bool     more = n > 0;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    fo[k] = 0;
+    fl[k] = 0;
+    if (more) {
+      uint32_t q = p;
+      while (q < n && s[q] != '\t') ++q;
+      fo[k] = p;
+      fl[k] = q - p;
+      ntok  = k + 1;
+      more  = q < n;
+      p     = q + 1;
+    }
+  }
+  int  ulen = 0, c2 = 0, c3 = 0, rlen = 0;
+  bool bad  = ntok < 7 || !(dev_pyint(s + fo[1], fl[1], &ulen) && dev_pyint(s + fo[2], fl[2], &c2) &&
+                           dev_pyint(s + fo[3], fl[3], &c3) && dev_pyint(s + fo[6], fl[6], &rlen));
+  // positions index a list of `ulen` counters: a start below 0 or an end beyond the unitig raises IndexError (or,
+  // negative, silently wraps around in Python: reported as invalid here); an empty unitig has no maximum (ValueError)
+  if (!bad) bad = ulen <= 0 || c2 < 0 || c3 - 1 >= ulen;
+  uint8_t flags = 0;
+  if (!bad) {
+    flags           = kFAccepted;
+    f.c2[li]        = c2;
+    f.ir1[li]       = c3 - 1;
+    f.c6[li]        = rlen;
+    f.nr0[li]       = 0;
+    f.nr1[li]       = 0;
+    f.c9[li]        = ulen;
+    f.rname_rel[li] = fo[5];
+    f.rname_len[li] = fl[5];
+    f.uname_len[li] = fl[0];
+    f.rhash[li]     = name_hash(s + fo[5], fl[5], seed);
+    f.uhash[li]     = name_hash(s + fo[0], fl[0], seed ^ 0x9e3779b97f4a7c15ull);
+  }
+  *bad_out    = bad;
+  f.flags[li] = flags;
+  return !bad;
+}
+
 // One thread per line, a block per run of 256 consecutive lines.  A thread walks its line byte by byte; straight from
 // global memory that costs one L1 wavefront per lane and byte (32 lanes, 32 different cache lines).  So the block
 // first copies the text of its 256 lines — one contiguous piece of the buffer — into shared memory with coalesced
@@ -352,7 +403,7 @@ __device__ __forceinline__ bool parse_one_line_scrubber(const char *s, uint64_t 
 constexpr int      kParseBlock = 256;
 constexpr uint32_t kParseStage = 40 * 1024;
 
-template <bool kScrubber>
+template <int kMode> // 0: BlastFileReader's rules, 1: the scrubber's, 2: the unitig filter's
 __global__ void __launch_bounds__(kParseBlock)
     parse_lines_kernel(const char *__restrict__ paf, uint64_t n_bytes, const uint64_t *__restrict__ line_start,
                        uint64_t seed, LineFields f, IngestStatus *status) {
@@ -379,7 +430,10 @@ __global__ void __launch_bounds__(kParseBlock)
       const uint64_t len = line_start[li + 1] - ls - 1; // getLine() drops the last character of the line
       const char    *s   = staged ? stage + a0 + (ls - b0) : paf + ls;
       bool           bad;
-      if (kScrubber ? parse_one_line_scrubber(s, len, li, seed, f, &bad) : parse_one_line(s, len, li, seed, f, &bad)) ++n_acc;
+      const bool acc = kMode == 1   ? parse_one_line_scrubber(s, len, li, seed, f, &bad)
+                       : kMode == 2 ? parse_one_line_coverage(s, len, li, seed, f, &bad)
+                                    : parse_one_line(s, len, li, seed, f, &bad);
+      if (acc) ++n_acc;
       if (bad) atomicMin(&status->first_bad_line, (unsigned long long)li);
     }
   }
@@ -539,6 +593,22 @@ __global__ void __launch_bounds__(256)
        li += uint64_t(gridDim.x) * blockDim.x) {
     uint8_t fl = flags[li];
     if ((fl & kFAccepted) && dt.minline[dslot[li]] == uint32_t(li)) flags[li] = fl | kFSurvivor;
+  }
+}
+
+// the unitig filter keeps EVERY line (its per-read dedup is per block, done after the blocks are known)
+__global__ void __launch_bounds__(256)
+    all_survive_kernel(const IngestStatus *__restrict__ status, uint8_t *__restrict__ flags, InternTable rt,
+                       const uint32_t *__restrict__ rslot, InternTable ut, const uint32_t *__restrict__ uslot,
+                       uint32_t *__restrict__ rid_of_line, uint32_t *__restrict__ uid_of_line) {
+  const uint64_t n_parse = status->n_parse;
+  for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
+       li += uint64_t(gridDim.x) * blockDim.x) {
+    const uint8_t fl = flags[li];
+    if (!(fl & kFAccepted)) continue;
+    rid_of_line[li] = rt.id[rslot[li]];
+    uid_of_line[li] = ut.id[uslot[li]];
+    flags[li]       = fl | kFSurvivor;
   }
 }
 
@@ -755,7 +825,8 @@ void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &m, uint64_t n_unit
 }
 
 void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
-                ReadTable &reads, UnitigTable &unitigs, MatchSoA &m, bool drop_last_line, bool scrubber) {
+                ReadTable &reads, UnitigTable &unitigs, MatchSoA &m, bool drop_last_line, int mode) {
+  const bool scrubber = mode != 0; // (1: scrubber, 2: unitig filter — both keep the records in line order)
   reads = ReadTable{};
   unitigs = UnitigTable{};
   m = MatchSoA{};
@@ -823,10 +894,12 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     // seeds are odd multiples of a constant, never 0; the test hook makes the first attempt collide on purpose
     const bool     force = attempt == 0 && std::getenv("MSGPU_TEST_FORCE_COLLISION") != nullptr;
     const uint64_t seed  = force ? 0ull : 0x243f6a8885a308d3ull * uint64_t(attempt + 1);
-    if (scrubber)
-      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<true><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
+    if (mode == 1)
+      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<1><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
+    else if (mode == 2)
+      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<2><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
     else
-      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<false><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
+      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<0><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
 
     const ScanLive live_lines{nullptr, &d_status->n_lines, 0}; // the per-line scans stop at the actual line count
     // ---- K3 interning
@@ -845,8 +918,12 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
                       NameJob{&d_status->n_unitigs, usrc, ulen, &d_status->unitig_name_bytes, &unitigs});
 
     // ---- K4 dedup
-    MSGPU_LAUNCH("dedup_insert", st, dedup_insert_kernel<<<grid_lines, 256, 0, st>>>(d_status, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line, uid_of_line));
-    MSGPU_LAUNCH("dedup_flag", st, dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(d_status, f.flags, dt, dslot));
+    if (mode == 2) {
+      MSGPU_LAUNCH("all_survive", st, all_survive_kernel<<<grid_lines, 256, 0, st>>>(d_status, f.flags, rt, rslot, ut, uslot, rid_of_line, uid_of_line));
+    } else {
+      MSGPU_LAUNCH("dedup_insert", st, dedup_insert_kernel<<<grid_lines, 256, 0, st>>>(d_status, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line, uid_of_line));
+      MSGPU_LAUNCH("dedup_flag", st, dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(d_status, f.flags, dt, dslot));
+    }
 
     // ---- K5 compaction
     exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFSurvivor}, cap, rank_a, &d_status->n_matches, live_lines);

@@ -119,7 +119,7 @@ struct BuildError {
 // ingest.cu : PAF text in HBM -> read table, unitig table (+ group offsets), match SoA   (K1-K5)
 void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_bytes, uint64_t *n_lines_out,
                 ReadTable &reads, UnitigTable &unitigs, MatchSoA &matches, bool drop_last_line = true,
-                bool scrubber = false);
+                int mode = 0 /* 0 BlastFileReader's rules, 1 scrubber_bfs.py's, 2 unitig_filter.py's */);
 // scrubber mode: block id of every record (records in line order) + the anchor of every block; returns the block count
 uint64_t run_scrubber_blocks(Arena &arena, cudaStream_t st, const MatchSoA &matches, uint32_t **block_out,
                              uint32_t **block_unitig_out);
@@ -173,6 +173,29 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
 
 // digest.cu : order-independent checksum + structural invariants of the edge tables, in HBM
 void run_digest(Arena &arena, cudaStream_t st, const EdgeTables &edges, msgpu_digest *out);
+
+// coverage.cu : the per-unitig coverage profiles of the pipeline's unitig filter (pipeline/unitig_filter.py)
+struct CoverageTables {
+  bool      valid = false, cut_valid = false;
+  uint64_t  n_unitigs = 0, n_blocks = 0, n_positions = 0;
+  MatchSoA  m;                       // the records (every PAF line), in line order
+  uint32_t *rec_block = nullptr;     // block of every record
+  uint32_t *block_unitig = nullptr, *block_len = nullptr, *block_n_reads = nullptr, *block_max = nullptr;
+  uint64_t *block_off = nullptr;     // first counter slot of the block (length + 1 slots each)
+  uint32_t *starts = nullptr, *ends = nullptr, *slot = nullptr;
+  struct {
+    unsigned long long *keys = nullptr;
+    uint32_t           *minline = nullptr;
+    uint64_t            mask = 0;
+  } first_hit;
+  // pass 2
+  uint8_t  *block_outlier = nullptr;
+  uint64_t  n_frags = 0;
+  uint32_t *frag_block = nullptr;
+  int32_t  *frag_start = nullptr, *frag_end = nullptr;
+};
+void run_unitig_coverage(Arena &arena, cudaStream_t st, const MatchSoA &matches, uint64_t n_unitigs, CoverageTables &out);
+void run_unitig_cut(Arena &arena, cudaStream_t st, CoverageTables &cov, double cutoff, double q3);
 
 // chain.cu : the stage after construction — per edge chaining of its edge matches and the overlap geometry
 // (src/main.cpp:328-414, mpp.cpp:38-305, ol.cpp:31-101) -> shadow flag + EdgeOrder rows

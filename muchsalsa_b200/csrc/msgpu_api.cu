@@ -96,6 +96,9 @@ struct msgpu_ctx {
   cudaEvent_t  copy_done[2]{};
   bool         copy_pending[2] = {false, false}; // a download of that buffer set is in flight on copy_stream
 
+  CoverageTables coverage; // msgpu_unitig_coverage_*
+  PinnedBuf      host_coverage, host_fragments;
+
   SeqStore *seq = nullptr;
   Profiler  profiler;
 };
@@ -398,7 +401,7 @@ void anchor_graph_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes) {
   ctx->arena.reset();
   ctx->profiler.clear();
   MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
-  run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches, false, true);
+  run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches, false, 1);
   MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
   // groups = blocks of consecutive processed lines naming the same anchor; every pair of a block is an edge
   uint32_t *block = nullptr, *block_unitig = nullptr;
@@ -442,6 +445,100 @@ int msgpu_anchor_graph_from_paf_buffer(msgpu_ctx *ctx, const char *host_paf, siz
     anchor_graph_device(ctx, d_paf, n_bytes);
     ctx->timings.h2d_ms = elapsed(ctx->ev[0], ctx->ev[1]);
     ctx->timings.total_ms += ctx->timings.h2d_ms;
+  });
+}
+
+namespace {
+void unitig_coverage_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes, msgpu_coverage *out) {
+  cudaStream_t st  = ctx->stream;
+  ctx->have_result = false;
+  ctx->host_valid  = false;
+  ctx->n_parts     = 1;
+  ctx->orders      = OrderTables{};
+  ctx->filters     = FilterTables{};
+  ctx->coverage    = CoverageTables{};
+  {
+    cudaEvent_t keep      = ctx->chunks.rows_done;
+    ctx->chunks           = msgpu_ctx::Chunks{};
+    ctx->chunks.rows_done = keep;
+  }
+  ctx->arena.reset();
+  ctx->profiler.clear();
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
+  run_ingest(ctx->arena, st, d_paf, n_bytes, &ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches, false, 2);
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[2], st));
+  run_unitig_coverage(ctx->arena, st, ctx->matches, ctx->unitigs.n, ctx->coverage);
+  ctx->edges          = EdgeTables{}; // no graph: the read / unitig / record tables are what msgpu_result_host returns
+  ctx->edges.em_begin = ctx->arena.alloc<uint64_t>(1);
+  MSGPU_CUDA(cudaMemsetAsync(ctx->edges.em_begin, 0, sizeof(uint64_t), st));
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[3], st));
+  const CoverageTables &c = ctx->coverage;
+  const uint64_t        B = c.n_blocks;
+  char *h = static_cast<char *>(ctx->host_coverage.get(4 * (B + 1) * sizeof(uint32_t) + 64));
+  uint32_t *hu = reinterpret_cast<uint32_t *>(h);
+  const uint32_t *src[4] = {c.block_unitig, c.block_n_reads, c.block_len, c.block_max};
+  for (int k = 0; k < 4; ++k)
+    if (B) MSGPU_CUDA(cudaMemcpyAsync(hu + k * (B + 1), src[k], B * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  MSGPU_CUDA(cudaEventRecord(ctx->ev[4], st));
+  MSGPU_CUDA(cudaStreamSynchronize(st));
+  ctx->timings           = msgpu_timings{};
+  ctx->timings.ingest_ms = elapsed(ctx->ev[1], ctx->ev[2]);
+  ctx->timings.pair_ms   = elapsed(ctx->ev[2], ctx->ev[3]);
+  ctx->timings.total_ms  = elapsed(ctx->ev[1], ctx->ev[4]);
+  ctx->have_result       = true;
+  out->n_blocks          = B;
+  out->block_unitig      = hu;
+  out->block_n_reads     = hu + (B + 1);
+  out->block_len         = hu + 2 * (B + 1);
+  out->block_max_cov     = hu + 3 * (B + 1);
+}
+} // namespace
+
+int msgpu_unitig_coverage_from_paf_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_bytes, msgpu_coverage *out) {
+  if (!out) return MSGPU_ERR_INVALID_ARG;
+  return guarded(ctx, [&] {
+    if (!dev_paf && n_bytes) throw BuildError{MSGPU_ERR_INVALID_ARG, "null PAF buffer"};
+    unitig_coverage_device(ctx, dev_paf, n_bytes, out);
+  });
+}
+
+int msgpu_unitig_coverage_from_paf_buffer(msgpu_ctx *ctx, const char *host_paf, size_t n_bytes, msgpu_coverage *out) {
+  if (!out) return MSGPU_ERR_INVALID_ARG;
+  return guarded(ctx, [&] {
+    if (!host_paf && n_bytes) throw BuildError{MSGPU_ERR_INVALID_ARG, "null PAF buffer"};
+    cudaStream_t st = ctx->stream;
+    ctx->input_arena.reset();
+    char *d_paf = ctx->input_arena.alloc<char>(n_bytes + 16);
+    if (n_bytes) MSGPU_CUDA(cudaMemcpyAsync(d_paf, host_paf, n_bytes, cudaMemcpyHostToDevice, st));
+    unitig_coverage_device(ctx, d_paf, n_bytes, out);
+  });
+}
+
+int msgpu_unitig_coverage_cut(msgpu_ctx *ctx, double cutoff, double q3, msgpu_fragments *out) {
+  if (!out) return MSGPU_ERR_INVALID_ARG;
+  return guarded(ctx, [&] {
+    if (!ctx->have_result || !ctx->coverage.valid)
+      throw BuildError{MSGPU_ERR_NO_RESULT, "msgpu_unitig_coverage_cut needs msgpu_unitig_coverage_from_paf_* first"};
+    cudaStream_t st = ctx->stream;
+    ctx->profiler.clear();
+    run_unitig_cut(ctx->arena, st, ctx->coverage, cutoff, q3);
+    const CoverageTables &c = ctx->coverage;
+    const uint64_t        B = c.n_blocks, F = c.n_frags;
+    const size_t o_block = (B + 64) & ~size_t(63), o_start = o_block + (F + 1) * 4, o_end = o_start + (F + 1) * 4;
+    char *h = static_cast<char *>(ctx->host_fragments.get(o_end + (F + 1) * 4 + 64));
+    if (B) MSGPU_CUDA(cudaMemcpyAsync(h, c.block_outlier, B, cudaMemcpyDeviceToHost, st));
+    if (F) {
+      MSGPU_CUDA(cudaMemcpyAsync(h + o_block, c.frag_block, F * 4, cudaMemcpyDeviceToHost, st));
+      MSGPU_CUDA(cudaMemcpyAsync(h + o_start, c.frag_start, F * 4, cudaMemcpyDeviceToHost, st));
+      MSGPU_CUDA(cudaMemcpyAsync(h + o_end, c.frag_end, F * 4, cudaMemcpyDeviceToHost, st));
+    }
+    MSGPU_CUDA(cudaStreamSynchronize(st));
+    out->n_blocks      = B;
+    out->n_fragments   = F;
+    out->block_outlier = reinterpret_cast<const uint8_t *>(h);
+    out->frag_block    = reinterpret_cast<const uint32_t *>(h + o_block);
+    out->frag_start    = reinterpret_cast<const int32_t *>(h + o_start);
+    out->frag_end      = reinterpret_cast<const int32_t *>(h + o_end);
   });
 }
 
