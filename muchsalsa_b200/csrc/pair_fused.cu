@@ -59,7 +59,10 @@ constexpr uint32_t kSrcCapWide = 1u << kSrcBitsWide; // edge cannot hold more ed
 constexpr uint32_t kHalfCap    = kTileCap / 2;
 constexpr uint32_t kSrcRatio   = kHalfCap / (kSrcCap / 2); // a source weighs at least this much when tiles are packed
 constexpr int      kItems      = kTileCap / kFusedBlock;   // sort items per thread
-constexpr int      kMergeCtas  = kIdxBits <= 12 ? 4 : 2;    // resident CTAs of the merge kernel per SM (narrow words)
+#ifndef MSGPU_MERGE_CTAS
+#define MSGPU_MERGE_CTAS (MSGPU_IDX_BITS <= 12 ? 4 : 2)
+#endif
+constexpr int      kMergeCtas  = MSGPU_MERGE_CTAS;          // resident CTAs of the merge kernel per SM (narrow words)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // pre-pass 1: order every group by read id, build the pair rows, and accumulate per read its number of sources and
@@ -567,30 +570,43 @@ __device__ __forceinline__ uint32_t enumerate_candidates(const TileArgs &a, Merg
 
 // the merge levels; returns the buffer that holds the sorted words (the other one is free afterwards).  Starts and
 // ends with a barrier.
+#ifndef MSGPU_MERGE_ODD
+#define MSGPU_MERGE_ODD 1
+#endif
 template <class W, int kSB>
 __device__ __forceinline__ W *merge_levels(MergeShared<kSB> &s, W *wa, W *wb, uint32_t n_ent) {
-  const unsigned t   = threadIdx.x;
-  const uint32_t per = (n_ent + kFusedBlock - 1) / kFusedBlock;
+  constexpr uint32_t kSrcMask = MergeShared<kSB>::kSrcMask;
+  const unsigned t = threadIdx.x;
+  // `per` consecutive outputs per thread.  An ODD count: lane l starts at word l * per, and an odd stride spreads the
+  // 32 lanes of a warp over all 32 banks (a stride of 8 puts four lanes on every bank it touches).
+  uint32_t per = (n_ent + kFusedBlock - 1) / kFusedBlock;
+  if (MSGPU_MERGE_ODD) per |= 1u;
   __syncthreads();
   W *in = wa, *out = wb;
   const uint32_t max_row = s.max_row_src;
+  const uint32_t pos0 = t * per;
+  const uint32_t oe   = pos0 + per < n_ent ? pos0 + per : n_ent;
   for (uint32_t lvl = 0; (1u << lvl) < max_row; ++lvl) {
-    const uint32_t G   = 1u << lvl;
-    uint32_t       pos = t * per; // `per` consecutive outputs per thread: every thread of the block has work
-    const uint32_t oe  = pos + per < n_ent ? pos + per : n_ent;
-    while (pos < oe) {
-      const uint32_t j  = s.ent_src[pos] & MergeShared<kSB>::kSrcMask; // slice that owns output position pos
-      const uint32_t rf = s.src.row_first[j], re = s.src.row_end[j];
-      const uint32_t s0 = rf + (((j - rf) >> (lvl + 1)) << (lvl + 1)); // the pair: runs [s0, s1) and [s1, s2)
-      const uint32_t s1 = s0 + G < re ? s0 + G : re, s2 = s0 + 2 * G < re ? s0 + 2 * G : re;
-      const uint32_t a0 = s.src.base[s0], a1 = s.src.base[s1], b1 = s.src.base[s2];
-      const uint32_t seg_end = oe < b1 ? oe : b1;
-      if (a1 == b1 || a0 == a1) { // one side empty: the run is copied
-        for (uint32_t p = pos; p < seg_end; ++p) out[p] = in[p];
+    if (pos0 < oe) {
+      const uint32_t G = 1u << lvl;
+      // the pair of runs whose outputs contain position p: [a0, a1) and [a1, b1), found from the slice that owns slot p
+      uint32_t a0, a1, b1;
+      auto pair_of = [&](uint32_t p) {
+        const uint32_t j  = s.ent_src[p] & kSrcMask;
+        const uint32_t rf = s.src.row_first[j], re = s.src.row_end[j];
+        const uint32_t s0 = rf + (((j - rf) >> (lvl + 1)) << (lvl + 1));
+        const uint32_t s1 = s0 + G < re ? s0 + G : re, s2 = s0 + 2 * G < re ? s0 + 2 * G : re;
+        a0 = s.src.base[s0];
+        a1 = s.src.base[s1];
+        b1 = s.src.base[s2];
+      };
+      pair_of(pos0);
+      if (a1 == b1 && b1 >= oe) { // a run without a partner that covers this thread's outputs: copied
+        for (uint32_t p = pos0; p < oe; ++p) out[p] = in[p];
       } else {
-        const uint32_t k  = pos - a0, na = a1 - a0, nb = b1 - a1;
+        const uint32_t k  = pos0 - a0, na = a1 - a0, nb = b1 - a1;
         uint32_t       lo = k > nb ? k - nb : 0u, hi = k < na ? k : na; // merge path: elements of A among the first k
-        while (lo < hi) {
+        while (lo < hi) {                                               // (an empty side leaves lo == hi)
           const uint32_t mid = (lo + hi) >> 1;
           if (in[a0 + mid] < in[a1 + (k - 1 - mid)]) lo = mid + 1; else hi = mid;
         }
@@ -598,8 +614,15 @@ __device__ __forceinline__ W *merge_levels(MergeShared<kSB> &s, W *wa, W *wb, ui
         // below 2^20 - 1, and 64-bit words have their top bits clear), so one compare decides a step.
         uint32_t ia = a0 + lo, ib = a1 + (k - lo);
         W        xa = ia < a1 ? in[ia] : ~W(0), xb = ib < b1 ? in[ib] : ~W(0);
-        for (uint32_t p = pos; p < seg_end; ++p) { // branch-free step: one select, one reload of the side that moved
-          const bool take_a = xa < xb;
+        for (uint32_t p = pos0; p < oe; ++p) { // one loop for all of the thread's outputs: every lane of a warp runs
+          if (p == b1) {                       // the same `per` steps; a lane that crosses into the next pair of runs
+            pair_of(p);                        // starts it at its beginning, where the partition is trivial
+            ia = a0;
+            ib = a1;
+            xa = ia < a1 ? in[ia] : ~W(0);
+            xb = ib < b1 ? in[ib] : ~W(0);
+          }
+          const bool take_a = xa < xb; // branch-free step: one select, one reload of the side that moved
           out[p]            = take_a ? xa : xb;
           ia += take_a ? 1u : 0u;
           ib += take_a ? 0u : 1u;
@@ -609,7 +632,6 @@ __device__ __forceinline__ W *merge_levels(MergeShared<kSB> &s, W *wa, W *wb, ui
           xb                = take_a ? xb : v;
         }
       }
-      pos = seg_end;
     }
     __syncthreads();
     W *tmp = in;
@@ -859,12 +881,19 @@ struct EmitArgs {
 };
 
 
+#ifndef MSGPU_EMIT_CTAS
+#define MSGPU_EMIT_CTAS 3
+#endif
+#ifndef MSGPU_EMIT_BATCH
+#define MSGPU_EMIT_BATCH 4
+#endif
 constexpr int kEmitBlock = 256;
-constexpr int kEmitBatch = 4; // records in flight per thread: the partner gathers are latency-bound, so overlap them
+constexpr int kEmitCtas  = MSGPU_EMIT_CTAS;  // resident CTAs per SM the emission kernels are compiled for
+constexpr int kEmitBatch = MSGPU_EMIT_BATCH; // records in flight per thread: the partner gathers are latency-bound
 
 // One CTA per tile (strided).  The tile's sources (the `first` side of its records, <= 512 rows) are staged in shared
 // memory once; every record then needs ONE dependent gather (its partner's row) after its own coalesced load.
-__global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs a) {
+__global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_kernel(EmitArgs a) {
   __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
   const unsigned   t = threadIdx.x;
   if (blockIdx.x == 0 && t == 0) a.out.em_begin[a.totals[1]] = a.em_value_base + a.totals[0]; // closes the CSR
@@ -952,7 +981,7 @@ __global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_kernel(EmitArgs 
 // candidates x 12 bytes would take the shared memory that buys the kernel its four resident CTAs.)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
-__global__ void __launch_bounds__(kEmitBlock, 3) pair_emit_rows_bulk_kernel(EmitArgs a) {
+__global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_bulk_kernel(EmitArgs a) {
   __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
   __shared__ __align__(8) unsigned long long bar;
   extern __shared__ __align__(16) unsigned char bulk_raw[];

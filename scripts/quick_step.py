@@ -35,3 +35,7 @@ with GraphBuilder(0) as gb:
     print(w, "wall ms/step", [round(t, 3) for t in ts], "timings", gb.timings())
     print(dict(sorted(ks.items(), key=lambda kv: -kv[1])))
     print({k: c[k] for k in ("n_edges", "n_edge_matches")})
+    import json  # noqa: E402
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "sum_digests.json"))).get(w + "x1")
+    d = gb.digest()
+    print("digest", "== golden" if gold and all(int(d[k]) == int(gold[k]) for k in ("edge_sum", "em_sum", "n_edges", "n_edge_matches")) else ("!= golden" if gold else "(no golden)"), d)
