@@ -172,6 +172,31 @@ def test_read_that_shares_more_unitigs_than_a_product_tile_stages(builder, oracl
     assert int(np.diff(got.edge_em_begin.astype(np.int64)).max()) >= n_unitigs // 3
 
 
+def hub_rows_paf(n_unitigs, per_unitig, pool=60, seed=3):
+    """A read (`hub`) that shares `n_unitigs` unitigs with `per_unitig` reads each, drawn from a pool of `pool` reads:
+    its row of the edge table has n_unitigs sources and n_unitigs * per_unitig candidates — more than a tile, so the row
+    is split by value ranges across ALL its sources; the pool reads' rows are heavy too."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    L = util.paf_line
+    rows = []
+    for u in range(n_unitigs):
+        a = u * 3000
+        rows.append(L(f"u{u}", 5000, 0, 3000, "+", "hub", 20_000_000, a, a + 3000, 2900))
+        for r in rng.choice(pool, min(per_unitig, pool), replace=False):
+            s = int(rng.integers(0, 1500))
+            rows.append(L(f"u{u}", 5000, s, s + 3000, "+-"[int(r) % 2], f"x{int(r)}", 15_000_000, a + 200, a + 3200, 2800))
+    return b"".join(rows) + L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
+
+
+@pytest.mark.parametrize("n_unitigs,per_unitig", [(100, 100), (300, 30), (500, 20)])
+def test_heavy_rows_with_hundreds_of_sources_vs_oracle(builder, oracle, n_unitigs, per_unitig):
+    """The value-range split of a heavy row bisects over all its sources at once (split_heavy_kernel: 1, 4 or 16
+    sources per lane, each with a shrinking window).  Rows with 100, 300 and 500 sources; bit-exact with the oracle."""
+    paf = hub_rows_paf(n_unitigs, per_unitig, pool=max(60, per_unitig + 20))
+    got = _same(builder, oracle, paf)
+    assert got.counts["em"] > n_unitigs * per_unitig
+
+
 def test_read_with_4096_shared_unitigs_is_the_limit(builder):
     """An edge cannot hold more edge matches than a pairing tile holds candidates (4096): a read sharing that many
     unitigs with partners (>= 10 Mb of read) is refused with MSGPU_ERR_LIMIT — not a crash, not a wrong answer."""
