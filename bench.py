@@ -351,7 +351,7 @@ def run_ours(args):
     if world > 1:
         x = [v for v in xch_ms if v is not None]
         x_ms = reduce(sum(x) / len(x), "MAX") if x else None
-        out["exchange"] = {"what": "all-gather of the ranks' match-table blobs (NCCL over NVLink)",
+        out["exchange"] = {"what": "the ranks' match-table blobs reach every rank: " + getattr(sb, "exchange_mode", "?"),
                            "bytes_received_per_rank": sb.exchange_bytes, "ms": x_ms,
                            "gbs_per_rank": (sb.exchange_bytes / x_ms / 1e6) if x_ms else None,
                            "nvlink_peak_gbs": 770.0}
@@ -609,7 +609,8 @@ def run_ours_big(args):
            "parity": parity["ok"], "parity_detail": parity,
            "device_mem_gb": round((torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 1e9, 1)}
     if world > 1:
-        out["exchange"] = {"bytes_received_per_rank": sb.exchange_bytes, "ms": sb.last_exchange_ms()}
+        out["exchange"] = {"what": getattr(sb, "exchange_mode", "?"), "bytes_received_per_rank": sb.exchange_bytes,
+                           "ms": sb.last_exchange_ms()}
     gb.close()
     if rank == 0:
         print(json.dumps(out), flush=True)

@@ -152,7 +152,8 @@ int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *dev_records,
  *   1. msgpu_shard_ingest_*   rank r parses the r-th contiguous chunk of the PAF (split at line boundaries; only the
  *                             last chunk drops its last line, BlastFileReader.cpp:76) -> chunk-local tables
  *   2. msgpu_shard_describe / msgpu_shard_export   the chunk-local tables as ONE flat device blob; the ranks
- *                             all-gather headers and blobs (NCCL over NVLink: torch.distributed.all_gather_into_tensor)
+ *                             all-gather headers and blobs (NCCL over NVLink: torch.distributed.all_gather_into_tensor),
+ *                             or msgpu_shard_export_peers writes the blob straight into every rank's buffer
  *   3. msgpu_build_from_shards   every rank merges all blobs into the global id space (ids = rank of first accepted
  *                             line over the whole file, keep-min-line across chunks, Registry.cpp:36-45,
  *                             MatchMap.cpp:64-73) and pairs ITS share `part` of `n_parts` of the edge rows.
@@ -169,6 +170,15 @@ int msgpu_shard_ingest_device(msgpu_ctx *ctx, const char *dev_paf, size_t n_byte
 int msgpu_shard_describe(const msgpu_ctx *ctx, msgpu_shard_header *out);
 /* writes blob_bytes bytes (see msgpu_shard_describe) to dev_blob, on the context's stream */
 int msgpu_shard_export(msgpu_ctx *ctx, void *dev_blob, uint64_t capacity);
+/* Export and all-gather in one kernel: writes the blob into dev_slots[0..n_slots) — this rank's slot of every rank's
+ * receive buffer, device pointers that may be PEER-mapped memory of other GPUs (CUDA IPC / symmetric memory; the
+ * stores to them travel over NVLink) — each `capacity` bytes, 16-byte aligned, n_slots <= 16.  Every unit of the blob
+ * is read once and stored n_slots times.  The header (the blob's first 64 bytes) is always written; the sections only
+ * if blob_bytes <= capacity, so after the caller's barrier every rank sees every size and all ranks reach the same
+ * verdict about a slot that was too small.  Asynchronous on the context's stream; ordering ACROSS ranks (all exports
+ * done before any rank reads its buffer; a buffer not overwritten while a peer still reads it) is the caller's:
+ * muchsalsa_b200/multi_gpu.py uses two buffer sets and one barrier per step. */
+int msgpu_shard_export_peers(msgpu_ctx *ctx, void *const *dev_slots, uint32_t n_slots, uint64_t capacity);
 int msgpu_build_from_shards(msgpu_ctx *ctx, uint32_t n_shards, const msgpu_shard_header *headers,
                             const void *const *dev_blobs, uint32_t part, uint32_t n_parts);
 

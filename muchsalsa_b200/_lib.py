@@ -108,6 +108,7 @@ SIGNATURES = {
     "msgpu_shard_ingest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "msgpu_shard_describe": (C.c_int, [C.c_void_p, C.POINTER(ShardHeader)]),
     "msgpu_shard_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "msgpu_shard_export_peers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint64]),
     "msgpu_build_from_shards": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(ShardHeader), C.POINTER(C.c_void_p),
                                           C.c_uint32, C.c_uint32]),
     "msgpu_result_counts": (C.c_int, [C.c_void_p, C.POINTER(Counts)]),

@@ -170,6 +170,12 @@ class GraphBuilder:
         self._check(self._lib.msgpu_shard_export(self._h, C.c_void_p(dev_ptr), capacity))
         return self
 
+    def shard_export_peers(self, dev_slots, capacity: int):
+        """The blob into this rank's slot of every rank's receive buffer (peer-mapped device pointers) in one kernel."""
+        arr = (C.c_void_p * len(dev_slots))(*[int(p) for p in dev_slots])
+        self._check(self._lib.msgpu_shard_export_peers(self._h, arr, len(dev_slots), capacity))
+        return self
+
     def build_from_shards(self, headers, blob_ptrs, part: int, n_parts: int):
         """headers: list of _lib.ShardHeader (one per rank, rank order); blob_ptrs: device pointers of the blobs."""
         n = len(headers)

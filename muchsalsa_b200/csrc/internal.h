@@ -167,6 +167,9 @@ msgpu_shard_header shard_describe(uint64_t n_lines, const ReadTable &reads, cons
                                   const MatchSoA &matches);
 void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable &reads, const UnitigTable &unitigs,
                   const MatchSoA &matches, void *dev_blob);
+constexpr uint32_t kMaxPeers = 16; // ranks one export kernel writes to (one node: 8 GPUs today)
+void shard_export_peers(cudaStream_t st, const msgpu_shard_header &h, const ReadTable &reads, const UnitigTable &unitigs,
+                        const MatchSoA &m, void *const *dev_slots, uint32_t n_slots, bool with_sections);
 void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msgpu_shard_header *headers,
                      const void *const *dev_blobs, uint64_t *n_lines_out, ReadTable &reads, UnitigTable &unitigs,
                      MatchSoA &matches);

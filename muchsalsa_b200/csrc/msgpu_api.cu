@@ -615,6 +615,19 @@ int msgpu_shard_export(msgpu_ctx *ctx, void *dev_blob, uint64_t capacity) {
   });
 }
 
+int msgpu_shard_export_peers(msgpu_ctx *ctx, void *const *dev_slots, uint32_t n_slots, uint64_t capacity) {
+  return guarded(ctx, [&] {
+    if (!ctx->have_result || !ctx->reads.name_off) throw BuildError{MSGPU_ERR_NO_RESULT, "no ingest result to export"};
+    if (!dev_slots || !n_slots || n_slots > kMaxPeers || capacity < sizeof(msgpu_shard_header))
+      throw BuildError{MSGPU_ERR_INVALID_ARG, "bad peer slots"};
+    for (uint32_t d = 0; d < n_slots; ++d)
+      if (!dev_slots[d] || (reinterpret_cast<uintptr_t>(dev_slots[d]) & 15u))
+        throw BuildError{MSGPU_ERR_INVALID_ARG, "peer slots must be 16-byte aligned device pointers"};
+    msgpu_shard_header h = shard_describe(ctx->n_lines, ctx->reads, ctx->unitigs, ctx->matches);
+    shard_export_peers(ctx->stream, h, ctx->reads, ctx->unitigs, ctx->matches, dev_slots, n_slots, h.blob_bytes <= capacity);
+  });
+}
+
 int msgpu_build_from_shards(msgpu_ctx *ctx, uint32_t n_shards, const msgpu_shard_header *headers,
                             const void *const *dev_blobs, uint32_t part, uint32_t n_parts) {
   return guarded(ctx, [&] {

@@ -95,13 +95,10 @@ __global__ void __launch_bounds__(256) pack_blob_kernel(PackJob job, char *__res
   }
 }
 
-void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable &reads, const UnitigTable &unitigs,
-                  const MatchSoA &m, void *dev_blob) {
+static PackJob pack_job(const msgpu_shard_header &h, const ReadTable &reads, const UnitigTable &unitigs, const MatchSoA &m) {
   const ShardLayout L = shard_layout(h);
-  char             *b = static_cast<char *>(dev_blob);
-  MSGPU_CUDA(cudaMemcpyAsync(b, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-  PackJob job{};
-  auto    put = [&](uint64_t off, const void *src, uint64_t bytes) {
+  PackJob           job{};
+  auto put = [&](uint64_t off, const void *src, uint64_t bytes) {
     if (!bytes) return;
     job.src[job.n]     = src;
     job.dst_off[job.n] = off;
@@ -124,7 +121,61 @@ void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable 
   put(L.m_score, m.score, M * 4);
   put(L.m_line, m.line, M * 4);
   put(L.m_flags, m.flags, M);
+  return job;
+}
+
+void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable &reads, const UnitigTable &unitigs,
+                  const MatchSoA &m, void *dev_blob) {
+  char *b = static_cast<char *>(dev_blob);
+  MSGPU_CUDA(cudaMemcpyAsync(b, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  const PackJob job = pack_job(h, reads, unitigs, m);
   if (job.n) MSGPU_LAUNCH("pack_blob", st, pack_blob_kernel<<<grid_for(h.blob_bytes / 16 + 1, 256, 2), 256, 0, st>>>(job, b));
+}
+
+// The export AND the all-gather in one kernel: every 16-byte unit of the blob is read once from this GPU's tables and
+// stored into this rank's slot of EVERY rank's receive buffer — peer-mapped device memory, so the stores to the other
+// ranks travel over NVLink / NVSwitch as posted writes while the kernel keeps reading.  No staging copy of the blob, no
+// collective launch; the caller orders the step with one barrier across the ranks afterwards.  The header rides in the
+// kernel's arguments and is written first (always: a rank whose blob does not fit its slot still tells the others how
+// big it is).
+struct PeerSlots {
+  char    *slot[kMaxPeers];
+  uint32_t n;
+};
+
+__global__ void __launch_bounds__(256) pack_blob_peers_kernel(PackJob job, PeerSlots dst, msgpu_shard_header h) {
+  const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = uint64_t(gridDim.x) * blockDim.x;
+  if (tid < sizeof(msgpu_shard_header) / 16) { // the header: four 16-byte units
+    const uint4 v = reinterpret_cast<const uint4 *>(&h)[tid];
+    for (uint32_t d = 0; d < dst.n; ++d) reinterpret_cast<uint4 *>(dst.slot[d])[tid] = v;
+  }
+  for (int k = 0; k < job.n; ++k) {
+    const char    *src = static_cast<const char *>(job.src[k]);
+    const uint64_t off = job.dst_off[k], nb = job.bytes[k];
+    uint64_t       done = 0;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) { // sections start 16-byte aligned in the blob
+      const uint64_t nv = nb >> 4;
+      for (uint64_t i = tid; i < nv; i += nth) {
+        const uint4 v = reinterpret_cast<const uint4 *>(src)[i];
+        for (uint32_t d = 0; d < dst.n; ++d) reinterpret_cast<uint4 *>(dst.slot[d] + off)[i] = v;
+      }
+      done = nv << 4;
+    }
+    for (uint64_t i = done + tid; i < nb; i += nth) {
+      const char v = src[i];
+      for (uint32_t d = 0; d < dst.n; ++d) dst.slot[d][off + i] = v;
+    }
+  }
+}
+
+void shard_export_peers(cudaStream_t st, const msgpu_shard_header &h, const ReadTable &reads, const UnitigTable &unitigs,
+                        const MatchSoA &m, void *const *dev_slots, uint32_t n_slots, bool with_sections) {
+  PeerSlots dst{};
+  dst.n = n_slots;
+  for (uint32_t d = 0; d < n_slots; ++d) dst.slot[d] = static_cast<char *>(dev_slots[d]);
+  PackJob job = pack_job(h, reads, unitigs, m);
+  if (!with_sections) job.n = 0;
+  MSGPU_LAUNCH("pack_blob_peers", st, pack_blob_peers_kernel<<<grid_for((with_sections ? h.blob_bytes : 0) / 16 + 1, 256, 2), 256, 0, st>>>(job, dst, h));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -122,6 +122,29 @@ class ShardedBuilder:
         gb, world = self.gb, self.world
         h = gb.shard_header()
         stride = getattr(self, "_stride", None)
+        peer = self._peer_buffers(stride) if stride is not None else None
+        if peer is not None:
+            # steady state on NVLink-connected GPUs: the export kernel stores the blob straight into every rank's
+            # receive buffer (msgpu_shard_export_peers), then ONE barrier across the ranks.  Two buffer sets alternate:
+            # a rank that is one step ahead writes the set its peers finished reading a step ago (its own barrier of
+            # the step in between completed only after every peer had queued that step's export behind those reads).
+            ev = self._timer()
+            tensor, hdl, ptrs = peer
+            self._peer_set = 1 - getattr(self, "_peer_set", 1)
+            base = self._peer_set * world * stride
+            gb.shard_export_peers([p + base + self.rank * stride for p in ptrs], stride)
+            hdl.barrier(channel=0)
+            local = tensor[base:base + world * stride].view(world, stride)
+            heads = local[:, :HEADER_BYTES].contiguous().view(torch.int64).view(world, HEADER_WORDS)
+            headers = tensor_to_headers(heads)  # device -> host: the one synchronisation of the exchange
+            if all(int(x.blob_bytes) <= stride for x in headers):
+                self._stop(ev)
+                self.exchange_mode = "peer stores (export kernel writes every rank's buffer over NVLink) + 1 barrier"
+                self.exchange_bytes = sum(int(x.blob_bytes) for i, x in enumerate(headers) if i != self.rank)
+                self._keep = tensor
+                return headers, [local.data_ptr() + s * stride for s in range(world)]
+            self._peer = None  # a blob outgrew its slot (every rank sees that): sizes first, below; new buffers next step
+            stride = None
         if stride is not None:
             # steady state: the stride that fitted every rank last time (plus slack) — ONE collective, one host sync
             ev = self._timer()
@@ -129,6 +152,7 @@ class ShardedBuilder:
                 h, lambda dst: gb.shard_export(dst.data_ptr(), dst.numel()), stride, world, self.dist, self.device)
             if ok:
                 self._stop(ev)
+                self.exchange_mode = "all-gather of [header | blob] slabs (NCCL over NVLink), one collective"
                 self.exchange_bytes = sum(int(x.blob_bytes) for i, x in enumerate(headers) if i != self.rank)
                 self._keep = blobs
                 return headers, [blobs.data_ptr() + s * stride + HEADER_BYTES for s in range(world)]
@@ -147,9 +171,45 @@ class ShardedBuilder:
             self._stop(ev)
         else:
             blobs = mine.view(1, stride)
+        self.exchange_mode = "all-gather of headers, then of blobs (NCCL over NVLink)"
         self.exchange_bytes = sum(int(x.blob_bytes) for i, x in enumerate(headers) if i != self.rank)
         self._keep = (mine, blobs)
         return headers, [blobs.data_ptr() + s * stride for s in range(world)]
+
+    PEER_BUFFER_LIMIT = 24 << 30  # bytes of peer-mapped receive buffers (two sets) a rank is willing to hold
+
+    def _peer_buffers(self, stride):
+        """(tensor, handle, peer pointers) of the symmetric receive buffers [2 sets][world][stride], allocated and
+        exchanged on first use (collective: every rank calls it in the same step with the same stride), or None when
+        peer memory is not available / disabled (MSGPU_PEER_EXCHANGE=0) — then the NCCL all-gather carries the blobs."""
+        import os
+        if self.world == 1 or self.stream is None or getattr(self, "_peer_off", False):
+            return None
+        cur = getattr(self, "_peer", None)
+        if cur is not None and cur[3] == stride:
+            return cur[:3]
+        if os.environ.get("MSGPU_PEER_EXCHANGE", "1") == "0" or 2 * self.world * stride > self.PEER_BUFFER_LIMIT:
+            self._peer_off = True
+            return None
+        ok, made = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(2 * self.world * stride, dtype=torch.uint8, device=self.device)
+            hdl = symm_mem.rendezvous(t, self.dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or any(p % 16 for p in ptrs):
+                raise RuntimeError("unexpected symmetric-memory layout")
+            made = (t, hdl, ptrs, stride)
+        except Exception as e:  # no peer access on this box: every rank must take the same decision (below)
+            ok = 0
+            self.peer_error = repr(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            self._peer_off = True
+            return None
+        self._peer = made
+        return made[:3]
 
     def _timer(self):
         if self.stream is None or self.world == 1:

@@ -16,23 +16,39 @@ from oracle.pyoracle import Orders, orders_equal, tables_digest, tables_equal
 pytestmark = pytest.mark.gpu
 
 
-def build_sharded(chunks, chain=False):
-    """chunks: the rank-ordered pieces of one PAF.  Returns the merged Construction."""
+def build_sharded(chunks, chain=False, peers=False):
+    """chunks: the rank-ordered pieces of one PAF.  Returns the merged Construction.  peers: every rank has its own
+    receive buffer [n][stride] and every export writes its slot of ALL of them in one kernel (the path real ranks take
+    over peer-mapped memory, msgpu_shard_export_peers)."""
     n = len(chunks)
     ranks = [GraphBuilder(0) for _ in range(n)]
     try:
         headers, blobs = [], []
         for r, (gb, chunk) in enumerate(zip(ranks, chunks)):
             gb.shard_ingest_buffer(chunk, r == n - 1)
-            h = gb.shard_header()
-            blob = torch.empty(int(h.blob_bytes) + 16, dtype=torch.uint8, device="cuda")
-            gb.shard_export(blob.data_ptr(), blob.numel())
-            headers.append(h)
-            blobs.append(blob)
+            headers.append(gb.shard_header())
+        if peers:
+            stride = (max(int(h.blob_bytes) for h in headers) + 255) & ~255
+            recv = [torch.full((n * stride,), 0xEE, dtype=torch.uint8, device="cuda") for _ in range(n)]
+            for r, gb in enumerate(ranks):
+                gb.shard_export_peers([b.data_ptr() + r * stride for b in recv], stride)
+            torch.cuda.synchronize()
+            for b in recv[1:]:
+                assert torch.equal(b, recv[0])
+            # the headers every rank reads out of its own buffer are the ones the exporters described
+            heads = recv[-1].view(n, stride)[:, :multi_gpu.HEADER_BYTES].contiguous().view(torch.int64)
+            seen = multi_gpu.tensor_to_headers(heads.view(n, multi_gpu.HEADER_WORDS))
+            assert [int(x.blob_bytes) for x in seen] == [int(h.blob_bytes) for h in headers]
+        else:
+            for gb, h in zip(ranks, headers):
+                blob = torch.empty(int(h.blob_bytes) + 16, dtype=torch.uint8, device="cuda")
+                gb.shard_export(blob.data_ptr(), blob.numel())
+                blobs.append(blob)
         torch.cuda.synchronize()
         parts = []
         for r, gb in enumerate(ranks):
-            gb.build_from_shards(headers, [b.data_ptr() for b in blobs], r, n)
+            ptrs = [recv[r].data_ptr() + s * stride for s in range(n)] if peers else [b.data_ptr() for b in blobs]
+            gb.build_from_shards(headers, ptrs, r, n)
             parts.append(gb.result())
             if chain:
                 parts[-1].orders = gb.chain_overlaps(300).orders()
@@ -50,6 +66,23 @@ def test_sharded_edge_cases_vs_oracle(oracle, name, n):
     paf = util.edge_case_pafs()[name]
     got, _ = build_sharded(multi_gpu.split_paf(paf, n))
     assert tables_equal(util.gpu_to_tables(got), oracle.build(paf)) == []
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_export_into_every_ranks_buffer_vs_oracle(oracle, n):
+    """msgpu_shard_export_peers: one kernel writes the blob into this rank's slot of every receive buffer; the result
+    built from those buffers is the oracle's.  A slot that is too small receives the header only."""
+    paf = util.edge_case_pafs()["duplicates_ungrouped"] if n == 2 else synth.generate_paf("small")
+    got, _ = build_sharded(multi_gpu.split_paf(paf, n), peers=True)
+    assert tables_equal(util.gpu_to_tables(got), oracle.build(paf)) == []
+    with GraphBuilder(0) as gb:
+        gb.shard_ingest_buffer(paf, True)
+        h = gb.shard_header()
+        small = torch.full((256,), 0xEE, dtype=torch.uint8, device="cuda")
+        gb.shard_export_peers([small.data_ptr()], 128)
+        torch.cuda.synchronize()
+        assert int(small[:64].view(torch.int64)[7].item()) == int(h.blob_bytes) > 128
+        assert bool((small[64:] == 0xEE).all())
 
 
 @pytest.mark.parametrize("n", [2, 4])
