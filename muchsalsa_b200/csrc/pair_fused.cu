@@ -524,6 +524,7 @@ template <int kSB> struct MergeShared { // everything but the two word buffers, 
   MergeStage<kSB> src;
   uint32_t        scan[33];
   uint32_t        warp_tot[kFusedWarps];
+  uint32_t        row_start[kTileCap / 32 + 1]; // bit p: a row's candidates start at position p (positions = slots of the row)
   uint32_t        smin, smax, max_row_src;
 };
 constexpr uint16_t kDropped = 0x8000u;
@@ -573,13 +574,17 @@ __device__ __forceinline__ uint32_t enumerate_candidates(const TileArgs &a, Merg
 #ifndef MSGPU_MERGE_ODD
 #define MSGPU_MERGE_ODD 1
 #endif
+#ifndef MSGPU_MERGE_MULT
+#define MSGPU_MERGE_MULT 2 // outputs per thread and level = this x the even share: with 2, half of the threads merge 17
+#endif                     // outputs each and the other half idles — one merge-path search per 17 outputs instead of per
+                           // 9 outweighs it (0.709 -> 0.699 ms at yeast scale, profiles/r2_ab_heads_rowmask_merge_mult.log)
 template <class W, int kSB>
 __device__ __forceinline__ W *merge_levels(MergeShared<kSB> &s, W *wa, W *wb, uint32_t n_ent) {
   constexpr uint32_t kSrcMask = MergeShared<kSB>::kSrcMask;
   const unsigned t = threadIdx.x;
   // `per` consecutive outputs per thread.  An ODD count: lane l starts at word l * per, and an odd stride spreads the
   // 32 lanes of a warp over all 32 banks (a stride of 8 puts four lanes on every bank it touches).
-  uint32_t per = (n_ent + kFusedBlock - 1) / kFusedBlock;
+  uint32_t per = (n_ent + kFusedBlock - 1) / kFusedBlock * MSGPU_MERGE_MULT;
   if (MSGPU_MERGE_ODD) per |= 1u;
   __syncthreads();
   W *in = wa, *out = wb;
@@ -653,8 +658,8 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared<kSB> &
 
   // ---- run heads = edges of this tile.  A candidate that failed the overlap test stays in its run (it has the key
   // of its pair) but is skipped; the head of a run is its first surviving candidate.
-  W        xs[kItems];                             // this lane's sorted words, kept for the record pass
-  uint32_t vmask = 0, hmask = 0, n_v = 0, n_h = 0; // bit `it`: this lane's item of iteration `it` survives / is a head
+  W        xs[kItems];          // this lane's sorted words, kept for the record pass
+  uint32_t vmask = 0, hmask = 0; // bit `it`: this lane's item of iteration `it` survives / is a head
 #pragma unroll
   for (int it = 0; it < kItems; ++it) {
     xs[it] = W(0);
@@ -662,18 +667,23 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared<kSB> &
       const uint32_t k = wbase + it * 32 + l;
       bool           ok = false, head = false;
       if (k < n_ent) {
-        const W x = sorted[k];
-        xs[it]    = x;
-        ok        = !(s.ent_src[uint32_t(x) & (kTileCap - 1)] & kDropped);
-        if (ok) {
-          head = true;
+        // the warp's 32 positions share one word of the row-start bits (wbase is a multiple of 32): one broadcast load
+        const bool first_of_row = (s.row_start[(wbase >> 5) + it] >> l) & 1u;
+        const W    x            = sorted[k];
+        xs[it] = x;
+        ok     = !(s.ent_src[uint32_t(x) & (kTileCap - 1)] & kDropped);
+        if (ok && !first_of_row) { // (position 0 starts a row)
           const W key = x >> kIdxBits;
-          // almost always the predecessor has another key: then this is a head and nothing else is looked at
-          if (k > 0 && (sorted[k - 1] >> kIdxBits) == key) {
-            const uint32_t row_start = s.src.base[s.src.row_first[s.ent_src[k] & kSrcMask]];
-            for (uint32_t p = k; p > row_start;) {
+          W       y   = sorted[k - 1];
+          if ((y >> kIdxBits) != key) {
+            head = true; // the usual case: the predecessor belongs to another read pair
+          } else if (s.ent_src[uint32_t(y) & (kTileCap - 1)] & kDropped) {
+            // rare: the predecessor has the key but failed the overlap test — walk back over such candidates to the
+            // nearest survivor with the key, the first one with another key, or the start of the row
+            head = true;
+            for (uint32_t p = k - 1; !((s.row_start[p >> 5] >> (p & 31)) & 1u);) {
               --p;
-              const W y = sorted[p];
+              y = sorted[p];
               if ((y >> kIdxBits) != key) break;
               if (!(s.ent_src[uint32_t(y) & (kTileCap - 1)] & kDropped)) {
                 head = false;
@@ -681,14 +691,15 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared<kSB> &
               }
             }
           }
+        } else {
+          head = ok;
         }
       }
       vmask |= (ok ? 1u : 0u) << it;
       hmask |= (head ? 1u : 0u) << it;
-      n_v += __popc(__ballot_sync(0xffffffffu, ok));
-      n_h += __popc(__ballot_sync(0xffffffffu, head));
     }
   }
+  const uint32_t n_v = __reduce_add_sync(0xffffffffu, __popc(vmask)), n_h = __reduce_add_sync(0xffffffffu, __popc(hmask));
   if (l == 0) s.warp_tot[w] = n_v | (n_h << 16);
   __syncthreads();
   uint32_t before = 0, total = 0;
@@ -742,6 +753,7 @@ __global__ void __launch_bounds__(kFusedBlock, kSB == kSrcBits ? kMergeCtas : 1)
       s.smax        = 0;
       s.max_row_src = 0;
     }
+    if (t < kTileCap / 32 + 1) s.row_start[t] = 0;
     __syncthreads();
     const uint32_t st_idx = tile - a.tile_lo;
     const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
@@ -795,7 +807,11 @@ __global__ void __launch_bounds__(kFusedBlock, kSB == kSrcBits ? kMergeCtas : 1)
         }
       }
       uint32_t tot, ex = block_exclusive_scan<uint32_t>(len, s.scan, &tot);
-      if (j < n_src) s.src.base[j] = carry + ex;
+      if (j < n_src) {
+        s.src.base[j] = carry + ex;
+        // the first source of a row marks where the row's candidates start (a tile that overflows is refused below)
+        if (s.src.row_first[j] == j && carry + ex <= kTileCap) atomicOr(&s.row_start[(carry + ex) >> 5], 1u << ((carry + ex) & 31));
+      }
       carry += tot;
     }
     if (t == 0) s.src.base[n_src] = carry;
