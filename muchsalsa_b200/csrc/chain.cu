@@ -124,9 +124,9 @@ struct Vm { // the fields of one VertexMatch the stage reads
   bool   dir;
 };
 
-__device__ __forceinline__ Vm load_vm(const ChainArgs &a, uint32_t pos) { // two 128-bit loads = one 32-byte sector
-  const uint4 *q = reinterpret_cast<const uint4 *>(a.vm + pos);
-  const uint4  x = __ldg(q), y = __ldg(q + 1);
+__device__ __forceinline__ Vm load_vm(const ChainArgs &a, uint32_t pos) { // one 256-bit load = one 32-byte sector
+  uint4 x, y;
+  ld_row32(a.vm + pos, x, y);
   Vm           v;
   v.nr0    = int32_t(x.x);
   v.nr1    = int32_t(x.y);

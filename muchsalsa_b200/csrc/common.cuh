@@ -49,6 +49,29 @@ public:
       m_scan_state[k]       = nullptr;
       m_scan_state_bytes[k] = 0;
     }
+    if (m_side) cudaStreamDestroy(m_side);
+    m_side = nullptr;
+    for (auto ev : m_events) cudaEventDestroy(ev);
+    m_events.clear();
+  }
+  // A second, high-priority stream of the context for work that runs BESIDE the build's stream (the emission kernel of
+  // one chunk underneath the tile kernel of the next, pair_fused.cu), and events to order the two.  The caller joins the
+  // side stream back into the build's stream before the build returns.
+  cudaStream_t side_stream() {
+    if (!m_side) {
+      int least = 0, greatest = 0;
+      MSGPU_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      MSGPU_CUDA(cudaStreamCreateWithPriority(&m_side, cudaStreamNonBlocking, greatest));
+    }
+    return m_side;
+  }
+  cudaEvent_t sync_event(size_t i) {
+    while (m_events.size() <= i) {
+      cudaEvent_t ev;
+      MSGPU_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      m_events.push_back(ev);
+    }
+    return m_events[i];
   }
   // Status words of the single-pass scans (scan.cuh): regions that outlive reset() and that nothing else writes, one
   // per slot (up to four scans run concurrently in one launch).  Every call hands out the next epoch; flags written
@@ -160,6 +183,8 @@ private:
   size_t            m_scan_state_bytes[4] = {0, 0, 0, 0};
   unsigned          m_epoch = 0;
   unsigned          m_ticket_base[4] = {0, 0, 0, 0};
+  cudaStream_t             m_side = nullptr;
+  std::vector<cudaEvent_t> m_events;
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -290,6 +315,29 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
+}
+
+// One 32-byte record (a PairRow / VmRow: one L2 sector) fetched by ONE 256-bit read-only load (sm_100: SASS
+// LDG.E.ENL2.256.CONSTANT) instead of two 128-bit ones.  The gathers of the emission and chaining kernels hit a
+// different line per lane, so every load instruction costs one L1 wavefront per lane: one instruction per record
+// halves them (MSGPU_LD256=0 keeps the two-load form for the A/B).  `p` must be 32-byte aligned.
+#ifndef MSGPU_LD256
+#define MSGPU_LD256 1
+#endif
+__device__ __forceinline__ void ld_row32(const void *p, uint4 &x, uint4 &y) {
+#if MSGPU_LD256 == 2 // development A/B: the same load without allocating the line in L1
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w), "=r"(y.x), "=r"(y.y), "=r"(y.z), "=r"(y.w)
+               : "l"(p));
+#elif MSGPU_LD256
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w), "=r"(y.x), "=r"(y.y), "=r"(y.z), "=r"(y.w)
+               : "l"(p));
+#else
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  x = __ldg(q);
+  y = __ldg(q + 1);
+#endif
 }
 
 // 64-bit mix (splitmix64 finaliser) — used to spread keys over the open-addressing tables

@@ -106,7 +106,7 @@ struct PairPlan {
 
 // scratch of one emission (a range of tiles): compact records, per-tile counts and offsets, totals
 struct PairScratch {
-  uint32_t            max_tiles = 0;
+  uint32_t            max_tiles = 0, n_chunks = 1; // n_chunks: pairs of totals the last emission left (pipelined: one per chunk)
   uint2              *records = nullptr, *tile_cnt = nullptr;
   unsigned long long *em_base = nullptr, *ed_base = nullptr, *status = nullptr, *totals = nullptr;
 };

@@ -76,8 +76,6 @@ struct RankArgs {
   int32_t            *p_ir0, *p_ir1;
   uint32_t           *deg;
   unsigned long long *wgt;
-  uint32_t           *heavy_list; // matches of groups too long for one thread each
-  unsigned int       *heavy_n;
 };
 
 // match i is the q-th of its group in read order: write its pair row and account its partners to its read
@@ -123,13 +121,13 @@ template <bool kCta> __device__ __forceinline__ void bitonic_sort_shared(unsigne
 }
 
 constexpr uint32_t kSortWarpMax = 128;  // groups up to this size: one warp sorts them
-constexpr uint32_t kSortCtaMax  = 4096; // ... up to this size: one CTA; longer ones are ranked by counting (below)
-constexpr uint32_t kCountCtaMax = 1024; // inside the CTA kernel: groups up to this size are ranked by counting
+constexpr uint32_t kRankChunk   = 256;  // longer groups: one CTA ranks this many members of a group by counting ...
+constexpr uint32_t kRankTile    = 4096; // ... against all of the group's read ids, staged this many at a time
 
 // One warp per group: the keys (read id << 32 | row of the match) are sorted in shared memory, then lane by lane the
 // matches are placed at their position in read order.  Reads are unique inside a group (MatchMap.cpp:64-73 keeps one
-// match per (read, unitig)), so the order is total.  Groups too long for a warp go to `big_groups`.
-__global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a, uint32_t n_groups, uint32_t *__restrict__ big_groups,
+// match per (read, unitig)), so the order is total.  Groups too long for a warp become work items of the CTA kernel.
+__global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a, uint32_t n_groups, uint2 *__restrict__ big_items,
                                                         unsigned int *__restrict__ n_big) {
   __shared__ unsigned long long sm[256 / 32][kSortWarpMax];
   const MatchSoA &m = a.m;
@@ -139,8 +137,12 @@ __global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a, uint32_t n_g
   for (uint64_t u = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; u < n_groups; u += nw) {
     const uint32_t g0 = a.grp_off[u], g1 = a.grp_off[u + 1], k = g1 - g0;
     if (k == 0) continue;
-    if (k > kSortWarpMax) {
-      if (l == 0) big_groups[atomicAdd(n_big, 1u)] = uint32_t(u);
+    if (k > kSortWarpMax) { // one work item per kRankChunk members for rank_rows_cta_kernel
+      const uint32_t nc = (k + kRankChunk - 1) / kRankChunk;
+      uint32_t       base = 0;
+      if (l == 0) base = atomicAdd(n_big, nc);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (uint32_t c = l; c < nc; c += 32) big_items[base + c] = make_uint2(uint32_t(u), c);
       continue;
     }
     uint32_t n = 2;
@@ -154,67 +156,41 @@ __global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a, uint32_t n_g
   }
 }
 
-// One CTA per longer group; groups beyond kSortCtaMax hand their members to the counting kernel
-__global__ void __launch_bounds__(1024) rank_rows_cta_kernel(RankArgs a, const uint32_t *__restrict__ big_groups,
-                                                            const unsigned int *__restrict__ n_big) {
-  extern __shared__ __align__(16) unsigned long long keys_cta[];
+// Longer groups, ranked by counting: a work item is (group, chunk of kRankChunk members).  The CTA stages the group's
+// read ids in shared memory, kRankTile at a time, and every thread counts for ITS member the smaller ids among them
+// (k compares per member served by shared-memory broadcasts, no barrier per step).  The k^2 compares of a long group
+// are spread over k / 256 CTAs, so what the kernel costs is the latency of one item, whatever the longest group is
+// (round 2 until here: one 1024-thread CTA per group up to 4096 — counting up to 1024, a sorting network beyond — and
+// one warp per member over global memory for longer groups: 41 + 7 us at yeast scale, set by the longest groups).
+__global__ void __launch_bounds__(kRankChunk) rank_rows_cta_kernel(RankArgs a, const uint2 *__restrict__ big_items,
+                                                                  const unsigned int *__restrict__ n_big) {
+  __shared__ uint32_t ids[kRankTile];
   const MatchSoA &m = a.m;
-  const uint32_t  nb = *n_big;
-  for (uint32_t x = blockIdx.x; x < nb; x += gridDim.x) {
-    const uint32_t u = big_groups[x], g0 = a.grp_off[u], g1 = a.grp_off[u + 1], k = g1 - g0;
-    if (k > kSortCtaMax) {
-      __shared__ unsigned int base;
-      if (threadIdx.x == 0) base = atomicAdd(a.heavy_n, k);
+  const uint32_t  n = *n_big;
+  for (uint32_t x = blockIdx.x; x < n; x += gridDim.x) {
+    const uint2    item = big_items[x];
+    const uint32_t u = item.x, g0 = a.grp_off[u], g1 = a.grp_off[u + 1], k = g1 - g0;
+    const uint32_t j   = item.y * kRankChunk + threadIdx.x; // this thread's member
+    const bool     has = j < k;
+    const uint32_t my  = has ? m.read[g0 + j] : 0u;
+    uint32_t       r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    for (uint32_t t0 = 0; t0 < k; t0 += kRankTile) {
+      const uint32_t tn = k - t0 < kRankTile ? k - t0 : kRankTile;
+      __syncthreads(); // the previous tile (or item) is consumed
+      for (uint32_t i = threadIdx.x; i < tn; i += kRankChunk) ids[i] = m.read[g0 + t0 + i];
       __syncthreads();
-      for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) a.heavy_list[base + i] = g0 + i;
-      __syncthreads();
-      continue;
-    }
-    if (k <= kCountCtaMax) {
-      // a group of a few hundred matches: every thread counts, for its members, the smaller read ids among all of
-      // them (k^2 compares served by shared-memory broadcasts, no barrier per step) — cheaper here than ~50 stages
-      // of a sorting network with a barrier each
-      uint32_t *ids = reinterpret_cast<uint32_t *>(keys_cta);
-      for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) ids[i] = m.read[g0 + i];
-      __syncthreads();
-      for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {
-        const uint32_t my = ids[j];
-        uint32_t       r0 = 0, r1 = 0, r2 = 0, r3 = 0, i = 0;
-        for (; i + 4 <= k; i += 4) {
+      if (has) {
+        uint32_t i = 0;
+        for (; i + 4 <= tn; i += 4) {
           r0 += ids[i] < my;
           r1 += ids[i + 1] < my;
           r2 += ids[i + 2] < my;
           r3 += ids[i + 3] < my;
         }
-        for (; i < k; ++i) r0 += ids[i] < my;
-        place_row(a, g0 + j, u, g0 + r0 + r1 + r2 + r3, g1);
+        for (; i < tn; ++i) r0 += ids[i] < my;
       }
-      __syncthreads();
-      continue;
     }
-    uint32_t n = 2;
-    while (n < k) n <<= 1;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
-      keys_cta[i] = i < k ? ((unsigned long long)m.read[g0 + i] << 32 | (g0 + i)) : ~0ull;
-    __syncthreads();
-    bitonic_sort_shared<true>(keys_cta, n, threadIdx.x, blockDim.x);
-    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) place_row(a, uint32_t(keys_cta[j]), u, g0 + j, g1);
-    __syncthreads();
-  }
-}
-
-// one warp per member of a long group: the lanes share the count
-__global__ void __launch_bounds__(256) rank_rows_heavy_kernel(RankArgs a) {
-  const MatchSoA &m  = a.m;
-  const unsigned  l  = threadIdx.x & 31;
-  const uint64_t  nw = (uint64_t(gridDim.x) * blockDim.x) >> 5, n = *a.heavy_n;
-  for (uint64_t x = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; x < n; x += nw) {
-    const uint64_t i = a.heavy_list[x];
-    const uint32_t u = m.unitig[i], g0 = a.grp_off[u], g1 = a.grp_off[u + 1], my = m.read[i];
-    uint32_t       r = 0;
-    for (uint32_t j = g0 + l; j < g1; j += 32) r += m.read[j] < my;
-    r = warp_reduce_sum(r);
-    if (l == 0) place_row(a, i, u, g0 + r, g1);
+    if (has) place_row(a, g0 + j, u, g0 + r0 + r1 + r2 + r3, g1);
   }
 }
 
@@ -356,11 +332,33 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *__restrict__
   return lo;
 }
 
+// the bisection bracket of a heavy row from the lanes' smallest first / largest last partner ids (all lanes take part)
+__device__ __forceinline__ void warp_value_range(uint32_t vmin, uint32_t vmax, uint32_t n_reads, uint32_t *lo, uint32_t *hi) {
+  vmin = __reduce_min_sync(0xffffffffu, vmin);
+  vmax = __reduce_max_sync(0xffffffffu, vmax);
+  if (vmin <= vmax) { // (a row without candidates keeps the full bracket; it has no sub-tile beyond the first anyway)
+    *lo = vmin;
+    *hi = vmax + 1u < n_reads ? vmax + 1u : n_reads;
+  }
+}
+__device__ __forceinline__ void row_value_range(bool has, const uint32_t *__restrict__ p_read, uint32_t b, uint32_t e,
+                                                uint32_t n_reads, uint32_t *lo, uint32_t *hi) {
+  uint32_t vmin = 0xffffffffu, vmax = 0;
+  if (has) {
+    vmin = p_read[b];
+    vmax = p_read[e - 1];
+  }
+  warp_value_range(vmin, vmax, n_reads, lo, hi);
+}
+
 // Heavy rows: one warp per sub-tile finds the value s_j that starts the sub-tile, the largest s with
 //   C(s) := #{candidates of the row with second < s}  <=  j * T,   T = kTileCap - deg,
 // by bisection over s (C is monotone; every source suffix is sorted by read id, so C is a sum of lower bounds).  One
 // value of `second` occurs at most once per source, so C jumps by <= deg and sub-tile j = [s_j, s_j+1) holds fewer
 // than T + deg = kTileCap candidates.  Written out: for every source the row position where each sub-tile begins.
+// Sub-tile 0 starts where the slices start (no search: most heavy rows at yeast scale are ONE sub-tile), and the
+// bracket of the others is the row's own value range [smallest first partner, largest last partner + 1], not all
+// read ids: C is 0 at its lower end and the row's weight at its upper end.
 __global__ void __launch_bounds__(256)
     split_heavy_kernel(const uint32_t *__restrict__ tile_row, const uint32_t *__restrict__ tile_kind, uint32_t t_begin,
                        uint32_t n_tiles, RowPlan plan, const uint64_t *__restrict__ slice_off, const uint32_t *__restrict__ rd_off,
@@ -389,6 +387,11 @@ __global__ void __launch_bounds__(256)
         e                = grp_off[rows[q].unitig + 1];
       }
       uint32_t wlo = b, whi = e, lo = 0, hi = n_reads; // invariant: C(lo) <= target, wlo = lower bound of lo
+      if (j == 0) {
+        hi = 0; // nothing to search: the sub-tile starts at the slices' starts
+      } else {
+        row_value_range(has && e > b, p_read, b, e, n_reads, &lo, &hi);
+      }
       while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo + 1) >> 1);
         const uint32_t pos = has ? lower_bound_u32(p_read, wlo, whi, mid) : 0u;
@@ -423,6 +426,19 @@ __global__ void __launch_bounds__(256)
         whi[i] = e[i];
       }
       uint32_t lo = 0, hi = n_reads; // invariant: C(lo) <= target, wlo = lower bounds of lo
+      if (j == 0) {
+        hi = 0;
+      } else {
+        uint32_t vmin = 0xffffffffu, vmax = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (e[i] > b[i]) {
+            const uint32_t x0 = p_read[b[i]], x1 = p_read[e[i] - 1];
+            vmin = x0 < vmin ? x0 : vmin;
+            vmax = x1 > vmax ? x1 : vmax;
+          }
+        warp_value_range(vmin, vmax, n_reads, &lo, &hi);
+      }
       while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo + 1) >> 1);
         uint32_t       pos[4];
@@ -455,6 +471,20 @@ __global__ void __launch_bounds__(256)
     }
     // bisection: largest s in [0, n_reads] with C(s) <= target
     uint32_t lo = 0, hi = n_reads; // invariant: C(lo) <= target
+    if (j == 0) {
+      hi = 0; // (the loop below then writes b for every source: lower_bound is not consulted for j == 0)
+    } else {
+      uint32_t vmin = 0xffffffffu, vmax = 0;
+      for (uint32_t a = l; a < d; a += 32) {
+        const uint32_t q = rd_src[q0 + a], b = q + 1, e = grp_off[rows[q].unitig + 1];
+        if (e > b) {
+          const uint32_t x0 = p_read[b], x1 = p_read[e - 1];
+          vmin = x0 < vmin ? x0 : vmin;
+          vmax = x1 > vmax ? x1 : vmax;
+        }
+      }
+      warp_value_range(vmin, vmax, n_reads, &lo, &hi);
+    }
     while (lo < hi) {
       uint32_t mid = lo + ((hi - lo + 1) >> 1);
       uint64_t c   = 0;
@@ -856,9 +886,9 @@ __global__ void __launch_bounds__(kFusedBlock, kSB == kSrcBits ? kMergeCtas : 1)
   }
 }
 
-__device__ __forceinline__ PairRow ld_row(const PairRow *p) { // two 128-bit read-only loads = one 32-byte sector
-  const uint4 *q = reinterpret_cast<const uint4 *>(p);
-  uint4        x = __ldg(q), y = __ldg(q + 1);
+__device__ __forceinline__ PairRow ld_row(const PairRow *p) { // one 256-bit read-only load = one 32-byte sector
+  uint4 x, y;
+  ld_row32(p, x, y);
   PairRow      r;
   r.ir0    = int32_t(x.x);
   r.ir1    = int32_t(x.y);
@@ -893,8 +923,23 @@ struct EmitArgs {
   const uint2    *records, *tile_cnt;
   const unsigned long long *em_base, *edge_base, *totals; // totals: (edge matches, edges) of this launch
   unsigned long long em_value_base; // added to the em_begin VALUES (rows of earlier chunks of the same slice)
+  // pipelined emission into ONE resident table (pairing_pipelined): the rows of this launch continue those of the
+  // `n_prev` launches before it, whose totals (4 words each) start at prev_totals; only the last launch closes the CSR
+  const unsigned long long *prev_totals;
+  uint32_t        n_prev, close_csr;
   EdgeTables      out;
 };
+
+// rows (edge matches, edges) written by the earlier launches of a pipelined emission
+__device__ __forceinline__ void rows_before(const EmitArgs &a, unsigned long long *em, unsigned long long *ed) {
+  unsigned long long x = 0, y = 0;
+  for (uint32_t c = 0; c < a.n_prev; ++c) {
+    x += a.prev_totals[4 * c];
+    y += a.prev_totals[4 * c + 1];
+  }
+  *em = x;
+  *ed = y;
+}
 
 
 #ifndef MSGPU_EMIT_CTAS
@@ -903,20 +948,27 @@ struct EmitArgs {
 #ifndef MSGPU_EMIT_BATCH
 #define MSGPU_EMIT_BATCH 4
 #endif
+constexpr uint32_t kMaxPipeChunks  = 16;   // chunks of a pipelined emission (pairing_pipelined)
 constexpr int kEmitBlock = 256;
 constexpr int kEmitCtas  = MSGPU_EMIT_CTAS;  // resident CTAs per SM the emission kernels are compiled for
 constexpr int kEmitBatch = MSGPU_EMIT_BATCH; // records in flight per thread: the partner gathers are latency-bound
+#ifndef MSGPU_EMIT_BATCH_UNDER
+#define MSGPU_EMIT_BATCH_UNDER 2
+#endif
+constexpr int kEmitBatchUnder = MSGPU_EMIT_BATCH_UNDER; // ... of the 64-register instantiation that runs underneath the tile kernel
 
 // One CTA per tile (strided).  The tile's sources (the `first` side of its records, <= 512 rows) are staged in shared
 // memory once; every record then needs ONE dependent gather (its partner's row) after its own coalesced load.
 __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_kernel(EmitArgs a) {
   __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
   const unsigned   t = threadIdx.x;
-  if (blockIdx.x == 0 && t == 0) a.out.em_begin[a.totals[1]] = a.em_value_base + a.totals[0]; // closes the CSR
+  unsigned long long em_before, ed_before;
+  rows_before(a, &em_before, &ed_before);
+  if (blockIdx.x == 0 && t == 0 && a.close_csr) a.out.em_begin[ed_before + a.totals[1]] = a.em_value_base + em_before + a.totals[0];
   for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
     const uint32_t           tile    = a.tile_lo + ti;
     const uint32_t           n_valid = a.tile_cnt[ti].x;
-    const unsigned long long em0 = a.em_base[ti], ed0 = a.edge_base[ti];
+    const unsigned long long em0 = em_before + a.em_base[ti], ed0 = ed_before + a.edge_base[ti];
     const uint32_t           r0 = a.tile_row[tile], q0 = a.rd_off[r0];
     const uint32_t n_src = (a.tile_kind[tile] ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
     const uint2   *rec   = a.records + uint64_t(ti) * kTileCap;
@@ -930,9 +982,7 @@ __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_kernel(E
     const bool staged = n_src <= kSrcCap; // (rows with more sources: their rows are read in place, one more gather)
     if (n_valid && staged)
       for (uint32_t j = t; j < n_src; j += kEmitBlock) {
-        const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
-        src_lo[j]      = __ldg(q);
-        src_hi[j]      = __ldg(q + 1);
+        ld_row32(a.rows + a.rd_src[q0 + j], src_lo[j], src_hi[j]);
       }
     __syncthreads();
     for (uint32_t k0 = t; k0 < n_valid; k0 += kEmitBlock * kEmitBatch) {
@@ -956,9 +1006,7 @@ __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_kernel(E
           lo = src_lo[j];
           hi = src_hi[j];
         } else {
-          const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
-          lo             = __ldg(q);
-          hi             = __ldg(q + 1);
+          ld_row32(a.rows + a.rd_src[q0 + j], lo, hi);
         }
         const int      a0 = int32_t(lo.x), a1 = int32_t(lo.y), b0 = pb[u].ir0, b1 = pb[u].ir1;
         const int      ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
@@ -997,7 +1045,10 @@ __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_kernel(E
 // candidates x 12 bytes would take the shared memory that buys the kernel its four resident CTAs.)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
-__global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_bulk_kernel(EmitArgs a) {
+// kCtas = resident CTAs per SM the kernel is compiled for: kEmitCtas on its own; 4 (at most 64 registers: one such
+// CTA takes exactly the registers, and less than the shared memory, that one CTA of the tile kernel leaves behind)
+// when it runs underneath the tile kernel of the next chunk (pairing_pipelined).
+template <int kCtas, int kBatch> __global__ void __launch_bounds__(kEmitBlock, kCtas) pair_emit_rows_bulk_kernel(EmitArgs a) {
   __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
   __shared__ __align__(8) unsigned long long bar;
   extern __shared__ __align__(16) unsigned char bulk_raw[];
@@ -1009,11 +1060,13 @@ __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_bulk_ker
   }
   __syncthreads();
   uint32_t phase = 0;
-  if (blockIdx.x == 0 && t == 0) a.out.em_begin[a.totals[1]] = a.em_value_base + a.totals[0]; // closes the CSR
+  unsigned long long em_before, ed_before;
+  rows_before(a, &em_before, &ed_before);
+  if (blockIdx.x == 0 && t == 0 && a.close_csr) a.out.em_begin[ed_before + a.totals[1]] = a.em_value_base + em_before + a.totals[0];
   for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
     const uint32_t           tile    = a.tile_lo + ti;
     const uint32_t           n_valid = a.tile_cnt[ti].x;
-    const unsigned long long em0 = a.em_base[ti], ed0 = a.edge_base[ti];
+    const unsigned long long em0 = em_before + a.em_base[ti], ed0 = ed_before + a.edge_base[ti];
     const uint32_t           r0 = a.tile_row[tile], q0 = a.rd_off[r0];
     const uint32_t n_src = (a.tile_kind[tile] ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
     const uint2   *rec   = a.records + uint64_t(ti) * kTileCap;
@@ -1030,9 +1083,7 @@ __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_bulk_ker
     const bool staged = n_src <= kSrcCap;
     if (n_valid && staged)
       for (uint32_t j = t; j < n_src; j += kEmitBlock) {
-        const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
-        src_lo[j]      = __ldg(q);
-        src_hi[j]      = __ldg(q + 1);
+        ld_row32(a.rows + a.rd_src[q0 + j], src_lo[j], src_hi[j]);
       }
     __syncthreads();
     if (n_valid) { // every thread waits for the copy (hardware sleep, not a poll)
@@ -1044,18 +1095,18 @@ __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_bulk_ker
                      : "memory");
       phase ^= 1u;
     }
-    for (uint32_t k0 = t; k0 < n_valid; k0 += kEmitBlock * kEmitBatch) {
-      uint2   cur[kEmitBatch];
-      PairRow pb[kEmitBatch];
+    for (uint32_t k0 = t; k0 < n_valid; k0 += kEmitBlock * kBatch) {
+      uint2   cur[kBatch];
+      PairRow pb[kBatch];
 #pragma unroll
-      for (int u = 0; u < kEmitBatch; ++u) {
+      for (int u = 0; u < kBatch; ++u) {
         const uint32_t k = k0 + u * kEmitBlock;
         cur[u]           = k < n_valid ? recs[k] : make_uint2(0, 0);
       }
 #pragma unroll
-      for (int u = 0; u < kEmitBatch; ++u) pb[u] = ld_row(a.rows + cur[u].x);
+      for (int u = 0; u < kBatch; ++u) pb[u] = ld_row(a.rows + cur[u].x);
 #pragma unroll
-      for (int u = 0; u < kEmitBatch; ++u) {
+      for (int u = 0; u < kBatch; ++u) {
         const uint32_t k = k0 + u * kEmitBlock;
         if (k >= n_valid) continue;
         const uint32_t j = cur[u].y & ((1u << kRecSrcBits) - 1u);
@@ -1064,9 +1115,7 @@ __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_bulk_ker
           lo = src_lo[j];
           hi = src_hi[j];
         } else {
-          const uint4 *q = reinterpret_cast<const uint4 *>(a.rows + a.rd_src[q0 + j]);
-          lo             = __ldg(q);
-          hi             = __ldg(q + 1);
+          ld_row32(a.rows + a.rd_src[q0 + j], lo, hi);
         }
         const int a0 = int32_t(lo.x), a1 = int32_t(lo.y), b0 = pb[u].ir0, b1 = pb[u].ir1;
         const int ov0 = a0 > b0 ? a0 : b0, ov1 = a1 < b1 ? a1 : b1;
@@ -1121,19 +1170,18 @@ void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const Unitig
   uint32_t           *cursor = reinterpret_cast<uint32_t *>(zero + z_cursor);
   unsigned long long *wgt    = reinterpret_cast<unsigned long long *>(zero + z_wgt);
   uint32_t           *d_u32  = reinterpret_cast<uint32_t *>(zero + z_u32); // [0] sources [1] tiles [2] too many sources
-                                                                           // [3] tile error [4] big groups [5] heavy matches
+                                                                           // [3] tile error [4] work items of the longer groups [5] -
                                                                            // [6] tiles with > 512 sources [7] cursor of their list
   uint64_t           *d_u64  = reinterpret_cast<uint64_t *>(zero + z_u64);
   uint32_t           *rd_off = arena.alloc<uint32_t>(R + 1);
   const int gm = grid_for(M, 256), gr = grid_for(R, 256);
   if (M) {
-    RankArgs ra{m, unitigs.grp_off, rows, p_read, p_ir0, p_ir1, deg, wgt, arena.alloc<uint32_t>(M), d_u32 + 5};
-    // groups ordered by read id: a warp sorts a short group, a CTA a longer one, the longest are ranked by counting
+    RankArgs ra{m, unitigs.grp_off, rows, p_read, p_ir0, p_ir1, deg, wgt};
+    // groups ordered by read id: a warp sorts a short group, CTAs rank the members of a longer one by counting
     const uint32_t U = uint32_t(unitigs.n);
-    uint32_t      *big_groups = arena.alloc<uint32_t>(U + 1);
-    MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<grid_for(uint64_t(U) * 32, 256), 256, 0, st>>>(ra, U, big_groups, d_u32 + 4));
-    MSGPU_LAUNCH("rank_rows_cta", st, rank_rows_cta_kernel<<<kNumSMs * 2, 1024, kSortCtaMax * sizeof(unsigned long long), st>>>(ra, big_groups, d_u32 + 4));
-    MSGPU_LAUNCH("rank_rows_heavy", st, rank_rows_heavy_kernel<<<grid_for(M * 32, 256, 4), 256, 0, st>>>(ra));
+    uint2         *big_items = arena.alloc<uint2>(uint64_t(U) + M / kRankChunk + 1);
+    MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<grid_for(uint64_t(U) * 32, 256), 256, 0, st>>>(ra, U, big_items, d_u32 + 4));
+    MSGPU_LAUNCH("rank_rows_cta", st, rank_rows_cta_kernel<<<kNumSMs * 8, kRankChunk, 0, st>>>(ra, big_items, d_u32 + 4));
   }
   // ---- tile planning: four independent scans over the reads in one launch (source offsets, clipped row weights,
   // slice-table offsets, the pair count), then the tile index, which needs the weights' prefix
@@ -1209,7 +1257,7 @@ void pairing_scratch_alloc(Arena &arena, uint32_t max_tiles, PairScratch &sc) {
   sc.em_base   = arena.alloc<unsigned long long>(uint64_t(max_tiles) + 1);
   sc.ed_base   = arena.alloc<unsigned long long>(uint64_t(max_tiles) + 1);
   sc.status    = arena.alloc<unsigned long long>(2 * uint64_t(max_tiles) + 2);
-  sc.totals    = arena.alloc<unsigned long long>(4); // [0] edge matches [1] edges [2] ticket of the one-kernel variant
+  sc.totals    = arena.alloc<unsigned long long>(4 * kMaxPipeChunks); // per chunk of a pipelined emission: [0] edge matches [1] edges
 }
 
 uint64_t pairing_rows_bound(const PairPlan &pl, uint32_t n_tiles) { // output rows a range of tiles can produce at most
@@ -1229,7 +1277,8 @@ void pairing_outputs_alloc(Arena &arena, uint64_t cap, EdgeTables &e) {
   e.em_begin  = arena.alloc<uint64_t>(cap + 1);
 }
 
-static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, const PairScratch &sc) {
+// `off`: where the range's first tile sits in the scratch arrays (0 unless several ranges share one scratch)
+static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, const PairScratch &sc, uint32_t off = 0) {
   TileArgs a;
   a.rows      = pl.rows;
   a.p_read    = pl.p_read;
@@ -1244,8 +1293,8 @@ static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, cons
   a.slices    = pl.slices;
   a.tile_lo   = t_lo;
   a.tile_hi   = t_hi;
-  a.records   = sc.records;
-  a.tile_cnt  = sc.tile_cnt;
+  a.records   = sc.records + uint64_t(off) * kTileCap;
+  a.tile_cnt  = sc.tile_cnt + off;
   a.wide_list = pl.wide_list;
   a.n_wide    = pl.n_wide;
   a.error     = pl.flags + 3;
@@ -1259,12 +1308,9 @@ static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, cons
 // First half of the emission of tiles [t_lo, t_hi): enumerate + sort every tile into compact records, then the two
 // scans that turn the tiles' counts into row offsets.  Needs nothing from earlier ranges, so the tiles of the next
 // chunk can run while the rows of this one are consumed.  Asynchronous; sc.totals (device) = the range's row counts.
-void pairing_tiles(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, PairScratch &sc) {
+static void tiles_launch(cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, const PairScratch &sc, uint32_t off) {
   const uint32_t n = t_hi - t_lo;
-  if (n > sc.max_tiles) throw BuildError{MSGPU_ERR_INTERNAL, "pairing: emission scratch too small"};
-  MSGPU_CUDA(cudaMemsetAsync(sc.totals, 0, 4 * sizeof(unsigned long long), st));
-  if (!n) return;
-  const TileArgs a = tile_args(pl, t_lo, t_hi, sc);
+  const TileArgs a = tile_args(pl, t_lo, t_hi, sc, off);
   // (the shared-memory opt-in is an attribute of the function ON THE CURRENT DEVICE: set before every launch — a
   //  context per GPU in one process is supported, and the call costs less than a microsecond)
   MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel<kSrcBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
@@ -1278,21 +1324,28 @@ void pairing_tiles(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t
     int gw = pl.n_wide < uint32_t(kNumSMs) ? int(pl.n_wide) : kNumSMs;
     MSGPU_LAUNCH("pair_tiles_wide", st, pair_tiles_merge_kernel<kSrcBitsWide><<<gw, kFusedBlock, bytes, st>>>(a));
   }
-  run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{sc.tile_cnt}, n, sc.em_base, sc.totals + 0),
-            scan_job<unsigned long long>(arena, st, 1, TileHeads{sc.tile_cnt}, n, sc.ed_base, sc.totals + 1));
+}
+static void tiles_scans(Arena &arena, cudaStream_t st, uint32_t n, const PairScratch &sc, uint32_t off, unsigned long long *totals) {
+  run_scans(arena, st, scan_job<unsigned long long>(arena, st, 0, TileValid{sc.tile_cnt + off}, n, sc.em_base + off, totals + 0),
+            scan_job<unsigned long long>(arena, st, 1, TileHeads{sc.tile_cnt + off}, n, sc.ed_base + off, totals + 1));
+}
+void pairing_tiles(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, PairScratch &sc) {
+  const uint32_t n = t_hi - t_lo;
+  if (n > sc.max_tiles) throw BuildError{MSGPU_ERR_INTERNAL, "pairing: emission scratch too small"};
+  sc.n_chunks = 1;
+  MSGPU_CUDA(cudaMemsetAsync(sc.totals, 0, 4 * sizeof(unsigned long long), st));
+  if (!n) return;
+  tiles_launch(st, pl, t_lo, t_hi, sc, 0);
+  tiles_scans(arena, st, n, sc, 0, sc.totals);
 }
 
 // Second half: the records of the range -> the columns of `e` (indexed from the range's first edge match / edge; the
 // em_begin VALUES start at em_value_base = the rows of the earlier ranges of the same slice).  Asynchronous.
-void pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, PairScratch &sc,
-                  EdgeTables &e, uint64_t em_value_base) {
-  (void)arena;
+// `chunk` of a pipelined emission: its rows continue those of the chunks before it (see EmitArgs); `underneath`: the
+// launch is meant to run beside the tile kernel of the next chunk.
+static void rows_launch(cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, const PairScratch &sc, uint32_t off,
+                        const EdgeTables &e, uint64_t em_value_base, uint32_t chunk, bool last, bool underneath) {
   const uint32_t n = t_hi - t_lo;
-  e.em_value_base  = em_value_base;
-  if (!n) {
-    MSGPU_CUDA(cudaMemcpyAsync(e.em_begin, &e.em_value_base, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); // empty CSR
-    return;
-  }
   EmitArgs ea;
   ea.rows          = pl.rows;
   ea.rd_off        = pl.rd_off;
@@ -1301,11 +1354,14 @@ void pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_
   ea.tile_kind     = pl.tile_kind;
   ea.tile_lo       = t_lo;
   ea.n_tiles       = n;
-  ea.records       = sc.records;
-  ea.tile_cnt      = sc.tile_cnt;
-  ea.em_base       = sc.em_base;
-  ea.edge_base     = sc.ed_base;
-  ea.totals        = sc.totals;
+  ea.records       = sc.records + uint64_t(off) * kTileCap;
+  ea.tile_cnt      = sc.tile_cnt + off;
+  ea.em_base       = sc.em_base + off;
+  ea.edge_base     = sc.ed_base + off;
+  ea.totals        = sc.totals + 4 * chunk;
+  ea.prev_totals   = sc.totals;
+  ea.n_prev        = chunk;
+  ea.close_csr     = last ? 1u : 0u;
   ea.em_value_base = em_value_base;
   ea.out           = e;
   int grid         = kNumSMs * 8;
@@ -1322,8 +1378,54 @@ void pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_
     return;
   }
   const int bytes = int(kTileCap * sizeof(uint2));
-  MSGPU_CUDA(cudaFuncSetAttribute(pair_emit_rows_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_bulk_kernel<<<grid, kEmitBlock, bytes, st>>>(ea));
+  if (underneath) {
+    MSGPU_CUDA(cudaFuncSetAttribute(pair_emit_rows_bulk_kernel<4, kEmitBatchUnder>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_bulk_kernel<4, kEmitBatchUnder><<<grid, kEmitBlock, bytes, st>>>(ea));
+  } else {
+    MSGPU_CUDA(cudaFuncSetAttribute(pair_emit_rows_bulk_kernel<kEmitCtas, kEmitBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_bulk_kernel<kEmitCtas, kEmitBatch><<<grid, kEmitBlock, bytes, st>>>(ea));
+  }
+}
+void pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, PairScratch &sc,
+                  EdgeTables &e, uint64_t em_value_base) {
+  (void)arena;
+  const uint32_t n = t_hi - t_lo;
+  e.em_value_base  = em_value_base;
+  if (!n) {
+    MSGPU_CUDA(cudaMemcpyAsync(e.em_begin, &e.em_value_base, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); // empty CSR
+    return;
+  }
+  rows_launch(st, pl, t_lo, t_hi, sc, 0, e, em_value_base, 0, true, false);
+}
+
+// The whole emission of tiles [t_lo, t_hi) into ONE resident table, software-pipelined over `n_chunks` ranges of tiles
+// on two streams: while the tile kernel (bound by instruction issue, 5 % of the DRAM bandwidth) sorts chunk c + 1 on
+// `st`, the offsets scan and the emission kernel (bound by DRAM writes and gather latency, a third of the issue slots)
+// of chunk c run on the arena's high-priority side stream.  The tile kernel's CTAs of a chunk live for about one tile,
+// and an emission CTA compiled for 64 registers fits exactly into what one of them leaves behind (16 384 registers,
+// 51 KB of shared memory), so the two kernels share every SM instead of taking turns.  The rows of chunk c start where
+// those of the chunks before it end: the emission kernel adds up their totals itself (<= 16 words), nothing returns
+// to the host in between.
+static void pairing_pipelined(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, PairScratch &sc,
+                              EdgeTables &e, uint32_t n_chunks) {
+  const uint32_t n = t_hi - t_lo;
+  e.em_value_base  = 0;
+  sc.n_chunks      = n_chunks;
+  MSGPU_CUDA(cudaMemsetAsync(sc.totals, 0, 4 * n_chunks * sizeof(unsigned long long), st));
+  cudaStream_t side = arena.side_stream();
+  for (uint32_t c = 0; c < n_chunks; ++c) {
+    const uint32_t lo = t_lo + uint32_t(uint64_t(n) * c / n_chunks), hi = t_lo + uint32_t(uint64_t(n) * (c + 1) / n_chunks);
+    if (hi == lo) continue;
+    tiles_launch(st, pl, lo, hi, sc, lo - t_lo);
+    cudaEvent_t sorted = arena.sync_event(c);
+    MSGPU_CUDA(cudaEventRecord(sorted, st));
+    MSGPU_CUDA(cudaStreamWaitEvent(side, sorted, 0));
+    tiles_scans(arena, side, hi - lo, sc, lo - t_lo, sc.totals + 4 * c);
+    rows_launch(side, pl, lo, hi, sc, lo - t_lo, e, 0, c, c + 1 == n_chunks, c + 1 < n_chunks);
+  }
+  cudaEvent_t done = arena.sync_event(n_chunks);
+  MSGPU_CUDA(cudaEventRecord(done, side));
+  MSGPU_CUDA(cudaStreamWaitEvent(st, done, 0));
 }
 
 // reads the row counts of the last emission and the error flags of the plan (one round trip); throws on the
@@ -1332,10 +1434,15 @@ void pairing_finish(Arena &arena, cudaStream_t st, const PairPlan &pl, const Pai
                     uint64_t *n_edges) {
   char *h = static_cast<char *>(arena.host_scratch());
   MSGPU_CUDA(cudaMemcpyAsync(h, pl.flags, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  MSGPU_CUDA(cudaMemcpyAsync(h + 64, sc.totals, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  const uint32_t nc = sc.n_chunks ? sc.n_chunks : 1;
+  MSGPU_CUDA(cudaMemcpyAsync(h + 64, sc.totals, 4 * nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   MSGPU_CUDA(cudaStreamSynchronize(st));
   const uint32_t           *h_flags = reinterpret_cast<const uint32_t *>(h);
-  const unsigned long long *h_tot   = reinterpret_cast<const unsigned long long *>(h + 64);
+  unsigned long long       *h_tot   = reinterpret_cast<unsigned long long *>(h + 64);
+  for (uint32_t c = 1; c < nc; ++c) { // a pipelined emission keeps one pair of totals per chunk
+    h_tot[0] += h_tot[4 * c];
+    h_tot[1] += h_tot[4 * c + 1];
+  }
   if (h_flags[2])
     throw BuildError{MSGPU_ERR_LIMIT, "a read shares " + std::to_string(kSrcCapWide) + " or more unitigs with other reads (one "
                                       "edge of it could hold more edge matches than a pairing tile holds candidates)"};
@@ -1357,8 +1464,20 @@ void run_pairing_fused(Arena &arena, cudaStream_t st, const MatchSoA &m, const U
   PairScratch sc;
   pairing_scratch_alloc(arena, my_tiles, sc);
   if (ev_pair_done) MSGPU_CUDA(cudaEventRecord(ev_pair_done, st)); // planning done; what follows is "merge" time
-  pairing_tiles(arena, st, pl, pl.tile_lo, pl.tile_hi, sc);
-  pairing_rows(arena, st, pl, pl.tile_lo, pl.tile_hi, sc, e, 0);
+  // emission pipelined chunk by chunk underneath the tile kernel (pairing_pipelined):
+  // (measured, round 2, and OFF by default: at yeast scale 1.70 ms per construction with 0, 2, 4 or 6 chunks, 1.76 / 1.81 /
+  //  1.89 ms with 8 / 12 / 16, profiles/r2_ab_pipelined_emission_yeast.log — the two kernels do share the SMs, and each
+  //  loses what the other gains: the tile kernel needs its four resident CTAs to hide its barriers)
+  uint32_t n_chunks = 0;
+  if (const char *pc = std::getenv("MSGPU_PIPE_CHUNKS")) n_chunks = uint32_t(std::atoi(pc)); // development A/B
+  if (n_chunks > kMaxPipeChunks) n_chunks = kMaxPipeChunks;
+  if (n_chunks > my_tiles / 64) n_chunks = my_tiles / 64; // (no empty chunks)
+  if (n_chunks >= 2) {
+    pairing_pipelined(arena, st, pl, pl.tile_lo, pl.tile_hi, sc, e, n_chunks);
+  } else {
+    pairing_tiles(arena, st, pl, pl.tile_lo, pl.tile_hi, sc);
+    pairing_rows(arena, st, pl, pl.tile_lo, pl.tile_hi, sc, e, 0);
+  }
   pairing_finish(arena, st, pl, sc, &e.n_em, &e.n_edges);
   e.pair_rows = pl.rows; // kept (in the arena) for the stage that follows: msgpu_chain_overlaps
   e.p_read    = pl.p_read;

@@ -2,8 +2,9 @@
 //
 // The arrays scanned on this path are per-line, per-match, per-read or per-unitig: one to a few hundred tiles, so what
 // a scan costs is its latency, not its bytes.  One kernel: a block takes a ticket (tiles are numbered in the order
-// blocks start, so a tile only ever waits for tiles that are already running), reduces its 8192 items (a warp owns
-// 512 consecutive ones, lane-striped, so every load and store is one contiguous run), publishes the tile aggregate,
+// blocks start, so a tile only ever waits for tiles that are already running), reduces its items (512 threads x 2, 8
+// or 16 items by the length of the scan; a warp owns consecutive ones, lane-striped, so every load and store is one
+// contiguous run), publishes the tile aggregate,
 // looks back over its predecessors' aggregates / inclusive prefixes, publishes its own inclusive prefix and writes
 // its outputs.  Every input value is evaluated once.  Input values come from a functor so flags packed in bytes /
 // derived counts need no staging array.  Up to four independent scans share one launch (blockIdx.y picks the scan).
@@ -13,8 +14,8 @@
 // observes value and state together and no fence is needed.  The epoch is the serial number of the scan that wrote
 // the word: stale words read as "not ready" and no launch is spent on clearing them.  Sums must stay below 2^46
 // (7e13; the largest quantity scanned here is the pair count, ~1e11 at human scale); a larger one traps.
-// The look-back window is the whole block (512 predecessors per round trip) and a tile holds 8192 items, so the scans of
-// this path (at most a few hundred tiles) resolve in one round trip after their own reduce.
+// The look-back window is the whole block (512 predecessors per round trip), so the scans of this path (at most a few
+// hundred tiles) resolve in one or two round trips after their own reduce.
 // `live` (optional): a count in device memory; items at index >= live contribute nothing and their outputs are not
 // written, tiles entirely behind it retire at once.  Lets a scan be launched over a capacity bound when the actual
 // count is only known on the device.
@@ -25,8 +26,18 @@
 namespace msgpu {
 
 constexpr int      kScanBlock     = 512;
-constexpr int      kScanItems     = 16; // items per thread (lane-striped inside the warp's run of 512)
+constexpr int      kScanItems     = 16; // items per thread (lane-striped inside the warp's run) of a LONG scan
 constexpr int      kScanTile      = kScanBlock * kScanItems;
+// A thread evaluates its items one after the other, and the input functors of this path are chains of dependent loads
+// (a row's weight, the prefix before it, ...): at 16 items per thread a scan over 7e4 reads is nine blocks that each
+// wait for 16 round trips to L2 (ncu: three quarters of the stall samples of such a scan sit on the functor's loads).
+// Short scans therefore take 2 (or 8) items per thread — as many tiles as fit the GPU in one wave (4 blocks per SM).
+constexpr uint64_t kScanWaveBlocks = 148 * 4;
+inline int scan_items_for(uint64_t n) {
+  if (n <= kScanWaveBlocks * kScanBlock * 2) return 2;
+  if (n <= kScanWaveBlocks * kScanBlock * 8) return 8;
+  return kScanItems;
+}
 constexpr int      kScanValShift  = 18;
 constexpr unsigned kScanEpochMask = 0xffffu;
 
@@ -48,18 +59,21 @@ template <class T, class InFn> struct ScanJob {
   unsigned            epoch;
   unsigned           *ticket;      // the slot's ticket counter (grows forever) ...
   unsigned            ticket_base; // ... and its value when this scan starts (host bookkeeping, Arena::scan_state)
+  int                 items;       // items per thread: 2, 8 or kScanItems (scan_items_for)
+  unsigned            n_tiles;     // tiles of n_cap at that size
 };
 
 // the work of one block of one scan; blocks past the scan's tiles (a launch is sized for its longest scan) leave
-template <class Job> __device__ __forceinline__ void scan_block(const Job &job) {
+template <int kItems, class Job> __device__ __forceinline__ void scan_block_n(const Job &job) {
   using T = typename Job::value_type;
   constexpr int       kWarps = kScanBlock / 32;
+  constexpr int       kTile  = kScanBlock * kItems;
   __shared__ unsigned s_tile;
   __shared__ uint64_t s_n;
   __shared__ T        w_tot[kWarps]; // warp totals of the tile
   __shared__ T        w_sum[kWarps];
   __shared__ unsigned w_inc[kWarps];
-  const uint64_t n_tiles_cap = (job.n_cap + kScanTile - 1) / kScanTile;
+  const uint64_t n_tiles_cap = job.n_tiles;
   if (blockIdx.x >= n_tiles_cap) return;
   const unsigned epoch = job.epoch;
   const unsigned l = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -77,20 +91,20 @@ template <class Job> __device__ __forceinline__ void scan_block(const Job &job) 
   __syncthreads();
   const unsigned tile      = s_tile;
   const uint64_t n         = s_n;
-  const unsigned last_tile = n ? unsigned((n - 1) / kScanTile) : 0u; // the tile that reports the total
+  const unsigned last_tile = n ? unsigned((n - 1) / kTile) : 0u; // the tile that reports the total
   if (tile > last_tile) return;
   // a warp owns 512 consecutive items; lane l takes items l, l + 32, ... of them, so every load and store of the warp
   // is one contiguous run
-  const uint64_t wbase = uint64_t(tile) * kScanTile + uint64_t(w) * (32 * kScanItems);
-  T              v[kScanItems];
+  const uint64_t wbase = uint64_t(tile) * kTile + uint64_t(w) * (32 * kItems);
+  T              v[kItems];
 #pragma unroll
-  for (int j = 0; j < kScanItems; ++j) {
+  for (int j = 0; j < kItems; ++j) {
     const uint64_t i = wbase + uint64_t(j) * 32 + l;
     v[j]             = i < n ? job.in(i) : T(0);
   }
   T carry = 0; // exclusive prefix inside the warp's run
 #pragma unroll
-  for (int j = 0; j < kScanItems; ++j) {
+  for (int j = 0; j < kItems; ++j) {
     const T incl = warp_inclusive_scan(v[j]);
     const T row  = __shfl_sync(0xffffffffu, incl, 31);
     v[j]         = carry + incl - v[j];
@@ -150,11 +164,17 @@ template <class Job> __device__ __forceinline__ void scan_block(const Job &job) 
   if (job.out) {
     const T off = prefix + wex;
 #pragma unroll
-    for (int j = 0; j < kScanItems; ++j) {
+    for (int j = 0; j < kItems; ++j) {
       const uint64_t i = wbase + uint64_t(j) * 32 + l;
       if (i < n) job.out[i] = off + v[j];
     }
   }
+}
+
+template <class Job> __device__ __forceinline__ void scan_block(const Job &job) {
+  if (job.items == 2) scan_block_n<2>(job);
+  else if (job.items == 8) scan_block_n<8>(job);
+  else scan_block_n<kScanItems>(job);
 }
 
 // up to four independent scans in ONE launch (blockIdx.y picks the scan): they cost the latency of one
@@ -176,33 +196,33 @@ __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, J1 j1, J2 j2, J
 template <class T, class InFn>
 ScanJob<T, InFn> scan_job(Arena &arena, cudaStream_t st, int slot, InFn in, uint64_t n, T *out, T *total_out,
                           ScanLive live = ScanLive{}) {
-  const uint64_t n_tiles = (n + kScanTile - 1) / kScanTile;
+  const int      items   = scan_items_for(n);
+  const uint64_t n_tiles = (n + uint64_t(kScanBlock) * items - 1) / (uint64_t(kScanBlock) * items);
   unsigned       epoch = 0, *ticket = nullptr, ticket_base = 0;
   // the launch covers this scan's tiles whenever it happens at all (run_scans sizes the grid for the longest job and
   // skips the launch only when every job is empty), so a multi-tile scan takes exactly n_tiles tickets
   auto *state = static_cast<unsigned long long *>(arena.scan_state(
       slot, n_tiles * sizeof(unsigned long long), st, &epoch, n_tiles > 1 ? unsigned(n_tiles) : 0u, &ticket, &ticket_base));
-  return ScanJob<T, InFn>{in, n, live, out, total_out, state, epoch, ticket, ticket_base};
+  return ScanJob<T, InFn>{in, n, live, out, total_out, state, epoch, ticket, ticket_base, items, unsigned(n_tiles)};
 }
-inline unsigned scan_grid(uint64_t n) { return unsigned((n + kScanTile - 1) / kScanTile); }
 
 template <class J0> void run_scans(Arena &arena, cudaStream_t st, const J0 &j0) {
   if (!j0.n_cap) return;
-  MSGPU_LAUNCH("scan", st, scan_kernel<J0><<<scan_grid(j0.n_cap), kScanBlock, 0, st>>>(j0));
+  MSGPU_LAUNCH("scan", st, scan_kernel<J0><<<j0.n_tiles, kScanBlock, 0, st>>>(j0));
 }
 template <class J0, class J1> void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1) {
-  const uint64_t n = j0.n_cap > j1.n_cap ? j0.n_cap : j1.n_cap;
+  const unsigned n = j0.n_tiles > j1.n_tiles ? j0.n_tiles : j1.n_tiles; // (an empty scan has no tiles)
   if (!n) return;
-  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1><<<dim3(scan_grid(n), 2), kScanBlock, 0, st>>>(j0, j1)));
+  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1><<<dim3(n, 2), kScanBlock, 0, st>>>(j0, j1)));
 }
 template <class J0, class J1, class J2, class J3>
 void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1, const J2 &j2, const J3 &j3) {
-  uint64_t n = j0.n_cap;
-  n          = j1.n_cap > n ? j1.n_cap : n;
-  n          = j2.n_cap > n ? j2.n_cap : n;
-  n          = j3.n_cap > n ? j3.n_cap : n;
+  unsigned n = j0.n_tiles;
+  n          = j1.n_tiles > n ? j1.n_tiles : n;
+  n          = j2.n_tiles > n ? j2.n_tiles : n;
+  n          = j3.n_tiles > n ? j3.n_tiles : n;
   if (!n) return;
-  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1, J2, J3><<<dim3(scan_grid(n), 4), kScanBlock, 0, st>>>(j0, j1, j2, j3)));
+  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1, J2, J3><<<dim3(n, 4), kScanBlock, 0, st>>>(j0, j1, j2, j3)));
 }
 
 // a single scan.  n == 0 is allowed (total = 0).
