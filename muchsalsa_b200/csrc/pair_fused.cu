@@ -62,6 +62,9 @@ constexpr int      kItems      = kTileCap / kFusedBlock;   // sort items per thr
 #ifndef MSGPU_MERGE_CTAS
 #define MSGPU_MERGE_CTAS (MSGPU_IDX_BITS <= 12 ? 4 : 2)
 #endif
+#ifndef MSGPU_TICKETS
+#define MSGPU_TICKETS 1 // 0: tiles strided over the grid (the A/B of the ticket counters)
+#endif
 constexpr int      kMergeCtas  = MSGPU_MERGE_CTAS;          // resident CTAs of the merge kernel per SM (narrow words)
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -525,6 +528,7 @@ struct TileArgs {
   uint32_t        n_wide;
   uint2          *tile_cnt;         // per tile: (surviving candidates, run heads)
   unsigned int   *error;
+  unsigned int   *ticket;           // zero at launch: hands out the tiles behind the first gridDim.x
   uint32_t        wide; // 0: every sort word fits 32 bits for any tile, so the launch carries the small buffers only
   uint32_t        no_overlap_test; // the scrubber's pairing: every pair of a group is kept (scrubber_bfs.py:109-113)
 };
@@ -555,7 +559,7 @@ template <int kSB> struct MergeShared { // everything but the two word buffers, 
   uint32_t        scan[33];
   uint32_t        warp_tot[kFusedWarps];
   uint32_t        row_start[kTileCap / 32 + 1]; // bit p: a row's candidates start at position p (positions = slots of the row)
-  uint32_t        smin, smax, max_row_src;
+  uint32_t        smin, smax, max_row_src, next_item;
 };
 constexpr uint16_t kDropped = 0x8000u;
 template <int kSB> constexpr size_t merge_off() { return (sizeof(MergeShared<kSB>) + 15) & ~size_t(15); }
@@ -774,7 +778,13 @@ __global__ void __launch_bounds__(kFusedBlock, kSB == kSrcBits ? kMergeCtas : 1)
   constexpr bool     kIsWide = kSB != kSrcBits;
   const uint32_t     n_items = kIsWide ? a.n_wide : a.tile_hi - a.tile_lo;
 
-  for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+  // A CTA's first tile is its block index; the next ones come from a ticket counter (tiles differ in candidates and
+  // merge levels, and a fixed stride left the average SM idle for the last 6 % of the kernel: ncu sm__cycles_active).
+  // The ticket for the NEXT tile is drawn by thread 0 between the two barriers that open a tile, so the atomic's
+  // round trip hides behind the staging of this one.  (The instantiation for many sources keeps its stride.)
+  uint32_t nxt = 0;
+  for (uint32_t item = blockIdx.x; item < n_items; item = nxt) {
+    nxt = item + gridDim.x;
     const uint32_t tile = kIsWide ? a.wide_list[item] : a.tile_lo + item;
     if (kIsWide && (tile < a.tile_lo || tile >= a.tile_hi)) continue; // (a chunk takes the listed tiles of its range)
     __syncthreads(); // previous tile fully done with shared memory
@@ -782,9 +792,11 @@ __global__ void __launch_bounds__(kFusedBlock, kSB == kSrcBits ? kMergeCtas : 1)
       s.smin        = 0xffffffffu;
       s.smax        = 0;
       s.max_row_src = 0;
+      if (!kIsWide && MSGPU_TICKETS) s.next_item = gridDim.x + atomicAdd(a.ticket, 1u);
     }
     if (t < kTileCap / 32 + 1) s.row_start[t] = 0;
     __syncthreads();
+    if (!kIsWide && MSGPU_TICKETS) nxt = s.next_item;
     const uint32_t st_idx = tile - a.tile_lo;
     const uint32_t r0 = a.tile_row[tile], kind = a.tile_kind[tile];
     const uint32_t q0 = a.rd_off[r0];
@@ -927,6 +939,7 @@ struct EmitArgs {
   // `n_prev` launches before it, whose totals (4 words each) start at prev_totals; only the last launch closes the CSR
   const unsigned long long *prev_totals;
   uint32_t        n_prev, close_csr;
+  unsigned int   *ticket; // zero at launch: hands out the tiles behind the first gridDim.x
   EdgeTables      out;
 };
 
@@ -965,7 +978,9 @@ __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_kernel(E
   unsigned long long em_before, ed_before;
   rows_before(a, &em_before, &ed_before);
   if (blockIdx.x == 0 && t == 0 && a.close_csr) a.out.em_begin[ed_before + a.totals[1]] = a.em_value_base + em_before + a.totals[0];
-  for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
+  __shared__ uint32_t next_ti; // tiles by tickets, as in the bulk-copy kernel
+  uint32_t            nxt = 0;
+  for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti = nxt) {
     const uint32_t           tile    = a.tile_lo + ti;
     const uint32_t           n_valid = a.tile_cnt[ti].x;
     const unsigned long long em0 = em_before + a.em_base[ti], ed0 = ed_before + a.edge_base[ti];
@@ -979,12 +994,14 @@ __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_kernel(E
       r[u]             = k < n_valid ? __ldg(rec + k) : make_uint2(0, 0);
     }
     __syncthreads(); // previous tile done with the staged sources
+    if (t == 0) next_ti = MSGPU_TICKETS ? gridDim.x + atomicAdd(a.ticket, 1u) : ti + gridDim.x;
     const bool staged = n_src <= kSrcCap; // (rows with more sources: their rows are read in place, one more gather)
     if (n_valid && staged)
       for (uint32_t j = t; j < n_src; j += kEmitBlock) {
         ld_row32(a.rows + a.rd_src[q0 + j], src_lo[j], src_hi[j]);
       }
     __syncthreads();
+    nxt = next_ti;
     for (uint32_t k0 = t; k0 < n_valid; k0 += kEmitBlock * kEmitBatch) {
       PairRow pb[kEmitBatch];
 #pragma unroll
@@ -1063,7 +1080,11 @@ template <int kCtas, int kBatch> __global__ void __launch_bounds__(kEmitBlock, k
   unsigned long long em_before, ed_before;
   rows_before(a, &em_before, &ed_before);
   if (blockIdx.x == 0 && t == 0 && a.close_csr) a.out.em_begin[ed_before + a.totals[1]] = a.em_value_base + em_before + a.totals[0];
-  for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti += gridDim.x) {
+  // tiles by tickets, as in the tile kernel (a tile holds 500 .. 4096 records: with a fixed stride the average SM idled
+  // for 9 % of the kernel); thread 0 draws the next ticket while the sources of this tile are staged
+  __shared__ uint32_t next_ti;
+  uint32_t            nxt = 0;
+  for (uint32_t ti = blockIdx.x; ti < a.n_tiles; ti = nxt) {
     const uint32_t           tile    = a.tile_lo + ti;
     const uint32_t           n_valid = a.tile_cnt[ti].x;
     const unsigned long long em0 = em_before + a.em_base[ti], ed0 = ed_before + a.edge_base[ti];
@@ -1071,6 +1092,7 @@ template <int kCtas, int kBatch> __global__ void __launch_bounds__(kEmitBlock, k
     const uint32_t n_src = (a.tile_kind[tile] ? a.rd_off[r0 + 1] : a.rd_off[a.tile_row[tile + 1]]) - q0;
     const uint2   *rec   = a.records + uint64_t(ti) * kTileCap;
     __syncthreads(); // previous tile done with the records and the staged sources
+    if (t == 0) next_ti = MSGPU_TICKETS ? gridDim.x + atomicAdd(a.ticket, 1u) : ti + gridDim.x;
     if (t == 0 && n_valid) {
       const uint32_t bytes = (n_valid * uint32_t(sizeof(uint2)) + 15u) & ~15u; // (a tile's slots are 32 KB: in bounds)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1086,6 +1108,7 @@ template <int kCtas, int kBatch> __global__ void __launch_bounds__(kEmitBlock, k
         ld_row32(a.rows + a.rd_src[q0 + j], src_lo[j], src_hi[j]);
       }
     __syncthreads();
+    nxt = next_ti;
     if (n_valid) { // every thread waits for the copy (hardware sleep, not a poll)
       uint32_t done = 0;
       while (!done)
@@ -1298,6 +1321,7 @@ static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, cons
   a.wide_list = pl.wide_list;
   a.n_wide    = pl.n_wide;
   a.error     = pl.flags + 3;
+  a.ticket    = nullptr; // (set by tiles_launch)
   // a merge word is (second - min second) << 12 | slot: 32 bits are enough when read ids have <= 20 bits; otherwise
   // tiles choose per tile and the launch carries the 64-bit buffers
   a.wide = pl.n_reads > (1ull << (32 - kIdxBits)) - 1 ? 1u : 0u; // (then second - min second <= 2^20 - 2: no word is ~0)
@@ -1308,14 +1332,18 @@ static TileArgs tile_args(const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, cons
 // First half of the emission of tiles [t_lo, t_hi): enumerate + sort every tile into compact records, then the two
 // scans that turn the tiles' counts into row offsets.  Needs nothing from earlier ranges, so the tiles of the next
 // chunk can run while the rows of this one are consumed.  Asynchronous; sc.totals (device) = the range's row counts.
-static void tiles_launch(cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, const PairScratch &sc, uint32_t off) {
+// `totals`: the four zeroed words of this emission — [0] edge matches, [1] edges (written by the scans), [2] / [3] the
+// tile tickets of the tile kernel / of the emission kernel
+static void tiles_launch(cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, const PairScratch &sc, uint32_t off,
+                         unsigned long long *totals) {
   const uint32_t n = t_hi - t_lo;
-  const TileArgs a = tile_args(pl, t_lo, t_hi, sc, off);
+  TileArgs       a = tile_args(pl, t_lo, t_hi, sc, off);
+  a.ticket         = reinterpret_cast<unsigned int *>(totals + 2);
   // (the shared-memory opt-in is an attribute of the function ON THE CURRENT DEVICE: set before every launch — a
   //  context per GPU in one process is supported, and the call costs less than a microsecond)
   MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel<kSrcBits>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kMergeBytesWide)));
-  // 32 registers, 51 KB (narrow): four resident CTAs per SM; a few waves of them, tiles strided over the grid
-  int grid = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * 4;
+  // 32 registers, 51 KB (narrow): four resident CTAs per SM, one wave of them, tiles handed out by tickets
+  int grid = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * (MSGPU_TICKETS ? 1 : 4);
   if (uint32_t(grid) > n) grid = int(n);
   MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<kSrcBits><<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
   if (pl.n_wide) { // sub-tiles of rows with 513 .. 4095 sources (skipped above): the same kernel staged for that many
@@ -1335,7 +1363,7 @@ void pairing_tiles(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t
   sc.n_chunks = 1;
   MSGPU_CUDA(cudaMemsetAsync(sc.totals, 0, 4 * sizeof(unsigned long long), st));
   if (!n) return;
-  tiles_launch(st, pl, t_lo, t_hi, sc, 0);
+  tiles_launch(st, pl, t_lo, t_hi, sc, 0, sc.totals);
   tiles_scans(arena, st, n, sc, 0, sc.totals);
 }
 
@@ -1359,12 +1387,13 @@ static void rows_launch(cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint
   ea.em_base       = sc.em_base + off;
   ea.edge_base     = sc.ed_base + off;
   ea.totals        = sc.totals + 4 * chunk;
+  ea.ticket        = reinterpret_cast<unsigned int *>(sc.totals + 4 * chunk + 3);
   ea.prev_totals   = sc.totals;
   ea.n_prev        = chunk;
   ea.close_csr     = last ? 1u : 0u;
   ea.em_value_base = em_value_base;
   ea.out           = e;
-  int grid         = kNumSMs * 8;
+  int grid         = MSGPU_TICKETS ? kNumSMs * (underneath ? 4 : kEmitCtas) : kNumSMs * 8; // one wave; the tiles behind it go by tickets
   if (uint32_t(grid) > n) grid = int(n);
   // (measured and not kept, round 2: the same emission with four consecutive rows per thread and 128-bit column
   //  stores — 0.75 ms instead of 0.49 ms at yeast scale, profiles/r2_ab_emit_vec_vs_scalar_and_fused.log: the kernel is
@@ -1416,7 +1445,7 @@ static void pairing_pipelined(Arena &arena, cudaStream_t st, const PairPlan &pl,
   for (uint32_t c = 0; c < n_chunks; ++c) {
     const uint32_t lo = t_lo + uint32_t(uint64_t(n) * c / n_chunks), hi = t_lo + uint32_t(uint64_t(n) * (c + 1) / n_chunks);
     if (hi == lo) continue;
-    tiles_launch(st, pl, lo, hi, sc, lo - t_lo);
+    tiles_launch(st, pl, lo, hi, sc, lo - t_lo, sc.totals + 4 * c);
     cudaEvent_t sorted = arena.sync_event(c);
     MSGPU_CUDA(cudaEventRecord(sorted, st));
     MSGPU_CUDA(cudaStreamWaitEvent(side, sorted, 0));
