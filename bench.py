@@ -287,18 +287,25 @@ def run_ours(args):
 
     # ---- the stage that consumes the tables while they are in HBM (chaining + overlaps per edge);
     # reported beside the metric, not part of it.  Device time from the library's own events.
-    chain_ms, filter_ms = [], []
+    chain_ms, filter_ms, filter_wall_ms = [], [], []
     for it in range(min(args.steps, 3) + 1):
         step_device()
         gb.chain_overlaps(300)
-        if world == 1:  # the contraction test needs the whole edge table on one device (msgpu.h: msgpu_edge_filters)
+        if world == 1:
             gb.edge_filters(300)
+        else:  # the contraction test reads rows of other ranks: the views of the slices travel first (one all-gather)
+            barrier()
+            t0 = time.perf_counter()
+            sb.edge_filters(300)
+            torch.cuda.synchronize()
+            filter_wall = 1e3 * (time.perf_counter() - t0)
         if it:  # the first call grows the arena (cudaMalloc inside the timed span): warm-up
             chain_ms.append(gb.chain_ms())
-            if world == 1:
-                filter_ms.append(gb.edge_filters_ms())
+            filter_ms.append(gb.edge_filters_ms())
+            if world > 1:
+                filter_wall_ms.append(filter_wall)
     chain_t = reduce(sum(chain_ms) / len(chain_ms), "MAX")
-    filter_t = sum(filter_ms) / len(filter_ms) if filter_ms else None
+    filter_t = reduce(sum(filter_ms) / len(filter_ms), "MAX") if filter_ms else None
 
     # ---- K8: the resident sequence store + batched slice / reverse complement (rank 0 at N = 1)
     sequence = bench_sequences(gb, args.workload, stream) if world == 1 and not args.no_sequence else None
@@ -344,8 +351,17 @@ def run_ours(args):
                     "reference (tests/test_filters_gpu.py)",
             "ms": round(filter_t, 3), "edges_per_s": n_edges / filter_t * 1e3,
             "cpu_reference": ((cpu or {}).get("chain") or {}).get("filters")}
-    else:
-        out["edge_filters"] = {"skipped": "needs the whole edge table on one device; every rank holds one slice"}
+        if world > 1:
+            f = gb.filters()
+            out["edge_filters"]["sharded"] = {
+                "what": "every rank publishes a compact view of its slice (per edge: first, second, orders, shadow; per "
+                        "order: offsets, flags), ONE all-gather carries the views, the passes run on the rank's own edges "
+                        "against their concatenation (msgpu_edge_filters_sharded; tests/test_multi_gpu.py compares the "
+                        "slices' verdicts with the reference's)",
+                "ms_with_exchange": round(reduce(sum(filter_wall_ms) / len(filter_wall_ms), "MAX"), 3),
+                "view_bytes_received_per_rank": int(getattr(sb, "filter_exchange_bytes", 0)),
+                "contraction_edges": int(reduce(int((f["contraction_order"] >= 0).sum()), "SUM")),
+                "deletable_edges": int(reduce(int(f["deletable"].sum()), "SUM"))}
     if sequence is not None:
         out["sequence"] = sequence
     if world > 1:

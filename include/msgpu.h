@@ -343,6 +343,27 @@ int msgpu_edge_filters_device(const msgpu_ctx *ctx, msgpu_edge_filter_tables *ou
 int msgpu_edge_filters_host(msgpu_ctx *ctx, msgpu_edge_filter_tables *out); /* pinned host copy */
 int msgpu_edge_filters_ms(const msgpu_ctx *ctx, float *out); /* device time of the last msgpu_edge_filters, ms */
 
+/* The same passes on ONE SLICE of a multi-GPU build (msgpu_build_from_shards with n_parts > 1).  findContractionEdges
+ * walks the edges around an order's start vertex and the third edge of every triangle (src/main.cpp:432-443,
+ * Graph::getNeighbors / hasEdge / getEdge) — rows that live on other ranks — so every rank first publishes a compact
+ * VIEW of its slice: per edge (first, second, number of orders, shadow flag), per order (leftOffset, rightOffset,
+ * flags), orders packed densely.
+ *   msgpu_filter_view_describe : sizes of this rank's view (after msgpu_chain_overlaps); blob_bytes is what
+ *                                msgpu_filter_view_export writes
+ *   msgpu_filter_view_export   : the view into a device buffer of at least blob_bytes (16-byte aligned)
+ *   msgpu_edge_filters_sharded : the caller has exchanged headers and views (an all-gather: host code's business);
+ *                                headers[r] / dev_blobs[r] = rank r's, device pointers, rank order.  Verdicts are
+ *                                produced for THIS rank's edges (msgpu_edge_filters_device / _host as usual) and are
+ *                                the ones msgpu_edge_filters gives on one device for the same edges.
+ * msgpu_edge_filters itself refuses a slice (MSGPU_ERR_LIMIT) rather than answer without the neighbours. */
+typedef struct msgpu_filter_view_header {
+  uint64_t n_edges, n_orders, blob_bytes, reserved;
+} msgpu_filter_view_header;
+int msgpu_filter_view_describe(msgpu_ctx *ctx, msgpu_filter_view_header *out);
+int msgpu_filter_view_export(msgpu_ctx *ctx, void *dev_dst, uint64_t capacity);
+int msgpu_edge_filters_sharded(msgpu_ctx *ctx, uint32_t n_parts, uint32_t part, const msgpu_filter_view_header *headers,
+                               const void *const *dev_blobs, uint64_t wiggle_room);
+
 /* Device time of the stages of the last build, milliseconds (CUDA events on the context's stream). */
 typedef struct msgpu_timings {
   float h2d_ms, ingest_ms, pair_ms, merge_ms, d2h_ms, total_ms;

@@ -83,6 +83,10 @@ class EdgeFilters(C.Structure):
                 ("n_kept_orders", u32p), ("weight", u64p), ("consensus", u8p)]
 
 
+class FilterViewHeader(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_edges", "n_orders", "blob_bytes", "reserved")]
+
+
 class SeqReq(C.Structure):
     _fields_ = [("which", C.c_uint32), ("id", C.c_uint32), ("left", C.c_int32), ("right", C.c_int32),
                 ("direction", C.c_uint32)]
@@ -126,6 +130,10 @@ SIGNATURES = {
     "msgpu_edge_filters_device": (C.c_int, [C.c_void_p, C.POINTER(EdgeFilters)]),
     "msgpu_edge_filters_host": (C.c_int, [C.c_void_p, C.POINTER(EdgeFilters)]),
     "msgpu_edge_filters_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "msgpu_filter_view_describe": (C.c_int, [C.c_void_p, C.POINTER(FilterViewHeader)]),
+    "msgpu_filter_view_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "msgpu_edge_filters_sharded": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(FilterViewHeader),
+                                             C.POINTER(C.c_void_p), C.c_uint64]),
     "msgpu_result_timings": (C.c_int, [C.c_void_p, C.POINTER(Timings)]),
     "msgpu_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "msgpu_profile_read": (C.c_int, [C.c_void_p, C.POINTER(KernelStat), C.c_size_t, C.POINTER(C.c_size_t)]),

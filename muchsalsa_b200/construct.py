@@ -319,6 +319,24 @@ class GraphBuilder:
         self._check(self._lib.msgpu_edge_filters(self._h, wiggle_room))
         return self
 
+    def filter_view_header(self) -> "_lib.FilterViewHeader":
+        """Sizes of this rank's view of its edges and orders (multi-GPU edge filters; after chain_overlaps)."""
+        h = _lib.FilterViewHeader()
+        self._check(self._lib.msgpu_filter_view_describe(self._h, C.byref(h)))
+        return h
+
+    def filter_view_export(self, dev_ptr: int, capacity: int):
+        self._check(self._lib.msgpu_filter_view_export(self._h, C.c_void_p(dev_ptr), capacity))
+        return self
+
+    def edge_filters_sharded(self, headers, blob_ptrs, part: int, n_parts: int, wiggle_room: int = 300):
+        """The edge filters on one slice of a multi-GPU build: headers[r] / blob_ptrs[r] = the view of rank r (device
+        pointers, rank order).  Verdicts for this rank's edges (filters())."""
+        hs = (_lib.FilterViewHeader * n_parts)(*headers)
+        ps = (C.c_void_p * n_parts)(*[C.c_void_p(int(p)) for p in blob_ptrs])
+        self._check(self._lib.msgpu_edge_filters_sharded(self._h, n_parts, part, hs, ps, wiggle_room))
+        return self
+
     def edge_filters_ms(self) -> float:
         ms = C.c_float()
         self._check(self._lib.msgpu_edge_filters_ms(self._h, C.byref(ms)))

@@ -210,5 +210,20 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
 // computeBitweight (src/main.cpp:416-460, 534-573, sc.cpp:29-88)
 void run_edge_filters(Arena &arena, cudaStream_t st, uint64_t n_reads, const EdgeTables &edges, const OrderTables &orders,
                       uint64_t wiggle_room, FilterTables &out, float *ms_out);
+// the same on one slice of a multi-GPU build: every rank describes and exports a compact view of its edges and orders
+// (what the contraction test reads of a neighbour edge), the views travel, and the passes run on this rank's edges
+// against the concatenation of all views
+struct FilterView {
+  bool      valid = false;
+  uint64_t  n_edges = 0, n_orders = 0, bytes = 0;
+  uint64_t *ord_prefix = nullptr; // first packed order slot of every edge of this device
+};
+void filter_view_describe(Arena &arena, cudaStream_t st, const EdgeTables &edges, const OrderTables &orders, FilterView &view);
+void filter_view_export(cudaStream_t st, const EdgeTables &edges, const OrderTables &orders, const FilterView &view,
+                        void *dev_dst);
+void run_edge_filters_sharded(Arena &arena, cudaStream_t st, uint64_t n_reads, const EdgeTables &edges,
+                              const OrderTables &orders, uint64_t wiggle_room, uint32_t n_parts, uint32_t part,
+                              const msgpu_filter_view_header *headers, const void *const *dev_blobs, FilterTables &out,
+                              float *ms_out);
 
 } // namespace msgpu

@@ -70,6 +70,7 @@ struct msgpu_ctx {
   bool         orders_host_valid = false;
   msgpu_orders host_orders_view{};
 
+  FilterView               filter_view; // msgpu_filter_view_describe
   FilterTables             filters; // msgpu_edge_filters
   float                    filter_ms = 0.f;
   PinnedBuf                host_filters;
@@ -244,6 +245,7 @@ void build_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes, bool pair =
   ctx->n_parts     = 1;
   ctx->orders      = OrderTables{};
   ctx->filters     = FilterTables{};
+  ctx->filter_view = FilterView{};
   ctx->arena.reset();
   ctx->profiler.clear();
   MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
@@ -393,6 +395,7 @@ void anchor_graph_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes) {
   ctx->n_parts     = 1;
   ctx->orders      = OrderTables{};
   ctx->filters     = FilterTables{};
+  ctx->filter_view = FilterView{};
   {
     cudaEvent_t keep      = ctx->chunks.rows_done;
     ctx->chunks           = msgpu_ctx::Chunks{};
@@ -456,6 +459,7 @@ void unitig_coverage_device(msgpu_ctx *ctx, const char *d_paf, size_t n_bytes, m
   ctx->n_parts     = 1;
   ctx->orders      = OrderTables{};
   ctx->filters     = FilterTables{};
+  ctx->filter_view = FilterView{};
   ctx->coverage    = CoverageTables{};
   {
     cudaEvent_t keep      = ctx->chunks.rows_done;
@@ -550,6 +554,7 @@ int msgpu_build_from_records(msgpu_ctx *ctx, const msgpu_match_soa *r, uint32_t 
     ctx->host_valid  = false;
     ctx->orders      = OrderTables{};
     ctx->filters     = FilterTables{};
+    ctx->filter_view = FilterView{};
     ctx->arena.reset();
     ctx->profiler.clear();
     ctx->n_parts = 1;
@@ -638,6 +643,7 @@ int msgpu_build_from_shards(msgpu_ctx *ctx, uint32_t n_shards, const msgpu_shard
     ctx->host_valid  = false;
     ctx->orders      = OrderTables{};
     ctx->filters     = FilterTables{};
+    ctx->filter_view = FilterView{};
     ctx->arena.reset();
     ctx->profiler.clear();
     MSGPU_CUDA(cudaEventRecord(ctx->ev[1], st));
@@ -882,6 +888,7 @@ int msgpu_chain_overlaps(msgpu_ctx *ctx, uint64_t wiggle_room) {
     ctx->orders             = OrderTables{};
     ctx->orders_host_valid  = false;
     ctx->filters            = FilterTables{};
+    ctx->filter_view = FilterView{};
     ctx->filters_host_valid = false;
     ctx->profiler.clear();
     run_chain_overlaps(ctx->arena, ctx->stream, ctx->reads, ctx->unitigs, ctx->matches, ctx->edges, wiggle_room,
@@ -967,12 +974,46 @@ int msgpu_edge_filters(msgpu_ctx *ctx, uint64_t wiggle_room) {
     if (ctx->n_parts > 1)
       throw BuildError{MSGPU_ERR_LIMIT,
                        "msgpu_edge_filters needs the whole edge table on one device; this context holds one slice of " +
-                           std::to_string(ctx->n_parts) + " (multi-GPU build)"};
+                           std::to_string(ctx->n_parts) + " (multi-GPU build: exchange the views and call msgpu_edge_filters_sharded)"};
     ctx->filters            = FilterTables{};
     ctx->filters_host_valid = false;
     ctx->profiler.clear();
     run_edge_filters(ctx->arena, ctx->stream, ctx->reads.n, ctx->edges, ctx->orders, wiggle_room, ctx->filters,
                      &ctx->filter_ms);
+  });
+}
+
+int msgpu_filter_view_describe(msgpu_ctx *ctx, msgpu_filter_view_header *out) {
+  if (!out) return MSGPU_ERR_INVALID_ARG;
+  return guarded(ctx, [&] {
+    if (!ctx->have_result || !ctx->orders.valid)
+      throw BuildError{MSGPU_ERR_NO_RESULT, "the filter view needs msgpu_chain_overlaps first"};
+    filter_view_describe(ctx->arena, ctx->stream, ctx->edges, ctx->orders, ctx->filter_view);
+    *out = msgpu_filter_view_header{ctx->filter_view.n_edges, ctx->filter_view.n_orders, ctx->filter_view.bytes, 0};
+  });
+}
+
+int msgpu_filter_view_export(msgpu_ctx *ctx, void *dev_dst, uint64_t capacity) {
+  return guarded(ctx, [&] {
+    if (!ctx->have_result || !ctx->orders.valid || !ctx->filter_view.valid)
+      throw BuildError{MSGPU_ERR_NO_RESULT, "msgpu_filter_view_describe first"};
+    if (!dev_dst || capacity < ctx->filter_view.bytes || (reinterpret_cast<uintptr_t>(dev_dst) & 15))
+      throw BuildError{MSGPU_ERR_INVALID_ARG, "filter view: destination missing, misaligned or smaller than blob_bytes"};
+    filter_view_export(ctx->stream, ctx->edges, ctx->orders, ctx->filter_view, dev_dst);
+  });
+}
+
+int msgpu_edge_filters_sharded(msgpu_ctx *ctx, uint32_t n_parts, uint32_t part, const msgpu_filter_view_header *headers,
+                               const void *const *dev_blobs, uint64_t wiggle_room) {
+  if (!headers || !dev_blobs || n_parts == 0) return MSGPU_ERR_INVALID_ARG;
+  return guarded(ctx, [&] {
+    if (!ctx->have_result || !ctx->orders.valid)
+      throw BuildError{MSGPU_ERR_NO_RESULT, "the edge filters need msgpu_chain_overlaps first"};
+    ctx->filters            = FilterTables{};
+    ctx->filters_host_valid = false;
+    ctx->profiler.clear();
+    run_edge_filters_sharded(ctx->arena, ctx->stream, ctx->reads.n, ctx->edges, ctx->orders, wiggle_room, n_parts, part,
+                             headers, dev_blobs, ctx->filters, &ctx->filter_ms);
   });
 }
 

@@ -235,6 +235,39 @@ class ShardedBuilder:
         self.gb.build_from_shards(headers, ptrs, self.rank, self.world)
         return self.gb
 
+    def edge_filters(self, wiggle_room: int = 300):
+        """findContractionEdges / findDeletableEdges / computeBitweight for this rank's slice of the edges (after
+        `chain_overlaps` on the builder).  The contraction test reads edges that live on other ranks, so every rank
+        publishes a compact view of its slice (msgpu_filter_view_*), ONE all-gather carries the views, and the passes
+        run against their concatenation (msgpu_edge_filters_sharded).  Returns the builder (verdicts: .filters())."""
+        gb, world = self.gb, self.world
+        with self._on_stream():
+            h = gb.filter_view_header()
+            if world == 1:
+                blob = torch.empty(max(int(h.blob_bytes), 16), dtype=torch.uint8, device=self.device)
+                gb.filter_view_export(blob.data_ptr(), blob.numel())
+                gb.edge_filters_sharded([h], [blob.data_ptr()], 0, 1, wiggle_room)
+                return gb
+            mine = torch.tensor([int(h.n_edges), int(h.n_orders), int(h.blob_bytes), 0], dtype=torch.int64,
+                                device=self.device)
+            heads = torch.empty(world * 4, dtype=torch.int64, device=self.device)
+            self.dist.all_gather_into_tensor(heads, mine)
+            rows = heads.view(world, 4).cpu().tolist()  # device -> host: the sizes decide the allocations below
+            headers = []
+            for row in rows:
+                x = _lib.FilterViewHeader()
+                x.n_edges, x.n_orders, x.blob_bytes, x.reserved = row
+                headers.append(x)
+            stride = (max(int(x.blob_bytes) for x in headers) + 255) & ~255
+            blob = torch.empty(max(stride, 256), dtype=torch.uint8, device=self.device)
+            gb.filter_view_export(blob.data_ptr(), blob.numel())
+            views = gather_blobs(blob, world, self.dist)
+            self.filter_exchange_bytes = sum(int(x.blob_bytes) for i, x in enumerate(headers) if i != self.rank)
+            gb.edge_filters_sharded(headers, [views.data_ptr() + r * blob.numel() for r in range(world)], self.rank,
+                                    world, wiggle_room)
+            self._keep_views = views
+        return gb
+
     def last_exchange_ms(self):
         ev = getattr(self, "_events", None)
         if not ev:

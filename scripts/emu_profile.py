@@ -32,6 +32,15 @@ gb = ranks[0]
 ptrs = [b.data_ptr() for b in blobs]
 for _ in range(3):
     gb.build_from_shards(headers, ptrs, 0, n)
+torch.cuda.synchronize()
+import time  # noqa: E402
+ts = []
+for _ in range(5):
+    t0 = time.perf_counter()
+    gb.build_from_shards(headers, ptrs, 0, n)
+    torch.cuda.synchronize()
+    ts.append(round((time.perf_counter() - t0) * 1e3, 3))
+print("build_from_shards wall ms", ts)
 gb.profile(True)
 gb.build_from_shards(headers, ptrs, 0, n)
 ks = {k: (v[0], round(v[1], 3)) for k, v in gb.kernel_stats().items()}

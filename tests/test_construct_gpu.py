@@ -109,11 +109,30 @@ def test_heavy_rows_vs_oracle(builder, oracle):
 
 
 def test_group_longer_than_the_cta_sort_vs_oracle(builder, oracle):
-    """A unitig matched by 4 500 reads: its group is too long for the shared-memory sorts of rank_rows (warp: 128,
-    CTA: 4096) and is ranked by the counting kernel; next to it groups of every other size class."""
+    """A unitig matched by 4 500 reads: its group is ranked by counting, 256 members per CTA against the group's read
+    ids staged 4096 at a time (two passes here); next to it groups of every other size class."""
     paf = util.heavy_rows_paf(k0=4500, k1=700, shared_from=4200, seed=5, small_groups=60)
     got = _same(builder, oracle, paf)
     assert got.counts["em"] > 2_000_000
+
+
+def test_group_sizes_around_the_ranking_boundaries_vs_oracle(builder, oracle):
+    """Groups of exactly the sizes where rank_rows changes its method: one warp sorts up to 128 members; longer groups
+    become (group, 256-member chunk) work items of the counting kernel."""
+    paf = util.group_sizes_paf([1, 2, 127, 128, 129, 255, 256, 257, 511, 512, 513, 1024, 1025])
+    _same(builder, oracle, paf)
+
+
+def test_pipelined_emission_agrees_with_the_product(builder, monkeypatch):
+    """MSGPU_PIPE_CHUNKS=n emits the tiles in n ranges, the emission kernel of one range on a second stream underneath
+    the tile kernel of the next (measured and off by default).  Same tables, bit for bit."""
+    paf = util.heavy_rows_paf()
+    want = util.gpu_to_tables(builder.build_from_buffer(paf).result())
+    for n in ("2", "5"):
+        monkeypatch.setenv("MSGPU_PIPE_CHUNKS", n)
+        got = util.gpu_to_tables(builder.build_from_buffer(paf).result())
+        monkeypatch.delenv("MSGPU_PIPE_CHUNKS")
+        assert tables_equal(want, got) == []
 
 
 def test_sort_based_variant_agrees_with_fused(builder, monkeypatch):

@@ -89,3 +89,69 @@ def test_variable_size_all_gather_over_gloo_world_2():
     for p in procs:
         p.join(timeout=30)
     assert res == [(0, True), (1, True)]
+
+
+class _FakeFilterBuilder:
+    """Stands in for GraphBuilder in the host logic of ShardedBuilder.edge_filters: a view of rank-dependent size whose
+    bytes are a known pattern; records what the sharded entry point is handed."""
+
+    def __init__(self, rank):
+        self.rank, self.seen = rank, None
+
+    def set_stream(self, s):
+        pass
+
+    def _bytes(self, r):
+        return np.random.default_rng(100 + r).integers(0, 256, 500 + 333 * r, dtype=np.uint8)
+
+    def filter_view_header(self):
+        h = _lib.FilterViewHeader()
+        h.n_edges, h.n_orders, h.blob_bytes = 10 + self.rank, 20 + self.rank, self._bytes(self.rank).size
+        return h
+
+    def filter_view_export(self, ptr, cap):
+        import ctypes
+        b = self._bytes(self.rank)
+        assert cap >= b.size
+        ctypes.memmove(ptr, b.ctypes.data, b.size)
+
+    def edge_filters_sharded(self, headers, ptrs, part, n_parts, wiggle):
+        import ctypes
+        got = [np.ctypeslib.as_array((ctypes.c_uint8 * int(h.blob_bytes)).from_address(int(p))).copy()
+               for h, p in zip(headers, ptrs)]
+        self.seen = (part, n_parts, wiggle, [int(h.n_edges) for h in headers], [int(h.n_orders) for h in headers], got)
+
+
+def _filter_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fake = _FakeFilterBuilder(rank)
+        sb = multi_gpu.ShardedBuilder(fake, rank, world, dist, "cpu")
+        sb.edge_filters(123)
+        part, n_parts, wiggle, ne, no, blobs = fake.seen
+        ok = (part, n_parts, wiggle) == (rank, world, 123) and ne == [10 + r for r in range(world)]
+        ok = ok and no == [20 + r for r in range(world)]
+        for r in range(world):
+            ok = ok and np.array_equal(blobs[r], fake._bytes(r))
+        ok = ok and sb.filter_exchange_bytes == sum(fake._bytes(r).size for r in range(world) if r != rank)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_filter_views_exchange_over_gloo_world_2():
+    """ShardedBuilder.edge_filters: sizes first, then ONE all-gather of the padded views; every rank hands the entry
+    point all views in rank order."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_filter_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == [(0, True), (1, True)]

@@ -140,3 +140,80 @@ def test_sharded_chain_vs_reference(reference, n):
     cat["edge_order_begin"] = np.concatenate(ob + [np.array([o0])]).astype(np.uint64)
     cat["ids_begin"] = np.concatenate(ib + [np.array([i0])]).astype(np.uint64)
     assert orders_equal(Orders(**cat), reference.chain(paf)) == []
+
+
+def sharded_filters(chunks, wiggle=300):
+    """Build + chain on n emulated ranks, exchange the filter views (here: every rank is handed the same list of
+    blobs), run the sharded edge filters on every rank; returns the verdicts concatenated in rank order."""
+    from oracle.pyoracle import FILTER_FIELDS
+    n = len(chunks)
+    ranks = [GraphBuilder(0) for _ in range(n)]
+    try:
+        headers, blobs = [], []
+        for r, (gb, chunk) in enumerate(zip(ranks, chunks)):
+            gb.shard_ingest_buffer(chunk, r == n - 1)
+            headers.append(gb.shard_header())
+        for gb, h in zip(ranks, headers):
+            blob = torch.empty(int(h.blob_bytes) + 16, dtype=torch.uint8, device="cuda")
+            gb.shard_export(blob.data_ptr(), blob.numel())
+            blobs.append(blob)
+        torch.cuda.synchronize()
+        vh, views = [], []
+        for r, gb in enumerate(ranks):
+            gb.build_from_shards(headers, [b.data_ptr() for b in blobs], r, n)
+            gb.chain_overlaps(wiggle)
+            h = gb.filter_view_header()
+            v = torch.full((int(h.blob_bytes) + 16,), 0xEE, dtype=torch.uint8, device="cuda")
+            gb.filter_view_export(v.data_ptr(), v.numel())
+            vh.append(h)
+            views.append(v)
+        torch.cuda.synchronize()
+        parts = []
+        for r, gb in enumerate(ranks):
+            if n > 1:
+                from muchsalsa_b200.construct import MsGpuError
+                with pytest.raises(MsGpuError):  # the one-device entry refuses a slice
+                    gb.edge_filters(wiggle)
+            parts.append(gb.edge_filters_sharded(vh, [v.data_ptr() for v in views], r, n, wiggle).filters())
+        return {k: np.concatenate([p[k] for p in parts]) for k in FILTER_FIELDS}, [int(h.n_edges) for h in vh]
+    finally:
+        for gb in ranks:
+            gb.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
+@pytest.mark.parametrize("name", ["kat8", "heavy_group", "small"])
+def test_sharded_edge_filters_vs_reference(reference, name, n):
+    """findContractionEdges reads the edges around an order's start vertex and the third edge of every triangle — rows
+    of OTHER ranks on a sharded build.  With the views exchanged, the verdicts of the slices appended in rank order are
+    the reference's (src/main.cpp:416-460, 534-573)."""
+    from oracle.pyoracle import FILTER_FIELDS
+    paf = synth.generate_paf("small") if name == "small" else util.edge_case_pafs()[name]
+    got, sizes = sharded_filters(multi_gpu.split_paf(paf, n))
+    want = reference.filters(paf)
+    assert [k for k in FILTER_FIELDS if got[k].shape != want[k].shape or not np.array_equal(got[k], want[k])] == []
+    if name == "small" and n > 1:
+        assert min(sizes) > 0 and int((got["contraction_order"] >= 0).sum()) > 0
+
+
+def test_sharded_edge_filters_ecoli_equal_one_device(builder):
+    """E. coli scale on 3 emulated ranks against the one-device verdicts (themselves pinned on the reference by
+    tests/test_filters_gpu.py): 4.5e5 edges, thousands of contraction edges whose neighbours sit on other ranks."""
+    from oracle.pyoracle import FILTER_FIELDS
+    paf = synth.generate_paf("ecoli")
+    want = builder.build_from_buffer(paf).chain_overlaps(300).edge_filters(300).filters()
+    want = {k: np.array(want[k]) for k in FILTER_FIELDS}
+    got, sizes = sharded_filters(multi_gpu.split_paf(paf, 3))
+    assert [k for k in FILTER_FIELDS if not np.array_equal(got[k], want[k])] == []
+    assert int((want["contraction_order"] >= 0).sum()) > 100 and min(sizes) > 0
+
+
+def test_sharded_builder_world_1_edge_filters(builder):
+    paf = synth.generate_paf("small")
+    want = builder.build_from_buffer(paf).chain_overlaps(300).edge_filters(300).filters()
+    want = {k: np.array(v) for k, v in want.items()}
+    with GraphBuilder(0) as gb:
+        sb = multi_gpu.ShardedBuilder(gb, 0, 1, None, torch.device("cuda", 0))
+        sb.build_buffer(paf).chain_overlaps(300)
+        got = sb.edge_filters(300).filters()
+        assert all(np.array_equal(got[k], want[k]) for k in want)

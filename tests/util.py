@@ -202,6 +202,25 @@ def heavy_rows_paf(k0=3000, k1=2500, shared_from=1000, seed=11, small_groups=40)
     return b"".join(r[1] for r in rows) + sentinel
 
 
+def group_sizes_paf(sizes, seed=23) -> bytes:
+    """One unitig per entry of `sizes`, matched by that many reads drawn from a common pool (so the groups share reads
+    and rows get several sources); the lines of all groups are shuffled, so read ids are not monotone inside a group."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    L = paf_line
+    pool = max(sizes) + 50
+    rows = []
+    for g, k in enumerate(sizes):
+        for r in rng.choice(pool, k, replace=False):
+            a = int(rng.integers(0, 3000))
+            b = int(a + rng.integers(420, 6000))
+            rows.append((int(rng.integers(0, 1 << 30)),
+                         L(f"g{g}", 9000, a, b, "+-"[int(rng.integers(0, 2))], f"x{r}", 60000, 100, 100 + (b - a),
+                           int((b - a) * 0.9))))
+    rows.sort(key=lambda t: t[0])
+    sentinel = L("zz", 900, 0, 300, "+", "zr", 1000, 0, 300, 290)
+    return b"".join(r[1] for r in rows) + sentinel
+
+
 def merge_parts(parts):
     """Concatenate the per-rank results of a multi-GPU construction (rank order) into one Construction: the global
     tables are taken from rank 0 (they are replicated), the edge slices are appended."""
