@@ -20,11 +20,13 @@
 //                                     match; the fields come from a 32-byte row (one L2 sector) in pairing order
 //   getVertexMatches(read)         -> a per-read list of unitig ids ordered by (nanoporeRange, unitig), built here
 //
-// Three launches share the per-edge programme.  74 % of the edges at yeast scale hold ONE edge match: for them the
-// dynamic programme is the identity and chain_single_kernel does the whole job in registers.  Edges with 2..8 edge
-// matches go to the programme instantiated with 8-entry state arrays (they stay in L1), the rest to the 96-entry
-// instantiation; the two lists are filled by warp-aggregated appends, and every result is written at a position that
-// depends on the edge alone, so the output does not depend on the order of the lists.
+// Five launches share the per-edge programme.  90 % of the edges at yeast scale hold ONE edge match: for them the
+// dynamic programme is the identity and chain_single_kernel does the whole job in registers.  Edges with 2..4 edge
+// matches go to the programme instantiated with 4-entry state arrays, those with 5..8 to the 8-entry one, the rest to
+// the 96-entry instantiation (and beyond 96 of one direction to a fallback over a global scratch slab); the lists are
+// filled by warp-aggregated appends, and every result is written at a position that depends on the edge alone, so the
+// output does not depend on the order of the lists.  (Measured and not kept, round 2: the state arrays in shared
+// memory instead of local memory — the few threads per SM that fit no longer cover the programme's global loads.)
 #include <string>
 
 #include "../../include/msgpu.h"

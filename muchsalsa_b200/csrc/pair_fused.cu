@@ -18,7 +18,8 @@
 //     heavier than a tile (a read that crosses a high-multiplicity repeat) is split into sub-tiles by VALUE RANGES of
 //     `second`: the boundaries are found by bisection on the merged rank over the row's sorted suffixes, so every
 //     sub-tile is bounded, no edge straddles two sub-tiles and the sub-tiles of a row are in output order.
-//   * pair_tiles_merge_kernel, one CTA per tile, no dependency between tiles: stage the sources, enumerate the
+//   * pair_tiles_merge_kernel, one CTA per tile at a time (one resident wave of CTAs, tiles handed out by a ticket
+//     counter), no dependency between tiles: stage the sources, enumerate the
 //     candidates into shared memory, merge-sort them there by (row, second) starting from the slices, which are
 //     sorted runs already — stable, and candidates are generated in unitig order, so rows of one edge come out by
 //     unitig — find the run heads (= edges) and write the tile's surviving candidates as compact 8-byte records
@@ -970,7 +971,7 @@ constexpr int kEmitBatch = MSGPU_EMIT_BATCH; // records in flight per thread: th
 #endif
 constexpr int kEmitBatchUnder = MSGPU_EMIT_BATCH_UNDER; // ... of the 64-register instantiation that runs underneath the tile kernel
 
-// One CTA per tile (strided).  The tile's sources (the `first` side of its records, <= 512 rows) are staged in shared
+// One CTA per tile at a time (tiles by tickets).  The tile's sources (the `first` side of its records, <= 512 rows) are staged in shared
 // memory once; every record then needs ONE dependent gather (its partner's row) after its own coalesced load.
 __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_kernel(EmitArgs a) {
   __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
