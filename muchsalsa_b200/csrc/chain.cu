@@ -48,6 +48,7 @@ struct __align__(16) VmRow {
 
 __global__ void __launch_bounds__(256)
     build_vm_rows_kernel(MatchSoA m, const PairRow *__restrict__ rows, VmRow *__restrict__ vm) {
+  pdl_sync();
   for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < m.n; q += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t i = rows[q].orig;
     VmRow          v;
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     read_degree_kernel(const uint32_t *__restrict__ read, uint64_t n, uint32_t *__restrict__ deg) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
     atomicAdd(&deg[read[i]], 1u);
 }
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     read_scatter_kernel(const uint32_t *__restrict__ read, uint64_t n, const uint32_t *__restrict__ off,
                         uint32_t *__restrict__ cursor, uint32_t *__restrict__ tmp) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
     uint32_t r                             = read[i];
     tmp[off[r] + atomicAdd(&cursor[r], 1u)] = uint32_t(i);
@@ -89,6 +92,7 @@ __device__ __forceinline__ bool nano_less(const MatchSoA &m, uint32_t a, uint32_
 __global__ void __launch_bounds__(256)
     read_order_kernel(MatchSoA m, const uint32_t *__restrict__ off, const uint32_t *__restrict__ tmp,
                       uint32_t *__restrict__ list_unitig) {
+  pdl_sync();
   for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < m.n; x += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t me = tmp[x], r = m.read[me], lo = off[r], hi = off[r + 1];
     uint32_t       rank = 0;
@@ -144,6 +148,7 @@ __device__ __forceinline__ Vm load_vm(const ChainArgs &a, uint32_t pos) { // one
 __global__ void __launch_bounds__(256)
     chain_rows_kernel(EdgeTables e, const uint32_t *__restrict__ grp_off, const uint32_t *__restrict__ p_read,
                       uint32_t *__restrict__ em_row1, uint32_t *__restrict__ em_row2) {
+  pdl_sync();
   for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < e.n_edges;
        x += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t v1 = e.first[x], v2 = e.second[x];
@@ -597,6 +602,7 @@ template <int kCap> __device__ __forceinline__ void chain_one_edge(const ChainAr
 // the shadow test walks a path of length one (mpp.cpp:245-302), chainingAndOverlaps' filters keep the single path
 // (main.cpp:355-397) and the order comes from one getOverlap (ol.cpp:53-101).  Everything else is handed on.
 __global__ void __launch_bounds__(256) chain_single_kernel(ChainArgs a) {
+  pdl_sync();
   for (uint64_t base = uint64_t(blockIdx.x) * blockDim.x; base < a.e.n_edges; base += uint64_t(gridDim.x) * blockDim.x) {
     const uint64_t e    = base + threadIdx.x;
     const bool     live = e < a.e.n_edges;
@@ -668,6 +674,7 @@ __global__ void __launch_bounds__(256) chain_single_kernel(ChainArgs a) {
 
 // the edges of a list through the programme with kCap-entry arrays; longer edges are handed on (kHandOn)
 template <int kCap, bool kHandOn> __global__ void __launch_bounds__(128) chain_list_kernel(ChainArgs a) {
+  pdl_sync();
   const uint64_t n = *a.n_in;
   for (uint64_t base = uint64_t(blockIdx.x) * blockDim.x; base < n; base += uint64_t(gridDim.x) * blockDim.x) {
     const uint64_t x    = base + threadIdx.x;
@@ -686,6 +693,7 @@ template <int kCap, bool kHandOn> __global__ void __launch_bounds__(128) chain_l
 // the fallback: one thread per listed edge, state arrays sized by the edge in the scratch slab (slow — the dynamic
 // programme is quadratic in the edge matches of a direction and runs on one thread — but nothing is refused)
 __global__ void __launch_bounds__(64) chain_huge_kernel(ChainArgs a, uint32_t n_huge) {
+  pdl_sync();
   for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < n_huge; x += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t e   = a.huge_list[x];
     const uint64_t n   = a.e.em_begin[e + 1] - a.e.em_begin[e];
@@ -713,11 +721,11 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
   MSGPU_CUDA(cudaMemsetAsync(cursor, 0, (R + 1) * sizeof(uint32_t), st));
   MSGPU_CUDA(cudaMemsetAsync(d_tot, 0, 2 * sizeof(uint32_t), st));
   const int gm = grid_for(M, 256);
-  if (M) MSGPU_LAUNCH("read_degree", st, read_degree_kernel<<<gm, 256, 0, st>>>(m.read, M, deg));
+  if (M) MSGPU_LAUNCH("read_degree", st, launch_k(read_degree_kernel, gm, 256, 0, st, m.read, M, deg));
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{deg}, R + 1, rm_off, d_tot);
   if (M) {
-    MSGPU_LAUNCH("read_scatter", st, read_scatter_kernel<<<gm, 256, 0, st>>>(m.read, M, rm_off, cursor, tmp));
-    MSGPU_LAUNCH("read_order", st, read_order_kernel<<<gm, 256, 0, st>>>(m, rm_off, tmp, list));
+    MSGPU_LAUNCH("read_scatter", st, launch_k(read_scatter_kernel, gm, 256, 0, st, m.read, M, rm_off, cursor, tmp));
+    MSGPU_LAUNCH("read_order", st, launch_k(read_order_kernel, gm, 256, 0, st, m, rm_off, tmp, list));
   }
 
   out.edge_shadow   = arena.alloc<uint8_t>(E);
@@ -739,8 +747,8 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
   // match fields in pairing order, and the position of both vertices' matches for every edge match
   VmRow    *vm      = arena.alloc<VmRow>(M);
   uint32_t *em_row1 = arena.alloc<uint32_t>(EM), *em_row2 = arena.alloc<uint32_t>(EM);
-  if (M) MSGPU_LAUNCH("build_vm_rows", st, build_vm_rows_kernel<<<gm, 256, 0, st>>>(m, e.pair_rows, vm));
-  if (E) MSGPU_LAUNCH("chain_rows", st, chain_rows_kernel<<<grid_for(E, 256, 64), 256, 0, st>>>(e, unitigs.grp_off, e.p_read, em_row1, em_row2));
+  if (M) MSGPU_LAUNCH("build_vm_rows", st, launch_k(build_vm_rows_kernel, gm, 256, 0, st, m, e.pair_rows, vm));
+  if (E) MSGPU_LAUNCH("chain_rows", st, launch_k(chain_rows_kernel, grid_for(E, 256, 64), 256, 0, st, e, unitigs.grp_off, e.p_read, em_row1, em_row2));
 
   if (E >= 0xffffffffull) throw BuildError{MSGPU_ERR_LIMIT, "chaining supports < 2^32 edges per device"};
   uint32_t     *multi = arena.alloc<uint32_t>(E), *big = arena.alloc<uint32_t>(E);
@@ -773,23 +781,23 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
     a.n_in     = nullptr;
     a.list_out = multi;
     a.n_out    = d_cnt + 0;
-    MSGPU_LAUNCH("chain_single", st, chain_single_kernel<<<grid_for(E, 256, 64), 256, 0, st>>>(a));
+    MSGPU_LAUNCH("chain_single", st, launch_k(chain_single_kernel, grid_for(E, 256, 64), 256, 0, st, a));
     // the lists are sized on the device; the grids are bounded by E and stride over what is there
     a.list_in  = multi;
     a.n_in     = d_cnt + 0;
     a.list_out = big;
     a.n_out    = d_cnt + 1;
-    MSGPU_LAUNCH("chain_tiny", st, (chain_list_kernel<kChainTiny, true><<<grid_for(E, 128, 16), 128, 0, st>>>(a)));
+    MSGPU_LAUNCH("chain_tiny", st, (launch_k(chain_list_kernel<kChainTiny, true>, grid_for(E, 128, 16), 128, 0, st, a)));
     a.list_in  = big;
     a.n_in     = d_cnt + 1;
     a.list_out = multi;
     a.n_out    = d_cnt + 2;
-    MSGPU_LAUNCH("chain_small", st, (chain_list_kernel<kChainSmall, true><<<grid_for(E, 128, 16), 128, 0, st>>>(a)));
+    MSGPU_LAUNCH("chain_small", st, (launch_k(chain_list_kernel<kChainSmall, true>, grid_for(E, 128, 16), 128, 0, st, a)));
     a.list_in  = multi;
     a.n_in     = d_cnt + 2;
     a.list_out = nullptr;
     a.n_out    = nullptr;
-    MSGPU_LAUNCH("chain_large", st, (chain_list_kernel<kChainMax, false><<<grid_for(E, 128, 4), 128, 0, st>>>(a)));
+    MSGPU_LAUNCH("chain_large", st, (launch_k(chain_list_kernel<kChainMax, false>, grid_for(E, 128, 4), 128, 0, st, a)));
   }
   unsigned long long *h_huge = static_cast<unsigned long long *>(arena.host_scratch());
   MSGPU_CUDA(cudaMemcpyAsync(h_huge, d_huge, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -798,7 +806,7 @@ void run_chain_overlaps(Arena &arena, cudaStream_t st, const ReadTable &reads, c
   if (n_huge) { // rare: edges beyond the fast instantiations, one thread each over a scratch slab sized by the edges
     const uint64_t huge_em = h_huge[1];
     a.huge_scratch = arena.alloc<char>(152 * huge_em + 128 * uint64_t(n_huge));
-    MSGPU_LAUNCH("chain_huge", st, chain_huge_kernel<<<grid_for(n_huge, 64, 8), 64, 0, st>>>(a, n_huge));
+    MSGPU_LAUNCH("chain_huge", st, launch_k(chain_huge_kernel, grid_for(n_huge, 64, 8), 64, 0, st, a, n_huge));
   }
   MSGPU_CUDA(cudaEventRecord(ev1, st));
   MSGPU_CUDA(cudaStreamSynchronize(st));

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <utility>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -247,6 +249,45 @@ struct KernelScope {
     if (stop) cudaEventRecord(stop, st);
   }
 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launches.  A construction is a chain of ~30 short kernels, each depending on the one before
+// it; between two of them the GPU sits idle for the launch latency of the second.  Every kernel of the library opens
+// with pdl_sync(): wait until the grid before it in the stream has COMPLETED and its writes are visible
+// (griddepcontrol.wait — a no-op for a kernel launched the ordinary way), then allow the grid behind it to be scheduled
+// (griddepcontrol.launch_dependents).  launch_k() launches with the programmatic-stream-serialization attribute, so
+// the CTAs of the next kernel are placed on the SMs while this one drains and start the moment it has finished,
+// instead of being launched only then.  Ordering and visibility are exactly those of an ordinary stream (every thread
+// waits before it touches anything); copies, memsets and events between kernels serialise as always.  MSGPU_PDL=0
+// launches without the attribute.
+// ---------------------------------------------------------------------------------------------------------------------
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = std::getenv("MSGPU_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim          = grid;
+  cfg.blockDim         = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream           = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs    = attr;
+  cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...); // (MSGPU_LAUNCH checks the error)
+}
+#endif
 
 #define MSGPU_LAUNCH(name, stream, ...)        \
   do {                                         \

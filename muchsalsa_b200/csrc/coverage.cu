@@ -33,6 +33,7 @@ struct BlockReadTable {
 __global__ void __launch_bounds__(256)
     cov_first_hit_insert_kernel(MatchSoA m, const uint32_t *__restrict__ block, BlockReadTable t,
                                 uint32_t *__restrict__ slot) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += uint64_t(gridDim.x) * blockDim.x) {
     const unsigned long long key = ((unsigned long long)block[i] << 32 | m.read[i]) + 1ull;
     uint64_t                 q   = mix64(key) & t.mask;
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(256)
 // block_len = the unitig length of the block's first line (the script sizes the profile from it, unitig_filter.py:67)
 __global__ void __launch_bounds__(256)
     cov_block_len_kernel(MatchSoA m, const uint32_t *__restrict__ block, uint32_t *__restrict__ block_len) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += uint64_t(gridDim.x) * blockDim.x)
     if (i == 0 || block[i] != block[i - 1]) block_len[block[i]] = uint32_t(m.score[i]);
 }
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256)
                       const uint32_t *__restrict__ block_len, BlockReadTable t, const uint32_t *__restrict__ slot,
                       const uint8_t *__restrict__ outlier, uint32_t *__restrict__ starts, uint32_t *__restrict__ ends,
                       uint32_t *__restrict__ block_n_reads, unsigned int *__restrict__ bad) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < m.n; i += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t b = block[i];
     if (kPass1) {
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(256)
                           const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends,
                           uint32_t *__restrict__ block_max, const uint8_t *__restrict__ outlier, double q3,
                           uint8_t *__restrict__ run_start_flag) {
+  pdl_sync();
   const unsigned l  = threadIdx.x & 31;
   const uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
   for (uint64_t b = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < n_blocks; b += nw) {
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(256)
                     const uint8_t *__restrict__ outlier, double q3, const uint8_t *__restrict__ run_start_flag,
                     const uint32_t *__restrict__ run_index, uint32_t *__restrict__ run_block,
                     int32_t *__restrict__ run_start, int32_t *__restrict__ run_end) {
+  pdl_sync();
   const unsigned l  = threadIdx.x & 31;
   const uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
   for (uint64_t b = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < n_blocks; b += nw) {
@@ -157,6 +162,7 @@ struct LongRun { // cut_peaks keeps a run iff it is at least 500 positions long 
 __global__ void __launch_bounds__(256)
     cov_keep_runs_kernel(uint64_t n_runs, LongRun keep, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ run_block,
                          uint32_t *__restrict__ frag_block, int32_t *__restrict__ frag_start, int32_t *__restrict__ frag_end) {
+  pdl_sync();
   for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < n_runs; k += uint64_t(gridDim.x) * blockDim.x) {
     if (!keep(k)) continue;
     const uint32_t o = pos[k];
@@ -169,12 +175,14 @@ __global__ void __launch_bounds__(256)
 // the LAST block of every unitig decides (mapping_freq is a dict keyed by the unitig: later blocks overwrite)
 __global__ void __launch_bounds__(256)
     cov_last_block_kernel(uint64_t n_blocks, const uint32_t *__restrict__ block_unitig, uint32_t *__restrict__ last_block) {
+  pdl_sync();
   for (uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; b < n_blocks; b += uint64_t(gridDim.x) * blockDim.x)
     atomicMax(&last_block[block_unitig[b]], uint32_t(b));
 }
 __global__ void __launch_bounds__(256)
     cov_outlier_kernel(uint64_t n_blocks, const uint32_t *__restrict__ block_unitig, const uint32_t *__restrict__ last_block,
                        const uint32_t *__restrict__ block_max, double cutoff, uint8_t *__restrict__ outlier) {
+  pdl_sync();
   for (uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; b < n_blocks; b += uint64_t(gridDim.x) * blockDim.x)
     outlier[b] = double(block_max[last_block[block_unitig[b]]]) > cutoff ? 1 : 0;
 }

@@ -32,6 +32,7 @@ struct DigestAcc { // device-resident accumulator; zeroed by the caller
 };
 
 __global__ void __launch_bounds__(256) digest_kernel(EdgeTables e, DigestAcc *acc) {
+  pdl_sync();
   unsigned long long es = 0, ms = 0, bad = 0;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < e.n_edges; i += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t f = e.first[i], s = e.second[i];
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) digest_kernel(EdgeTables e, DigestAcc *ac
 void run_digest(Arena &arena, cudaStream_t st, const EdgeTables &e, msgpu_digest *out) {
   DigestAcc *d_acc = arena.alloc<DigestAcc>(1);
   MSGPU_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(DigestAcc), st));
-  if (e.n_edges) MSGPU_LAUNCH("digest", st, digest_kernel<<<grid_for(e.n_edges, 256, 16), 256, 0, st>>>(e, d_acc));
+  if (e.n_edges) MSGPU_LAUNCH("digest", st, launch_k(digest_kernel, grid_for(e.n_edges, 256, 16), 256, 0, st, e, d_acc));
   struct Tail {
     DigestAcc acc;
     uint32_t  f0, s0, f1, s1;

@@ -32,6 +32,7 @@ constexpr uint8_t kOStartFirst = 1, kOContained = 2, kODirection = 4, kOPrimary 
 // row_off[v] = first edge whose first vertex is >= v   (v in [0, n_reads])
 __global__ void __launch_bounds__(256)
     edge_rows_kernel(const uint32_t *__restrict__ first, uint64_t n_edges, uint32_t n_reads, uint32_t *__restrict__ row_off) {
+  pdl_sync();
   for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e <= n_edges; e += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t lo = e == 0 ? 0u : first[e - 1] + 1u;        // vertices in [lo, hi] start at edge e
     const uint32_t hi = e == n_edges ? n_reads : first[e];
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     lower_degree_kernel(const uint32_t *__restrict__ second, uint64_t n_edges, uint32_t *__restrict__ deg) {
+  pdl_sync();
   for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n_edges; e += uint64_t(gridDim.x) * blockDim.x)
     atomicAdd(&deg[second[e]], 1u);
 }
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     lower_scatter_kernel(const uint32_t *__restrict__ second, uint64_t n_edges, const uint32_t *__restrict__ off,
                          uint32_t *__restrict__ cursor, uint32_t *__restrict__ list) {
+  pdl_sync();
   for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n_edges; e += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t v                        = second[e];
     list[off[v] + atomicAdd(&cursor[v], 1u)] = uint32_t(e);
@@ -80,6 +83,7 @@ struct FilterArgs {
 // findDeletableEdges + computeBitweight for every edge; edges with a contained primary order are listed for the
 // contraction test
 __global__ void __launch_bounds__(256) edge_verdicts_kernel(FilterArgs a) {
+  pdl_sync();
   for (uint64_t base = uint64_t(blockIdx.x) * blockDim.x; base < a.e.n_edges; base += uint64_t(gridDim.x) * blockDim.x) {
     const uint64_t e    = base + threadIdx.x;
     const bool     live = e < a.e.n_edges;
@@ -217,6 +221,7 @@ __device__ bool sanity_check(const FilterArgs &a, uint32_t e_on, uint32_t e_for,
 
 // findContractionEdges: one warp per listed edge; the lanes share the neighbours of the order's start vertex
 __global__ void __launch_bounds__(256) contraction_edges_kernel(FilterArgs a) {
+  pdl_sync();
   const unsigned l  = threadIdx.x & 31;
   const uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5, n = *a.n_cand;
   for (uint64_t x = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; x < n; x += nw) {
@@ -263,10 +268,10 @@ static void filters_core(Arena &arena, cudaStream_t st, uint64_t n_reads, const 
   MSGPU_CUDA(cudaMemsetAsync(cursor, 0, (R + 2) * sizeof(uint32_t), st));
   MSGPU_CUDA(cudaMemsetAsync(d_n, 0, 2 * sizeof(unsigned int), st));
   const int gg = grid_for(G + 1, 256, 32);
-  MSGPU_LAUNCH("edge_rows", st, edge_rows_kernel<<<gg, 256, 0, st>>>(g.first, G, uint32_t(R), row_off));
-  if (G) MSGPU_LAUNCH("lower_degree", st, lower_degree_kernel<<<gg, 256, 0, st>>>(g.second, G, low_deg));
+  MSGPU_LAUNCH("edge_rows", st, launch_k(edge_rows_kernel, gg, 256, 0, st, g.first, G, uint32_t(R), row_off));
+  if (G) MSGPU_LAUNCH("lower_degree", st, launch_k(lower_degree_kernel, gg, 256, 0, st, g.second, G, low_deg));
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{low_deg}, R + 1, low_off, (uint32_t *)nullptr);
-  if (G) MSGPU_LAUNCH("lower_scatter", st, lower_scatter_kernel<<<gg, 256, 0, st>>>(g.second, G, low_off, cursor, low_list));
+  if (G) MSGPU_LAUNCH("lower_scatter", st, launch_k(lower_scatter_kernel, gg, 256, 0, st, g.second, G, low_off, cursor, low_list));
 
   out.contraction = arena.alloc<int32_t>(E);
   out.deletable   = arena.alloc<uint8_t>(E);
@@ -286,8 +291,8 @@ static void filters_core(Arena &arena, cudaStream_t st, uint64_t n_reads, const 
   a.cand      = cand;
   a.n_cand    = d_n;
   if (E) {
-    MSGPU_LAUNCH("edge_verdicts", st, edge_verdicts_kernel<<<grid_for(E, 256, 32), 256, 0, st>>>(a));
-    MSGPU_LAUNCH("contraction_edges", st, contraction_edges_kernel<<<grid_for(E * 32, 256, 8), 256, 0, st>>>(a));
+    MSGPU_LAUNCH("edge_verdicts", st, launch_k(edge_verdicts_kernel, grid_for(E, 256, 32), 256, 0, st, a));
+    MSGPU_LAUNCH("contraction_edges", st, launch_k(contraction_edges_kernel, grid_for(E * 32, 256, 8), 256, 0, st, a));
   }
   out.n_edges = E;
   out.valid   = true;
@@ -348,6 +353,7 @@ static ViewLayout view_layout(uint64_t E, uint64_t O) {
 __global__ void __launch_bounds__(256)
     pack_orders_kernel(EdgeTables e, OrderTables o, const uint64_t *__restrict__ ord_prefix, double *__restrict__ left,
                        double *__restrict__ right, uint8_t *__restrict__ flags) {
+  pdl_sync();
   for (uint64_t x = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < e.n_edges; x += uint64_t(gridDim.x) * blockDim.x) {
     const uint64_t k0 = e.em_begin[x] - e.em_value_base, w0 = ord_prefix[x];
     const uint32_t n  = o.edge_n_orders[x];
@@ -384,7 +390,7 @@ void filter_view_export(cudaStream_t st, const EdgeTables &e, const OrderTables 
     MSGPU_CUDA(cudaMemcpyAsync(d + l.second, e.second, E * 4, cudaMemcpyDeviceToDevice, st));
     MSGPU_CUDA(cudaMemcpyAsync(d + l.n_orders, o.edge_n_orders, E * 4, cudaMemcpyDeviceToDevice, st));
     MSGPU_CUDA(cudaMemcpyAsync(d + l.shadow, o.edge_shadow, E, cudaMemcpyDeviceToDevice, st));
-    MSGPU_LAUNCH("pack_orders", st, pack_orders_kernel<<<grid_for(E, 256, 32), 256, 0, st>>>(
+    MSGPU_LAUNCH("pack_orders", st, launch_k(pack_orders_kernel, grid_for(E, 256, 32), 256, 0, st, 
                                         e, o, v.ord_prefix, reinterpret_cast<double *>(d + l.left),
                                         reinterpret_cast<double *>(d + l.right), reinterpret_cast<uint8_t *>(d + l.flags)));
   }

@@ -70,6 +70,7 @@ __device__ __forceinline__ unsigned nl_mask32(const uint4 *aligned, uint64_t vb,
 
 __global__ void __launch_bounds__(kNlBlock)
     newline_count_kernel(const uint4 *__restrict__ aligned, uint64_t mis, uint64_t nv, uint32_t *__restrict__ tile_cnt) {
+  pdl_sync();
   __shared__ uint32_t sm[33];
   const uint64_t      base = uint64_t(blockIdx.x) * kNlTile + uint64_t(threadIdx.x) * 32;
   uint32_t            c    = 0;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(kNlBlock)
 __global__ void __launch_bounds__(kNlBlock)
     newline_write_kernel(const uint4 *__restrict__ aligned, uint64_t mis, uint64_t nv,
                          const uint32_t *__restrict__ tile_off, uint64_t cap_lines, uint64_t *__restrict__ line_start) {
+  pdl_sync();
   __shared__ uint32_t sm[33];
   const uint64_t      base  = uint64_t(blockIdx.x) * kNlTile + uint64_t(threadIdx.x) * 32;
   uint32_t            carry = tile_off[blockIdx.x];
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(kNlBlock)
 __global__ void line_index_finish_kernel(const char *__restrict__ paf, uint64_t n, const uint32_t *n_newlines,
                                          uint64_t cap_lines, int drop_last_line, uint64_t *line_start,
                                          IngestStatus *status) {
+  pdl_sync();
   // a trailing run of bytes without '\n' is one more line (IO.cpp:92-95); give it a virtual terminator so that
   // length(line i) = line_start[i+1] - line_start[i] - 1 holds for every line
   uint64_t nn   = *n_newlines;
@@ -407,6 +410,7 @@ template <int kMode> // 0: BlastFileReader's rules, 1: the scrubber's, 2: the un
 __global__ void __launch_bounds__(kParseBlock)
     parse_lines_kernel(const char *__restrict__ paf, uint64_t n_bytes, const uint64_t *__restrict__ line_start,
                        uint64_t seed, LineFields f, IngestStatus *status) {
+  pdl_sync();
   __shared__ __align__(16) char stage[kParseStage + 32];
   const uint64_t n_parse = status->n_parse;
   unsigned       n_acc   = 0;
@@ -456,6 +460,7 @@ __global__ void __launch_bounds__(256)
     intern_insert_kernel(const uint8_t *__restrict__ flags, const uint64_t *__restrict__ rhash,
                          const uint64_t *__restrict__ uhash, const IngestStatus *__restrict__ status, InternTable rt,
                          InternTable ut, uint32_t *__restrict__ rslot, uint32_t *__restrict__ uslot) {
+  pdl_sync();
   const uint64_t *__restrict__ hash = blockIdx.y ? uhash : rhash;
   const InternTable t               = blockIdx.y ? ut : rt;
   uint32_t *__restrict__ slot_of_line = blockIdx.y ? uslot : rslot;
@@ -481,6 +486,7 @@ __global__ void __launch_bounds__(256)
     intern_verify_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ line_start, LineFields f,
                          InternTable rt, const uint32_t *__restrict__ rslot, InternTable ut,
                          const uint32_t *__restrict__ uslot, IngestStatus *status) {
+  pdl_sync();
   const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
@@ -522,6 +528,7 @@ __global__ void __launch_bounds__(256)
                          int32_t *__restrict__ read_nlen, uint32_t *__restrict__ read_line,
                          uint64_t *__restrict__ read_name_src, uint32_t *__restrict__ read_name_len,
                          uint64_t *__restrict__ unitig_name_src, uint32_t *__restrict__ unitig_name_len) {
+  pdl_sync();
   const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
@@ -547,6 +554,7 @@ __global__ void __launch_bounds__(256)
     gather_names_kernel(const char *__restrict__ paf, const uint64_t *__restrict__ src,
                         const uint64_t *__restrict__ dst_off, const unsigned *__restrict__ d_n,
                         char *__restrict__ out) {
+  pdl_sync();
   // one warp per name
   const uint64_t n = *d_n;
   uint64_t w  = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -566,6 +574,7 @@ __global__ void __launch_bounds__(256)
                         const uint32_t *__restrict__ rslot, InternTable ut, const uint32_t *__restrict__ uslot,
                         InternTable dt, uint32_t *__restrict__ dslot, uint32_t *__restrict__ rid_of_line,
                         uint32_t *__restrict__ uid_of_line) {
+  pdl_sync();
   const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
@@ -588,6 +597,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     dedup_flag_kernel(const IngestStatus *__restrict__ status, uint8_t *__restrict__ flags, InternTable dt,
                       const uint32_t *__restrict__ dslot) {
+  pdl_sync();
   const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
@@ -601,6 +611,7 @@ __global__ void __launch_bounds__(256)
     all_survive_kernel(const IngestStatus *__restrict__ status, uint8_t *__restrict__ flags, InternTable rt,
                        const uint32_t *__restrict__ rslot, InternTable ut, const uint32_t *__restrict__ uslot,
                        uint32_t *__restrict__ rid_of_line, uint32_t *__restrict__ uid_of_line) {
+  pdl_sync();
   const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
@@ -619,6 +630,7 @@ __global__ void __launch_bounds__(256)
     compact_matches_kernel(const IngestStatus *__restrict__ status, LineFields f, const uint32_t *__restrict__ pos,
                            const uint32_t *__restrict__ rid_of_line, const uint32_t *__restrict__ uid_of_line,
                            MatchSoA m) {
+  pdl_sync();
   const uint64_t n_parse = status->n_parse;
   for (uint64_t li = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; li < n_parse;
        li += uint64_t(gridDim.x) * blockDim.x) {
@@ -643,6 +655,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     check_grouped_kernel(const uint32_t *__restrict__ unitig, const unsigned *__restrict__ d_n, uint64_t n_host,
                          uint32_t *unsorted) {
+  pdl_sync();
   const uint64_t n = d_n ? uint64_t(*d_n) : n_host;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x + 1; i < n;
        i += uint64_t(gridDim.x) * blockDim.x)
@@ -652,11 +665,13 @@ __global__ void __launch_bounds__(256)
 template <class T>
 __global__ void __launch_bounds__(256)
     gather_kernel(const T *__restrict__ in, const uint32_t *__restrict__ idx, uint64_t n, T *__restrict__ out) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
     out[i] = in[idx[i]];
 }
 
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t *out, uint64_t n) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x)
     out[i] = uint32_t(i);
 }
@@ -667,6 +682,7 @@ __global__ void __launch_bounds__(256) iota_kernel(uint32_t *out, uint64_t n) {
 __global__ void __launch_bounds__(256)
     group_bounds_kernel(const uint32_t *__restrict__ unitig, uint64_t n, uint32_t n_unitigs,
                         uint32_t *__restrict__ grp_off) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i <= n; i += uint64_t(gridDim.x) * blockDim.x) {
     uint32_t lo = i == 0 ? 0u : unitig[i - 1] + 1u;       // first id not yet started before row i
     uint32_t hi = i == n ? n_unitigs : unitig[i];         // ids lo..hi start at row i
@@ -685,6 +701,7 @@ struct BlockStart {
 __global__ void __launch_bounds__(256)
     block_ids_kernel(const uint32_t *__restrict__ unitig, uint64_t n, const uint32_t *__restrict__ before,
                      uint32_t *__restrict__ block, uint32_t *__restrict__ block_unitig) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
     const bool     start = i == 0 || unitig[i] != unitig[i - 1];
     const uint32_t b     = before[i] + (start ? 1u : 0u) - 1u;
@@ -701,7 +718,7 @@ uint64_t run_scrubber_blocks(Arena &arena, cudaStream_t st, const MatchSoA &m, u
   uint32_t *before = arena.alloc<uint32_t>(M + 1), *block = arena.alloc<uint32_t>(M + 1);
   uint32_t *block_unitig = arena.alloc<uint32_t>(M + 1), *d_n = arena.alloc<uint32_t>(1);
   exclusive_scan<uint32_t>(arena, st, BlockStart{m.unitig}, M, before, d_n);
-  if (M) MSGPU_LAUNCH("block_ids", st, block_ids_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, M, before, block, block_unitig));
+  if (M) MSGPU_LAUNCH("block_ids", st, launch_k(block_ids_kernel, grid_for(M, 256), 256, 0, st, m.unitig, M, before, block, block_unitig));
   *block_out        = block;
   *block_unitig_out = block_unitig;
   return uint64_t(read_back(arena, st, d_n));
@@ -768,14 +785,14 @@ static void build_name_tables(Arena &arena, cudaStream_t st, const char *d_paf, 
   for (const NameJob *j : {&a, &b}) {
     j->out->names = arena.alloc<char>(cap_bytes);
     if (cap) {
-      MSGPU_LAUNCH("gather_names", st, gather_names_kernel<<<grid_for(cap * 32, 256, 2), 256, 0, st>>>(d_paf, j->src, j->out->name_off, j->d_n, j->out->names));
+      MSGPU_LAUNCH("gather_names", st, launch_k(gather_names_kernel, grid_for(cap * 32, 256, 2), 256, 0, st, d_paf, j->src, j->out->name_off, j->d_n, j->out->names));
     }
   }
 }
 
 void build_group_offsets(Arena &arena, cudaStream_t st, const MatchSoA &m, UnitigTable &unitigs) {
   unitigs.grp_off = arena.alloc<uint32_t>(unitigs.n + 1);
-  MSGPU_LAUNCH("group_bounds", st, group_bounds_kernel<<<grid_for(m.n + 1, 256), 256, 0, st>>>(m.unitig, m.n, uint32_t(unitigs.n), unitigs.grp_off));
+  MSGPU_LAUNCH("group_bounds", st, launch_k(group_bounds_kernel, grid_for(m.n + 1, 256), 256, 0, st, m.unitig, m.n, uint32_t(unitigs.n), unitigs.grp_off));
 }
 
 void alloc_match_soa(Arena &arena, MatchSoA &s, uint64_t M) {
@@ -800,14 +817,14 @@ void group_by_unitig(Arena &arena, cudaStream_t st, MatchSoA &m, uint64_t n_unit
   if (known_unsorted < 0) {
     uint32_t *d_unsorted = arena.alloc<uint32_t>(1);
     MSGPU_CUDA(cudaMemsetAsync(d_unsorted, 0, sizeof(uint32_t), st));
-    MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(M, 256), 256, 0, st>>>(m.unitig, nullptr, M, d_unsorted));
+    MSGPU_LAUNCH("check_grouped", st, launch_k(check_grouped_kernel, grid_for(M, 256), 256, 0, st, m.unitig, nullptr, M, d_unsorted));
     if (!read_back(arena, st, d_unsorted)) return;
   }
   uint32_t *keys = arena.alloc<uint32_t>(M), *keys2 = arena.alloc<uint32_t>(M);
   uint32_t *idx = arena.alloc<uint32_t>(M), *idx2 = arena.alloc<uint32_t>(M);
   int       g = grid_for(M, 256);
   MSGPU_CUDA(cudaMemcpyAsync(keys, m.unitig, M * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-  MSGPU_LAUNCH("iota", st, iota_kernel<<<g, 256, 0, st>>>(idx, M));
+  MSGPU_LAUNCH("iota", st, launch_k(iota_kernel, g, 256, 0, st, idx, M));
   radix_sort_pairs<uint32_t, uint32_t>(arena, st, keys, idx, keys2, idx2, M, {0, bits_for(n_unitigs ? n_unitigs : 1)});
   MatchSoA s;
   alloc_match_soa(arena, s, M);
@@ -848,11 +865,11 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
   IngestStatus *d_status = arena.alloc<IngestStatus>(1);
   uint64_t    *line_start = arena.alloc<uint64_t>(cap + 2);
   if (n_tiles) {
-    MSGPU_LAUNCH("newline_count", st, newline_count_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt));
+    MSGPU_LAUNCH("newline_count", st, launch_k(newline_count_kernel, (unsigned)n_tiles, kNlBlock, 0, st, aligned, mis, nv, tile_cnt));
   }
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint32_t, uint32_t>{tile_cnt}, n_tiles, tile_cnt, d_n_nl);
   if (n_tiles) {
-    MSGPU_LAUNCH("newline_write", st, newline_write_kernel<<<(unsigned)n_tiles, kNlBlock, 0, st>>>(aligned, mis, nv, tile_cnt, cap, line_start));
+    MSGPU_LAUNCH("newline_write", st, launch_k(newline_write_kernel, (unsigned)n_tiles, kNlBlock, 0, st, aligned, mis, nv, tile_cnt, cap, line_start));
   }
 
   LineFields f;
@@ -890,28 +907,28 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
     init.first_bad_line = ~0ull;
     MSGPU_CUDA(cudaMemcpyAsync(d_status, &init, sizeof(init), cudaMemcpyHostToDevice, st));
     MSGPU_CUDA(cudaMemsetAsync(f.flags, 0, cap, st)); // the scans below run over the capacity
-    MSGPU_LAUNCH("line_index_finish", st, line_index_finish_kernel<<<1, 1, 0, st>>>(d_paf, n_bytes, d_n_nl, cap, drop_last_line ? 1 : 0, line_start, d_status));
+    MSGPU_LAUNCH("line_index_finish", st, launch_k(line_index_finish_kernel, 1, 1, 0, st, d_paf, n_bytes, d_n_nl, cap, drop_last_line ? 1 : 0, line_start, d_status));
     // seeds are odd multiples of a constant, never 0; the test hook makes the first attempt collide on purpose
     const bool     force = attempt == 0 && std::getenv("MSGPU_TEST_FORCE_COLLISION") != nullptr;
     const uint64_t seed  = force ? 0ull : 0x243f6a8885a308d3ull * uint64_t(attempt + 1);
     if (mode == 1)
-      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<1><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
+      MSGPU_LAUNCH("parse_lines", st, launch_k(parse_lines_kernel<1>, grid_for(cap, kParseBlock, 4), kParseBlock, 0, st, d_paf, n_bytes, line_start, seed, f, d_status));
     else if (mode == 2)
-      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<2><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
+      MSGPU_LAUNCH("parse_lines", st, launch_k(parse_lines_kernel<2>, grid_for(cap, kParseBlock, 4), kParseBlock, 0, st, d_paf, n_bytes, line_start, seed, f, d_status));
     else
-      MSGPU_LAUNCH("parse_lines", st, parse_lines_kernel<0><<<grid_for(cap, kParseBlock, 4), kParseBlock, 0, st>>>(d_paf, n_bytes, line_start, seed, f, d_status));
+      MSGPU_LAUNCH("parse_lines", st, launch_k(parse_lines_kernel<0>, grid_for(cap, kParseBlock, 4), kParseBlock, 0, st, d_paf, n_bytes, line_start, seed, f, d_status));
 
     const ScanLive live_lines{nullptr, &d_status->n_lines, 0}; // the per-line scans stop at the actual line count
     // ---- K3 interning
     InternTable tables[3];
     make_tables(arena, st, cap_acc + cap_acc / 2, tables);
     const InternTable rt = tables[0], ut = tables[1], dt = tables[2];
-    MSGPU_LAUNCH("intern_insert", st, intern_insert_kernel<<<dim3(grid_lines, 2), 256, 0, st>>>(f.flags, f.rhash, f.uhash, d_status, rt, ut, rslot, uslot));
-    MSGPU_LAUNCH("intern_verify", st, intern_verify_kernel<<<grid_lines, 256, 0, st>>>(d_paf, line_start, f, rt, rslot, ut, uslot, d_status));
+    MSGPU_LAUNCH("intern_insert", st, launch_k(intern_insert_kernel, dim3(grid_lines, 2), 256, 0, st, f.flags, f.rhash, f.uhash, d_status, rt, ut, rslot, uslot));
+    MSGPU_LAUNCH("intern_verify", st, launch_k(intern_verify_kernel, grid_lines, 256, 0, st, d_paf, line_start, f, rt, rslot, ut, uslot, d_status));
     run_scans(arena, st,
               scan_job<uint32_t>(arena, st, 0, FlagBit<uint32_t>{f.flags, kFFirstRead}, cap, rank_a, &d_status->n_reads, live_lines),
               scan_job<uint32_t>(arena, st, 1, FlagBit<uint32_t>{f.flags, kFFirstUnitig}, cap, rank_b, &d_status->n_unitigs, live_lines));
-    MSGPU_LAUNCH("intern_assign", st, intern_assign_kernel<<<grid_lines, 256, 0, st>>>(line_start, d_status, f, rt, rslot, rank_a, ut, uslot, rank_b,
+    MSGPU_LAUNCH("intern_assign", st, launch_k(intern_assign_kernel, grid_lines, 256, 0, st, line_start, d_status, f, rt, rslot, rank_a, ut, uslot, rank_b,
                                                      reads.nlen, reads.line, rsrc, rlen, usrc, ulen));
     build_name_tables(arena, st, d_paf, cap_acc, n_bytes,
                       NameJob{&d_status->n_reads, rsrc, rlen, &d_status->read_name_bytes, &reads},
@@ -919,16 +936,16 @@ void run_ingest(Arena &arena, cudaStream_t st, const char *d_paf, uint64_t n_byt
 
     // ---- K4 dedup
     if (mode == 2) {
-      MSGPU_LAUNCH("all_survive", st, all_survive_kernel<<<grid_lines, 256, 0, st>>>(d_status, f.flags, rt, rslot, ut, uslot, rid_of_line, uid_of_line));
+      MSGPU_LAUNCH("all_survive", st, launch_k(all_survive_kernel, grid_lines, 256, 0, st, d_status, f.flags, rt, rslot, ut, uslot, rid_of_line, uid_of_line));
     } else {
-      MSGPU_LAUNCH("dedup_insert", st, dedup_insert_kernel<<<grid_lines, 256, 0, st>>>(d_status, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line, uid_of_line));
-      MSGPU_LAUNCH("dedup_flag", st, dedup_flag_kernel<<<grid_lines, 256, 0, st>>>(d_status, f.flags, dt, dslot));
+      MSGPU_LAUNCH("dedup_insert", st, launch_k(dedup_insert_kernel, grid_lines, 256, 0, st, d_status, f, rt, rslot, ut, uslot, dt, dslot, rid_of_line, uid_of_line));
+      MSGPU_LAUNCH("dedup_flag", st, launch_k(dedup_flag_kernel, grid_lines, 256, 0, st, d_status, f.flags, dt, dslot));
     }
 
     // ---- K5 compaction
     exclusive_scan<uint32_t>(arena, st, FlagBit<uint32_t>{f.flags, kFSurvivor}, cap, rank_a, &d_status->n_matches, live_lines);
-    MSGPU_LAUNCH("compact_matches", st, compact_matches_kernel<<<grid_lines, 256, 0, st>>>(d_status, f, rank_a, rid_of_line, uid_of_line, m));
-    MSGPU_LAUNCH("check_grouped", st, check_grouped_kernel<<<grid_for(cap_acc, 256, 2), 256, 0, st>>>(m.unitig, &d_status->n_matches, 0, &d_status->unsorted));
+    MSGPU_LAUNCH("compact_matches", st, launch_k(compact_matches_kernel, grid_lines, 256, 0, st, d_status, f, rank_a, rid_of_line, uid_of_line, m));
+    MSGPU_LAUNCH("check_grouped", st, launch_k(check_grouped_kernel, grid_for(cap_acc, 256, 2), 256, 0, st, m.unitig, &d_status->n_matches, 0, &d_status->unsorted));
 
     // ---- the one round trip of the ingest
     h = read_back(arena, st, d_status);

@@ -383,6 +383,7 @@ int msgpu_build_from_paf(msgpu_ctx *ctx, const char *paf_path) {
 namespace {
 __global__ void __launch_bounds__(256)
     block_to_anchor_kernel(uint32_t *__restrict__ em_unitig, uint64_t n, const uint32_t *__restrict__ block_unitig) {
+  pdl_sync();
   for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += uint64_t(gridDim.x) * blockDim.x)
     em_unitig[k] = block_unitig[em_unitig[k]];
 }

@@ -133,6 +133,7 @@ constexpr uint32_t kRankTile    = 4096; // ... against all of the group's read i
 // match per (read, unitig)), so the order is total.  Groups too long for a warp become work items of the CTA kernel.
 __global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a, uint32_t n_groups, uint2 *__restrict__ big_items,
                                                         unsigned int *__restrict__ n_big) {
+  pdl_sync();
   __shared__ unsigned long long sm[256 / 32][kSortWarpMax];
   const MatchSoA &m = a.m;
   const unsigned  l = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(256) rank_rows_kernel(RankArgs a, uint32_t n_g
 // one warp per member over global memory for longer groups: 41 + 7 us at yeast scale, set by the longest groups).
 __global__ void __launch_bounds__(kRankChunk) rank_rows_cta_kernel(RankArgs a, const uint2 *__restrict__ big_items,
                                                                   const unsigned int *__restrict__ n_big) {
+  pdl_sync();
   __shared__ uint32_t ids[kRankTile];
   const MatchSoA &m = a.m;
   const uint32_t  n = *n_big;
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(256)
     scatter_sources_kernel(const uint32_t *__restrict__ p_read, const PairRow *__restrict__ rows,
                            const uint32_t *__restrict__ grp_off, uint64_t n, const uint32_t *__restrict__ rd_off,
                            uint32_t *__restrict__ cursor, uint32_t *__restrict__ rd_tmp, RowRange rows_of) {
+  pdl_sync();
   const uint32_t r_lo = rows_of.lo(), r_hi = rows_of.hi();
   for (uint64_t q = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; q < n; q += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t r = p_read[q];
@@ -229,6 +232,7 @@ __global__ void __launch_bounds__(256)
     order_sources_kernel(const uint32_t *__restrict__ p_read, const uint32_t *__restrict__ rd_off,
                          const uint32_t *__restrict__ rd_tmp, uint64_t n_src, uint32_t *__restrict__ rd_src,
                          RowRange rows_of) {
+  pdl_sync();
   const uint64_t x_lo = rd_off[rows_of.lo()], x_hi = rd_off[rows_of.hi()]; // (rd_off has n_reads + 1 entries)
   for (uint64_t x = x_lo + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; x < x_hi && x < n_src;
        x += uint64_t(gridDim.x) * blockDim.x) {
@@ -301,6 +305,7 @@ __global__ void __launch_bounds__(256)
                        uint32_t *__restrict__ tile_row, uint32_t *__restrict__ tile_kind,
                        uint32_t *__restrict__ too_many_sources, uint32_t *__restrict__ wide_list,
                        unsigned int *__restrict__ wide_cursor) {
+  pdl_sync();
   for (uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n_reads;
        r += uint64_t(gridDim.x) * blockDim.x) {
     if (tc.p.deg[r] >= kSrcCapWide) *too_many_sources = 1; // an edge of such a row could outgrow a tile
@@ -369,6 +374,7 @@ __global__ void __launch_bounds__(256)
                        const uint32_t *__restrict__ rd_src, const PairRow *__restrict__ rows,
                        const uint32_t *__restrict__ grp_off, const uint32_t *__restrict__ p_read, uint32_t n_reads,
                        uint32_t *__restrict__ slices) {
+  pdl_sync();
   const unsigned l  = threadIdx.x & 31;
   uint64_t       wi = t_begin + ((uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
   const uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
@@ -772,6 +778,7 @@ __device__ __forceinline__ void merge_tail(const TileArgs &a, MergeShared<kSB> &
 // sources: a read that crosses that many shared unitigs is rare but legal input), one resident CTA per SM.
 template <int kSB>
 __global__ void __launch_bounds__(kFusedBlock, kSB == kSrcBits ? kMergeCtas : 1) pair_tiles_merge_kernel(TileArgs a) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MergeShared<kSB>  &s = *reinterpret_cast<MergeShared<kSB> *>(smem_raw);
   const unsigned     t = threadIdx.x, l = t & 31;
@@ -974,6 +981,7 @@ constexpr int kEmitBatchUnder = MSGPU_EMIT_BATCH_UNDER; // ... of the 64-registe
 // One CTA per tile at a time (tiles by tickets).  The tile's sources (the `first` side of its records, <= 512 rows) are staged in shared
 // memory once; every record then needs ONE dependent gather (its partner's row) after its own coalesced load.
 __global__ void __launch_bounds__(kEmitBlock, kEmitCtas) pair_emit_rows_kernel(EmitArgs a) {
+  pdl_sync();
   __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
   const unsigned   t = threadIdx.x;
   unsigned long long em_before, ed_before;
@@ -1067,6 +1075,7 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) { return uint32_t(_
 // CTA takes exactly the registers, and less than the shared memory, that one CTA of the tile kernel leaves behind)
 // when it runs underneath the tile kernel of the next chunk (pairing_pipelined).
 template <int kCtas, int kBatch> __global__ void __launch_bounds__(kEmitBlock, kCtas) pair_emit_rows_bulk_kernel(EmitArgs a) {
+  pdl_sync();
   __shared__ uint4 src_lo[kSrcCap], src_hi[kSrcCap]; // PairRow halves of the tile's sources
   __shared__ __align__(8) unsigned long long bar;
   extern __shared__ __align__(16) unsigned char bulk_raw[];
@@ -1204,8 +1213,8 @@ void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const Unitig
     // groups ordered by read id: a warp sorts a short group, CTAs rank the members of a longer one by counting
     const uint32_t U = uint32_t(unitigs.n);
     uint2         *big_items = arena.alloc<uint2>(uint64_t(U) + M / kRankChunk + 1);
-    MSGPU_LAUNCH("rank_rows", st, rank_rows_kernel<<<grid_for(uint64_t(U) * 32, 256), 256, 0, st>>>(ra, U, big_items, d_u32 + 4));
-    MSGPU_LAUNCH("rank_rows_cta", st, rank_rows_cta_kernel<<<kNumSMs * 8, kRankChunk, 0, st>>>(ra, big_items, d_u32 + 4));
+    MSGPU_LAUNCH("rank_rows", st, launch_k(rank_rows_kernel, grid_for(uint64_t(U) * 32, 256), 256, 0, st, ra, U, big_items, d_u32 + 4));
+    MSGPU_LAUNCH("rank_rows_cta", st, launch_k(rank_rows_cta_kernel, kNumSMs * 8, kRankChunk, 0, st, ra, big_items, d_u32 + 4));
   }
   // ---- tile planning: four independent scans over the reads in one launch (source offsets, clipped row weights,
   // slice-table offsets, the pair count), then the tile index, which needs the weights' prefix
@@ -1230,7 +1239,7 @@ void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const Unitig
 
   uint32_t *tile_row = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1), *tile_kind = arena.alloc<uint32_t>(uint64_t(n_tiles) + 1);
   uint32_t *wide_list = arena.alloc<uint32_t>(uint64_t(n_wide) + 1);
-  if (R) MSGPU_LAUNCH("write_tiles", st, write_tiles_kernel<<<gr, 256, 0, st>>>(tc, tile_idx, R, n_tiles, tile_row, tile_kind, d_u32 + 2, wide_list, d_u32 + 7));
+  if (R) MSGPU_LAUNCH("write_tiles", st, launch_k(write_tiles_kernel, gr, 256, 0, st, tc, tile_idx, R, n_tiles, tile_row, tile_kind, d_u32 + 2, wide_list, d_u32 + 7));
   uint32_t *rd_tmp = arena.alloc<uint32_t>(n_src), *rd_src = arena.alloc<uint32_t>(n_src);
   // ---- this device's share: a contiguous range of tiles (tiles weigh about the same)
   if (n_parts == 0) n_parts = 1;
@@ -1240,14 +1249,14 @@ void pairing_plan(Arena &arena, cudaStream_t st, const MatchSoA &m, const Unitig
   // source lists: of every row on one device, of the rows of this device's tiles (+ the one after) on several
   RowRange rows_of{nullptr, 0u, 0u, uint32_t(R)};
   if (n_parts > 1) rows_of = RowRange{tile_row, tile_lo, tile_hi < n_tiles ? tile_hi : n_tiles, uint32_t(R)};
-  if (M) MSGPU_LAUNCH("scatter_sources", st, scatter_sources_kernel<<<gm, 256, 0, st>>>(p_read, rows, unitigs.grp_off, M, rd_off, cursor, rd_tmp, rows_of));
-  if (n_src) MSGPU_LAUNCH("order_sources", st, order_sources_kernel<<<grid_for(n_src, 256), 256, 0, st>>>(p_read, rd_off, rd_tmp, n_src, rd_src, rows_of));
+  if (M) MSGPU_LAUNCH("scatter_sources", st, launch_k(scatter_sources_kernel, gm, 256, 0, st, p_read, rows, unitigs.grp_off, M, rd_off, cursor, rd_tmp, rows_of));
+  if (n_src) MSGPU_LAUNCH("order_sources", st, launch_k(order_sources_kernel, grid_for(n_src, 256), 256, 0, st, p_read, rd_off, rd_tmp, n_src, rd_src, rows_of));
   // heavy rows: every sub-tile computes its START boundary; its end boundary is the start of the next sub-tile, so
   // the range includes one tile past this device's share (a last sub-tile writes the end of its row itself)
   uint32_t *slices = arena.alloc<uint32_t>(n_slices);
   if (n_slices && my_tiles) {
     const uint32_t t_end = tile_hi < n_tiles ? tile_hi + 1 : n_tiles;
-    MSGPU_LAUNCH("split_heavy", st, split_heavy_kernel<<<grid_for(uint64_t(t_end - tile_lo) * 32, 256), 256, 0, st>>>(
+    MSGPU_LAUNCH("split_heavy", st, launch_k(split_heavy_kernel, grid_for(uint64_t(t_end - tile_lo) * 32, 256), 256, 0, st, 
                                         tile_row, tile_kind, tile_lo, t_end, plan, slice_off, rd_off, rd_src, rows,
                                         unitigs.grp_off, p_read, uint32_t(R), slices));
   }
@@ -1346,12 +1355,12 @@ static void tiles_launch(cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uin
   // 32 registers, 51 KB (narrow): four resident CTAs per SM, one wave of them, tiles handed out by tickets
   int grid = kNumSMs * (a.wide ? (kIdxBits <= 12 ? 2 : 1) : kMergeCtas) * (MSGPU_TICKETS ? 1 : 4);
   if (uint32_t(grid) > n) grid = int(n);
-  MSGPU_LAUNCH("pair_tiles", st, pair_tiles_merge_kernel<kSrcBits><<<grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st>>>(a));
+  MSGPU_LAUNCH("pair_tiles", st, launch_k(pair_tiles_merge_kernel<kSrcBits>, grid, kFusedBlock, a.wide ? kMergeBytesWide : kMergeBytesNarrow, st, a));
   if (pl.n_wide) { // sub-tiles of rows with 513 .. 4095 sources (skipped above): the same kernel staged for that many
     const size_t bytes = merge_bytes<kSrcBitsWide>(a.wide != 0);
     MSGPU_CUDA(cudaFuncSetAttribute(pair_tiles_merge_kernel<kSrcBitsWide>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(merge_bytes<kSrcBitsWide>(true))));
     int gw = pl.n_wide < uint32_t(kNumSMs) ? int(pl.n_wide) : kNumSMs;
-    MSGPU_LAUNCH("pair_tiles_wide", st, pair_tiles_merge_kernel<kSrcBitsWide><<<gw, kFusedBlock, bytes, st>>>(a));
+    MSGPU_LAUNCH("pair_tiles_wide", st, launch_k(pair_tiles_merge_kernel<kSrcBitsWide>, gw, kFusedBlock, bytes, st, a));
   }
 }
 static void tiles_scans(Arena &arena, cudaStream_t st, uint32_t n, const PairScratch &sc, uint32_t off, unsigned long long *totals) {
@@ -1404,16 +1413,16 @@ static void rows_launch(cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint
   // yeast scale, profiles/r2_ab_emit_bulk_vs_scalar_yeast.log); MSGPU_EMIT=scalar keeps the per-thread loads as the A/B.
   const char *emit = std::getenv("MSGPU_EMIT");
   if (emit && std::string(emit) == "scalar") {
-    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_kernel<<<grid, kEmitBlock, 0, st>>>(ea));
+    MSGPU_LAUNCH("pair_emit_rows", st, launch_k(pair_emit_rows_kernel, grid, kEmitBlock, 0, st, ea));
     return;
   }
   const int bytes = int(kTileCap * sizeof(uint2));
   if (underneath) {
     MSGPU_CUDA(cudaFuncSetAttribute(pair_emit_rows_bulk_kernel<4, kEmitBatchUnder>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_bulk_kernel<4, kEmitBatchUnder><<<grid, kEmitBlock, bytes, st>>>(ea));
+    MSGPU_LAUNCH("pair_emit_rows", st, launch_k(pair_emit_rows_bulk_kernel<4, kEmitBatchUnder>, grid, kEmitBlock, bytes, st, ea));
   } else {
     MSGPU_CUDA(cudaFuncSetAttribute(pair_emit_rows_bulk_kernel<kEmitCtas, kEmitBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    MSGPU_LAUNCH("pair_emit_rows", st, pair_emit_rows_bulk_kernel<kEmitCtas, kEmitBatch><<<grid, kEmitBlock, bytes, st>>>(ea));
+    MSGPU_LAUNCH("pair_emit_rows", st, launch_k(pair_emit_rows_bulk_kernel<kEmitCtas, kEmitBatch>, grid, kEmitBlock, bytes, st, ea));
   }
 }
 void pairing_rows(Arena &arena, cudaStream_t st, const PairPlan &pl, uint32_t t_lo, uint32_t t_hi, PairScratch &sc,

@@ -68,6 +68,7 @@ constexpr int kPairBlock = 256;
 __global__ void __launch_bounds__(kPairBlock)
     pair_count_kernel(MatchSoA m, const uint64_t *__restrict__ pair_off, const uint32_t *__restrict__ grp_off,
                       uint32_t n_unitigs, uint64_t n_pairs, uint64_t per_block, uint32_t *__restrict__ block_cnt) {
+  pdl_sync();
   __shared__ uint32_t sm[33];
   uint64_t            begin = uint64_t(blockIdx.x) * per_block;
   uint64_t            end   = begin + per_block < n_pairs ? begin + per_block : n_pairs;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kPairBlock)
     pair_emit_kernel(MatchSoA m, const uint64_t *__restrict__ pair_off, const uint32_t *__restrict__ grp_off,
                      uint32_t n_unitigs, uint64_t n_pairs, uint64_t per_block, const uint32_t *__restrict__ block_off,
                      Candidates c) {
+  pdl_sync();
   __shared__ uint32_t sm[33];
   uint64_t            begin = uint64_t(blockIdx.x) * per_block;
   uint64_t            end   = begin + per_block < n_pairs ? begin + per_block : n_pairs;
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(kPairBlock)
 __global__ void __launch_bounds__(256)
     gather_sorted_kernel(const unsigned long long *__restrict__ key, const uint32_t *__restrict__ idx, uint64_t n,
                          Candidates c, EdgeTables e, uint8_t *__restrict__ head) {
+  pdl_sync();
   for (uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += uint64_t(gridDim.x) * blockDim.x) {
     uint32_t s     = idx[r];
     e.em_unitig[r] = c.unitig[s];
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     write_edges_kernel(const unsigned long long *__restrict__ key, const uint8_t *__restrict__ head,
                        const uint32_t *__restrict__ edge_rank, uint64_t n, EdgeTables e, const uint32_t *n_edges) {
+  pdl_sync();
   for (uint64_t r = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; r < n; r += uint64_t(gridDim.x) * blockDim.x) {
     if (head[r]) {
       uint32_t k    = edge_rank[r];

@@ -24,6 +24,7 @@ template <class K>
 __global__ void __launch_bounds__(kSortBlock)
     radix_hist_kernel(const K *__restrict__ keys, uint64_t n, int shift, unsigned mask, uint32_t n_tiles,
                       uint32_t *__restrict__ hist /* [256][n_tiles] */) {
+  pdl_sync();
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(kSortBlock)
     radix_scatter_kernel(const K *__restrict__ keys_in, const V *__restrict__ vals_in, K *__restrict__ keys_out,
                          V *__restrict__ vals_out, uint64_t n, int shift, unsigned mask, uint32_t n_tiles,
                          const uint32_t *__restrict__ hist_scanned) {
+  pdl_sync();
   constexpr int       kWarps = kSortBlock / 32;
   __shared__ uint32_t warp_cnt[kWarps][256];
   __shared__ uint32_t bin_base[256];

@@ -178,12 +178,17 @@ template <class Job> __device__ __forceinline__ void scan_block(const Job &job) 
 }
 
 // up to four independent scans in ONE launch (blockIdx.y picks the scan): they cost the latency of one
-template <class J0> __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0) { scan_block(j0); }
+template <class J0> __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0) {
+  pdl_sync();
+  scan_block(j0);
+}
 template <class J0, class J1> __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, J1 j1) {
+  pdl_sync();
   if (blockIdx.y == 0) scan_block(j0); else scan_block(j1);
 }
 template <class J0, class J1, class J2, class J3>
 __global__ void __launch_bounds__(kScanBlock) scan_kernel(J0 j0, J1 j1, J2 j2, J3 j3) {
+  pdl_sync();
   if (blockIdx.y == 0) scan_block(j0);
   else if (blockIdx.y == 1) scan_block(j1);
   else if (blockIdx.y == 2) scan_block(j2);
@@ -208,12 +213,12 @@ ScanJob<T, InFn> scan_job(Arena &arena, cudaStream_t st, int slot, InFn in, uint
 
 template <class J0> void run_scans(Arena &arena, cudaStream_t st, const J0 &j0) {
   if (!j0.n_cap) return;
-  MSGPU_LAUNCH("scan", st, scan_kernel<J0><<<j0.n_tiles, kScanBlock, 0, st>>>(j0));
+  MSGPU_LAUNCH("scan", st, launch_k(scan_kernel<J0>, j0.n_tiles, kScanBlock, 0, st, j0));
 }
 template <class J0, class J1> void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1) {
   const unsigned n = j0.n_tiles > j1.n_tiles ? j0.n_tiles : j1.n_tiles; // (an empty scan has no tiles)
   if (!n) return;
-  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1><<<dim3(n, 2), kScanBlock, 0, st>>>(j0, j1)));
+  MSGPU_LAUNCH("scan", st, (launch_k(scan_kernel<J0, J1>, dim3(n, 2), kScanBlock, 0, st, j0, j1)));
 }
 template <class J0, class J1, class J2, class J3>
 void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1, const J2 &j2, const J3 &j3) {
@@ -222,7 +227,7 @@ void run_scans(Arena &arena, cudaStream_t st, const J0 &j0, const J1 &j1, const 
   n          = j2.n_tiles > n ? j2.n_tiles : n;
   n          = j3.n_tiles > n ? j3.n_tiles : n;
   if (!n) return;
-  MSGPU_LAUNCH("scan", st, (scan_kernel<J0, J1, J2, J3><<<dim3(n, 4), kScanBlock, 0, st>>>(j0, j1, j2, j3)));
+  MSGPU_LAUNCH("scan", st, (launch_k(scan_kernel<J0, J1, J2, J3>, dim3(n, 4), kScanBlock, 0, st, j0, j1, j2, j3)));
 }
 
 // a single scan.  n == 0 is allowed (total = 0).

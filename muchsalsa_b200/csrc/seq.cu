@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kStripBlock)
     strip_kernel(const char *__restrict__ raw, uint64_t n, const uint64_t *__restrict__ rec_begin,
                  const uint64_t *__restrict__ rec_end, uint64_t n_rec, uint64_t *__restrict__ tile_cnt_or_off,
                  char *__restrict__ packed, uint64_t *__restrict__ packed_begin, uint64_t *__restrict__ packed_end) {
+  pdl_sync();
   __shared__ uint32_t sm[33];
   uint64_t            b0 = uint64_t(blockIdx.x) * kStripTile + uint64_t(threadIdx.x) * kStripPer;
   unsigned            keep = 0;
@@ -234,6 +235,7 @@ struct Window {
 __global__ void __launch_bounds__(256)
     seq_window_kernel(SeqIndexDev idx, const msgpu_seq_req *__restrict__ reqs, uint64_t n,
                       Window *__restrict__ win, uint8_t *__restrict__ status) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
     msgpu_seq_req q = reqs[i];
     Window        w{0, 0};
@@ -256,6 +258,7 @@ __global__ void __launch_bounds__(256)
     text_window_kernel(const uint64_t *__restrict__ text_off, const int32_t *__restrict__ left,
                        const int32_t *__restrict__ right, uint64_t n, Window *__restrict__ win,
                        uint8_t *__restrict__ status) {
+  pdl_sync();
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
     uint64_t s, c;
     Window   w{0, 0};
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(256)
     slice_copy_kernel(SrcSel src_sel, RevSel rev_sel, const Window *__restrict__ win,
                       const uint64_t *__restrict__ out_off, uint64_t n, uint64_t cap, char *__restrict__ out,
                       uint8_t *__restrict__ status) {
+  pdl_sync();
   uint64_t       w  = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
   const unsigned l  = lane_id();

@@ -77,6 +77,7 @@ struct PackJob {
 };
 
 __global__ void __launch_bounds__(256) pack_blob_kernel(PackJob job, char *__restrict__ blob) {
+  pdl_sync();
   for (int k = 0; k < job.n; ++k) {
     const char    *src = static_cast<const char *>(job.src[k]);
     char          *dst = blob + job.dst_off[k];
@@ -129,7 +130,7 @@ void shard_export(cudaStream_t st, const msgpu_shard_header &h, const ReadTable 
   char *b = static_cast<char *>(dev_blob);
   MSGPU_CUDA(cudaMemcpyAsync(b, &h, sizeof(h), cudaMemcpyHostToDevice, st));
   const PackJob job = pack_job(h, reads, unitigs, m);
-  if (job.n) MSGPU_LAUNCH("pack_blob", st, pack_blob_kernel<<<grid_for(h.blob_bytes / 16 + 1, 256, 2), 256, 0, st>>>(job, b));
+  if (job.n) MSGPU_LAUNCH("pack_blob", st, launch_k(pack_blob_kernel, grid_for(h.blob_bytes / 16 + 1, 256, 2), 256, 0, st, job, b));
 }
 
 // The export AND the all-gather in one kernel: every 16-byte unit of the blob is read once from this GPU's tables and
@@ -144,6 +145,7 @@ struct PeerSlots {
 };
 
 __global__ void __launch_bounds__(256) pack_blob_peers_kernel(PackJob job, PeerSlots dst, msgpu_shard_header h) {
+  pdl_sync();
   const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nth = uint64_t(gridDim.x) * blockDim.x;
   if (tid < sizeof(msgpu_shard_header) / 16) { // the header: four 16-byte units
     const uint4 v = reinterpret_cast<const uint4 *>(&h)[tid];
@@ -175,7 +177,7 @@ void shard_export_peers(cudaStream_t st, const msgpu_shard_header &h, const Read
   for (uint32_t d = 0; d < n_slots; ++d) dst.slot[d] = static_cast<char *>(dev_slots[d]);
   PackJob job = pack_job(h, reads, unitigs, m);
   if (!with_sections) job.n = 0;
-  MSGPU_LAUNCH("pack_blob_peers", st, pack_blob_peers_kernel<<<grid_for((with_sections ? h.blob_bytes : 0) / 16 + 1, 256, 2), 256, 0, st>>>(job, dst, h));
+  MSGPU_LAUNCH("pack_blob_peers", st, launch_k(pack_blob_peers_kernel, grid_for((with_sections ? h.blob_bytes : 0) / 16 + 1, 256, 2), 256, 0, st, job, dst, h));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -222,6 +224,7 @@ __global__ void __launch_bounds__(256)
     entry_insert_kernel(const ShardView *__restrict__ sh, uint32_t n_shards, int which, uint64_t n_entries,
                         uint64_t seed, EntryTable t, const char **__restrict__ name_ptr, uint32_t *__restrict__ name_len,
                         uint32_t *__restrict__ slot) {
+  pdl_sync();
   for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n_entries;
        e += uint64_t(gridDim.x) * blockDim.x) {
     uint64_t       i;
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(256)
     entry_verify_kernel(uint64_t n_entries, EntryTable t, const char *const *__restrict__ name_ptr,
                         const uint32_t *__restrict__ name_len, const uint32_t *__restrict__ slot,
                         uint8_t *__restrict__ first, uint32_t *__restrict__ collision) {
+  pdl_sync();
   for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n_entries;
        e += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t rep = t.min_entry[slot[e]];
@@ -270,6 +274,7 @@ __global__ void __launch_bounds__(256)
                         const uint32_t *__restrict__ name_len, const char **__restrict__ out_name_ptr,
                         uint32_t *__restrict__ out_name_len, int32_t *__restrict__ read_nlen,
                         uint32_t *__restrict__ read_line) {
+  pdl_sync();
   for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n_entries;
        e += uint64_t(gridDim.x) * blockDim.x) {
     if (!first[e]) continue;
@@ -289,6 +294,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     entry_gid_kernel(uint64_t n_entries, EntryTable t, const uint32_t *__restrict__ slot, uint32_t *__restrict__ gid,
                      const uint8_t *__restrict__ first, uint8_t *__restrict__ shared /* may be null */) {
+  pdl_sync();
   for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n_entries;
        e += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t id = t.id[slot[e]];
@@ -300,6 +306,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     gather_names_abs_kernel(const char *const *__restrict__ src, const uint64_t *__restrict__ dst_off, uint64_t n,
                             char *__restrict__ out) {
+  pdl_sync();
   uint64_t w  = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; // one warp per name
   uint64_t nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
   for (; w < n; w += nw) {
@@ -312,6 +319,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     remap_matches_kernel(const ShardView *__restrict__ sh, uint32_t n_shards, uint64_t n_total,
                          const uint32_t *__restrict__ gid_read, const uint32_t *__restrict__ gid_unitig, MatchSoA c) {
+  pdl_sync();
   for (uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < n_total;
        g += uint64_t(gridDim.x) * blockDim.x) {
     uint32_t s = 0;
@@ -340,6 +348,7 @@ constexpr uint32_t kNoSlot = 0xffffffffu;
 __global__ void __launch_bounds__(256)
     shard_dedup_insert_kernel(MatchSoA c, EntryTable t, const uint8_t *__restrict__ shared_unitig,
                               uint32_t *__restrict__ slot) {
+  pdl_sync();
   for (uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < c.n; g += uint64_t(gridDim.x) * blockDim.x) {
     if (!shared_unitig[c.unitig[g]]) {
       slot[g] = kNoSlot;
@@ -367,6 +376,7 @@ struct KeepFlag {
 
 __global__ void __launch_bounds__(256)
     shard_compact_kernel(MatchSoA c, KeepFlag keep, const uint32_t *__restrict__ pos, MatchSoA m) {
+  pdl_sync();
   for (uint64_t g = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; g < c.n; g += uint64_t(gridDim.x) * blockDim.x) {
     if (!keep(g)) continue;
     const uint32_t o = pos[g];
@@ -423,6 +433,7 @@ struct IdNameLen { // lengths of the first *d_n names, 0 behind them (the scan r
 __global__ void __launch_bounds__(256)
     gather_names_abs_n_kernel(const char *const *__restrict__ src, const uint64_t *__restrict__ dst_off,
                               const unsigned *__restrict__ d_n, char *__restrict__ out) {
+  pdl_sync();
   const uint64_t n  = *d_n;
   uint64_t       w  = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; // one warp per name
   uint64_t       nw = (uint64_t(gridDim.x) * blockDim.x) >> 5;
@@ -435,6 +446,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     shard_check_grouped_kernel(const uint32_t *__restrict__ unitig, const unsigned *__restrict__ d_n,
                                unsigned *unsorted) {
+  pdl_sync();
   const uint64_t n = *d_n;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x + 1; i < n; i += uint64_t(gridDim.x) * blockDim.x)
     if (unitig[i] < unitig[i - 1]) *unsorted = 1;
@@ -459,19 +471,19 @@ static void merge_names(Arena &arena, cudaStream_t st, const ShardView *d_sh, ui
     read_line = arena.alloc<uint32_t>(n_entries);
   }
   if (n_entries) {
-    MSGPU_LAUNCH("entry_insert", st, entry_insert_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, which, n_entries, seed, t, name_ptr, name_len, slot));
-    MSGPU_LAUNCH("entry_verify", st, entry_verify_kernel<<<g, 256, 0, st>>>(n_entries, t, name_ptr, name_len, slot, first, &d_status->collision));
+    MSGPU_LAUNCH("entry_insert", st, launch_k(entry_insert_kernel, g, 256, 0, st, d_sh, n_shards, which, n_entries, seed, t, name_ptr, name_len, slot));
+    MSGPU_LAUNCH("entry_verify", st, launch_k(entry_verify_kernel, g, 256, 0, st, n_entries, t, name_ptr, name_len, slot, first, &d_status->collision));
   }
   exclusive_scan<uint32_t>(arena, st, LoadAs<uint8_t, uint32_t>{first}, n_entries, rank, &d_status->n_ids[which]);
   if (n_entries) {
-    MSGPU_LAUNCH("entry_assign", st, entry_assign_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, which, n_entries, t, slot, first, rank, name_ptr, name_len, id_name_ptr, id_name_len, read_nlen, read_line));
-    MSGPU_LAUNCH("entry_gid", st, entry_gid_kernel<<<g, 256, 0, st>>>(n_entries, t, slot, gid, first, shared));
+    MSGPU_LAUNCH("entry_assign", st, launch_k(entry_assign_kernel, g, 256, 0, st, d_sh, n_shards, which, n_entries, t, slot, first, rank, name_ptr, name_len, id_name_ptr, id_name_len, read_nlen, read_line));
+    MSGPU_LAUNCH("entry_gid", st, launch_k(entry_gid_kernel, g, 256, 0, st, n_entries, t, slot, gid, first, shared));
   }
   out.name_off = arena.alloc<uint64_t>(n_entries + 1);
   exclusive_scan<uint64_t>(arena, st, IdNameLen{id_name_len, &d_status->n_ids[which]}, n_entries + 1, out.name_off,
                            reinterpret_cast<uint64_t *>(&d_status->name_bytes[which]));
   out.names = arena.alloc<char>(name_bytes_bound);
-  if (n_entries) MSGPU_LAUNCH("gather_names", st, gather_names_abs_n_kernel<<<grid_for(n_entries * 32, 256, 2), 256, 0, st>>>(id_name_ptr, out.name_off, &d_status->n_ids[which], out.names));
+  if (n_entries) MSGPU_LAUNCH("gather_names", st, launch_k(gather_names_abs_n_kernel, grid_for(n_entries * 32, 256, 2), 256, 0, st, id_name_ptr, out.name_off, &d_status->n_ids[which], out.names));
 }
 
 void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msgpu_shard_header *headers,
@@ -558,15 +570,15 @@ void run_shard_merge(Arena &arena, cudaStream_t st, uint32_t n_shards, const msg
     MatchSoA c;
     alloc_match_soa(arena, c, mb);
     const int g = grid_for(mb, 256);
-    if (mb) MSGPU_LAUNCH("remap_matches", st, remap_matches_kernel<<<g, 256, 0, st>>>(d_sh, n_shards, mb, gid_r, gid_u, c));
+    if (mb) MSGPU_LAUNCH("remap_matches", st, launch_k(remap_matches_kernel, g, 256, 0, st, d_sh, n_shards, mb, gid_r, gid_u, c));
     EntryTable dt   = make_entry_table(arena, st, mb);
     uint32_t  *slot = arena.alloc<uint32_t>(mb), *pos = arena.alloc<uint32_t>(mb);
-    if (mb) MSGPU_LAUNCH("dedup_insert", st, shard_dedup_insert_kernel<<<g, 256, 0, st>>>(c, dt, shared_u, slot));
+    if (mb) MSGPU_LAUNCH("dedup_insert", st, launch_k(shard_dedup_insert_kernel, g, 256, 0, st, c, dt, shared_u, slot));
     KeepFlag keep{c.line, slot, dt.min_entry};
     exclusive_scan<uint32_t>(arena, st, keep, mb, pos, &d_status->n_matches);
     if (mb) {
-      MSGPU_LAUNCH("compact_matches", st, shard_compact_kernel<<<g, 256, 0, st>>>(c, keep, pos, m));
-      MSGPU_LAUNCH("check_grouped", st, shard_check_grouped_kernel<<<g, 256, 0, st>>>(m.unitig, &d_status->n_matches, &d_status->unsorted));
+      MSGPU_LAUNCH("compact_matches", st, launch_k(shard_compact_kernel, g, 256, 0, st, c, keep, pos, m));
+      MSGPU_LAUNCH("check_grouped", st, launch_k(shard_check_grouped_kernel, g, 256, 0, st, m.unitig, &d_status->n_matches, &d_status->unsorted));
     }
     // ---- the one round trip of the merge
     static_assert(sizeof(MergeStatus) <= 256, "host scratch layout");
