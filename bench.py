@@ -322,6 +322,8 @@ def run_ours(args):
                 filter_ms.append(gb.edge_filters_ms())
                 if world > 1:
                     filter_wall_ms.append(filter_wall)
+    # the verdicts of the last pass against the reference's (golden digests; every rank takes part)
+    filter_parity = check_filters_parity(gb, args.workload, rank, world, dist) if filter_error is None else None
     chain_t = reduce(sum(chain_ms) / len(chain_ms), "MAX")
     filter_t = reduce(sum(filter_ms) / len(filter_ms), "MAX") if filter_ms and filter_error is None else None
 
@@ -368,7 +370,8 @@ def run_ours(args):
                     "(src/main.cpp:416-460, 534-573, sc.cpp) on the device-resident order tables; identical to the "
                     "reference (tests/test_filters_gpu.py)",
             "ms": round(filter_t, 3), "edges_per_s": n_edges / filter_t * 1e3,
-            "cpu_reference": ((cpu or {}).get("chain") or {}).get("filters")}
+            "cpu_reference": ((cpu or {}).get("chain") or {}).get("filters"),
+            "parity": (filter_parity or {}).get("ok"), "parity_detail": filter_parity}
         if world > 1 and filter_wall_ms:
             f = gb.filters()
             out["edge_filters"]["sharded"] = {
@@ -700,6 +703,81 @@ def check_parity(gb, workload, rank, world, dist):
     else:
         out["note"] = "no golden digest for this workload: invariants only"
         out["invariants_ok"] = bool(ordered and tot["violations"] == 0)
+    return out
+
+
+def filters_sum_digest(f, base=0):
+    """Order-independent digest of per-edge filter verdicts (the arrays of GraphBuilder.filters(), or of the
+    reference's jobs): sum over the edges of a 64-bit mix of (global edge index, contraction order, deletable, kept
+    orders, weight, consensus), mod 2^64.  `base` = global index of the first edge of the slice, so the digests of the
+    slices of a multi-GPU build add up to the digest of the whole table."""
+    import numpy as np
+
+    def mix(x):
+        x = x ^ (x >> np.uint64(30))
+        x = x * np.uint64(0xbf58476d1ce4e5b9)
+        x = x ^ (x >> np.uint64(27))
+        x = x * np.uint64(0x94d049bb133111eb)
+        return x ^ (x >> np.uint64(31))
+
+    E = int(f["deletable"].shape[0])
+    with np.errstate(over="ignore"):
+        h = mix(np.arange(base, base + E, dtype=np.uint64) + np.uint64(0x9e3779b97f4a7c15))
+        h = mix(h ^ f["contraction_order"].astype(np.int64).astype(np.uint64))
+        small = (f["deletable"].astype(np.uint64) | (f["consensus"].astype(np.uint64) << np.uint64(8))
+                 | (f["n_kept_orders"].astype(np.uint64) << np.uint64(16)))
+        h = mix(h ^ small)
+        h = mix(h ^ f["weight"].astype(np.uint64))
+        total = int(h.sum(dtype=np.uint64)) if E else 0
+    return {"n_edges": E, "sum": total & ((1 << 64) - 1),
+            "contraction_edges": int((f["contraction_order"] >= 0).sum()), "deletable_edges": int(f["deletable"].sum())}
+
+
+def check_filters_parity(gb, workload, rank, world, dist):
+    """Are the edge-filter verdicts of the timed configuration the reference's?  Every rank digests the verdicts of its
+    own edges (host copy, numpy) with the global index of its first edge as base; the sums over the ranks must equal the
+    digest recorded from the REFERENCE's own jobs for the same PAF (tests/golden/sum_digests.json, key
+    filters_<workload>x<N>, written by tests/golden/make_sum_digests.py --filters).  Never raises: a failure is
+    reported in the line, and every rank takes part in both collectives whatever happens locally."""
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"  # (cpu: the gloo test of this function)
+    E_local, err = 0, None
+    try:
+        E_local = int(gb.counts()["n_edges"])
+    except Exception as e:  # noqa: BLE001
+        err = repr(e)[:200]
+    mine = torch.tensor([E_local], dtype=torch.int64, device=dev)
+    if dist is not None:
+        allE = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allE, mine)
+        allE = allE.cpu().tolist()
+    else:
+        allE = [E_local]
+    part = None
+    if err is None:
+        try:
+            part = filters_sum_digest(gb.filters(), base=sum(allE[:rank]))
+        except Exception as e:  # noqa: BLE001
+            err = repr(e)[:200]
+    vals = [0, 0, 0, 0, 0] if part is None else [1, part["sum"] & 0xffffffff, part["sum"] >> 32,
+                                                  part["contraction_edges"], part["deletable_edges"]]
+    t = torch.tensor(vals, dtype=torch.int64, device=dev)
+    if dist is not None:
+        allv = torch.empty(world * t.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allv, t)
+        allv = allv.view(world, -1).cpu().tolist()
+    else:
+        allv = [vals]
+    if not all(r[0] == 1 for r in allv):
+        return {"ok": None, "error": err or "a rank could not digest its verdicts"}
+    tot = {"n_edges": sum(allE), "sum": (sum(r[1] for r in allv) + (sum(r[2] for r in allv) << 32)) & ((1 << 64) - 1),
+           "contraction_edges": sum(r[3] for r in allv), "deletable_edges": sum(r[4] for r in allv)}
+    gp = os.path.join(ROOT, "tests", "golden", "sum_digests.json")
+    gold = json.load(open(gp)).get(f"filters_{workload}x{world}") if os.path.exists(gp) else None
+    out = {"digest": tot, "golden": None, "ok": None}
+    if gold is not None:
+        out["golden"] = f"tests/golden/sum_digests.json[filters_{workload}x{world}] (recorded from the reference's own jobs)"
+        out["ok"] = bool(all(tot[k] == gold[k] for k in ("n_edges", "sum", "contraction_edges", "deletable_edges")))
     return out
 
 

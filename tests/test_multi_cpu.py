@@ -155,3 +155,57 @@ def test_filter_views_exchange_over_gloo_world_2():
     for p in procs:
         p.join(timeout=30)
     assert res == [(0, True), (1, True)]
+
+
+class _FakeVerdictBuilder:
+    """One rank's slice of the reference's filter verdicts (small x2), as GraphBuilder.counts() / .filters() give them."""
+
+    def __init__(self, rank, world, broken=False):
+        from oracle.pyoracle import FILTER_FIELDS, Reference
+        paf = b"".join(synth.rank_chunk("small", r, 2) for r in range(2))
+        f = Reference().filters(paf, 300)
+        E = int(f["deletable"].shape[0])
+        a, b = E * rank // world + (7 if 0 < rank else 0), E * (rank + 1) // world + (7 if rank + 1 < world else 0)
+        self.f, self.broken = {k: f[k][a:b] for k in FILTER_FIELDS}, broken
+
+    def counts(self):
+        return {"n_edges": int(self.f["deletable"].shape[0])}
+
+    def filters(self):
+        if self.broken:
+            raise RuntimeError("no verdicts on this rank")
+        return self.f
+
+
+def _parity_worker(rank, world, port, q):
+    import sys
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        good = bench.check_filters_parity(_FakeVerdictBuilder(rank, world), "small", rank, world, dist)
+        # a rank that cannot produce its verdicts: every rank still leaves both collectives, nobody claims parity
+        bad = bench.check_filters_parity(_FakeVerdictBuilder(rank, world, broken=(rank == 1)), "small", rank, world, dist)
+        q.put((rank, good["ok"] is True and good["digest"]["n_edges"] == 2941, bad["ok"] is None and "error" in bad))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_filter_verdict_parity_check_over_gloo_world_2():
+    """bench.check_filters_parity: the digests of the ranks' slices (uneven cut) add up to the golden recorded from
+    the reference; a failing rank degrades the answer to 'unknown' on every rank instead of hanging the others."""
+    if not os.path.exists(os.path.join(os.path.dirname(os.path.abspath(_lib.__file__)), "..", "oracle", "_ref", "libmsref.so")):
+        pytest.skip("oracle/_ref/libmsref.so not built")
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_parity_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=150) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == [(0, True, True), (1, True, True)]
